@@ -1,0 +1,195 @@
+/* mlgi.h -- C ABI of the B200-native GI frame pipeline (libmlgi.so).
+ *
+ * Drop-in boundary for the hot path of karyon/many-lights-gi: the stage objects that
+ * MultiFramePainter wires together (source/mfs-painters/multiframepainter/):
+ *     VPLProcessor::process          VPLProcessor.h:22        -> mlgi_vpl_process
+ *     ImperfectShadowmap::process    ImperfectShadowmap.h:30  -> mlgi_ism_points + mlgi_ism_splat + mlgi_ism_pullpush
+ *     ClusteredShading::process      ClusteredShading.h:30    -> mlgi_cull_clustered   (tiled variant: mlgi_cull_tiled)
+ *     GIStage::compute_final_gathering GIStage.cpp:261        -> mlgi_final_gather
+ *     GIStage::blur                  GIStage.cpp:308          -> mlgi_gi_blur
+ *     GIStage::process               GIStage.cpp:346          -> mlgi_frame / mlgi_frame_host
+ * The reference has no FFI of its own (it is a gloperate plugin, plugin.cpp:9-17); these
+ * entry points are what a maintainer would bind from the C++ stage classes, see
+ * INTEGRATION.md and many-lights-gi_b200/host/mlgi_stages.hpp.
+ *
+ * Conventions
+ *  - plain C, pointers + sizes only. All matrices are column-major float[16] (GLSL/glm).
+ *  - every function returns 0 on success or a negative mlgi_status; mlgi_last_error(ctx)
+ *    returns a message. There is NO CPU fallback: without a CUDA device mlgi_create fails.
+ *  - unless stated otherwise pointers are DEVICE pointers; inputs are caller-owned and must
+ *    stay valid until the stream reaches the call; outputs are owned by the ctx and
+ *    exposed through mlgi_get_buffer. All calls are asynchronous on `stream`
+ *    (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *  - one ctx per GPU, not thread-safe (mirrors the reference's single GL thread).
+ */
+#ifndef MLGI_H
+#define MLGI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MLGI_API __attribute__((visibility("default")))
+#else
+#define MLGI_API
+#endif
+
+typedef struct mlgi_ctx mlgi_ctx;
+
+typedef enum {
+    MLGI_OK = 0,
+    MLGI_E_INVALID = -1,      /* bad argument / configuration */
+    MLGI_E_CUDA = -2,         /* CUDA runtime error (message has the cudaError string) */
+    MLGI_E_NO_DEVICE = -3,    /* no usable CUDA device: the product has no CPU path */
+    MLGI_E_UNSUPPORTED = -4,  /* reference feature outside the hot path (scaled ISMs, non push-pull ...) */
+    MLGI_E_CAPACITY = -5,     /* a ctx buffer is too small for the input (e.g. max_points) */
+    MLGI_E_ORDER = -6         /* a stage was called before the stage that produces its input */
+} mlgi_status;
+
+typedef enum { MLGI_CULL_CLUSTERED = 0, MLGI_CULL_TILED = 1, MLGI_CULL_NONE = 2 } mlgi_cull_mode;
+
+/* Sizes fixed at creation (the reference hard-codes them: SURVEY.md Appendix D). */
+typedef struct {
+    int device;          /* CUDA device ordinal */
+    int width, height;   /* camera viewport (GIStage::resizeTexture, GIStage.cpp:468) */
+    int vpl_count;       /* N = totalVplCount; multiple of 16 and of ceil(sqrt(N)); 64..16384 */
+    int rsm_width, rsm_height; /* RSM size (1024x256 in GIStage.cpp:236) */
+    int max_triangles;   /* capacity of the scene mesh handed to mlgi_ism_points */
+    int max_points;      /* capacity of the point buffer (reference: 2^23, ImperfectShadowmap.cpp:95) */
+    int class_lo, class_hi; /* interleave classes [lo,hi) owned by this ctx; 0,16 = all (multi-GPU shard) */
+    int enable_timers;   /* record per-stage cudaEvents (PerfCounter.cpp:50-76 scope names) */
+} mlgi_config;
+
+/* Tunables; names and defaults mirror GIStage (GIStage.h:84-100, GIStage.cpp:215-232). */
+typedef struct {
+    float light_intensity;        /* 5.0   */
+    float gi_intensity_factor;    /* 3000  */
+    float vpl_clamping_value;     /* 0.001 */
+    int   vpl_start_index;        /* 0     */
+    int   vpl_end_index;          /* N     (only affects normalisation: Q12) */
+    int   scale_isms;             /* 0     (1 -> MLGI_E_UNSUPPORTED) */
+    int   points_only_into_scaled_isms; /* 0 (1 -> MLGI_E_UNSUPPORTED) */
+    float tess_level_factor;      /* 2.0   */
+    int   use_push_pull;          /* 1     (0 = legacy point-sprite raster path -> MLGI_E_UNSUPPORTED) */
+    int   enable_shadowing;       /* 1     */
+    int   show_vpl_positions;     /* 0     (debug overlay; 1 -> MLGI_E_UNSUPPORTED) */
+    int   use_interleaving;       /* 1     (0 is broken upstream, SURVEY A.9 -> MLGI_E_UNSUPPORTED) */
+    int   shuffle_lights;         /* 1     */
+    float z_near, z_far;          /* camera AND light projection planes (GIStage.cpp:240-241); 0.05 / 50 */
+    int   cull_mode;              /* mlgi_cull_mode used by mlgi_frame / mlgi_final_gather */
+} mlgi_params;
+
+typedef struct {
+    float view[16];
+    float proj[16];
+} mlgi_camera;
+
+/* RSM G-buffer in (RasterizationStage.cpp:139-149): */
+typedef struct {
+    const uint32_t* diffuse;      /* RGBA8, r in byte 0 (GL_RGB8)           rsm_width*rsm_height */
+    const uint32_t* face_normal;  /* RGB10_A2 unorm of n*0.5+0.5, r in bits 0-9 */
+    const float*    depth;        /* window-space depth [0,1]               */
+} mlgi_rsm;
+
+/* camera G-buffer in (MultiFramePainter.cpp:115-119): */
+typedef struct {
+    const float*    depth;        /* width*height fp32 window-space depth */
+    const uint32_t* face_normal;  /* width*height RGB10_A2 */
+} mlgi_gbuffer;
+
+/* scene triangles in (ModelLoadingStage drawables, ImperfectShadowmap.cpp:225-240) */
+typedef struct {
+    const float*    vertices;     /* 3 floats per vertex */
+    const float*    normals;      /* 3 floats per vertex */
+    const uint32_t* indices;      /* 3 per triangle */
+    const uint32_t* prim_id;      /* gl_PrimitiveIDIn of each triangle (index inside its draw call) */
+    int num_vertices, num_triangles;
+} mlgi_mesh;
+
+/* Buffers a caller may inspect (the reference's BlitStage list, MultiFramePainter.cpp:153-176). */
+typedef enum {
+    MLGI_BUF_VPL = 0,              /* N x 12 float {pos,_,nrm,_,col,_}          VPLProcessor.cpp:34-41   */
+    MLGI_BUF_PACKED_VPL,           /* N x 4 float (pos, pack3SN(nrm))           VPLProcessor.cpp:29-32   */
+    MLGI_BUF_SHUFFLE,              /* N x int32 permutation                     VPLProcessor.cpp:58-65   */
+    MLGI_BUF_POINTS,               /* P x 4 float (pos, unorm4x8(nrm, r/25)), grouped by bucket */
+    MLGI_BUF_BUCKET_START,         /* (N+1) x uint32 prefix of bucket sizes (replaces atomicCounter[N]) */
+    MLGI_BUF_ATLAS,                /* A x A uint32 depth24<<8|radius8           ImperfectShadowmap.cpp:76-80 */
+    MLGI_BUF_ISM,                  /* A x A uint16 R16 unorm push-pull result   ImperfectShadowmap.cpp:102-106 */
+    MLGI_BUF_COMPACT_CLUSTER_IDS,  /* numUsed x uint32 x|y<<8|slice<<16         ClusteredShading.cpp:121 */
+    MLGI_BUF_LIGHT_LIST_IDS,       /* [16][Y][X] uint16, 0xFFFF = unused        ClusteredShading.cpp:122 */
+    MLGI_BUF_LIGHT_LISTS,          /* [numUsed][16][L+1] uint16                 ClusteredShading.cpp:124 */
+    MLGI_BUF_TILE_LISTS,           /* [BY*BX][16][L+1] uint16 (tiled variant)   */
+    MLGI_BUF_NUM_USED_CLUSTERS,    /* 1 x uint32                                */
+    MLGI_BUF_GI,                   /* width*height x 4 float RGBA raster        GIStage giBuffer */
+    MLGI_BUF_GI_PLANAR,            /* [class_hi-class_lo][ceil(H/4)][ceil(W/4)] x 4 float (multi-GPU exchange layout) */
+    MLGI_BUF_GI_BLUR,              /* width*height x 4 float                    GIStage giBlurFinalBuffer */
+    MLGI_BUF_COUNT
+} mlgi_buffer_id;
+
+MLGI_API int  mlgi_version(void);
+MLGI_API void mlgi_default_params(mlgi_params* p, int vpl_count);
+MLGI_API int  mlgi_create(const mlgi_config* cfg, mlgi_ctx** out);
+MLGI_API void mlgi_destroy(mlgi_ctx* ctx);
+MLGI_API const char* mlgi_last_error(const mlgi_ctx* ctx);   /* ctx may be NULL: last create error */
+
+/* a1  VPLProcessor::process (VPLProcessor.cpp:73-101, vpl_processor.comp:41-72) */
+MLGI_API int mlgi_vpl_process(mlgi_ctx*, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_params*, void* stream);
+
+/* a2  scene -> points (ism.tesc/tese/geom, ImperfectShadowmap.cpp:225-240); deterministic tessellator */
+MLGI_API int mlgi_ism_points(mlgi_ctx*, const mlgi_mesh* mesh, const mlgi_params*, void* stream);
+/* caller-supplied point list instead (parity interface "given the same point list"):
+ * points grouped by bucket, bucket_start has N+1 entries; both DEVICE pointers, copied into the ctx */
+MLGI_API int mlgi_ism_set_points(mlgi_ctx*, const float* points, const uint32_t* bucket_start, int num_points, void* stream);
+
+/* a3  ism.comp:54-139 (ImperfectShadowmap.cpp:244-258 + clear :212) */
+MLGI_API int mlgi_ism_splat(mlgi_ctx*, const mlgi_params*, void* stream);
+/* a4+a5  pull.comp x6 + push.comp x6 (ImperfectShadowmap.cpp:121-182) as one shared-memory pyramid per ISM.
+ * atlas_override (device, A*A uint32) may replace the ctx atlas as input; NULL = ctx atlas. */
+MLGI_API int mlgi_ism_pullpush(mlgi_ctx*, const uint32_t* atlas_override, const mlgi_params*, void* stream);
+
+/* a6+a7  clustering.comp + light_lists.comp (ClusteredShading.cpp:70-112) */
+MLGI_API int mlgi_cull_clustered(mlgi_ctx*, const mlgi_gbuffer*, const mlgi_camera*, const mlgi_params*, void* stream);
+/* a8  tiled variant (upstream branch tiled_shading, README.md:10; spec in DESIGN.md) */
+MLGI_API int mlgi_cull_tiled(mlgi_ctx*, const mlgi_gbuffer*, const mlgi_camera*, const mlgi_params*, void* stream);
+
+/* a9  final_gathering.comp:63-135 (GIStage.cpp:261-306). ism_override (device A*A uint16) may replace the ctx ISM. */
+MLGI_API int mlgi_final_gather(mlgi_ctx*, const mlgi_gbuffer*, const mlgi_camera*, const uint16_t* ism_override,
+                               const mlgi_params*, void* stream);
+/* n1  gi_blur.frag x2 (GIStage.cpp:308-344) */
+MLGI_API int mlgi_gi_blur(mlgi_ctx*, const mlgi_gbuffer*, const mlgi_camera*, void* stream);
+
+/* a10 GIStage::process (GIStage.cpp:346-418) minus the RSM raster: a1..a9 in order, device inputs. */
+MLGI_API int mlgi_frame(mlgi_ctx*, const mlgi_rsm*, const mlgi_camera* light, const mlgi_mesh*,
+                        const mlgi_gbuffer*, const mlgi_camera* cam, const mlgi_params*, void* stream);
+
+/* Same, but the per-frame inputs (RSM + camera G-buffer) are HOST pointers (pinned for
+ * full speed) and the GI image is copied back to host_gi (width*height*4 float, may be
+ * NULL to skip). The mesh stays resident on the device (it is static scene data in the
+ * reference too). Synchronises the stream before returning. This is the end-to-end call. */
+MLGI_API int mlgi_frame_host(mlgi_ctx*, const mlgi_rsm* host_rsm, const mlgi_camera* light, const mlgi_mesh* dev_mesh,
+                             const mlgi_gbuffer* host_gbuffer, const mlgi_camera* cam, const mlgi_params*,
+                             float* host_gi, void* stream);
+
+/* inspection */
+MLGI_API int mlgi_get_buffer(mlgi_ctx*, int buffer_id, void** dev_ptr, size_t* bytes);
+/* synchronous device->host copy of `bytes` bytes of a ctx buffer starting at byte `offset` (test/debug path) */
+MLGI_API int mlgi_read_buffer(mlgi_ctx*, int buffer_id, void* host_dst, size_t bytes, size_t offset);
+MLGI_API int mlgi_get_counts(mlgi_ctx*, int* num_points, int* num_used_clusters);  /* synchronises */
+/* exact work counters of the last mlgi_final_gather when cfg.enable_timers: pairs listed / lit */
+MLGI_API int mlgi_get_gather_stats(mlgi_ctx*, unsigned long long* pairs_listed, unsigned long long* pairs_lit);
+
+/* per-stage timers (names of PerfCounter scopes, GIStage.cpp:368-411): fills up to `cap`
+ * entries, returns the count. Synchronises. */
+typedef struct { char name[24]; float ms; int launches; } mlgi_timing;
+MLGI_API int mlgi_get_timings(mlgi_ctx*, mlgi_timing* out, int cap);
+/* number of kernels this library launched since creation (bench.py's gpu_launches) */
+MLGI_API unsigned long long mlgi_launch_count(const mlgi_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLGI_H */

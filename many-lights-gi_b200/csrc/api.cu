@@ -1,0 +1,572 @@
+// api.cu -- context, host orchestration and the C ABI declared in include/mlgi.h.
+// Host-side matrix math follows glm's evaluation order in fp32 (the reference computes these
+// on the host with glm: VPLProcessor.cpp:82,91, ClusteredShading.cpp:105, GIStage.cpp:289).
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace mlgi;
+
+namespace {
+
+std::string g_create_error;
+
+// ---- glm-order fp32 matrix helpers (column-major) ----
+void mat_mul(const float* a, const float* b, float* r) {        // r = a*b; column j = ((a0*b0j + a1*b1j) + a2*b2j) + a3*b3j
+    float t[16];
+    for (int j = 0; j < 4; j++)
+        for (int i = 0; i < 4; i++)
+            t[4 * j + i] = ((a[i] * b[4 * j] + a[4 + i] * b[4 * j + 1]) + a[8 + i] * b[4 * j + 2]) + a[12 + i] * b[4 * j + 3];
+    memcpy(r, t, sizeof(t));
+}
+void mat_inverse(const float* m, float* out) {                  // glm::inverse (cofactors)
+#define M(c, r) m[4 * (c) + (r)]
+    float c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3), c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3), c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
+    float c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3), c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3), c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+    float c08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2), c10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2), c11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2);
+    float c12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3), c14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3), c15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+    float c16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2), c18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2), c19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2);
+    float c20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1), c22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1), c23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+    const float F0[4] = {c00, c00, c02, c03}, F1[4] = {c04, c04, c06, c07}, F2[4] = {c08, c08, c10, c11};
+    const float F3[4] = {c12, c12, c14, c15}, F4[4] = {c16, c16, c18, c19}, F5[4] = {c20, c20, c22, c23};
+    const float V0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)}, V1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)};
+    const float V2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)}, V3[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+    const float SA[4] = {1, -1, 1, -1}, SB[4] = {-1, 1, -1, 1};
+    float inv[16];
+    for (int i = 0; i < 4; i++) {
+        inv[0 + i] = ((V1[i] * F0[i] - V2[i] * F1[i]) + V3[i] * F2[i]) * SA[i];
+        inv[4 + i] = ((V0[i] * F0[i] - V2[i] * F3[i]) + V3[i] * F4[i]) * SB[i];
+        inv[8 + i] = ((V0[i] * F1[i] - V1[i] * F3[i]) + V3[i] * F5[i]) * SA[i];
+        inv[12 + i] = ((V0[i] * F2[i] - V1[i] * F4[i]) + V2[i] * F5[i]) * SB[i];
+    }
+    const float d0 = M(0, 0) * inv[0], d1 = M(0, 1) * inv[4], d2 = M(0, 2) * inv[8], d3 = M(0, 3) * inv[12];
+    const float det = (d0 + d1) + (d2 + d3);
+    const float ood = 1.0f / det;
+    for (int i = 0; i < 16; i++) out[i] = inv[i] * ood;
+#undef M
+}
+Mat4 to_mat4(const float* p) { Mat4 r; memcpy(r.m, p, 64); return r; }
+
+int ism_indices_1d(int n) {                                     // next even power of two (ism.comp:39)
+    int l = 0;
+    while ((1 << l) < n) l++;
+    return 1 << ((l + 1) / 2);
+}
+SliceTable slice_table(float zFar) {                            // 2^((s+3)/sf), sf = 19/log2(zFar) (clustering.comp:22-24)
+    SliceTable t;
+    const double sf = 19.0 / std::log2((double)zFar);
+    for (int s = 0; s <= 16; s++) t.b[s] = (float)std::exp2(double(s + 3) / sf);
+    return t;
+}
+
+enum TimerId { T_VPLP = 0, T_POINTS, T_SPLAT, T_PULLPUSH, T_CLUSTERIDS, T_LIGHTLISTS, T_TILED, T_FG, T_BLUR, T_H2D, T_D2H, T_COUNT };
+const char* kTimerNames[T_COUNT] = {"VPLP", "ISM render", "ISM CS", "PullPush", "ClusterIDs", "Light Lists", "Tiled cull", "FG", "GI blur", "H2D", "D2H"};
+
+}  // namespace
+
+struct mlgi_ctx {
+    mlgi_config cfg;
+    int S, A, L;                    // ISMs per atlas row, atlas edge, VPLs per class
+    int X, Y, TX, TY;               // clustered / tiled grids
+    std::string err;
+    unsigned long long launches = 0;
+    // device buffers
+    float* vpl = nullptr; float* packed = nullptr; VplRecord* records = nullptr; int32_t* shuffle = nullptr;
+    uint32_t* tri_offsets = nullptr; uint32_t* scan_tmp = nullptr;
+    float4* points_unsorted = nullptr; float4* points = nullptr; uint32_t* point_bucket = nullptr;
+    uint32_t* bucket_hist = nullptr; uint32_t* bucket_cursor = nullptr; uint32_t* bucket_start = nullptr;
+    uint32_t* counters = nullptr;   // [0] num points (clamped), [1] generated points, [2] num used clusters
+    uint32_t* atlas = nullptr; uint16_t* ism = nullptr;
+    uint32_t* tile_masks = nullptr; uint32_t* compact_ids = nullptr; uint16_t* light_list_ids = nullptr;
+    uint16_t* light_lists = nullptr; uint16_t* tile_lists = nullptr;
+    float4* gi = nullptr; float4* gi_planar = nullptr; float4* gi_tmp = nullptr; float4* gi_blur = nullptr;
+    unsigned long long* stats = nullptr;
+    // staging for mlgi_frame_host
+    uint32_t* st_rsm_diffuse = nullptr; uint32_t* st_rsm_normal = nullptr; float* st_rsm_depth = nullptr;
+    float* st_depth = nullptr; uint32_t* st_normal = nullptr;
+    // stage bookkeeping
+    bool have_vpl = false, have_points = false, have_atlas = false, have_ism = false, have_clustered = false, have_tiled = false, have_gi = false;
+    cudaEvent_t ev[T_COUNT][2];
+    bool ev_used[T_COUNT];
+    bool events_created = false;
+    int ev_launches[T_COUNT];
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+int fail(mlgi_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, MLGI_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(mlgi_ctx* c, T** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) c->allocs.push_back(*p);
+    return e;
+}
+
+int check_params(mlgi_ctx* ctx, const mlgi_params* p) {
+    if (!p) return fail(ctx, MLGI_E_INVALID, "params is NULL");
+    if (p->scale_isms || p->points_only_into_scaled_isms)
+        return fail(ctx, MLGI_E_UNSUPPORTED, "scaleISMs / pointsOnlyIntoScaledISMs are outside the hot path (SURVEY 8f n3)");
+    if (!p->use_push_pull) return fail(ctx, MLGI_E_UNSUPPORTED, "usePushPull=false (legacy point-sprite raster path) is out of scope");
+    if (p->show_vpl_positions) return fail(ctx, MLGI_E_UNSUPPORTED, "SHOW_VPL_POSITIONS debug overlay is out of scope");
+    if (!p->use_interleaving) return fail(ctx, MLGI_E_UNSUPPORTED, "USE_INTERLEAVING=false is broken upstream (SURVEY A.9) and out of scope");
+    if (!(p->z_far > p->z_near) || !(p->z_near > 0.0f)) return fail(ctx, MLGI_E_INVALID, "need 0 < z_near < z_far");
+    if (p->vpl_end_index <= p->vpl_start_index) return fail(ctx, MLGI_E_INVALID, "vpl_end_index must exceed vpl_start_index");
+    return MLGI_OK;
+}
+
+struct StageTimer {
+    mlgi_ctx* c; int id; cudaStream_t st; unsigned long long l0;
+    StageTimer(mlgi_ctx* c_, int id_, cudaStream_t st_) : c(c_), id(id_), st(st_), l0(c_->launches) {
+        if (c->cfg.enable_timers) cudaEventRecord(c->ev[id][0], st);
+    }
+    ~StageTimer() {
+        if (c->cfg.enable_timers) { cudaEventRecord(c->ev[id][1], st); c->ev_used[id] = true; c->ev_launches[id] = (int)(c->launches - l0); }
+    }
+};
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+MLGI_API int mlgi_version(void) { return 100; }
+
+MLGI_API void mlgi_default_params(mlgi_params* p, int vpl_count) {   // GIStage.cpp:215-232
+    memset(p, 0, sizeof(*p));
+    p->light_intensity = 5.0f;
+    p->gi_intensity_factor = 3000.0f;
+    p->vpl_clamping_value = 0.001f;
+    p->vpl_start_index = 0;
+    p->vpl_end_index = vpl_count;
+    p->tess_level_factor = 2.0f;
+    p->use_push_pull = 1;
+    p->enable_shadowing = 1;
+    p->use_interleaving = 1;
+    p->shuffle_lights = 1;
+    p->z_near = 0.05f;
+    p->z_far = 50.0f;
+    p->cull_mode = MLGI_CULL_TILED;
+}
+
+MLGI_API const char* mlgi_last_error(const mlgi_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
+    mlgi_ctx* ctx = nullptr;   // for fail()/CK before allocation
+    if (!cfg || !out) return fail(nullptr, MLGI_E_INVALID, "cfg/out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, MLGI_E_NO_DEVICE, "no CUDA device: libmlgi has no CPU path");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MLGI_E_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    const int N = cfg->vpl_count;
+    if (N < 16 || N > 16384 || N % 16) return fail(nullptr, MLGI_E_INVALID, "vpl_count must be a multiple of 16 in [16,16384]");
+    const int ax = (int)std::ceil(std::sqrt((float)N));
+    if (N % ax) return fail(nullptr, MLGI_E_INVALID, "vpl_count must be a multiple of ceil(sqrt(N)) (vpl_processor.comp:38-50)");
+    if (cfg->width < 1 || cfg->height < 1 || cfg->rsm_width < 1 || cfg->rsm_height < 1) return fail(nullptr, MLGI_E_INVALID, "bad image size");
+    if ((cfg->width + 127) / 128 > 255 || (cfg->height + 127) / 128 > 255) return fail(nullptr, MLGI_E_INVALID, "viewport too large for 8-bit cluster coords (clustering.comp:83)");
+    if (cfg->class_lo < 0 || cfg->class_hi > 16 || cfg->class_lo >= cfg->class_hi) return fail(nullptr, MLGI_E_INVALID, "need 0 <= class_lo < class_hi <= 16");
+    if (cfg->max_points < 1 || cfg->max_triangles < 1) return fail(nullptr, MLGI_E_INVALID, "max_points / max_triangles must be positive");
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, MLGI_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+
+    ctx = new mlgi_ctx();
+    ctx->cfg = *cfg;
+    ctx->S = ism_indices_1d(N);
+    ctx->A = 64 * ctx->S;
+    ctx->L = N / 16;
+    ctx->X = (cfg->width + 127) / 128; ctx->Y = (cfg->height + 127) / 128;
+    ctx->TX = (cfg->width + kTile - 1) / kTile; ctx->TY = (cfg->height + kTile - 1) / kTile;
+    memset(ctx->ev_used, 0, sizeof(ctx->ev_used));
+    memset(ctx->ev_launches, 0, sizeof(ctx->ev_launches));
+    const size_t WH = (size_t)cfg->width * cfg->height, AA = (size_t)ctx->A * ctx->A, RS = (size_t)cfg->rsm_width * cfg->rsm_height;
+    const size_t PW = (cfg->width + 3) / 4, PH = (cfg->height + 3) / 4;
+    const size_t maxClusters = (size_t)ctx->X * ctx->Y * 16;
+#define ALLOC(ptr, count)                                                                                     \
+    do {                                                                                                      \
+        cudaError_t e2 = dalloc(ctx, &ctx->ptr, (count));                                                     \
+        if (e2 != cudaSuccess) {                                                                              \
+            fail(nullptr, MLGI_E_CUDA, "cudaMalloc(" #ptr ", %zu): %s", (size_t)(count), cudaGetErrorString(e2)); \
+            mlgi_destroy(ctx);                                                                                \
+            return MLGI_E_CUDA;                                                                               \
+        }                                                                                                     \
+    } while (0)
+    ALLOC(vpl, (size_t)N * 12); ALLOC(packed, (size_t)N * 4); ALLOC(records, (size_t)N); ALLOC(shuffle, (size_t)N);
+    ALLOC(tri_offsets, (size_t)cfg->max_triangles + 1); ALLOC(scan_tmp, (size_t)cfg->max_triangles / 2048 + 4);
+    ALLOC(points_unsorted, (size_t)cfg->max_points); ALLOC(points, (size_t)cfg->max_points); ALLOC(point_bucket, (size_t)cfg->max_points);
+    ALLOC(bucket_hist, (size_t)N); ALLOC(bucket_cursor, (size_t)N); ALLOC(bucket_start, (size_t)N + 1);
+    ALLOC(counters, 4);
+    ALLOC(atlas, AA); ALLOC(ism, AA);
+    ALLOC(tile_masks, (size_t)ctx->X * ctx->Y); ALLOC(compact_ids, maxClusters); ALLOC(light_list_ids, maxClusters);
+    ALLOC(light_lists, maxClusters * 16 * (ctx->L + 1));
+    ALLOC(tile_lists, (size_t)ctx->TX * ctx->TY * 16 * (ctx->L + 1));
+    ALLOC(gi, WH); ALLOC(gi_planar, (size_t)(cfg->class_hi - cfg->class_lo) * PW * PH); ALLOC(gi_tmp, WH); ALLOC(gi_blur, WH);
+    ALLOC(stats, 2);
+    ALLOC(st_rsm_diffuse, RS); ALLOC(st_rsm_normal, RS); ALLOC(st_rsm_depth, RS); ALLOC(st_depth, WH); ALLOC(st_normal, WH);
+#undef ALLOC
+    // VPLProcessor.cpp:58-65: fixed-seed shuffle table (libstdc++ std::shuffle; Q13)
+    std::vector<int32_t> v(N);
+    std::iota(v.begin(), v.end(), 0);
+    std::mt19937 g(1979982);
+    std::shuffle(v.begin(), v.end(), g);
+    e = cudaMemcpy(ctx->shuffle, v.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->gi, 0, WH * sizeof(float4));
+    if (e != cudaSuccess) { fail(nullptr, MLGI_E_CUDA, "init: %s", cudaGetErrorString(e)); mlgi_destroy(ctx); return MLGI_E_CUDA; }
+    for (int i = 0; i < T_COUNT; i++) { cudaEventCreate(&ctx->ev[i][0]); cudaEventCreate(&ctx->ev[i][1]); }
+    ctx->events_created = true;
+    *out = ctx;
+    return MLGI_OK;
+}
+
+MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->events_created)
+        for (int i = 0; i < T_COUNT; i++) { cudaEventDestroy(ctx->ev[i][0]); cudaEventDestroy(ctx->ev[i][1]); }
+    cudaGetLastError();
+    delete ctx;
+}
+
+// ------------------------------------------------------------------------------------- a1
+MLGI_API int mlgi_vpl_process(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!rsm || !light || !rsm->diffuse || !rsm->face_normal || !rsm->depth) return fail(ctx, MLGI_E_INVALID, "rsm/light is NULL");
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // VPLProcessor.cpp:76-82,91: inverse(bias * P_light * V_light)
+    const float bias[16] = {0.5f, 0, 0, 0, 0, 0.5f, 0, 0, 0, 0, 0.5f, 0, 0.5f, 0.5f, 0.5f, 1.0f};
+    float bp[16], bpv[16], inv[16];
+    mat_mul(bias, light->proj, bp);
+    mat_mul(bp, light->view, bpv);
+    mat_inverse(bpv, inv);
+    StageTimer t(ctx, T_VPLP, st);
+    ctx->launches += launch_vpl_process(*rsm, ctx->cfg.rsm_width, ctx->cfg.rsm_height, ctx->cfg.vpl_count, to_mat4(inv), p->light_intensity,
+                                        p->shuffle_lights, ctx->shuffle, ctx->S, ctx->vpl, ctx->packed, ctx->records, st);
+    CK(cudaGetLastError());
+    ctx->have_vpl = true;
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- a2
+MLGI_API int mlgi_ism_points(mlgi_ctx* ctx, const mlgi_mesh* mesh, const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!mesh || !mesh->vertices || !mesh->normals || !mesh->indices || !mesh->prim_id) return fail(ctx, MLGI_E_INVALID, "mesh is NULL");
+    if (mesh->num_triangles < 1) return fail(ctx, MLGI_E_INVALID, "mesh has no triangles");
+    if (mesh->num_triangles > ctx->cfg.max_triangles) return fail(ctx, MLGI_E_CAPACITY, "mesh has %d triangles, ctx capacity %d", mesh->num_triangles, ctx->cfg.max_triangles);
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer t(ctx, T_POINTS, st);
+    ctx->launches += launch_point_counts(*mesh, p->tess_level_factor, ctx->tri_offsets, ctx->scan_tmp, st);
+    ctx->launches += launch_point_generate(*mesh, p->tess_level_factor, ctx->cfg.vpl_count, ctx->tri_offsets, ctx->cfg.max_points,
+                                           ctx->points_unsorted, ctx->point_bucket, ctx->bucket_hist, ctx->bucket_start, ctx->bucket_cursor,
+                                           ctx->points, ctx->counters, st);
+    CK(cudaGetLastError());
+    ctx->have_points = true;
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_ism_set_points(mlgi_ctx* ctx, const float* points, const uint32_t* bucket_start, int num_points, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!points || !bucket_start || num_points < 0) return fail(ctx, MLGI_E_INVALID, "points/bucket_start is NULL");
+    if (num_points > ctx->cfg.max_points) return fail(ctx, MLGI_E_CAPACITY, "%d points exceed ctx capacity %d", num_points, ctx->cfg.max_points);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(ctx->points, points, sizeof(float4) * (size_t)num_points, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->bucket_start, bucket_start, sizeof(uint32_t) * ((size_t)ctx->cfg.vpl_count + 1), cudaMemcpyDeviceToDevice, st));
+    const uint32_t np[2] = {(uint32_t)num_points, (uint32_t)num_points};
+    CK(cudaMemcpyAsync(ctx->counters, np, sizeof(np), cudaMemcpyHostToDevice, st));
+    ctx->have_points = true;
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- a3
+MLGI_API int mlgi_ism_splat(mlgi_ctx* ctx, const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!ctx->have_vpl || !ctx->have_points) return fail(ctx, MLGI_E_ORDER, "mlgi_ism_splat needs mlgi_vpl_process and mlgi_ism_points first");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer t(ctx, T_SPLAT, st);
+    ctx->launches += launch_splat(ctx->points, ctx->bucket_start, (const float4*)ctx->packed, ctx->cfg.vpl_count, ctx->S, p->z_far, ctx->atlas, st);
+    CK(cudaGetLastError());
+    ctx->have_atlas = true;
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- a4+a5
+MLGI_API int mlgi_ism_pullpush(mlgi_ctx* ctx, const uint32_t* atlas_override, const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!atlas_override && !ctx->have_atlas) return fail(ctx, MLGI_E_ORDER, "mlgi_ism_pullpush needs mlgi_ism_splat first (or an atlas override)");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer t(ctx, T_PULLPUSH, st);
+    ctx->launches += launch_pullpush(atlas_override ? atlas_override : ctx->atlas, ctx->S, p->z_far, ctx->ism, st);
+    CK(cudaGetLastError());
+    ctx->have_ism = true;
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- a6+a7
+MLGI_API int mlgi_cull_clustered(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!gb || !gb->depth || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!ctx->have_vpl) return fail(ctx, MLGI_E_ORDER, "culling needs mlgi_vpl_process first");
+    cudaStream_t st = (cudaStream_t)stream;
+    const SliceTable tab = slice_table(p->z_far);
+    float pv[16], inv[16];
+    mat_mul(cam->proj, cam->view, pv);          // ClusteredShading.cpp:105 inverse(projection * view)
+    mat_inverse(pv, inv);
+    {
+        StageTimer t(ctx, T_CLUSTERIDS, st);
+        ctx->launches += launch_clustering(gb->depth, ctx->cfg.width, ctx->cfg.height, cam->proj[10], cam->proj[14], tab, ctx->tile_masks,
+                                           ctx->compact_ids, ctx->light_list_ids, ctx->counters + 2, st);
+    }
+    {
+        StageTimer t(ctx, T_LIGHTLISTS, st);
+        ctx->launches += launch_light_lists((const float4*)ctx->packed, ctx->cfg.vpl_count, ctx->compact_ids, ctx->counters + 2,
+                                            ctx->X * ctx->Y * 16, to_mat4(inv), cam->proj[10], cam->proj[14], ctx->cfg.width, ctx->cfg.height,
+                                            tab, ctx->cfg.class_lo, ctx->cfg.class_hi, ctx->light_lists, st);
+    }
+    CK(cudaGetLastError());
+    ctx->have_clustered = true;
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- a8
+MLGI_API int mlgi_cull_tiled(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!gb || !gb->depth || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!ctx->have_vpl) return fail(ctx, MLGI_E_ORDER, "culling needs mlgi_vpl_process first");
+    cudaStream_t st = (cudaStream_t)stream;
+    float pv[16], inv[16];
+    mat_mul(cam->proj, cam->view, pv);
+    mat_inverse(pv, inv);
+    StageTimer t(ctx, T_TILED, st);
+    ctx->launches += launch_cull_tiled(gb->depth, ctx->cfg.width, ctx->cfg.height, (const float4*)ctx->packed, ctx->cfg.vpl_count, to_mat4(inv),
+                                       ctx->cfg.class_lo, ctx->cfg.class_hi, ctx->tile_lists, st);
+    CK(cudaGetLastError());
+    ctx->have_tiled = true;
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- a9
+MLGI_API int mlgi_final_gather(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const uint16_t* ism_override,
+                               const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!gb || !gb->depth || !gb->face_normal || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!ctx->have_vpl) return fail(ctx, MLGI_E_ORDER, "mlgi_final_gather needs mlgi_vpl_process first");
+    if (p->enable_shadowing && !ism_override && !ctx->have_ism) return fail(ctx, MLGI_E_ORDER, "shadowing needs mlgi_ism_pullpush first (or an ISM override)");
+    if (p->cull_mode == MLGI_CULL_CLUSTERED && !ctx->have_clustered) return fail(ctx, MLGI_E_ORDER, "clustered gathering needs mlgi_cull_clustered first");
+    if (p->cull_mode == MLGI_CULL_TILED && !ctx->have_tiled) return fail(ctx, MLGI_E_ORDER, "tiled gathering needs mlgi_cull_tiled first");
+    if (p->cull_mode < 0 || p->cull_mode > MLGI_CULL_NONE) return fail(ctx, MLGI_E_INVALID, "bad cull_mode");
+    cudaStream_t st = (cudaStream_t)stream;
+    GatherArgs a;
+    memset(&a, 0, sizeof(a));
+    a.depth = gb->depth; a.face_normal = gb->face_normal; a.W = ctx->cfg.width; a.H = ctx->cfg.height;
+    a.records = ctx->records; a.N = ctx->cfg.vpl_count; a.S = ctx->S;
+    a.ism = ism_override ? ism_override : ctx->ism;
+    a.cull_mode = p->cull_mode;
+    a.lists.light_list_ids = ctx->light_list_ids;
+    a.lists.lists = (p->cull_mode == MLGI_CULL_CLUSTERED) ? ctx->light_lists : ctx->tile_lists;
+    a.lists.X = ctx->X; a.lists.Y = ctx->Y; a.lists.TX = ctx->TX;
+    float vi[16], pi[16], vpi[16];
+    mat_inverse(cam->view, vi);                 // GIStage.cpp:289: viewInverted * projectionInverted
+    mat_inverse(cam->proj, pi);
+    mat_mul(vi, pi, vpi);
+    a.inv_vp = to_mat4(vpi);
+    a.projA = cam->proj[10]; a.projB = cam->proj[14];
+    a.tab = slice_table(p->z_far);
+    a.zFar = p->z_far;
+    a.giScale = p->gi_intensity_factor / float(p->vpl_end_index - p->vpl_start_index) * 16.0f;   // final_gathering.comp:132
+    a.clampv = p->vpl_clamping_value;
+    a.enable_shadowing = p->enable_shadowing;
+    a.class_lo = ctx->cfg.class_lo; a.class_hi = ctx->cfg.class_hi;
+    a.out_raster = ctx->gi;
+    a.out_planar = ctx->gi_planar;
+    a.stats = nullptr;
+    if (ctx->cfg.enable_timers) {
+        // exact work counters for the roofline accounting: an extra, untimed launch of the counting variant
+        CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), st));
+        GatherArgs b = a;
+        b.stats = ctx->stats;
+        ctx->launches += launch_final_gather(b, st);
+    }
+    {
+        StageTimer t(ctx, T_FG, st);
+        ctx->launches += launch_final_gather(a, st);
+    }
+    CK(cudaGetLastError());
+    ctx->have_gi = true;
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- n1
+MLGI_API int mlgi_gi_blur(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!gb || !gb->depth || !gb->face_normal || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
+    if (!ctx->have_gi) return fail(ctx, MLGI_E_ORDER, "mlgi_gi_blur needs mlgi_final_gather first");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer t(ctx, T_BLUR, st);
+    ctx->launches += launch_gi_blur(ctx->gi, gb->depth, gb->face_normal, ctx->cfg.width, ctx->cfg.height, cam->proj[10], cam->proj[14],
+                                    ctx->gi_tmp, ctx->gi_blur, st);
+    CK(cudaGetLastError());
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- a10
+MLGI_API int mlgi_frame(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
+                        const mlgi_camera* cam, const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    int rc;
+    if ((rc = mlgi_vpl_process(ctx, rsm, light, p, stream))) return rc;          // GIStage.cpp:373-376
+    if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;                  // :378-389 ISM render
+    if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;                         //          ISM CS
+    if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;             //          pull / push
+    if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, gb, cam, p, stream))) return rc; }   // :392-403
+    else if (p->cull_mode == MLGI_CULL_TILED) { if ((rc = mlgi_cull_tiled(ctx, gb, cam, p, stream))) return rc; }
+    return mlgi_final_gather(ctx, gb, cam, nullptr, p, stream);                   // :405-408
+}
+
+MLGI_API int mlgi_frame_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
+                             const mlgi_camera* cam, const mlgi_params* p, float* host_gi, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!hr || !hg || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t RS = (size_t)ctx->cfg.rsm_width * ctx->cfg.rsm_height, WH = (size_t)ctx->cfg.width * ctx->cfg.height;
+    {
+        StageTimer t(ctx, T_H2D, st);
+        CK(cudaMemcpyAsync(ctx->st_rsm_diffuse, hr->diffuse, RS * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->st_rsm_normal, hr->face_normal, RS * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->st_rsm_depth, hr->depth, RS * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->st_depth, hg->depth, WH * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->st_normal, hg->face_normal, WH * 4, cudaMemcpyHostToDevice, st));
+    }
+    mlgi_rsm dr = {ctx->st_rsm_diffuse, ctx->st_rsm_normal, ctx->st_rsm_depth};
+    mlgi_gbuffer dg = {ctx->st_depth, ctx->st_normal};
+    int rc = mlgi_frame(ctx, &dr, light, mesh, &dg, cam, p, stream);
+    if (rc) return rc;
+    if (host_gi) {
+        StageTimer t(ctx, T_D2H, st);
+        CK(cudaMemcpyAsync(host_gi, ctx->gi, WH * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- inspection
+MLGI_API int mlgi_get_buffer(mlgi_ctx* ctx, int id, void** dev_ptr, size_t* bytes) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!dev_ptr || !bytes) return fail(ctx, MLGI_E_INVALID, "dev_ptr/bytes is NULL");
+    const size_t N = ctx->cfg.vpl_count, WH = (size_t)ctx->cfg.width * ctx->cfg.height, AA = (size_t)ctx->A * ctx->A;
+    const size_t maxClusters = (size_t)ctx->X * ctx->Y * 16, L1 = ctx->L + 1;
+    const size_t PW = (ctx->cfg.width + 3) / 4, PH = (ctx->cfg.height + 3) / 4;
+    switch (id) {
+        case MLGI_BUF_VPL: *dev_ptr = ctx->vpl; *bytes = N * 48; break;
+        case MLGI_BUF_PACKED_VPL: *dev_ptr = ctx->packed; *bytes = N * 16; break;
+        case MLGI_BUF_SHUFFLE: *dev_ptr = ctx->shuffle; *bytes = N * 4; break;
+        case MLGI_BUF_POINTS: *dev_ptr = ctx->points; *bytes = (size_t)ctx->cfg.max_points * 16; break;
+        case MLGI_BUF_BUCKET_START: *dev_ptr = ctx->bucket_start; *bytes = (N + 1) * 4; break;
+        case MLGI_BUF_ATLAS: *dev_ptr = ctx->atlas; *bytes = AA * 4; break;
+        case MLGI_BUF_ISM: *dev_ptr = ctx->ism; *bytes = AA * 2; break;
+        case MLGI_BUF_COMPACT_CLUSTER_IDS: *dev_ptr = ctx->compact_ids; *bytes = maxClusters * 4; break;
+        case MLGI_BUF_LIGHT_LIST_IDS: *dev_ptr = ctx->light_list_ids; *bytes = maxClusters * 2; break;
+        case MLGI_BUF_LIGHT_LISTS: *dev_ptr = ctx->light_lists; *bytes = maxClusters * 16 * L1 * 2; break;
+        case MLGI_BUF_TILE_LISTS: *dev_ptr = ctx->tile_lists; *bytes = (size_t)ctx->TX * ctx->TY * 16 * L1 * 2; break;
+        case MLGI_BUF_NUM_USED_CLUSTERS: *dev_ptr = ctx->counters + 2; *bytes = 4; break;
+        case MLGI_BUF_GI: *dev_ptr = ctx->gi; *bytes = WH * 16; break;
+        case MLGI_BUF_GI_PLANAR: *dev_ptr = ctx->gi_planar; *bytes = (size_t)(ctx->cfg.class_hi - ctx->cfg.class_lo) * PW * PH * 16; break;
+        case MLGI_BUF_GI_BLUR: *dev_ptr = ctx->gi_blur; *bytes = WH * 16; break;
+        default: return fail(ctx, MLGI_E_INVALID, "unknown buffer id %d", id);
+    }
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_read_buffer(mlgi_ctx* ctx, int id, void* host_dst, size_t bytes, size_t offset) {
+    if (!ctx) return MLGI_E_INVALID;
+    void* p = nullptr;
+    size_t n = 0;
+    int rc = mlgi_get_buffer(ctx, id, &p, &n);
+    if (rc) return rc;
+    if (!host_dst || offset + bytes > n) return fail(ctx, MLGI_E_INVALID, "read of %zu bytes at %zu exceeds buffer %d (%zu bytes)", bytes, offset, id, n);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host_dst, (const char*)p + offset, bytes, cudaMemcpyDeviceToHost));
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_get_counts(mlgi_ctx* ctx, int* num_points, int* num_used_clusters) {
+    if (!ctx) return MLGI_E_INVALID;
+    uint32_t h[4];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, ctx->counters, sizeof(h), cudaMemcpyDeviceToHost));
+    if (num_points) *num_points = (int)h[0];
+    if (num_used_clusters) *num_used_clusters = (int)h[2];
+    if (h[1] > h[0]) return fail(ctx, MLGI_E_CAPACITY, "point buffer overflow: %u points generated, capacity %d", h[1], ctx->cfg.max_points);
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_get_gather_stats(mlgi_ctx* ctx, unsigned long long* listed, unsigned long long* lit) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!ctx->cfg.enable_timers) return fail(ctx, MLGI_E_INVALID, "gather stats need cfg.enable_timers");
+    unsigned long long h[2];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
+    if (listed) *listed = h[0];
+    if (lit) *lit = h[1];
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_get_timings(mlgi_ctx* ctx, mlgi_timing* out, int cap) {
+    if (!ctx || !out) return 0;
+    if (!ctx->cfg.enable_timers) return 0;
+    cudaDeviceSynchronize();
+    int n = 0;
+    for (int i = 0; i < T_COUNT && n < cap; i++) {
+        if (!ctx->ev_used[i]) continue;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[i][0], ctx->ev[i][1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        snprintf(out[n].name, sizeof(out[n].name), "%s", kTimerNames[i]);
+        out[n].ms = ms;
+        out[n].launches = ctx->ev_launches[i];
+        n++;
+    }
+    return n;
+}
+
+MLGI_API unsigned long long mlgi_launch_count(const mlgi_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+}  // extern "C"

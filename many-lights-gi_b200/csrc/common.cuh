@@ -1,0 +1,156 @@
+// common.cuh -- shared declarations of libmlgi (B200 / sm_100a).
+//
+// Numerical contract (DESIGN.md "bit-exactness"): the translation unit exact.cu is
+// compiled with -fmad=false and only uses the helpers below, which fix the evaluation
+// order (glm's: ((x*x)+(y*y))+(z*z), (m0*x+m1*y)+(m2*z+m3*w)), IEEE division/sqrt
+// (nvcc defaults -prec-div=true -prec-sqrt=true) and GLSL-style min/max ternaries, so the
+// integer outputs (atlas, ISM R16, cluster ids, light lists) agree bit for bit with the CPU
+// oracle. gather.cu (radiance, 1e-3 tolerance) is compiled with FMA contraction on.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/mlgi.h"
+
+namespace mlgi {
+
+// ---------------------------------------------------------------------------------------
+// column-major 4x4 passed by value to kernels
+struct Mat4 { float m[16]; };
+
+// Hoisted per-VPL record used by the gathering kernel (80 B, 5 x float4):
+//   r0 = (pos.xyz, tile_x*64 + 32)   r1 = (nrm.xyz, tile_y*64 + 32)
+//   r2 = (s.xyz, 0)   r3 = (u.xyz, 0)   (lookAtRH rows, ism_utils.glsl:5-13)
+//   r4 = (col.xyz, 0)
+struct VplRecord { float4 r[5]; };
+
+struct DevLists {              // what the gathering kernel needs to find a pixel's list
+    const uint16_t* light_list_ids;  // clustered: [16][Y][X]
+    const uint16_t* lists;           // [list][16][L+1]
+    int X, Y;                        // clustered tile grid
+    int TX;                          // tiled: tiles per row
+};
+
+// ---------------------------------------------------------------------------------------
+// exact helpers (device)
+#ifdef __CUDACC__
+__device__ __forceinline__ float gmin(float a, float b) { return (b < a) ? b : a; }   // GLSL min
+__device__ __forceinline__ float gmax(float a, float b) { return (a < b) ? b : a; }   // GLSL max
+__device__ __forceinline__ float gclamp(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 sub3(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 add3(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 mul3s(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 div3s(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float3 neg3(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ float len3(float3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) {
+    return f3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+__device__ __forceinline__ float3 normalize3(float3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return mul3s(a, inv); }
+__device__ __forceinline__ float4 mat4_mul_vec4(const Mat4& M, float x, float y, float z, float w) {
+    float4 r;
+    r.x = (M.m[0] * x + M.m[4] * y) + (M.m[8] * z + M.m[12] * w);
+    r.y = (M.m[1] * x + M.m[5] * y) + (M.m[9] * z + M.m[13] * w);
+    r.z = (M.m[2] * x + M.m[6] * y) + (M.m[10] * z + M.m[14] * w);
+    r.w = (M.m[3] * x + M.m[7] * y) + (M.m[11] * z + M.m[15] * w);
+    return r;
+}
+__device__ __forceinline__ int f2i(float f) { return __float2int_rz(f); }          // NaN -> 0, saturating
+__device__ __forceinline__ uint32_t f2u(float f) { return __float2uint_rz(f); }    // NaN/neg -> 0, saturating
+
+// floatpacking.glsl:46-66
+__device__ __forceinline__ float3 unpack3SN(float packed) {
+    uint32_t u = __float_as_uint(packed);
+    float a = float(u & 0x3FFu) / 1023.0f;
+    float b = float((u >> 10) & 0x3FFu) / 1023.0f;
+    float c = (float((u >> 20) & 0x3FFu) - 1.5f) / 1021.0f;
+    return f3(a * 2.0f - 1.0f, b * 2.0f - 1.0f, c * 2.0f - 1.0f);
+}
+// floatpacking.glsl:26-44
+__device__ __forceinline__ float pack3SN(float3 n) {
+    float cx = n.x * 0.5f + 0.5f, cy = n.y * 0.5f + 0.5f, cz = n.z * 0.5f + 0.5f;
+    uint32_t u = f2u(cx * 1023.0f + 0.5f);
+    u |= f2u(cy * 1023.0f + 0.5f) << 10;
+    u |= f2u(cz * 1021.0f + 1.5f) << 20;
+    return __uint_as_float(u);
+}
+// RGB10_A2 unorm fetch * 2 - 1
+__device__ __forceinline__ float3 decode_rgb10_sn(uint32_t n10) {
+    return f3(float(n10 & 0x3FFu) / 1023.0f * 2.0f - 1.0f, float((n10 >> 10) & 0x3FFu) / 1023.0f * 2.0f - 1.0f,
+              float((n10 >> 20) & 0x3FFu) / 1023.0f * 2.0f - 1.0f);
+}
+__device__ __forceinline__ uint32_t pack_unorm8(float c) { return __float2uint_rn(gclamp(c, 0.0f, 1.0f) * 255.0f) & 0xFFu; }
+__device__ __forceinline__ uint32_t pack_half2(float x, float y) {
+    return (uint32_t)__half_as_ushort(__float2half_rn(x)) | ((uint32_t)__half_as_ushort(__float2half_rn(y)) << 16);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t p) {
+    return make_float2(__half2float(__ushort_as_half((unsigned short)(p & 0xFFFFu))), __half2float(__ushort_as_half((unsigned short)(p >> 16))));
+}
+// reprojection.glsl:6-14
+__device__ __forceinline__ float linear_depth(float depthSample, float A, float B) {
+    float z_n = 2.0f * depthSample - 1.0f;
+    return -B / (A + z_n);
+}
+// reprojection.glsl:16-24
+__device__ __forceinline__ float log_depth(float z, float A, float B) {
+    float z_n = (1.0f / z * -B) - A;
+    return (z_n + 1.0f) / 2.0f;
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------
+// kernel launchers (defined in exact.cu / gather.cu, called from api.cpp). All return the
+// number of kernels they launched so the ctx can keep mlgi_launch_count honest.
+struct SliceTable { float b[17]; };
+
+int launch_vpl_process(const mlgi_rsm& rsm, int rsm_w, int rsm_h, int N, const Mat4& inv_biased_light_vp,
+                       float lightIntensity, int shuffle, const int32_t* shuffled, int S,
+                       float* vpl, float* packed, VplRecord* records, cudaStream_t st);
+
+int launch_point_counts(const mlgi_mesh& mesh, float tessLevelFactor, uint32_t* tri_offsets /*ntri+1*/,
+                        uint32_t* scan_tmp, cudaStream_t st);
+int launch_point_generate(const mlgi_mesh& mesh, float tessLevelFactor, int N, const uint32_t* tri_offsets,
+                          int max_points, float4* points_unsorted, uint32_t* point_bucket, uint32_t* bucket_hist,
+                          uint32_t* bucket_start, uint32_t* bucket_cursor, float4* points_sorted,
+                          uint32_t* num_points_dev, cudaStream_t st);
+int launch_bucket_scan(int N, const uint32_t* bucket_start_in, cudaStream_t st);
+
+int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S,
+                 float zFar, uint32_t* atlas, cudaStream_t st);
+int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, cudaStream_t st);
+
+int launch_clustering(const float* depth, int W, int H, float projA, float projB, const SliceTable& tab,
+                      uint32_t* tile_masks, uint32_t* compact_ids, uint16_t* light_list_ids, uint32_t* num_used,
+                      cudaStream_t st);
+int launch_light_lists(const float4* packed_vpl, int N, const uint32_t* compact_ids, const uint32_t* num_used,
+                       int max_clusters, const Mat4& inv_vp, float projA, float projB, int W, int H,
+                       const SliceTable& tab, int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);
+int launch_cull_tiled(const float* depth, int W, int H, const float4* packed_vpl, int N, const Mat4& inv_vp,
+                      int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);
+
+struct GatherArgs {
+    const float* depth; const uint32_t* face_normal; int W, H;
+    const VplRecord* records; int N; int S;
+    const uint16_t* ism;
+    DevLists lists; int cull_mode;
+    Mat4 inv_vp;            // viewInverted * projectionInverted (GIStage.cpp:289)
+    float projA, projB;     // P[2][2], P[3][2]
+    SliceTable tab;
+    float zFar, giScale /* giIntensityFactor / vplCount * 16 */, clampv;
+    int enable_shadowing;
+    int class_lo, class_hi;
+    float4* out_raster;     // may be null
+    float4* out_planar;     // may be null
+    unsigned long long* stats;  // null, or 2 counters (pairs listed / lit)
+};
+int launch_final_gather(const GatherArgs& a, cudaStream_t st);
+int launch_gi_blur(const float4* gi, const float* depth, const uint32_t* face_normal, int W, int H, float projA,
+                   float projB, float4* tmp, float4* out, cudaStream_t st);
+int launch_planar_to_raster(const float4* planar, int W, int H, int class_lo, int class_hi, float4* raster, cudaStream_t st);
+
+constexpr int kTile = 64;  // tiled-culling tile edge in pixels (one gathering CTA = one class of one tile)
+
+}  // namespace mlgi

@@ -1,0 +1,841 @@
+// exact.cu -- the stages whose outputs are under a bit-exact contract with the CPU oracle.
+// Compiled with -fmad=false (no FMA contraction); see common.cuh for the numeric rules.
+//
+//   a1  vpl_process_kernel      (vpl_processor.comp:41-72)
+//   a2  point_count / point_generate / point_scatter   (ism.tesc/tese/geom, deterministic tessellator)
+//   a3  splat_kernel            (ism.comp:54-139)  warp-aggregated atomicMin into the R32UI atlas
+//   a4+a5 pullpush_kernel       (pull.comp x6 + push.comp x6) one 64x64 ISM per CTA, pyramid in smem
+//   a6  cluster_mask / cluster_compact                 (clustering.comp:30-88)
+//   a7  light_lists_kernel      (light_lists.comp:50-126) ballot + popc compaction, ascending ids
+//   a8  cull_tiled_kernel       (tiled variant)
+#include "common.cuh"
+
+namespace mlgi {
+
+static constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// =====================================================================================
+// a1: one thread per VPL. Also emits the hoisted record the gathering kernel consumes
+// (lookAtRH basis + atlas tile origin are pure functions of the VPL, ism_utils.glsl:5-13,35-38).
+// =====================================================================================
+__global__ void vpl_process_kernel(const uint32_t* __restrict__ diffuse, const uint32_t* __restrict__ normal10,
+                                   const float* __restrict__ depth, int rsm_w, int rsm_h, int N, Mat4 inv,
+                                   float lightIntensity, int shuffle, const int32_t* __restrict__ shuffled, int S,
+                                   float* __restrict__ vpl, float* __restrict__ packed, VplRecord* __restrict__ records) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint32_t)N) return;
+    const uint32_t ax = (uint32_t)ceilf(sqrtf(float(N)));            // vpl_processor.comp:38
+    const uint32_t ay = (uint32_t)N / ax;                             // :46
+    uint32_t tcx = (idx % ax) * (uint32_t)rsm_w / ax;                 // :50
+    uint32_t tcy = (idx / ax) * (uint32_t)rsm_h / ay;
+    float tfx = float(tcx) / float(rsm_w), tfy = float(tcy) / float(rsm_h);  // :51
+    size_t t = (size_t)tcy * rsm_w + tcx;
+    uint32_t d8 = diffuse[t];
+    float3 dif = f3(float(d8 & 0xFFu) / 255.0f, float((d8 >> 8) & 0xFFu) / 255.0f, float((d8 >> 16) & 0xFFu) / 255.0f);
+    float3 nrm = decode_rgb10_sn(normal10[t]);                        // :54
+    float dep = depth[t];
+    float4 wc = mat4_mul_vec4(inv, tfx, tfy, dep, 1.0f);              // :57
+    float3 w = f3(wc.x / wc.w, wc.y / wc.w, wc.z / wc.w);             // :58
+    float3 col = mul3s(dif, lightIntensity);                          // :60
+    uint32_t slot = shuffle ? (uint32_t)shuffled[idx] : idx;          // :62-63
+    float pn = pack3SN(nrm);                                          // :65
+    float3 un = unpack3SN(pn);                                        // :68
+    float* o = vpl + (size_t)slot * 12;
+    o[0] = w.x; o[1] = w.y; o[2] = w.z; o[3] = 0.0f;
+    o[4] = un.x; o[5] = un.y; o[6] = un.z; o[7] = 0.0f;
+    o[8] = col.x; o[9] = col.y; o[10] = col.z; o[11] = 0.0f;
+    float* p = packed + (size_t)slot * 4;
+    p[0] = w.x; p[1] = w.y; p[2] = w.z; p[3] = pn;
+    // hoisted record
+    float3 up = f3(0.0f, 1.0f, 0.01f);
+    float3 s = normalize3(cross3(un, up));
+    float3 u = cross3(s, un);
+    int ty = (int)slot / S, tx = (int)slot - ty * S;
+    VplRecord r;
+    r.r[0] = make_float4(w.x, w.y, w.z, float(tx * 64 + 32));
+    r.r[1] = make_float4(un.x, un.y, un.z, float(ty * 64 + 32));
+    r.r[2] = make_float4(s.x, s.y, s.z, 0.0f);
+    r.r[3] = make_float4(u.x, u.y, u.z, 0.0f);
+    r.r[4] = make_float4(col.x, col.y, col.z, 0.0f);
+    records[slot] = r;
+}
+
+int launch_vpl_process(const mlgi_rsm& rsm, int rsm_w, int rsm_h, int N, const Mat4& inv, float lightIntensity,
+                       int shuffle, const int32_t* shuffled, int S, float* vpl, float* packed, VplRecord* records,
+                       cudaStream_t st) {
+    vpl_process_kernel<<<(N + 63) / 64, 64, 0, st>>>(rsm.diffuse, rsm.face_normal, rsm.depth, rsm_w, rsm_h, N, inv,
+                                                    lightIntensity, shuffle, shuffled, S, vpl, packed, records);
+    return 1;
+}
+
+// =====================================================================================
+// device-wide exclusive scan of uint32 (3 small kernels; n up to a few million)
+// =====================================================================================
+static constexpr int SCAN_THREADS = 1024;
+static constexpr int SCAN_ITEMS = 2;
+static constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0u;
+        uint32_t y = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t z = __shfl_up_sync(FULL, y, o);
+            if (lane >= o) y += z;
+        }
+        warp_sums[lane] = y - ws;           // exclusive
+        if (lane == 31) *total = y;
+    }
+    __syncthreads();
+    uint32_t r = warp_sums[warp] + x - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint32_t* __restrict__ in, int n, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t total;
+    int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) s += in[base + k];
+    block_exclusive_scan(s, &total, ws);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+// single block: exclusive scan of block_sums in place (loops for > 1024 blocks); writes grand total to block_sums[nb]
+__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(uint32_t* __restrict__ block_sums, int nb) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    for (int base = 0; base < nb; base += SCAN_THREADS) {
+        int i = base + threadIdx.x;
+        uint32_t v = (i < nb) ? block_sums[i] : 0u;
+        uint32_t e = block_exclusive_scan(v, &total, ws);
+        if (i < nb) block_sums[i] = carry + e;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[nb] = carry;
+}
+// out[i] = exclusive prefix; out[n] = total
+__global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(const uint32_t* in, int n, const uint32_t* __restrict__ block_sums,
+                                                                   int nb, uint32_t* out) {   // in may alias out
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t total;
+    int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : 0u; s += v[k]; }
+    uint32_t e = block_exclusive_scan(s, &total, ws) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = e; e += v[k]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[nb];
+}
+// in may alias out. tmp needs ceil(n/SCAN_BLOCK)+1 words.
+static int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int n, uint32_t* tmp, cudaStream_t st) {
+    int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nb < 1) nb = 1;
+    scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, tmp);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(tmp, nb);
+    scan_final_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, tmp, nb, out);
+    return 3;
+}
+
+// =====================================================================================
+// a2: points. Deterministic tessellator:
+//   n = ceil(clamp(max edge * tessLevelFactor, 1, 64)), n^2 sub-triangles, sub id k enumerates
+//   rows j = 0..n-1, inside a row i = 0..n-1-j: up(i,j) then down(i,j).
+// =====================================================================================
+__device__ __forceinline__ float3 load_vertex(const float* __restrict__ v, uint32_t i) { return f3(v[3 * i], v[3 * i + 1], v[3 * i + 2]); }
+
+__device__ __forceinline__ int tess_n(float3 v0, float3 v1, float3 v2, float tf) {
+    float l0 = len3(sub3(v1, v2)), l1 = len3(sub3(v2, v0)), l2 = len3(sub3(v0, v1));  // ism.tesc:13-15
+    float o0 = l0 * tf, o1 = l1 * tf, o2 = l2 * tf;                                    // :16-18
+    float inner = gmax(gmax(o0, o1), o2);                                              // :20
+    return f2i(ceilf(gclamp(inner, 1.0f, 64.0f)));
+}
+
+__global__ void point_count_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ indices, int ntri, float tf,
+                                   uint32_t* __restrict__ counts) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntri) return;
+    float3 v0 = load_vertex(verts, indices[3 * t]), v1 = load_vertex(verts, indices[3 * t + 1]), v2 = load_vertex(verts, indices[3 * t + 2]);
+    int n = tess_n(v0, v1, v2, tf);
+    counts[t] = (uint32_t)(n * n);
+}
+
+int launch_point_counts(const mlgi_mesh& mesh, float tf, uint32_t* tri_offsets, uint32_t* scan_tmp, cudaStream_t st) {
+    int ntri = mesh.num_triangles;
+    point_count_kernel<<<(ntri + 255) / 256, 256, 0, st>>>(mesh.vertices, mesh.indices, ntri, tf, tri_offsets);
+    return 1 + exclusive_scan_u32(tri_offsets, tri_offsets, ntri, scan_tmp, st);
+}
+
+// random.glsl:34-46,50-59,65
+__device__ __forceinline__ uint32_t hash1(uint32_t x) {
+    x += (x << 10u); x ^= (x >> 6u); x += (x << 3u); x ^= (x >> 11u); x += (x << 15u);
+    return x;
+}
+__device__ __forceinline__ float random3(float3 v) {
+    uint32_t h = hash1(__float_as_uint(v.x) ^ hash1(__float_as_uint(v.y)) ^ hash1(__float_as_uint(v.z)));
+    return __uint_as_float((h & 0x007FFFFFu) | 0x3F800000u) - 1.0f;
+}
+
+__global__ void __launch_bounds__(256) point_generate_kernel(const float* __restrict__ verts, const float* __restrict__ normals,
+                                                             const uint32_t* __restrict__ indices, const uint32_t* __restrict__ prim_id,
+                                                             int ntri, int N, const uint32_t* __restrict__ tri_offsets, int max_points,
+                                                             float4* __restrict__ points_unsorted, uint32_t* __restrict__ point_bucket,
+                                                             uint32_t* __restrict__ bucket_hist, uint32_t* __restrict__ num_points_dev) {
+    const uint32_t total = tri_offsets[ntri];
+    const uint32_t P = total < (uint32_t)max_points ? total : (uint32_t)max_points;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { num_points_dev[0] = P; num_points_dev[1] = total; }
+    const float sqrtN = sqrtf(float(N));
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        // triangle owning point p: largest t with tri_offsets[t] <= p
+        int lo = 0, hi = ntri - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (tri_offsets[mid] <= p) lo = mid; else hi = mid - 1;
+        }
+        const int t = lo;
+        const uint32_t start = tri_offsets[t];
+        const int k = (int)(p - start);
+        const int nn = (int)(tri_offsets[t + 1] - start);
+        int n = __float2int_rn(sqrtf(float(nn)));
+        // row j: largest j with 2nj - j^2 <= k
+        int j = (int)(float(n) - sqrtf(float(nn - k)));
+        if (j < 0) j = 0;
+        if (j > n - 1) j = n - 1;
+        while (j > 0 && 2 * n * j - j * j > k) j--;
+        while (j < n - 1 && 2 * n * (j + 1) - (j + 1) * (j + 1) <= k) j++;
+        const int r = k - (2 * n * j - j * j);
+        const int i = r >> 1, down = r & 1;
+        uint32_t i0 = indices[3 * t], i1 = indices[3 * t + 1], i2 = indices[3 * t + 2];
+        float3 v0 = load_vertex(verts, i0), v1 = load_vertex(verts, i1), v2 = load_vertex(verts, i2);
+        float3 te_normal = load_vertex(normals, i0);                        // ism.tese:22
+        int gi[3], gj[3];
+        if (!down) { gi[0] = i; gj[0] = j; gi[1] = i + 1; gj[1] = j; gi[2] = i; gj[2] = j + 1; }
+        else       { gi[0] = i + 1; gj[0] = j; gi[1] = i + 1; gj[1] = j + 1; gi[2] = i; gj[2] = j + 1; }
+        const float fn = float(n);
+        float3 tc[3], pp[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            tc[q] = f3(float(n - gi[q] - gj[q]) / fn, float(gi[q]) / fn, float(gj[q]) / fn);
+            pp[q] = add3(add3(mul3s(v0, tc[q].x), mul3s(v1, tc[q].y)), mul3s(v2, tc[q].z));   // ism.tese:9-12
+        }
+        float3 position = div3s(add3(add3(pp[0], pp[1]), pp[2]), 3.0f);       // ism.geom:51
+        float3 bary = div3s(add3(add3(tc[0], tc[1]), tc[2]), 3.0f);           // :52
+        float maxdist = gmax(gmax(len3(sub3(position, pp[0])), len3(sub3(position, pp[1]))), len3(sub3(position, pp[2])));  // :54
+        float sd = float(prim_id[t] % 4096u) / 4096.0f;                       // :56
+        float3 seed = f3(bary.x + sd, bary.y + sd, bary.z + sd);
+        int base = f2i(random3(seed) * float(N));                             // :57
+        if (base >= N) base = N - 1;
+        float radius = maxdist * sqrtN;                                       // :63
+        uint32_t nr = pack_unorm8(te_normal.x * 0.5f + 0.5f) | (pack_unorm8(te_normal.y * 0.5f + 0.5f) << 8) |
+                      (pack_unorm8(te_normal.z * 0.5f + 0.5f) << 16) | (pack_unorm8(radius / 25.0f) << 24);  // :64
+        points_unsorted[p] = make_float4(position.x, position.y, position.z, __uint_as_float(nr));
+        point_bucket[p] = (uint32_t)base;
+        atomicAdd(&bucket_hist[base], 1u);                                    // :66 (counter only; slot assigned after the scan)
+    }
+}
+
+__global__ void __launch_bounds__(256) point_scatter_kernel(const float4* __restrict__ points_unsorted, const uint32_t* __restrict__ point_bucket,
+                                                            const uint32_t* __restrict__ num_points_dev, const uint32_t* __restrict__ bucket_start,
+                                                            uint32_t* __restrict__ bucket_cursor, float4* __restrict__ points_sorted) {
+    const uint32_t P = num_points_dev[0];
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        uint32_t b = point_bucket[p];
+        uint32_t slot = bucket_start[b] + atomicAdd(&bucket_cursor[b], 1u);
+        points_sorted[slot] = points_unsorted[p];
+    }
+}
+
+// single-block exclusive scan for the bucket histogram (N <= 16384): out has N+1 entries
+__global__ void __launch_bounds__(SCAN_THREADS) bucket_scan_kernel(const uint32_t* __restrict__ hist, int N, uint32_t* __restrict__ out) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    for (int base = 0; base < N; base += SCAN_THREADS) {
+        int i = base + threadIdx.x;
+        uint32_t v = (i < N) ? hist[i] : 0u;
+        uint32_t e = block_exclusive_scan(v, &total, ws);
+        if (i < N) out[i] = carry + e;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[N] = carry;
+}
+
+int launch_point_generate(const mlgi_mesh& mesh, float tf, int N, const uint32_t* tri_offsets, int max_points,
+                          float4* points_unsorted, uint32_t* point_bucket, uint32_t* bucket_hist, uint32_t* bucket_start,
+                          uint32_t* bucket_cursor, float4* points_sorted, uint32_t* num_points_dev, cudaStream_t st) {
+    (void)tf;
+    cudaMemsetAsync(bucket_hist, 0, sizeof(uint32_t) * N, st);
+    cudaMemsetAsync(bucket_cursor, 0, sizeof(uint32_t) * N, st);
+    const int grid = 148 * 8;
+    point_generate_kernel<<<grid, 256, 0, st>>>(mesh.vertices, mesh.normals, mesh.indices, mesh.prim_id, mesh.num_triangles, N,
+                                                tri_offsets, max_points, points_unsorted, point_bucket, bucket_hist, num_points_dev);
+    bucket_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(bucket_hist, N, bucket_start);
+    point_scatter_kernel<<<grid, 256, 0, st>>>(points_unsorted, point_bucket, num_points_dev, bucket_start, bucket_cursor, points_sorted);
+    return 3;
+}
+
+// =====================================================================================
+// a3: splat. One CTA per bucket (ism.comp: one workgroup per bucket, 128 threads); the
+// 16-VPL window (position, unpacked normal, lookAtRH rows) is staged in shared memory.
+// atomicMin on (depth24<<8 | radius8) is warp-aggregated: lanes that hit the same texel are
+// grouped with __match_any_sync and reduced with __reduce_min_sync, one RED per group.
+// =====================================================================================
+struct WinVpl { float3 pos, nrm, s, u; float tile_x, tile_y; };
+
+__global__ void __launch_bounds__(128) splat_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ bucket_start,
+                                                    const float4* __restrict__ packed_vpl, int N, int S, float zFar,
+                                                    uint32_t* __restrict__ atlas) {
+    __shared__ WinVpl win[16];
+    const int b = blockIdx.x;
+    if (threadIdx.x < 16) {                                  // ism.comp:60-69
+        int index = (b + (int)threadIdx.x) % N;
+        float4 pv = packed_vpl[index];
+        WinVpl w;
+        w.pos = f3(pv.x, pv.y, pv.z);
+        w.nrm = unpack3SN(pv.w);
+        float3 up = f3(0.0f, 1.0f, 0.01f);                   // ism_utils.glsl:5-13
+        w.s = normalize3(cross3(w.nrm, up));
+        w.u = cross3(w.s, w.nrm);
+        float ismIndex = float(index);                       // ism_utils.glsl:35-36
+        float y = float(f2i(ismIndex / float(S)));
+        w.tile_x = float(f2i(ismIndex - y * float(S)));
+        w.tile_y = float(f2i(y));
+        win[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const uint32_t begin = bucket_start[b], end = bucket_start[b + 1];
+    const float fA = float(64 * S);
+    const int A = 64 * S;
+    for (uint32_t base = begin; base < end; base += blockDim.x) {   // warp-uniform trip count
+        const uint32_t pid = base + threadIdx.x;
+        const bool have = pid < end;
+        float3 position = f3(0, 0, 0), pointNormal = f3(0, 0, 0);
+        float pointRadius = 0.0f;
+        uint32_t survivors = 0;   // bit i set: window VPL i passed both hemisphere tests
+        if (have) {
+            float4 rd = points[pid];
+            position = f3(rd.x, rd.y, rd.z);
+            uint32_t nr = __float_as_uint(rd.w);                   // ism.comp:85-87
+            pointNormal = f3(float(nr & 0xFFu) / 255.0f * 2.0f - 1.0f, float((nr >> 8) & 0xFFu) / 255.0f * 2.0f - 1.0f,
+                             float((nr >> 16) & 0xFFu) / 255.0f * 2.0f - 1.0f);
+            pointRadius = float((nr >> 24) & 0xFFu) / 255.0f * 25.0f;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {                         // :94-107
+                float3 rel = sub3(position, win[i].pos);
+                bool cull = dot3(win[i].nrm, rel) < 0.0f || dot3(pointNormal, neg3(rel)) < 0.0f;
+                if (!cull) survivors |= 1u << i;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {                              // :112-137
+            bool active = survivors != 0;                          // first <= 4 survivors in window order
+            uint32_t val = 0xFFFFFFFFu;
+            uint32_t addr = 0xFFFFFFFFu;
+            if (active) {
+                const WinVpl& w = win[__ffs(survivors) - 1];
+                survivors &= survivors - 1;
+                float3 rel = sub3(position, w.pos);
+                float dist = len3(rel);
+                // paraboloid_project(rel, dist, nrm, zFar, id, S, true)  ism_utils.glsl:15-40
+                float vx = (w.s.x * rel.x + w.s.y * rel.y) + w.s.z * rel.z;
+                float vy = (w.u.x * rel.x + w.u.y * rel.y) + w.u.z * rel.z;
+                float vz = -dot3(w.nrm, rel);
+                float sg = (vz > 0.0f) ? 1.0f : ((vz < 0.0f) ? -1.0f : 0.0f);
+                vx = vx / dist; vy = vy / dist; vz = vz / dist;
+                vz = 1.0f - vz;
+                vx = vx / vz; vy = vy / vz;
+                vz = dist / zFar;
+                vz = vz * -sg;
+                vx += 1.0f; vy += 1.0f;
+                vx /= 2.0f; vy /= 2.0f;
+                vx += w.tile_x; vy += w.tile_y;
+                vx /= float(S); vy /= float(S);
+                vx *= fA; vy *= fA;                                // ism.comp:131
+                vz *= 16777216.0f;                                 // :132
+                uint32_t depth24 = f2u(vz);
+                if (depth24 > 0xFFFFFFu) depth24 = 0xFFFFFFu;      // Q10
+                val = (depth24 << 8) | (f2u(pointRadius * 10.0f / 2.0f) & 0xFFu);  // :134-135
+                int tx = f2i(vx), ty = f2i(vy);
+                if (tx < 0 || ty < 0 || tx >= A || ty >= A) active = false;
+                else addr = (uint32_t)ty * (uint32_t)A + (uint32_t)tx;
+            }
+            unsigned act = __ballot_sync(FULL, active);
+            if (active) {
+                unsigned grp = __match_any_sync(act, addr);
+                uint32_t mn = __reduce_min_sync(grp, val);
+                if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicMin(&atlas[addr], mn);  // imageAtomicMin :136
+            }
+        }
+    }
+}
+
+int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S, float zFar,
+                 uint32_t* atlas, cudaStream_t st) {
+    const size_t A = 64 * (size_t)S;
+    cudaMemsetAsync(atlas, 0xFF, A * A * sizeof(uint32_t), st);   // ImperfectShadowmap.cpp:212
+    splat_kernel<<<N, 128, 0, st>>>(points, bucket_start, packed_vpl, N, S, zFar, atlas);
+    return 1;
+}
+
+// =====================================================================================
+// a4+a5: pull-push. One CTA per 64x64 ISM; the whole 6-level pyramid lives in shared memory
+// (16 KB level 0 + 21.3 KB RGBA32F levels 1..6); HBM traffic = 4 B read + 2 B written per
+// atlas texel instead of the reference's 12 full-atlas passes. Per-ISM independence: pull
+// 2x2 blocks never straddle a 64-px tile; push masks every coarse tap of another ISM
+// (push.comp:77-86), so out-of-tile taps are zero-filled (what an out-of-bounds imageLoad
+// returns) and carry weight 0. Coordinates in the arithmetic are GLOBAL atlas coordinates
+// because fp32 rounding of (coord + 0.5 + displacement) depends on their magnitude.
+// =====================================================================================
+static constexpr int PP_THREADS = 256;
+
+struct PullSample { float depth, maxDepth, radius; float2 disp; };
+
+// pull.comp:67-123 given the four decoded inputs (absolute input coords ix0.., output coord ox,oy)
+__device__ __forceinline__ float4 pull_combine(const PullSample* smp, int ix0, int iy0, int ox, int oy, int level) {
+    const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};   // pull.comp:24
+    float depthSamples[4], maxDepths[4], radiuses[4];
+    float2 dv[4];
+    bool valid[4];
+    const float scale = __int_as_float((127 - level) << 23);     // 2^-level, exact
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float ndx = (float(ix0 + offx[i]) + 0.5f + smp[i].disp.x) / 2.0f - (float(ox) + 0.5f);   // :69
+        float ndy = (float(iy0 + offy[i]) + 0.5f + smp[i].disp.y) / 2.0f - (float(oy) + 0.5f);
+        float dist = sqrtf(ndx * ndx + ndy * ndy);                // :70
+        float scaledRadius = smp[i].radius * scale;               // :72
+        bool radiusCheckPassed = dist <= scaledRadius;            // :74
+        depthSamples[i] = smp[i].depth; maxDepths[i] = smp[i].maxDepth; radiuses[i] = smp[i].radius;
+        dv[i] = make_float2(ndx, ndy);
+        valid[i] = (smp[i].depth != 1.0f) && radiusCheckPassed;   // :80-81
+    }
+    float minimum = __int_as_float(0x7f800000);                   // :84
+    float maxDepth = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (!valid[i]) continue;
+        minimum = gmin(depthSamples[i], minimum);
+        if (minimum == depthSamples[i]) maxDepth = maxDepths[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (depthSamples[i] > maxDepth) valid[i] = false;         // :94-97
+    float depthAcc = 0.0f, radiusAcc = 0.0f, maxValidMaxDepth = 0.0f, dax = 0.0f, day = 0.0f;
+    uint32_t numValid = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                                 // :104-113
+        if (!valid[i]) continue;
+        depthAcc += depthSamples[i];
+        dax += dv[i].x; day += dv[i].y;
+        radiusAcc += radiuses[i];
+        maxValidMaxDepth = gmax(maxValidMaxDepth, maxDepths[i]);
+        numValid++;
+    }
+    if (numValid > 0) {                                           // :116-123
+        float nv = float(numValid);
+        return make_float4(depthAcc / nv, maxValidMaxDepth, radiusAcc / nv, __uint_as_float(pack_half2(dax / nv, day / nv)));
+    }
+    return make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// push.comp:44-165 for one thread T (absolute), tile-local bookkeeping by the caller.
+struct PushCoarse { float depth[4], maxDepth[4], radius[4]; float2 disp[4]; bool in_tile[4]; };
+
+__device__ __forceinline__ float4 push_pixel(const PushCoarse& c, int Tx, int Ty, int outputPixel, int px, int py, int level,
+                                             float4 origSample) {
+    const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 1, 0};    // push.comp:48
+    const int weightsX[4] = {9, 3, 1, 3};                         // :70
+    int weights[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) weights[i] = weightsX[(i - outputPixel + 4) & 3];
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (!c.in_tile[i]) weights[i] = 0;            // :77-86 (other ISM)
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (c.depth[i] == 1.0f) weights[i] = 0;       // :89-93
+    const float scale = __int_as_float((127 - level) << 23);
+    float2 dv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                                             // :96-110
+        float ctx = (float(Tx - 1 + offx[i]) + 0.5f) * 2.0f, cty = (float(Ty - 1 + offy[i]) + 0.5f) * 2.0f;
+        float ttx = float(px) + 0.5f, tty = float(py) + 0.5f;
+        dv[i] = make_float2((ctx - ttx) + c.disp[i].x * 2.0f, (cty - tty) + c.disp[i].y * 2.0f);
+        float dist = sqrtf(dv[i].x * dv[i].x + dv[i].y * dv[i].y);
+        float radius = c.radius[i] * scale;
+        if (dist > radius) weights[i] = 0;
+    }
+    float minimum = 9001.0f;                                                  // :113
+    float maxDepth = 0.0f;
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (weights[i] == 0) continue;
+        any = true;
+        minimum = gmin(c.depth[i], minimum);
+        if (minimum == c.depth[i]) maxDepth = c.maxDepth[i];
+    }
+    if (any) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (c.depth[i] > maxDepth) weights[i] = 0;   // :123-126
+    }
+    float depthAcc = 0.0f, radiusAcc = 0.0f, maxDepthAcc = 0.0f, dax = 0.0f, day = 0.0f;
+    int weightAcc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                                             // :135-141
+        float w = float(weights[i]);
+        depthAcc += c.depth[i] * w;
+        maxDepthAcc += c.maxDepth[i] * w;
+        radiusAcc += c.radius[i] * w;
+        dax += dv[i].x * w; day += dv[i].y * w;
+        weightAcc += weights[i];
+    }
+    const bool allSamplesInvalid = weightAcc <= 0;                            // :158
+    float4 result = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (!allSamplesInvalid) {                                                 // :144-147
+        float wa = float(weightAcc);
+        result = make_float4(depthAcc / wa, maxDepthAcc / wa, radiusAcc / wa, __uint_as_float(pack_half2(dax / wa, day / wa)));
+    }
+    const bool invalid = origSample.x == 1.0f;                                // :151
+    bool occluded = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) occluded = occluded || (weights[i] > 0 && origSample.x > c.maxDepth[i]);   // :153-156
+    if (allSamplesInvalid || (!invalid && !occluded)) result = origSample;    // :159-161
+    return result;
+}
+
+__global__ void __launch_bounds__(PP_THREADS) pullpush_kernel(const uint32_t* __restrict__ atlas, int S, float zFar, uint16_t* __restrict__ ism) {
+    __shared__ __align__(16) uint32_t L0[64 * 64];
+    __shared__ __align__(16) float4 PY[1024 + 256 + 64 + 16 + 4 + 1];
+    // float4 offset of pyramid level l (1..6) inside PY: sum_{k<l} 4^(6-k)
+    auto lvl_off = [](int l) { return (4096 - (4096 >> (2 * (l - 1)))) / 3; };
+    const int A = 64 * S;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const int gx0 = tile_x * 64, gy0 = tile_y * 64;
+    const int tid = threadIdx.x;
+
+    // ---- load the 64x64 R32UI tile: 1024 x uint4, coalesced 256 B rows ----
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int q = tid + k * PP_THREADS;          // uint4 index 0..1023
+        int row = q >> 4, c4 = q & 15;
+        uint4 v = *reinterpret_cast<const uint4*>(atlas + (size_t)(gy0 + row) * A + gx0 + c4 * 4);
+        *reinterpret_cast<uint4*>(&L0[row * 64 + c4 * 4]) = v;
+    }
+    __syncthreads();
+
+    // ---- pull level 1 (LEVEL_ZERO variant, pull.comp:37-41,55-65) ----
+    const float ismPixelSize = 64.0f;          // A / S  (ImperfectShadowmap.cpp:187-191)
+    for (int o = tid; o < 1024; o += PP_THREADS) {
+        int lx = o & 31, ly = o >> 5;
+        PullSample smp[4];
+        const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t u = L0[(ly * 2 + offy[i]) * 64 + lx * 2 + offx[i]];
+            float depthSample = float(u >> 8) / 16777216.0f;
+            float radius = float(u & 0xFFu) / 10.0f;
+            float maxDepth = depthSample + (radius * 2.0f) / zFar * 0.6f;      // :57
+            float distToCamera = depthSample * zFar;                           // :60
+            radius = radius / distToCamera / 3.14f * ismPixelSize;             // :61
+            radius *= 1.3f;                                                    // :63
+            radius = gmin(radius, 15.0f);                                      // :65
+            smp[i].depth = depthSample; smp[i].maxDepth = maxDepth; smp[i].radius = radius; smp[i].disp = make_float2(0.0f, 0.0f);
+        }
+        int ox = (gx0 >> 1) + lx, oy = (gy0 >> 1) + ly;
+        PY[lvl_off(1) + o] = pull_combine(smp, ox * 2, oy * 2, ox, oy, 1);
+    }
+    __syncthreads();
+    // ---- pull levels 2..6 ----
+#pragma unroll 1
+    for (int level = 2; level <= 6; level++) {
+        const int osz = 64 >> level, isz = osz * 2;
+        const float4* in = PY + lvl_off(level - 1);
+        for (int o = tid; o < osz * osz; o += PP_THREADS) {
+            int lx = o % osz, ly = o / osz;
+            PullSample smp[4];
+            const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float4 rd = in[(ly * 2 + offy[i]) * isz + lx * 2 + offx[i]];   // :43-47
+                smp[i].depth = rd.x; smp[i].maxDepth = rd.y; smp[i].radius = rd.z;
+                smp[i].disp = unpack_half2(__float_as_uint(rd.w));
+            }
+            int ox = (gx0 >> level) + lx, oy = (gy0 >> level) + ly;
+            PY[lvl_off(level) + o] = pull_combine(smp, ox * 2, oy * 2, ox, oy, level);
+        }
+        __syncthreads();
+    }
+    // ---- push levels 5..0 (in place: push[i] overwrites pull[i]; only the owning thread reads orig) ----
+#pragma unroll 1
+    for (int level = 5; level >= 0; level--) {
+        const int size = 64 >> level, csz = size >> 1;        // this level / coarser level, tile-local
+        const int nT = csz + 1;
+        const float4* coarse = PY + lvl_off(level + 1);
+        float4* same = (level >= 1) ? PY + lvl_off(level) : nullptr;
+        const int gxl = gx0 >> level, gyl = gy0 >> level;     // tile origin at this level
+        for (int it = tid; it < nT * nT; it += PP_THREADS) {
+            int tlx = it % nT, tly = it / nT;                 // local T
+            int Tx = (gxl >> 1) + tlx, Ty = (gyl >> 1) + tly; // absolute T (push.comp:46: coarserLowerLeft = T - 1)
+            PushCoarse c;
+            const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 1, 0};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {                     // :55-62
+                int cx = tlx - 1 + offx[i], cy = tly - 1 + offy[i];
+                bool in = cx >= 0 && cy >= 0 && cx < csz && cy < csz;
+                float4 cs = in ? coarse[cy * csz + cx] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                c.depth[i] = cs.x; c.maxDepth[i] = cs.y; c.radius[i] = cs.z;
+                c.disp[i] = unpack_half2(__float_as_uint(cs.w));
+                c.in_tile[i] = in;
+            }
+#pragma unroll
+            for (int op = 0; op < 4; op++) {
+                int plx = tlx * 2 - 1 + offx[op], ply = tly * 2 - 1 + offy[op];   // tile-local pixel (:67)
+                if (plx < 0 || ply < 0 || plx >= size || ply >= size) continue;   // belongs to a neighbouring ISM's CTA
+                int px = gxl + plx, py = gyl + ply;
+                float4 orig;
+                if (level == 0) orig = make_float4(float(L0[ply * 64 + plx] >> 8) / 16777216.0f, 0.0f, 0.0f, 0.0f);  // :19-27
+                else orig = same[ply * size + plx];
+                float4 res = push_pixel(c, Tx, Ty, op, px, py, level, orig);
+                if (level == 0) {                                                 // :29-41 R16 unorm
+                    float r = gclamp(res.x, 0.0f, 1.0f);
+                    L0[ply * 64 + plx] = __float2uint_rn(r * 65535.0f);
+                } else {
+                    same[ply * size + plx] = res;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- store the R16 tile: 64 rows x 128 B, coalesced uint4 ----
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int q = tid + k * PP_THREADS;          // 0..511, 8 texels each
+        int row = q >> 3, c8 = q & 7;
+        const uint32_t* src = &L0[row * 64 + c8 * 8];
+        uint4 v;
+        v.x = src[0] | (src[1] << 16); v.y = src[2] | (src[3] << 16); v.z = src[4] | (src[5] << 16); v.w = src[6] | (src[7] << 16);
+        *reinterpret_cast<uint4*>(ism + (size_t)(gy0 + row) * A + gx0 + c8 * 8) = v;
+    }
+}
+
+int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, cudaStream_t st) {
+    dim3 grid(S, S);
+    pullpush_kernel<<<grid, PP_THREADS, 0, st>>>(atlas, S, zFar, ism);
+    return 1;
+}
+
+// =====================================================================================
+// a6: clustering. slice = #{s in 1..15 : -z >= 2^((s+3)/sf)} (table form of clustering.comp:50)
+// =====================================================================================
+__device__ __forceinline__ int slice_of(float zView, const SliceTable& tab) {
+    float d = -zView;
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i <= 15; i++) if (d >= tab.b[i]) s = i;
+    return s;
+}
+
+__global__ void __launch_bounds__(256) cluster_mask_kernel(const float* __restrict__ depth, int W, int H, float projA, float projB,
+                                                           SliceTable tab, uint32_t* __restrict__ tile_masks) {
+    __shared__ uint32_t smask;
+    if (threadIdx.x == 0) smask = 0;
+    __syncthreads();
+    const int cx = blockIdx.x, cy = blockIdx.y;
+    uint32_t m = 0;
+    for (int p = threadIdx.x; p < 128 * 128; p += 256) {
+        int fx = cx * 128 + (p & 127), fy = cy * 128 + (p >> 7);
+        if (fx < W && fy < H) {                                   // clustering.comp:52
+            float z = linear_depth(depth[(size_t)fy * W + fx], projA, projB);   // :48
+            m |= 1u << slice_of(z, tab);                          // :50,54
+        }
+    }
+    m = __reduce_or_sync(FULL, m);
+    if ((threadIdx.x & 31) == 0) atomicOr(&smask, m);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_masks[cy * gridDim.x + cx] = smask;
+}
+
+// canonical compact ids: ascending (tileY, tileX, slice)  (Q5)
+__global__ void __launch_bounds__(SCAN_THREADS) cluster_compact_kernel(const uint32_t* __restrict__ tile_masks, int X, int Y,
+                                                                        uint32_t* __restrict__ compact_ids, uint16_t* __restrict__ light_list_ids,
+                                                                        uint32_t* __restrict__ num_used) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    const int nt = X * Y;
+    for (int base = 0; base < nt; base += SCAN_THREADS) {
+        int t = base + threadIdx.x;
+        uint32_t m = (t < nt) ? tile_masks[t] : 0u;
+        uint32_t e = carry + block_exclusive_scan(__popc(m), &total, ws);
+        if (t < nt) {
+            int cx = t % X, cy = t / X;
+#pragma unroll
+            for (int s = 0; s < 16; s++) {
+                uint16_t id = 0xFFFF;
+                if (m & (1u << s)) {
+                    compact_ids[e] = (uint32_t)cx | ((uint32_t)cy << 8) | ((uint32_t)s << 16);   // clustering.comp:83
+                    id = (uint16_t)e;
+                    e++;
+                }
+                light_list_ids[((size_t)s * Y + cy) * X + cx] = id;                                // :86
+            }
+        }
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *num_used = carry;
+}
+
+int launch_clustering(const float* depth, int W, int H, float projA, float projB, const SliceTable& tab, uint32_t* tile_masks,
+                      uint32_t* compact_ids, uint16_t* light_list_ids, uint32_t* num_used, cudaStream_t st) {
+    const int X = (W + 127) / 128, Y = (H + 127) / 128;
+    cluster_mask_kernel<<<dim3(X, Y), 256, 0, st>>>(depth, W, H, projA, projB, tab, tile_masks);
+    cluster_compact_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_masks, X, Y, compact_ids, light_list_ids, num_used);
+    return 2;
+}
+
+// =====================================================================================
+// a7 / a8 shared: one warp builds one (volume, class) sub-list. Lanes 0..7 unproject one
+// corner each (light_lists.comp:85-90), every lane then tests VPLs lane, lane+32, ... of the
+// class against the 8 corners; __ballot_sync + __popc give ascending, deterministic slots.
+// =====================================================================================
+__device__ __forceinline__ float3 unproject_corner(const Mat4& inv, float x, float y, float z) {
+    float4 v = mat4_mul_vec4(inv, x * 2.0f - 1.0f, y * 2.0f - 1.0f, z * 2.0f - 1.0f, 1.0f * 2.0f - 1.0f);
+    return f3(v.x / v.w, v.y / v.w, v.z / v.w);
+}
+
+__device__ __forceinline__ void build_sublist(float3 my_corner, const float4* __restrict__ packed_vpl, int L, int k,
+                                              uint16_t* __restrict__ sub) {
+    const int lane = threadIdx.x & 31;
+    float3 corners[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        corners[j].x = __shfl_sync(FULL, my_corner.x, j);
+        corners[j].y = __shfl_sync(FULL, my_corner.y, j);
+        corners[j].z = __shfl_sync(FULL, my_corner.z, j);
+    }
+    uint32_t counter = 1;                                          // light_lists.comp:99
+    for (int base = 0; base < L; base += 32) {
+        int t = base + lane;
+        bool found = false;
+        uint32_t vplID = (uint32_t)(k * L + t);                    // :104-106
+        if (t < L) {
+            float4 pv = packed_vpl[vplID];
+            float3 vp = f3(pv.x, pv.y, pv.z);
+            float3 vn = unpack3SN(pv.w);
+#pragma unroll
+            for (int j = 0; j < 8; j++) found = found || (dot3(sub3(corners[j], vp), vn) >= 0.0f);   // :109-114
+        }
+        unsigned bal = __ballot_sync(FULL, found);
+        if (found) sub[counter + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)vplID;                // :116-119
+        counter += __popc(bal);
+    }
+    if (lane == 0) sub[0] = (uint16_t)counter;                     // :124-125
+}
+
+__global__ void __launch_bounds__(128) light_lists_kernel(const float4* __restrict__ packed_vpl, int N, const uint32_t* __restrict__ compact_ids,
+                                                          const uint32_t* __restrict__ num_used, Mat4 inv_vp, float projA, float projB,
+                                                          int W, int H, SliceTable tab, int class_lo, int class_hi,
+                                                          uint16_t* __restrict__ lists) {
+    const int L = N / 16;
+    const int ncls = class_hi - class_lo;
+    const uint32_t pairs = num_used[0] * (uint32_t)ncls;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pair < pairs; pair += warps_total) {
+        const uint32_t id = pair / ncls;
+        const int k = class_lo + (int)(pair % ncls);
+        const uint32_t clusterID = compact_ids[id];
+        const uint32_t clusterX = clusterID & 0xFFu, clusterY = (clusterID >> 8) & 0xFFu, clusterZ = (clusterID >> 16) & 0xFFu;
+        // light_lists.comp:42-47 (Q4: slice 0 front = +nearPlane), :64-73
+        float zFront = (clusterZ == 0) ? 0.05f : -tab.b[clusterZ];
+        float zBack = -tab.b[clusterZ + 1];
+        float ndcL = float(clusterX) * 128.0f / float(W);
+        float ndcR = float(clusterX + 1) * 128.0f / float(W);
+        float ndcB = float(clusterY) * 128.0f / float(H);
+        float ndcT = float(clusterY + 1) * 128.0f / float(H);
+        float ndcFront = log_depth(zFront, projA, projB);
+        float ndcBack = log_depth(zBack, projA, projB);
+        // corners 0..7 (:76-83). Q4: corners 6,7 repeat 4,5 (ndcL, ndcT).
+        const int j = lane & 7;
+        float cx = (j == 2 || j == 3) ? ndcR : ndcL;
+        float cy = (j >= 4) ? ndcT : ndcB;
+        float cz = (j & 1) ? ndcBack : ndcFront;
+        float3 corner = unproject_corner(inv_vp, cx, cy, cz);
+        build_sublist(corner, packed_vpl, L, k, lists + ((size_t)id * 16 + k) * (L + 1));
+    }
+}
+
+int launch_light_lists(const float4* packed_vpl, int N, const uint32_t* compact_ids, const uint32_t* num_used, int max_clusters,
+                       const Mat4& inv_vp, float projA, float projB, int W, int H, const SliceTable& tab, int class_lo,
+                       int class_hi, uint16_t* lists, cudaStream_t st) {
+    (void)max_clusters;
+    light_lists_kernel<<<148 * 8, 128, 0, st>>>(packed_vpl, N, compact_ids, num_used, inv_vp, projA, projB, W, H, tab, class_lo,
+                                                class_hi, lists);
+    return 1;
+}
+
+// a8: one CTA per 64x64 tile: depth bounds -> 8 corners -> 16 class sub-lists (2 per warp)
+__global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict__ depth, int W, int H, const float4* __restrict__ packed_vpl,
+                                                         int N, Mat4 inv_vp, int class_lo, int class_hi, uint16_t* __restrict__ lists) {
+    __shared__ float smin[8], smax[8];
+    __shared__ float3 scorner[8];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
+    for (int p = threadIdx.x; p < kTile * kTile; p += 256) {
+        int x = bx * kTile + (p % kTile), y = by * kTile + (p / kTile);
+        if (x < W && y < H) {
+            float d = depth[(size_t)y * W + x];
+            dmin = fminf(dmin, d); dmax = fmaxf(dmax, d);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, o));
+        dmax = fmaxf(dmax, __shfl_xor_sync(FULL, dmax, o));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { smin[warp] = dmin; smax[warp] = dmax; }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float mn = smin[0], mx = smax[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) { mn = fminf(mn, smin[i]); mx = fmaxf(mx, smax[i]); }
+        const int j = threadIdx.x;
+        float ndcL = float(bx) * float(kTile) / float(W), ndcR = float(bx + 1) * float(kTile) / float(W);
+        float ndcB = float(by) * float(kTile) / float(H), ndcT = float(by + 1) * float(kTile) / float(H);
+        float cx = (j & 2) ? ndcR : ndcL;
+        float cy = (j & 4) ? ndcT : ndcB;
+        float cz = (j & 1) ? mx : mn;
+        scorner[j] = unproject_corner(inv_vp, cx, cy, cz);
+    }
+    __syncthreads();
+    const int L = N / 16;
+    const size_t tile = (size_t)by * gridDim.x + bx;
+    float3 corner = scorner[lane & 7];
+    for (int k = class_lo + warp; k < class_hi; k += 8)
+        build_sublist(corner, packed_vpl, L, k, lists + (tile * 16 + k) * (L + 1));
+}
+
+int launch_cull_tiled(const float* depth, int W, int H, const float4* packed_vpl, int N, const Mat4& inv_vp, int class_lo,
+                      int class_hi, uint16_t* lists, cudaStream_t st) {
+    dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile);
+    cull_tiled_kernel<<<grid, 256, 0, st>>>(depth, W, H, packed_vpl, N, inv_vp, class_lo, class_hi, lists);
+    return 1;
+}
+
+}  // namespace mlgi

@@ -1,0 +1,921 @@
+// oracle/oracle.cpp -- TEST INFRASTRUCTURE ONLY: CPU oracle for the GI frame pipeline.
+//
+// PARITY UNPINNED BY THE REFERENCE: karyon/many-lights-gi ships no tests, golden
+// vectors or fixtures, it is GLSL that needs a GL driver,
+// and neither glm nor any GLSL compiler exists in this image, so the reference itself
+// cannot be executed here. This file is a line-by-line restatement of the reference's
+// GLSL in C++ against oracle/glsl_compat.h; it is pinned by (i) the known-answer values
+// of SURVEY.md Appendix E (tests/test_oracle_kat.py) and (ii) structural invariants.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load this library. The product (libmlgi.so) never links or calls it.
+//
+// Reference files restated (paths relative to /root/reference):
+//   data/shaders/common/{floatpacking,reprojection,random}.glsl
+//   data/shaders/ism/{ism_utils.glsl,ism.tesc,ism.tese,ism.geom,ism.comp,pull.comp,push.comp}
+//   data/shaders/gi/{vpl_processor.comp,final_gathering.comp,gi_blur.frag}
+//   data/shaders/clustered_shading/{clustering.comp,light_lists.comp}
+//   source/mfs-painters/multiframepainter/{VPLProcessor,ImperfectShadowmap,ClusteredShading,GIStage}.cpp
+//
+// Documented deviations from the reference: Q2 (L+1 list slots),
+// Q3 (local size 64), Q5/Q6 (canonical orders), Q7 (slice clamped to 15), Q8 (zFar
+// parameterised), Q9 (no bucket cap), Q10 (depth clamped to 2^24-1), Q11 (dead code
+// dropped). The cluster slice is evaluated against a table of 2^((s+3)/sf) boundaries
+// instead of a per-pixel log2 so that CPU and GPU agree bit for bit (SURVEY.md section 7,
+// "hard parts"); orc_slice_log2() keeps the literal log2 formula for cross-checking.
+#include "glsl_compat.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <random>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace glsl;
+
+#define ORC_API extern "C" __attribute__((visibility("default")))
+
+// =====================================================================================
+// common/floatpacking.glsl
+// =====================================================================================
+// floatpacking.glsl:26-38
+static float pack3UNToFloat(vec3 channel) {
+    uint uValue;
+    uValue = f2u(channel.x * 1023.0f + 0.5f);
+    uValue |= f2u(channel.y * 1023.0f + 0.5f) << 10;
+    uValue |= f2u(channel.z * 1021.0f + 1.5f) << 20;
+    return uintBitsToFloat(uValue);
+}
+// floatpacking.glsl:40-44
+static float pack3SNToFloat(vec3 channel) {
+    vec3 channel2 = channel * 0.5f + 0.5f;
+    return pack3UNToFloat(channel2);
+}
+// floatpacking.glsl:46-60
+static vec3 unpack3UNFromFloat(float f) {
+    uint u = floatBitsToUint(f);
+    float a = float(u & 0x3FFu) / 1023.0f;
+    float b = float((u >> 10) & 0x3FFu) / 1023.0f;
+    float c = (float((u >> 20) & 0x3FFu) - 1.5f) / 1021.0f;
+    return vec3(a, b, c);
+}
+// floatpacking.glsl:62-66
+static vec3 unpack3SNFromFloat(float f) { return unpack3UNFromFloat(f) * 2.0f - 1.0f; }
+// floatpacking.glsl:10-13, 20-23
+static float pack4UNToFloat(vec4 c) { return uintBitsToFloat(packUnorm4x8(c)); }
+static vec4 unpack4UNFromFloat(float f) { return unpackUnorm4x8(floatBitsToUint(f)); }
+// floatpacking.glsl:68-76
+static float pack2FloatsToFloat(vec2 c) { return uintBitsToFloat(packHalf2x16(c)); }
+static vec2 unpack2FloatsFromFloat(float f) { return unpackHalf2x16(floatBitsToUint(f)); }
+
+// =====================================================================================
+// common/reprojection.glsl
+// =====================================================================================
+// reprojection.glsl:6-14
+static float linearDepth(float depthSample, const mat4& P) {
+    float z_b = depthSample;
+    float z_n = 2.0f * z_b - 1.0f;
+    float A = P[2][2];
+    float B = P[3][2];
+    float z_e = -B / (A + z_n);
+    return z_e;
+}
+// reprojection.glsl:16-24
+static float logDepth(float depthSample, const mat4& P) {
+    float A = P[2][2];
+    float B = P[3][2];
+    float z_n = (1.0f / depthSample * -B) - A;
+    float z_b = (z_n + 1.0f) / 2.0f;
+    return z_b;
+}
+
+// =====================================================================================
+// common/random.glsl
+// =====================================================================================
+// random.glsl:34-41
+static uint hash1(uint x) {
+    x += (x << 10u);
+    x ^= (x >> 6u);
+    x += (x << 3u);
+    x ^= (x >> 11u);
+    x += (x << 15u);
+    return x;
+}
+// random.glsl:45 (uvec3)
+static uint hash3(uint x, uint y, uint z) { return hash1(x ^ hash1(y) ^ hash1(z)); }
+// random.glsl:50-59
+static float floatConstruct(uint m) {
+    m &= 0x007FFFFFu;
+    m |= 0x3F800000u;
+    float f = uintBitsToFloat(m);
+    return f - 1.0f;
+}
+// random.glsl:65
+static float random3(vec3 v) { return floatConstruct(hash3(floatBitsToUint(v.x), floatBitsToUint(v.y), floatBitsToUint(v.z))); }
+
+// =====================================================================================
+// ism/ism_utils.glsl
+// =====================================================================================
+// ism_utils.glsl:5-13
+static mat3 lookAtRH(vec3 normalizedNormal) {
+    vec3 up = vec3(0.0f, 1.0f, 0.01f);
+    vec3 f = normalizedNormal;
+    vec3 s = normalize(cross(f, up));
+    vec3 u = cross(s, f);
+    return transpose(mat3(s, u, -f));
+}
+// ism_utils.glsl:15-40
+static vec3 paraboloid_project(vec3 positionRelativeToCamera, float distToCamera, vec3 vplNormal, float zFar,
+                               float ismIndex, int ismIndices1d, bool preserveSign) {
+    mat3 vplView = lookAtRH(vplNormal);
+    vec3 v = vplView * positionRelativeToCamera;
+    float signOfV = sign(v.z);
+    v = v / distToCamera;
+    v.z = 1.0f - v.z;
+    v.x = v.x / v.z;
+    v.y = v.y / v.z;
+    v.z = distToCamera / zFar;
+    if (preserveSign) v.z *= -signOfV;
+    v.x += 1.0f; v.y += 1.0f;
+    v.x /= 2.0f; v.y /= 2.0f;
+    float y = float(f2i(ismIndex / float(ismIndices1d)));
+    int ix = f2i(ismIndex - y * float(ismIndices1d));
+    v.x += float(ix); v.y += float(f2i(y));
+    v.x /= float(ismIndices1d); v.y /= float(ismIndices1d);
+    return v;
+}
+
+// next even power of two: int(pow(2, ceil(log2(ismCount)/2)))  (ism.comp:39, final_gathering.comp:46)
+static int ism_indices_1d(int ismCount) {
+    int l = 0;
+    while ((1 << l) < ismCount) l++;  // ceil(log2)
+    return 1 << ((l + 1) / 2);
+}
+ORC_API int orc_ism_indices_1d(int n) { return ism_indices_1d(n); }
+
+// =====================================================================================
+// cluster slice helpers (clustering.comp:22-24,50; light_lists.comp:40-47; final_gathering.comp:81-85)
+// =====================================================================================
+static const int numDepthSlices = 16;
+static const int numSlicesIntoFirstSlice = 3;
+
+// boundaries[s] = 2^((s+3)/sf), sf = 19/log2(zFar), s = 0..16 (double math, rounded to fp32 once)
+ORC_API void orc_slice_boundaries(float zFar, float* b17) {
+    double sf = double(numDepthSlices + numSlicesIntoFirstSlice) / std::log2((double)zFar);
+    for (int s = 0; s <= 16; s++) b17[s] = (float)std::exp2(double(s + numSlicesIntoFirstSlice) / sf);
+}
+// slice = int(max(log2(-z)*sf - 3, 0)) evaluated as #{s>=1 : -z >= B[s]}, clamped to 15 (Q7)
+static int slice_of(float zView, const float* B) {
+    float d = -zView;
+    int s = 0;
+    for (int i = 1; i <= 15; i++)
+        if (d >= B[i]) s = i;
+    return s;
+}
+// the literal formula (clustering.comp:50) for cross-checking the table form
+ORC_API int orc_slice_log2(float zView, float zFar) {
+    float scaleFactor = float(numDepthSlices + numSlicesIntoFirstSlice) / log2f(zFar);
+    return f2i(max(log2f(-zView) * scaleFactor - float(numSlicesIntoFirstSlice), 0.0f));
+}
+ORC_API int orc_slice_table(float zView, float zFar) {
+    float B[17];
+    orc_slice_boundaries(zFar, B);
+    return slice_of(zView, B);
+}
+ORC_API float orc_linear_depth(float d, const float* proj) { return linearDepth(d, mat4(proj)); }
+
+// =====================================================================================
+// known-answer hooks
+// =====================================================================================
+ORC_API uint32_t orc_hash(uint32_t x) { return hash1(x); }
+ORC_API float orc_random3(float x, float y, float z) { return random3(vec3(x, y, z)); }
+ORC_API uint32_t orc_pack3SN(float x, float y, float z) { return floatBitsToUint(pack3SNToFloat(vec3(x, y, z))); }
+ORC_API void orc_unpack3SN(uint32_t bits, float* out3) {
+    vec3 v = unpack3SNFromFloat(uintBitsToFloat(bits));
+    out3[0] = v.x; out3[1] = v.y; out3[2] = v.z;
+}
+ORC_API uint32_t orc_packUnorm4x8(float x, float y, float z, float w) { return packUnorm4x8(vec4(x, y, z, w)); }
+ORC_API uint32_t orc_packHalf2x16(float x, float y) { return packHalf2x16(vec2(x, y)); }
+ORC_API void orc_unpackHalf2x16(uint32_t p, float* out2) { vec2 v = unpackHalf2x16(p); out2[0] = v.x; out2[1] = v.y; }
+ORC_API void orc_mat4_inverse(const float* m, float* out) { inverse(mat4(m)).store(out); }
+ORC_API void orc_mat4_mul(const float* a, const float* b, float* out) { (mat4(a) * mat4(b)).store(out); }
+ORC_API void orc_paraboloid_project(const float* rel3, const float* n3, float zFar, float ismIndex, int S, int preserveSign, float* out3) {
+    vec3 rel(rel3[0], rel3[1], rel3[2]);
+    vec3 v = paraboloid_project(rel, length(rel), vec3(n3[0], n3[1], n3[2]), zFar, ismIndex, S, preserveSign != 0);
+    out3[0] = v.x; out3[1] = v.y; out3[2] = v.z;
+}
+// VPLProcessor.cpp:58-62 -- std::shuffle(iota(N), mt19937(1979982)) with this libstdc++
+ORC_API void orc_shuffle_table(int n, int32_t* out) {
+    std::vector<int> v(n);
+    std::iota(v.begin(), v.end(), 0);
+    std::mt19937 g(1979982);
+    std::shuffle(v.begin(), v.end(), g);
+    for (int i = 0; i < n; i++) out[i] = v[i];
+}
+ORC_API int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// =====================================================================================
+// a1: gi/vpl_processor.comp:41-72 + VPLProcessor.cpp:73-101
+//   rsm_diffuse: RGBA8 (r in byte 0), rsm_normal: RGB10_A2 (r in bits 0-9), rsm_depth: fp32
+//   vpl_out: N x 12 floats {pos, pad, nrm, pad, col, pad} (VPLProcessor.cpp:34-41)
+//   packed_out: N x 4 floats (pos, pack3SN(nrm))           (VPLProcessor.cpp:29-32)
+// =====================================================================================
+ORC_API void orc_vpl_process(const uint32_t* rsm_diffuse, const uint32_t* rsm_normal, const float* rsm_depth,
+                             int rsm_w, int rsm_h, int N, const float* light_view, const float* light_proj,
+                             float lightIntensity, int shuffleLights, const int32_t* shuffled,
+                             float* vpl_out, float* packed_out) {
+    // VPLProcessor.cpp:76-82,91
+    mat4 shadowBias(1.0f);
+    shadowBias[0] = vec4(0.5f, 0, 0, 0); shadowBias[1] = vec4(0, 0.5f, 0, 0);
+    shadowBias[2] = vec4(0, 0, 0.5f, 0); shadowBias[3] = vec4(0.5f, 0.5f, 0.5f, 1.0f);
+    mat4 biasedShadowTransform = (shadowBias * mat4(light_proj)) * mat4(light_view);
+    mat4 inv = inverse(biasedShadowTransform);
+
+    const uint rsmSamples1d = (uint)ceilf(sqrtf(float(N)));  // vpl_processor.comp:38
+    for (uint resultIndex = 0; resultIndex < (uint)N; resultIndex++) {
+        uint totalWorkCount = (uint)N;
+        uvec2 lightsOnAxis(rsmSamples1d, totalWorkCount / rsmSamples1d);                 // :46
+        uvec2 texCoords((resultIndex % lightsOnAxis.x) * (uint)rsm_w / lightsOnAxis.x,
+                        (resultIndex / lightsOnAxis.x) * (uint)rsm_h / lightsOnAxis.y);  // :50
+        vec2 texCoordsf(float(texCoords.x) / float(rsm_w), float(texCoords.y) / float(rsm_h));  // :51
+        size_t t = (size_t)texCoords.y * rsm_w + texCoords.x;
+        uint d8 = rsm_diffuse[t];
+        vec3 diffuse(float(d8 & 0xFFu) / 255.0f, float((d8 >> 8) & 0xFFu) / 255.0f, float((d8 >> 16) & 0xFFu) / 255.0f);
+        uint n10 = rsm_normal[t];
+        vec3 normal = vec3(float(n10 & 0x3FFu) / 1023.0f, float((n10 >> 10) & 0x3FFu) / 1023.0f,
+                           float((n10 >> 20) & 0x3FFu) / 1023.0f) * 2.0f - 1.0f;          // :54
+        float depth = rsm_depth[t];
+        vec4 worldcoords = inv * vec4(texCoordsf, depth, 1.0f);                          // :57
+        vec3 w = worldcoords.xyz() / worldcoords.w;                                      // :58
+        vec3 lightColor = diffuse * lightIntensity;                                      // :60
+        uint slot = resultIndex;
+        if (shuffleLights) slot = (uint)shuffled[resultIndex];                           // :62-63
+        float packedNormal = pack3SNToFloat(normal);                                     // :65
+        vec3 unpackedNormal = unpack3SNFromFloat(packedNormal);                          // :68
+        float* o = vpl_out + (size_t)slot * 12;
+        o[0] = w.x; o[1] = w.y; o[2] = w.z; o[3] = 0;
+        o[4] = unpackedNormal.x; o[5] = unpackedNormal.y; o[6] = unpackedNormal.z; o[7] = 0;
+        o[8] = lightColor.x; o[9] = lightColor.y; o[10] = lightColor.z; o[11] = 0;
+        float* p = packed_out + (size_t)slot * 4;
+        p[0] = w.x; p[1] = w.y; p[2] = w.z; p[3] = packedNormal;
+    }
+}
+
+// =====================================================================================
+// a2: ism.tesc:11-23, ism.tese:14-24, ism.geom:49-70 with the deterministic tessellator
+// defined in SURVEY.md Appendix A.2 (the GL fixed-function tessellator is not reproducible):
+//   n = ceil(clamp(max outer level, 1, 64)); uniform n^2 barycentric split;
+//   sub id k enumerates row j = 0..n-1, within a row i = 0..n-1-j: up(i,j) then down(i,j).
+// Grid point (i,j): tessCoord = ((n-i-j)/n, i/n, j/n).
+// prim_id[t] = gl_PrimitiveIDIn of triangle t (its index within its mesh's draw call).
+// Output (canonical order: triangle, then sub id): points P x 4 floats, bucket P x int32.
+// Returns the number of points; if points==nullptr only counts.
+// =====================================================================================
+static int tess_n(vec3 v0, vec3 v1, vec3 v2, float tessLevelFactor) {
+    float length0 = length(v1 - v2);  // ism.tesc:13-15
+    float length1 = length(v2 - v0);
+    float length2 = length(v0 - v1);
+    float o0 = length0 * tessLevelFactor, o1 = length1 * tessLevelFactor, o2 = length2 * tessLevelFactor;
+    float inner = max(max(o0, o1), o2);  // ism.tesc:20
+    float c = clamp(inner, 1.0f, 64.0f);
+    return f2i(ceilf(c));
+}
+ORC_API long long orc_ism_points(const float* verts, const float* normals, const uint32_t* indices, int ntri,
+                                 const uint32_t* prim_id, float tessLevelFactor, int N,
+                                 float* points, int32_t* bucket, long long capacity) {
+    long long count = 0;
+    for (int t = 0; t < ntri; t++) {
+        uint i0 = indices[3 * t], i1 = indices[3 * t + 1], i2 = indices[3 * t + 2];
+        vec3 v0(verts[3 * i0], verts[3 * i0 + 1], verts[3 * i0 + 2]);
+        vec3 v1(verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]);
+        vec3 v2(verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]);
+        vec3 te_normal(normals[3 * i0], normals[3 * i0 + 1], normals[3 * i0 + 2]);  // ism.tese:22 (vertex 0's normal)
+        int n = tess_n(v0, v1, v2, tessLevelFactor);
+        if (!points) { count += (long long)n * n; continue; }
+        float fn = float(n);
+        for (int j = 0; j < n; j++) {
+            for (int i = 0; i < n - j; i++) {
+                for (int down = 0; down < 2; down++) {
+                    if (down && i + j > n - 2) continue;
+                    int gi[3], gj[3];
+                    if (!down) { gi[0] = i; gj[0] = j; gi[1] = i + 1; gj[1] = j; gi[2] = i; gj[2] = j + 1; }
+                    else       { gi[0] = i + 1; gj[0] = j; gi[1] = i + 1; gj[1] = j + 1; gi[2] = i; gj[2] = j + 1; }
+                    vec3 tc[3], p[3];
+                    for (int k = 0; k < 3; k++) {
+                        tc[k] = vec3(float(n - gi[k] - gj[k]) / fn, float(gi[k]) / fn, float(gj[k]) / fn);
+                        p[k] = (vec3(tc[k].x) * v0 + vec3(tc[k].y) * v1) + vec3(tc[k].z) * v2;  // ism.tese:9-12
+                    }
+                    // ism.geom:51-56
+                    vec3 position = ((p[0] + p[1]) + p[2]) / 3.0f;
+                    vec3 barycentricCoord = ((tc[0] + tc[1]) + tc[2]) / 3.0f;
+                    float maxdist = max(max(length(position - p[0]), length(position - p[1])), length(position - p[2]));
+                    vec3 seed = barycentricCoord + float(prim_id[t] % 4096u) / 4096.0f;  // ism.geom:56
+                    int base = f2i(random3(seed) * float(N));                            // ism.geom:57
+                    if (base >= N) base = N - 1;  // random() < 1 so unreachable; guards fp32 product rounding up
+                    float pointWorldRadius = maxdist;
+                    pointWorldRadius *= sqrtf(float(N));                                 // ism.geom:63
+                    float normalRadius = pack4UNToFloat(vec4(te_normal * 0.5f + 0.5f, pointWorldRadius / 25.0f));  // :64
+                    if (count < capacity) {
+                        float* o = points + 4 * count;
+                        o[0] = position.x; o[1] = position.y; o[2] = position.z; o[3] = normalRadius;
+                        bucket[count] = base;
+                    }
+                    count++;
+                }
+            }
+        }
+    }
+    return count;
+}
+
+// =====================================================================================
+// a3: ism/ism.comp:54-139 (scaleISMs=false, pointsOnlyIntoScaledISMs=false)
+//   points are grouped by bucket: bucket b owns points[bucket_start[b] .. bucket_start[b+1])
+//   atlas: A x A uint32, A = 64*S, must be pre-cleared to 0xFFFFFFFF by the caller or clear=1
+// =====================================================================================
+ORC_API void orc_ism_splat(const float* points, const uint32_t* bucket_start, const float* packed_vpl, int N,
+                           float zFar, uint32_t* atlas, int clear) {
+    const int S = ism_indices_1d(N);
+    const int A = 64 * S;
+    if (clear) std::fill(atlas, atlas + (size_t)A * A, 0xFFFFFFFFu);  // ImperfectShadowmap.cpp:212
+    const int maxVplTestCount = 16, maxVplCollectCount = 4;            // ism.comp:44,49
+    // serial over buckets: min is order independent, but keep it simple and race free
+    for (int b = 0; b < N; b++) {
+        vec4 vpls[16]; int vplIDs[16];
+        for (int t = 0; t < maxVplTestCount; t++) {                    // ism.comp:60-69
+            int index = (b + t) % N;
+            vplIDs[t] = index;
+            const float* p = packed_vpl + 4 * (size_t)index;
+            vpls[t] = vec4(p[0], p[1], p[2], p[3]);
+        }
+        for (uint pid = bucket_start[b]; pid < bucket_start[b + 1]; pid++) {
+            const float* r = points + 4 * (size_t)pid;
+            vec3 position(r[0], r[1], r[2]);
+            vec4 nr = unpack4UNFromFloat(r[3]);                        // ism.comp:85
+            vec3 pointNormal = vec3(nr.x, nr.y, nr.z) * 2.0f - 1.0f;   // :86
+            float pointRadius = nr.w * 25.0f;                          // :87
+            int used[4]; int found = 0;
+            for (int i = 0; i < maxVplTestCount; i++) {                // :94-107
+                vec3 vplPosition = vpls[i].xyz();
+                vec3 vplNormal2 = unpack3SNFromFloat(vpls[i].w);
+                vec3 rel = position - vplPosition;
+                bool cull = dot(vplNormal2, rel) < 0.0f || dot(pointNormal, -rel) < 0.0f;
+                if (!cull && found < maxVplCollectCount) used[found++] = i;
+            }
+            for (int i = 0; i < found; i++) {                          // :112-137
+                int localVplID = used[i];
+                int globalVplID = vplIDs[localVplID];
+                vec3 vplPosition = vpls[localVplID].xyz();
+                vec3 vplNormal2 = unpack3SNFromFloat(vpls[localVplID].w);
+                vec3 rel = position - vplPosition;
+                float distToCamera = length(rel);
+                float ismIndex = float(globalVplID);
+                vec3 v = paraboloid_project(rel, distToCamera, vplNormal2, zFar, ismIndex, S, true);
+                v.x *= float(A); v.y *= float(A);                      // :131
+                v.z *= 16777216.0f;                                    // :132
+                uint depth24 = f2u(v.z);
+                if (depth24 > 0xFFFFFFu) depth24 = 0xFFFFFFu;          // Q10
+                uint currentDepthValue = depth24 << 8;
+                currentDepthValue |= f2u(pointRadius * 10.0f / 2.0f) & 0xFFu;  // :135, sqrt(float(4)) = 2
+                int tx = f2i(v.x), ty = f2i(v.y);                      // ivec2(v.xy)
+                if (tx < 0 || ty < 0 || tx >= A || ty >= A) continue;  // out-of-bounds image access: no-op
+                uint32_t& dst = atlas[(size_t)ty * A + tx];
+                if (currentDepthValue < dst) dst = currentDepthValue;  // imageAtomicMin
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// a4+a5: ism/pull.comp:20-126 x6 and ism/push.comp:44-165 x6, pass order of
+// ImperfectShadowmap.cpp:121-182. Full-atlas passes over RGBA32F mips, exactly like the
+// reference (the CUDA kernel instead runs one 64x64 ISM per CTA in shared memory; bit-exact
+// agreement between the two is the test of the per-ISM independence argument).
+//   optional dumps: pull_dump / push_dump = arrays of 7 pointers (index = level), may be null.
+// =====================================================================================
+struct Img4 {
+    int size;
+    std::vector<vec4> px;
+    vec4 load(int x, int y) const {
+        if (x < 0 || y < 0 || x >= size || y >= size) return vec4(0.0f);  // OOB imageLoad returns 0
+        return px[(size_t)y * size + x];
+    }
+};
+
+static void pull_pass(int level, const uint32_t* atlas, int A, const Img4* in, Img4& out, float zFar, int ismPixelSize) {
+    const int osz = A >> level;
+    out.size = osz;
+    out.px.resize((size_t)osz * osz);
+    const bool LEVEL_ZERO = (level == 1);  // ImperfectShadowmap.cpp:138
+    const ivec2 offsets[4] = { {0, 0}, {0, 1}, {1, 0}, {1, 1} };  // pull.comp:24
+#pragma omp parallel for schedule(static)
+    for (int oy = 0; oy < osz; oy++) {
+        for (int ox = 0; ox < osz; ox++) {
+            float depthSamples[4], maxDepths[4], radiuses[4];
+            vec2 displacementVectors[4];
+            bool valid[4];
+            for (int i = 0; i < 4; i++) {
+                ivec2 inputPixelCoord(ox * 2 + offsets[i].x, oy * 2 + offsets[i].y);
+                float depthSample, radius, maxDepth;
+                vec2 displacementVector;
+                if (LEVEL_ZERO) {
+                    uint depthRadiusSample = atlas[(size_t)inputPixelCoord.y * A + inputPixelCoord.x];  // :37
+                    depthSample = float(depthRadiusSample >> 8) / 16777216.0f;                        // :38
+                    radius = float(depthRadiusSample & 0xFFu) / 10.0f;                                 // :39
+                    displacementVector = vec2(0.0f);
+                    float magicFactor = 0.6f;                                                          // :55
+                    maxDepth = depthSample + (radius * 2.0f) / zFar * magicFactor;                     // :57
+                    float distToCamera = depthSample * zFar;                                           // :60
+                    radius = radius / distToCamera / 3.14f * float(ismPixelSize);                      // :61
+                    radius *= 1.3f;                                                                    // :63
+                    radius = min(radius, 15.0f);                                                       // :65
+                } else {
+                    vec4 read = in->load(inputPixelCoord.x, inputPixelCoord.y);                        // :43-47
+                    depthSample = read.x; maxDepth = read.y;
+                    displacementVector = unpack2FloatsFromFloat(read.w);
+                    radius = read.z;
+                }
+                // pull.comp:69-74
+                vec2 newDisplacementVector((float(inputPixelCoord.x) + 0.5f + displacementVector.x) / 2.0f - (float(ox) + 0.5f),
+                                           (float(inputPixelCoord.y) + 0.5f + displacementVector.y) / 2.0f - (float(oy) + 0.5f));
+                float dist = length(newDisplacementVector);
+                float scaledRadius = radius * exp2i(-level);
+                bool radiusCheckPassed = dist <= scaledRadius;
+                depthSamples[i] = depthSample; maxDepths[i] = maxDepth; radiuses[i] = radius;
+                displacementVectors[i] = newDisplacementVector;
+                valid[i] = depthSample != 1.0f;                        // :80
+                valid[i] = valid[i] && radiusCheckPassed;              // :81
+            }
+            float minimum = INFINITY;                                  // :84
+            float maxDepth = 0.0f;                                     // undefined in GLSL; irrelevant when nothing valid
+            for (int i = 0; i < 4; i++) {
+                if (!valid[i]) continue;
+                minimum = min(depthSamples[i], minimum);
+                if (minimum == depthSamples[i]) maxDepth = maxDepths[i];
+            }
+            for (int i = 0; i < 4; i++)
+                if (depthSamples[i] > maxDepth) valid[i] = false;      // :94-97
+            float depthAcc = 0.0f, radiusAcc = 0.0f, maxValidMaxDepth = 0.0f;
+            vec2 displacementAcc(0.0f);
+            uint numValid = 0;
+            for (int i = 0; i < 4; i++) {                              // :104-113
+                if (!valid[i]) continue;
+                depthAcc += depthSamples[i];
+                displacementAcc = displacementAcc + displacementVectors[i];
+                radiusAcc += radiuses[i];
+                maxValidMaxDepth = max(maxValidMaxDepth, maxDepths[i]);
+                numValid++;
+            }
+            vec4 result;
+            if (numValid > 0) {                                        // :116-123
+                result.x = depthAcc / float(numValid);
+                result.y = maxValidMaxDepth;
+                result.z = radiusAcc / float(numValid);
+                result.w = pack2FloatsToFloat(displacementAcc / float(numValid));
+            } else {
+                result = vec4(1.0f, 0.0f, 0.0f, 0.0f);
+            }
+            out.px[(size_t)oy * osz + ox] = result;
+        }
+    }
+}
+
+static void push_pass(int level, const uint32_t* atlas, int A, const Img4* same, const Img4& coarse, Img4* out, uint16_t* out_last) {
+    const int size = A >> level;
+    const bool LEVEL_ZERO = (level == 0);
+    if (out) { out->size = size; out->px.assign((size_t)size * size, vec4(0.0f)); }
+    const ivec2 offsets[4] = { {0, 0}, {0, 1}, {1, 1}, {1, 0} };  // push.comp:48
+    const int nT = size / 2 + 1;  // threads with at least one in-bounds output pixel (ImperfectShadowmap.cpp:170-175)
+#pragma omp parallel for schedule(static)
+    for (int Ty = 0; Ty < nT; Ty++) {
+        for (int Tx = 0; Tx < nT; Tx++) {
+            ivec2 coarserLowerLeftPixel(Tx - 1, Ty - 1);               // :46
+            float depths[4], maxDepths[4], radiuses[4];
+            vec2 displacementVectorsCoarse[4];
+            for (int i = 0; i < 4; i++) {                              // :55-62
+                vec4 c = coarse.load(coarserLowerLeftPixel.x + offsets[i].x, coarserLowerLeftPixel.y + offsets[i].y);
+                depths[i] = c.x; maxDepths[i] = c.y; radiuses[i] = c.z;
+                displacementVectorsCoarse[i] = unpack2FloatsFromFloat(c.w);
+            }
+            for (int outputPixel = 0; outputPixel < 4; outputPixel++) {
+                ivec2 pixelCoordinate(Tx * 2 - 1 + offsets[outputPixel].x, Ty * 2 - 1 + offsets[outputPixel].y);  // :67
+                if (pixelCoordinate.x < 0 || pixelCoordinate.y < 0 || pixelCoordinate.x >= size || pixelCoordinate.y >= size)
+                    continue;  // out-of-bounds imageStore is dropped; nothing else observes this iteration
+                const int weightsX[4] = { 9, 3, 1, 3 };                // :70
+                int weights[4];
+                for (int i = 0; i < 4; i++) weights[i] = weightsX[(i - outputPixel + 4) % 4];
+                ivec2 origTexCoord(pixelCoordinate.x / 2, pixelCoordinate.y / 2);  // :78
+                const int sh = 6 - (level + 1);
+                for (int i = 0; i < 4; i++) {                          // :79-86
+                    ivec2 inputPixelCoords(coarserLowerLeftPixel.x + offsets[i].x, coarserLowerLeftPixel.y + offsets[i].y);
+                    if ((origTexCoord.x >> sh) != (inputPixelCoords.x >> sh) || (origTexCoord.y >> sh) != (inputPixelCoords.y >> sh))
+                        weights[i] = 0;
+                }
+                for (int i = 0; i < 4; i++)                            // :89-93
+                    if (depths[i] == 1.0f) weights[i] = 0;
+                vec2 displacementVectors[4];
+                for (int i = 0; i < 4; i++) {                          // :96-110
+                    vec2 coarserTexCoord((float(coarserLowerLeftPixel.x + offsets[i].x) + 0.5f) * 2.0f,
+                                         (float(coarserLowerLeftPixel.y + offsets[i].y) + 0.5f) * 2.0f);
+                    vec2 thisTexCoord(float(pixelCoordinate.x) + 0.5f, float(pixelCoordinate.y) + 0.5f);
+                    displacementVectors[i] = (coarserTexCoord - thisTexCoord) + displacementVectorsCoarse[i] * 2.0f;
+                    float dist = length(displacementVectors[i]);
+                    float radius = radiuses[i];
+                    radius *= exp2i(-level);
+                    if (dist > radius) weights[i] = 0;
+                }
+                float minimum = 9001.0f;                               // :113
+                float maxDepth = 0.0f;
+                for (int i = 0; i < 4; i++) {
+                    if (weights[i] == 0) continue;
+                    minimum = min(depths[i], minimum);
+                    if (minimum == depths[i]) maxDepth = maxDepths[i];
+                }
+                bool any = false;
+                for (int i = 0; i < 4; i++) any = any || weights[i] != 0;
+                if (any)
+                    for (int i = 0; i < 4; i++)                        // :123-126 (maxDepth undefined when !any; weights already 0)
+                        if (depths[i] > maxDepth) weights[i] = 0;
+                float depthAcc = 0.0f, radiusAcc = 0.0f, maxDepthAcc = 0.0f;
+                vec2 displacementAcc(0.0f);
+                int weightAcc = 0;
+                for (int i = 0; i < 4; i++) {                          // :135-141
+                    depthAcc += depths[i] * float(weights[i]);
+                    maxDepthAcc += maxDepths[i] * float(weights[i]);
+                    radiusAcc += radiuses[i] * float(weights[i]);
+                    displacementAcc = displacementAcc + displacementVectors[i] * float(weights[i]);
+                    weightAcc += weights[i];
+                }
+                vec4 result(0.0f);
+                vec4 origSample;
+                if (LEVEL_ZERO) {                                      // :19-27
+                    float depthSample = float(atlas[(size_t)pixelCoordinate.y * A + pixelCoordinate.x] >> 8) / 16777216.0f;
+                    origSample = vec4(depthSample, 0.0f, 0.0f, 0.0f);
+                } else {
+                    origSample = same->load(pixelCoordinate.x, pixelCoordinate.y);
+                }
+                bool allSamplesInvalid = weightAcc <= 0;               // :158
+                if (!allSamplesInvalid) {
+                    result.x = depthAcc / float(weightAcc);            // :144-147
+                    result.y = maxDepthAcc / float(weightAcc);
+                    result.z = radiusAcc / float(weightAcc);
+                    result.w = pack2FloatsToFloat(displacementAcc / float(weightAcc));
+                }
+                bool invalid = origSample.x == 1.0f;                   // :151
+                bool occluded = false;
+                for (int i = 0; i < 4; i++)
+                    occluded = occluded || (weights[i] > 0 && origSample.x > maxDepths[i]);  // :153-156
+                if (allSamplesInvalid || (!invalid && !occluded)) result = origSample;       // :159-161
+                if (LEVEL_ZERO) {                                      // :29-41, R16 unorm store
+                    float r = clamp(result.x, 0.0f, 1.0f);
+                    out_last[(size_t)pixelCoordinate.y * size + pixelCoordinate.x] = (uint16_t)rintf(r * 65535.0f);
+                } else {
+                    out->px[(size_t)pixelCoordinate.y * size + pixelCoordinate.x] = result;
+                }
+            }
+        }
+    }
+}
+
+ORC_API void orc_ism_pullpush(const uint32_t* atlas, int N, float zFar, uint16_t* result_r16,
+                              float** pull_dump, float** push_dump) {
+    const int S = ism_indices_1d(N);
+    const int A = 64 * S;
+    const int ismPixelSize = A / S;  // ImperfectShadowmap.cpp:187-191
+    Img4 pull[7], push[7];
+    for (int i = 1; i <= 6; i++)     // ImperfectShadowmap.cpp:128-150
+        pull_pass(i, atlas, A, i == 1 ? nullptr : &pull[i - 1], pull[i], zFar, ismPixelSize);
+    for (int i = 5; i >= 0; i--) {   // ImperfectShadowmap.cpp:155-181
+        const Img4& coarse = (i == 5) ? pull[6] : push[i + 1];
+        push_pass(i, atlas, A, i == 0 ? nullptr : &pull[i], coarse, i == 0 ? nullptr : &push[i], result_r16);
+    }
+    for (int i = 1; i <= 6; i++) {
+        if (pull_dump && pull_dump[i]) memcpy(pull_dump[i], pull[i].px.data(), pull[i].px.size() * sizeof(vec4));
+        if (push_dump && i <= 5 && push_dump[i]) memcpy(push_dump[i], push[i].px.data(), push[i].px.size() * sizeof(vec4));
+    }
+}
+
+// =====================================================================================
+// a6: clustered_shading/clustering.comp:30-88 + ClusteredShading.cpp:82-94,115-127
+//   canonical compact ids: ascending (tileY, tileX, slice)   (Q5)
+//   light_list_ids: [16][Y][X] uint16 (GL 3D texture x-fastest), 0xFFFF = unused
+//   returns numUsedClusters
+// =====================================================================================
+ORC_API int orc_clustering(const float* depth, int W, int H, const float* proj, float zFar,
+                           uint32_t* compact_ids, uint16_t* light_list_ids) {
+    const int X = (W + 127) / 128, Y = (H + 127) / 128;
+    mat4 P(proj);
+    float B[17];
+    orc_slice_boundaries(zFar, B);
+    std::vector<uint32_t> masks((size_t)X * Y, 0);
+#pragma omp parallel for schedule(dynamic)
+    for (int t = 0; t < X * Y; t++) {
+        int cx = t % X, cy = t / X;
+        uint32_t m = 0;
+        for (int i = 0; i < 128; i++)
+            for (int lx = 0; lx < 128; lx++) {
+                int fx = cx * 128 + lx, fy = cy * 128 + i;
+                if (fx >= W || fy >= H) continue;                      // inImageBounds, clustering.comp:52
+                float z = linearDepth(depth[(size_t)fy * W + fx], P);  // :48
+                m |= 1u << slice_of(z, B);                             // :50,54
+            }
+        masks[t] = m;
+    }
+    std::fill(light_list_ids, light_list_ids + (size_t)X * Y * 16, (uint16_t)0xFFFF);
+    int n = 0;
+    for (int cy = 0; cy < Y; cy++)
+        for (int cx = 0; cx < X; cx++)
+            for (int s = 0; s < 16; s++)
+                if (masks[(size_t)cy * X + cx] & (1u << s)) {
+                    compact_ids[n] = (uint)cx | ((uint)cy << 8) | ((uint)s << 16);  // :83
+                    light_list_ids[((size_t)s * Y + cy) * X + cx] = (uint16_t)n;     // :86
+                    n++;
+                }
+    return n;
+}
+
+// =====================================================================================
+// a7: clustered_shading/light_lists.comp:50-126 + ClusteredShading.cpp:96-111
+//   lists: [numUsed][16][L+1] uint16, L = N/16; slot 0 = 1 + count, then ascending ids (Q2, Q6)
+// =====================================================================================
+static float sliceToZ(uint slice, const float* B) {  // light_lists.comp:42-47 (Q4: +nearPlane)
+    const float nearPlane = 0.05f;
+    if (slice == 0) return nearPlane;
+    return -B[slice];
+}
+ORC_API void orc_light_lists(const float* packed_vpl, int N, const uint32_t* compact_ids, int numUsed,
+                             const float* view, const float* proj, int W, int H, float zFar, uint16_t* lists) {
+    mat4 P(proj), V(view);
+    mat4 viewProjectionInverseMatrix = inverse(P * V);  // ClusteredShading.cpp:105
+    float B[17];
+    orc_slice_boundaries(zFar, B);
+    const int L = N / 16;
+    const float pixelsPerCluster = 128.0f;
+#pragma omp parallel for schedule(dynamic)
+    for (int id = 0; id < numUsed; id++) {
+        uint clusterID = compact_ids[id];
+        uint clusterX = clusterID & 0xFFu, clusterY = (clusterID >> 8) & 0xFFu, clusterZ = (clusterID >> 16) & 0xFFu;
+        float viewSpaceZFront = sliceToZ(clusterZ, B);       // :64-65
+        float viewSpaceZBack = sliceToZ(clusterZ + 1, B);
+        float ndcL = float(clusterX) * pixelsPerCluster / float(W);        // :67-70
+        float ndcR = float(clusterX + 1) * pixelsPerCluster / float(W);
+        float ndcB = float(clusterY) * pixelsPerCluster / float(H);
+        float ndcT = float(clusterY + 1) * pixelsPerCluster / float(H);
+        float ndcFront = logDepth(viewSpaceZFront, P);                     // :72-73
+        float ndcBack = logDepth(viewSpaceZBack, P);
+        (void)ndcR;
+        vec3 corners[8];
+        corners[0] = vec3(ndcL, ndcB, ndcFront); corners[1] = vec3(ndcL, ndcB, ndcBack);
+        corners[2] = vec3(ndcR, ndcB, ndcFront); corners[3] = vec3(ndcR, ndcB, ndcBack);
+        corners[4] = vec3(ndcL, ndcT, ndcFront); corners[5] = vec3(ndcL, ndcT, ndcBack);
+        corners[6] = vec3(ndcL, ndcT, ndcFront); corners[7] = vec3(ndcL, ndcT, ndcBack);  // :82-83 (Q4: L, not R)
+        for (int i = 0; i < 8; i++) {                                      // :85-90
+            vec4 v(corners[i], 1.0f);
+            v = v * 2.0f - 1.0f;
+            v = viewProjectionInverseMatrix * v;
+            corners[i] = v.xyz() / v.w;
+        }
+        for (int k = 0; k < 16; k++) {
+            uint16_t* sub = lists + ((size_t)id * 16 + k) * (L + 1);
+            uint counter = 1;                                              // :99
+            for (int t = 0; t < L; t++) {
+                uint vplID = (uint)(k * L + t);                            // :104-106
+                const float* pv = packed_vpl + 4 * (size_t)vplID;
+                vec3 vp(pv[0], pv[1], pv[2]);
+                vec3 vplNormal = unpack3SNFromFloat(pv[3]);
+                bool found = false;
+                for (int j = 0; j < 8; j++) {                              // :109-114
+                    vec3 vplToCorner = corners[j] - vp;
+                    found = found || (dot(vplToCorner, vplNormal) >= 0.0f);
+                }
+                if (found) sub[counter++] = (uint16_t)vplID;               // :116-119
+            }
+            sub[0] = (uint16_t)counter;                                    // :124-125
+        }
+    }
+}
+
+// =====================================================================================
+// a8: tiled variant (not in the reference snapshot; spec = SURVEY.md Appendix A.8)
+//   block = tile x tile px (the product uses 64: one gathering CTA = one class of one 64x64
+//   tile); bounds = block rect x [min,max] window depth over in-image pixels;
+//   8 proper corners; same hemisphere test; lists [BY*BX][16][L+1], slot0 = 1+count.
+// =====================================================================================
+ORC_API void orc_cull_tiled(const float* depth, int W, int H, const float* packed_vpl, int N,
+                            const float* view, const float* proj, int tile, uint16_t* lists) {
+    mat4 P(proj), V(view);
+    mat4 inv = inverse(P * V);
+    const int BX = (W + tile - 1) / tile, BY = (H + tile - 1) / tile;
+    const float ftile = float(tile);
+    const int L = N / 16;
+#pragma omp parallel for schedule(dynamic)
+    for (int b = 0; b < BX * BY; b++) {
+        int bx = b % BX, by = b / BX;
+        float dmin = INFINITY, dmax = -INFINITY;
+        for (int y = by * tile; y < by * tile + tile && y < H; y++)
+            for (int x = bx * tile; x < bx * tile + tile && x < W; x++) {
+                float d = depth[(size_t)y * W + x];
+                dmin = min(dmin, d); dmax = max(dmax, d);
+            }
+        float ndcL = float(bx) * ftile / float(W), ndcR = float(bx + 1) * ftile / float(W);
+        float ndcB = float(by) * ftile / float(H), ndcT = float(by + 1) * ftile / float(H);
+        vec3 corners[8] = { vec3(ndcL, ndcB, dmin), vec3(ndcL, ndcB, dmax), vec3(ndcR, ndcB, dmin), vec3(ndcR, ndcB, dmax),
+                            vec3(ndcL, ndcT, dmin), vec3(ndcL, ndcT, dmax), vec3(ndcR, ndcT, dmin), vec3(ndcR, ndcT, dmax) };
+        for (int i = 0; i < 8; i++) {
+            vec4 v(corners[i], 1.0f);
+            v = v * 2.0f - 1.0f;
+            v = inv * v;
+            corners[i] = v.xyz() / v.w;
+        }
+        for (int k = 0; k < 16; k++) {
+            uint16_t* sub = lists + ((size_t)b * 16 + k) * (L + 1);
+            uint counter = 1;
+            for (int t = 0; t < L; t++) {
+                uint vplID = (uint)(k * L + t);
+                const float* pv = packed_vpl + 4 * (size_t)vplID;
+                vec3 vp(pv[0], pv[1], pv[2]);
+                vec3 vplNormal = unpack3SNFromFloat(pv[3]);
+                bool found = false;
+                for (int j = 0; j < 8; j++) found = found || (dot(corners[j] - vp, vplNormal) >= 0.0f);
+                if (found) sub[counter++] = (uint16_t)vplID;
+            }
+            sub[0] = (uint16_t)counter;
+        }
+    }
+}
+
+// =====================================================================================
+// a9: gi/final_gathering.comp:63-135 + GIStage.cpp:261-306
+//   cull_mode 0: clustered (light_list_ids [16][Y][X], lists [cluster][16][L+1])
+//   cull_mode 1: tiled     (lists [block][16][L+1], block = tile x tile px)
+//   cull_mode 2: none      (every VPL of the class, for plumbing tests)
+//   out_rgb: W*H*3 fp32 raster. out_lo/out_hi (optional): bounds of the result when the
+//   nearest-texel ISM fetch of a pair lies within tie_eps texels of a texel border (both
+//   neighbours considered); lets the GPU comparison be rigorous about the one discontinuous
+//   operation on this path. stats (optional, 2 x int64): pairs_listed, pairs_lit.
+// =====================================================================================
+ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, int W, int H,
+                              const float* vpl, int N, const uint16_t* ism_r16,
+                              int cull_mode, const uint16_t* light_list_ids, const uint16_t* lists,
+                              const float* view, const float* proj, float zFar,
+                              float giIntensityFactor, float vplClampingValue, int vplStartIndex, int vplEndIndex,
+                              int enableShadowing, int class_lo, int class_hi, int tile,
+                              float* out_rgb, float* out_lo, float* out_hi, float tie_eps, long long* stats) {
+    mat4 P(proj), V(view);
+    // GIStage.cpp:289: camera->viewInverted() * projection->projectionInverted()
+    mat4 viewProjectionInvertedMatrix = inverse(V) * inverse(P);
+    const int S = ism_indices_1d(N);  // final_gathering.comp:45-46 (SCALE_ISMS false)
+    const int A = 64 * S;
+    const int L = N / 16;
+    const int vplCount = vplEndIndex - vplStartIndex;  // :42
+    const int X = (W + 127) / 128, Y = (H + 127) / 128;
+    const int BX = (W + tile - 1) / tile;
+    float B[17];
+    orc_slice_boundaries(zFar, B);
+    long long listed = 0, lit = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : listed, lit)
+    for (int fy = 0; fy < H; fy++) {
+        for (int fx = 0; fx < W; fx++) {
+            // :65-68 -- the workgroup decomposition reduces to: class = (x&3, y&3)
+            uvec2 interleavedPixel((uint)fx & 3u, (uint)fy & 3u);
+            uint interleavedPixel1d = interleavedPixel.x + interleavedPixel.y * 4u;  // :91
+            float* o = out_rgb + 3 * ((size_t)fy * W + fx);
+            if ((int)interleavedPixel1d < class_lo || (int)interleavedPixel1d >= class_hi) continue;
+            vec2 v_uv(float(fx) / float(W), float(fy) / float(H));                   // :70
+            float depthSample = depth[(size_t)fy * W + fx];                          // :73
+            vec4 ndc = vec4(v_uv, depthSample, 1.0f) * 2.0f - 1.0f;                  // :74
+            vec4 fragWorldCoordWithW = viewProjectionInvertedMatrix * ndc;           // :75
+            vec3 fragWorldCoord = fragWorldCoordWithW.xyz() / fragWorldCoordWithW.w; // :76
+            uint n10 = face_normal[(size_t)fy * W + fx];
+            vec3 fragNormal = vec3(float(n10 & 0x3FFu) / 1023.0f, float((n10 >> 10) & 0x3FFu) / 1023.0f,
+                                   float((n10 >> 20) & 0x3FFu) / 1023.0f) * 2.0f - 1.0f;  // :79
+            const uint16_t* sub = nullptr;
+            if (cull_mode == 0) {
+                float dlin = linearDepth(depthSample, P);                            // :84
+                int clusterZ = slice_of(dlin, B);                                    // :85
+                uint cx = (uint)fx / 128u, cy = (uint)fy / 128u;                     // :88
+                uint lightListId = light_list_ids[((size_t)clusterZ * Y + cy) * X + cx];  // :89
+                sub = lists + ((size_t)lightListId * 16 + interleavedPixel1d) * (L + 1);
+            } else if (cull_mode == 1) {
+                size_t blk = (size_t)(fy / tile) * BX + (fx / tile);
+                sub = lists + (blk * 16 + interleavedPixel1d) * (L + 1);
+            }
+            uint startIndex = (uint)L * interleavedPixel1d;                          // :93
+            uint numLights = sub ? sub[0] : (uint)(L + 1);                           // :94
+            vec3 acc(0.0f), accLo(0.0f), accHi(0.0f);
+            for (uint lightIndex = 1; lightIndex < numLights; lightIndex++) {        // :97
+                uint vplIndex = sub ? sub[lightIndex] : startIndex + lightIndex - 1; // :98
+                const float* pv = vpl + 12 * (size_t)vplIndex;
+                vec3 vpos(pv[0], pv[1], pv[2]), vnrm(pv[4], pv[5], pv[6]), vcol(pv[8], pv[9], pv[10]);
+                listed++;
+                vec3 diff = fragWorldCoord - vpos;                                   // :102
+                float dist = length(diff);
+                vec3 normalizedDiff = diff / dist;                                   // :104
+                float angleFactor = max(0.0f, dot(vnrm, normalizedDiff)) * max(0.0f, dot(fragNormal, -normalizedDiff));  // :112
+                if (angleFactor <= 0.0f) continue;                                   // :113-114
+                lit++;
+                float d2 = dist * dist;
+                float attenuation = 1.0f / (d2 * d2);                                // :115 pow(dist, 4.0)
+                float geometryTerm = angleFactor * attenuation;
+                geometryTerm = min(geometryTerm, vplClampingValue);                  // :117
+                float gLo = geometryTerm, gHi = geometryTerm;
+                if (enableShadowing) {                                               // :119-127
+                    float ismIndex = float(vplIndex);
+                    vec3 v = paraboloid_project(diff, dist, vnrm, zFar, ismIndex, S, false);
+                    // textureLod(..., NEAREST, CLAMP_TO_EDGE): texel = floor(uv * size), clamped
+                    float sx = v.x * float(A), sy = v.y * float(A);
+                    int tx = (int)floorf(sx), ty = (int)floorf(sy);
+                    float sLo = INFINITY, sHi = -INFINITY, sMid = 0.0f;
+                    for (int dy = -1; dy <= 1; dy++)
+                        for (int dx = -1; dx <= 1; dx++) {
+                            if (dx == -1 && !(sx - float(tx) < tie_eps)) continue;
+                            if (dx == 1 && !(float(tx + 1) - sx < tie_eps)) continue;
+                            if (dy == -1 && !(sy - float(ty) < tie_eps)) continue;
+                            if (dy == 1 && !(float(ty + 1) - sy < tie_eps)) continue;
+                            int cx = glsl::min(glsl::max(tx + dx, 0), A - 1), cy = glsl::min(glsl::max(ty + dy, 0), A - 1);
+                            float occluderDepth = float(ism_r16[(size_t)cy * A + cx]) / 65535.0f;
+                            float shadowValue = v.z - occluderDepth;                 // :123
+                            float shadowBias = 0.02f;
+                            shadowValue = smoothstep(1.0f - shadowBias, 1.0f, 1.0f - shadowValue);  // :125
+                            if (dx == 0 && dy == 0) sMid = shadowValue;
+                            sLo = min(sLo, shadowValue); sHi = max(sHi, shadowValue);
+                        }
+                    gLo = geometryTerm * sLo; gHi = geometryTerm * sHi;
+                    geometryTerm *= sMid;                                            // :126
+                }
+                acc = acc + vcol * geometryTerm;                                     // :129
+                accLo = accLo + vcol * gLo; accHi = accHi + vcol * gHi;
+            }
+            // :132  vec3(acc * giIntensityFactor / vplCount) * interleavedPixels
+            vec3 resultColor = (acc * giIntensityFactor / float(vplCount)) * 16.0f;
+            o[0] = resultColor.x; o[1] = resultColor.y; o[2] = resultColor.z;
+            if (out_lo) {
+                vec3 r = (accLo * giIntensityFactor / float(vplCount)) * 16.0f;
+                float* q = out_lo + 3 * ((size_t)fy * W + fx); q[0] = r.x; q[1] = r.y; q[2] = r.z;
+            }
+            if (out_hi) {
+                vec3 r = (accHi * giIntensityFactor / float(vplCount)) * 16.0f;
+                float* q = out_hi + 3 * ((size_t)fy * W + fx); q[0] = r.x; q[1] = r.y; q[2] = r.z;
+            }
+        }
+    }
+    if (stats) { stats[0] = listed; stats[1] = lit; }
+}
+
+// =====================================================================================
+// n1 ("next" row): gi/gi_blur.frag:24-72, two passes (GIStage.cpp:308-344, :425-439)
+//   in/out: W*H*3 fp32. direction 0 = (1,0), 1 = (0,1). texelFetch outside the image is
+//   undefined in GL; here out-of-image taps are skipped (weight 0) -- documented choice.
+// =====================================================================================
+static float blur_weight(float r, float depthDiff, float normalDiff) {  // gi_blur.frag:24-35
+    const int KERNEL_RADIUS = 3;
+    float factor = (float(KERNEL_RADIUS) - r + 1.0f) / 4.0f;
+    float w = factor - depthDiff * depthDiff - normalDiff * normalDiff;
+    return max(0.0f, w);
+}
+ORC_API void orc_gi_blur_pass(const float* gi, const float* depth, const uint32_t* face_normal, int W, int H,
+                              const float* proj, int direction, float* out) {
+    mat4 P(proj);
+    const int dxs = direction == 0 ? 1 : 0, dys = direction == 0 ? 0 : 1;
+    auto normalAt = [&](int x, int y) {
+        uint n10 = face_normal[(size_t)y * W + x];
+        return vec3(float(n10 & 0x3FFu) / 1023.0f, float((n10 >> 10) & 0x3FFu) / 1023.0f, float((n10 >> 20) & 0x3FFu) / 1023.0f) * 2.0f - 1.0f;
+    };
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            vec3 acc(0.0f);
+            float factorAcc = 0.0f;
+            float d = linearDepth(depth[(size_t)y * W + x], P);  // :58 (v_uv at pixel centre -> same texel)
+            vec3 Nn = normalAt(x, y);                            // :59
+            const float* c = gi + 3 * ((size_t)y * W + x);
+            acc = acc + vec3(c[0], c[1], c[2]);                  // :60
+            factorAcc += 1.0f;
+            for (int sgn = -1; sgn <= 1; sgn += 2)               // :63-69 (negative direction first)
+                for (int i = 1; i <= 3; i++) {
+                    int tx = x + sgn * dxs * i, ty = y + sgn * dys * i;
+                    if (tx < 0 || ty < 0 || tx >= W || ty >= H) continue;
+                    const float* g = gi + 3 * ((size_t)ty * W + tx);
+                    vec3 normalSample = normalAt(tx, ty);
+                    float depthSample = linearDepth(depth[(size_t)ty * W + tx], P);
+                    float normalFactor = 1.0f - max(0.0f, dot(Nn, normalSample));  // :44
+                    float depthDiff = (depthSample - d) / 1.0f;
+                    float factor = blur_weight(float(i), depthDiff, normalFactor * 5.0f);
+                    factorAcc += factor;
+                    acc = acc + vec3(g[0], g[1], g[2]) * factor;
+                }
+            vec3 r = acc / factorAcc;                            // :71
+            float* o = out + 3 * ((size_t)y * W + x);
+            o[0] = r.x; o[1] = r.y; o[2] = r.z;
+        }
+}

@@ -1,0 +1,339 @@
+"""Parity tests proper: every stage of the CUDA path, called through the C ABI, against the
+CPU oracle on the same seeded inputs. Bit-exact for integer/byte outputs (atlas, ISM R16,
+cluster ids, light lists, packed normals, buckets); 1e-3 relative for radiance."""
+import numpy as np
+import pytest
+
+import mlgi
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+class Gpu:
+    """uploads a Case's inputs and owns a ctx"""
+
+    def __init__(self, case, class_lo=0, class_hi=16, timers=False, max_points=1 << 22):
+        torch = _torch()
+        self.case, wl = case, case.wl
+        dev = torch.device("cuda:0")
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        sc = wl.scene
+        self.t = dict(rsm_diffuse=up(wl.rsm_diffuse), rsm_normal=up(wl.rsm_normal), rsm_depth=up(wl.rsm_depth),
+                      depth=up(wl.depth), normal=up(wl.normal), verts=up(sc.vertices), normals=up(sc.normals),
+                      indices=up(sc.indices), prim=up(sc.prim_id))
+        self.ctx = mlgi.Context(case.W, case.H, case.N, wl.rsm_w, wl.rsm_h, sc.num_triangles, max_points, device=0,
+                                class_lo=class_lo, class_hi=class_hi, enable_timers=timers)
+        self.params = mlgi.default_params(case.N)
+        self.rsm = mlgi.make_rsm(self.t["rsm_diffuse"], self.t["rsm_normal"], self.t["rsm_depth"])
+        self.gb = mlgi.make_gbuffer(self.t["depth"], self.t["normal"])
+        self.mesh = mlgi.make_mesh(self.t["verts"], self.t["normals"], self.t["indices"], self.t["prim"], sc.num_vertices, sc.num_triangles)
+        self.light = mlgi.Camera.make(wl.light_view, wl.light_proj)
+        self.cam = mlgi.Camera.make(wl.cam_view, wl.cam_proj)
+        self.up = up
+
+    def close(self):
+        self.ctx.close()
+
+
+@pytest.fixture(scope="module", params=["small", "c1", "mid"])
+def gpu_case(request, case_small, case_c1, case_mid):
+    case = {"small": case_small, "c1": case_c1, "mid": case_mid}[request.param]
+    g = Gpu(case)
+    yield g
+    g.close()
+
+
+def _sorted_points(points, bucket_start, N):
+    """canonical form of a bucketed point list: rows sorted inside each bucket"""
+    out = []
+    for b in range(N):
+        seg = points[bucket_start[b]:bucket_start[b + 1]]
+        if len(seg):
+            v = seg.view(np.uint32).reshape(-1, 4)
+            order = np.lexsort((v[:, 3], v[:, 2], v[:, 1], v[:, 0]))
+            out.append(v[order])
+    return np.concatenate(out) if out else np.zeros((0, 4), np.uint32)
+
+
+def test_a1_vpl_buffer_bit_exact(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    g.ctx.vpl_process(g.rsm, g.light, g.params)
+    vpl = g.ctx.download(mlgi.BUF_VPL, np.float32).reshape(c.N, 12)
+    packed = g.ctx.download(mlgi.BUF_PACKED_VPL, np.float32).reshape(c.N, 4)
+    shuffle = g.ctx.download(mlgi.BUF_SHUFFLE, np.int32)
+    import oracle_py as O
+    assert np.array_equal(shuffle, O.shuffle_table(c.N))
+    assert np.array_equal(vpl.view(np.uint32), c.get("vpl").view(np.uint32))
+    assert np.array_equal(packed.view(np.uint32), c.get("packed").view(np.uint32))
+
+
+def test_a1_unshuffled(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    import oracle_py as O
+    wl = c.wl
+    p = mlgi.default_params(c.N)
+    p.shuffle_lights = 0
+    p.light_intensity = 2.5
+    g.ctx.vpl_process(g.rsm, g.light, p)
+    vpl = g.ctx.download(mlgi.BUF_VPL, np.float32).reshape(c.N, 12)
+    ref, _ = O.vpl_process(wl.rsm_diffuse, wl.rsm_normal, wl.rsm_depth, c.N, wl.light_view, wl.light_proj, 2.5, False)
+    assert np.array_equal(vpl.view(np.uint32), ref.view(np.uint32))
+    g.ctx.vpl_process(g.rsm, g.light, g.params)   # restore default state for later tests
+
+
+def test_a2_point_list_bit_exact_as_set(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    g.ctx.vpl_process(g.rsm, g.light, g.params)
+    g.ctx.ism_points(g.mesh, g.params)
+    npts, _ = g.ctx.counts()
+    ref_pts, ref_start = c.get("points"), c.get("bucket_start")
+    assert npts == ref_pts.shape[0]
+    start = g.ctx.download(mlgi.BUF_BUCKET_START, np.uint32)
+    assert np.array_equal(start, ref_start)
+    pts = g.ctx.download(mlgi.BUF_POINTS, np.float32, count=npts * 4).reshape(npts, 4)
+    assert np.array_equal(_sorted_points(pts, start, c.N), _sorted_points(ref_pts, ref_start, c.N))
+
+
+def test_a3_atlas_bit_exact_given_oracle_point_list(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    g.ctx.vpl_process(g.rsm, g.light, g.params)
+    pts, start = c.get("points"), c.get("bucket_start")
+    g.ctx.ism_set_points(g.up(pts), g.up(start), pts.shape[0])
+    g.ctx.ism_splat(g.params)
+    atlas = g.ctx.download(mlgi.BUF_ATLAS, np.uint32)
+    assert np.array_equal(atlas, c.get("atlas").ravel())
+
+
+def test_a3_atlas_bit_exact_from_own_points_and_order_independent(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    g.ctx.vpl_process(g.rsm, g.light, g.params)
+    g.ctx.ism_points(g.mesh, g.params)
+    g.ctx.ism_splat(g.params)
+    atlas = g.ctx.download(mlgi.BUF_ATLAS, np.uint32)
+    assert np.array_equal(atlas, c.get("atlas").ravel())
+    # permute the points inside every bucket: min is order independent
+    pts, start = c.get("points").copy(), c.get("bucket_start")
+    rng = np.random.default_rng(7)
+    for b in range(c.N):
+        s, e = int(start[b]), int(start[b + 1])
+        pts[s:e] = pts[s:e][rng.permutation(e - s)]
+    g.ctx.ism_set_points(g.up(pts), g.up(start), pts.shape[0])
+    g.ctx.ism_splat(g.params)
+    assert np.array_equal(g.ctx.download(mlgi.BUF_ATLAS, np.uint32), atlas)
+
+
+def test_a45_pullpush_r16_bit_exact(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    d_atlas = g.up(c.get("atlas"))
+    g.ctx.ism_pullpush(g.params, atlas_override=d_atlas)
+    ism = g.ctx.download(mlgi.BUF_ISM, np.uint16)
+    ref = c.get("ism").ravel()
+    bad = np.flatnonzero(ism != ref)
+    assert bad.size == 0, "%d of %d ISM texels differ, first at %s" % (bad.size, ref.size, bad[:8])
+
+
+def test_a45_pullpush_synthetic_atlases(gpu_case):
+    """edge cases: completely empty atlas, fully dense random atlas, single texel per ISM"""
+    g, c = gpu_case, gpu_case.case
+    import oracle_py as O
+    A = c.get("atlas").shape[0]
+    rng = np.random.default_rng(11)
+    empty = np.full((A, A), 0xFFFFFFFF, np.uint32)
+    dense = ((rng.integers(1 << 18, 1 << 24, (A, A), dtype=np.uint64) << 8) | rng.integers(0, 126, (A, A), dtype=np.uint64)).astype(np.uint32)
+    single = empty.copy()
+    single[32::64, 32::64] = (np.uint32(3_000_000) << 8) | np.uint32(40)
+    sparse = empty.copy()
+    m = rng.random((A, A)) < 0.05
+    sparse[m] = dense[m]
+    zero_depth = sparse.copy()
+    zero_depth[5::64, 7::64] = np.uint32(9)       # depth24 == 0 -> distToCamera == 0 -> inf radius path
+    for name, atl in (("empty", empty), ("dense", dense), ("single", single), ("sparse", sparse), ("zero_depth", zero_depth)):
+        g.ctx.ism_pullpush(g.params, atlas_override=g.up(atl))
+        ism = g.ctx.download(mlgi.BUF_ISM, np.uint16)
+        ref = O.ism_pullpush(atl, c.N, 50.0).ravel()
+        assert np.array_equal(ism, ref), name
+
+
+def test_a67_clustered_lists_bit_exact(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    g.ctx.vpl_process(g.rsm, g.light, g.params)
+    g.ctx.cull_clustered(g.gb, g.cam, g.params)
+    _, nused = g.ctx.counts()
+    assert nused == c.get("num_used")
+    X, Y, L = (c.W + 127) // 128, (c.H + 127) // 128, c.N // 16
+    compact = g.ctx.download(mlgi.BUF_COMPACT_CLUSTER_IDS, np.uint32, count=nused)
+    ids = g.ctx.download(mlgi.BUF_LIGHT_LIST_IDS, np.uint16).reshape(16, Y, X)
+    lists = g.ctx.download(mlgi.BUF_LIGHT_LISTS, np.uint16, count=nused * 16 * (L + 1)).reshape(nused, 16, L + 1)
+    assert np.array_equal(compact, c.get("compact"))
+    assert np.array_equal(ids, c.get("list_ids"))
+    ref = c.get("light_lists")
+    assert np.array_equal(lists[:, :, 0], ref[:, :, 0])
+    for i in range(nused):
+        for k in range(16):
+            n = int(ref[i, k, 0])
+            assert np.array_equal(lists[i, k, 1:n], ref[i, k, 1:n])
+            assert np.all(np.diff(lists[i, k, 1:n].astype(np.int32)) > 0)   # canonical ascending ids (Q6)
+
+
+def test_a8_tiled_lists_bit_exact(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    g.ctx.vpl_process(g.rsm, g.light, g.params)
+    g.ctx.cull_tiled(g.gb, g.cam, g.params)
+    L = c.N // 16
+    ref = c.get("tile_lists")
+    lists = g.ctx.download(mlgi.BUF_TILE_LISTS, np.uint16).reshape(ref.shape)
+    assert np.array_equal(lists[:, :, 0], ref[:, :, 0])
+    for i in range(ref.shape[0]):
+        for k in range(16):
+            n = int(ref[i, k, 0])
+            assert np.array_equal(lists[i, k, 1:n], ref[i, k, 1:n])
+
+
+def _check_radiance(gi, ref, what):
+    rgb, lo, hi = ref["rgb"], ref["lo"], ref["hi"]
+    scale = float(rgb.mean()) + 1e-30
+    atol = 1e-6 * scale
+    inside = (gi >= lo * (1 - 1e-3) - atol) & (gi <= hi * (1 + 1e-3) + atol)
+    assert inside.all(), "%s: %d values outside the oracle's 1e-3 bounds (max rel %.3g)" % (
+        what, int((~inside).sum()), float(np.max(np.abs(gi - rgb) / (np.abs(rgb) + atol))))
+    # the plain criterion on pixels whose shadow lookups have no nearest-texel tie
+    notie = (lo == hi)
+    rel = np.abs(gi - rgb)[notie] / (np.abs(rgb)[notie] + atol)
+    assert rel.size > 0.5 * rgb.size
+    assert float(rel.max()) <= 1e-3, "%s: max relative error %.3g on tie-free pixels" % (what, float(rel.max()))
+
+
+@pytest.mark.parametrize("mode", [mlgi.CULL_TILED, mlgi.CULL_CLUSTERED, mlgi.CULL_NONE])
+@pytest.mark.parametrize("shadows", [True, False])
+def test_a9_radiance_within_1e3(gpu_case, mode, shadows):
+    g, c = gpu_case, gpu_case.case
+    p = mlgi.default_params(c.N)
+    p.cull_mode = mode
+    p.enable_shadowing = int(shadows)
+    g.ctx.vpl_process(g.rsm, g.light, p)
+    if mode == mlgi.CULL_TILED:
+        g.ctx.cull_tiled(g.gb, g.cam, p)
+    elif mode == mlgi.CULL_CLUSTERED:
+        g.ctx.cull_clustered(g.gb, g.cam, p)
+    g.ctx.final_gather(g.gb, g.cam, p, ism_override=g.up(c.get("ism")) if shadows else None)
+    gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)
+    assert np.all(gi[:, :, 3] == 0)
+    _check_radiance(gi[:, :, :3], c.gather(mode, shadows), "mode %d shadows %s" % (mode, shadows))
+
+
+def test_a10_full_frame_and_stage_order(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    for mode in (mlgi.CULL_TILED, mlgi.CULL_CLUSTERED):
+        p = mlgi.default_params(c.N)
+        p.cull_mode = mode
+        g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+        assert np.array_equal(g.ctx.download(mlgi.BUF_ISM, np.uint16), c.get("ism").ravel())
+        gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
+        _check_radiance(gi, c.gather(mode, True), "frame mode %d" % mode)
+
+
+def test_frame_host_end_to_end_matches_device_frame(gpu_case):
+    torch = _torch()
+    g, c = gpu_case, gpu_case.case
+    wl = c.wl
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
+    host_gi = torch.empty((c.H, c.W, 4), dtype=torch.float32).pin_memory()
+    p = mlgi.default_params(c.N)
+    g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    dev_gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)
+    g.ctx.frame_host(mlgi.make_rsm(h[0], h[1], h[2]), g.light, g.mesh, mlgi.make_gbuffer(h[3], h[4]), g.cam, p, host_gi=host_gi)
+    assert np.array_equal(host_gi.numpy(), dev_gi)
+
+
+def test_planar_output_and_class_sharding_is_bit_identical(case_small, case_mid):
+    """multi-GPU contract: a ctx that owns classes [lo,hi) produces exactly the
+    1-GPU pixels of those classes; the class-planar sub-images tile the full image."""
+    for case in (case_small, case_mid):
+        full = Gpu(case)
+        p = mlgi.default_params(case.N)
+        full.ctx.frame(full.rsm, full.light, full.mesh, full.gb, full.cam, p)
+        gi_full = full.ctx.download(mlgi.BUF_GI, np.float32).reshape(case.H, case.W, 4)
+        planar_full = full.ctx.download(mlgi.BUF_GI_PLANAR, np.float32)
+        PH, PW = (case.H + 3) // 4, (case.W + 3) // 4
+        planar_full = planar_full.reshape(16, PH, PW, 4)
+        for cls in range(16):
+            cx, cy = cls & 3, cls >> 2
+            sub = gi_full[cy::4, cx::4]
+            assert np.array_equal(planar_full[cls, :sub.shape[0], :sub.shape[1]], sub)
+        full.close()
+        parts = []
+        for lo, hi in ((0, 4), (4, 8), (8, 12), (12, 16)):
+            g = Gpu(case, class_lo=lo, class_hi=hi)
+            g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+            parts.append(g.ctx.download(mlgi.BUF_GI_PLANAR, np.float32).reshape(hi - lo, PH, PW, 4))
+            g.close()
+        gathered = np.concatenate(parts)   # what ncclAllGather would assemble
+        for cls in range(16):
+            cx, cy = cls & 3, cls >> 2
+            sub = gi_full[cy::4, cx::4]
+            assert np.array_equal(gathered[cls, :sub.shape[0], :sub.shape[1]], sub)
+
+
+def test_n1_blur_within_tolerance(gpu_case):
+    g, c = gpu_case, gpu_case.case
+    import oracle_py as O
+    p = mlgi.default_params(c.N)
+    g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
+    g.ctx.gi_blur(g.gb, g.cam)
+    blur = g.ctx.download(mlgi.BUF_GI_BLUR, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
+    ref = O.gi_blur(gi, c.wl.depth, c.wl.normal, c.wl.cam_proj)   # oracle blur of the SAME gi image
+    np.testing.assert_allclose(blur, ref, rtol=1e-4, atol=1e-6 * float(ref.mean()))
+
+
+def test_error_behaviour(case_small):
+    g = Gpu(case_small)
+    p = mlgi.default_params(case_small.N)
+    with pytest.raises(mlgi.MlgiError) as e:      # stage order
+        g.ctx.ism_splat(p)
+    assert e.value.code == mlgi.E_ORDER
+    for field in ("scale_isms", "points_only_into_scaled_isms", "show_vpl_positions"):
+        q = mlgi.default_params(case_small.N)
+        setattr(q, field, 1)
+        with pytest.raises(mlgi.MlgiError) as e:
+            g.ctx.vpl_process(g.rsm, g.light, q)
+        assert e.value.code == mlgi.E_UNSUPPORTED
+    q = mlgi.default_params(case_small.N)
+    q.use_push_pull = 0
+    with pytest.raises(mlgi.MlgiError) as e:
+        g.ctx.vpl_process(g.rsm, g.light, q)
+    assert e.value.code == mlgi.E_UNSUPPORTED
+    g.close()
+    with pytest.raises(mlgi.MlgiError) as e:      # N must be a multiple of 16 and of ceil(sqrt(N))
+        mlgi.Context(64, 64, 100, 128, 128, 10, 10)
+    assert e.value.code == mlgi.E_INVALID
+    small = Gpu(case_small, max_points=100)       # point buffer overflow is reported, not silent
+    small.ctx.vpl_process(small.rsm, small.light, p)
+    small.ctx.ism_points(small.mesh, p)
+    with pytest.raises(mlgi.MlgiError) as e:
+        small.ctx.counts()
+    assert e.value.code == mlgi.E_CAPACITY
+    small.close()
+
+
+def test_timers_and_launch_count(case_small):
+    g = Gpu(case_small, timers=True)
+    p = mlgi.default_params(case_small.N)
+    n0 = g.ctx.launch_count()
+    g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    assert g.ctx.launch_count() - n0 >= 10
+    t = g.ctx.timings()
+    for name in ("VPLP", "ISM render", "ISM CS", "PullPush", "Tiled cull", "FG"):   # PerfCounter scope names
+        assert name in t and t[name][0] >= 0.0
+    listed, lit = g.ctx.gather_stats()
+    ref = case_small.gather(mlgi.CULL_TILED, True)
+    assert listed == ref["listed"]
+    assert abs(lit - ref["lit"]) <= 1e-4 * ref["lit"] + 8    # sign tests of ~0 values may flip under FMA
+    g.close()
