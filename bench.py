@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- GI frame benchmark (BASELINE.json metric) for the B200-native pipeline.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU restatement of the GLSL
+                                                           # (the reference itself is GL-only and cannot run here)
+
+A "step" is one GI frame of the hot path on one batch of synthetic input: VPL build, scene->points,
+ISM splat, pull-push, tiled culling, final gathering (GIStage::process minus the RSM raster,
+GIStage.cpp:346-418). Workload at every N: 3840x2160, 4096 VPLs / ISMs of 64^2 in a 4096^2 atlas,
+~250k-triangle procedural atrium (BASELINE.json configs[2]); for N>1 the frame is sharded by
+interleave class and assembled with one NCCL all-gather (strong scaling).
+
+Prints ONE JSON line (rank 0). `value` = nominal interleaved (pixel,VPL) pairs per second over the
+whole frame with inputs resident in HBM; `e2e` = the same through mlgi_frame_host (pinned host
+G-buffers/RSM in, GI image out, copies inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200"))
+
+WORKLOADS = {
+    # name: (W, H, N, rsm_w, rsm_h, cell_size)
+    "c1_256_64": (256, 256, 64, 128, 128, 0.155),
+    "1080p_1024": (1920, 1080, 1024, 1024, 256, 0.155),
+    "4k_4096": (3840, 2160, 4096, 1024, 256, 0.155),
+    "8k_16384": (7680, 4320, 16384, 1024, 256, 0.155),
+}
+# FMA = 2, rsqrt/rcp = 1, min/max = 1
+FLOP_LISTED, FLOP_LIT, FLOP_PIXEL = 26.0, 48.0, 60.0
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t1:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name):
+    from mlgi.scene import Workload
+    W, H, N, rw, rh, cell = WORKLOADS[name]
+    return Workload(W, H, N, rsm_w=rw, rsm_h=rh, cell_size=cell)
+
+
+# ---------------------------------------------------------------------------------------
+# CPU side: the oracle (a port of the reference GLSL) on the host cores. bench.py may touch oracle/
+# ONLY here (cpu_baseline leg and --impl reference).
+# ---------------------------------------------------------------------------------------
+class CpuPort:
+    def __init__(self, wl):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py as O
+        self.O, self.wl = O, wl
+        self.cores = O.num_threads()
+        self.prepared = False
+
+    def prepare(self):
+        """all stages before final gathering, full size, timed once"""
+        O, wl = self.O, self.wl
+        sc, N = wl.scene, wl.N
+        t = {}
+        t0 = time.time(); self.vpl, self.packed = O.vpl_process(wl.rsm_diffuse, wl.rsm_normal, wl.rsm_depth, N, wl.light_view, wl.light_proj); t["VPLP"] = time.time() - t0
+        t0 = time.time(); pts, bkt = O.ism_points(sc.vertices, sc.normals, sc.indices, sc.prim_id, 2.0, N); pg, bs = O.group_by_bucket(pts, bkt, N); t["ISM render"] = time.time() - t0
+        t0 = time.time(); atlas = O.ism_splat(pg, bs, self.packed, N, wl.z_far); t["ISM CS"] = time.time() - t0
+        t0 = time.time(); self.ism = O.ism_pullpush(atlas, N, wl.z_far); t["PullPush"] = time.time() - t0
+        t0 = time.time(); self.tiles = O.cull_tiled(wl.depth, self.packed, N, wl.cam_view, wl.cam_proj, 64); t["Tiled cull"] = time.time() - t0
+        self.t_other = sum(t.values())
+        self.stage_s = t
+        self.prepared = True
+
+    def gather_rows(self, r0, r1):
+        O, wl = self.O, self.wl
+        t0 = time.time()
+        O.final_gather(wl.depth, wl.normal, self.vpl, wl.N, self.ism, 1, None, self.tiles, wl.cam_view, wl.cam_proj, wl.z_far, rows=(r0, r1))
+        return time.time() - t0
+
+    def pick_rows(self, budget_s):
+        """rows (multiple of 4 so every interleave class is hit) whose gathering fits budget_s"""
+        H = self.wl.H
+        mid = (H // 2) & ~3
+        t4 = max(self.gather_rows(mid, mid + 4), 1e-4)
+        rows = int(max(4, min(H, (budget_s / t4) * 4))) & ~3
+        r0 = max(0, ((H - rows) // 2) & ~3)
+        return r0, min(H, r0 + rows)
+
+    def frame_estimate(self, r0, r1, t_rows):
+        wl = self.wl
+        t_frame = self.t_other + t_rows * wl.H / float(r1 - r0)
+        pairs = wl.W * wl.H * (wl.N // 16)
+        return pairs / t_frame / 1e9, t_frame
+
+
+def run_reference(args, rank, world):
+    """reference arm: the reference's algorithm on the host CPU (oracle port; the GL original cannot run)."""
+    if rank != 0:
+        return
+    wl = build_workload(args.workload)
+    cpu = CpuPort(wl)
+    cpu.prepare()
+    per_step = max(0.5, 150.0 / float(args.steps + args.warmup))
+    r0, r1 = cpu.pick_rows(per_step)
+    for _ in range(args.warmup):
+        cpu.gather_rows(r0, r1)
+    ts = [cpu.gather_rows(r0, r1) for _ in range(args.steps)]
+    t_rows = sum(ts) / len(ts)
+    value, t_frame = cpu.frame_estimate(r0, r1, t_rows)
+    sample = ("per step: final gathering of rows [%d,%d) of %d (all 16 classes), extrapolated to the frame; VPL/points/splat/"
+              "pull-push/tiled-cull timed once at full size = %.2f s" % (r0, r1, wl.H, cpu.t_other))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_frame * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": bench_config(args, wl, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+METRIC = "final-gather Gpixel*VPL/s over the whole GI frame (ISM build + pull-push + tiled culling + final gathering)"
+UNIT = "Gpixel*VPL/s"
+
+
+def bench_config(args, wl, world):
+    return {"workload": "%s: %dx%d, %d VPLs, %d ISMs of 64^2 in a %d^2 atlas, RSM %dx%d, %d-triangle procedural atrium" % (
+                args.workload, wl.W, wl.H, wl.N, wl.N, 64 * isqrt_pow2(wl.N), wl.rsm_w, wl.rsm_h, wl.scene.num_triangles),
+            "cull": args.cull, "interleave": "4x4", "shadows": True,
+            "parallelism": "interleave-class shard x%d + NCCL all-gather" % world if world > 1 else "single GPU",
+            "l2": "no flush: per-step working set (G-buffer + atlas + ISM + tile lists + GI image) exceeds the 126 MB L2"}
+
+
+def isqrt_pow2(n):
+    l = 0
+    while (1 << l) < n:
+        l += 1
+    return 1 << ((l + 1) // 2)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k_4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--cull", default="tiled", choices=["tiled", "clustered"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import mlgi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = build_workload(args.workload)
+    sc, W, H, N = wl.scene, wl.W, wl.H, wl.N
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = dict(rsm_diffuse=up(wl.rsm_diffuse), rsm_normal=up(wl.rsm_normal), rsm_depth=up(wl.rsm_depth), depth=up(wl.depth),
+             normal=up(wl.normal), verts=up(sc.vertices), normals=up(sc.normals), indices=up(sc.indices), prim=up(sc.prim_id))
+    per = 16 // world
+    lo, hi = rank * per, (rank + 1) * per
+    ctx = mlgi.Context(W, H, N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 23, device=local, class_lo=lo, class_hi=hi)
+    params = mlgi.default_params(N)
+    params.cull_mode = mlgi.CULL_TILED if args.cull == "tiled" else mlgi.CULL_CLUSTERED
+    rsm = mlgi.make_rsm(d["rsm_diffuse"], d["rsm_normal"], d["rsm_depth"])
+    gb = mlgi.make_gbuffer(d["depth"], d["normal"])
+    mesh = mlgi.make_mesh(d["verts"], d["normals"], d["indices"], d["prim"], sc.num_vertices, sc.num_triangles)
+    light = mlgi.Camera.make(wl.light_view, wl.light_proj)
+    cam = mlgi.Camera.make(wl.cam_view, wl.cam_proj)
+    PH, PW = (H + 3) // 4, (W + 3) // 4
+    planar = None
+    if world > 1:
+        planar = torch.zeros((16, PH, PW, 4), dtype=torch.float32, device=dev)
+        ctx.bind_planar_output(planar)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ctx.frame(rsm, light, mesh, gb, cam, params, stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(planar.view(world, -1), planar[lo:hi].reshape(-1))   # in place, NVLink
+            ctx.planar_to_raster(planar, None, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    pairs = W * H * (N // 16)
+    value = pairs / (ms_step * 1e-3) / 1e9
+
+    # ---- per-stage times + the dominant kernel's live duration (events on the launching stream) ----
+    ctx.set_timers(True)
+    acc = {}
+    for _ in range(min(args.steps, 50)):
+        step()
+        torch.cuda.synchronize()
+        for k, (ms, n) in ctx.timings().items():
+            a = acc.setdefault(k, [0.0, 0, n])
+            a[0] += ms; a[1] += 1
+    ctx.set_timers(False)
+    stages = {k: v[0] / v[1] for k, v in acc.items()}
+    stage_launches = {k: v[2] for k, v in acc.items()}
+    fg_ms = stages.get("FG", float("nan"))
+    pp_ms = stages.get("PullPush", float("nan"))
+    clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- end to end: host buffers through mlgi_frame_host ----
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
+        host_gi = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        hr, hg = mlgi.make_rsm(h[0], h[1], h[2]), mlgi.make_gbuffer(h[3], h[4])
+        ctx.bind_planar_output(None)     # the end-to-end call returns this rank's raster pixels to the host
+        n_e2e = max(5, min(args.steps, 50))
+        for _ in range(3):
+            ctx.frame_host(hr, light, mesh, hg, cam, params, host_gi=host_gi, stream=stream)
+        barrier()
+        t0 = time.time()
+        for _ in range(n_e2e):
+            ctx.frame_host(hr, light, mesh, hg, cam, params, host_gi=host_gi, stream=stream)
+        barrier()
+        dt = (time.time() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = sum(x.numel() * x.element_size() for x in h)
+        e2e = {"value": pairs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_gi.numel() * 4,
+               "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "call": "mlgi_frame_host (pinned host RSM + G-buffer in, fp32 RGBA GI image out, stream sync)"}
+        if planar is not None:
+            ctx.bind_planar_output(planar)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (final gathering, FP32 pipe) and of pull-push (HBM) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    listed, lit = ctx.gather_stats(gb, cam, params)
+    npx = (W * H * (hi - lo)) // 16
+    fg_flops = FLOP_LISTED * listed + FLOP_LIT * lit + FLOP_PIXEL * npx
+    fp32_peak = ctx.fp32_peak_tflops()
+    fg_tflops = fg_flops / (fg_ms * 1e-3) / 1e12
+    A = 64 * isqrt_pow2(N)
+    pp_bytes = 6.0 * A * A * (hi - lo) / 16.0
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"kernel": "final_gather_kernel", "bound": "fp32", "achieved": fg_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": fg_tflops / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+                "peak_source": "FFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP32-pipe figure; nominal 148*128*2*1.965 GHz = 74.4)",
+                "algorithmic_flops_per_launch": fg_flops, "pairs_listed": listed, "pairs_lit": lit, "pixels": npx,
+                "flop_model": "26*listed + 48*lit + 60*pixels (SURVEY 8d)", "kernel_ms": fg_ms,
+                "share_of_step": fg_ms / ms_step}
+    roofline_hbm = {"kernel": "pullpush_kernel", "bound": "hbm", "achieved": pp_bytes / (pp_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": pp_bytes / (pp_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                    "algorithmic_bytes_per_launch": pp_bytes, "kernel_ms": pp_ms}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cpu = CpuPort(wl)
+        cpu.prepare()
+        r0, r1 = cpu.pick_rows(12.0)
+        t_rows = cpu.gather_rows(r0, r1)
+        v, t_frame = cpu.frame_estimate(r0, r1, t_rows)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cpu.cores, "kind": "port",
+                        "sample": "oracle (C++ port of the reference GLSL, OpenMP): VPL/points/splat/pull-push/tiled-cull at full size (%.2f s) + "
+                                  "final gathering of rows [%d,%d) of %d (%.2f s), extrapolated to one frame = %.1f s" % (
+                                      cpu.t_other, r0, r1, H, t_rows, t_frame),
+                        "frame_s_estimate": t_frame, "stage_s": cpu.stage_s}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": bench_config(args, wl, world), "gi_ms_per_frame": ms_step,
+           "fg_gpixel_vpl_per_s": pairs * ((hi - lo) / 16.0) / (fg_ms * 1e-3) / 1e9 * world if world > 1 else pairs / (fg_ms * 1e-3) / 1e9,
+           "stage_ms": stages, "stage_launches": stage_launches, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+           "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline}
+    print(json.dumps(out), flush=True)
+    sampler.stop()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -125,7 +125,8 @@ typedef enum {
     MLGI_BUF_TILE_LISTS,           /* [BY*BX][16][L+1] uint16 (tiled variant)   */
     MLGI_BUF_NUM_USED_CLUSTERS,    /* 1 x uint32                                */
     MLGI_BUF_GI,                   /* width*height x 4 float RGBA raster        GIStage giBuffer */
-    MLGI_BUF_GI_PLANAR,            /* [class_hi-class_lo][ceil(H/4)][ceil(W/4)] x 4 float (multi-GPU exchange layout) */
+    MLGI_BUF_GI_PLANAR,            /* [class_hi-class_lo][ceil(H/4)][ceil(W/4)] x 4 float, written when the ctx owns a strict
+                                      subset of the classes and no exchange buffer is bound (multi-GPU layout) */
     MLGI_BUF_GI_BLUR,              /* width*height x 4 float                    GIStage giBlurFinalBuffer */
     MLGI_BUF_COUNT
 } mlgi_buffer_id;
@@ -179,13 +180,25 @@ MLGI_API int mlgi_get_buffer(mlgi_ctx*, int buffer_id, void** dev_ptr, size_t* b
 /* synchronous device->host copy of `bytes` bytes of a ctx buffer starting at byte `offset` (test/debug path) */
 MLGI_API int mlgi_read_buffer(mlgi_ctx*, int buffer_id, void* host_dst, size_t bytes, size_t offset);
 MLGI_API int mlgi_get_counts(mlgi_ctx*, int* num_points, int* num_used_clusters);  /* synchronises */
-/* exact work counters of the last mlgi_final_gather when cfg.enable_timers: pairs listed / lit */
-MLGI_API int mlgi_get_gather_stats(mlgi_ctx*, unsigned long long* pairs_listed, unsigned long long* pairs_lit);
+/* exact work counters of final gathering for the roofline accounting: runs the counting variant of the
+ * kernel on the same inputs (no image is written) and returns (pixel,VPL) pairs listed / lit. Synchronises. */
+MLGI_API int mlgi_gather_stats(mlgi_ctx*, const mlgi_gbuffer*, const mlgi_camera*, const uint16_t* ism_override,
+                               const mlgi_params*, unsigned long long* pairs_listed, unsigned long long* pairs_lit);
+/* FFMA micro-benchmark on the ctx device: the FP32-pipe roofline denominator in TFLOP/s. Synchronises. */
+MLGI_API float mlgi_measure_fp32_peak_tflops(mlgi_ctx*);
+
+/* multi-GPU exchange: the gathering kernel writes the class-planar planes of the classes this
+ * ctx owns straight into a caller-owned [16][ceil(H/4)][ceil(W/4)] x 4 float device buffer (plane c at
+ * c*PH*PW), so one in-place all-gather over ranks assembles the image; NULL unbinds. */
+MLGI_API int mlgi_bind_planar_output(mlgi_ctx*, float* dev_planar16);
+/* consumer-side de-interleave of a complete planar image into raster order (dev_raster NULL = ctx GI buffer) */
+MLGI_API int mlgi_planar_to_raster(mlgi_ctx*, const float* dev_planar16, float* dev_raster, void* stream);
 
 /* per-stage timers (names of PerfCounter scopes, GIStage.cpp:368-411): fills up to `cap`
  * entries, returns the count. Synchronises. */
 typedef struct { char name[24]; float ms; int launches; } mlgi_timing;
 MLGI_API int mlgi_get_timings(mlgi_ctx*, mlgi_timing* out, int cap);
+MLGI_API int mlgi_set_timers(mlgi_ctx*, int enable);   /* toggle cfg.enable_timers at run time */
 /* number of kernels this library launched since creation (bench.py's gpu_launches) */
 MLGI_API unsigned long long mlgi_launch_count(const mlgi_ctx*);
 

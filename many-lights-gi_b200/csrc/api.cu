@@ -89,6 +89,7 @@ struct mlgi_ctx {
     uint16_t* light_lists = nullptr; uint16_t* tile_lists = nullptr;
     float4* gi = nullptr; float4* gi_planar = nullptr; float4* gi_tmp = nullptr; float4* gi_blur = nullptr;
     unsigned long long* stats = nullptr;
+    float4* planar_ext = nullptr;   // caller-owned [16][PH][PW] float4 exchange buffer (mlgi_bind_planar_output)
     // staging for mlgi_frame_host
     uint32_t* st_rsm_diffuse = nullptr; uint32_t* st_rsm_normal = nullptr; float* st_rsm_depth = nullptr;
     float* st_depth = nullptr; uint32_t* st_normal = nullptr;
@@ -315,7 +316,8 @@ MLGI_API int mlgi_ism_splat(mlgi_ctx* ctx, const mlgi_params* p, void* stream) {
     if (!ctx->have_vpl || !ctx->have_points) return fail(ctx, MLGI_E_ORDER, "mlgi_ism_splat needs mlgi_vpl_process and mlgi_ism_points first");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_SPLAT, st);
-    ctx->launches += launch_splat(ctx->points, ctx->bucket_start, (const float4*)ctx->packed, ctx->cfg.vpl_count, ctx->S, p->z_far, ctx->atlas, st);
+    ctx->launches += launch_splat(ctx->points, ctx->bucket_start, (const float4*)ctx->packed, ctx->cfg.vpl_count, ctx->S, p->z_far, ctx->atlas,
+                                  ctx->cfg.class_lo * ctx->L, ctx->cfg.class_hi * ctx->L, st);
     CK(cudaGetLastError());
     ctx->have_atlas = true;
     return MLGI_OK;
@@ -329,7 +331,8 @@ MLGI_API int mlgi_ism_pullpush(mlgi_ctx* ctx, const uint32_t* atlas_override, co
     if (!atlas_override && !ctx->have_atlas) return fail(ctx, MLGI_E_ORDER, "mlgi_ism_pullpush needs mlgi_ism_splat first (or an atlas override)");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_PULLPUSH, st);
-    ctx->launches += launch_pullpush(atlas_override ? atlas_override : ctx->atlas, ctx->S, p->z_far, ctx->ism, st);
+    ctx->launches += launch_pullpush(atlas_override ? atlas_override : ctx->atlas, ctx->S, p->z_far, ctx->ism,
+                                     ctx->cfg.class_lo * ctx->L, ctx->cfg.class_hi * ctx->L, st);
     CK(cudaGetLastError());
     ctx->have_ism = true;
     return MLGI_OK;
@@ -383,9 +386,8 @@ MLGI_API int mlgi_cull_tiled(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
 }
 
 // ------------------------------------------------------------------------------------- a9
-MLGI_API int mlgi_final_gather(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const uint16_t* ism_override,
-                               const mlgi_params* p, void* stream) {
-    if (!ctx) return MLGI_E_INVALID;
+static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const uint16_t* ism_override,
+                             const mlgi_params* p, GatherArgs* out) {
     if (!gb || !gb->depth || !gb->face_normal || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
     int rc = check_params(ctx, p);
     if (rc) return rc;
@@ -394,8 +396,7 @@ MLGI_API int mlgi_final_gather(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi
     if (p->cull_mode == MLGI_CULL_CLUSTERED && !ctx->have_clustered) return fail(ctx, MLGI_E_ORDER, "clustered gathering needs mlgi_cull_clustered first");
     if (p->cull_mode == MLGI_CULL_TILED && !ctx->have_tiled) return fail(ctx, MLGI_E_ORDER, "tiled gathering needs mlgi_cull_tiled first");
     if (p->cull_mode < 0 || p->cull_mode > MLGI_CULL_NONE) return fail(ctx, MLGI_E_INVALID, "bad cull_mode");
-    cudaStream_t st = (cudaStream_t)stream;
-    GatherArgs a;
+    GatherArgs& a = *out;
     memset(&a, 0, sizeof(a));
     a.depth = gb->depth; a.face_normal = gb->face_normal; a.W = ctx->cfg.width; a.H = ctx->cfg.height;
     a.records = ctx->records; a.N = ctx->cfg.vpl_count; a.S = ctx->S;
@@ -416,16 +417,23 @@ MLGI_API int mlgi_final_gather(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi
     a.clampv = p->vpl_clamping_value;
     a.enable_shadowing = p->enable_shadowing;
     a.class_lo = ctx->cfg.class_lo; a.class_hi = ctx->cfg.class_hi;
-    a.out_raster = ctx->gi;
-    a.out_planar = ctx->gi_planar;
+    // output routing: a bound exchange buffer receives the class planes and the raster image is rebuilt by the
+    // consumer (mlgi_planar_to_raster) after the all-gather; otherwise the raster image is written directly, plus
+    // the ctx-owned planar sub-image when this ctx owns only some of the classes.
+    const bool partial = ctx->cfg.class_lo != 0 || ctx->cfg.class_hi != 16;
+    if (ctx->planar_ext) { a.out_raster = nullptr; a.out_planar = ctx->planar_ext; a.planar_class0 = 0; }
+    else { a.out_raster = ctx->gi; a.out_planar = partial ? ctx->gi_planar : nullptr; a.planar_class0 = ctx->cfg.class_lo; }
     a.stats = nullptr;
-    if (ctx->cfg.enable_timers) {
-        // exact work counters for the roofline accounting: an extra, untimed launch of the counting variant
-        CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), st));
-        GatherArgs b = a;
-        b.stats = ctx->stats;
-        ctx->launches += launch_final_gather(b, st);
-    }
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_final_gather(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const uint16_t* ism_override,
+                               const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    GatherArgs a;
+    int rc = build_gather_args(ctx, gb, cam, ism_override, p, &a);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
     {
         StageTimer t(ctx, T_FG, st);
         ctx->launches += launch_final_gather(a, st);
@@ -433,6 +441,53 @@ MLGI_API int mlgi_final_gather(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi
     CK(cudaGetLastError());
     ctx->have_gi = true;
     return MLGI_OK;
+}
+
+MLGI_API int mlgi_gather_stats(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const uint16_t* ism_override,
+                               const mlgi_params* p, unsigned long long* listed, unsigned long long* lit) {
+    if (!ctx) return MLGI_E_INVALID;
+    GatherArgs a;
+    int rc = build_gather_args(ctx, gb, cam, ism_override, p, &a);
+    if (rc) return rc;
+    a.stats = ctx->stats;
+    a.out_raster = nullptr;     // counting variant: same loop, counters instead of stores
+    a.out_planar = nullptr;
+    CK(cudaMemset(ctx->stats, 0, 2 * sizeof(unsigned long long)));
+    ctx->launches += launch_final_gather(a, 0);
+    unsigned long long h[2];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
+    if (listed) *listed = h[0];
+    if (lit) *lit = h[1];
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_bind_planar_output(mlgi_ctx* ctx, float* dev_planar16) {
+    if (!ctx) return MLGI_E_INVALID;
+    ctx->planar_ext = (float4*)dev_planar16;
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_planar_to_raster(mlgi_ctx* ctx, const float* dev_planar16, float* dev_raster, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!dev_planar16) return fail(ctx, MLGI_E_INVALID, "planar buffer is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    ctx->launches += launch_planar_to_raster((const float4*)dev_planar16, ctx->cfg.width, ctx->cfg.height, 0, 16,
+                                             dev_raster ? (float4*)dev_raster : ctx->gi, st);
+    CK(cudaGetLastError());
+    ctx->have_gi = true;
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_set_timers(mlgi_ctx* ctx, int enable) {
+    if (!ctx) return MLGI_E_INVALID;
+    ctx->cfg.enable_timers = enable ? 1 : 0;
+    return MLGI_OK;
+}
+
+MLGI_API float mlgi_measure_fp32_peak_tflops(mlgi_ctx* ctx) {
+    if (!ctx) return -1.0f;
+    return measure_fp32_peak_tflops(0);
 }
 
 // ------------------------------------------------------------------------------------- n1
@@ -536,17 +591,6 @@ MLGI_API int mlgi_get_counts(mlgi_ctx* ctx, int* num_points, int* num_used_clust
     if (num_points) *num_points = (int)h[0];
     if (num_used_clusters) *num_used_clusters = (int)h[2];
     if (h[1] > h[0]) return fail(ctx, MLGI_E_CAPACITY, "point buffer overflow: %u points generated, capacity %d", h[1], ctx->cfg.max_points);
-    return MLGI_OK;
-}
-
-MLGI_API int mlgi_get_gather_stats(mlgi_ctx* ctx, unsigned long long* listed, unsigned long long* lit) {
-    if (!ctx) return MLGI_E_INVALID;
-    if (!ctx->cfg.enable_timers) return fail(ctx, MLGI_E_INVALID, "gather stats need cfg.enable_timers");
-    unsigned long long h[2];
-    CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
-    if (listed) *listed = h[0];
-    if (lit) *lit = h[1];
     return MLGI_OK;
 }
 

@@ -119,8 +119,8 @@ int launch_point_generate(const mlgi_mesh& mesh, float tessLevelFactor, int N, c
 int launch_bucket_scan(int N, const uint32_t* bucket_start_in, cudaStream_t st);
 
 int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S,
-                 float zFar, uint32_t* atlas, cudaStream_t st);
-int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, cudaStream_t st);
+                 float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, cudaStream_t st);
+int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st);
 
 int launch_clustering(const float* depth, int W, int H, float projA, float projB, const SliceTable& tab,
                       uint32_t* tile_masks, uint32_t* compact_ids, uint16_t* light_list_ids, uint32_t* num_used,
@@ -143,12 +143,14 @@ struct GatherArgs {
     int enable_shadowing;
     int class_lo, class_hi;
     float4* out_raster;     // may be null
-    float4* out_planar;     // may be null
+    float4* out_planar;     // may be null; plane of class c starts at (c - planar_class0) * PH * PW
+    int planar_class0;
     unsigned long long* stats;  // null, or 2 counters (pairs listed / lit)
 };
 int launch_final_gather(const GatherArgs& a, cudaStream_t st);
 int launch_gi_blur(const float4* gi, const float* depth, const uint32_t* face_normal, int W, int H, float projA,
                    float projB, float4* tmp, float4* out, cudaStream_t st);
+float measure_fp32_peak_tflops(cudaStream_t st);   // FFMA micro-benchmark: the FP32-pipe roofline denominator
 int launch_planar_to_raster(const float4* planar, int W, int H, int class_lo, int class_hi, float4* raster, cudaStream_t st);
 
 constexpr int kTile = 64;  // tiled-culling tile edge in pixels (one gathering CTA = one class of one tile)

@@ -300,9 +300,10 @@ struct WinVpl { float3 pos, nrm, s, u; float tile_x, tile_y; };
 
 __global__ void __launch_bounds__(128) splat_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ bucket_start,
                                                     const float4* __restrict__ packed_vpl, int N, int S, float zFar,
-                                                    uint32_t* __restrict__ atlas) {
+                                                    uint32_t* __restrict__ atlas, int bucket0, int vpl_lo, int vpl_hi) {
     __shared__ WinVpl win[16];
-    const int b = blockIdx.x;
+    __shared__ int win_id[16];
+    const int b = (bucket0 + (int)blockIdx.x) % N;
     if (threadIdx.x < 16) {                                  // ism.comp:60-69
         int index = (b + (int)threadIdx.x) % N;
         float4 pv = packed_vpl[index];
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(128) splat_kernel(const float4* __restrict__ p
         w.tile_x = float(f2i(ismIndex - y * float(S)));
         w.tile_y = float(f2i(y));
         win[threadIdx.x] = w;
+        win_id[threadIdx.x] = index;
     }
     __syncthreads();
     const uint32_t begin = bucket_start[b], end = bucket_start[b + 1];
@@ -348,8 +350,11 @@ __global__ void __launch_bounds__(128) splat_kernel(const float4* __restrict__ p
             uint32_t val = 0xFFFFFFFFu;
             uint32_t addr = 0xFFFFFFFFu;
             if (active) {
-                const WinVpl& w = win[__ffs(survivors) - 1];
+                const int wi = __ffs(survivors) - 1;
+                const WinVpl& w = win[wi];
                 survivors &= survivors - 1;
+                const int gid = win_id[wi];
+                const bool owned = gid >= vpl_lo && gid < vpl_hi;   // multi-GPU shard: only this rank's ISMs
                 float3 rel = sub3(position, w.pos);
                 float dist = len3(rel);
                 // paraboloid_project(rel, dist, nrm, zFar, id, S, true)  ism_utils.glsl:15-40
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(128) splat_kernel(const float4* __restrict__ p
                 if (depth24 > 0xFFFFFFu) depth24 = 0xFFFFFFu;      // Q10
                 val = (depth24 << 8) | (f2u(pointRadius * 10.0f / 2.0f) & 0xFFu);  // :134-135
                 int tx = f2i(vx), ty = f2i(vy);
-                if (tx < 0 || ty < 0 || tx >= A || ty >= A) active = false;
+                if (!owned || tx < 0 || ty < 0 || tx >= A || ty >= A) active = false;
                 else addr = (uint32_t)ty * (uint32_t)A + (uint32_t)tx;
             }
             unsigned act = __ballot_sync(FULL, active);
@@ -385,11 +390,16 @@ __global__ void __launch_bounds__(128) splat_kernel(const float4* __restrict__ p
     }
 }
 
+// ISMs [vpl_lo, vpl_hi) live in atlas tile rows [vpl_lo/S, ceil(vpl_hi/S)); only those rows are
+// cleared, and only the buckets whose 16-VPL window can reach the range are visited.
 int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S, float zFar,
-                 uint32_t* atlas, cudaStream_t st) {
+                 uint32_t* atlas, int vpl_lo, int vpl_hi, cudaStream_t st) {
     const size_t A = 64 * (size_t)S;
-    cudaMemsetAsync(atlas, 0xFF, A * A * sizeof(uint32_t), st);   // ImperfectShadowmap.cpp:212
-    splat_kernel<<<N, 128, 0, st>>>(points, bucket_start, packed_vpl, N, S, zFar, atlas);
+    const int ty0 = vpl_lo / S, ty1 = (vpl_hi + S - 1) / S;
+    cudaMemsetAsync(atlas + (size_t)ty0 * 64 * A, 0xFF, (size_t)(ty1 - ty0) * 64 * A * sizeof(uint32_t), st);   // ImperfectShadowmap.cpp:212
+    int nb = vpl_hi - vpl_lo + 15, b0 = ((vpl_lo - 15) % N + N) % N;
+    if (nb >= N) { nb = N; b0 = 0; }
+    splat_kernel<<<nb, 128, 0, st>>>(points, bucket_start, packed_vpl, N, S, zFar, atlas, b0, vpl_lo, vpl_hi);
     return 1;
 }
 
@@ -517,13 +527,13 @@ __device__ __forceinline__ float4 push_pixel(const PushCoarse& c, int Tx, int Ty
     return result;
 }
 
-__global__ void __launch_bounds__(PP_THREADS) pullpush_kernel(const uint32_t* __restrict__ atlas, int S, float zFar, uint16_t* __restrict__ ism) {
+__global__ void __launch_bounds__(PP_THREADS) pullpush_kernel(const uint32_t* __restrict__ atlas, int S, float zFar, uint16_t* __restrict__ ism, int tile_y0) {
     __shared__ __align__(16) uint32_t L0[64 * 64];
     __shared__ __align__(16) float4 PY[1024 + 256 + 64 + 16 + 4 + 1];
     // float4 offset of pyramid level l (1..6) inside PY: sum_{k<l} 4^(6-k)
     auto lvl_off = [](int l) { return (4096 - (4096 >> (2 * (l - 1)))) / 3; };
     const int A = 64 * S;
-    const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + tile_y0;
     const int gx0 = tile_x * 64, gy0 = tile_y * 64;
     const int tid = threadIdx.x;
 
@@ -632,9 +642,10 @@ __global__ void __launch_bounds__(PP_THREADS) pullpush_kernel(const uint32_t* __
     }
 }
 
-int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, cudaStream_t st) {
-    dim3 grid(S, S);
-    pullpush_kernel<<<grid, PP_THREADS, 0, st>>>(atlas, S, zFar, ism);
+int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st) {
+    const int ty0 = vpl_lo / S, ty1 = (vpl_hi + S - 1) / S;
+    dim3 grid(S, ty1 - ty0);
+    pullpush_kernel<<<grid, PP_THREADS, 0, st>>>(atlas, S, zFar, ism, ty0);
     return 1;
 }
 

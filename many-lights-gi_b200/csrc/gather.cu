@@ -95,18 +95,22 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
         p.n = make_float3(0.0f, 0.0f, 0.0f);
         if (p.valid) {
             const float depthSample = a.depth[(size_t)y * a.W + x];                // :73
-            const float nx = float(x) / float(a.W) * 2.0f - 1.0f, ny = float(y) / float(a.H) * 2.0f - 1.0f;   // :70,74
-            const float nz = depthSample * 2.0f - 1.0f;
+            // World position and normal are evaluated with the oracle's exact operation order (IEEE
+            // mul/add/div, no FMA): unprojecting a window depth near 1 cancels catastrophically, so a
+            // differently rounded P would move every pair of this pixel by far more than 1e-3.
+            const float nx = __fadd_rn(__fmul_rn(__fdiv_rn(float(x), float(a.W)), 2.0f), -1.0f);   // :70,74
+            const float ny = __fadd_rn(__fmul_rn(__fdiv_rn(float(y), float(a.H)), 2.0f), -1.0f);
+            const float nz = __fadd_rn(__fmul_rn(depthSample, 2.0f), -1.0f);
             const float* m = a.inv_vp.m;
-            const float wx = m[0] * nx + m[4] * ny + m[8] * nz + m[12];            // :75
-            const float wy = m[1] * nx + m[5] * ny + m[9] * nz + m[13];
-            const float wz = m[2] * nx + m[6] * ny + m[10] * nz + m[14];
-            const float ww = m[3] * nx + m[7] * ny + m[11] * nz + m[15];
-            const float iw = 1.0f / ww;
-            p.P = make_float3(wx * iw, wy * iw, wz * iw);                          // :76
+            float w4[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++)                                            // :75  (m0*x + m1*y) + (m2*z + m3*1)
+                w4[r] = __fadd_rn(__fadd_rn(__fmul_rn(m[r], nx), __fmul_rn(m[4 + r], ny)), __fadd_rn(__fmul_rn(m[8 + r], nz), m[12 + r]));
+            p.P = make_float3(__fdiv_rn(w4[0], w4[3]), __fdiv_rn(w4[1], w4[3]), __fdiv_rn(w4[2], w4[3]));   // :76
             const uint32_t n10 = a.face_normal[(size_t)y * a.W + x];
-            p.n = make_float3(float(n10 & 0x3FFu) * (2.0f / 1023.0f) - 1.0f, float((n10 >> 10) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f,
-                              float((n10 >> 20) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f);   // :79
+            p.n = make_float3(__fadd_rn(__fmul_rn(__fdiv_rn(float(n10 & 0x3FFu), 1023.0f), 2.0f), -1.0f),
+                              __fadd_rn(__fmul_rn(__fdiv_rn(float((n10 >> 10) & 0x3FFu), 1023.0f), 2.0f), -1.0f),
+                              __fadd_rn(__fmul_rn(__fdiv_rn(float((n10 >> 20) & 0x3FFu), 1023.0f), 2.0f), -1.0f));   // :79
             if (MODE == MLGI_CULL_CLUSTERED) {
                 // the slice decides WHICH list is read: keep it exact (same table + IEEE ops as clustering)
                 const float zlin = __fdiv_rn(-a.projB, __fadd_rn(a.projA, __fadd_rn(__fmul_rn(2.0f, depthSample), -1.0f)));   // :84
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
         if (!px[k].valid) continue;
         const float4 o = make_float4(px[k].acc.x * a.giScale, px[k].acc.y * a.giScale, px[k].acc.z * a.giScale, 0.0f);
         if (a.out_raster) a.out_raster[(size_t)sy[k] * a.W + sx[k]] = o;
-        if (a.out_planar) a.out_planar[((size_t)(cls - a.class_lo) * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = o;
+        if (a.out_planar) a.out_planar[((size_t)(cls - a.planar_class0) * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = o;
     }
     if (STATS) {
 #pragma unroll
@@ -220,6 +224,44 @@ __global__ void planar_to_raster_kernel(const float4* __restrict__ planar, int W
 int launch_planar_to_raster(const float4* planar, int W, int H, int class_lo, int class_hi, float4* raster, cudaStream_t st) {
     planar_to_raster_kernel<<<dim3((W + 255) / 256, H), 256, 0, st>>>(planar, W, H, class_lo, class_hi, raster);
     return 1;
+}
+
+// =====================================================================================
+// FP32-pipe peak: 8 independent FFMA chains per thread, enough CTAs to fill every SM.
+// =====================================================================================
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456f) out[0] = r;
+}
+float measure_fp32_peak_tflops(cudaStream_t st) {
+    float* d = nullptr;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return -1.0f;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 1 << 15, blocks = sms * 8;
+    fp32_peak_kernel<<<blocks, 256, 0, st>>>(d, 1024, 0.999f, 0.001f);   // warm-up
+    float best = 0.0f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, st);
+        fp32_peak_kernel<<<blocks, 256, 0, st>>>(d, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * double(iters) * 256.0 * double(blocks);
+        best = fmaxf(best, float(flops / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
 }
 
 // =====================================================================================

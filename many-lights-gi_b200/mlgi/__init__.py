@@ -72,7 +72,7 @@ EXPORTS = [
     "mlgi_version", "mlgi_default_params", "mlgi_create", "mlgi_destroy", "mlgi_last_error",
     "mlgi_vpl_process", "mlgi_ism_points", "mlgi_ism_set_points", "mlgi_ism_splat", "mlgi_ism_pullpush",
     "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_frame", "mlgi_frame_host",
-    "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_get_counts", "mlgi_get_gather_stats", "mlgi_get_timings", "mlgi_launch_count",
+    "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
 ]
 
 _lib = None
@@ -117,8 +117,14 @@ def load():
     lib.mlgi_get_buffer.argtypes = [P, C.c_int, C.POINTER(P), C.POINTER(C.c_size_t)]
     lib.mlgi_read_buffer.argtypes = [P, C.c_int, P, C.c_size_t, C.c_size_t]
     lib.mlgi_get_counts.argtypes = [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    lib.mlgi_get_gather_stats.argtypes = [P, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.mlgi_gather_stats.argtypes = [P, C.POINTER(GBuffer), C.POINTER(Camera), P, C.POINTER(Params),
+                                      C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.mlgi_measure_fp32_peak_tflops.argtypes = [P]
+    lib.mlgi_measure_fp32_peak_tflops.restype = C.c_float
+    lib.mlgi_bind_planar_output.argtypes = [P, P]
+    lib.mlgi_planar_to_raster.argtypes = [P, P, P, P]
     lib.mlgi_get_timings.argtypes = [P, C.POINTER(Timing), C.c_int]
+    lib.mlgi_set_timers.argtypes = [P, C.c_int]
     lib.mlgi_launch_count.argtypes = [P]
     lib.mlgi_launch_count.restype = C.c_ulonglong
     _lib = lib
@@ -238,15 +244,28 @@ class Context:
         self._ck(self.lib.mlgi_get_counts(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def gather_stats(self):
+    def gather_stats(self, gb, cam, params, ism_override=None):
         a, b = C.c_ulonglong(), C.c_ulonglong()
-        self._ck(self.lib.mlgi_get_gather_stats(self.h, C.byref(a), C.byref(b)))
+        self._ck(self.lib.mlgi_gather_stats(self.h, C.byref(gb), C.byref(cam), _ptr(ism_override), C.byref(params),
+                                            C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def fp32_peak_tflops(self):
+        return float(self.lib.mlgi_measure_fp32_peak_tflops(self.h))
+
+    def bind_planar_output(self, planar16):
+        self._ck(self.lib.mlgi_bind_planar_output(self.h, _ptr(planar16)))
+
+    def planar_to_raster(self, planar16, raster=None, stream=None):
+        self._ck(self.lib.mlgi_planar_to_raster(self.h, _ptr(planar16), _ptr(raster), stream))
 
     def timings(self):
         arr = (Timing * 16)()
         n = self.lib.mlgi_get_timings(self.h, arr, 16)
         return {arr[i].name.decode(): (arr[i].ms, arr[i].launches) for i in range(n)}
+
+    def set_timers(self, enable):
+        self._ck(self.lib.mlgi_set_timers(self.h, int(enable)))
 
     def launch_count(self):
         return int(self.lib.mlgi_launch_count(self.h))

@@ -759,7 +759,7 @@ ORC_API void orc_cull_tiled(const float* depth, int W, int H, const float* packe
 //   cull_mode 0: clustered (light_list_ids [16][Y][X], lists [cluster][16][L+1])
 //   cull_mode 1: tiled     (lists [block][16][L+1], block = tile x tile px)
 //   cull_mode 2: none      (every VPL of the class, for plumbing tests)
-//   out_rgb: W*H*3 fp32 raster. out_lo/out_hi (optional): bounds of the result when the
+//   rows [row_begin,row_end) only (bounded CPU-baseline samples). out_rgb: W*H*3 fp32 raster. out_lo/out_hi (optional): bounds of the result when the
 //   nearest-texel ISM fetch of a pair lies within tie_eps texels of a texel border (both
 //   neighbours considered); lets the GPU comparison be rigorous about the one discontinuous
 //   operation on this path. stats (optional, 2 x int64): pairs_listed, pairs_lit.
@@ -769,7 +769,7 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
                               int cull_mode, const uint16_t* light_list_ids, const uint16_t* lists,
                               const float* view, const float* proj, float zFar,
                               float giIntensityFactor, float vplClampingValue, int vplStartIndex, int vplEndIndex,
-                              int enableShadowing, int class_lo, int class_hi, int tile,
+                              int enableShadowing, int class_lo, int class_hi, int tile, int row_begin, int row_end,
                               float* out_rgb, float* out_lo, float* out_hi, float tie_eps, long long* stats) {
     mat4 P(proj), V(view);
     // GIStage.cpp:289: camera->viewInverted() * projection->projectionInverted()
@@ -784,7 +784,7 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
     orc_slice_boundaries(zFar, B);
     long long listed = 0, lit = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : listed, lit)
-    for (int fy = 0; fy < H; fy++) {
+    for (int fy = row_begin; fy < row_end; fy++) {
         for (int fx = 0; fx < W; fx++) {
             // :65-68 -- the workgroup decomposition reduces to: class = (x&3, y&3)
             uvec2 interleavedPixel((uint)fx & 3u, (uint)fy & 3u);

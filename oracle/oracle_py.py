@@ -48,7 +48,7 @@ def load():
         lib.orc_light_lists.argtypes = [P, C.c_int, P, C.c_int, P, P, C.c_int, C.c_int, C.c_float, P]
         lib.orc_cull_tiled.argtypes = [P, C.c_int, C.c_int, P, C.c_int, P, P, C.c_int, P]
         lib.orc_final_gather.argtypes = [P, P, C.c_int, C.c_int, P, C.c_int, P, C.c_int, P, P, P, P, C.c_float,
-                                         C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          P, P, P, C.c_float, P]
         lib.orc_gi_blur_pass.argtypes = [P, P, P, C.c_int, C.c_int, P, C.c_int, P]
         _lib = lib
@@ -174,7 +174,7 @@ def cull_tiled(depth, packed_vpl, N, view, proj, tile=64):
 
 def final_gather(depth, normal, vpl, N, ism, cull_mode, light_list_ids, lists, view, proj, z_far,
                  gi_intensity_factor=3000.0, clamp=0.001, vpl_start=0, vpl_end=None, shadows=True,
-                 class_lo=0, class_hi=16, tile=64, bounds=False, tie_eps=None):
+                 class_lo=0, class_hi=16, tile=64, bounds=False, tie_eps=None, rows=None):
     """returns dict(rgb[H,W,3], lo, hi, listed, lit)"""
     H, W = depth.shape
     if vpl_end is None:
@@ -184,11 +184,12 @@ def final_gather(depth, normal, vpl, N, ism, cull_mode, light_list_ids, lists, v
     hi = np.zeros((H, W, 3), np.float32) if bounds else None
     stats = np.zeros(2, np.int64)
     if tie_eps is None:
-        tie_eps = 64 * ism_indices_1d(N) * 4e-7
+        tie_eps = 64 * ism_indices_1d(N) * 1e-6   # a few fp32 ulps of the atlas coordinate, in texels
+    r0, r1 = (0, H) if rows is None else rows
     v, p = _f32(view), _f32(proj)
     load().orc_final_gather(_p(depth), _p(normal), W, H, _p(vpl), N, _p(ism), cull_mode, _p(light_list_ids), _p(lists),
                             _p(v), _p(p), z_far, gi_intensity_factor, clamp, vpl_start, vpl_end, int(shadows),
-                            class_lo, class_hi, tile, _p(out), _p(lo), _p(hi), tie_eps, _p(stats))
+                            class_lo, class_hi, tile, r0, r1, _p(out), _p(lo), _p(hi), tie_eps, _p(stats))
     return dict(rgb=out, lo=lo, hi=hi, listed=int(stats[0]), lit=int(stats[1]))
 
 

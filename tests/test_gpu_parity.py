@@ -256,17 +256,27 @@ def test_planar_output_and_class_sharding_is_bit_identical(case_small, case_mid)
     """multi-GPU contract: a ctx that owns classes [lo,hi) produces exactly the
     1-GPU pixels of those classes; the class-planar sub-images tile the full image."""
     for case in (case_small, case_mid):
+        torch = _torch()
+        PH, PW = (case.H + 3) // 4, (case.W + 3) // 4
         full = Gpu(case)
         p = mlgi.default_params(case.N)
         full.ctx.frame(full.rsm, full.light, full.mesh, full.gb, full.cam, p)
         gi_full = full.ctx.download(mlgi.BUF_GI, np.float32).reshape(case.H, case.W, 4)
-        planar_full = full.ctx.download(mlgi.BUF_GI_PLANAR, np.float32)
-        PH, PW = (case.H + 3) // 4, (case.W + 3) // 4
-        planar_full = planar_full.reshape(16, PH, PW, 4)
+        # bound exchange buffer: the kernel writes class planes only; planar_to_raster rebuilds the image
+        ext = torch.zeros((16, PH, PW, 4), dtype=torch.float32, device="cuda:0")
+        full.ctx.bind_planar_output(ext)
+        full.ctx.frame(full.rsm, full.light, full.mesh, full.gb, full.cam, p)
+        torch.cuda.synchronize()
+        planar_full = ext.cpu().numpy()
         for cls in range(16):
             cx, cy = cls & 3, cls >> 2
             sub = gi_full[cy::4, cx::4]
             assert np.array_equal(planar_full[cls, :sub.shape[0], :sub.shape[1]], sub)
+        raster = torch.zeros((case.H, case.W, 4), dtype=torch.float32, device="cuda:0")
+        full.ctx.planar_to_raster(ext, raster)
+        torch.cuda.synchronize()
+        assert np.array_equal(raster.cpu().numpy(), gi_full)
+        full.ctx.bind_planar_output(None)
         full.close()
         parts = []
         for lo, hi in ((0, 4), (4, 8), (8, 12), (12, 16)):
@@ -332,7 +342,7 @@ def test_timers_and_launch_count(case_small):
     t = g.ctx.timings()
     for name in ("VPLP", "ISM render", "ISM CS", "PullPush", "Tiled cull", "FG"):   # PerfCounter scope names
         assert name in t and t[name][0] >= 0.0
-    listed, lit = g.ctx.gather_stats()
+    listed, lit = g.ctx.gather_stats(g.gb, g.cam, p)
     ref = case_small.gather(mlgi.CULL_TILED, True)
     assert listed == ref["listed"]
     assert abs(lit - ref["lit"]) <= 1e-4 * ref["lit"] + 8    # sign tests of ~0 values may flip under FMA
