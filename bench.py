@@ -134,7 +134,9 @@ class CpuPort:
         """rows (multiple of 4 so every interleave class is hit) whose gathering fits budget_s"""
         H = self.wl.H
         mid = (H // 2) & ~3
-        t4 = max(self.gather_rows(mid, mid + 4), 1e-4)
+        self.gather_rows(mid, mid + 4)                     # thread-pool warm-up
+        probe = min(H - mid, 32) & ~3
+        t4 = max(self.gather_rows(mid, mid + probe), 1e-4) * 4.0 / probe
         rows = int(max(4, min(H, (budget_s / t4) * 4))) & ~3
         r0 = max(0, ((H - rows) // 2) & ~3)
         return r0, min(H, r0 + rows)
