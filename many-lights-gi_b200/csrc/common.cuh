@@ -19,10 +19,12 @@ namespace mlgi {
 // column-major 4x4 passed by value to kernels
 struct Mat4 { float m[16]; };
 
-// Hoisted per-VPL record used by the gathering kernel (80 B, 5 x float4):
-//   r0 = (pos.xyz, tile_x*64 + 32)   r1 = (nrm.xyz, tile_y*64 + 32)
-//   r2 = (s.xyz, 0)   r3 = (u.xyz, 0)   (lookAtRH rows, ism_utils.glsl:5-13)
-//   r4 = (col.xyz, 0)
+// Hoisted per-VPL record used by the gathering kernel (80 B, 5 x float4, in the order the kernel
+// consumes it; lookAtRH rows s,u from ism_utils.glsl:5-13 and the atlas tile origin :35-38 are pure
+// functions of the VPL):
+//   r0 = (-pos.x, -pos.y, -pos.z, nrm.x)   r1 = (nrm.y, nrm.z, s.x, s.y)   r2 = (s.z, u.x, u.y, u.z)
+//   r3 = (col.r, col.g, col.b, Cx)         r4 = (Cy, 0, 0, 0)
+//   Cx = 1.5*2^23 + tile_x*64 + 32, Cy likewise: round-down FMA onto it yields floor(texel coordinate).
 struct VplRecord { float4 r[5]; };
 
 struct DevLists {              // what the gathering kernel needs to find a pixel's list

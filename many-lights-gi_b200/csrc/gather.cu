@@ -17,53 +17,84 @@ namespace mlgi {
 
 static constexpr int FG_THREADS = 128;
 static constexpr int FG_CHUNK = 64;
+static constexpr int FG_REC_Q = 5;       // float4 per staged VPL (same layout as VplRecord)
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 
-struct Pixel {
-    float3 P;       // world position
-    float3 n;       // face normal (10-bit decoded, not renormalised)
-    float3 acc;
-    int slice;      // clustered mode
-    bool valid;
+// ---- packed fp32x2 helpers (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two pixels) ----
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 dup(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsq_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float2 lo2(const float4& q) { return make_float2(q.x, q.y); }
+__device__ __forceinline__ float2 hi2(const float4& q) { return make_float2(q.z, q.w); }
+
+// Two pixels of one thread, component-wise packed: .x = pixel 0, .y = pixel 1
+struct PixelPair {
+    float2 Px, Py, Pz;      // world position
+    float2 Nx, Ny, Nz;      // NEGATED face normal (10-bit decoded, not renormalised): b = N . d
+    float2 ar, ag, ab;      // accumulators
+    int slice0, slice1;     // clustered mode
+    bool valid0, valid1;
 };
 
-__device__ __forceinline__ void shade_pair(Pixel& px, const float4& r0, const float4& r1, const float4& r2, const float4& r3,
-                                           const float4& r4, const uint16_t* __restrict__ ism, int A, float invZFar,
-                                           float clampv, bool shadow, bool active, unsigned long long& listed,
-                                           unsigned long long& lit, bool stats) {
-    const float dx = px.P.x - r0.x, dy = px.P.y - r0.y, dz = px.P.z - r0.z;      // final_gathering.comp:102
-    const float a = r1.x * dx + r1.y * dy + r1.z * dz;                             // dist * dot(vpl.normal, w)
-    const float b = -(px.n.x * dx + px.n.y * dy + px.n.z * dz);                    // dist * dot(fragNormal, -w)
-    if (stats && active) listed++;
-    if (active && a > 0.0f && b > 0.0f) {                                          // :112-114
-        if (stats) lit++;
-        const float d2 = dx * dx + dy * dy + dz * dz;
-        const float inv = rsqrtf(d2);
-        const float inv2 = inv * inv;
-        float g = fminf(a * b * inv2 * inv2 * inv2, clampv);                       // :115-117 (angle/d^2 * 1/d^4)
-        if (shadow) {                                                              // :119-127
-            const float dist = d2 * inv;
-            const float sx = r2.x * dx + r2.y * dy + r2.z * dz;
-            const float sy = r3.x * dx + r3.y * dy + r3.z * dz;
-            const float q = __fdividef(32.0f, dist + a);                           // v.xy/(1 - v.z), v.z = -a/dist
-            int tx = __float2int_rd(fmaf(sx, q, r0.w));                            // tile_x*64 + 32 + 32*px
-            int ty = __float2int_rd(fmaf(sy, q, r1.w));
-            tx = min(max(tx, 0), A - 1);                                           // CLAMP_TO_EDGE, NEAREST
-            ty = min(max(ty, 0), A - 1);
-            const float occ = float(__ldg(ism + (size_t)ty * A + tx)) * (1.0f / 65535.0f);
-            float t = (0.02f - dist * invZFar + occ) * 50.0f;                      // smoothstep(0.98, 1, 1 - (z - occ))
-            t = __saturatef(t);
-            g *= t * t * (3.0f - 2.0f * t);
+// One staged VPL = VplRecord (5 float4 in shared memory, read by broadcast):
+//   r0 = (-px,-py,-pz,nx) r1 = (ny,nz,sx,sy) r2 = (sz,ux,uy,uz) r3 = (cr,cg,cb,Cx) r4 = (Cy,0,0,0)
+//   Cx = 1.5*2^23 + tile_x*64 + 32: adding it with round-down leaves floor(texel x) in the mantissa.
+// VPL scalars enter the packed instructions through their scalar-broadcast operand form (R.F32).
+template <bool SHADOW, bool STATS>
+__device__ __forceinline__ void shade_vpl(PixelPair& px, const float4* __restrict__ rec, const uint16_t* __restrict__ ism,
+                                          int A, float kz, float clampv, bool act0, bool act1,
+                                          unsigned long long& listed, unsigned long long& lit) {
+    const float4 r0 = rec[0], r1 = rec[1];
+    const float2 dx = add2(px.Px, dup(r0.x)), dy = add2(px.Py, dup(r0.y)), dz = add2(px.Pz, dup(r0.z));   // final_gathering.comp:102
+    const float2 a = fma2(dup(r1.y), dz, fma2(dup(r1.x), dy, mul2(dup(r0.w), dx)));   // dist * dot(vpl.normal, w)
+    const float2 b = fma2(px.Nz, dz, fma2(px.Ny, dy, mul2(px.Nx, dx)));               // dist * dot(fragNormal, -w)
+    const bool lit0 = act0 && a.x > 0.0f && b.x > 0.0f;                               // :112-114
+    const bool lit1 = act1 && a.y > 0.0f && b.y > 0.0f;
+    if (STATS) { listed += (act0 ? 1 : 0) + (act1 ? 1 : 0); lit += (lit0 ? 1 : 0) + (lit1 ? 1 : 0); }
+    if (lit0 || lit1) {
+        const float2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+        const float2 inv = make_float2(rsq_approx(d2.x), rsq_approx(d2.y));
+        const float2 inv2 = mul2(inv, inv);
+        const float2 inv4 = mul2(inv2, inv2);
+        float2 g = mul2(mul2(a, b), mul2(inv4, inv2));                                // :115-116  angle/d^2 * 1/d^4
+        g.x = fminf(g.x, clampv); g.y = fminf(g.y, clampv);                           // :117
+        const float4 r3 = rec[3];
+        if (SHADOW) {                                                                 // :119-127
+            const float4 r2 = rec[2];
+            const float cy = rec[4].x;
+            const float2 dist = mul2(d2, inv);
+            const float2 sx = fma2(dup(r2.x), dz, fma2(dup(r1.w), dy, mul2(dup(r1.z), dx)));
+            const float2 sy = fma2(dup(r2.w), dz, fma2(dup(r2.z), dy, mul2(dup(r2.y), dx)));
+            const float2 den = add2(dist, a);                                         // dist * (1 - v.z), v.z = -a/dist
+            const float2 q = make_float2(rcp_approx(den.x) * 32.0f, rcp_approx(den.y) * 32.0f);
+            const float2 fx = __ffma2_rd(sx, q, dup(r3.w));                           // 1.5*2^23 + floor(texel x)
+            const float2 fy = __ffma2_rd(sy, q, dup(cy));
+            int tx0 = __float_as_int(fx.x) - 0x4B400000, ty0 = __float_as_int(fy.x) - 0x4B400000;
+            int tx1 = __float_as_int(fx.y) - 0x4B400000, ty1 = __float_as_int(fy.y) - 0x4B400000;
+            tx0 = min(max(tx0, 0), A - 1); ty0 = min(max(ty0, 0), A - 1);             // NEAREST, CLAMP_TO_EDGE
+            tx1 = min(max(tx1, 0), A - 1); ty1 = min(max(ty1, 0), A - 1);
+            const uint32_t u0 = __ldg(ism + (uint32_t)(ty0 * A + tx0));
+            const uint32_t u1 = __ldg(ism + (uint32_t)(ty1 * A + tx1));
+            // u16 -> float without the conversion pipe: 2^23 + u as bits, minus 2^23
+            const float2 occ = add2(make_float2(__uint_as_float(0x4B000000u | u0), __uint_as_float(0x4B000000u | u1)), dup(-8388608.0f));
+            float2 t = fma2(dist, dup(kz), dup(1.0f));                                // (0.02 - dist/zFar) * 50
+            t = fma2(occ, dup(50.0f / 65535.0f), t);                                  // smoothstep(0.98, 1, 1 - (z - occ))
+            t.x = __saturatef(t.x); t.y = __saturatef(t.y);
+            g = mul2(g, mul2(mul2(t, t), fma2(t, dup(-2.0f), dup(3.0f))));            // :125-126
         }
-        px.acc.x = fmaf(r4.x, g, px.acc.x);                                        // :129
-        px.acc.y = fmaf(r4.y, g, px.acc.y);
-        px.acc.z = fmaf(r4.z, g, px.acc.z);
+        g.x = lit0 ? g.x : 0.0f; g.y = lit1 ? g.y : 0.0f;
+        px.ar = fma2(dup(r3.x), g, px.ar);                                            // :129
+        px.ag = fma2(dup(r3.y), g, px.ag);
+        px.ab = fma2(dup(r3.z), g, px.ab);
     }
 }
 
 template <int MODE, bool SHADOW, bool STATS>
 __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherArgs a) {
-    __shared__ float4 srec[FG_CHUNK * 5];
+    __shared__ float4 srec[FG_CHUNK * FG_REC_Q];
     __shared__ uint32_t s_slices;
 
     const int ncls = a.class_hi - a.class_lo;
@@ -80,20 +111,19 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
 
     if (MODE == MLGI_CULL_CLUSTERED) { if (threadIdx.x == 0) s_slices = 0; __syncthreads(); }
 
-    Pixel px[2];
-    int sx[2], sy[2];
+    float P[2][3], Nn[2][3];
+    int sx[2], sy[2], slice[2];
+    bool valid[2];
     uint32_t my_slices = 0;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const int x = tile_x * kTile + 4 * pi + cxo, y = tile_y * kTile + 4 * (pj0 + 4 * k) + cyo;
         sx[k] = x; sy[k] = y;
-        Pixel& p = px[k];
-        p.valid = x < a.W && y < a.H;
-        p.acc = make_float3(0.0f, 0.0f, 0.0f);
-        p.slice = 0;
-        p.P = make_float3(0.0f, 0.0f, 0.0f);
-        p.n = make_float3(0.0f, 0.0f, 0.0f);
-        if (p.valid) {
+        valid[k] = x < a.W && y < a.H;
+        slice[k] = 0;
+        P[k][0] = P[k][1] = P[k][2] = 0.0f;
+        Nn[k][0] = Nn[k][1] = Nn[k][2] = 0.0f;
+        if (valid[k]) {
             const float depthSample = a.depth[(size_t)y * a.W + x];                // :73
             // World position and normal are evaluated with the oracle's exact operation order (IEEE
             // mul/add/div, no FMA): unprojecting a window depth near 1 cancels catastrophically, so a
@@ -106,11 +136,11 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
 #pragma unroll
             for (int r = 0; r < 4; r++)                                            // :75  (m0*x + m1*y) + (m2*z + m3*1)
                 w4[r] = __fadd_rn(__fadd_rn(__fmul_rn(m[r], nx), __fmul_rn(m[4 + r], ny)), __fadd_rn(__fmul_rn(m[8 + r], nz), m[12 + r]));
-            p.P = make_float3(__fdiv_rn(w4[0], w4[3]), __fdiv_rn(w4[1], w4[3]), __fdiv_rn(w4[2], w4[3]));   // :76
-            const uint32_t n10 = a.face_normal[(size_t)y * a.W + x];
-            p.n = make_float3(__fadd_rn(__fmul_rn(__fdiv_rn(float(n10 & 0x3FFu), 1023.0f), 2.0f), -1.0f),
-                              __fadd_rn(__fmul_rn(__fdiv_rn(float((n10 >> 10) & 0x3FFu), 1023.0f), 2.0f), -1.0f),
-                              __fadd_rn(__fmul_rn(__fdiv_rn(float((n10 >> 20) & 0x3FFu), 1023.0f), 2.0f), -1.0f));   // :79
+            P[k][0] = __fdiv_rn(w4[0], w4[3]); P[k][1] = __fdiv_rn(w4[1], w4[3]); P[k][2] = __fdiv_rn(w4[2], w4[3]);   // :76
+            const uint32_t n10 = a.face_normal[(size_t)y * a.W + x];               // :79 (negated: b = -n . d)
+            Nn[k][0] = -__fadd_rn(__fmul_rn(__fdiv_rn(float(n10 & 0x3FFu), 1023.0f), 2.0f), -1.0f);
+            Nn[k][1] = -__fadd_rn(__fmul_rn(__fdiv_rn(float((n10 >> 10) & 0x3FFu), 1023.0f), 2.0f), -1.0f);
+            Nn[k][2] = -__fadd_rn(__fmul_rn(__fdiv_rn(float((n10 >> 20) & 0x3FFu), 1023.0f), 2.0f), -1.0f);
             if (MODE == MLGI_CULL_CLUSTERED) {
                 // the slice decides WHICH list is read: keep it exact (same table + IEEE ops as clustering)
                 const float zlin = __fdiv_rn(-a.projB, __fadd_rn(a.projA, __fadd_rn(__fmul_rn(2.0f, depthSample), -1.0f)));   // :84
@@ -118,11 +148,17 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
                 int s = 0;
 #pragma unroll
                 for (int i = 1; i <= 15; i++) if (d >= a.tab.b[i]) s = i;          // :85
-                p.slice = s;
+                slice[k] = s;
                 my_slices |= 1u << s;
             }
         }
     }
+    PixelPair px;
+    px.Px = make_float2(P[0][0], P[1][0]); px.Py = make_float2(P[0][1], P[1][1]); px.Pz = make_float2(P[0][2], P[1][2]);
+    px.Nx = make_float2(Nn[0][0], Nn[1][0]); px.Ny = make_float2(Nn[0][1], Nn[1][1]); px.Nz = make_float2(Nn[0][2], Nn[1][2]);
+    px.ar = px.ag = px.ab = make_float2(0.0f, 0.0f);
+    px.valid0 = valid[0]; px.valid1 = valid[1]; px.slice0 = slice[0]; px.slice1 = slice[1];
+
     uint32_t slices = 1u;
     if (MODE == MLGI_CULL_CLUSTERED) {
         my_slices = __reduce_or_sync(FULL, my_slices);
@@ -132,7 +168,7 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
     }
 
     unsigned long long listed = 0, lit = 0;
-    const float invZFar = 1.0f / a.zFar;
+    const float kz = -50.0f / a.zFar;
 
     while (slices) {
         const int s = __ffs(slices) - 1;
@@ -149,13 +185,13 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
             sub = a.lists.lists + ((size_t)tile * 16 + cls) * (L + 1);
             count = (int)sub[0] - 1;
         }
-        const bool act0 = px[0].valid && (MODE != MLGI_CULL_CLUSTERED || px[0].slice == s);
-        const bool act1 = px[1].valid && (MODE != MLGI_CULL_CLUSTERED || px[1].slice == s);
+        const bool act0 = px.valid0 && (MODE != MLGI_CULL_CLUSTERED || px.slice0 == s);
+        const bool act1 = px.valid1 && (MODE != MLGI_CULL_CLUSTERED || px.slice1 == s);
 
         for (int base = 0; base < count; base += FG_CHUNK) {
             const int n = min(FG_CHUNK, count - base);
             __syncthreads();                                    // previous chunk fully consumed
-            // stage n records: 5 float4 each, 128 threads copy float4 granules
+            // stage n records (5 float4 each) cooperatively
             for (int q = threadIdx.x; q < n * 5; q += FG_THREADS) {
                 const int e = q / 5, part = q - e * 5;
                 const uint32_t id = sub ? (uint32_t)sub[1 + base + e] : (uint32_t)(cls * L + base + e);   // :98
@@ -163,11 +199,8 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
             }
             __syncthreads();
 #pragma unroll 2
-            for (int e = 0; e < n; e++) {                       // :97
-                const float4 r0 = srec[e * 5 + 0], r1 = srec[e * 5 + 1], r2 = srec[e * 5 + 2], r3 = srec[e * 5 + 3], r4 = srec[e * 5 + 4];
-                shade_pair(px[0], r0, r1, r2, r3, r4, a.ism, A, invZFar, a.clampv, SHADOW, act0, listed, lit, STATS);
-                shade_pair(px[1], r0, r1, r2, r3, r4, a.ism, A, invZFar, a.clampv, SHADOW, act1, listed, lit, STATS);
-            }
+            for (int e = 0; e < n; e++)                         // :97
+                shade_vpl<SHADOW, STATS>(px, srec + e * FG_REC_Q, a.ism, A, kz, a.clampv, act0, act1, listed, lit);
         }
     }
 
@@ -175,8 +208,9 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
     const int PW = (a.W + 3) >> 2, PH = (a.H + 3) >> 2;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        if (!px[k].valid) continue;
-        const float4 o = make_float4(px[k].acc.x * a.giScale, px[k].acc.y * a.giScale, px[k].acc.z * a.giScale, 0.0f);
+        if (!valid[k]) continue;
+        const float r = k ? px.ar.y : px.ar.x, g = k ? px.ag.y : px.ag.x, b = k ? px.ab.y : px.ab.x;
+        const float4 o = make_float4(r * a.giScale, g * a.giScale, b * a.giScale, 0.0f);
         if (a.out_raster) a.out_raster[(size_t)sy[k] * a.W + sx[k]] = o;
         if (a.out_planar) a.out_planar[((size_t)(cls - a.planar_class0) * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = o;
     }
