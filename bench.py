@@ -215,6 +215,7 @@ def main():
     import numpy as np
     import torch
     import mlgi
+    from mlgi import dist as mdist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
@@ -249,7 +250,7 @@ def main():
     def step():
         ctx.frame(rsm, light, mesh, gb, cam, params, stream=stream)
         if world > 1:
-            dist.all_gather_into_tensor(planar.view(world, -1), planar[lo:hi].reshape(-1))   # in place, NVLink
+            mdist.allgather_planar(planar, rank, world)                                      # in place, NCCL over NVLink
             ctx.planar_to_raster(planar, None, stream=stream)
 
     def barrier():

@@ -22,7 +22,7 @@ struct Mat4 { float m[16]; };
 // Hoisted per-VPL record used by the gathering kernel (80 B, 5 x float4, in the order the kernel
 // consumes it; lookAtRH rows s,u from ism_utils.glsl:5-13 and the atlas tile origin :35-38 are pure
 // functions of the VPL):
-//   r0 = (-pos.x, -pos.y, -pos.z, nrm.x)   r1 = (nrm.y, nrm.z, s.x, s.y)   r2 = (s.z, u.x, u.y, u.z)
+//   r0 = (-pos.x, -pos.y, -pos.z, nrm.x)   r1 = (nrm.y, nrm.z, 32 s.x, 32 s.y)   r2 = (32 s.z, 32 u.x, 32 u.y, 32 u.z)
 //   r3 = (col.r, col.g, col.b, Cx)         r4 = (Cy, 0, 0, 0)
 //   Cx = 1.5*2^23 + tile_x*64 + 32, Cy likewise: round-down FMA onto it yields floor(texel coordinate).
 struct VplRecord { float4 r[5]; };

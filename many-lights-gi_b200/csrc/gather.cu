@@ -16,6 +16,9 @@
 namespace mlgi {
 
 static constexpr int FG_THREADS = 128;
+#ifndef FG_MIN_BLOCKS
+#define FG_MIN_BLOCKS 9
+#endif
 static constexpr int FG_CHUNK = 64;
 static constexpr int FG_REC_Q = 5;       // float4 per staged VPL (same layout as VplRecord)
 static constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -30,6 +33,8 @@ __device__ __forceinline__ float rsq_approx(float x) { float r; asm("rsqrt.appro
 __device__ __forceinline__ float2 lo2(const float4& q) { return make_float2(q.x, q.y); }
 __device__ __forceinline__ float2 hi2(const float4& q) { return make_float2(q.z, q.w); }
 
+struct Normal2 { float2 x, y, z; };   // negated face normals of the two pixels; zero for a pixel that is not active
+
 // Two pixels of one thread, component-wise packed: .x = pixel 0, .y = pixel 1
 struct PixelPair {
     float2 Px, Py, Pz;      // world position
@@ -40,21 +45,21 @@ struct PixelPair {
 };
 
 // One staged VPL = VplRecord (5 float4 in shared memory, read by broadcast):
-//   r0 = (-px,-py,-pz,nx) r1 = (ny,nz,sx,sy) r2 = (sz,ux,uy,uz) r3 = (cr,cg,cb,Cx) r4 = (Cy,0,0,0)
+//   r0 = (-px,-py,-pz,nx) r1 = (ny,nz,32sx,32sy) r2 = (32sz,32ux,32uy,32uz) r3 = (cr,cg,cb,Cx) r4 = (Cy,0,0,0)
 //   Cx = 1.5*2^23 + tile_x*64 + 32: adding it with round-down leaves floor(texel x) in the mantissa.
 // VPL scalars enter the packed instructions through their scalar-broadcast operand form (R.F32).
 template <bool SHADOW, bool STATS>
 __device__ __forceinline__ void shade_vpl(PixelPair& px, const float4* __restrict__ rec, const uint16_t* __restrict__ ism,
-                                          int A, float kz, float clampv, bool act0, bool act1,
+                                          int A, float kz, float clampv, const Normal2& N, int nact,
                                           unsigned long long& listed, unsigned long long& lit) {
     const float4 r0 = rec[0], r1 = rec[1];
     const float2 dx = add2(px.Px, dup(r0.x)), dy = add2(px.Py, dup(r0.y)), dz = add2(px.Pz, dup(r0.z));   // final_gathering.comp:102
     const float2 a = fma2(dup(r1.y), dz, fma2(dup(r1.x), dy, mul2(dup(r0.w), dx)));   // dist * dot(vpl.normal, w)
-    const float2 b = fma2(px.Nz, dz, fma2(px.Ny, dy, mul2(px.Nx, dx)));               // dist * dot(fragNormal, -w)
-    const bool lit0 = act0 && a.x > 0.0f && b.x > 0.0f;                               // :112-114
-    const bool lit1 = act1 && a.y > 0.0f && b.y > 0.0f;
-    if (STATS) { listed += (act0 ? 1 : 0) + (act1 ? 1 : 0); lit += (lit0 ? 1 : 0) + (lit1 ? 1 : 0); }
-    if (lit0 || lit1) {
+    const float2 b = fma2(N.z, dz, fma2(N.y, dy, mul2(N.x, dx)));                     // dist * dot(fragNormal, -w)
+    // angleFactor > 0  <=>  min(a, b) > 0   (:112-114); inactive pixels carry a zero normal, so b == 0
+    const float m0 = fminf(a.x, b.x), m1 = fminf(a.y, b.y);
+    if (STATS) { listed += nact; lit += (m0 > 0.0f ? 1 : 0) + (m1 > 0.0f ? 1 : 0); }
+    if (fmaxf(m0, m1) > 0.0f) {
         const float2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
         const float2 inv = make_float2(rsq_approx(d2.x), rsq_approx(d2.y));
         const float2 inv2 = mul2(inv, inv);
@@ -66,10 +71,10 @@ __device__ __forceinline__ void shade_vpl(PixelPair& px, const float4* __restric
             const float4 r2 = rec[2];
             const float cy = rec[4].x;
             const float2 dist = mul2(d2, inv);
-            const float2 sx = fma2(dup(r2.x), dz, fma2(dup(r1.w), dy, mul2(dup(r1.z), dx)));
-            const float2 sy = fma2(dup(r2.w), dz, fma2(dup(r2.z), dy, mul2(dup(r2.y), dx)));
+            const float2 sx = fma2(dup(r2.x), dz, fma2(dup(r1.w), dy, mul2(dup(r1.z), dx)));   // 32 * (s . d)
+            const float2 sy = fma2(dup(r2.w), dz, fma2(dup(r2.z), dy, mul2(dup(r2.y), dx)));   // 32 * (u . d)
             const float2 den = add2(dist, a);                                         // dist * (1 - v.z), v.z = -a/dist
-            const float2 q = make_float2(rcp_approx(den.x) * 32.0f, rcp_approx(den.y) * 32.0f);
+            const float2 q = make_float2(rcp_approx(den.x), rcp_approx(den.y));
             const float2 fx = __ffma2_rd(sx, q, dup(r3.w));                           // 1.5*2^23 + floor(texel x)
             const float2 fy = __ffma2_rd(sy, q, dup(cy));
             int tx0 = __float_as_int(fx.x) - 0x4B400000, ty0 = __float_as_int(fy.x) - 0x4B400000;
@@ -85,7 +90,7 @@ __device__ __forceinline__ void shade_vpl(PixelPair& px, const float4* __restric
             t.x = __saturatef(t.x); t.y = __saturatef(t.y);
             g = mul2(g, mul2(mul2(t, t), fma2(t, dup(-2.0f), dup(3.0f))));            // :125-126
         }
-        g.x = lit0 ? g.x : 0.0f; g.y = lit1 ? g.y : 0.0f;
+        g.x = m0 > 0.0f ? g.x : 0.0f; g.y = m1 > 0.0f ? g.y : 0.0f;
         px.ar = fma2(dup(r3.x), g, px.ar);                                            // :129
         px.ag = fma2(dup(r3.y), g, px.ag);
         px.ab = fma2(dup(r3.z), g, px.ab);
@@ -93,7 +98,7 @@ __device__ __forceinline__ void shade_vpl(PixelPair& px, const float4* __restric
 }
 
 template <int MODE, bool SHADOW, bool STATS>
-__global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherArgs a) {
+__global__ void __launch_bounds__(FG_THREADS, FG_MIN_BLOCKS) final_gather_kernel(const GatherArgs a) {
     __shared__ float4 srec[FG_CHUNK * FG_REC_Q];
     __shared__ uint32_t s_slices;
 
@@ -187,6 +192,11 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
         }
         const bool act0 = px.valid0 && (MODE != MLGI_CULL_CLUSTERED || px.slice0 == s);
         const bool act1 = px.valid1 && (MODE != MLGI_CULL_CLUSTERED || px.slice1 == s);
+        Normal2 N;   // a zero normal makes b == 0, i.e. "not lit", for pixels outside the viewport / other slices
+        N.x = make_float2(act0 ? px.Nx.x : 0.0f, act1 ? px.Nx.y : 0.0f);
+        N.y = make_float2(act0 ? px.Ny.x : 0.0f, act1 ? px.Ny.y : 0.0f);
+        N.z = make_float2(act0 ? px.Nz.x : 0.0f, act1 ? px.Nz.y : 0.0f);
+        const int nact = (act0 ? 1 : 0) + (act1 ? 1 : 0);
 
         for (int base = 0; base < count; base += FG_CHUNK) {
             const int n = min(FG_CHUNK, count - base);
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(FG_THREADS) final_gather_kernel(const GatherAr
             __syncthreads();
 #pragma unroll 2
             for (int e = 0; e < n; e++)                         // :97
-                shade_vpl<SHADOW, STATS>(px, srec + e * FG_REC_Q, a.ism, A, kz, a.clampv, act0, act1, listed, lit);
+                shade_vpl<SHADOW, STATS>(px, srec + e * FG_REC_Q, a.ism, A, kz, a.clampv, N, nact, listed, lit);
         }
     }
 

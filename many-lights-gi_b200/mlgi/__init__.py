@@ -12,7 +12,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libmlgi.so")
+LIB_PATH = os.environ.get("MLGI_LIB_PATH") or os.path.join(PKG_ROOT, "lib", "libmlgi.so")   # override: A/B builds of the CUDA library
 
 CULL_CLUSTERED, CULL_TILED, CULL_NONE = 0, 1, 2
 

@@ -1,0 +1,55 @@
+"""Host-side logic of the multi-GPU decomposition.
+
+One process per GPU. The frame shards by interleave class: rank r of G owns classes
+[r*16/G, (r+1)*16/G) = pixels with (x&3) + 4*(y&3) in that range = VPL slots [lo*N/16, hi*N/16) =
+a contiguous band of ISM rows. Each rank writes its classes' planes into the same
+[16][ceil(H/4)][ceil(W/4)][4] fp32 exchange buffer; ONE in-place all-gather assembles the image
+(equal-sized contributions), and the consumer de-interleaves it (mlgi_planar_to_raster on the GPU).
+No arithmetic depends on G, so the G-GPU image is bit-identical to the 1-GPU image.
+Backend-agnostic torch.distributed calls: NCCL over NVLink on the GPU box, gloo in the CPU tests.
+"""
+import numpy as np
+
+NUM_CLASSES = 16
+
+
+def class_range(rank, world):
+    if world < 1 or NUM_CLASSES % world:
+        raise ValueError("world size must divide 16 interleave classes, got %d" % world)
+    per = NUM_CLASSES // world
+    return rank * per, (rank + 1) * per
+
+
+def planar_shape(width, height):
+    return (NUM_CLASSES, (height + 3) // 4, (width + 3) // 4, 4)
+
+
+def allgather_planar(planar, rank, world, group=None):
+    """in-place all-gather of the class planes: `planar` is the full [16,PH,PW,4] tensor on every rank,
+    rank r has filled planar[lo:hi]."""
+    import torch.distributed as dist
+    lo, hi = class_range(rank, world)
+    dist.all_gather_into_tensor(planar.view(-1), planar[lo:hi].reshape(-1), group=group)
+    return planar
+
+
+def raster_to_planar(raster):
+    """numpy reference of the layout: raster [H,W,C] -> planar [16,PH,PW,C] (zero padded)"""
+    H, W, C = raster.shape
+    PH, PW = (H + 3) // 4, (W + 3) // 4
+    out = np.zeros((NUM_CLASSES, PH, PW, C), raster.dtype)
+    for cls in range(NUM_CLASSES):
+        cx, cy = cls & 3, cls >> 2
+        sub = raster[cy::4, cx::4]
+        out[cls, :sub.shape[0], :sub.shape[1]] = sub
+    return out
+
+
+def planar_to_raster(planar, width, height):
+    """numpy reference of mlgi_planar_to_raster"""
+    out = np.zeros((height, width, planar.shape[-1]), planar.dtype)
+    for cls in range(NUM_CLASSES):
+        cx, cy = cls & 3, cls >> 2
+        sub = out[cy::4, cx::4]
+        sub[...] = planar[cls, :sub.shape[0], :sub.shape[1]]
+    return out
