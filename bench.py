@@ -107,7 +107,7 @@ class CpuPort:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_py as O
         self.O, self.wl = O, wl
-        self.cores = O.num_threads()
+        self.cores = O.use_all_cores()
         self.prepared = False
 
     def prepare(self):

@@ -14,6 +14,9 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define SCN_API extern "C" __attribute__((visibility("default")))
 
@@ -239,6 +242,9 @@ SCN_API long long mlgi_scene_render(void* s, const float* view, const float* pro
     M4 PV = mul(P, V), inv;
     if (!invert(PV, inv)) return -1;
     long long misses = 0;
+#ifdef _OPENMP
+    omp_set_num_threads(omp_get_num_procs());   // torchrun exports OMP_NUM_THREADS=1; this fixture is untimed
+#endif
 #pragma omp parallel for schedule(dynamic, 8) reduction(+ : misses)
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) {

@@ -216,6 +216,12 @@ ORC_API void orc_shuffle_table(int n, int32_t* out) {
     std::shuffle(v.begin(), v.end(), g);
     for (int i = 0; i < n; i++) out[i] = v[i];
 }
+// torchrun exports OMP_NUM_THREADS=1; the CPU baseline must still use every host core
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
 ORC_API int orc_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -34,6 +34,7 @@ def load():
         lib.orc_paraboloid_project.argtypes = [P, P, C.c_float, C.c_float, C.c_int, C.c_int, P]
         lib.orc_shuffle_table.argtypes = [C.c_int, P]
         lib.orc_num_threads.restype = C.c_int
+        lib.orc_set_num_threads.argtypes = [C.c_int]
         lib.orc_ism_indices_1d.argtypes = [C.c_int]; lib.orc_ism_indices_1d.restype = C.c_int
         lib.orc_slice_boundaries.argtypes = [C.c_float, P]
         lib.orc_slice_log2.argtypes = [C.c_float, C.c_float]; lib.orc_slice_log2.restype = C.c_int
@@ -65,6 +66,13 @@ def _f32(a):
 
 def num_threads():
     return load().orc_num_threads()
+
+
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1; take every core this process may run on"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    load().orc_set_num_threads(n)
+    return num_threads()
 
 
 def ism_indices_1d(n):
