@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <random>
@@ -89,6 +90,9 @@ struct mlgi_ctx {
     uint16_t* light_lists = nullptr; uint16_t* tile_lists = nullptr;
     float4* gi = nullptr; float4* gi_planar = nullptr; float4* gi_tmp = nullptr; float4* gi_blur = nullptr;
     unsigned long long* stats = nullptr;
+    cudaTextureObject_t ism_tex = 0;      // ctx ISM atlas as an R16-unorm point-sampled texture
+    cudaTextureObject_t override_tex = 0; const uint16_t* override_ptr = nullptr;   // cached texture of the last ISM override
+    int use_texture = 1;
     float4* planar_ext = nullptr;   // caller-owned [16][PH][PW] float4 exchange buffer (mlgi_bind_planar_output)
     // staging for mlgi_frame_host
     uint32_t* st_rsm_diffuse = nullptr; uint32_t* st_rsm_normal = nullptr; float* st_rsm_depth = nullptr;
@@ -118,6 +122,26 @@ int fail(mlgi_ctx* c, int code, const char* fmt, ...) {
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) return fail(ctx, MLGI_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
+
+// the R16 atlas as a texture: unnormalised coordinates, point sampling, clamp-to-edge, unorm -> float
+// (what the reference's sampler does: ImperfectShadowmap.cpp:102-106, final_gathering.comp:122)
+cudaError_t make_ism_texture(const uint16_t* ptr, int A, cudaTextureObject_t* out) {
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypePitch2D;
+    rd.res.pitch2D.devPtr = const_cast<uint16_t*>(ptr);
+    rd.res.pitch2D.desc = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    rd.res.pitch2D.width = A;
+    rd.res.pitch2D.height = A;
+    rd.res.pitch2D.pitchInBytes = (size_t)A * sizeof(uint16_t);
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 0;
+    return cudaCreateTextureObject(out, &rd, &td, nullptr);
+}
 
 template <typename T>
 cudaError_t dalloc(mlgi_ctx* c, T** p, size_t count) {
@@ -240,6 +264,8 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     if (e != cudaSuccess) { fail(nullptr, MLGI_E_CUDA, "init: %s", cudaGetErrorString(e)); mlgi_destroy(ctx); return MLGI_E_CUDA; }
     for (int i = 0; i < T_COUNT; i++) { cudaEventCreate(&ctx->ev[i][0]); cudaEventCreate(&ctx->ev[i][1]); }
     ctx->events_created = true;
+    if (const char* e2 = getenv("MLGI_ISM_FETCH")) ctx->use_texture = strcmp(e2, "ldg") != 0;   // A/B switch: tex (default) | ldg
+    if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
     *out = ctx;
     return MLGI_OK;
 }
@@ -248,6 +274,8 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
+    if (ctx->ism_tex) cudaDestroyTextureObject(ctx->ism_tex);
+    if (ctx->override_tex) cudaDestroyTextureObject(ctx->override_tex);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->events_created)
         for (int i = 0; i < T_COUNT; i++) { cudaEventDestroy(ctx->ev[i][0]); cudaEventDestroy(ctx->ev[i][1]); }
@@ -357,7 +385,7 @@ MLGI_API int mlgi_cull_clustered(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const ml
     }
     {
         StageTimer t(ctx, T_LIGHTLISTS, st);
-        ctx->launches += launch_light_lists((const float4*)ctx->packed, ctx->cfg.vpl_count, ctx->compact_ids, ctx->counters + 2,
+        ctx->launches += launch_light_lists(ctx->records, ctx->cfg.vpl_count, ctx->compact_ids, ctx->counters + 2,
                                             ctx->X * ctx->Y * 16, to_mat4(inv), cam->proj[10], cam->proj[14], ctx->cfg.width, ctx->cfg.height,
                                             tab, ctx->cfg.class_lo, ctx->cfg.class_hi, ctx->light_lists, st);
     }
@@ -378,7 +406,7 @@ MLGI_API int mlgi_cull_tiled(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     mat_mul(cam->proj, cam->view, pv);
     mat_inverse(pv, inv);
     StageTimer t(ctx, T_TILED, st);
-    ctx->launches += launch_cull_tiled(gb->depth, ctx->cfg.width, ctx->cfg.height, (const float4*)ctx->packed, ctx->cfg.vpl_count, to_mat4(inv),
+    ctx->launches += launch_cull_tiled(gb->depth, ctx->cfg.width, ctx->cfg.height, ctx->records, ctx->cfg.vpl_count, to_mat4(inv),
                                        ctx->cfg.class_lo, ctx->cfg.class_hi, ctx->tile_lists, st);
     CK(cudaGetLastError());
     ctx->have_tiled = true;
@@ -401,6 +429,19 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     a.depth = gb->depth; a.face_normal = gb->face_normal; a.W = ctx->cfg.width; a.H = ctx->cfg.height;
     a.records = ctx->records; a.N = ctx->cfg.vpl_count; a.S = ctx->S;
     a.ism = ism_override ? ism_override : ctx->ism;
+    a.ism_tex = 0;
+    if (ctx->use_texture) {
+        if (!ism_override) a.ism_tex = ctx->ism_tex;
+        else {
+            if (ctx->override_ptr != ism_override) {
+                if (ctx->override_tex) cudaDestroyTextureObject(ctx->override_tex);
+                ctx->override_tex = 0; ctx->override_ptr = nullptr;
+                if (make_ism_texture(ism_override, ctx->A, &ctx->override_tex) == cudaSuccess) ctx->override_ptr = ism_override;
+                else cudaGetLastError();
+            }
+            a.ism_tex = ctx->override_tex;
+        }
+    }
     a.cull_mode = p->cull_mode;
     a.lists.light_list_ids = ctx->light_list_ids;
     a.lists.lists = (p->cull_mode == MLGI_CULL_CLUSTERED) ? ctx->light_lists : ctx->tile_lists;

@@ -127,16 +127,17 @@ int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int
 int launch_clustering(const float* depth, int W, int H, float projA, float projB, const SliceTable& tab,
                       uint32_t* tile_masks, uint32_t* compact_ids, uint16_t* light_list_ids, uint32_t* num_used,
                       cudaStream_t st);
-int launch_light_lists(const float4* packed_vpl, int N, const uint32_t* compact_ids, const uint32_t* num_used,
+int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_ids, const uint32_t* num_used,
                        int max_clusters, const Mat4& inv_vp, float projA, float projB, int W, int H,
                        const SliceTable& tab, int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);
-int launch_cull_tiled(const float* depth, int W, int H, const float4* packed_vpl, int N, const Mat4& inv_vp,
+int launch_cull_tiled(const float* depth, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
                       int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);
 
 struct GatherArgs {
     const float* depth; const uint32_t* face_normal; int W, H;
     const VplRecord* records; int N; int S;
     const uint16_t* ism;
+    cudaTextureObject_t ism_tex;   // R16 unorm, point sampling, clamp: the same atlas through the texture unit (0 = use LDG)
     DevLists lists; int cull_mode;
     Mat4 inv_vp;            // viewInverted * projectionInverted (GIStage.cpp:289)
     float projA, projB;     // P[2][2], P[3][2]

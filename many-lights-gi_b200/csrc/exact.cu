@@ -3,7 +3,7 @@
 //
 //   a1  vpl_process_kernel      (vpl_processor.comp:41-72)
 //   a2  point_count / point_generate / point_scatter   (ism.tesc/tese/geom, deterministic tessellator)
-//   a3  splat_kernel            (ism.comp:54-139)  warp-aggregated atomicMin into the R32UI atlas
+//   a3  splat_kernel            (ism.comp:54-139)  one warp per bucket, RED.MIN into the R32UI atlas
 //   a4+a5 pullpush_kernel       (pull.comp x6 + push.comp x6) one 64x64 ISM per CTA, pyramid in smem
 //   a6  cluster_mask / cluster_compact                 (clustering.comp:30-88)
 //   a7  light_lists_kernel      (light_lists.comp:50-126) ballot + popc compaction, ascending ids
@@ -291,41 +291,47 @@ int launch_point_generate(const mlgi_mesh& mesh, float tf, int N, const uint32_t
 }
 
 // =====================================================================================
-// a3: splat. One CTA per bucket (ism.comp: one workgroup per bucket, 128 threads); the
-// 16-VPL window (position, unpacked normal, lookAtRH rows) is staged in shared memory.
-// atomicMin on (depth24<<8 | radius8) is warp-aggregated: lanes that hit the same texel are
-// grouped with __match_any_sync and reduced with __reduce_min_sync, one RED per group.
+// a3: splat. One warp per bucket (ism.comp: one workgroup of 128 per bucket); the bucket's 16-VPL window
+// (position, unpacked normal, lookAtRH rows, atlas tile) is staged in shared memory per warp; the first <= 4
+// survivors of the two hemisphere tests are projected and written with atomicMin on (depth24<<8 | radius8).
 // =====================================================================================
 struct WinVpl { float3 pos, nrm, s, u; float tile_x, tile_y; };
+static constexpr int SPLAT_WARPS = 4;      // buckets per CTA: one warp per bucket
 
-__global__ void __launch_bounds__(128) splat_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ bucket_start,
-                                                    const float4* __restrict__ packed_vpl, int N, int S, float zFar,
-                                                    uint32_t* __restrict__ atlas, int bucket0, int vpl_lo, int vpl_hi) {
-    __shared__ WinVpl win[16];
-    __shared__ int win_id[16];
-    const int b = (bucket0 + (int)blockIdx.x) % N;
-    if (threadIdx.x < 16) {                                  // ism.comp:60-69
-        int index = (b + (int)threadIdx.x) % N;
+__global__ void __launch_bounds__(SPLAT_WARPS * 32) splat_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ bucket_start,
+                                                                   const float4* __restrict__ packed_vpl, int N, int S, float zFar,
+                                                                   uint32_t* __restrict__ atlas, int bucket0, int num_buckets, int vpl_lo, int vpl_hi) {
+    __shared__ WinVpl win_s[SPLAT_WARPS][16];
+    __shared__ int win_id_s[SPLAT_WARPS][16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bi = blockIdx.x * SPLAT_WARPS + warp;
+    if (bi >= num_buckets) return;                             // whole warp; only __syncwarp below
+    const int b = (bucket0 + bi) % N;
+    WinVpl* win = win_s[warp];
+    int* win_id = win_id_s[warp];
+    if (lane < 16) {                                           // ism.comp:60-69
+        int index = (b + lane) % N;
         float4 pv = packed_vpl[index];
         WinVpl w;
         w.pos = f3(pv.x, pv.y, pv.z);
         w.nrm = unpack3SN(pv.w);
-        float3 up = f3(0.0f, 1.0f, 0.01f);                   // ism_utils.glsl:5-13
+        float3 up = f3(0.0f, 1.0f, 0.01f);                     // ism_utils.glsl:5-13
         w.s = normalize3(cross3(w.nrm, up));
         w.u = cross3(w.s, w.nrm);
-        float ismIndex = float(index);                       // ism_utils.glsl:35-36
+        float ismIndex = float(index);                         // ism_utils.glsl:35-36
         float y = float(f2i(ismIndex / float(S)));
         w.tile_x = float(f2i(ismIndex - y * float(S)));
         w.tile_y = float(f2i(y));
-        win[threadIdx.x] = w;
-        win_id[threadIdx.x] = index;
+        win[lane] = w;
+        win_id[lane] = index;
     }
-    __syncthreads();
+    __syncwarp();
     const uint32_t begin = bucket_start[b], end = bucket_start[b + 1];
     const float fA = float(64 * S);
+    const float invS = 1.0f / float(S);                        // S is a power of two: x * invS == x / S exactly
     const int A = 64 * S;
-    for (uint32_t base = begin; base < end; base += blockDim.x) {   // warp-uniform trip count
-        const uint32_t pid = base + threadIdx.x;
+    for (uint32_t base = begin; base < end; base += 32) {      // warp-uniform trip count
+        const uint32_t pid = base + lane;
         const bool have = pid < end;
         float3 position = f3(0, 0, 0), pointNormal = f3(0, 0, 0);
         float pointRadius = 0.0f;
@@ -344,9 +350,10 @@ __global__ void __launch_bounds__(128) splat_kernel(const float4* __restrict__ p
                 if (!cull) survivors |= 1u << i;
             }
         }
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 4; i++) {                              // :112-137
             bool active = survivors != 0;                          // first <= 4 survivors in window order
+            if (!__any_sync(FULL, active)) break;
             uint32_t val = 0xFFFFFFFFu;
             uint32_t addr = 0xFFFFFFFFu;
             if (active) {
@@ -368,24 +375,22 @@ __global__ void __launch_bounds__(128) splat_kernel(const float4* __restrict__ p
                 vz = dist / zFar;
                 vz = vz * -sg;
                 vx += 1.0f; vy += 1.0f;
-                vx /= 2.0f; vy /= 2.0f;
+                vx *= 0.5f; vy *= 0.5f;
                 vx += w.tile_x; vy += w.tile_y;
-                vx /= float(S); vy /= float(S);
+                vx *= invS; vy *= invS;
                 vx *= fA; vy *= fA;                                // ism.comp:131
                 vz *= 16777216.0f;                                 // :132
                 uint32_t depth24 = f2u(vz);
                 if (depth24 > 0xFFFFFFu) depth24 = 0xFFFFFFu;      // Q10
-                val = (depth24 << 8) | (f2u(pointRadius * 10.0f / 2.0f) & 0xFFu);  // :134-135
+                val = (depth24 << 8) | (f2u(pointRadius * 10.0f * 0.5f) & 0xFFu);  // :134-135  (/ sqrt(4.0))
                 int tx = f2i(vx), ty = f2i(vy);
                 if (!owned || tx < 0 || ty < 0 || tx >= A || ty >= A) active = false;
                 else addr = (uint32_t)ty * (uint32_t)A + (uint32_t)tx;
             }
-            unsigned act = __ballot_sync(FULL, active);
-            if (active) {
-                unsigned grp = __match_any_sync(act, addr);
-                uint32_t mn = __reduce_min_sync(grp, val);
-                if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicMin(&atlas[addr], mn);  // imageAtomicMin :136
-            }
+            // imageAtomicMin :136. No warp aggregation: with 16 candidate ISMs x 4096 texels per bucket two lanes of a
+            // warp almost never hit the same texel, and ncu showed match.any + redux costing 43% of the kernel's
+            // stall samples (profiles/r1_splat_v1); a plain RED.MIN per splat is what the L2 handles best here.
+            if (active) atomicMin(&atlas[addr], val);
         }
     }
 }
@@ -399,7 +404,7 @@ int launch_splat(const float4* points, const uint32_t* bucket_start, const float
     cudaMemsetAsync(atlas + (size_t)ty0 * 64 * A, 0xFF, (size_t)(ty1 - ty0) * 64 * A * sizeof(uint32_t), st);   // ImperfectShadowmap.cpp:212
     int nb = vpl_hi - vpl_lo + 15, b0 = ((vpl_lo - 15) % N + N) % N;
     if (nb >= N) { nb = N; b0 = 0; }
-    splat_kernel<<<nb, 128, 0, st>>>(points, bucket_start, packed_vpl, N, S, zFar, atlas, b0, vpl_lo, vpl_hi);
+    splat_kernel<<<(nb + SPLAT_WARPS - 1) / SPLAT_WARPS, SPLAT_WARPS * 32, 0, st>>>(points, bucket_start, packed_vpl, N, S, zFar, atlas, b0, nb, vpl_lo, vpl_hi);
     return 1;
 }
 
@@ -413,6 +418,9 @@ int launch_splat(const float4* points, const uint32_t* bucket_start, const float
 // because fp32 rounding of (coord + 0.5 + displacement) depends on their magnitude.
 // =====================================================================================
 static constexpr int PP_THREADS = 256;
+#ifndef PP_MINB
+#define PP_MINB 4
+#endif
 
 struct PullSample { float depth, maxDepth, radius; float2 disp; };
 
@@ -427,9 +435,8 @@ __device__ __forceinline__ float4 pull_combine(const PullSample* smp, int ix0, i
     for (int i = 0; i < 4; i++) {
         float ndx = (float(ix0 + offx[i]) + 0.5f + smp[i].disp.x) / 2.0f - (float(ox) + 0.5f);   // :69
         float ndy = (float(iy0 + offy[i]) + 0.5f + smp[i].disp.y) / 2.0f - (float(oy) + 0.5f);
-        float dist = sqrtf(ndx * ndx + ndy * ndy);                // :70
-        float scaledRadius = smp[i].radius * scale;               // :72
-        bool radiusCheckPassed = dist <= scaledRadius;            // :74
+        const float scaledRadius = smp[i].radius * scale;         // :72
+        const bool radiusCheckPassed = sqrtf(ndx * ndx + ndy * ndy) <= scaledRadius;   // :70,74
         depthSamples[i] = smp[i].depth; maxDepths[i] = smp[i].maxDepth; radiuses[i] = smp[i].radius;
         dv[i] = make_float2(ndx, ndy);
         valid[i] = (smp[i].depth != 1.0f) && radiusCheckPassed;   // :80-81
@@ -463,73 +470,119 @@ __device__ __forceinline__ float4 pull_combine(const PullSample* smp, int ix0, i
     return make_float4(1.0f, 0.0f, 0.0f, 0.0f);
 }
 
-// push.comp:44-165 for one thread T (absolute), tile-local bookkeeping by the caller.
-struct PushCoarse { float depth[4], maxDepth[4], radius[4]; float2 disp[4]; bool in_tile[4]; };
+// push.comp:44-165 for one thread T (absolute), tile-local bookkeeping by the caller. Everything that does not
+// depend on the output pixel is hoisted into PushCoarse once per T (same values, same roundings).
+struct PushCoarse {
+    float depth[4], maxDepth[4], radius[4];
+    float rs[4];            // radius * 2^-level                                  (push.comp:104-105)
+    float w0[4];            // 1 if the tap may contribute at all (same ISM, depth != 1.0), else 0   (:77-93)
+    float cx[4], cy[4];     // (coarse tap coordinate + 0.5) * 2                   (:98)
+    float d2x[4], d2y[4];   // coarse displacement * 2                             (:101)
+};
 
-__device__ __forceinline__ float4 push_pixel(const PushCoarse& c, int Tx, int Ty, int outputPixel, int px, int py, int level,
-                                             float4 origSample) {
-    const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 1, 0};    // push.comp:48
-    const int weightsX[4] = {9, 3, 1, 3};                         // :70
-    int weights[4];
+// LEVEL0: only the depth of the result is consumed (R16 store, push.comp:29-41), so the other weighted means,
+// their divisions and the half packing are not evaluated; at every level the means are evaluated only when the
+// texel is actually replaced (:159-161). Skipped work never feeds a stored value, so results stay bit-exact.
+template <bool LEVEL0>
+__device__ __forceinline__ float4 push_pixel(const PushCoarse& c, int outputPixel, int px, int py, float4 origSample) {
+    // weights are the small integers {9,3,1,3} rotated by the output pixel (:70-74); kept as floats (exact)
+    const float weightsX[4] = {9.0f, 3.0f, 1.0f, 3.0f};
+    float weights[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) weights[i] = weightsX[(i - outputPixel + 4) & 3];
-#pragma unroll
-    for (int i = 0; i < 4; i++) if (!c.in_tile[i]) weights[i] = 0;            // :77-86 (other ISM)
-#pragma unroll
-    for (int i = 0; i < 4; i++) if (c.depth[i] == 1.0f) weights[i] = 0;       // :89-93
-    const float scale = __int_as_float((127 - level) << 23);
+    for (int i = 0; i < 4; i++) weights[i] = weightsX[(i - outputPixel + 4) & 3] * c.w0[i];   // :77-93
+    const float ttx = float(px) + 0.5f, tty = float(py) + 0.5f;
     float2 dv[4];
 #pragma unroll
+#pragma unroll
     for (int i = 0; i < 4; i++) {                                             // :96-110
-        float ctx = (float(Tx - 1 + offx[i]) + 0.5f) * 2.0f, cty = (float(Ty - 1 + offy[i]) + 0.5f) * 2.0f;
-        float ttx = float(px) + 0.5f, tty = float(py) + 0.5f;
-        dv[i] = make_float2((ctx - ttx) + c.disp[i].x * 2.0f, (cty - tty) + c.disp[i].y * 2.0f);
-        float dist = sqrtf(dv[i].x * dv[i].x + dv[i].y * dv[i].y);
-        float radius = c.radius[i] * scale;
-        if (dist > radius) weights[i] = 0;
+        dv[i] = make_float2((c.cx[i] - ttx) + c.d2x[i], (c.cy[i] - tty) + c.d2y[i]);
+        // (a squared-distance guard band that skips most square roots was measured and is slower: 0.43 vs 0.38 ms)
+        if (sqrtf(dv[i].x * dv[i].x + dv[i].y * dv[i].y) > c.rs[i]) weights[i] = 0.0f;
     }
     float minimum = 9001.0f;                                                  // :113
     float maxDepth = 0.0f;
     bool any = false;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        if (weights[i] == 0) continue;
+        if (weights[i] == 0.0f) continue;
         any = true;
         minimum = gmin(c.depth[i], minimum);
         if (minimum == c.depth[i]) maxDepth = c.maxDepth[i];
     }
     if (any) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) if (c.depth[i] > maxDepth) weights[i] = 0;   // :123-126
+        for (int i = 0; i < 4; i++) if (c.depth[i] > maxDepth) weights[i] = 0.0f;   // :123-126
     }
-    float depthAcc = 0.0f, radiusAcc = 0.0f, maxDepthAcc = 0.0f, dax = 0.0f, day = 0.0f;
-    int weightAcc = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {                                             // :135-141
-        float w = float(weights[i]);
-        depthAcc += c.depth[i] * w;
-        maxDepthAcc += c.maxDepth[i] * w;
-        radiusAcc += c.radius[i] * w;
-        dax += dv[i].x * w; day += dv[i].y * w;
-        weightAcc += weights[i];
-    }
-    const bool allSamplesInvalid = weightAcc <= 0;                            // :158
-    float4 result = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (!allSamplesInvalid) {                                                 // :144-147
-        float wa = float(weightAcc);
-        result = make_float4(depthAcc / wa, maxDepthAcc / wa, radiusAcc / wa, __uint_as_float(pack_half2(dax / wa, day / wa)));
-    }
+    const float wa = (weights[0] + weights[1]) + (weights[2] + weights[3]);   // integer-valued, <= 16: exact
+    const bool allSamplesInvalid = wa <= 0.0f;                                // :158
     const bool invalid = origSample.x == 1.0f;                                // :151
     bool occluded = false;
 #pragma unroll
-    for (int i = 0; i < 4; i++) occluded = occluded || (weights[i] > 0 && origSample.x > c.maxDepth[i]);   // :153-156
-    if (allSamplesInvalid || (!invalid && !occluded)) result = origSample;    // :159-161
-    return result;
+    for (int i = 0; i < 4; i++) occluded = occluded || (weights[i] > 0.0f && origSample.x > c.maxDepth[i]);   // :153-156
+    if (allSamplesInvalid || (!invalid && !occluded)) return origSample;      // :159-161
+    float depthAcc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) depthAcc += c.depth[i] * weights[i];          // :135-141
+    if (LEVEL0) return make_float4(depthAcc / wa, 0.0f, 0.0f, 0.0f);          // :144
+    float radiusAcc = 0.0f, maxDepthAcc = 0.0f, dax = 0.0f, day = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float w = weights[i];
+        maxDepthAcc += c.maxDepth[i] * w;
+        radiusAcc += c.radius[i] * w;
+        dax += dv[i].x * w; day += dv[i].y * w;
+    }
+    return make_float4(depthAcc / wa, maxDepthAcc / wa, radiusAcc / wa, __uint_as_float(pack_half2(dax / wa, day / wa)));   // :144-147
 }
 
-__global__ void __launch_bounds__(PP_THREADS) pullpush_kernel(const uint32_t* __restrict__ atlas, int S, float zFar, uint16_t* __restrict__ ism, int tile_y0) {
+// one push pass (level i) over a 64x64 ISM tile held in shared memory
+template <bool LEVEL0>
+__device__ __forceinline__ void push_level(int level, uint32_t* __restrict__ L0, float4* __restrict__ PY, int coarse_off, int same_off,
+                                           int gx0, int gy0, int tid) {
+    const int size = 64 >> level, csz = size >> 1;        // this level / coarser level, tile-local
+    const int nT = csz + 1;
+    const float4* coarse = PY + coarse_off;
+    float4* same = PY + same_off;
+    const int gxl = gx0 >> level, gyl = gy0 >> level;     // tile origin at this level
+    const float scale = __int_as_float((127 - level) << 23);
+    for (int it = tid; it < nT * nT; it += PP_THREADS) {
+        const int tlx = it % nT, tly = it / nT;           // local T
+        const int Tx = (gxl >> 1) + tlx, Ty = (gyl >> 1) + tly;   // absolute T (push.comp:46: coarserLowerLeft = T - 1)
+        PushCoarse c;
+        const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 1, 0};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {                     // :55-62
+            const int cx = tlx - 1 + offx[i], cy = tly - 1 + offy[i];
+            const bool in = cx >= 0 && cy >= 0 && cx < csz && cy < csz;
+            const float4 cs = in ? coarse[cy * csz + cx] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            c.depth[i] = cs.x; c.maxDepth[i] = cs.y; c.radius[i] = cs.z;
+            const float2 disp = unpack_half2(__float_as_uint(cs.w));
+            c.rs[i] = cs.z * scale;
+            c.w0[i] = (in && cs.x != 1.0f) ? 1.0f : 0.0f;
+            c.cx[i] = (float(Tx - 1 + offx[i]) + 0.5f) * 2.0f; c.cy[i] = (float(Ty - 1 + offy[i]) + 0.5f) * 2.0f;
+            c.d2x[i] = disp.x * 2.0f; c.d2y[i] = disp.y * 2.0f;
+        }
+#pragma unroll
+        for (int op = 0; op < 4; op++) {
+            const int plx = tlx * 2 - 1 + offx[op], ply = tly * 2 - 1 + offy[op];   // tile-local pixel (:67)
+            if (plx < 0 || ply < 0 || plx >= size || ply >= size) continue;         // belongs to a neighbouring ISM's CTA
+            const int px = gxl + plx, py = gyl + ply;
+            if (LEVEL0) {
+                const float4 orig = make_float4(float(L0[ply * 64 + plx] >> 8) / 16777216.0f, 0.0f, 0.0f, 0.0f);   // :19-27
+                const float4 res = push_pixel<true>(c, op, px, py, orig);
+                L0[ply * 64 + plx] = __float2uint_rn(gclamp(res.x, 0.0f, 1.0f) * 65535.0f);                         // :29-41 R16 unorm
+            } else {
+                const float4 orig = same[ply * size + plx];
+                same[ply * size + plx] = push_pixel<false>(c, op, px, py, orig);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PP_THREADS, PP_MINB) pullpush_kernel(const uint32_t* __restrict__ atlas, int S, float zFar, uint16_t* __restrict__ ism, int tile_y0) {
     __shared__ __align__(16) uint32_t L0[64 * 64];
     __shared__ __align__(16) float4 PY[1024 + 256 + 64 + 16 + 4 + 1];
+    __shared__ float lut_r[256], lut_md[256];
     // float4 offset of pyramid level l (1..6) inside PY: sum_{k<l} 4^(6-k)
     auto lvl_off = [](int l) { return (4096 - (4096 >> (2 * (l - 1)))) / 3; };
     const int A = 64 * S;
@@ -537,6 +590,11 @@ __global__ void __launch_bounds__(PP_THREADS) pullpush_kernel(const uint32_t* __
     const int gx0 = tile_x * 64, gy0 = tile_y * 64;
     const int tid = threadIdx.x;
 
+    {
+        const float r = float(tid) / 10.0f;                // PP_THREADS == 256 entries
+        lut_r[tid] = r;
+        lut_md[tid] = (r * 2.0f) / zFar * 0.6f;
+    }
     // ---- load the 64x64 R32UI tile: 1024 x uint4, coalesced 256 B rows ----
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -548,6 +606,7 @@ __global__ void __launch_bounds__(PP_THREADS) pullpush_kernel(const uint32_t* __
     __syncthreads();
 
     // ---- pull level 1 (LEVEL_ZERO variant, pull.comp:37-41,55-65) ----
+    // the 8-bit radius only takes 256 values: its two division chains are tabulated per CTA (same IEEE ops)
     const float ismPixelSize = 64.0f;          // A / S  (ImperfectShadowmap.cpp:187-191)
     for (int o = tid; o < 1024; o += PP_THREADS) {
         int lx = o & 31, ly = o >> 5;
@@ -557,8 +616,8 @@ __global__ void __launch_bounds__(PP_THREADS) pullpush_kernel(const uint32_t* __
         for (int i = 0; i < 4; i++) {
             uint32_t u = L0[(ly * 2 + offy[i]) * 64 + lx * 2 + offx[i]];
             float depthSample = float(u >> 8) / 16777216.0f;
-            float radius = float(u & 0xFFu) / 10.0f;
-            float maxDepth = depthSample + (radius * 2.0f) / zFar * 0.6f;      // :57
+            float radius = lut_r[u & 0xFFu];                                   // float(u & 0xFF) / 10      :39
+            float maxDepth = depthSample + lut_md[u & 0xFFu];                  // + (radius*2)/zFar*0.6     :57
             float distToCamera = depthSample * zFar;                           // :60
             radius = radius / distToCamera / 3.14f * ismPixelSize;             // :61
             radius *= 1.3f;                                                    // :63
@@ -591,45 +650,12 @@ __global__ void __launch_bounds__(PP_THREADS) pullpush_kernel(const uint32_t* __
     }
     // ---- push levels 5..0 (in place: push[i] overwrites pull[i]; only the owning thread reads orig) ----
 #pragma unroll 1
-    for (int level = 5; level >= 0; level--) {
-        const int size = 64 >> level, csz = size >> 1;        // this level / coarser level, tile-local
-        const int nT = csz + 1;
-        const float4* coarse = PY + lvl_off(level + 1);
-        float4* same = (level >= 1) ? PY + lvl_off(level) : nullptr;
-        const int gxl = gx0 >> level, gyl = gy0 >> level;     // tile origin at this level
-        for (int it = tid; it < nT * nT; it += PP_THREADS) {
-            int tlx = it % nT, tly = it / nT;                 // local T
-            int Tx = (gxl >> 1) + tlx, Ty = (gyl >> 1) + tly; // absolute T (push.comp:46: coarserLowerLeft = T - 1)
-            PushCoarse c;
-            const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 1, 0};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {                     // :55-62
-                int cx = tlx - 1 + offx[i], cy = tly - 1 + offy[i];
-                bool in = cx >= 0 && cy >= 0 && cx < csz && cy < csz;
-                float4 cs = in ? coarse[cy * csz + cx] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                c.depth[i] = cs.x; c.maxDepth[i] = cs.y; c.radius[i] = cs.z;
-                c.disp[i] = unpack_half2(__float_as_uint(cs.w));
-                c.in_tile[i] = in;
-            }
-#pragma unroll
-            for (int op = 0; op < 4; op++) {
-                int plx = tlx * 2 - 1 + offx[op], ply = tly * 2 - 1 + offy[op];   // tile-local pixel (:67)
-                if (plx < 0 || ply < 0 || plx >= size || ply >= size) continue;   // belongs to a neighbouring ISM's CTA
-                int px = gxl + plx, py = gyl + ply;
-                float4 orig;
-                if (level == 0) orig = make_float4(float(L0[ply * 64 + plx] >> 8) / 16777216.0f, 0.0f, 0.0f, 0.0f);  // :19-27
-                else orig = same[ply * size + plx];
-                float4 res = push_pixel(c, Tx, Ty, op, px, py, level, orig);
-                if (level == 0) {                                                 // :29-41 R16 unorm
-                    float r = gclamp(res.x, 0.0f, 1.0f);
-                    L0[ply * 64 + plx] = __float2uint_rn(r * 65535.0f);
-                } else {
-                    same[ply * size + plx] = res;
-                }
-            }
-        }
+    for (int level = 5; level >= 1; level--) {
+        push_level<false>(level, L0, PY, lvl_off(level + 1), lvl_off(level), gx0, gy0, tid);
         __syncthreads();
     }
+    push_level<true>(0, L0, PY, lvl_off(1), 0, gx0, gy0, tid);
+    __syncthreads();
     // ---- store the R16 tile: 64 rows x 128 B, coalesced uint4 ----
 #pragma unroll
     for (int k = 0; k < 2; k++) {
@@ -729,7 +755,7 @@ __device__ __forceinline__ float3 unproject_corner(const Mat4& inv, float x, flo
     return f3(v.x / v.w, v.y / v.w, v.z / v.w);
 }
 
-__device__ __forceinline__ void build_sublist(float3 my_corner, const float4* __restrict__ packed_vpl, int L, int k,
+__device__ __forceinline__ void build_sublist(float3 my_corner, const VplRecord* __restrict__ records, int L, int k,
                                               uint16_t* __restrict__ sub) {
     const int lane = threadIdx.x & 31;
     float3 corners[8];
@@ -741,24 +767,30 @@ __device__ __forceinline__ void build_sublist(float3 my_corner, const float4* __
     }
     uint32_t counter = 1;                                          // light_lists.comp:99
     for (int base = 0; base < L; base += 32) {
-        int t = base + lane;
-        bool found = false;
-        uint32_t vplID = (uint32_t)(k * L + t);                    // :104-106
+        const int t = base + lane;
+        const uint32_t vplID = (uint32_t)(k * L + t);              // :104-106
+        bool found = t >= L;                                       // lanes past the end do not hold up the early exit
         if (t < L) {
-            float4 pv = packed_vpl[vplID];
-            float3 vp = f3(pv.x, pv.y, pv.z);
-            float3 vn = unpack3SN(pv.w);
+            // the record holds -pos and unpack3SN(packed normal), the very values light_lists.comp:108-110 derives
+            // per test (corner - p == corner + (-p) exactly in IEEE arithmetic)
+            const float4 r0 = __ldg(&records[vplID].r[0]);
+            const float2 r1 = __ldg(reinterpret_cast<const float2*>(&records[vplID].r[1]));
+            const float3 np = f3(r0.x, r0.y, r0.z), vn = f3(r0.w, r1.x, r1.y);
 #pragma unroll
-            for (int j = 0; j < 8; j++) found = found || (dot3(sub3(corners[j], vp), vn) >= 0.0f);   // :109-114
+            for (int j = 0; j < 8; j++) {                          // :109-114 `found = found || ...` is order independent
+                found = found || (dot3(add3(corners[j], np), vn) >= 0.0f);
+                if (__all_sync(__activemask(), found)) break;      // most VPLs pass at the first corner
+            }
         }
-        unsigned bal = __ballot_sync(FULL, found);
+        found = found && t < L;
+        const unsigned bal = __ballot_sync(FULL, found);
         if (found) sub[counter + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)vplID;                // :116-119
         counter += __popc(bal);
     }
     if (lane == 0) sub[0] = (uint16_t)counter;                     // :124-125
 }
 
-__global__ void __launch_bounds__(128) light_lists_kernel(const float4* __restrict__ packed_vpl, int N, const uint32_t* __restrict__ compact_ids,
+__global__ void __launch_bounds__(128) light_lists_kernel(const VplRecord* __restrict__ records, int N, const uint32_t* __restrict__ compact_ids,
                                                           const uint32_t* __restrict__ num_used, Mat4 inv_vp, float projA, float projB,
                                                           int W, int H, SliceTable tab, int class_lo, int class_hi,
                                                           uint16_t* __restrict__ lists) {
@@ -787,21 +819,21 @@ __global__ void __launch_bounds__(128) light_lists_kernel(const float4* __restri
         float cy = (j >= 4) ? ndcT : ndcB;
         float cz = (j & 1) ? ndcBack : ndcFront;
         float3 corner = unproject_corner(inv_vp, cx, cy, cz);
-        build_sublist(corner, packed_vpl, L, k, lists + ((size_t)id * 16 + k) * (L + 1));
+        build_sublist(corner, records, L, k, lists + ((size_t)id * 16 + k) * (L + 1));
     }
 }
 
-int launch_light_lists(const float4* packed_vpl, int N, const uint32_t* compact_ids, const uint32_t* num_used, int max_clusters,
+int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_ids, const uint32_t* num_used, int max_clusters,
                        const Mat4& inv_vp, float projA, float projB, int W, int H, const SliceTable& tab, int class_lo,
                        int class_hi, uint16_t* lists, cudaStream_t st) {
     (void)max_clusters;
-    light_lists_kernel<<<148 * 8, 128, 0, st>>>(packed_vpl, N, compact_ids, num_used, inv_vp, projA, projB, W, H, tab, class_lo,
+    light_lists_kernel<<<148 * 8, 128, 0, st>>>(records, N, compact_ids, num_used, inv_vp, projA, projB, W, H, tab, class_lo,
                                                 class_hi, lists);
     return 1;
 }
 
 // a8: one CTA per 64x64 tile: depth bounds -> 8 corners -> 16 class sub-lists (2 per warp)
-__global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict__ depth, int W, int H, const float4* __restrict__ packed_vpl,
+__global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict__ depth, int W, int H, const VplRecord* __restrict__ records,
                                                          int N, Mat4 inv_vp, int class_lo, int class_hi, uint16_t* __restrict__ lists) {
     __shared__ float smin[8], smax[8];
     __shared__ float3 scorner[8];
@@ -839,13 +871,13 @@ __global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict
     const size_t tile = (size_t)by * gridDim.x + bx;
     float3 corner = scorner[lane & 7];
     for (int k = class_lo + warp; k < class_hi; k += 8)
-        build_sublist(corner, packed_vpl, L, k, lists + (tile * 16 + k) * (L + 1));
+        build_sublist(corner, records, L, k, lists + (tile * 16 + k) * (L + 1));
 }
 
-int launch_cull_tiled(const float* depth, int W, int H, const float4* packed_vpl, int N, const Mat4& inv_vp, int class_lo,
+int launch_cull_tiled(const float* depth, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp, int class_lo,
                       int class_hi, uint16_t* lists, cudaStream_t st) {
     dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile);
-    cull_tiled_kernel<<<grid, 256, 0, st>>>(depth, W, H, packed_vpl, N, inv_vp, class_lo, class_hi, lists);
+    cull_tiled_kernel<<<grid, 256, 0, st>>>(depth, W, H, records, N, inv_vp, class_lo, class_hi, lists);
     return 1;
 }
 

@@ -48,9 +48,9 @@ struct PixelPair {
 //   r0 = (-px,-py,-pz,nx) r1 = (ny,nz,32sx,32sy) r2 = (32sz,32ux,32uy,32uz) r3 = (cr,cg,cb,Cx) r4 = (Cy,0,0,0)
 //   Cx = 1.5*2^23 + tile_x*64 + 32: adding it with round-down leaves floor(texel x) in the mantissa.
 // VPL scalars enter the packed instructions through their scalar-broadcast operand form (R.F32).
-template <bool SHADOW, bool STATS>
+template <bool SHADOW, bool STATS, bool TEX>
 __device__ __forceinline__ void shade_vpl(PixelPair& px, const float4* __restrict__ rec, const uint16_t* __restrict__ ism,
-                                          int A, float kz, float clampv, const Normal2& N, int nact,
+                                          cudaTextureObject_t ism_tex, int A, float kz, float clampv, const Normal2& N, int nact,
                                           unsigned long long& listed, unsigned long long& lit) {
     const float4 r0 = rec[0], r1 = rec[1];
     const float2 dx = add2(px.Px, dup(r0.x)), dy = add2(px.Py, dup(r0.y)), dz = add2(px.Pz, dup(r0.z));   // final_gathering.comp:102
@@ -77,16 +77,28 @@ __device__ __forceinline__ void shade_vpl(PixelPair& px, const float4* __restric
             const float2 q = make_float2(rcp_approx(den.x), rcp_approx(den.y));
             const float2 fx = __ffma2_rd(sx, q, dup(r3.w));                           // 1.5*2^23 + floor(texel x)
             const float2 fy = __ffma2_rd(sy, q, dup(cy));
-            int tx0 = __float_as_int(fx.x) - 0x4B400000, ty0 = __float_as_int(fy.x) - 0x4B400000;
-            int tx1 = __float_as_int(fx.y) - 0x4B400000, ty1 = __float_as_int(fy.y) - 0x4B400000;
-            tx0 = min(max(tx0, 0), A - 1); ty0 = min(max(ty0, 0), A - 1);             // NEAREST, CLAMP_TO_EDGE
-            tx1 = min(max(tx1, 0), A - 1); ty1 = min(max(ty1, 0), A - 1);
-            const uint32_t u0 = __ldg(ism + (uint32_t)(ty0 * A + tx0));
-            const uint32_t u1 = __ldg(ism + (uint32_t)(ty1 * A + tx1));
-            // u16 -> float without the conversion pipe: 2^23 + u as bits, minus 2^23
-            const float2 occ = add2(make_float2(__uint_as_float(0x4B000000u | u0), __uint_as_float(0x4B000000u | u1)), dup(-8388608.0f));
             float2 t = fma2(dist, dup(kz), dup(1.0f));                                // (0.02 - dist/zFar) * 50
-            t = fma2(occ, dup(50.0f / 65535.0f), t);                                  // smoothstep(0.98, 1, 1 - (z - occ))
+            if (TEX) {
+                // textureLod(ismDepthSampler, v.xy, 0) with NEAREST + CLAMP_TO_EDGE (final_gathering.comp:122) on the
+                // texture unit: address, clamp and R16-unorm -> float conversion cost no SM instructions. The coordinate
+                // handed over is the already floored texel index (an exact integer), so the unit's own rounding cannot
+                // pick a neighbouring texel.
+                const float2 kx = add2(fx, dup(-12582912.0f)), ky = add2(fy, dup(-12582912.0f));
+                float o0 = 0.0f, o1 = 0.0f;
+                if (m0 > 0.0f) o0 = tex2D<float>(ism_tex, kx.x, ky.x);
+                if (m1 > 0.0f) o1 = tex2D<float>(ism_tex, kx.y, ky.y);
+                t = fma2(make_float2(o0, o1), dup(50.0f), t);                         // smoothstep(0.98, 1, 1 - (z - occ))
+            } else {
+                int tx0 = __float_as_int(fx.x) - 0x4B400000, ty0 = __float_as_int(fy.x) - 0x4B400000;
+                int tx1 = __float_as_int(fx.y) - 0x4B400000, ty1 = __float_as_int(fy.y) - 0x4B400000;
+                tx0 = min(max(tx0, 0), A - 1); ty0 = min(max(ty0, 0), A - 1);         // NEAREST, CLAMP_TO_EDGE
+                tx1 = min(max(tx1, 0), A - 1); ty1 = min(max(ty1, 0), A - 1);
+                const uint32_t u0 = __ldg(ism + (uint32_t)(ty0 * A + tx0));
+                const uint32_t u1 = __ldg(ism + (uint32_t)(ty1 * A + tx1));
+                // u16 -> float without the conversion pipe: 2^23 + u as bits, minus 2^23
+                const float2 occ = add2(make_float2(__uint_as_float(0x4B000000u | u0), __uint_as_float(0x4B000000u | u1)), dup(-8388608.0f));
+                t = fma2(occ, dup(50.0f / 65535.0f), t);                              // smoothstep(0.98, 1, 1 - (z - occ))
+            }
             t.x = __saturatef(t.x); t.y = __saturatef(t.y);
             g = mul2(g, mul2(mul2(t, t), fma2(t, dup(-2.0f), dup(3.0f))));            // :125-126
         }
@@ -97,7 +109,7 @@ __device__ __forceinline__ void shade_vpl(PixelPair& px, const float4* __restric
     }
 }
 
-template <int MODE, bool SHADOW, bool STATS>
+template <int MODE, bool SHADOW, bool STATS, bool TEX>
 __global__ void __launch_bounds__(FG_THREADS, FG_MIN_BLOCKS) final_gather_kernel(const GatherArgs a) {
     __shared__ float4 srec[FG_CHUNK * FG_REC_Q];
     __shared__ uint32_t s_slices;
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(FG_THREADS, FG_MIN_BLOCKS) final_gather_kernel
             __syncthreads();
 #pragma unroll 2
             for (int e = 0; e < n; e++)                         // :97
-                shade_vpl<SHADOW, STATS>(px, srec + e * FG_REC_Q, a.ism, A, kz, a.clampv, N, nact, listed, lit);
+                shade_vpl<SHADOW, STATS, TEX>(px, srec + e * FG_REC_Q, a.ism, a.ism_tex, A, kz, a.clampv, N, nact, listed, lit);
         }
     }
 
@@ -237,10 +249,13 @@ __global__ void __launch_bounds__(FG_THREADS, FG_MIN_BLOCKS) final_gather_kernel
 template <int MODE>
 static void launch_fg_mode(const GatherArgs& a, dim3 grid, cudaStream_t st) {
     const bool sh = a.enable_shadowing != 0, stt = a.stats != nullptr;
-    if (sh && !stt) final_gather_kernel<MODE, true, false><<<grid, FG_THREADS, 0, st>>>(a);
-    else if (sh && stt) final_gather_kernel<MODE, true, true><<<grid, FG_THREADS, 0, st>>>(a);
-    else if (!sh && !stt) final_gather_kernel<MODE, false, false><<<grid, FG_THREADS, 0, st>>>(a);
-    else final_gather_kernel<MODE, false, true><<<grid, FG_THREADS, 0, st>>>(a);
+    const bool tex = sh && a.ism_tex != 0;      // the ISM is fetched through the texture unit whenever a texture object exists
+    if (stt) {                                   // counting variant (work counters for the roofline accounting)
+        if (sh) final_gather_kernel<MODE, true, true, false><<<grid, FG_THREADS, 0, st>>>(a);
+        else final_gather_kernel<MODE, false, true, false><<<grid, FG_THREADS, 0, st>>>(a);
+    } else if (!sh) final_gather_kernel<MODE, false, false, false><<<grid, FG_THREADS, 0, st>>>(a);
+    else if (tex) final_gather_kernel<MODE, true, false, true><<<grid, FG_THREADS, 0, st>>>(a);
+    else final_gather_kernel<MODE, true, false, false><<<grid, FG_THREADS, 0, st>>>(a);
 }
 
 int launch_final_gather(const GatherArgs& a, cudaStream_t st) {
