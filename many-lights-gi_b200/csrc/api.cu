@@ -93,6 +93,7 @@ struct mlgi_ctx {
     cudaTextureObject_t ism_tex = 0;      // ctx ISM atlas as an R16-unorm point-sampled texture
     cudaTextureObject_t override_tex = 0; const uint16_t* override_ptr = nullptr;   // cached texture of the last ISM override
     int use_texture = 1;
+    int fg_pairs = 1;
     float4* planar_ext = nullptr;   // caller-owned [16][PH][PW] float4 exchange buffer (mlgi_bind_planar_output)
     // staging for mlgi_frame_host
     uint32_t* st_rsm_diffuse = nullptr; uint32_t* st_rsm_normal = nullptr; float* st_rsm_depth = nullptr;
@@ -265,6 +266,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     for (int i = 0; i < T_COUNT; i++) { cudaEventCreate(&ctx->ev[i][0]); cudaEventCreate(&ctx->ev[i][1]); }
     ctx->events_created = true;
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) ctx->use_texture = strcmp(e2, "ldg") != 0;   // A/B switch: tex (default) | ldg
+    if (const char* e3 = getenv("MLGI_FG_PAIRS")) ctx->fg_pairs = atoi(e3) == 2 ? 2 : 1;         // A/B switch: pixels per thread / 2
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
     *out = ctx;
     return MLGI_OK;
@@ -457,6 +459,7 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     a.giScale = p->gi_intensity_factor / float(p->vpl_end_index - p->vpl_start_index) * 16.0f;   // final_gathering.comp:132
     a.clampv = p->vpl_clamping_value;
     a.enable_shadowing = p->enable_shadowing;
+    a.pairs_per_thread = ctx->fg_pairs;
     a.class_lo = ctx->cfg.class_lo; a.class_hi = ctx->cfg.class_hi;
     // output routing: a bound exchange buffer receives the class planes and the raster image is rebuilt by the
     // consumer (mlgi_planar_to_raster) after the all-gather; otherwise the raster image is written directly, plus

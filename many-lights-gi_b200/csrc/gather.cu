@@ -15,10 +15,6 @@
 
 namespace mlgi {
 
-static constexpr int FG_THREADS = 128;
-#ifndef FG_MIN_BLOCKS
-#define FG_MIN_BLOCKS 9
-#endif
 static constexpr int FG_CHUNK = 64;
 static constexpr int FG_REC_Q = 5;       // float4 per staged VPL (same layout as VplRecord)
 static constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -48,69 +44,82 @@ struct PixelPair {
 //   r0 = (-px,-py,-pz,nx) r1 = (ny,nz,32sx,32sy) r2 = (32sz,32ux,32uy,32uz) r3 = (cr,cg,cb,Cx) r4 = (Cy,0,0,0)
 //   Cx = 1.5*2^23 + tile_x*64 + 32: adding it with round-down leaves floor(texel x) in the mantissa.
 // VPL scalars enter the packed instructions through their scalar-broadcast operand form (R.F32).
-template <bool SHADOW, bool STATS, bool TEX>
-__device__ __forceinline__ void shade_vpl(PixelPair& px, const float4* __restrict__ rec, const uint16_t* __restrict__ ism,
-                                          cudaTextureObject_t ism_tex, int A, float kz, float clampv, const Normal2& N, int nact,
+template <bool SHADOW, bool STATS, bool TEX, int NP>
+__device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __restrict__ rec, const uint16_t* __restrict__ ism,
+                                          cudaTextureObject_t ism_tex, int A, float kz, float clampv, const Normal2 (&N)[NP], int nact,
                                           unsigned long long& listed, unsigned long long& lit) {
     const float4 r0 = rec[0], r1 = rec[1];
-    const float2 dx = add2(px.Px, dup(r0.x)), dy = add2(px.Py, dup(r0.y)), dz = add2(px.Pz, dup(r0.z));   // final_gathering.comp:102
-    const float2 a = fma2(dup(r1.y), dz, fma2(dup(r1.x), dy, mul2(dup(r0.w), dx)));   // dist * dot(vpl.normal, w)
-    const float2 b = fma2(N.z, dz, fma2(N.y, dy, mul2(N.x, dx)));                     // dist * dot(fragNormal, -w)
-    // angleFactor > 0  <=>  min(a, b) > 0   (:112-114); inactive pixels carry a zero normal, so b == 0
-    const float m0 = fminf(a.x, b.x), m1 = fminf(a.y, b.y);
-    if (STATS) { listed += nact; lit += (m0 > 0.0f ? 1 : 0) + (m1 > 0.0f ? 1 : 0); }
-    if (fmaxf(m0, m1) > 0.0f) {
-        const float2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-        const float2 inv = make_float2(rsq_approx(d2.x), rsq_approx(d2.y));
-        const float2 inv2 = mul2(inv, inv);
-        const float2 inv4 = mul2(inv2, inv2);
-        float2 g = mul2(mul2(a, b), mul2(inv4, inv2));                                // :115-116  angle/d^2 * 1/d^4
-        g.x = fminf(g.x, clampv); g.y = fminf(g.y, clampv);                           // :117
+    float2 dx[NP], dy[NP], dz[NP], a[NP], b[NP];
+    float m0[NP], m1[NP];
+    float mmax = -1.0f;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        dx[p] = add2(px[p].Px, dup(r0.x)); dy[p] = add2(px[p].Py, dup(r0.y)); dz[p] = add2(px[p].Pz, dup(r0.z));   // final_gathering.comp:102
+        a[p] = fma2(dup(r1.y), dz[p], fma2(dup(r1.x), dy[p], mul2(dup(r0.w), dx[p])));   // dist * dot(vpl.normal, w)
+        b[p] = fma2(N[p].z, dz[p], fma2(N[p].y, dy[p], mul2(N[p].x, dx[p])));            // dist * dot(fragNormal, -w)
+        // angleFactor > 0  <=>  min(a, b) > 0   (:112-114); inactive pixels carry a zero normal, so b == 0
+        m0[p] = fminf(a[p].x, b[p].x); m1[p] = fminf(a[p].y, b[p].y);
+        mmax = fmaxf(mmax, fmaxf(m0[p], m1[p]));
+        if (STATS) lit += (m0[p] > 0.0f ? 1 : 0) + (m1[p] > 0.0f ? 1 : 0);
+    }
+    if (STATS) listed += nact;
+    if (mmax > 0.0f) {
         const float4 r3 = rec[3];
-        if (SHADOW) {                                                                 // :119-127
-            const float4 r2 = rec[2];
-            const float cy = rec[4].x;
-            const float2 dist = mul2(d2, inv);
-            const float2 sx = fma2(dup(r2.x), dz, fma2(dup(r1.w), dy, mul2(dup(r1.z), dx)));   // 32 * (s . d)
-            const float2 sy = fma2(dup(r2.w), dz, fma2(dup(r2.z), dy, mul2(dup(r2.y), dx)));   // 32 * (u . d)
-            const float2 den = add2(dist, a);                                         // dist * (1 - v.z), v.z = -a/dist
-            const float2 q = make_float2(rcp_approx(den.x), rcp_approx(den.y));
-            const float2 fx = __ffma2_rd(sx, q, dup(r3.w));                           // 1.5*2^23 + floor(texel x)
-            const float2 fy = __ffma2_rd(sy, q, dup(cy));
-            float2 t = fma2(dist, dup(kz), dup(1.0f));                                // (0.02 - dist/zFar) * 50
-            if (TEX) {
-                // textureLod(ismDepthSampler, v.xy, 0) with NEAREST + CLAMP_TO_EDGE (final_gathering.comp:122) on the
-                // texture unit: address, clamp and R16-unorm -> float conversion cost no SM instructions. The coordinate
-                // handed over is the already floored texel index (an exact integer), so the unit's own rounding cannot
-                // pick a neighbouring texel.
-                const float2 kx = add2(fx, dup(-12582912.0f)), ky = add2(fy, dup(-12582912.0f));
-                float o0 = 0.0f, o1 = 0.0f;
-                if (m0 > 0.0f) o0 = tex2D<float>(ism_tex, kx.x, ky.x);
-                if (m1 > 0.0f) o1 = tex2D<float>(ism_tex, kx.y, ky.y);
-                t = fma2(make_float2(o0, o1), dup(50.0f), t);                         // smoothstep(0.98, 1, 1 - (z - occ))
-            } else {
-                int tx0 = __float_as_int(fx.x) - 0x4B400000, ty0 = __float_as_int(fy.x) - 0x4B400000;
-                int tx1 = __float_as_int(fx.y) - 0x4B400000, ty1 = __float_as_int(fy.y) - 0x4B400000;
-                tx0 = min(max(tx0, 0), A - 1); ty0 = min(max(ty0, 0), A - 1);         // NEAREST, CLAMP_TO_EDGE
-                tx1 = min(max(tx1, 0), A - 1); ty1 = min(max(ty1, 0), A - 1);
-                const uint32_t u0 = __ldg(ism + (uint32_t)(ty0 * A + tx0));
-                const uint32_t u1 = __ldg(ism + (uint32_t)(ty1 * A + tx1));
-                // u16 -> float without the conversion pipe: 2^23 + u as bits, minus 2^23
-                const float2 occ = add2(make_float2(__uint_as_float(0x4B000000u | u0), __uint_as_float(0x4B000000u | u1)), dup(-8388608.0f));
-                t = fma2(occ, dup(50.0f / 65535.0f), t);                              // smoothstep(0.98, 1, 1 - (z - occ))
+        float4 r2; float cy;
+        if (SHADOW) { r2 = rec[2]; cy = rec[4].x; }
+#pragma unroll
+        for (int p = 0; p < NP; p++) {                  // NP independent chains: the compiler interleaves them (ILP)
+            const float2 d2 = fma2(dz[p], dz[p], fma2(dy[p], dy[p], mul2(dx[p], dx[p])));
+            const float2 inv = make_float2(rsq_approx(d2.x), rsq_approx(d2.y));
+            const float2 inv2 = mul2(inv, inv);
+            const float2 inv4 = mul2(inv2, inv2);
+            float2 g = mul2(mul2(a[p], b[p]), mul2(inv4, inv2));                          // :115-116  angle/d^2 * 1/d^4
+            g.x = fminf(g.x, clampv); g.y = fminf(g.y, clampv);                           // :117
+            if (SHADOW) {                                                                 // :119-127
+                const float2 dist = mul2(d2, inv);
+                const float2 sx = fma2(dup(r2.x), dz[p], fma2(dup(r1.w), dy[p], mul2(dup(r1.z), dx[p])));   // 32 * (s . d)
+                const float2 sy = fma2(dup(r2.w), dz[p], fma2(dup(r2.z), dy[p], mul2(dup(r2.y), dx[p])));   // 32 * (u . d)
+                const float2 den = add2(dist, a[p]);                                      // dist * (1 - v.z), v.z = -a/dist
+                const float2 q = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+                const float2 fx = __ffma2_rd(sx, q, dup(r3.w));                           // 1.5*2^23 + floor(texel x)
+                const float2 fy = __ffma2_rd(sy, q, dup(cy));
+                float2 t = fma2(dist, dup(kz), dup(1.0f));                                // (0.02 - dist/zFar) * 50
+                if (TEX) {
+                    // textureLod(ismDepthSampler, v.xy, 0) with NEAREST + CLAMP_TO_EDGE (final_gathering.comp:122) on the
+                    // texture unit: address, clamp and R16-unorm -> float conversion cost no SM instructions. The coordinate
+                    // handed over is the already floored texel index (an exact integer), so the unit's own rounding cannot
+                    // pick a neighbouring texel.
+                    const float2 kx = add2(fx, dup(-12582912.0f)), ky = add2(fy, dup(-12582912.0f));
+                    float o0 = 0.0f, o1 = 0.0f;
+                    if (m0[p] > 0.0f) o0 = tex2D<float>(ism_tex, kx.x, ky.x);
+                    if (m1[p] > 0.0f) o1 = tex2D<float>(ism_tex, kx.y, ky.y);
+                    t = fma2(make_float2(o0, o1), dup(50.0f), t);                         // smoothstep(0.98, 1, 1 - (z - occ))
+                } else {
+                    int tx0 = __float_as_int(fx.x) - 0x4B400000, ty0 = __float_as_int(fy.x) - 0x4B400000;
+                    int tx1 = __float_as_int(fx.y) - 0x4B400000, ty1 = __float_as_int(fy.y) - 0x4B400000;
+                    tx0 = min(max(tx0, 0), A - 1); ty0 = min(max(ty0, 0), A - 1);         // NEAREST, CLAMP_TO_EDGE
+                    tx1 = min(max(tx1, 0), A - 1); ty1 = min(max(ty1, 0), A - 1);
+                    const uint32_t u0 = __ldg(ism + (uint32_t)(ty0 * A + tx0));
+                    const uint32_t u1 = __ldg(ism + (uint32_t)(ty1 * A + tx1));
+                    // u16 -> float without the conversion pipe: 2^23 + u as bits, minus 2^23
+                    const float2 occ = add2(make_float2(__uint_as_float(0x4B000000u | u0), __uint_as_float(0x4B000000u | u1)), dup(-8388608.0f));
+                    t = fma2(occ, dup(50.0f / 65535.0f), t);                              // smoothstep(0.98, 1, 1 - (z - occ))
+                }
+                t.x = __saturatef(t.x); t.y = __saturatef(t.y);
+                g = mul2(g, mul2(mul2(t, t), fma2(t, dup(-2.0f), dup(3.0f))));            // :125-126
             }
-            t.x = __saturatef(t.x); t.y = __saturatef(t.y);
-            g = mul2(g, mul2(mul2(t, t), fma2(t, dup(-2.0f), dup(3.0f))));            // :125-126
+            g.x = m0[p] > 0.0f ? g.x : 0.0f; g.y = m1[p] > 0.0f ? g.y : 0.0f;
+            px[p].ar = fma2(dup(r3.x), g, px[p].ar);                                      // :129
+            px[p].ag = fma2(dup(r3.y), g, px[p].ag);
+            px[p].ab = fma2(dup(r3.z), g, px[p].ab);
         }
-        g.x = m0 > 0.0f ? g.x : 0.0f; g.y = m1 > 0.0f ? g.y : 0.0f;
-        px.ar = fma2(dup(r3.x), g, px.ar);                                            // :129
-        px.ag = fma2(dup(r3.y), g, px.ag);
-        px.ab = fma2(dup(r3.z), g, px.ab);
     }
 }
 
-template <int MODE, bool SHADOW, bool STATS, bool TEX>
-__global__ void __launch_bounds__(FG_THREADS, FG_MIN_BLOCKS) final_gather_kernel(const GatherArgs a) {
+template <int MODE, bool SHADOW, bool STATS, bool TEX, int NP>
+__global__ void __launch_bounds__(256 / (2 * NP)) final_gather_kernel(const GatherArgs a) {
+    constexpr int THREADS = 256 / (2 * NP);     // 256 pixels of one class per CTA, 2*NP pixels per thread
+    constexpr int NPX = 2 * NP;
     __shared__ float4 srec[FG_CHUNK * FG_REC_Q];
     __shared__ uint32_t s_slices;
 
@@ -123,17 +132,19 @@ __global__ void __launch_bounds__(FG_THREADS, FG_MIN_BLOCKS) final_gather_kernel
     const int L = a.N / 16;
     const int A = 64 * a.S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // class-tile pixel (i, j) in 16x16. A warp owns 8 columns x 4 rows (an 8x4 patch = 32x16 screen pixels);
+    // the 2*NP pixels of a thread are 4 rows apart. NP=1: 4 warps (2x2 quadrants). NP=2: 2 warps (8-column strips).
     const int pi = 8 * (warp & 1) + (lane & 7);
-    const int pj0 = 8 * (warp >> 1) + (lane >> 3);
+    const int pj0 = (NP == 1 ? 8 * (warp >> 1) : 0) + (lane >> 3);
 
     if (MODE == MLGI_CULL_CLUSTERED) { if (threadIdx.x == 0) s_slices = 0; __syncthreads(); }
 
-    float P[2][3], Nn[2][3];
-    int sx[2], sy[2], slice[2];
-    bool valid[2];
+    float P[NPX][3], Nn[NPX][3];
+    int sx[NPX], sy[NPX], slice[NPX];
+    bool valid[NPX];
     uint32_t my_slices = 0;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < NPX; k++) {
         const int x = tile_x * kTile + 4 * pi + cxo, y = tile_y * kTile + 4 * (pj0 + 4 * k) + cyo;
         sx[k] = x; sy[k] = y;
         valid[k] = x < a.W && y < a.H;
@@ -170,11 +181,15 @@ __global__ void __launch_bounds__(FG_THREADS, FG_MIN_BLOCKS) final_gather_kernel
             }
         }
     }
-    PixelPair px;
-    px.Px = make_float2(P[0][0], P[1][0]); px.Py = make_float2(P[0][1], P[1][1]); px.Pz = make_float2(P[0][2], P[1][2]);
-    px.Nx = make_float2(Nn[0][0], Nn[1][0]); px.Ny = make_float2(Nn[0][1], Nn[1][1]); px.Nz = make_float2(Nn[0][2], Nn[1][2]);
-    px.ar = px.ag = px.ab = make_float2(0.0f, 0.0f);
-    px.valid0 = valid[0]; px.valid1 = valid[1]; px.slice0 = slice[0]; px.slice1 = slice[1];
+    PixelPair px[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        const int k0 = 2 * p, k1 = 2 * p + 1;
+        px[p].Px = make_float2(P[k0][0], P[k1][0]); px[p].Py = make_float2(P[k0][1], P[k1][1]); px[p].Pz = make_float2(P[k0][2], P[k1][2]);
+        px[p].Nx = make_float2(Nn[k0][0], Nn[k1][0]); px[p].Ny = make_float2(Nn[k0][1], Nn[k1][1]); px[p].Nz = make_float2(Nn[k0][2], Nn[k1][2]);
+        px[p].ar = px[p].ag = px[p].ab = make_float2(0.0f, 0.0f);
+        px[p].valid0 = valid[k0]; px[p].valid1 = valid[k1]; px[p].slice0 = slice[k0]; px[p].slice1 = slice[k1];
+    }
 
     uint32_t slices = 1u;
     if (MODE == MLGI_CULL_CLUSTERED) {
@@ -202,19 +217,23 @@ __global__ void __launch_bounds__(FG_THREADS, FG_MIN_BLOCKS) final_gather_kernel
             sub = a.lists.lists + ((size_t)tile * 16 + cls) * (L + 1);
             count = (int)sub[0] - 1;
         }
-        const bool act0 = px.valid0 && (MODE != MLGI_CULL_CLUSTERED || px.slice0 == s);
-        const bool act1 = px.valid1 && (MODE != MLGI_CULL_CLUSTERED || px.slice1 == s);
-        Normal2 N;   // a zero normal makes b == 0, i.e. "not lit", for pixels outside the viewport / other slices
-        N.x = make_float2(act0 ? px.Nx.x : 0.0f, act1 ? px.Nx.y : 0.0f);
-        N.y = make_float2(act0 ? px.Ny.x : 0.0f, act1 ? px.Ny.y : 0.0f);
-        N.z = make_float2(act0 ? px.Nz.x : 0.0f, act1 ? px.Nz.y : 0.0f);
-        const int nact = (act0 ? 1 : 0) + (act1 ? 1 : 0);
+        Normal2 N[NP];   // a zero normal makes b == 0, i.e. "not lit", for pixels outside the viewport / other slices
+        int nact = 0;
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const bool act0 = px[p].valid0 && (MODE != MLGI_CULL_CLUSTERED || px[p].slice0 == s);
+            const bool act1 = px[p].valid1 && (MODE != MLGI_CULL_CLUSTERED || px[p].slice1 == s);
+            N[p].x = make_float2(act0 ? px[p].Nx.x : 0.0f, act1 ? px[p].Nx.y : 0.0f);
+            N[p].y = make_float2(act0 ? px[p].Ny.x : 0.0f, act1 ? px[p].Ny.y : 0.0f);
+            N[p].z = make_float2(act0 ? px[p].Nz.x : 0.0f, act1 ? px[p].Nz.y : 0.0f);
+            nact += (act0 ? 1 : 0) + (act1 ? 1 : 0);
+        }
 
         for (int base = 0; base < count; base += FG_CHUNK) {
             const int n = min(FG_CHUNK, count - base);
             __syncthreads();                                    // previous chunk fully consumed
             // stage n records (5 float4 each) cooperatively
-            for (int q = threadIdx.x; q < n * 5; q += FG_THREADS) {
+            for (int q = threadIdx.x; q < n * 5; q += THREADS) {
                 const int e = q / 5, part = q - e * 5;
                 const uint32_t id = sub ? (uint32_t)sub[1 + base + e] : (uint32_t)(cls * L + base + e);   // :98
                 srec[q] = __ldg(&a.records[id].r[part]);
@@ -222,16 +241,17 @@ __global__ void __launch_bounds__(FG_THREADS, FG_MIN_BLOCKS) final_gather_kernel
             __syncthreads();
 #pragma unroll 2
             for (int e = 0; e < n; e++)                         // :97
-                shade_vpl<SHADOW, STATS, TEX>(px, srec + e * FG_REC_Q, a.ism, a.ism_tex, A, kz, a.clampv, N, nact, listed, lit);
+                shade_vpl<SHADOW, STATS, TEX, NP>(px, srec + e * FG_REC_Q, a.ism, a.ism_tex, A, kz, a.clampv, N, nact, listed, lit);
         }
     }
 
     // ---- epilogue: result = acc * giIntensityFactor / vplCount * 16  (:132) ----
     const int PW = (a.W + 3) >> 2, PH = (a.H + 3) >> 2;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < NPX; k++) {
         if (!valid[k]) continue;
-        const float r = k ? px.ar.y : px.ar.x, g = k ? px.ag.y : px.ag.x, b = k ? px.ab.y : px.ab.x;
+        const PixelPair& pp = px[k >> 1];
+        const float r = (k & 1) ? pp.ar.y : pp.ar.x, g = (k & 1) ? pp.ag.y : pp.ag.x, b = (k & 1) ? pp.ab.y : pp.ab.x;
         const float4 o = make_float4(r * a.giScale, g * a.giScale, b * a.giScale, 0.0f);
         if (a.out_raster) a.out_raster[(size_t)sy[k] * a.W + sx[k]] = o;
         if (a.out_planar) a.out_planar[((size_t)(cls - a.planar_class0) * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = o;
@@ -251,11 +271,12 @@ static void launch_fg_mode(const GatherArgs& a, dim3 grid, cudaStream_t st) {
     const bool sh = a.enable_shadowing != 0, stt = a.stats != nullptr;
     const bool tex = sh && a.ism_tex != 0;      // the ISM is fetched through the texture unit whenever a texture object exists
     if (stt) {                                   // counting variant (work counters for the roofline accounting)
-        if (sh) final_gather_kernel<MODE, true, true, false><<<grid, FG_THREADS, 0, st>>>(a);
-        else final_gather_kernel<MODE, false, true, false><<<grid, FG_THREADS, 0, st>>>(a);
-    } else if (!sh) final_gather_kernel<MODE, false, false, false><<<grid, FG_THREADS, 0, st>>>(a);
-    else if (tex) final_gather_kernel<MODE, true, false, true><<<grid, FG_THREADS, 0, st>>>(a);
-    else final_gather_kernel<MODE, true, false, false><<<grid, FG_THREADS, 0, st>>>(a);
+        if (sh) final_gather_kernel<MODE, true, true, false, 1><<<grid, 128, 0, st>>>(a);
+        else final_gather_kernel<MODE, false, true, false, 1><<<grid, 128, 0, st>>>(a);
+    } else if (!sh) final_gather_kernel<MODE, false, false, false, 1><<<grid, 128, 0, st>>>(a);
+    else if (!tex) final_gather_kernel<MODE, true, false, false, 1><<<grid, 128, 0, st>>>(a);
+    else if (a.pairs_per_thread == 2) final_gather_kernel<MODE, true, false, true, 2><<<grid, 64, 0, st>>>(a);
+    else final_gather_kernel<MODE, true, false, true, 1><<<grid, 128, 0, st>>>(a);
 }
 
 int launch_final_gather(const GatherArgs& a, cudaStream_t st) {
