@@ -100,6 +100,8 @@ struct mlgi_ctx {
     float* st_depth = nullptr; uint32_t* st_normal = nullptr;
     // stage bookkeeping
     bool have_vpl = false, have_points = false, have_atlas = false, have_ism = false, have_clustered = false, have_tiled = false, have_gi = false;
+    cudaStream_t side = nullptr;          // culling runs beside the ISM build (both only depend on the VPL stage)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[T_COUNT][2];
     bool ev_used[T_COUNT];
     bool events_created = false;
@@ -265,6 +267,9 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     if (e != cudaSuccess) { fail(nullptr, MLGI_E_CUDA, "init: %s", cudaGetErrorString(e)); mlgi_destroy(ctx); return MLGI_E_CUDA; }
     for (int i = 0; i < T_COUNT; i++) { cudaEventCreate(&ctx->ev[i][0]); cudaEventCreate(&ctx->ev[i][1]); }
     ctx->events_created = true;
+    cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) ctx->use_texture = strcmp(e2, "ldg") != 0;   // A/B switch: tex (default) | ldg
     if (const char* e3 = getenv("MLGI_FG_PAIRS")) ctx->fg_pairs = atoi(e3) == 2 ? 2 : 1;         // A/B switch: pixels per thread / 2
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
@@ -276,6 +281,9 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ism_tex) cudaDestroyTextureObject(ctx->ism_tex);
     if (ctx->override_tex) cudaDestroyTextureObject(ctx->override_tex);
     for (void* p : ctx->allocs) cudaFree(p);
@@ -553,11 +561,22 @@ MLGI_API int mlgi_frame(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* l
     if (!ctx) return MLGI_E_INVALID;
     int rc;
     if ((rc = mlgi_vpl_process(ctx, rsm, light, p, stream))) return rc;          // GIStage.cpp:373-376
+    // The reference runs ISM build and culling back to back on one GL queue (GIStage.cpp:378-403); they only share
+    // the VPL buffer as input, so culling is forked onto a side stream and joined before gathering.
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fork = ctx->side != nullptr && p->cull_mode != MLGI_CULL_NONE;
+    if (fork) {
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        void* cs = (void*)ctx->side;
+        if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, gb, cam, p, cs))) return rc; }   // :392-403
+        else { if ((rc = mlgi_cull_tiled(ctx, gb, cam, p, cs))) return rc; }
+        CK(cudaEventRecord(ctx->ev_join, ctx->side));
+    }
     if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;                  // :378-389 ISM render
     if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;                         //          ISM CS
     if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;             //          pull / push
-    if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, gb, cam, p, stream))) return rc; }   // :392-403
-    else if (p->cull_mode == MLGI_CULL_TILED) { if ((rc = mlgi_cull_tiled(ctx, gb, cam, p, stream))) return rc; }
+    if (fork) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     return mlgi_final_gather(ctx, gb, cam, nullptr, p, stream);                   // :405-408
 }
 

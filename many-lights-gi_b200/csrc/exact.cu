@@ -779,7 +779,6 @@ __device__ __forceinline__ void build_sublist(float3 my_corner, const VplRecord*
 #pragma unroll
             for (int j = 0; j < 8; j++) {                          // :109-114 `found = found || ...` is order independent
                 found = found || (dot3(add3(corners[j], np), vn) >= 0.0f);
-                if (__all_sync(__activemask(), found)) break;      // most VPLs pass at the first corner
             }
         }
         found = found && t < L;
@@ -832,19 +831,25 @@ int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_
     return 1;
 }
 
-// a8: one CTA per 64x64 tile: depth bounds -> 8 corners -> 16 class sub-lists (2 per warp)
+// a8: one CTA per 64x64 tile: depth bounds -> 8 corners -> bounding sphere -> 16 class sub-lists (2 per warp).
+// A VPL is kept iff the sphere reaches its positive half-space: one exact test per VPL.
 __global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict__ depth, int W, int H, const VplRecord* __restrict__ records,
                                                          int N, Mat4 inv_vp, int class_lo, int class_hi, uint16_t* __restrict__ lists) {
     __shared__ float smin[8], smax[8];
     __shared__ float3 scorner[8];
+    __shared__ float4 ssphere;
     const int bx = blockIdx.x, by = blockIdx.y;
     float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
-    for (int p = threadIdx.x; p < kTile * kTile; p += 256) {
-        int x = bx * kTile + (p % kTile), y = by * kTile + (p / kTile);
-        if (x < W && y < H) {
-            float d = depth[(size_t)y * W + x];
-            dmin = fminf(dmin, d); dmax = fmaxf(dmax, d);
+    {   // 16 independent (predicated) loads per thread, all in flight before the first compare
+        float dv[kTile * kTile / 256];
+#pragma unroll
+        for (int q = 0; q < kTile * kTile / 256; q++) {
+            const int p = threadIdx.x + q * 256;
+            const int x = bx * kTile + (p % kTile), y = by * kTile + (p / kTile);
+            dv[q] = (x < W && y < H) ? __ldg(depth + (size_t)y * W + x) : __int_as_float(0x7fc00000);   // NaN: ignored by fmin/fmax
         }
+#pragma unroll
+        for (int q = 0; q < kTile * kTile / 256; q++) { dmin = fminf(dmin, dv[q]); dmax = fmaxf(dmax, dv[q]); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -867,11 +872,44 @@ __global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict
         scorner[j] = unproject_corner(inv_vp, cx, cy, cz);
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        const float3* c = scorner;
+        float3 centre = mul3s(add3(add3(add3(c[0], c[1]), add3(c[2], c[3])), add3(add3(c[4], c[5]), add3(c[6], c[7]))), 0.125f);
+        float radius = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) radius = gmax(radius, len3(sub3(c[i], centre)));
+        radius *= 1.01f;
+        ssphere = make_float4(centre.x, centre.y, centre.z, radius);
+    }
+    __syncthreads();
+    const float3 centre = f3(ssphere.x, ssphere.y, ssphere.z);
+    const float nradius = -ssphere.w;
     const int L = N / 16;
     const size_t tile = (size_t)by * gridDim.x + bx;
-    float3 corner = scorner[lane & 7];
-    for (int k = class_lo + warp; k < class_hi; k += 8)
-        build_sublist(corner, records, L, k, lists + (tile * 16 + k) * (L + 1));
+    for (int k = class_lo + warp; k < class_hi; k += 8) {
+        uint16_t* sub = lists + (tile * 16 + k) * (L + 1);
+        uint32_t counter = 1;
+        constexpr int G = 4;                                  // chunks of 32 VPLs in flight per warp (ILP over the record loads)
+        for (int base = 0; base < L; base += 32 * G) {
+            float4 r0[G]; float2 r1[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int t = base + 32 * g + lane;
+                const uint32_t id = (uint32_t)(k * L + (t < L ? t : 0));
+                r0[g] = __ldg(&records[id].r[0]);                                         // (-pos, nrm.x); centre - p == centre + (-p)
+                r1[g] = __ldg(reinterpret_cast<const float2*>(&records[id].r[1]));
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int t = base + 32 * g + lane;
+                const bool found = t < L && dot3(add3(centre, f3(r0[g].x, r0[g].y, r0[g].z)), f3(r0[g].w, r1[g].x, r1[g].y)) >= nradius;
+                const unsigned bal = __ballot_sync(FULL, found);
+                if (found) sub[counter + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(k * L + t);
+                counter += __popc(bal);
+            }
+        }
+        if (lane == 0) sub[0] = (uint16_t)counter;
+    }
 }
 
 int launch_cull_tiled(const float* depth, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp, int class_lo,

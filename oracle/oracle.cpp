@@ -712,11 +712,13 @@ ORC_API void orc_light_lists(const float* packed_vpl, int N, const uint32_t* com
 }
 
 // =====================================================================================
-// a8: tiled variant (not in the reference snapshot; spec = SURVEY.md Appendix A.8)
+// a8: tiled variant (not in the reference snapshot; spec = DESIGN.md section 4, refining SURVEY.md A.8)
 //   block = tile x tile px (the product uses 64: one gathering CTA = one class of one 64x64
-//   tile); bounds = block rect x [min,max] window depth over in-image pixels;
-//   8 proper corners; same hemisphere test; lists [BY*BX][16][L+1], slot0 = 1+count.
-// =====================================================================================
+//   tile); bounds = block rect x [min,max] window depth over in-image pixels, 8 proper corners
+//   unprojected with inverse(P*V); the corners are enclosed in a sphere (centre = mean, radius = max
+//   distance * 1.01) and a VPL is kept iff the sphere reaches its positive half-space:
+//   dot(centre - p, n) >= -radius  (the hemisphere rule of light_lists.comp:108-114 on a bounding sphere:
+//   one test instead of eight, conservative). Lists [BY*BX][16][L+1], slot0 = 1+count.
 ORC_API void orc_cull_tiled(const float* depth, int W, int H, const float* packed_vpl, int N,
                             const float* view, const float* proj, int tile, uint16_t* lists) {
     mat4 P(proj), V(view);
@@ -743,6 +745,10 @@ ORC_API void orc_cull_tiled(const float* depth, int W, int H, const float* packe
             v = inv * v;
             corners[i] = v.xyz() / v.w;
         }
+        vec3 centre = (((corners[0] + corners[1]) + (corners[2] + corners[3])) + ((corners[4] + corners[5]) + (corners[6] + corners[7]))) * 0.125f;
+        float radius = 0.0f;
+        for (int i = 0; i < 8; i++) radius = max(radius, length(corners[i] - centre));
+        radius *= 1.01f;   // covers |n| up to 1.01 (10-bit normals are not unit) and the rounding of the centre
         for (int k = 0; k < 16; k++) {
             uint16_t* sub = lists + ((size_t)b * 16 + k) * (L + 1);
             uint counter = 1;
@@ -751,9 +757,7 @@ ORC_API void orc_cull_tiled(const float* depth, int W, int H, const float* packe
                 const float* pv = packed_vpl + 4 * (size_t)vplID;
                 vec3 vp(pv[0], pv[1], pv[2]);
                 vec3 vplNormal = unpack3SNFromFloat(pv[3]);
-                bool found = false;
-                for (int j = 0; j < 8; j++) found = found || (dot(corners[j] - vp, vplNormal) >= 0.0f);
-                if (found) sub[counter++] = (uint16_t)vplID;
+                if (dot(centre - vp, vplNormal) >= -radius) sub[counter++] = (uint16_t)vplID;
             }
             sub[0] = (uint16_t)counter;
         }
