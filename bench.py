@@ -232,7 +232,9 @@ def main():
              normal=up(wl.normal), verts=up(sc.vertices), normals=up(sc.normals), indices=up(sc.indices), prim=up(sc.prim_id))
     per = 16 // world
     lo, hi = rank * per, (rank + 1) * per
-    ctx = mlgi.Context(W, H, N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 23, device=local, class_lo=lo, class_hi=hi)
+    # gi_packed: besides the fp32 image the gathering kernel emits the reference's giBuffer format (GL_R11F_G11F_B10F,
+    # GIStage.cpp:470); that is what crosses NVLink (multi-GPU) and PCIe (end-to-end call)
+    ctx = mlgi.Context(W, H, N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 23, device=local, class_lo=lo, class_hi=hi, gi_packed=True)
     params = mlgi.default_params(N)
     params.cull_mode = mlgi.CULL_TILED if args.cull == "tiled" else mlgi.CULL_CLUSTERED
     rsm = mlgi.make_rsm(d["rsm_diffuse"], d["rsm_normal"], d["rsm_depth"])
@@ -243,7 +245,7 @@ def main():
     PH, PW = (H + 3) // 4, (W + 3) // 4
     planar = None
     if world > 1:
-        planar = torch.zeros((16, PH, PW, 4), dtype=torch.float32, device=dev)
+        planar = torch.zeros((16, PH, PW), dtype=torch.int32, device=dev)      # R11F_G11F_B10F class planes
         ctx.bind_planar_output(planar)
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -304,16 +306,16 @@ def main():
     if not args.no_e2e:
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
-        host_gi = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        host_gi = torch.empty((H, W), dtype=torch.int32).pin_memory()          # R11F_G11F_B10F
         hr, hg = mlgi.make_rsm(h[0], h[1], h[2]), mlgi.make_gbuffer(h[3], h[4])
         ctx.bind_planar_output(None)     # the end-to-end call returns this rank's raster pixels to the host
         n_e2e = max(5, min(args.steps, 50))
         for _ in range(3):
-            ctx.frame_host(hr, light, mesh, hg, cam, params, host_gi=host_gi, stream=stream)
+            ctx.frame_host_packed(hr, light, mesh, hg, cam, params, host_gi_packed=host_gi, stream=stream)
         barrier()
         t0 = time.time()
         for _ in range(n_e2e):
-            ctx.frame_host(hr, light, mesh, hg, cam, params, host_gi=host_gi, stream=stream)
+            ctx.frame_host_packed(hr, light, mesh, hg, cam, params, host_gi_packed=host_gi, stream=stream)
         barrier()
         dt = (time.time() - t0) / n_e2e
         if world > 1:
@@ -323,7 +325,7 @@ def main():
         h2d = sum(x.numel() * x.element_size() for x in h)
         e2e = {"value": pairs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_gi.numel() * 4,
                "ms_per_step": dt * 1e3, "steps": n_e2e,
-               "call": "mlgi_frame_host (pinned host RSM + G-buffer in, fp32 RGBA GI image out, stream sync)"}
+               "call": "mlgi_frame_host_packed (pinned host RSM + G-buffer in, GL_R11F_G11F_B10F GI image out = the reference's giBuffer format, stream sync)"}
         if planar is not None:
             ctx.bind_planar_output(planar)
 

@@ -62,6 +62,8 @@ typedef struct {
     int max_points;      /* capacity of the point buffer (reference: 2^23, ImperfectShadowmap.cpp:95) */
     int class_lo, class_hi; /* interleave classes [lo,hi) owned by this ctx; 0,16 = all (multi-GPU shard) */
     int enable_timers;   /* record per-stage cudaEvents (PerfCounter.cpp:50-76 scope names) */
+    int gi_packed;       /* 1: gathering also emits the reference's giBuffer format GL_R11F_G11F_B10F (GIStage.cpp:470)
+                            into MLGI_BUF_GI_PACKED, and the multi-GPU exchange buffer is packed uint32 */
 } mlgi_config;
 
 /* Tunables; names and defaults mirror GIStage (GIStage.h:84-100, GIStage.cpp:215-232). */
@@ -128,6 +130,7 @@ typedef enum {
     MLGI_BUF_GI_PLANAR,            /* [class_hi-class_lo][ceil(H/4)][ceil(W/4)] x 4 float, written when the ctx owns a strict
                                       subset of the classes and no exchange buffer is bound (multi-GPU layout) */
     MLGI_BUF_GI_BLUR,              /* width*height x 4 float                    GIStage giBlurFinalBuffer */
+    MLGI_BUF_GI_PACKED,            /* width*height x uint32 R11F_G11F_B10F (r in bits 0-10), only with cfg.gi_packed */
     MLGI_BUF_COUNT
 } mlgi_buffer_id;
 
@@ -175,6 +178,12 @@ MLGI_API int mlgi_frame_host(mlgi_ctx*, const mlgi_rsm* host_rsm, const mlgi_cam
                              const mlgi_gbuffer* host_gbuffer, const mlgi_camera* cam, const mlgi_params*,
                              float* host_gi, void* stream);
 
+/* Same as mlgi_frame_host but the image comes back in the reference's own giBuffer format (GL_R11F_G11F_B10F,
+ * GIStage.cpp:470): width*height uint32. Needs cfg.gi_packed. A quarter of the device->host bytes. */
+MLGI_API int mlgi_frame_host_packed(mlgi_ctx*, const mlgi_rsm* host_rsm, const mlgi_camera* light, const mlgi_mesh* dev_mesh,
+                                    const mlgi_gbuffer* host_gbuffer, const mlgi_camera* cam, const mlgi_params*,
+                                    uint32_t* host_gi_packed, void* stream);
+
 /* inspection */
 MLGI_API int mlgi_get_buffer(mlgi_ctx*, int buffer_id, void** dev_ptr, size_t* bytes);
 /* synchronous device->host copy of `bytes` bytes of a ctx buffer starting at byte `offset` (test/debug path) */
@@ -189,10 +198,11 @@ MLGI_API float mlgi_measure_fp32_peak_tflops(mlgi_ctx*);
 
 /* multi-GPU exchange: the gathering kernel writes the class-planar planes of the classes this
  * ctx owns straight into a caller-owned [16][ceil(H/4)][ceil(W/4)] x 4 float device buffer (plane c at
- * c*PH*PW), so one in-place all-gather over ranks assembles the image; NULL unbinds. */
-MLGI_API int mlgi_bind_planar_output(mlgi_ctx*, float* dev_planar16);
+ * c*PH*PW), so one in-place all-gather over ranks assembles the image; NULL unbinds. With cfg.gi_packed the
+ * buffer holds one uint32 (R11F_G11F_B10F) per pixel instead of 4 floats. */
+MLGI_API int mlgi_bind_planar_output(mlgi_ctx*, void* dev_planar16);
 /* consumer-side de-interleave of a complete planar image into raster order (dev_raster NULL = ctx GI buffer) */
-MLGI_API int mlgi_planar_to_raster(mlgi_ctx*, const float* dev_planar16, float* dev_raster, void* stream);
+MLGI_API int mlgi_planar_to_raster(mlgi_ctx*, const void* dev_planar16, float* dev_raster, void* stream);
 
 /* per-stage timers (names of PerfCounter scopes, GIStage.cpp:368-411): fills up to `cap`
  * entries, returns the count. Synchronises. */

@@ -88,6 +88,7 @@ struct mlgi_ctx {
     uint32_t* atlas = nullptr; uint16_t* ism = nullptr;
     uint32_t* tile_masks = nullptr; uint32_t* compact_ids = nullptr; uint16_t* light_list_ids = nullptr;
     uint16_t* light_lists = nullptr; uint16_t* tile_lists = nullptr;
+    uint32_t* gi_packed = nullptr;
     float4* gi = nullptr; float4* gi_planar = nullptr; float4* gi_tmp = nullptr; float4* gi_blur = nullptr;
     unsigned long long* stats = nullptr;
     cudaTextureObject_t ism_tex = 0;      // ctx ISM atlas as an R16-unorm point-sampled texture
@@ -254,6 +255,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     ALLOC(tile_lists, (size_t)ctx->TX * ctx->TY * 16 * (ctx->L + 1));
     ALLOC(gi, WH); ALLOC(gi_planar, (size_t)(cfg->class_hi - cfg->class_lo) * PW * PH); ALLOC(gi_tmp, WH); ALLOC(gi_blur, WH);
     ALLOC(stats, 2);
+    if (cfg->gi_packed) ALLOC(gi_packed, WH);
     ALLOC(st_rsm_diffuse, RS); ALLOC(st_rsm_normal, RS); ALLOC(st_rsm_depth, RS); ALLOC(st_depth, WH); ALLOC(st_normal, WH);
 #undef ALLOC
     // VPLProcessor.cpp:58-65: fixed-seed shuffle table (libstdc++ std::shuffle; Q13)
@@ -473,8 +475,13 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     // consumer (mlgi_planar_to_raster) after the all-gather; otherwise the raster image is written directly, plus
     // the ctx-owned planar sub-image when this ctx owns only some of the classes.
     const bool partial = ctx->cfg.class_lo != 0 || ctx->cfg.class_hi != 16;
-    if (ctx->planar_ext) { a.out_raster = nullptr; a.out_planar = ctx->planar_ext; a.planar_class0 = 0; }
-    else { a.out_raster = ctx->gi; a.out_planar = partial ? ctx->gi_planar : nullptr; a.planar_class0 = ctx->cfg.class_lo; }
+    if (ctx->planar_ext) {
+        a.out_raster = nullptr; a.planar_class0 = 0;
+        if (ctx->cfg.gi_packed) a.out_planar_packed = (uint32_t*)ctx->planar_ext; else a.out_planar = ctx->planar_ext;
+    } else {
+        a.out_raster = ctx->gi; a.out_planar = partial ? ctx->gi_planar : nullptr; a.planar_class0 = ctx->cfg.class_lo;
+        a.out_packed = ctx->gi_packed;          // null unless cfg.gi_packed
+    }
     a.stats = nullptr;
     return MLGI_OK;
 }
@@ -503,7 +510,7 @@ MLGI_API int mlgi_gather_stats(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi
     if (rc) return rc;
     a.stats = ctx->stats;
     a.out_raster = nullptr;     // counting variant: same loop, counters instead of stores
-    a.out_planar = nullptr;
+    a.out_planar = nullptr; a.out_packed = nullptr; a.out_planar_packed = nullptr;
     CK(cudaMemset(ctx->stats, 0, 2 * sizeof(unsigned long long)));
     ctx->launches += launch_final_gather(a, 0);
     unsigned long long h[2];
@@ -514,17 +521,19 @@ MLGI_API int mlgi_gather_stats(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi
     return MLGI_OK;
 }
 
-MLGI_API int mlgi_bind_planar_output(mlgi_ctx* ctx, float* dev_planar16) {
+MLGI_API int mlgi_bind_planar_output(mlgi_ctx* ctx, void* dev_planar16) {
     if (!ctx) return MLGI_E_INVALID;
     ctx->planar_ext = (float4*)dev_planar16;
     return MLGI_OK;
 }
 
-MLGI_API int mlgi_planar_to_raster(mlgi_ctx* ctx, const float* dev_planar16, float* dev_raster, void* stream) {
+MLGI_API int mlgi_planar_to_raster(mlgi_ctx* ctx, const void* dev_planar16, float* dev_raster, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
     if (!dev_planar16) return fail(ctx, MLGI_E_INVALID, "planar buffer is NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    ctx->launches += launch_planar_to_raster((const float4*)dev_planar16, ctx->cfg.width, ctx->cfg.height, 0, 16,
+    if (ctx->cfg.gi_packed) ctx->launches += launch_planar_packed_to_raster((const uint32_t*)dev_planar16, ctx->cfg.width, ctx->cfg.height,
+                                                                           ctx->gi_packed, dev_raster ? (float4*)dev_raster : ctx->gi, st);
+    else ctx->launches += launch_planar_to_raster((const float4*)dev_planar16, ctx->cfg.width, ctx->cfg.height, 0, 16,
                                              dev_raster ? (float4*)dev_raster : ctx->gi, st);
     CK(cudaGetLastError());
     ctx->have_gi = true;
@@ -580,30 +589,55 @@ MLGI_API int mlgi_frame(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* l
     return mlgi_final_gather(ctx, gb, cam, nullptr, p, stream);                   // :405-408
 }
 
-MLGI_API int mlgi_frame_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
-                             const mlgi_camera* cam, const mlgi_params* p, float* host_gi, void* stream) {
+static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
+                           const mlgi_camera* cam, const mlgi_params* p, void* host_out, bool packed, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
     if (!hr || !hg || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer is NULL");
+    if (packed && !ctx->gi_packed) return fail(ctx, MLGI_E_INVALID, "mlgi_frame_host_packed needs cfg.gi_packed");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t RS = (size_t)ctx->cfg.rsm_width * ctx->cfg.rsm_height, WH = (size_t)ctx->cfg.width * ctx->cfg.height;
+    // The RSM (3 MB) goes first on the compute stream; the camera G-buffer (8 B/pixel) is uploaded on the side stream
+    // while VPL build, point generation, splat and pull-push (which do not read it) already run.
     {
         StageTimer t(ctx, T_H2D, st);
         CK(cudaMemcpyAsync(ctx->st_rsm_diffuse, hr->diffuse, RS * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(ctx->st_rsm_normal, hr->face_normal, RS * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(ctx->st_rsm_depth, hr->depth, RS * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->st_depth, hg->depth, WH * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->st_normal, hg->face_normal, WH * 4, cudaMemcpyHostToDevice, st));
     }
     mlgi_rsm dr = {ctx->st_rsm_diffuse, ctx->st_rsm_normal, ctx->st_rsm_depth};
     mlgi_gbuffer dg = {ctx->st_depth, ctx->st_normal};
-    int rc = mlgi_frame(ctx, &dr, light, mesh, &dg, cam, p, stream);
-    if (rc) return rc;
-    if (host_gi) {
+    int rc;
+    if ((rc = mlgi_vpl_process(ctx, &dr, light, p, stream))) return rc;
+    CK(cudaEventRecord(ctx->ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));        // also orders the upload after the previous frame's readers
+    CK(cudaMemcpyAsync(ctx->st_depth, hg->depth, WH * 4, cudaMemcpyHostToDevice, ctx->side));
+    CK(cudaMemcpyAsync(ctx->st_normal, hg->face_normal, WH * 4, cudaMemcpyHostToDevice, ctx->side));
+    void* cs = (void*)ctx->side;
+    if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, &dg, cam, p, cs))) return rc; }
+    else if (p->cull_mode == MLGI_CULL_TILED) { if ((rc = mlgi_cull_tiled(ctx, &dg, cam, p, cs))) return rc; }
+    CK(cudaEventRecord(ctx->ev_join, ctx->side));
+    if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;
+    if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;
+    if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;
+    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if ((rc = mlgi_final_gather(ctx, &dg, cam, nullptr, p, stream))) return rc;
+    if (host_out) {
         StageTimer t(ctx, T_D2H, st);
-        CK(cudaMemcpyAsync(host_gi, ctx->gi, WH * sizeof(float4), cudaMemcpyDeviceToHost, st));
+        if (packed) CK(cudaMemcpyAsync(host_out, ctx->gi_packed, WH * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        else CK(cudaMemcpyAsync(host_out, ctx->gi, WH * sizeof(float4), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
     return MLGI_OK;
+}
+
+MLGI_API int mlgi_frame_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
+                             const mlgi_camera* cam, const mlgi_params* p, float* host_gi, void* stream) {
+    return frame_host_impl(ctx, hr, light, mesh, hg, cam, p, host_gi, false, stream);
+}
+
+MLGI_API int mlgi_frame_host_packed(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
+                                    const mlgi_camera* cam, const mlgi_params* p, uint32_t* host_gi_packed, void* stream) {
+    return frame_host_impl(ctx, hr, light, mesh, hg, cam, p, host_gi_packed, true, stream);
 }
 
 // ------------------------------------------------------------------------------------- inspection
@@ -629,6 +663,9 @@ MLGI_API int mlgi_get_buffer(mlgi_ctx* ctx, int id, void** dev_ptr, size_t* byte
         case MLGI_BUF_GI: *dev_ptr = ctx->gi; *bytes = WH * 16; break;
         case MLGI_BUF_GI_PLANAR: *dev_ptr = ctx->gi_planar; *bytes = (size_t)(ctx->cfg.class_hi - ctx->cfg.class_lo) * PW * PH * 16; break;
         case MLGI_BUF_GI_BLUR: *dev_ptr = ctx->gi_blur; *bytes = WH * 16; break;
+        case MLGI_BUF_GI_PACKED:
+            if (!ctx->gi_packed) return fail(ctx, MLGI_E_INVALID, "MLGI_BUF_GI_PACKED needs cfg.gi_packed");
+            *dev_ptr = ctx->gi_packed; *bytes = WH * 4; break;
         default: return fail(ctx, MLGI_E_INVALID, "unknown buffer id %d", id);
     }
     return MLGI_OK;

@@ -101,6 +101,49 @@ __device__ __forceinline__ float log_depth(float z, float A, float B) {
     float z_n = (1.0f / z * -B) - A;
     return (z_n + 1.0f) / 2.0f;
 }
+// fp32 -> unsigned small float (5-bit exponent, bias 15, MBITS mantissa bits, no sign), round to nearest even;
+// negative and -0 -> 0, NaN -> NaN, values above the largest finite clamp to it (GL 4.3 spec 2.3.4.3 / 2.3.4.4)
+template <int MBITS>
+__host__ __device__ inline uint32_t pack_ufloat(uint32_t x) {
+    const uint32_t max_finite = (30u << MBITS) | ((1u << MBITS) - 1u);
+    if (x & 0x80000000u) return ((x & 0x7FFFFFFFu) > 0x7F800000u) ? ((31u << MBITS) | 1u) : 0u;   // negative: 0 (NaN stays NaN)
+    const uint32_t e = x >> 23, m = x & 0x7FFFFFu;
+    if (e == 0xFF) return m ? ((31u << MBITS) | 1u) : (31u << MBITS);
+    const int eh = (int)e - 127 + 15;
+    if (eh >= 31) return max_finite;
+    uint32_t r;
+    if (eh <= 0) {                                   // subnormal result
+        if (eh < -MBITS) return 0u;
+        const uint32_t mm = m | 0x800000u;
+        const int shift = (23 - MBITS) + 1 - eh;     // >= 24 - MBITS
+        r = mm >> shift;
+        const uint32_t rem = mm & ((1u << shift) - 1u), half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (r & 1u))) r++;
+    } else {
+        const int shift = 23 - MBITS;
+        r = ((uint32_t)eh << MBITS) | (m >> shift);
+        const uint32_t rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (r & 1u))) r++;
+    }
+    return r > max_finite ? max_finite : r;
+}
+template <int MBITS>
+__host__ __device__ inline uint32_t unpack_ufloat_bits(uint32_t v) {   // returns fp32 bits
+    const uint32_t e = v >> MBITS, m = v & ((1u << MBITS) - 1u);
+    if (e == 0) {
+        if (m == 0) return 0u;
+        int sh = 0; uint32_t mm = m;
+        while (!(mm & (1u << MBITS))) { mm <<= 1; sh++; }
+        return ((uint32_t)(127 - 15 + 1 - sh) << 23) | ((mm & ((1u << MBITS) - 1u)) << (23 - MBITS));
+    }
+    if (e == 31) return 0x7F800000u | (m << (23 - MBITS));
+    return ((e - 15 + 127) << 23) | (m << (23 - MBITS));
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t pack_r11g11b10(float r, float g, float b) {
+    return pack_ufloat<6>(__float_as_uint(r)) | (pack_ufloat<6>(__float_as_uint(g)) << 11) | (pack_ufloat<5>(__float_as_uint(b)) << 22);
+}
+#endif
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------
@@ -149,6 +192,8 @@ struct GatherArgs {
     float4* out_raster;     // may be null
     float4* out_planar;     // may be null; plane of class c starts at (c - planar_class0) * PH * PW
     int planar_class0;
+    uint32_t* out_packed;          // may be null: R11F_G11F_B10F raster
+    uint32_t* out_planar_packed;   // may be null: R11F_G11F_B10F class planes
     unsigned long long* stats;  // null, or 2 counters (pairs listed / lit)
 };
 int launch_final_gather(const GatherArgs& a, cudaStream_t st);
@@ -156,6 +201,7 @@ int launch_gi_blur(const float4* gi, const float* depth, const uint32_t* face_no
                    float projB, float4* tmp, float4* out, cudaStream_t st);
 float measure_fp32_peak_tflops(cudaStream_t st);   // FFMA micro-benchmark: the FP32-pipe roofline denominator
 int launch_planar_to_raster(const float4* planar, int W, int H, int class_lo, int class_hi, float4* raster, cudaStream_t st);
+int launch_planar_packed_to_raster(const uint32_t* planar, int W, int H, uint32_t* raster_packed, float4* raster, cudaStream_t st);
 
 constexpr int kTile = 64;  // tiled-culling tile edge in pixels (one gathering CTA = one class of one tile)
 

@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(256 / (2 * NP)) final_gather_kernel(const Gath
         const float4 o = make_float4(r * a.giScale, g * a.giScale, b * a.giScale, 0.0f);
         if (a.out_raster) a.out_raster[(size_t)sy[k] * a.W + sx[k]] = o;
         if (a.out_planar) a.out_planar[((size_t)(cls - a.planar_class0) * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = o;
+        if (a.out_packed) a.out_packed[(size_t)sy[k] * a.W + sx[k]] = pack_r11g11b10(o.x, o.y, o.z);
+        if (a.out_planar_packed) a.out_planar_packed[((size_t)cls * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = pack_r11g11b10(o.x, o.y, o.z);
     }
     if (STATS) {
 #pragma unroll
@@ -300,6 +302,21 @@ __global__ void planar_to_raster_kernel(const float4* __restrict__ planar, int W
     if (cls < class_lo || cls >= class_hi) return;
     const int PW = (W + 3) >> 2, PH = (H + 3) >> 2;
     raster[(size_t)y * W + x] = planar[((size_t)(cls - class_lo) * PH + (y >> 2)) * PW + (x >> 2)];
+}
+__global__ void planar_packed_to_raster_kernel(const uint32_t* __restrict__ planar, int W, int H, uint32_t* __restrict__ raster_packed,
+                                               float4* __restrict__ raster) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const int cls = (x & 3) + 4 * (y & 3);
+    const int PW = (W + 3) >> 2, PH = (H + 3) >> 2;
+    const uint32_t v = planar[((size_t)cls * PH + (y >> 2)) * PW + (x >> 2)];
+    if (raster_packed) raster_packed[(size_t)y * W + x] = v;
+    if (raster) raster[(size_t)y * W + x] = make_float4(__uint_as_float(unpack_ufloat_bits<6>(v & 0x7FFu)), __uint_as_float(unpack_ufloat_bits<6>((v >> 11) & 0x7FFu)),
+                                                         __uint_as_float(unpack_ufloat_bits<5>(v >> 22)), 0.0f);
+}
+int launch_planar_packed_to_raster(const uint32_t* planar, int W, int H, uint32_t* raster_packed, float4* raster, cudaStream_t st) {
+    planar_packed_to_raster_kernel<<<dim3((W + 255) / 256, H), 256, 0, st>>>(planar, W, H, raster_packed, raster);
+    return 1;
 }
 int launch_planar_to_raster(const float4* planar, int W, int H, int class_lo, int class_hi, float4* raster, cudaStream_t st) {
     planar_to_raster_kernel<<<dim3((W + 255) / 256, H), 256, 0, st>>>(planar, W, H, class_lo, class_hi, raster);

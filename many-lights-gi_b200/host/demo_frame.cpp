@@ -60,7 +60,7 @@ int main(int argc, char** argv) {
 
     mlgi_config cfg = {};
     cfg.device = 0; cfg.width = W; cfg.height = H; cfg.vpl_count = N; cfg.rsm_width = RW; cfg.rsm_height = RH;
-    cfg.max_triangles = nt; cfg.max_points = 1 << 23; cfg.class_lo = 0; cfg.class_hi = 16; cfg.enable_timers = 1;
+    cfg.max_triangles = nt; cfg.max_points = 1 << 23; cfg.class_lo = 0; cfg.class_hi = 16; cfg.enable_timers = 1; cfg.gi_packed = 0;
     try {
         mlgi::GIStage gi(cfg);
         gi.depthBuffer = upload(depth); gi.faceNormalBuffer = upload(normal);

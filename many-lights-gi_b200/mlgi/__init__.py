@@ -18,7 +18,7 @@ CULL_CLUSTERED, CULL_TILED, CULL_NONE = 0, 1, 2
 
 (BUF_VPL, BUF_PACKED_VPL, BUF_SHUFFLE, BUF_POINTS, BUF_BUCKET_START, BUF_ATLAS, BUF_ISM,
  BUF_COMPACT_CLUSTER_IDS, BUF_LIGHT_LIST_IDS, BUF_LIGHT_LISTS, BUF_TILE_LISTS, BUF_NUM_USED_CLUSTERS,
- BUF_GI, BUF_GI_PLANAR, BUF_GI_BLUR, BUF_COUNT) = range(16)
+ BUF_GI, BUF_GI_PLANAR, BUF_GI_BLUR, BUF_GI_PACKED, BUF_COUNT) = range(17)
 
 E_INVALID, E_CUDA, E_NO_DEVICE, E_UNSUPPORTED, E_CAPACITY, E_ORDER = -1, -2, -3, -4, -5, -6
 
@@ -28,7 +28,7 @@ TILE = 64  # tiled-culling tile edge (csrc/common.cuh kTile)
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("vpl_count", C.c_int),
                 ("rsm_width", C.c_int), ("rsm_height", C.c_int), ("max_triangles", C.c_int), ("max_points", C.c_int),
-                ("class_lo", C.c_int), ("class_hi", C.c_int), ("enable_timers", C.c_int)]
+                ("class_lo", C.c_int), ("class_hi", C.c_int), ("enable_timers", C.c_int), ("gi_packed", C.c_int)]
 
 
 class Params(C.Structure):
@@ -71,7 +71,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "mlgi_version", "mlgi_default_params", "mlgi_create", "mlgi_destroy", "mlgi_last_error",
     "mlgi_vpl_process", "mlgi_ism_points", "mlgi_ism_set_points", "mlgi_ism_splat", "mlgi_ism_pullpush",
-    "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_frame", "mlgi_frame_host",
+    "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_frame", "mlgi_frame_host", "mlgi_frame_host_packed",
     "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
 ]
 
@@ -114,6 +114,7 @@ def load():
                                C.POINTER(Params), P]
     lib.mlgi_frame_host.argtypes = [P, C.POINTER(Rsm), C.POINTER(Camera), C.POINTER(Mesh), C.POINTER(GBuffer), C.POINTER(Camera),
                                     C.POINTER(Params), P, P]
+    lib.mlgi_frame_host_packed.argtypes = lib.mlgi_frame_host.argtypes
     lib.mlgi_get_buffer.argtypes = [P, C.c_int, C.POINTER(P), C.POINTER(C.c_size_t)]
     lib.mlgi_read_buffer.argtypes = [P, C.c_int, P, C.c_size_t, C.c_size_t]
     lib.mlgi_get_counts.argtypes = [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -164,10 +165,10 @@ class Context:
     """One mlgi_ctx (one GPU). Thin 1:1 wrapper; every method raises MlgiError on a non-zero status."""
 
     def __init__(self, width, height, vpl_count, rsm_width, rsm_height, max_triangles, max_points,
-                 device=0, class_lo=0, class_hi=16, enable_timers=False):
+                 device=0, class_lo=0, class_hi=16, enable_timers=False, gi_packed=False):
         self.lib = load()
         self.cfg = Config(device, width, height, vpl_count, rsm_width, rsm_height, max_triangles, max_points,
-                          class_lo, class_hi, int(enable_timers))
+                          class_lo, class_hi, int(enable_timers), int(gi_packed))
         self.h = C.c_void_p()
         rc = self.lib.mlgi_create(C.byref(self.cfg), C.byref(self.h))
         if rc != 0:
@@ -222,6 +223,10 @@ class Context:
     def frame_host(self, host_rsm, light, dev_mesh, host_gb, cam, params, host_gi=None, stream=None):
         self._ck(self.lib.mlgi_frame_host(self.h, C.byref(host_rsm), C.byref(light), C.byref(dev_mesh), C.byref(host_gb),
                                           C.byref(cam), C.byref(params), _ptr(host_gi), stream))
+
+    def frame_host_packed(self, host_rsm, light, dev_mesh, host_gb, cam, params, host_gi_packed=None, stream=None):
+        self._ck(self.lib.mlgi_frame_host_packed(self.h, C.byref(host_rsm), C.byref(light), C.byref(dev_mesh), C.byref(host_gb),
+                                                 C.byref(cam), C.byref(params), _ptr(host_gi_packed), stream))
 
     def buffer(self, buf_id):
         p = C.c_void_p()

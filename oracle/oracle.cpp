@@ -883,6 +883,42 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
 }
 
 // =====================================================================================
+// n2 ("next" row): GL_R11F_G11F_B10F, the reference's giBuffer format (GIStage.cpp:470, final_gathering.comp:14).
+// Unsigned small floats of the GL 4.3 spec, sections 2.3.4.3 (11 bit: 5e6m) and 2.3.4.4 (10 bit: 5e5m): bias 15,
+// negative -> 0, NaN -> NaN, +Inf -> Inf, finite values above the largest finite clamp to it, round to nearest even.
+// =====================================================================================
+static uint32_t to_ufloat(float f, int mbits) {
+    const uint32_t maxFinite = (30u << mbits) | ((1u << mbits) - 1u);
+    if (f != f) return (31u << mbits) | 1u;
+    if (!(f > 0.0f)) return 0u;
+    if (std::isinf(f)) return 31u << mbits;
+    int e;
+    float m = frexpf(f, &e);                    // f = m * 2^e, m in [0.5, 1)
+    int eh = e - 1 + 15;                        // exponent field if normal: f = (1 + frac) * 2^(eh-15)
+    double scaled;
+    if (eh >= 1) scaled = ldexp((double)m * 2.0 - 1.0, mbits);          // fraction * 2^mbits
+    else { scaled = ldexp((double)f, 14 + mbits); eh = 0; }              // subnormal: f / 2^-14 * 2^mbits
+    double r = std::nearbyint(scaled);                                     // default rounding mode: nearest even
+    uint32_t v = ((uint32_t)eh << mbits) + (uint32_t)r;                   // a carry out of the fraction bumps the exponent
+    return v > maxFinite ? maxFinite : v;
+}
+ORC_API void orc_pack_r11g11b10(const float* rgb, long long n, int stride, uint32_t* out) {
+    for (long long i = 0; i < n; i++)
+        out[i] = to_ufloat(rgb[i * stride], 6) | (to_ufloat(rgb[i * stride + 1], 6) << 11) | (to_ufloat(rgb[i * stride + 2], 5) << 22);
+}
+static float from_ufloat(uint32_t v, int mbits) {
+    uint32_t e = v >> mbits, m = v & ((1u << mbits) - 1u);
+    if (e == 31) return m ? NAN : INFINITY;
+    if (e == 0) return ldexpf((float)m, -14 - mbits);
+    return ldexpf(1.0f + (float)m / (float)(1u << mbits), (int)e - 15);
+}
+ORC_API void orc_unpack_r11g11b10(const uint32_t* in, long long n, float* rgb) {
+    for (long long i = 0; i < n; i++) {
+        rgb[3 * i] = from_ufloat(in[i] & 0x7FFu, 6); rgb[3 * i + 1] = from_ufloat((in[i] >> 11) & 0x7FFu, 6); rgb[3 * i + 2] = from_ufloat(in[i] >> 22, 5);
+    }
+}
+
+// =====================================================================================
 // n1 ("next" row): gi/gi_blur.frag:24-72, two passes (GIStage.cpp:308-344, :425-439)
 //   in/out: W*H*3 fp32. direction 0 = (1,0), 1 = (0,1). texelFetch outside the image is
 //   undefined in GL; here out-of-image taps are skipped (weight 0) -- documented choice.

@@ -51,6 +51,8 @@ def load():
         lib.orc_final_gather.argtypes = [P, P, C.c_int, C.c_int, P, C.c_int, P, C.c_int, P, P, P, P, C.c_float,
                                          C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          P, P, P, C.c_float, P]
+        lib.orc_pack_r11g11b10.argtypes = [P, C.c_longlong, C.c_int, P]
+        lib.orc_unpack_r11g11b10.argtypes = [P, C.c_longlong, P]
         lib.orc_gi_blur_pass.argtypes = [P, P, P, C.c_int, C.c_int, P, C.c_int, P]
         _lib = lib
     return _lib
@@ -209,4 +211,20 @@ def gi_blur(gi_rgb, depth, normal, proj):
     g = np.ascontiguousarray(gi_rgb, dtype=np.float32)
     load().orc_gi_blur_pass(_p(g), _p(depth), _p(normal), W, H, _p(pr), 0, _p(tmp))
     load().orc_gi_blur_pass(_p(tmp), _p(depth), _p(normal), W, H, _p(pr), 1, _p(out))
+    return out
+
+
+def pack_r11g11b10(rgb):
+    """rgb [...,3 or 4] fp32 -> uint32 GL_R11F_G11F_B10F"""
+    a = np.ascontiguousarray(rgb, dtype=np.float32)
+    n = a.size // a.shape[-1]
+    out = np.empty(a.shape[:-1], np.uint32)
+    load().orc_pack_r11g11b10(_p(a), n, a.shape[-1], _p(out))
+    return out
+
+
+def unpack_r11g11b10(packed):
+    a = np.ascontiguousarray(packed, dtype=np.uint32)
+    out = np.empty(a.shape + (3,), np.float32)
+    load().orc_unpack_r11g11b10(_p(a), a.size, _p(out))
     return out

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
 
 def test_struct_sizes_match_header():
     # field counts of the POD structs in include/mlgi.h
-    assert C.sizeof(mlgi.Config) == 11 * 4
+    assert C.sizeof(mlgi.Config) == 12 * 4
     assert C.sizeof(mlgi.Params) == 16 * 4
     assert C.sizeof(mlgi.Camera) == 32 * 4
     assert C.sizeof(mlgi.Timing) == 32

@@ -352,3 +352,40 @@ def test_timers_and_launch_count(case_small):
     assert listed == ref["listed"]
     assert abs(lit - ref["lit"]) <= 1e-4 * ref["lit"] + 8    # sign tests of ~0 values may flip under FMA
     g.close()
+
+
+def test_n2_packed_output_r11g11b10(case_small, case_mid):
+    """cfg.gi_packed: the packed image equals the oracle's packing of the fp32 image bit for bit, also through the
+    host entry point and through the packed multi-GPU exchange layout"""
+    torch = _torch()
+    import oracle_py as O
+    for case in (case_small, case_mid):
+        wl = case.wl
+        sc = wl.scene
+        g = Gpu(case)
+        g.ctx.close()
+        g.ctx = mlgi.Context(case.W, case.H, case.N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 22, gi_packed=True)
+        p = mlgi.default_params(case.N)
+        g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+        gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(case.H, case.W, 4)
+        packed = g.ctx.download(mlgi.BUF_GI_PACKED, np.uint32).reshape(case.H, case.W)
+        ref = O.pack_r11g11b10(gi)
+        assert np.array_equal(packed, ref)
+        # host entry point
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
+        host = torch.zeros((case.H, case.W), dtype=torch.int32).pin_memory()
+        g.ctx.frame_host_packed(mlgi.make_rsm(h[0], h[1], h[2]), g.light, g.mesh, mlgi.make_gbuffer(h[3], h[4]), g.cam, p, host_gi_packed=host)
+        assert np.array_equal(host.numpy().view(np.uint32), ref)
+        # packed exchange buffer + de-interleave
+        PH, PW = (case.H + 3) // 4, (case.W + 3) // 4
+        ext = torch.zeros((16, PH, PW), dtype=torch.int32, device="cuda:0")
+        g.ctx.bind_planar_output(ext)
+        g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+        raster = torch.zeros((case.H, case.W, 4), dtype=torch.float32, device="cuda:0")
+        g.ctx.planar_to_raster(ext, raster)
+        torch.cuda.synchronize()
+        assert np.array_equal(g.ctx.download(mlgi.BUF_GI_PACKED, np.uint32).reshape(case.H, case.W), ref)
+        assert np.array_equal(raster.cpu().numpy()[:, :, :3], O.unpack_r11g11b10(ref))
+        g.ctx.bind_planar_output(None)
+        g.close()

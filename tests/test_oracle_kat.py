@@ -114,3 +114,21 @@ def test_paraboloid_projection_stays_in_its_tile():
         assert tx / S - 1e-6 <= out[0] <= (tx + 1) / S + 1e-6
         assert ty / S - 1e-6 <= out[1] <= (ty + 1) / S + 1e-6
         assert out[2] >= 0  # in front of the VPL -> positive depth with preserveSign
+
+
+def test_r11g11b10_packing_kats():
+    """GL_R11F_G11F_B10F (GIStage.cpp:470): 5-bit exponent bias 15, 6/6/5 mantissa bits, r in the low bits"""
+    pk = lambda r, g, b: int(O.pack_r11g11b10(np.array([[r, g, b]], np.float32))[0])
+    assert pk(1.0, 0.0, 0.0) == 0x3C0 and pk(0.0, 1.0, 0.0) == 0x3C0 << 11 and pk(0.0, 0.0, 1.0) == 0x1E0 << 22
+    assert pk(0.5, 2.0, 0.25) == (0x380 | (0x400 << 11) | (0x1A0 << 22))
+    assert pk(65024.0, 1e9, 64512.0) == (0x7BF | (0x7BF << 11) | (0x3DF << 22))      # largest finite / clamp
+    assert pk(-1.0, -0.0, -np.inf) == 0
+    assert pk(np.inf, np.nan, 0.0) == (0x7C0 | (0x7C1 << 11))
+    assert pk(2.0 ** -20, 2.0 ** -21, 2.0 ** -19) == (1 | (0 << 11) | (1 << 22))      # smallest subnormals, tie to even -> 0
+    assert pk(1.0 + 1.0 / 128, 1.0 + 3.0 / 128, 1.0 + 1.0 / 64) == (0x3C0 | (0x3C2 << 11) | (0x1E0 << 22))   # ties to even
+    rng = np.random.default_rng(4)
+    x = np.exp(rng.uniform(np.log(1e-6), np.log(6e4), (20000, 3))).astype(np.float32)
+    back = O.unpack_r11g11b10(O.pack_r11g11b10(x))
+    rel = np.abs(back - x) / x
+    assert rel[:, :2][x[:, :2] > 7e-5].max() <= 2.0 ** -7 and rel[:, 2][x[:, 2] > 7e-5].max() <= 2.0 ** -6
+    assert np.array_equal(O.pack_r11g11b10(back), O.pack_r11g11b10(x))                # idempotent
