@@ -90,9 +90,10 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
                     // handed over is the already floored texel index (an exact integer), so the unit's own rounding cannot
                     // pick a neighbouring texel.
                     const float2 kx = add2(fx, dup(-12582912.0f)), ky = add2(fy, dup(-12582912.0f));
-                    float o0 = 0.0f, o1 = 0.0f;
-                    if (m0[p] > 0.0f) o0 = tex2D<float>(ism_tex, kx.x, ky.x);
-                    if (m1[p] > 0.0f) o1 = tex2D<float>(ism_tex, kx.y, ky.y);
+                    // both fetches are unconditional: the pixel of the pair that is not lit has its g zeroed below and the
+                    // texture unit clamps whatever coordinate it is given (no predicates, no per-branch handle reload)
+                    const float o0 = tex2D<float>(ism_tex, kx.x, ky.x);
+                    const float o1 = tex2D<float>(ism_tex, kx.y, ky.y);
                     t = fma2(make_float2(o0, o1), dup(50.0f), t);                         // smoothstep(0.98, 1, 1 - (z - occ))
                 } else {
                     int tx0 = __float_as_int(fx.x) - 0x4B400000, ty0 = __float_as_int(fy.x) - 0x4B400000;
