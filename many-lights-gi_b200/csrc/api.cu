@@ -76,6 +76,7 @@ const char* kTimerNames[T_COUNT] = {"VPLP", "ISM render", "ISM CS", "PullPush", 
 struct mlgi_ctx {
     mlgi_config cfg;
     int S, A, L;                    // ISMs per atlas row, atlas edge, VPLs per class
+    int ism_lo, ism_hi;             // ISMs this ctx builds: its classes' VPL slots widened to whole atlas tile rows plus one halo row
     int X, Y, TX, TY;               // clustered / tiled grids
     std::string err;
     unsigned long long launches = 0;
@@ -95,6 +96,7 @@ struct mlgi_ctx {
     cudaTextureObject_t override_tex = 0; const uint16_t* override_ptr = nullptr;   // cached texture of the last ISM override
     int use_texture = 1;
     int fg_pairs = 1;
+    int fg_class_major = 0;
     float4* planar_ext = nullptr;   // caller-owned [16][PH][PW] float4 exchange buffer (mlgi_bind_planar_output)
     // staging for mlgi_frame_host
     uint32_t* st_rsm_diffuse = nullptr; uint32_t* st_rsm_normal = nullptr; float* st_rsm_depth = nullptr;
@@ -228,6 +230,16 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     ctx->S = ism_indices_1d(N);
     ctx->A = 64 * ctx->S;
     ctx->L = N / 16;
+    {   // A shadow lookup can land one texel outside its own ISM (10-bit normals are not unit length), i.e. in the tile
+        // row above or below; a class shard therefore also builds one halo row of ISMs on each side so that its pixels
+        // are bit-identical to the unsharded frame.
+        const int S = ctx->S, vlo = cfg->class_lo * ctx->L, vhi = cfg->class_hi * ctx->L;
+        int r0 = vlo / S, r1 = (vhi + S - 1) / S;
+        const int rows = (N + S - 1) / S;
+        if (cfg->class_lo != 0 || cfg->class_hi != 16) { r0 = std::max(0, r0 - 1); r1 = std::min(rows, r1 + 1); }
+        ctx->ism_lo = r0 * S;
+        ctx->ism_hi = std::min(N, r1 * S);
+    }
     ctx->X = (cfg->width + 127) / 128; ctx->Y = (cfg->height + 127) / 128;
     ctx->TX = (cfg->width + kTile - 1) / kTile; ctx->TY = (cfg->height + kTile - 1) / kTile;
     memset(ctx->ev_used, 0, sizeof(ctx->ev_used));
@@ -273,6 +285,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) ctx->use_texture = strcmp(e2, "ldg") != 0;   // A/B switch: tex (default) | ldg
+    if (const char* e4 = getenv("MLGI_FG_ORDER")) ctx->fg_class_major = strcmp(e4, "class") == 0;    // A/B switch: tile (default) | class
     if (const char* e3 = getenv("MLGI_FG_PAIRS")) ctx->fg_pairs = atoi(e3) == 2 ? 2 : 1;         // A/B switch: pixels per thread / 2
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
     *out = ctx;
@@ -319,8 +332,16 @@ MLGI_API int mlgi_vpl_process(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_cam
 // ------------------------------------------------------------------------------------- a2
 MLGI_API int mlgi_ism_points(mlgi_ctx* ctx, const mlgi_mesh* mesh, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
-    if (!mesh || !mesh->vertices || !mesh->normals || !mesh->indices || !mesh->prim_id) return fail(ctx, MLGI_E_INVALID, "mesh is NULL");
-    if (mesh->num_triangles < 1) return fail(ctx, MLGI_E_INVALID, "mesh has no triangles");
+    if (!mesh) return fail(ctx, MLGI_E_INVALID, "mesh is NULL");
+    if (mesh->num_triangles == 0) {            // no drawables (ImperfectShadowmap.cpp:225-240 draws nothing): empty buckets
+        cudaStream_t st0 = (cudaStream_t)stream;
+        CK(cudaMemsetAsync(ctx->bucket_start, 0, sizeof(uint32_t) * ((size_t)ctx->cfg.vpl_count + 1), st0));
+        CK(cudaMemsetAsync(ctx->counters, 0, 2 * sizeof(uint32_t), st0));
+        ctx->have_points = true;
+        return MLGI_OK;
+    }
+    if (!mesh->vertices || !mesh->normals || !mesh->indices || !mesh->prim_id) return fail(ctx, MLGI_E_INVALID, "mesh is NULL");
+    if (mesh->num_triangles < 0) return fail(ctx, MLGI_E_INVALID, "negative triangle count");
     if (mesh->num_triangles > ctx->cfg.max_triangles) return fail(ctx, MLGI_E_CAPACITY, "mesh has %d triangles, ctx capacity %d", mesh->num_triangles, ctx->cfg.max_triangles);
     int rc = check_params(ctx, p);
     if (rc) return rc;
@@ -357,7 +378,7 @@ MLGI_API int mlgi_ism_splat(mlgi_ctx* ctx, const mlgi_params* p, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_SPLAT, st);
     ctx->launches += launch_splat(ctx->points, ctx->bucket_start, (const float4*)ctx->packed, ctx->cfg.vpl_count, ctx->S, p->z_far, ctx->atlas,
-                                  ctx->cfg.class_lo * ctx->L, ctx->cfg.class_hi * ctx->L, st);
+                                  ctx->ism_lo, ctx->ism_hi, st);
     CK(cudaGetLastError());
     ctx->have_atlas = true;
     return MLGI_OK;
@@ -372,7 +393,7 @@ MLGI_API int mlgi_ism_pullpush(mlgi_ctx* ctx, const uint32_t* atlas_override, co
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_PULLPUSH, st);
     ctx->launches += launch_pullpush(atlas_override ? atlas_override : ctx->atlas, ctx->S, p->z_far, ctx->ism,
-                                     ctx->cfg.class_lo * ctx->L, ctx->cfg.class_hi * ctx->L, st);
+                                     ctx->ism_lo, ctx->ism_hi, st);
     CK(cudaGetLastError());
     ctx->have_ism = true;
     return MLGI_OK;
@@ -470,6 +491,7 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     a.clampv = p->vpl_clamping_value;
     a.enable_shadowing = p->enable_shadowing;
     a.pairs_per_thread = ctx->fg_pairs;
+    a.class_major = ctx->fg_class_major;
     a.class_lo = ctx->cfg.class_lo; a.class_hi = ctx->cfg.class_hi;
     // output routing: a bound exchange buffer receives the class planes and the raster image is rebuilt by the
     // consumer (mlgi_planar_to_raster) after the all-gather; otherwise the raster image is written directly, plus

@@ -187,6 +187,7 @@ struct GatherArgs {
     SliceTable tab;
     float zFar, giScale /* giIntensityFactor / vplCount * 16 */, clampv;
     int enable_shadowing;
+    int class_major;        // CTA enumeration order (see final_gather_kernel)
     int pairs_per_thread;   // 1: 128 threads x 2 pixels, 2: 64 threads x 4 pixels (two independent packed chains)
     int class_lo, class_hi;
     float4* out_raster;     // may be null

@@ -773,6 +773,9 @@ ORC_API void orc_cull_tiled(const float* depth, int W, int H, const float* packe
 //   nearest-texel ISM fetch of a pair lies within tie_eps texels of a texel border (both
 //   neighbours considered); lets the GPU comparison be rigorous about the one discontinuous
 //   operation on this path. stats (optional, 2 x int64): pairs_listed, pairs_lit.
+//   out_f64 (optional): the same sum with the per-pair geometry evaluated in float64 from the same fp32 inputs and
+//   the same texel fetches. |out_rgb - out_f64| is the fp32 restatement's own rounding uncertainty (large only where a
+//   cosine cancels to ~0 at grazing incidence); tests widen the 1e-3 tolerance by it.
 // =====================================================================================
 ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, int W, int H,
                               const float* vpl, int N, const uint16_t* ism_r16,
@@ -780,7 +783,7 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
                               const float* view, const float* proj, float zFar,
                               float giIntensityFactor, float vplClampingValue, int vplStartIndex, int vplEndIndex,
                               int enableShadowing, int class_lo, int class_hi, int tile, int row_begin, int row_end,
-                              float* out_rgb, float* out_lo, float* out_hi, float tie_eps, long long* stats) {
+                              float* out_rgb, float* out_lo, float* out_hi, float tie_eps, long long* stats, float* out_f64) {
     mat4 P(proj), V(view);
     // GIStage.cpp:289: camera->viewInverted() * projection->projectionInverted()
     mat4 viewProjectionInvertedMatrix = inverse(V) * inverse(P);
@@ -823,6 +826,7 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
             uint startIndex = (uint)L * interleavedPixel1d;                          // :93
             uint numLights = sub ? sub[0] : (uint)(L + 1);                           // :94
             vec3 acc(0.0f), accLo(0.0f), accHi(0.0f);
+            double acc64[3] = {0.0, 0.0, 0.0};
             for (uint lightIndex = 1; lightIndex < numLights; lightIndex++) {        // :97
                 uint vplIndex = sub ? sub[lightIndex] : startIndex + lightIndex - 1; // :98
                 const float* pv = vpl + 12 * (size_t)vplIndex;
@@ -832,6 +836,26 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
                 float dist = length(diff);
                 vec3 normalizedDiff = diff / dist;                                   // :104
                 float angleFactor = max(0.0f, dot(vnrm, normalizedDiff)) * max(0.0f, dot(fragNormal, -normalizedDiff));  // :112
+                // float64 shadow evaluation of the same pair (uncertainty estimate only; never feeds out_rgb)
+                double g64 = 0.0;
+                if (out_f64) {
+                    const double dx = (double)fragWorldCoord.x - vpos.x, dy = (double)fragWorldCoord.y - vpos.y, dz = (double)fragWorldCoord.z - vpos.z;
+                    const double dd = std::sqrt(dx * dx + dy * dy + dz * dz);
+                    const double ca = ((double)vnrm.x * dx + (double)vnrm.y * dy + (double)vnrm.z * dz) / dd;
+                    const double cb = -((double)fragNormal.x * dx + (double)fragNormal.y * dy + (double)fragNormal.z * dz) / dd;
+                    if (ca > 0.0 && cb > 0.0) {
+                        g64 = std::min(ca * cb / (dd * dd * dd * dd), (double)vplClampingValue);
+                        if (enableShadowing) {
+                            vec3 v = paraboloid_project(diff, dist, vnrm, zFar, float(vplIndex), S, false);
+                            int cx = glsl::min(glsl::max((int)floorf(v.x * float(A)), 0), A - 1), cy = glsl::min(glsl::max((int)floorf(v.y * float(A)), 0), A - 1);
+                            const double occ = (double)ism_r16[(size_t)cy * A + cx] / 65535.0;
+                            double t = (1.0 - (dd / (double)zFar - occ) - 0.98) / 0.02;
+                            t = std::min(std::max(t, 0.0), 1.0);
+                            g64 *= t * t * (3.0 - 2.0 * t);
+                        }
+                        acc64[0] += (double)vcol.x * g64; acc64[1] += (double)vcol.y * g64; acc64[2] += (double)vcol.z * g64;
+                    }
+                }
                 if (angleFactor <= 0.0f) continue;                                   // :113-114
                 lit++;
                 float d2 = dist * dist;
@@ -876,6 +900,10 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
             if (out_hi) {
                 vec3 r = (accHi * giIntensityFactor / float(vplCount)) * 16.0f;
                 float* q = out_hi + 3 * ((size_t)fy * W + fx); q[0] = r.x; q[1] = r.y; q[2] = r.z;
+            }
+            if (out_f64) {
+                float* q = out_f64 + 3 * ((size_t)fy * W + fx);
+                for (int k = 0; k < 3; k++) q[k] = (float)(acc64[k] * (double)giIntensityFactor / (double)vplCount * 16.0);
             }
         }
     }

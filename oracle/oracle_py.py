@@ -50,7 +50,7 @@ def load():
         lib.orc_cull_tiled.argtypes = [P, C.c_int, C.c_int, P, C.c_int, P, P, C.c_int, P]
         lib.orc_final_gather.argtypes = [P, P, C.c_int, C.c_int, P, C.c_int, P, C.c_int, P, P, P, P, C.c_float,
                                          C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                         P, P, P, C.c_float, P]
+                                         P, P, P, C.c_float, P, P]
         lib.orc_pack_r11g11b10.argtypes = [P, C.c_longlong, C.c_int, P]
         lib.orc_unpack_r11g11b10.argtypes = [P, C.c_longlong, P]
         lib.orc_gi_blur_pass.argtypes = [P, P, P, C.c_int, C.c_int, P, C.c_int, P]
@@ -185,13 +185,14 @@ def cull_tiled(depth, packed_vpl, N, view, proj, tile=64):
 def final_gather(depth, normal, vpl, N, ism, cull_mode, light_list_ids, lists, view, proj, z_far,
                  gi_intensity_factor=3000.0, clamp=0.001, vpl_start=0, vpl_end=None, shadows=True,
                  class_lo=0, class_hi=16, tile=64, bounds=False, tie_eps=None, rows=None):
-    """returns dict(rgb[H,W,3], lo, hi, listed, lit)"""
+    """returns dict(rgb[H,W,3], lo, hi, f64, listed, lit); lo/hi/f64 only with bounds=True"""
     H, W = depth.shape
     if vpl_end is None:
         vpl_end = N
     out = np.zeros((H, W, 3), np.float32)
     lo = np.zeros((H, W, 3), np.float32) if bounds else None
     hi = np.zeros((H, W, 3), np.float32) if bounds else None
+    f64 = np.zeros((H, W, 3), np.float32) if bounds else None
     stats = np.zeros(2, np.int64)
     if tie_eps is None:
         tie_eps = 64 * ism_indices_1d(N) * 1e-6   # a few fp32 ulps of the atlas coordinate, in texels
@@ -199,8 +200,8 @@ def final_gather(depth, normal, vpl, N, ism, cull_mode, light_list_ids, lists, v
     v, p = _f32(view), _f32(proj)
     load().orc_final_gather(_p(depth), _p(normal), W, H, _p(vpl), N, _p(ism), cull_mode, _p(light_list_ids), _p(lists),
                             _p(v), _p(p), z_far, gi_intensity_factor, clamp, vpl_start, vpl_end, int(shadows),
-                            class_lo, class_hi, tile, r0, r1, _p(out), _p(lo), _p(hi), tie_eps, _p(stats))
-    return dict(rgb=out, lo=lo, hi=hi, listed=int(stats[0]), lit=int(stats[1]))
+                            class_lo, class_hi, tile, r0, r1, _p(out), _p(lo), _p(hi), tie_eps, _p(stats), _p(f64))
+    return dict(rgb=out, lo=lo, hi=hi, f64=f64, listed=int(stats[0]), lit=int(stats[1]))
 
 
 def gi_blur(gi_rgb, depth, normal, proj):

@@ -196,22 +196,27 @@ def test_a8_tiled_lists_bit_exact(gpu_case):
 
 
 def _check_radiance(gi, ref, what):
-    """|gpu - oracle| <= 1e-3 * |oracle| + 1e-5 * mean(oracle).
+    """|gpu - oracle| <= 1e-3 * |oracle| + 1e-5 * mean(oracle) + 4 * |oracle - oracle_f64|.
 
-    The relative bound is north_star's. The absolute floor (1e-5 of the mean image radiance, 100x below
-    the relative bound at mean level) covers near-black pixels whose few contributions sit on the toe of
-    smoothstep(0.98, 1, 1 - (z - occ)): there 3t^2 amplifies the fp32 rounding of (1 - (z - occ)) itself,
-    so the oracle's own value is only defined to ~1e-7 * mean. Pairs whose nearest-texel ISM fetch lies
-    within a few ulps of a texel border may take either neighbour: for those the oracle returns [lo, hi]."""
+    The relative bound is north_star's. The absolute floor (1e-5 of the mean image radiance, 100x below the
+    relative bound at mean level) covers near-black pixels whose few contributions sit on the toe of
+    smoothstep(0.98, 1, 1 - (z - occ)): there 3t^2 amplifies the fp32 rounding of (1 - (z - occ)) itself.
+    The last term is the fp32 oracle's own distance to a float64 evaluation of the same formulas on the same
+    inputs and texels: it is ~1e-7 relative except where a cosine cancels to ~0 at grazing incidence and the fp32
+    restatement itself is only defined to a few tenths of a percent (dark pixels lit by one such VPL).
+    Pairs whose nearest-texel ISM fetch lies within a few ulps of a texel border may take either neighbour: for
+    those the oracle returns [lo, hi]."""
     rgb, lo, hi = ref["rgb"], ref["lo"], ref["hi"]
-    atol = 1e-5 * float(rgb.mean()) + 1e-30
+    atol = 1e-5 * float(rgb.mean()) + 1e-30 + 4.0 * np.abs(rgb - ref["f64"])
     inside = (gi >= lo - (1e-3 * np.abs(lo) + atol)) & (gi <= hi + (1e-3 * np.abs(hi) + atol))
     assert inside.all(), "%s: %d values outside the oracle's bounds (max err/tol %.3g)" % (
         what, int((~inside).sum()), float(np.max(np.abs(gi - rgb) / (1e-3 * np.abs(rgb) + atol))))
     notie = (lo == hi)           # pixels without any texel tie: the plain criterion
-    err = np.abs(gi - rgb)[notie] / (1e-3 * np.abs(rgb)[notie] + atol)
+    err = np.abs(gi - rgb)[notie] / (1e-3 * np.abs(rgb)[notie] + atol[notie])
     assert err.size > 0.5 * rgb.size
     assert float(err.max()) <= 1.0, "%s: max error %.3g x tolerance on tie-free pixels" % (what, float(err.max()))
+    # the uncertainty term must stay an exception, not a loophole
+    assert float(np.mean(4.0 * np.abs(rgb - ref["f64"]) > 1e-4 * np.abs(rgb) + 1e-5 * float(rgb.mean()))) < 1e-3
 
 
 @pytest.mark.parametrize("mode", [mlgi.CULL_TILED, mlgi.CULL_CLUSTERED, mlgi.CULL_NONE])
@@ -389,3 +394,94 @@ def test_n2_packed_output_r11g11b10(case_small, case_mid):
         assert np.array_equal(raster.cpu().numpy()[:, :, :3], O.unpack_r11g11b10(ref))
         g.ctx.bind_planar_output(None)
         g.close()
+
+
+def test_empty_scene_gives_empty_atlas_and_unshadowed_frame(case_small):
+    """no drawables: every ISM stays empty, pull-push of an empty atlas, frame still runs (edge case: empty input)"""
+    import oracle_py as O
+    c = case_small
+    g = Gpu(c)
+    p = mlgi.default_params(c.N)
+    empty_mesh = mlgi.make_mesh(None, None, None, None, 0, 0)
+    g.ctx.frame(g.rsm, g.light, empty_mesh, g.gb, g.cam, p)
+    assert g.ctx.counts()[0] == 0
+    atlas = g.ctx.download(mlgi.BUF_ATLAS, np.uint32)
+    assert np.all(atlas == 0xFFFFFFFF)
+    A = c.get("atlas").shape[0]
+    ism_ref = O.ism_pullpush(np.full((A, A), 0xFFFFFFFF, np.uint32), c.N, 50.0)
+    assert np.array_equal(g.ctx.download(mlgi.BUF_ISM, np.uint16), ism_ref.ravel())
+    gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
+    wl = c.wl
+    ref = O.final_gather(wl.depth, wl.normal, c.get("vpl"), c.N, ism_ref, 1, None, c.get("tile_lists"), wl.cam_view, wl.cam_proj, 50.0, bounds=True)
+    _check_radiance(gi, ref, "empty scene")
+    g.close()
+
+
+def test_animated_light_frames(case_small):
+    """BASELINE config 4 in miniature: the ISMs are rebuilt every frame as the sun moves (GIStage.cpp:357-365)"""
+    from conftest import Case
+    g = None
+    for sun in (266.0, 266.1, 300.0):
+        c = Case(case_small.W, case_small.H, case_small.N, 128, 128, cell=1.5, clutter=6, sun=sun)
+        if g is None:
+            g = Gpu(c)
+        up = g.up
+        wl = c.wl
+        rsm_t = [up(wl.rsm_diffuse), up(wl.rsm_normal), up(wl.rsm_depth)]
+        rsm = mlgi.make_rsm(*rsm_t)
+        light = mlgi.Camera.make(wl.light_view, wl.light_proj)
+        p = mlgi.default_params(c.N)
+        g.ctx.frame(rsm, light, g.mesh, g.gb, g.cam, p)          # same ctx, same camera G-buffer, new light
+        assert np.array_equal(g.ctx.download(mlgi.BUF_ISM, np.uint16), c.get("ism").ravel()), sun
+        gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
+        _check_radiance(gi, c.gather(mlgi.CULL_TILED, True), "sun %.1f" % sun)
+    g.close()
+
+
+def test_maximum_vpl_count_16384():
+    """largest supported configuration of the bit-exact stages: 16384 VPLs / ISMs, 8192^2 atlas (BASELINE config 3 sizes)"""
+    from conftest import Case
+    c = Case(128, 96, 16384, 128, 128, cell=1.0, clutter=6)
+    g = Gpu(c)
+    p = mlgi.default_params(c.N)
+    g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    assert np.array_equal(g.ctx.download(mlgi.BUF_VPL, np.float32).view(np.uint32), c.get("vpl").ravel().view(np.uint32))
+    assert np.array_equal(g.ctx.download(mlgi.BUF_ATLAS, np.uint32), c.get("atlas").ravel())
+    assert np.array_equal(g.ctx.download(mlgi.BUF_ISM, np.uint16), c.get("ism").ravel())
+    ref = c.get("tile_lists")
+    assert np.array_equal(g.ctx.download(mlgi.BUF_TILE_LISTS, np.uint16).reshape(ref.shape)[:, :, 0], ref[:, :, 0])
+    gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
+    _check_radiance(gi, c.gather(mlgi.CULL_TILED, True), "N=16384")
+    g.close()
+
+
+def test_full_size_4k_4096_frame():
+    """BASELINE config 2 at full size (3840x2160, 4096 VPLs, 4096^2 atlas, ~290k triangles): every integer stage bit-exact
+    against the oracle, radiance within the contract, plus size-independent properties (class sharding, order independence)"""
+    from conftest import Case
+    c = Case(3840, 2160, 4096, 1024, 256, cell=0.155, clutter=24)
+    g = Gpu(c, max_points=1 << 23)
+    p = mlgi.default_params(c.N)
+    g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    npts, _ = g.ctx.counts()
+    assert npts == c.get("points").shape[0]
+    assert np.array_equal(g.ctx.download(mlgi.BUF_BUCKET_START, np.uint32), c.get("bucket_start"))
+    assert np.array_equal(g.ctx.download(mlgi.BUF_ATLAS, np.uint32), c.get("atlas").ravel())
+    assert np.array_equal(g.ctx.download(mlgi.BUF_ISM, np.uint16), c.get("ism").ravel())
+    ref_lists = c.get("tile_lists")
+    lists = g.ctx.download(mlgi.BUF_TILE_LISTS, np.uint16).reshape(ref_lists.shape)
+    assert np.array_equal(lists[:, :, 0], ref_lists[:, :, 0])
+    n = ref_lists[:, :, 0].astype(np.int64)
+    mask = np.arange(ref_lists.shape[2])[None, None, :] < n[:, :, None]
+    assert np.array_equal(lists[mask], ref_lists[mask])
+    gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)
+    _check_radiance(gi[:, :, :3], c.gather(mlgi.CULL_TILED, True), "4K/4096")
+    g.close()
+    # property: two class shards reproduce the same pixels bit for bit
+    for lo, hi in ((0, 8), (8, 16)):
+        s = Gpu(c, class_lo=lo, class_hi=hi, max_points=1 << 23)
+        s.ctx.frame(s.rsm, s.light, s.mesh, s.gb, s.cam, p)
+        part = s.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)
+        for cls in range(lo, hi):
+            assert np.array_equal(part[cls >> 2::4, cls & 3::4], gi[cls >> 2::4, cls & 3::4])
+        s.close()

@@ -10,8 +10,9 @@ from test_gpu_parity import Gpu
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c1"
 case = {"small": lambda: Case(160, 100, 64, 128, 128, cell=1.5, clutter=6), "c1": lambda: Case(256, 256, 64, 128, 128, cell=0.8, clutter=8),
-        "mid": lambda: Case(384, 216, 1024, 1024, 256, cell=0.5, clutter=12)}[which]()
-g = Gpu(case)
+        "mid": lambda: Case(384, 216, 1024, 1024, 256, cell=0.5, clutter=12),
+        "4k": lambda: Case(3840, 2160, 4096, 1024, 256, cell=0.155, clutter=24)}[which]()
+g = Gpu(case, max_points=1 << 23)
 p = mlgi.default_params(case.N)
 p.cull_mode = mlgi.CULL_TILED
 g.ctx.vpl_process(g.rsm, g.light, p)
@@ -31,3 +32,16 @@ for i in idx:
     print("px(%d,%d) ch%d gpu %.8g ref %.8g rel %.3g  value/mean %.3g" % (x, y, c, gi[y, x, c], rgb[y, x, c], rel[y, x, c], rgb[y, x, c] / mean))
 for thr in (1e-3, 1e-4, 1e-5):
     print("pixels with rel >", thr, ":", int((rel_nt > thr).sum()), "of", rel.size)
+
+
+
+f64 = ref["f64"]
+atol = 1e-5 * mean + 2.0 * np.abs(rgb - f64)
+excess = np.maximum(lo - (1e-3 * np.abs(lo) + atol) - gi, gi - (hi + (1e-3 * np.abs(hi) + atol)))
+ratio = np.abs(gi - rgb) / (1e-3 * np.abs(rgb) + atol)
+bad = excess > 0
+print("outside:", int(bad.sum()))
+order = np.argsort(np.where(bad, ratio, 0).max(2).ravel())[::-1][:14]
+for i in order:
+    y, x = divmod(int(i), case.W)
+    print("px(%d,%d) cls %d err/tol %.1f gpu %s ref32 %s ref64 %s lo==hi %s" % (x, y, (x & 3) + 4 * (y & 3), ratio[y, x].max(), gi[y, x], rgb[y, x], f64[y, x], np.array_equal(lo[y, x], hi[y, x])))
