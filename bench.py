@@ -183,7 +183,7 @@ def bench_config(args, wl, world):
     return {"workload": "%s: %dx%d, %d VPLs, %d ISMs of 64^2 in a %d^2 atlas, RSM %dx%d, %d-triangle procedural atrium" % (
                 args.workload, wl.W, wl.H, wl.N, wl.N, 64 * isqrt_pow2(wl.N), wl.rsm_w, wl.rsm_h, wl.scene.num_triangles),
             "cull": args.cull, "interleave": "4x4", "shadows": True,
-            "parallelism": "interleave-class shard x%d + NCCL all-gather" % world if world > 1 else "single GPU",
+            "parallelism": ("interleave-class shard x%d + %s" % (world, "fused peer-store exchange over NVLink" if args.exchange == "fused" else "NCCL all-gather")) if world > 1 else "single GPU",
             "l2": "no flush: per-step working set (G-buffer + atlas + ISM + tile lists + GI image) exceeds the 126 MB L2"}
 
 
@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k_4096", choices=sorted(WORKLOADS))
     ap.add_argument("--cull", default="tiled", choices=["tiled", "clustered"])
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: gathering kernels store their planes into every peer over NVLink (fused) or one NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -244,14 +246,21 @@ def main():
     cam = mlgi.Camera.make(wl.cam_view, wl.cam_proj)
     PH, PW = (H + 3) // 4, (W + 3) // 4
     planar = None
-    if world > 1:
+    fused = world > 1 and args.exchange == "fused"
+    if fused:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.exchange_create(rank, world))        # 64-byte CUDA IPC handles, once
+        ctx.exchange_connect(handles)
+    elif world > 1:
         planar = torch.zeros((16, PH, PW), dtype=torch.int32, device=dev)      # R11F_G11F_B10F class planes
         ctx.bind_planar_output(planar)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         ctx.frame(rsm, light, mesh, gb, cam, params, stream=stream)
-        if world > 1:
+        if fused:
+            ctx.exchange_finish(stream=stream)           # flags in peer memory + de-interleave; the planes already crossed NVLink
+        elif world > 1:
             mdist.allgather_planar(planar, rank, world)                                      # in place, NCCL over NVLink
             ctx.planar_to_raster(planar, None, stream=stream)
 
@@ -308,14 +317,26 @@ def main():
         h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
         host_gi = torch.empty((H, W), dtype=torch.int32).pin_memory()          # R11F_G11F_B10F
         hr, hg = mlgi.make_rsm(h[0], h[1], h[2]), mlgi.make_gbuffer(h[3], h[4])
-        ctx.bind_planar_output(None)     # the end-to-end call returns this rank's raster pixels to the host
         n_e2e = max(5, min(args.steps, 50))
+        if world == 1:
+            def e2e_step():
+                ctx.frame_host_packed(hr, light, mesh, hg, cam, params, host_gi_packed=host_gi, stream=stream)
+        else:
+            # N > 1: every rank uploads the inputs, gathers its classes, takes part in the exchange and reads the
+            # assembled image back (the public calls of the multi-GPU path, copies inside the timed region)
+            keys = ("rsm_diffuse", "rsm_normal", "rsm_depth", "depth", "normal")
+            def e2e_step():
+                for k, src in zip(keys, h):
+                    d[k].copy_(src.view(d[k].dtype).reshape(d[k].shape), non_blocking=True)
+                step()
+                ctx.read_async(mlgi.BUF_GI_PACKED, host_gi, W * H * 4, stream=stream)
+                torch.cuda.current_stream().synchronize()
         for _ in range(3):
-            ctx.frame_host_packed(hr, light, mesh, hg, cam, params, host_gi_packed=host_gi, stream=stream)
+            e2e_step()
         barrier()
         t0 = time.time()
         for _ in range(n_e2e):
-            ctx.frame_host_packed(hr, light, mesh, hg, cam, params, host_gi_packed=host_gi, stream=stream)
+            e2e_step()
         barrier()
         dt = (time.time() - t0) / n_e2e
         if world > 1:
@@ -325,9 +346,9 @@ def main():
         h2d = sum(x.numel() * x.element_size() for x in h)
         e2e = {"value": pairs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_gi.numel() * 4,
                "ms_per_step": dt * 1e3, "steps": n_e2e,
-               "call": "mlgi_frame_host_packed (pinned host RSM + G-buffer in, GL_R11F_G11F_B10F GI image out = the reference's giBuffer format, stream sync)"}
-        if planar is not None:
-            ctx.bind_planar_output(planar)
+               "call": ("mlgi_frame_host_packed (pinned host RSM + G-buffer in, GL_R11F_G11F_B10F GI image out = the reference's giBuffer "
+                        "format, stream sync)") if world == 1 else
+                       "per rank: pinned-host input upload + mlgi_frame + exchange + read-back of the assembled GL_R11F_G11F_B10F image"}
 
     if rank != 0:
         if world > 1:

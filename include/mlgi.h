@@ -188,6 +188,8 @@ MLGI_API int mlgi_frame_host_packed(mlgi_ctx*, const mlgi_rsm* host_rsm, const m
 MLGI_API int mlgi_get_buffer(mlgi_ctx*, int buffer_id, void** dev_ptr, size_t* bytes);
 /* synchronous device->host copy of `bytes` bytes of a ctx buffer starting at byte `offset` (test/debug path) */
 MLGI_API int mlgi_read_buffer(mlgi_ctx*, int buffer_id, void* host_dst, size_t bytes, size_t offset);
+/* asynchronous variant on `stream` (host_dst should be pinned); no synchronisation */
+MLGI_API int mlgi_read_buffer_async(mlgi_ctx*, int buffer_id, void* host_dst, size_t bytes, size_t offset, void* stream);
 MLGI_API int mlgi_get_counts(mlgi_ctx*, int* num_points, int* num_used_clusters);  /* synchronises */
 /* exact work counters of final gathering for the roofline accounting: runs the counting variant of the
  * kernel on the same inputs (no image is written) and returns (pixel,VPL) pairs listed / lit. Synchronises. */
@@ -201,6 +203,19 @@ MLGI_API float mlgi_measure_fp32_peak_tflops(mlgi_ctx*);
  * c*PH*PW), so one in-place all-gather over ranks assembles the image; NULL unbinds. With cfg.gi_packed the
  * buffer holds one uint32 (R11F_G11F_B10F) per pixel instead of 4 floats. */
 MLGI_API int mlgi_bind_planar_output(mlgi_ctx*, void* dev_planar16);
+/* Fused exchange (B200/NVSwitch path, replaces the all-gather): every rank allocates an exchange buffer, the 64-byte
+ * CUDA IPC handles are swapped by the caller (any host transport), and from then on the gathering kernel of each rank
+ * stores its class planes straight into EVERY rank's buffer over NVLink while it is still gathering; completion flags
+ * in peer memory replace the collective. One process per GPU, all on one node, world <= 8.
+ *   mlgi_exchange_create : allocate, return this rank's handle (out_handle64 = 64 bytes)
+ *   mlgi_exchange_connect: all_handles = world x 64 bytes in rank order; maps the peers
+ *   mlgi_exchange_finish : after mlgi_frame on the same stream: signal, wait for all ranks, de-interleave into
+ *                          MLGI_BUF_GI (and MLGI_BUF_GI_PACKED). Asynchronous; bounded wait (no GPU hang if a peer dies)
+ *   mlgi_exchange_status : synchronises and reports a timed-out wait */
+MLGI_API int mlgi_exchange_create(mlgi_ctx*, int rank, int world, void* out_handle64);
+MLGI_API int mlgi_exchange_connect(mlgi_ctx*, const void* all_handles);
+MLGI_API int mlgi_exchange_finish(mlgi_ctx*, void* stream);
+MLGI_API int mlgi_exchange_status(mlgi_ctx*);
 /* consumer-side de-interleave of a complete planar image into raster order (dev_raster NULL = ctx GI buffer) */
 MLGI_API int mlgi_planar_to_raster(mlgi_ctx*, const void* dev_planar16, float* dev_raster, void* stream);
 

@@ -97,6 +97,17 @@ struct mlgi_ctx {
     int use_texture = 1;
     int fg_pairs = 1;
     int fg_class_major = 0;
+    // fused multi-GPU exchange (mlgi_exchange_*): two parity buffers + flag array in ONE IPC-exportable allocation
+    struct Exchange {
+        int rank = 0, world = 0;
+        char* base = nullptr;                 // own allocation: [flags 256 B][buffer 0][buffer 1]
+        size_t buf_bytes = 0;
+        char* peer_base[8] = {nullptr};       // peer-mapped allocations (own slot = base)
+        uint32_t** d_peer_flags = nullptr;    // device array of world pointers (for the signal kernel)
+        uint32_t* d_error = nullptr;
+        uint32_t frame = 0;
+        bool connected = false;
+    } xch;
     float4* planar_ext = nullptr;   // caller-owned [16][PH][PW] float4 exchange buffer (mlgi_bind_planar_output)
     // staging for mlgi_frame_host
     uint32_t* st_rsm_diffuse = nullptr; uint32_t* st_rsm_normal = nullptr; float* st_rsm_depth = nullptr;
@@ -299,6 +310,11 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (int g = 0; g < ctx->xch.world; g++)
+        if (g != ctx->xch.rank && ctx->xch.peer_base[g]) cudaIpcCloseMemHandle(ctx->xch.peer_base[g]);
+    if (ctx->xch.base) cudaFree(ctx->xch.base);
+    if (ctx->xch.d_peer_flags) cudaFree(ctx->xch.d_peer_flags);
+    if (ctx->xch.d_error) cudaFree(ctx->xch.d_error);
     if (ctx->ism_tex) cudaDestroyTextureObject(ctx->ism_tex);
     if (ctx->override_tex) cudaDestroyTextureObject(ctx->override_tex);
     for (void* p : ctx->allocs) cudaFree(p);
@@ -497,7 +513,12 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     // consumer (mlgi_planar_to_raster) after the all-gather; otherwise the raster image is written directly, plus
     // the ctx-owned planar sub-image when this ctx owns only some of the classes.
     const bool partial = ctx->cfg.class_lo != 0 || ctx->cfg.class_hi != 16;
-    if (ctx->planar_ext) {
+    if (ctx->xch.connected) {
+        a.out_raster = nullptr; a.planar_class0 = 0;
+        a.num_peers = ctx->xch.world; a.peer_packed = ctx->cfg.gi_packed;
+        const size_t boff = 256 + (size_t)((ctx->xch.frame + 1) & 1) * ctx->xch.buf_bytes;   // buffer of the frame being produced
+        for (int g = 0; g < ctx->xch.world; g++) a.peer_planar[g] = ctx->xch.peer_base[g] + boff;
+    } else if (ctx->planar_ext) {
         a.out_raster = nullptr; a.planar_class0 = 0;
         if (ctx->cfg.gi_packed) a.out_planar_packed = (uint32_t*)ctx->planar_ext; else a.out_planar = ctx->planar_ext;
     } else {
@@ -532,7 +553,7 @@ MLGI_API int mlgi_gather_stats(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi
     if (rc) return rc;
     a.stats = ctx->stats;
     a.out_raster = nullptr;     // counting variant: same loop, counters instead of stores
-    a.out_planar = nullptr; a.out_packed = nullptr; a.out_planar_packed = nullptr;
+    a.out_planar = nullptr; a.out_packed = nullptr; a.out_planar_packed = nullptr; a.num_peers = 0;
     CK(cudaMemset(ctx->stats, 0, 2 * sizeof(unsigned long long)));
     ctx->launches += launch_final_gather(a, 0);
     unsigned long long h[2];
@@ -559,6 +580,76 @@ MLGI_API int mlgi_planar_to_raster(mlgi_ctx* ctx, const void* dev_planar16, floa
                                              dev_raster ? (float4*)dev_raster : ctx->gi, st);
     CK(cudaGetLastError());
     ctx->have_gi = true;
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- fused exchange
+MLGI_API int mlgi_exchange_create(mlgi_ctx* ctx, int rank, int world, void* out_handle64) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (world < 2 || world > 8 || rank < 0 || rank >= world || !out_handle64) return fail(ctx, MLGI_E_INVALID, "exchange needs 2 <= world <= 8");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    auto& x = ctx->xch;
+    if (x.base) return fail(ctx, MLGI_E_INVALID, "exchange already created");
+    const size_t PW = (ctx->cfg.width + 3) / 4, PH = (ctx->cfg.height + 3) / 4;
+    x.buf_bytes = ((16 * PW * PH * (ctx->cfg.gi_packed ? 4 : 16)) + 255) & ~(size_t)255;
+    CK(cudaMalloc((void**)&x.base, 256 + 2 * x.buf_bytes));
+    CK(cudaMemset(x.base, 0, 256 + 2 * x.buf_bytes));
+    CK(cudaMalloc((void**)&x.d_peer_flags, 8 * sizeof(uint32_t*)));
+    CK(cudaMalloc((void**)&x.d_error, sizeof(uint32_t)));
+    CK(cudaMemset(x.d_error, 0, sizeof(uint32_t)));
+    x.rank = rank; x.world = world;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, x.base));
+    memcpy(out_handle64, &h, 64);
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_exchange_connect(mlgi_ctx* ctx, const void* all_handles) {
+    if (!ctx) return MLGI_E_INVALID;
+    auto& x = ctx->xch;
+    if (!x.base || !all_handles) return fail(ctx, MLGI_E_ORDER, "mlgi_exchange_connect needs mlgi_exchange_create first");
+    uint32_t* flags[8] = {nullptr};
+    for (int g = 0; g < x.world; g++) {
+        if (g == x.rank) x.peer_base[g] = x.base;
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)all_handles + 64 * g, 64);
+            void* p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            x.peer_base[g] = (char*)p;
+        }
+        flags[g] = (uint32_t*)x.peer_base[g];
+    }
+    CK(cudaMemcpy(x.d_peer_flags, flags, sizeof(flags), cudaMemcpyHostToDevice));
+    x.connected = true;
+    return MLGI_OK;
+}
+
+// signal peers that this rank's planes of the current frame are written, wait for every rank's signal, then
+// de-interleave the assembled planes into the ctx GI image(s). Call after mlgi_frame on the same stream.
+MLGI_API int mlgi_exchange_finish(mlgi_ctx* ctx, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    auto& x = ctx->xch;
+    if (!x.connected) return fail(ctx, MLGI_E_ORDER, "exchange is not connected");
+    cudaStream_t st = (cudaStream_t)stream;
+    x.frame++;
+    ctx->launches += launch_exchange_signal(x.d_peer_flags, x.world, x.rank, x.frame, st);
+    ctx->launches += launch_exchange_wait((const uint32_t*)x.base, x.world, x.frame, x.d_error, st);
+    const char* buf = x.base + 256 + (size_t)(x.frame & 1) * x.buf_bytes;
+    if (ctx->cfg.gi_packed) ctx->launches += launch_planar_packed_to_raster((const uint32_t*)buf, ctx->cfg.width, ctx->cfg.height, ctx->gi_packed, ctx->gi, st);
+    else ctx->launches += launch_planar_to_raster((const float4*)buf, ctx->cfg.width, ctx->cfg.height, 0, 16, ctx->gi, st);
+    CK(cudaGetLastError());
+    ctx->have_gi = true;
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_exchange_status(mlgi_ctx* ctx) {      // synchronises; 0 = ok, MLGI_E_CUDA if a peer never signalled
+    if (!ctx) return MLGI_E_INVALID;
+    if (!ctx->xch.d_error) return MLGI_OK;
+    uint32_t e = 0;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&e, ctx->xch.d_error, 4, cudaMemcpyDeviceToHost));
+    if (e) return fail(ctx, MLGI_E_CUDA, "exchange timed out waiting for rank %u", e - 1);
     return MLGI_OK;
 }
 
@@ -702,6 +793,17 @@ MLGI_API int mlgi_read_buffer(mlgi_ctx* ctx, int id, void* host_dst, size_t byte
     if (!host_dst || offset + bytes > n) return fail(ctx, MLGI_E_INVALID, "read of %zu bytes at %zu exceeds buffer %d (%zu bytes)", bytes, offset, id, n);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(host_dst, (const char*)p + offset, bytes, cudaMemcpyDeviceToHost));
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_read_buffer_async(mlgi_ctx* ctx, int id, void* host_dst, size_t bytes, size_t offset, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    void* p = nullptr;
+    size_t n = 0;
+    int rc = mlgi_get_buffer(ctx, id, &p, &n);
+    if (rc) return rc;
+    if (!host_dst || offset + bytes > n) return fail(ctx, MLGI_E_INVALID, "read of %zu bytes at %zu exceeds buffer %d (%zu bytes)", bytes, offset, id, n);
+    CK(cudaMemcpyAsync(host_dst, (const char*)p + offset, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return MLGI_OK;
 }
 

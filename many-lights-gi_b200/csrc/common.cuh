@@ -195,6 +195,10 @@ struct GatherArgs {
     int planar_class0;
     uint32_t* out_packed;          // may be null: R11F_G11F_B10F raster
     uint32_t* out_planar_packed;   // may be null: R11F_G11F_B10F class planes
+    // fused exchange: the class planes are stored straight into every rank's exchange buffer (peer-mapped over NVLink)
+    int num_peers;                 // 0 = off
+    int peer_packed;
+    void* peer_planar[8];          // element = uint32 (gi_packed) or float4
     unsigned long long* stats;  // null, or 2 counters (pairs listed / lit)
 };
 int launch_final_gather(const GatherArgs& a, cudaStream_t st);
@@ -202,6 +206,8 @@ int launch_gi_blur(const float4* gi, const float* depth, const uint32_t* face_no
                    float projB, float4* tmp, float4* out, cudaStream_t st);
 float measure_fp32_peak_tflops(cudaStream_t st);   // FFMA micro-benchmark: the FP32-pipe roofline denominator
 int launch_planar_to_raster(const float4* planar, int W, int H, int class_lo, int class_hi, float4* raster, cudaStream_t st);
+int launch_exchange_signal(uint32_t* const* peer_flags, int world, int rank, uint32_t frame_id, cudaStream_t st);
+int launch_exchange_wait(const uint32_t* flags, int world, uint32_t frame_id, uint32_t* error_flag, cudaStream_t st);
 int launch_planar_packed_to_raster(const uint32_t* planar, int W, int H, uint32_t* raster_packed, float4* raster, cudaStream_t st);
 
 constexpr int kTile = 64;  // tiled-culling tile edge in pixels (one gathering CTA = one class of one tile)

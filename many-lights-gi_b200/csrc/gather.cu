@@ -261,6 +261,19 @@ __global__ void __launch_bounds__(256 / (2 * NP)) final_gather_kernel(const Gath
         if (a.out_planar) a.out_planar[((size_t)(cls - a.planar_class0) * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = o;
         if (a.out_packed) a.out_packed[(size_t)sy[k] * a.W + sx[k]] = pack_r11g11b10(o.x, o.y, o.z);
         if (a.out_planar_packed) a.out_planar_packed[((size_t)cls * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = pack_r11g11b10(o.x, o.y, o.z);
+        if (a.num_peers) {
+            // fused exchange: this pixel's plane entry goes to every rank's buffer directly, so the
+            // NVLink transfer overlaps the gathering of the remaining tiles and no separate collective is launched
+            const size_t off = ((size_t)cls * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2);
+            if (a.peer_packed) {
+                const uint32_t v = pack_r11g11b10(o.x, o.y, o.z);
+#pragma unroll 1
+                for (int g = 0; g < a.num_peers; g++) static_cast<uint32_t*>(a.peer_planar[g])[off] = v;
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < a.num_peers; g++) static_cast<float4*>(a.peer_planar[g])[off] = o;
+            }
+        }
     }
     if (STATS) {
 #pragma unroll
@@ -307,6 +320,38 @@ __global__ void planar_to_raster_kernel(const float4* __restrict__ planar, int W
     const int PW = (W + 3) >> 2, PH = (H + 3) >> 2;
     raster[(size_t)y * W + x] = planar[((size_t)(cls - class_lo) * PH + (y >> 2)) * PW + (x >> 2)];
 }
+// ---- fused exchange: completion flags in peer memory -------------------------------------------------------------
+// After its gathering kernel (whose peer stores are complete at the kernel boundary) a rank writes the frame id into
+// slot [rank] of every peer's flag array; a rank may read its exchange buffer once all `world` slots show the frame id.
+__global__ void exchange_signal_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t frame_id) {
+    const int g = threadIdx.x;
+    if (g < world) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(peer_flags[g] + rank) = frame_id;
+        __threadfence_system();
+    }
+}
+__global__ void exchange_wait_kernel(const uint32_t* flags, int world, uint32_t frame_id, uint32_t* error_flag) {
+    const int g = threadIdx.x;
+    if (g < world) {
+        const volatile uint32_t* f = flags + g;
+        long long spins = 0;
+        while ((int)(*f - frame_id) < 0) {                  // wrap-safe "not yet"
+            __nanosleep(200);
+            if (++spins > 20000000LL) { atomicExch(error_flag, 1u + (uint32_t)g); break; }   // ~4 s: a peer died; do not hang the GPU
+        }
+        __threadfence_system();
+    }
+}
+int launch_exchange_signal(uint32_t* const* peer_flags, int world, int rank, uint32_t frame_id, cudaStream_t st) {
+    exchange_signal_kernel<<<1, 32, 0, st>>>(peer_flags, world, rank, frame_id);
+    return 1;
+}
+int launch_exchange_wait(const uint32_t* flags, int world, uint32_t frame_id, uint32_t* error_flag, cudaStream_t st) {
+    exchange_wait_kernel<<<1, 32, 0, st>>>(flags, world, frame_id, error_flag);
+    return 1;
+}
+
 __global__ void planar_packed_to_raster_kernel(const uint32_t* __restrict__ planar, int W, int H, uint32_t* __restrict__ raster_packed,
                                                float4* __restrict__ raster) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;

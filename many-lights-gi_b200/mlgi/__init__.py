@@ -72,7 +72,7 @@ EXPORTS = [
     "mlgi_version", "mlgi_default_params", "mlgi_create", "mlgi_destroy", "mlgi_last_error",
     "mlgi_vpl_process", "mlgi_ism_points", "mlgi_ism_set_points", "mlgi_ism_splat", "mlgi_ism_pullpush",
     "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_frame", "mlgi_frame_host", "mlgi_frame_host_packed",
-    "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
+    "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_read_buffer_async", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_exchange_create", "mlgi_exchange_connect", "mlgi_exchange_finish", "mlgi_exchange_status", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
 ]
 
 _lib = None
@@ -117,6 +117,7 @@ def load():
     lib.mlgi_frame_host_packed.argtypes = lib.mlgi_frame_host.argtypes
     lib.mlgi_get_buffer.argtypes = [P, C.c_int, C.POINTER(P), C.POINTER(C.c_size_t)]
     lib.mlgi_read_buffer.argtypes = [P, C.c_int, P, C.c_size_t, C.c_size_t]
+    lib.mlgi_read_buffer_async.argtypes = [P, C.c_int, P, C.c_size_t, C.c_size_t, P]
     lib.mlgi_get_counts.argtypes = [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mlgi_gather_stats.argtypes = [P, C.POINTER(GBuffer), C.POINTER(Camera), P, C.POINTER(Params),
                                       C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
@@ -124,6 +125,10 @@ def load():
     lib.mlgi_measure_fp32_peak_tflops.restype = C.c_float
     lib.mlgi_bind_planar_output.argtypes = [P, P]
     lib.mlgi_planar_to_raster.argtypes = [P, P, P, P]
+    lib.mlgi_exchange_create.argtypes = [P, C.c_int, C.c_int, P]
+    lib.mlgi_exchange_connect.argtypes = [P, P]
+    lib.mlgi_exchange_finish.argtypes = [P, P]
+    lib.mlgi_exchange_status.argtypes = [P]
     lib.mlgi_get_timings.argtypes = [P, C.POINTER(Timing), C.c_int]
     lib.mlgi_set_timers.argtypes = [P, C.c_int]
     lib.mlgi_launch_count.argtypes = [P]
@@ -244,6 +249,9 @@ class Context:
         self._ck(self.lib.mlgi_read_buffer(self.h, buf_id, out.ctypes.data, n * dt.itemsize, 0))
         return out
 
+    def read_async(self, buf_id, host_tensor, nbytes, stream=None):
+        self._ck(self.lib.mlgi_read_buffer_async(self.h, buf_id, _ptr(host_tensor), nbytes, 0, stream))
+
     def counts(self):
         a, b = C.c_int(), C.c_int()
         self._ck(self.lib.mlgi_get_counts(self.h, C.byref(a), C.byref(b)))
@@ -268,6 +276,22 @@ class Context:
         arr = (Timing * 16)()
         n = self.lib.mlgi_get_timings(self.h, arr, 16)
         return {arr[i].name.decode(): (arr[i].ms, arr[i].launches) for i in range(n)}
+
+    def exchange_create(self, rank, world):
+        """returns this rank's 64-byte IPC handle (bytes)"""
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.mlgi_exchange_create(self.h, rank, world, buf))
+        return buf.raw
+
+    def exchange_connect(self, handles):
+        blob = b"".join(handles)
+        self._ck(self.lib.mlgi_exchange_connect(self.h, C.c_char_p(blob)))
+
+    def exchange_finish(self, stream=None):
+        self._ck(self.lib.mlgi_exchange_finish(self.h, stream))
+
+    def exchange_status(self):
+        self._ck(self.lib.mlgi_exchange_status(self.h))
 
     def set_timers(self, enable):
         self._ck(self.lib.mlgi_set_timers(self.h, int(enable)))
