@@ -364,7 +364,7 @@ MLGI_API int mlgi_ism_points(mlgi_ctx* ctx, const mlgi_mesh* mesh, const mlgi_pa
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_POINTS, st);
     ctx->launches += launch_point_counts(*mesh, p->tess_level_factor, ctx->tri_offsets, ctx->scan_tmp, st);
-    ctx->launches += launch_point_generate(*mesh, p->tess_level_factor, ctx->cfg.vpl_count, ctx->tri_offsets, ctx->cfg.max_points,
+    ctx->launches += launch_point_generate(*mesh, ctx->cfg.vpl_count, ctx->tri_offsets, ctx->cfg.max_points,
                                            ctx->points_unsorted, ctx->point_bucket, ctx->bucket_hist, ctx->bucket_start, ctx->bucket_cursor,
                                            ctx->points, ctx->counters, st);
     CK(cudaGetLastError());
@@ -434,8 +434,7 @@ MLGI_API int mlgi_cull_clustered(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const ml
     }
     {
         StageTimer t(ctx, T_LIGHTLISTS, st);
-        ctx->launches += launch_light_lists(ctx->records, ctx->cfg.vpl_count, ctx->compact_ids, ctx->counters + 2,
-                                            ctx->X * ctx->Y * 16, to_mat4(inv), cam->proj[10], cam->proj[14], ctx->cfg.width, ctx->cfg.height,
+        ctx->launches += launch_light_lists(ctx->records, ctx->cfg.vpl_count, ctx->compact_ids, ctx->counters + 2, to_mat4(inv), cam->proj[10], cam->proj[14], ctx->cfg.width, ctx->cfg.height,
                                             tab, ctx->cfg.class_lo, ctx->cfg.class_hi, ctx->light_lists, st);
     }
     CK(cudaGetLastError());

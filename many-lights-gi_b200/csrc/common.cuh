@@ -157,11 +157,10 @@ int launch_vpl_process(const mlgi_rsm& rsm, int rsm_w, int rsm_h, int N, const M
 
 int launch_point_counts(const mlgi_mesh& mesh, float tessLevelFactor, uint32_t* tri_offsets /*ntri+1*/,
                         uint32_t* scan_tmp, cudaStream_t st);
-int launch_point_generate(const mlgi_mesh& mesh, float tessLevelFactor, int N, const uint32_t* tri_offsets,
+int launch_point_generate(const mlgi_mesh& mesh, int N, const uint32_t* tri_offsets,
                           int max_points, float4* points_unsorted, uint32_t* point_bucket, uint32_t* bucket_hist,
                           uint32_t* bucket_start, uint32_t* bucket_cursor, float4* points_sorted,
                           uint32_t* num_points_dev, cudaStream_t st);
-int launch_bucket_scan(int N, const uint32_t* bucket_start_in, cudaStream_t st);
 
 int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S,
                  float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, cudaStream_t st);
@@ -171,7 +170,7 @@ int launch_clustering(const float* depth, int W, int H, float projA, float projB
                       uint32_t* tile_masks, uint32_t* compact_ids, uint16_t* light_list_ids, uint32_t* num_used,
                       cudaStream_t st);
 int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_ids, const uint32_t* num_used,
-                       int max_clusters, const Mat4& inv_vp, float projA, float projB, int W, int H,
+                       const Mat4& inv_vp, float projA, float projB, int W, int H,
                        const SliceTable& tab, int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);
 int launch_cull_tiled(const float* depth, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
                       int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);

@@ -276,10 +276,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) bucket_scan_kernel(const uint32_
     if (threadIdx.x == 0) out[N] = carry;
 }
 
-int launch_point_generate(const mlgi_mesh& mesh, float tf, int N, const uint32_t* tri_offsets, int max_points,
+int launch_point_generate(const mlgi_mesh& mesh, int N, const uint32_t* tri_offsets, int max_points,
                           float4* points_unsorted, uint32_t* point_bucket, uint32_t* bucket_hist, uint32_t* bucket_start,
                           uint32_t* bucket_cursor, float4* points_sorted, uint32_t* num_points_dev, cudaStream_t st) {
-    (void)tf;
     cudaMemsetAsync(bucket_hist, 0, sizeof(uint32_t) * N, st);
     cudaMemsetAsync(bucket_cursor, 0, sizeof(uint32_t) * N, st);
     const int grid = 148 * 8;
@@ -822,10 +821,9 @@ __global__ void __launch_bounds__(128) light_lists_kernel(const VplRecord* __res
     }
 }
 
-int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_ids, const uint32_t* num_used, int max_clusters,
+int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_ids, const uint32_t* num_used,
                        const Mat4& inv_vp, float projA, float projB, int W, int H, const SliceTable& tab, int class_lo,
                        int class_hi, uint16_t* lists, cudaStream_t st) {
-    (void)max_clusters;
     light_lists_kernel<<<148 * 8, 128, 0, st>>>(records, N, compact_ids, num_used, inv_vp, projA, projB, W, H, tab, class_lo,
                                                 class_hi, lists);
     return 1;
