@@ -289,6 +289,10 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     e = cudaMemcpy(ctx->shuffle, v.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 4 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(ctx->gi, 0, WH * sizeof(float4));
+    // a class shard builds only ISMs [ism_lo, ism_hi); the discarded fetch of an unlit pixel in a pair may still touch
+    // the other rows, so give them a defined value ("no occluder") once
+    if (e == cudaSuccess) e = cudaMemset(ctx->ism, 0xFF, AA * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->atlas, 0xFF, AA * sizeof(uint32_t));
     if (e != cudaSuccess) { fail(nullptr, MLGI_E_CUDA, "init: %s", cudaGetErrorString(e)); mlgi_destroy(ctx); return MLGI_E_CUDA; }
     for (int i = 0; i < T_COUNT; i++) { cudaEventCreate(&ctx->ev[i][0]); cudaEventCreate(&ctx->ev[i][1]); }
     ctx->events_created = true;
