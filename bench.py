@@ -119,7 +119,7 @@ class CpuPort:
         t0 = time.time(); pts, bkt = O.ism_points(sc.vertices, sc.normals, sc.indices, sc.prim_id, 2.0, N); pg, bs = O.group_by_bucket(pts, bkt, N); t["ISM render"] = time.time() - t0
         t0 = time.time(); atlas = O.ism_splat(pg, bs, self.packed, N, wl.z_far); t["ISM CS"] = time.time() - t0
         t0 = time.time(); self.ism = O.ism_pullpush(atlas, N, wl.z_far); t["PullPush"] = time.time() - t0
-        t0 = time.time(); self.tiles = O.cull_tiled(wl.depth, self.packed, N, wl.cam_view, wl.cam_proj, 64); t["Tiled cull"] = time.time() - t0
+        t0 = time.time(); self.tiles = O.cull_tiled(wl.depth, wl.normal, self.vpl, N, wl.cam_view, wl.cam_proj, 64); t["Tiled cull"] = time.time() - t0
         self.t_other = sum(t.values())
         self.stage_s = t
         self.prepared = True

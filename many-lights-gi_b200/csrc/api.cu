@@ -449,16 +449,17 @@ MLGI_API int mlgi_cull_clustered(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const ml
 // ------------------------------------------------------------------------------------- a8
 MLGI_API int mlgi_cull_tiled(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
-    if (!gb || !gb->depth || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
+    if (!gb || !gb->depth || !gb->face_normal || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
     int rc = check_params(ctx, p);
     if (rc) return rc;
     if (!ctx->have_vpl) return fail(ctx, MLGI_E_ORDER, "culling needs mlgi_vpl_process first");
     cudaStream_t st = (cudaStream_t)stream;
-    float pv[16], inv[16];
-    mat_mul(cam->proj, cam->view, pv);
-    mat_inverse(pv, inv);
+    float vi[16], pi[16], inv[16];
+    mat_inverse(cam->view, vi);                 // the gathering pass's own unprojection (GIStage.cpp:289), so both see the same positions
+    mat_inverse(cam->proj, pi);
+    mat_mul(vi, pi, inv);
     StageTimer t(ctx, T_TILED, st);
-    ctx->launches += launch_cull_tiled(gb->depth, ctx->cfg.width, ctx->cfg.height, ctx->records, ctx->cfg.vpl_count, to_mat4(inv),
+    ctx->launches += launch_cull_tiled(gb->depth, gb->face_normal, ctx->cfg.width, ctx->cfg.height, ctx->records, ctx->cfg.vpl_count, to_mat4(inv),
                                        ctx->cfg.class_lo, ctx->cfg.class_hi, ctx->tile_lists, st);
     CK(cudaGetLastError());
     ctx->have_tiled = true;

@@ -172,7 +172,7 @@ int launch_clustering(const float* depth, int W, int H, float projA, float projB
 int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_ids, const uint32_t* num_used,
                        const Mat4& inv_vp, float projA, float projB, int W, int H,
                        const SliceTable& tab, int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);
-int launch_cull_tiled(const float* depth, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
+int launch_cull_tiled(const float* depth, const uint32_t* face_normal, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
                       int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);
 
 struct GatherArgs {

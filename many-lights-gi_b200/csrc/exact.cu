@@ -829,59 +829,88 @@ int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_
     return 1;
 }
 
-// a8: one CTA per 64x64 tile: depth bounds -> 8 corners -> bounding sphere -> 16 class sub-lists (2 per warp).
-// A VPL is kept iff the sphere reaches its positive half-space: one exact test per VPL.
-__global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict__ depth, int W, int H, const VplRecord* __restrict__ records,
-                                                         int N, Mat4 inv_vp, int class_lo, int class_hi, uint16_t* __restrict__ lists) {
-    __shared__ float smin[8], smax[8];
-    __shared__ float3 scorner[8];
-    __shared__ float4 ssphere;
+// a8: one CTA per 64x64 tile. Phase 1 unprojects the tile's pixels exactly as the gathering prologue does and reduces them
+// to 14 numbers (position AABB, normal box, emin, emag); phase 2 tests every VPL of the 16 classes against them (2 classes
+// per warp, ordered ballot compaction). The rule is stated in DESIGN.md section 4 / oracle.cpp tile_keeps_vpl.
+struct TileBounds { float pmin[3], pmax[3], nmin[3], nmax[3], emin, emag; };
+
+__global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict__ depth, const uint32_t* __restrict__ face_normal, int W, int H,
+                                                         const VplRecord* __restrict__ records, int N, Mat4 inv_vp, int class_lo,
+                                                         int class_hi, uint16_t* __restrict__ lists) {
+    __shared__ float sred[8][14];
+    __shared__ TileBounds stb;
+    __shared__ float s_n10[1024];     // 10-bit channel -> v / 1023 * 2 - 1 (the IEEE division once per code instead of three per pixel)
+    __shared__ float s_ndcy[kTile];   // tile row -> y / H * 2 - 1
+    for (int i = threadIdx.x; i < 1024; i += 256) s_n10[i] = float(i) / 1023.0f * 2.0f - 1.0f;                 // final_gathering.comp:79
+    if (threadIdx.x < kTile) s_ndcy[threadIdx.x] = float(blockIdx.y * kTile + threadIdx.x) / float(H) * 2.0f - 1.0f;   // :70,74
+    __syncthreads();
     const int bx = blockIdx.x, by = blockIdx.y;
-    float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
-    {   // 16 independent (predicated) loads per thread, all in flight before the first compare
-        float dv[kTile * kTile / 256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float INF = __int_as_float(0x7f800000);
+    float r[14];   // 0-2 pmin, 3-5 pmax, 6-8 nmin, 9-11 nmax, 12 emin, 13 emag
 #pragma unroll
-        for (int q = 0; q < kTile * kTile / 256; q++) {
+    for (int k = 0; k < 3; k++) { r[k] = INF; r[3 + k] = -INF; r[6 + k] = INF; r[9 + k] = -INF; }
+    r[12] = INF; r[13] = 0.0f;
+    {
+        constexpr int Q = kTile * kTile / 256;
+        float dv[Q]; uint32_t nv[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {              // all loads in flight before the first use
             const int p = threadIdx.x + q * 256;
             const int x = bx * kTile + (p % kTile), y = by * kTile + (p / kTile);
-            dv[q] = (x < W && y < H) ? __ldg(depth + (size_t)y * W + x) : __int_as_float(0x7fc00000);   // NaN: ignored by fmin/fmax
+            const bool in = x < W && y < H;
+            dv[q] = in ? __ldg(depth + (size_t)y * W + x) : 0.0f;
+            nv[q] = in ? __ldg(face_normal + (size_t)y * W + x) : 0u;
         }
+        const float* m = inv_vp.m;
 #pragma unroll
-        for (int q = 0; q < kTile * kTile / 256; q++) { dmin = fminf(dmin, dv[q]); dmax = fmaxf(dmax, dv[q]); }
-    }
+        for (int q = 0; q < Q; q++) {
+            const int p = threadIdx.x + q * 256;
+            const int x = bx * kTile + (p % kTile), y = by * kTile + (p / kTile);
+            if (x < W && y < H) {
+                const float nx = float(x) / float(W) * 2.0f - 1.0f;                // final_gathering.comp:70,74
+                const float ny = s_ndcy[p / kTile];
+                const float nz = dv[q] * 2.0f - 1.0f;
+                float w4[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, o));
-        dmax = fmaxf(dmax, __shfl_xor_sync(FULL, dmax, o));
+                for (int c = 0; c < 4; c++) w4[c] = (m[c] * nx + m[4 + c] * ny) + (m[8 + c] * nz + m[12 + c]);   // :75
+                float P[3], n[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) P[c] = w4[c] / w4[3];                  // :76
+                n[0] = s_n10[nv[q] & 0x3FFu]; n[1] = s_n10[(nv[q] >> 10) & 0x3FFu]; n[2] = s_n10[(nv[q] >> 20) & 0x3FFu];   // :79
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    r[c] = gmin(r[c], P[c]); r[3 + c] = gmax(r[3 + c], P[c]);
+                    r[6 + c] = gmin(r[6 + c], n[c]); r[9 + c] = gmax(r[9 + c], n[c]);
+                }
+                const float ex = n[0] * P[0], ey = n[1] * P[1], ez = n[2] * P[2];
+                r[12] = gmin(r[12], (ex + ey) + ez);
+                r[13] = gmax(r[13], (fabsf(ex) + fabsf(ey)) + fabsf(ez));
+            }
+        }
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { smin[warp] = dmin; smax[warp] = dmax; }
+    // min / max are exact and order-independent, so the reduction tree does not have to match the oracle's loop
+#pragma unroll
+    for (int i = 0; i < 14; i++) {
+        const bool is_min = i < 3 || (i >= 6 && i < 9) || i == 12;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float other = __shfl_xor_sync(FULL, r[i], o);
+            r[i] = is_min ? gmin(r[i], other) : gmax(r[i], other);
+        }
+        if (lane == 0) sred[warp][i] = r[i];
+    }
     __syncthreads();
-    if (threadIdx.x < 8) {
-        float mn = smin[0], mx = smax[0];
+    if (threadIdx.x < 14) {
+        const int i = threadIdx.x;
+        const bool is_min = i < 3 || (i >= 6 && i < 9) || i == 12;
+        float v = sred[0][i];
 #pragma unroll
-        for (int i = 1; i < 8; i++) { mn = fminf(mn, smin[i]); mx = fmaxf(mx, smax[i]); }
-        const int j = threadIdx.x;
-        float ndcL = float(bx) * float(kTile) / float(W), ndcR = float(bx + 1) * float(kTile) / float(W);
-        float ndcB = float(by) * float(kTile) / float(H), ndcT = float(by + 1) * float(kTile) / float(H);
-        float cx = (j & 2) ? ndcR : ndcL;
-        float cy = (j & 4) ? ndcT : ndcB;
-        float cz = (j & 1) ? mx : mn;
-        scorner[j] = unproject_corner(inv_vp, cx, cy, cz);
+        for (int w = 1; w < 8; w++) v = is_min ? gmin(v, sred[w][i]) : gmax(v, sred[w][i]);
+        reinterpret_cast<float*>(&stb)[i] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const float3* c = scorner;
-        float3 centre = mul3s(add3(add3(add3(c[0], c[1]), add3(c[2], c[3])), add3(add3(c[4], c[5]), add3(c[6], c[7]))), 0.125f);
-        float radius = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) radius = gmax(radius, len3(sub3(c[i], centre)));
-        radius *= 1.01f;
-        ssphere = make_float4(centre.x, centre.y, centre.z, radius);
-    }
-    __syncthreads();
-    const float3 centre = f3(ssphere.x, ssphere.y, ssphere.z);
-    const float nradius = -ssphere.w;
+    const TileBounds tb = stb;
     const int L = N / 16;
     const size_t tile = (size_t)by * gridDim.x + bx;
     for (int k = class_lo + warp; k < class_hi; k += 8) {
@@ -894,13 +923,29 @@ __global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict
             for (int g = 0; g < G; g++) {
                 const int t = base + 32 * g + lane;
                 const uint32_t id = (uint32_t)(k * L + (t < L ? t : 0));
-                r0[g] = __ldg(&records[id].r[0]);                                         // (-pos, nrm.x); centre - p == centre + (-p)
-                r1[g] = __ldg(reinterpret_cast<const float2*>(&records[id].r[1]));
+                r0[g] = __ldg(&records[id].r[0]);                                         // (-pos, nrm.x)
+                r1[g] = __ldg(reinterpret_cast<const float2*>(&records[id].r[1]));        // (nrm.y, nrm.z)
             }
 #pragma unroll
             for (int g = 0; g < G; g++) {
                 const int t = base + 32 * g + lane;
-                const bool found = t < L && dot3(add3(centre, f3(r0[g].x, r0[g].y, r0[g].z)), f3(r0[g].w, r1[g].x, r1[g].y)) >= nradius;
+                const float vv[3] = {-r0[g].x, -r0[g].y, -r0[g].z}, mm[3] = {r0[g].w, r1[g].x, r1[g].y};
+                float S1 = 0.0f, mA = 0.0f, tt = 0.0f, S2 = 0.0f, mB = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float lo = mm[c] * tb.pmin[c], hi = mm[c] * tb.pmax[c];
+                    S1 = S1 + gmax(lo, hi);
+                    mA = mA + gmax(fabsf(lo), fabsf(hi));
+                    const float tk = mm[c] * vv[c];
+                    tt = tt + tk;
+                    mA = mA + fabsf(tk);
+                    const float l2 = tb.nmin[c] * vv[c], h2 = tb.nmax[c] * vv[c];
+                    S2 = S2 + gmax(l2, h2);
+                    mB = mB + gmax(fabsf(l2), fabsf(h2));
+                }
+                const bool keepA = (S1 - tt) > -(1e-5f * mA);
+                const bool keepB = (S2 - tb.emin) > -(1e-5f * (mB + tb.emag));
+                const bool found = t < L && keepA && keepB;
                 const unsigned bal = __ballot_sync(FULL, found);
                 if (found) sub[counter + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(k * L + t);
                 counter += __popc(bal);
@@ -910,10 +955,10 @@ __global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict
     }
 }
 
-int launch_cull_tiled(const float* depth, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp, int class_lo,
-                      int class_hi, uint16_t* lists, cudaStream_t st) {
+int launch_cull_tiled(const float* depth, const uint32_t* face_normal, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
+                      int class_lo, int class_hi, uint16_t* lists, cudaStream_t st) {
     dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile);
-    cull_tiled_kernel<<<grid, 256, 0, st>>>(depth, W, H, records, N, inv_vp, class_lo, class_hi, lists);
+    cull_tiled_kernel<<<grid, 256, 0, st>>>(depth, face_normal, W, H, records, N, inv_vp, class_lo, class_hi, lists);
     return 1;
 }
 

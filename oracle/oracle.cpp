@@ -713,51 +713,74 @@ ORC_API void orc_light_lists(const float* packed_vpl, int N, const uint32_t* com
 
 // =====================================================================================
 // a8: tiled variant (not in the reference snapshot; spec = DESIGN.md section 4, refining SURVEY.md A.8)
-//   block = tile x tile px (the product uses 64: one gathering CTA = one class of one 64x64
-//   tile); bounds = block rect x [min,max] window depth over in-image pixels, 8 proper corners
-//   unprojected with inverse(P*V); the corners are enclosed in a sphere (centre = mean, radius = max
-//   distance * 1.01) and a VPL is kept iff the sphere reaches its positive half-space:
-//   dot(centre - p, n) >= -radius  (the hemisphere rule of light_lists.comp:108-114 on a bounding sphere:
-//   one test instead of eight, conservative). Lists [BY*BX][16][L+1], slot0 = 1+count.
-ORC_API void orc_cull_tiled(const float* depth, int W, int H, const float* packed_vpl, int N,
+//   block = tile x tile px (the product uses 64: one gathering CTA = one class of one 64x64 tile). Every in-image
+//   pixel of the block is unprojected exactly as final_gathering.comp:70-79 does (same matrix, same operation
+//   order), and the block is summarised by 14 numbers: the AABB of the world positions, the component-wise box of
+//   the face normals, emin = min(n . P) and emag = max(|n.x P.x| + |n.y P.y| + |n.z P.z|).
+//   A VPL (position v, normal m) is kept iff neither factor of final_gathering.comp:112 is provably <= 0 for
+//   every pixel of the block:
+//     a <= max_box(m . P) - m . v          (support function of the position AABB)
+//     b <= max_box(n . v) - emin           (support function of the normal box; b = n . (v - P))
+//   each with a slack of 1e-5 x the sum of the magnitudes involved (>= 20x the fp32 rounding of either side), so the
+//   rule never drops a pair whose angleFactor is > 0. Lists [BY*BX][16][L+1], slot0 = 1+count.
+struct TileBounds { vec3 pmin, pmax, nmin, nmax; float emin, emag; };
+static inline bool tile_keeps_vpl(const TileBounds& tb, const vec3& v, const vec3& m) {
+    const float px[3] = {tb.pmin.x, tb.pmin.y, tb.pmin.z}, qx[3] = {tb.pmax.x, tb.pmax.y, tb.pmax.z};
+    const float nx[3] = {tb.nmin.x, tb.nmin.y, tb.nmin.z}, ox[3] = {tb.nmax.x, tb.nmax.y, tb.nmax.z};
+    const float vv[3] = {v.x, v.y, v.z}, mm[3] = {m.x, m.y, m.z};
+    float S1 = 0.0f, mA = 0.0f, t = 0.0f, S2 = 0.0f, mB = 0.0f;
+    for (int k = 0; k < 3; k++) {
+        float lo = mm[k] * px[k], hi = mm[k] * qx[k];
+        S1 = S1 + max(lo, hi);
+        mA = mA + max(fabsf(lo), fabsf(hi));
+        float tk = mm[k] * vv[k];
+        t = t + tk;
+        mA = mA + fabsf(tk);
+        float l2 = nx[k] * vv[k], h2 = ox[k] * vv[k];
+        S2 = S2 + max(l2, h2);
+        mB = mB + max(fabsf(l2), fabsf(h2));
+    }
+    const bool keepA = (S1 - t) > -(1e-5f * mA);
+    const bool keepB = (S2 - tb.emin) > -(1e-5f * (mB + tb.emag));
+    return keepA && keepB;
+}
+
+ORC_API void orc_cull_tiled(const float* depth, const uint32_t* face_normal, int W, int H, const float* vpl, int N,
                             const float* view, const float* proj, int tile, uint16_t* lists) {
     mat4 P(proj), V(view);
-    mat4 inv = inverse(P * V);
+    mat4 inv = inverse(V) * inverse(P);                                   // GIStage.cpp:289, as in a9
     const int BX = (W + tile - 1) / tile, BY = (H + tile - 1) / tile;
-    const float ftile = float(tile);
     const int L = N / 16;
 #pragma omp parallel for schedule(dynamic)
     for (int b = 0; b < BX * BY; b++) {
         int bx = b % BX, by = b / BX;
-        float dmin = INFINITY, dmax = -INFINITY;
+        TileBounds tb;
+        tb.pmin = tb.nmin = vec3(INFINITY); tb.pmax = tb.nmax = vec3(-INFINITY);
+        tb.emin = INFINITY; tb.emag = 0.0f;
         for (int y = by * tile; y < by * tile + tile && y < H; y++)
             for (int x = bx * tile; x < bx * tile + tile && x < W; x++) {
-                float d = depth[(size_t)y * W + x];
-                dmin = min(dmin, d); dmax = max(dmax, d);
+                vec2 v_uv(float(x) / float(W), float(y) / float(H));      // final_gathering.comp:70
+                vec4 ndc = vec4(v_uv, depth[(size_t)y * W + x], 1.0f) * 2.0f - 1.0f;
+                vec4 w4 = inv * ndc;
+                vec3 p = w4.xyz() / w4.w;
+                uint n10 = face_normal[(size_t)y * W + x];
+                vec3 n = vec3(float(n10 & 0x3FFu) / 1023.0f, float((n10 >> 10) & 0x3FFu) / 1023.0f,
+                              float((n10 >> 20) & 0x3FFu) / 1023.0f) * 2.0f - 1.0f;
+                tb.pmin = vec3(min(tb.pmin.x, p.x), min(tb.pmin.y, p.y), min(tb.pmin.z, p.z));
+                tb.pmax = vec3(max(tb.pmax.x, p.x), max(tb.pmax.y, p.y), max(tb.pmax.z, p.z));
+                tb.nmin = vec3(min(tb.nmin.x, n.x), min(tb.nmin.y, n.y), min(tb.nmin.z, n.z));
+                tb.nmax = vec3(max(tb.nmax.x, n.x), max(tb.nmax.y, n.y), max(tb.nmax.z, n.z));
+                float ex = n.x * p.x, ey = n.y * p.y, ez = n.z * p.z;
+                tb.emin = min(tb.emin, (ex + ey) + ez);
+                tb.emag = max(tb.emag, (fabsf(ex) + fabsf(ey)) + fabsf(ez));
             }
-        float ndcL = float(bx) * ftile / float(W), ndcR = float(bx + 1) * ftile / float(W);
-        float ndcB = float(by) * ftile / float(H), ndcT = float(by + 1) * ftile / float(H);
-        vec3 corners[8] = { vec3(ndcL, ndcB, dmin), vec3(ndcL, ndcB, dmax), vec3(ndcR, ndcB, dmin), vec3(ndcR, ndcB, dmax),
-                            vec3(ndcL, ndcT, dmin), vec3(ndcL, ndcT, dmax), vec3(ndcR, ndcT, dmin), vec3(ndcR, ndcT, dmax) };
-        for (int i = 0; i < 8; i++) {
-            vec4 v(corners[i], 1.0f);
-            v = v * 2.0f - 1.0f;
-            v = inv * v;
-            corners[i] = v.xyz() / v.w;
-        }
-        vec3 centre = (((corners[0] + corners[1]) + (corners[2] + corners[3])) + ((corners[4] + corners[5]) + (corners[6] + corners[7]))) * 0.125f;
-        float radius = 0.0f;
-        for (int i = 0; i < 8; i++) radius = max(radius, length(corners[i] - centre));
-        radius *= 1.01f;   // covers |n| up to 1.01 (10-bit normals are not unit) and the rounding of the centre
         for (int k = 0; k < 16; k++) {
             uint16_t* sub = lists + ((size_t)b * 16 + k) * (L + 1);
             uint counter = 1;
             for (int t = 0; t < L; t++) {
                 uint vplID = (uint)(k * L + t);
-                const float* pv = packed_vpl + 4 * (size_t)vplID;
-                vec3 vp(pv[0], pv[1], pv[2]);
-                vec3 vplNormal = unpack3SNFromFloat(pv[3]);
-                if (dot(centre - vp, vplNormal) >= -radius) sub[counter++] = (uint16_t)vplID;
+                const float* pv = vpl + 12 * (size_t)vplID;
+                if (tile_keeps_vpl(tb, vec3(pv[0], pv[1], pv[2]), vec3(pv[4], pv[5], pv[6]))) sub[counter++] = (uint16_t)vplID;
             }
             sub[0] = (uint16_t)counter;
         }

@@ -47,7 +47,7 @@ def load():
         lib.orc_ism_pullpush.argtypes = [P, C.c_int, C.c_float, P, P, P]
         lib.orc_clustering.argtypes = [P, C.c_int, C.c_int, P, C.c_float, P, P]; lib.orc_clustering.restype = C.c_int
         lib.orc_light_lists.argtypes = [P, C.c_int, P, C.c_int, P, P, C.c_int, C.c_int, C.c_float, P]
-        lib.orc_cull_tiled.argtypes = [P, C.c_int, C.c_int, P, C.c_int, P, P, C.c_int, P]
+        lib.orc_cull_tiled.argtypes = [P, P, C.c_int, C.c_int, P, C.c_int, P, P, C.c_int, P]
         lib.orc_final_gather.argtypes = [P, P, C.c_int, C.c_int, P, C.c_int, P, C.c_int, P, P, P, P, C.c_float,
                                          C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          P, P, P, C.c_float, P, P]
@@ -172,13 +172,13 @@ def light_lists(packed_vpl, N, compact_ids, view, proj, W, H, z_far):
     return lists[:n]
 
 
-def cull_tiled(depth, packed_vpl, N, view, proj, tile=64):
+def cull_tiled(depth, normal, vpl, N, view, proj, tile=64):
     H, W = depth.shape
     BX, BY = (W + tile - 1) // tile, (H + tile - 1) // tile
     L = N // 16
     lists = np.zeros((BX * BY, 16, L + 1), np.uint16)
     v, p = _f32(view), _f32(proj)
-    load().orc_cull_tiled(_p(depth), W, H, _p(packed_vpl), N, _p(v), _p(p), tile, _p(lists))
+    load().orc_cull_tiled(_p(depth), _p(normal), W, H, _p(vpl), N, _p(v), _p(p), tile, _p(lists))
     return lists
 
 

@@ -64,7 +64,7 @@ class Case:
         elif key == "light_lists":
             c["light_lists"] = O.light_lists(self.get("packed"), N, self.get("compact"), wl.cam_view, wl.cam_proj, self.W, self.H, self.z_far)
         elif key == "tile_lists":
-            c["tile_lists"] = O.cull_tiled(wl.depth, self.get("packed"), N, wl.cam_view, wl.cam_proj, 64)
+            c["tile_lists"] = O.cull_tiled(wl.depth, wl.normal, self.get("vpl"), N, wl.cam_view, wl.cam_proj, 64)
         else:
             raise KeyError(key)
         return c[key]
