@@ -301,7 +301,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) ctx->use_texture = strcmp(e2, "ldg") != 0;   // A/B switch: tex (default) | ldg
     if (const char* e4 = getenv("MLGI_FG_ORDER")) ctx->fg_class_major = strcmp(e4, "class") == 0;    // A/B switch: tile (default) | class
-    if (const char* e3 = getenv("MLGI_FG_PAIRS")) ctx->fg_pairs = atoi(e3) == 2 ? 2 : 1;         // A/B switch: pixels per thread / 2
+    if (const char* e3 = getenv("MLGI_FG_PAIRS")) ctx->fg_pairs = atoi(e3);         // A/B switch: pixels per thread / 2
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
     *out = ctx;
     return MLGI_OK;

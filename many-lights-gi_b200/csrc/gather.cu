@@ -26,6 +26,7 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a
 __device__ __forceinline__ float2 dup(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsq_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fma_sat(float a, float b, float c) { float r; asm("fma.rn.sat.ftz.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float2 lo2(const float4& q) { return make_float2(q.x, q.y); }
 __device__ __forceinline__ float2 hi2(const float4& q) { return make_float2(q.z, q.w); }
 
@@ -41,7 +42,7 @@ struct PixelPair {
 };
 
 // One staged VPL = VplRecord (5 float4 in shared memory, read by broadcast):
-//   r0 = (-px,-py,-pz,nx) r1 = (ny,nz,32sx,32sy) r2 = (32sz,32ux,32uy,32uz) r3 = (cr,cg,cb,Cx) r4 = (Cy,0,0,0)
+//   r0 = (-px,-py,-pz,nx) r1 = (ny,nz,32sx,32ux) r2 = (32sy,32uy,32sz,32uz) r3 = (cr,cg,cb,0) r4 = (Cx,Cy,0,0)
 //   Cx = 1.5*2^23 + tile_x*64 + 32: adding it with round-down leaves floor(texel x) in the mantissa.
 // VPL scalars enter the packed instructions through their scalar-broadcast operand form (R.F32).
 template <bool SHADOW, bool STATS, bool TEX, int NP>
@@ -65,8 +66,12 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
     if (STATS) listed += nact;
     if (mmax > 0.0f) {
         const float4 r3 = rec[3];
-        float4 r2; float cy;
-        if (SHADOW) { r2 = rec[2]; cy = rec[4].x; }
+        float2 su_x, su_y, su_z, cxy;
+        if (SHADOW) {
+            const float4 r2 = rec[2];
+            su_x = make_float2(r1.z, r1.w); su_y = make_float2(r2.x, r2.y); su_z = make_float2(r2.z, r2.w);
+            cxy = *reinterpret_cast<const float2*>(rec + 4);
+        }
 #pragma unroll
         for (int p = 0; p < NP; p++) {                  // NP independent chains: the compiler interleaves them (ILP)
             const float2 d2 = fma2(dz[p], dz[p], fma2(dy[p], dy[p], mul2(dx[p], dx[p])));
@@ -77,36 +82,40 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
             g.x = fminf(g.x, clampv); g.y = fminf(g.y, clampv);                           // :117
             if (SHADOW) {                                                                 // :119-127
                 const float2 dist = mul2(d2, inv);
-                const float2 sx = fma2(dup(r2.x), dz[p], fma2(dup(r1.w), dy[p], mul2(dup(r1.z), dx[p])));   // 32 * (s . d)
-                const float2 sy = fma2(dup(r2.w), dz[p], fma2(dup(r2.z), dy[p], mul2(dup(r2.y), dx[p])));   // 32 * (u . d)
+                // paraboloid projection, packed by COORDINATE (lane x = 32 s.d, lane y = 32 u.d) with the pixel's offset as
+                // the broadcast operand: (texel x, texel y) of one pixel land in one register pair, which is what TEX takes
+                const float2 p0 = fma2(su_z, dup(dz[p].x), fma2(su_y, dup(dy[p].x), mul2(su_x, dup(dx[p].x))));
+                const float2 p1 = fma2(su_z, dup(dz[p].y), fma2(su_y, dup(dy[p].y), mul2(su_x, dup(dx[p].y))));
                 const float2 den = add2(dist, a[p]);                                      // dist * (1 - v.z), v.z = -a/dist
-                const float2 q = make_float2(rcp_approx(den.x), rcp_approx(den.y));
-                const float2 fx = __ffma2_rd(sx, q, dup(r3.w));                           // 1.5*2^23 + floor(texel x)
-                const float2 fy = __ffma2_rd(sy, q, dup(cy));
-                float2 t = fma2(dist, dup(kz), dup(1.0f));                                // (0.02 - dist/zFar) * 50
+                const float q0 = rcp_approx(den.x), q1 = rcp_approx(den.y);
+                const float2 f0 = __ffma2_rd(p0, dup(q0), cxy);                           // 1.5*2^23 + floor(texel x | y)
+                const float2 f1 = __ffma2_rd(p1, dup(q1), cxy);
+                const float2 tb = fma2(dist, dup(kz), dup(1.0f));                         // (0.02 - dist/zFar) * 50
+                float2 t;
                 if (TEX) {
                     // textureLod(ismDepthSampler, v.xy, 0) with NEAREST + CLAMP_TO_EDGE (final_gathering.comp:122) on the
                     // texture unit: address, clamp and R16-unorm -> float conversion cost no SM instructions. The coordinate
                     // handed over is the already floored texel index (an exact integer), so the unit's own rounding cannot
                     // pick a neighbouring texel.
-                    const float2 kx = add2(fx, dup(-12582912.0f)), ky = add2(fy, dup(-12582912.0f));
+                    const float2 k0 = add2(f0, dup(-12582912.0f)), k1 = add2(f1, dup(-12582912.0f));
                     // both fetches are unconditional: the pixel of the pair that is not lit has its g zeroed below and the
                     // texture unit clamps whatever coordinate it is given (no predicates, no per-branch handle reload)
-                    const float o0 = tex2D<float>(ism_tex, kx.x, ky.x);
-                    const float o1 = tex2D<float>(ism_tex, kx.y, ky.y);
-                    t = fma2(make_float2(o0, o1), dup(50.0f), t);                         // smoothstep(0.98, 1, 1 - (z - occ))
+                    const float o0 = tex2D<float>(ism_tex, k0.x, k0.y);
+                    const float o1 = tex2D<float>(ism_tex, k1.x, k1.y);
+                    // smoothstep(0.98, 1, 1 - (z - occ)); scalar FFMA.SAT: the packed form has no saturate modifier
+                    t.x = fma_sat(o0, 50.0f, tb.x); t.y = fma_sat(o1, 50.0f, tb.y);
                 } else {
-                    int tx0 = __float_as_int(fx.x) - 0x4B400000, ty0 = __float_as_int(fy.x) - 0x4B400000;
-                    int tx1 = __float_as_int(fx.y) - 0x4B400000, ty1 = __float_as_int(fy.y) - 0x4B400000;
+                    int tx0 = __float_as_int(f0.x) - 0x4B400000, ty0 = __float_as_int(f0.y) - 0x4B400000;
+                    int tx1 = __float_as_int(f1.x) - 0x4B400000, ty1 = __float_as_int(f1.y) - 0x4B400000;
                     tx0 = min(max(tx0, 0), A - 1); ty0 = min(max(ty0, 0), A - 1);         // NEAREST, CLAMP_TO_EDGE
                     tx1 = min(max(tx1, 0), A - 1); ty1 = min(max(ty1, 0), A - 1);
                     const uint32_t u0 = __ldg(ism + (uint32_t)(ty0 * A + tx0));
                     const uint32_t u1 = __ldg(ism + (uint32_t)(ty1 * A + tx1));
                     // u16 -> float without the conversion pipe: 2^23 + u as bits, minus 2^23
                     const float2 occ = add2(make_float2(__uint_as_float(0x4B000000u | u0), __uint_as_float(0x4B000000u | u1)), dup(-8388608.0f));
-                    t = fma2(occ, dup(50.0f / 65535.0f), t);                              // smoothstep(0.98, 1, 1 - (z - occ))
+                    t = fma2(occ, dup(50.0f / 65535.0f), tb);
+                    t.x = __saturatef(t.x); t.y = __saturatef(t.y);
                 }
-                t.x = __saturatef(t.x); t.y = __saturatef(t.y);
                 g = mul2(g, mul2(mul2(t, t), fma2(t, dup(-2.0f), dup(3.0f))));            // :125-126
             }
             g.x = m0[p] > 0.0f ? g.x : 0.0f; g.y = m1[p] > 0.0f ? g.y : 0.0f;
