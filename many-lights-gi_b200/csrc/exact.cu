@@ -423,6 +423,19 @@ static constexpr int PP_THREADS = 256;
 
 struct PullSample { float depth, maxDepth, radius; float2 disp; };
 
+// Exact square-root elimination. For a correctly rounded sqrtf and rs >= 0:  sqrtf(x) > rs  <=>  sqrt(x) > m, where
+// m = (rs + nextafter(rs)) / 2 is the rounding boundary above rs  <=>  x > m*m. m has 25 significant bits, so m*m is
+// exact in fp64 and is never itself a float; hence  sqrtf(x) > rs  <=>  x > T  with T = round_down_to_float(m*m).
+// One threshold per coarse tap replaces one square root per (pixel, tap). rs = inf / NaN give T = NaN (never greater,
+// like the original comparison); a negative rs (cannot occur: radii are means of non-negative values) keeps
+// "always greater" through T = -1.
+__device__ __forceinline__ float sqrt_gt_threshold(float rs) {
+    const float next = __uint_as_float(__float_as_uint(rs) + 1u);
+    const double m = ((double)rs + (double)next) * 0.5;
+    const float T = __double2float_rd(m * m);
+    return rs < 0.0f ? -1.0f : T;
+}
+
 // pull.comp:67-123 given the four decoded inputs (absolute input coords ix0.., output coord ox,oy)
 __device__ __forceinline__ float4 pull_combine(const PullSample* smp, int ix0, int iy0, int ox, int oy, int level) {
     const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};   // pull.comp:24
@@ -473,7 +486,7 @@ __device__ __forceinline__ float4 pull_combine(const PullSample* smp, int ix0, i
 // depend on the output pixel is hoisted into PushCoarse once per T (same values, same roundings).
 struct PushCoarse {
     float depth[4], maxDepth[4], radius[4];
-    float rs[4];            // radius * 2^-level                                  (push.comp:104-105)
+    float rs2[4];           // threshold T(radius * 2^-level): sqrt(x) > rs  <=>  x > T           (push.comp:104-108)
     float w0[4];            // 1 if the tap may contribute at all (same ISM, depth != 1.0), else 0   (:77-93)
     float cx[4], cy[4];     // (coarse tap coordinate + 0.5) * 2                   (:98)
     float d2x[4], d2y[4];   // coarse displacement * 2                             (:101)
@@ -495,8 +508,7 @@ __device__ __forceinline__ float4 push_pixel(const PushCoarse& c, int outputPixe
 #pragma unroll
     for (int i = 0; i < 4; i++) {                                             // :96-110
         dv[i] = make_float2((c.cx[i] - ttx) + c.d2x[i], (c.cy[i] - tty) + c.d2y[i]);
-        // (a squared-distance guard band that skips most square roots was measured and is slower: 0.43 vs 0.38 ms)
-        if (sqrtf(dv[i].x * dv[i].x + dv[i].y * dv[i].y) > c.rs[i]) weights[i] = 0.0f;
+        if (dv[i].x * dv[i].x + dv[i].y * dv[i].y > c.rs2[i]) weights[i] = 0.0f;   // == (sqrt(..) > rs), see sqrt_gt_threshold
     }
     float minimum = 9001.0f;                                                  // :113
     float maxDepth = 0.0f;
@@ -556,7 +568,7 @@ __device__ __forceinline__ void push_level(int level, uint32_t* __restrict__ L0,
             const float4 cs = in ? coarse[cy * csz + cx] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             c.depth[i] = cs.x; c.maxDepth[i] = cs.y; c.radius[i] = cs.z;
             const float2 disp = unpack_half2(__float_as_uint(cs.w));
-            c.rs[i] = cs.z * scale;
+            c.rs2[i] = sqrt_gt_threshold(cs.z * scale);
             c.w0[i] = (in && cs.x != 1.0f) ? 1.0f : 0.0f;
             c.cx[i] = (float(Tx - 1 + offx[i]) + 0.5f) * 2.0f; c.cy[i] = (float(Ty - 1 + offy[i]) + 0.5f) * 2.0f;
             c.d2x[i] = disp.x * 2.0f; c.d2y[i] = disp.y * 2.0f;
