@@ -116,6 +116,13 @@ struct mlgi_ctx {
     bool have_vpl = false, have_points = false, have_atlas = false, have_ism = false, have_clustered = false, have_tiled = false, have_gi = false;
     cudaStream_t side = nullptr;          // culling runs beside the ISM build (both only depend on the VPL stage)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // host-input frame (frame_host_impl): G-buffer slabs are uploaded (side), culled (aux), gathered (caller's stream) and
+    // read back (aux) as a pipeline
+    static constexpr int kSlabs = 16;
+    cudaStream_t aux = nullptr, fg2 = nullptr;   // fg2: odd slabs' gathering launches, so that one slab's tail overlaps the next slab
+    cudaEvent_t ev_ism = nullptr;
+    cudaEvent_t ev_up[kSlabs] = {nullptr}, ev_cull[kSlabs] = {nullptr}, ev_fg[kSlabs] = {nullptr};
+    int host_slabs = 6;     // measured at 4K on PCIe 5 x16: 1 slab 3.60 ms, 2: 2.95, 4: 2.49, 6: 2.42, 8: 2.49, 16: 2.51
     cudaEvent_t ev[T_COUNT][2];
     bool ev_used[T_COUNT];
     bool events_created = false;
@@ -299,6 +306,15 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->fg2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_ism, cudaEventDisableTiming);
+    for (int k = 0; k < mlgi_ctx::kSlabs; k++) {
+        cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_cull[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_fg[k], cudaEventDisableTiming);
+    }
+    if (const char* e5 = getenv("MLGI_HOST_SLABS")) ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5)));   // A/B switch
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) ctx->use_texture = strcmp(e2, "ldg") != 0;   // A/B switch: tex (default) | ldg
     if (const char* e4 = getenv("MLGI_FG_ORDER")) ctx->fg_class_major = strcmp(e4, "class") == 0;    // A/B switch: tile (default) | class
     if (const char* e3 = getenv("MLGI_FG_PAIRS")) ctx->fg_pairs = atoi(e3);         // A/B switch: pixels per thread / 2
@@ -314,6 +330,14 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->fg2) cudaStreamDestroy(ctx->fg2);
+    if (ctx->ev_ism) cudaEventDestroy(ctx->ev_ism);
+    for (int k = 0; k < mlgi_ctx::kSlabs; k++) {
+        if (ctx->ev_up[k]) cudaEventDestroy(ctx->ev_up[k]);
+        if (ctx->ev_cull[k]) cudaEventDestroy(ctx->ev_cull[k]);
+        if (ctx->ev_fg[k]) cudaEventDestroy(ctx->ev_fg[k]);
+    }
     for (int g = 0; g < ctx->xch.world; g++)
         if (g != ctx->xch.rank && ctx->xch.peer_base[g]) cudaIpcCloseMemHandle(ctx->xch.peer_base[g]);
     if (ctx->xch.base) cudaFree(ctx->xch.base);
@@ -460,7 +484,7 @@ MLGI_API int mlgi_cull_tiled(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     mat_mul(vi, pi, inv);
     StageTimer t(ctx, T_TILED, st);
     ctx->launches += launch_cull_tiled(gb->depth, gb->face_normal, ctx->cfg.width, ctx->cfg.height, ctx->records, ctx->cfg.vpl_count, to_mat4(inv),
-                                       ctx->cfg.class_lo, ctx->cfg.class_hi, ctx->tile_lists, st);
+                                       ctx->cfg.class_lo, ctx->cfg.class_hi, 0, ctx->TY, ctx->tile_lists, st);
     CK(cudaGetLastError());
     ctx->have_tiled = true;
     return MLGI_OK;
@@ -512,6 +536,7 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     a.enable_shadowing = p->enable_shadowing;
     a.pairs_per_thread = ctx->fg_pairs;
     a.class_major = ctx->fg_class_major;
+    a.tile_begin = 0; a.tile_count = ctx->TX * ctx->TY;
     a.class_lo = ctx->cfg.class_lo; a.class_hi = ctx->cfg.class_hi;
     // output routing: a bound exchange buffer receives the class planes and the raster image is rebuilt by the
     // consumer (mlgi_planar_to_raster) after the all-gather; otherwise the raster image is written directly, plus
@@ -725,6 +750,71 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
     mlgi_gbuffer dg = {ctx->st_depth, ctx->st_normal};
     int rc;
     if ((rc = mlgi_vpl_process(ctx, &dr, light, p, stream))) return rc;
+    const bool whole_image = !ctx->xch.connected && !ctx->planar_ext;
+    if (p->cull_mode == MLGI_CULL_TILED && whole_image && ctx->aux && ctx->fg2 && ctx->host_slabs > 1) {
+        // Slab pipeline: the image is cut into horizontal slabs of whole tile rows. Slab k is uploaded on the side stream,
+        // culled on the aux stream as soon as it has arrived, gathered on the caller's stream (after the ISM build) and
+        // read back on the aux stream while slab k+1 is still being gathered, so PCIe traffic in both directions hides
+        // behind the ISM build and the gathering instead of bracketing them.
+        const int K = std::min(ctx->host_slabs, ctx->TY), W = ctx->cfg.width, H = ctx->cfg.height;
+        int row0[mlgi_ctx::kSlabs + 1];
+        for (int k = 0; k <= K; k++) row0[k] = (int)((long long)ctx->TY * k / K);
+        float vi[16], pi[16], inv[16];
+        mat_inverse(cam->view, vi); mat_inverse(cam->proj, pi); mat_mul(vi, pi, inv);
+        // Enqueue order matters: the host issues ~10 calls per slab, so the first slab's upload and the ISM build are
+        // queued before the remaining slabs -- both the copy engine and the SMs have work while the host is still enqueueing.
+        // The uploads need no ordering against earlier work: this call returns only after every reader of the staging
+        // buffers has finished. Culling waits for the VPL records (ev_fork) and its slab (ev_up).
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        auto upload = [&](int k) -> int {
+            const size_t y0 = (size_t)row0[k] * kTile, y1 = std::min((size_t)H, (size_t)row0[k + 1] * kTile);
+            CK(cudaMemcpyAsync(ctx->st_depth + y0 * W, hg->depth + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
+            CK(cudaMemcpyAsync(ctx->st_normal + y0 * W, hg->face_normal + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
+            CK(cudaEventRecord(ctx->ev_up[k], ctx->side));
+            return MLGI_OK;
+        };
+        if ((rc = upload(0))) return rc;
+        if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;
+        if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;
+        if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;
+        for (int k = 0; k < K; k++) {
+            if (k > 0 && (rc = upload(k))) return rc;
+            CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_up[k], 0));
+            ctx->launches += launch_cull_tiled(ctx->st_depth, ctx->st_normal, W, H, ctx->records, ctx->cfg.vpl_count, to_mat4(inv),
+                                               ctx->cfg.class_lo, ctx->cfg.class_hi, row0[k], row0[k + 1], ctx->tile_lists, ctx->aux);
+            CK(cudaEventRecord(ctx->ev_cull[k], ctx->aux));
+        }
+        ctx->have_tiled = true;
+        GatherArgs a;
+        if ((rc = build_gather_args(ctx, &dg, cam, nullptr, p, &a))) return rc;
+        {
+            // consecutive slabs alternate between the caller's stream and fg2: the gathering kernel's tail (a few long-list
+            // tiles keeping a handful of SMs busy) then overlaps the next slab instead of idling the GPU once per slab
+            StageTimer t(ctx, T_FG, st);
+            CK(cudaEventRecord(ctx->ev_ism, st));
+            CK(cudaStreamWaitEvent(ctx->fg2, ctx->ev_ism, 0));
+            for (int k = 0; k < K; k++) {
+                cudaStream_t fs = (k & 1) ? ctx->fg2 : st;
+                CK(cudaStreamWaitEvent(fs, ctx->ev_cull[k], 0));
+                a.tile_begin = row0[k] * ctx->TX; a.tile_count = (row0[k + 1] - row0[k]) * ctx->TX;
+                ctx->launches += launch_final_gather(a, fs);
+                CK(cudaEventRecord(ctx->ev_fg[k], fs));
+                CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fg[k], 0));
+                if (host_out) {
+                    const size_t y0 = (size_t)row0[k] * kTile, y1 = std::min((size_t)H, (size_t)row0[k + 1] * kTile);
+                    if (packed) CK(cudaMemcpyAsync((uint32_t*)host_out + y0 * W, ctx->gi_packed + y0 * W, (y1 - y0) * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->aux));
+                    else CK(cudaMemcpyAsync((float4*)host_out + y0 * W, ctx->gi + y0 * W, (y1 - y0) * W * sizeof(float4), cudaMemcpyDeviceToHost, ctx->aux));
+                }
+            }
+            CK(cudaEventRecord(ctx->ev_join, ctx->aux));
+            CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        }
+        CK(cudaGetLastError());
+        ctx->have_gi = true;
+        CK(cudaStreamSynchronize(st));
+        return MLGI_OK;
+    }
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));        // also orders the upload after the previous frame's readers
     CK(cudaMemcpyAsync(ctx->st_depth, hg->depth, WH * 4, cudaMemcpyHostToDevice, ctx->side));

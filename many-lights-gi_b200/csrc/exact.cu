@@ -848,15 +848,15 @@ struct TileBounds { float pmin[3], pmax[3], nmin[3], nmax[3], emin, emag; };
 
 __global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict__ depth, const uint32_t* __restrict__ face_normal, int W, int H,
                                                          const VplRecord* __restrict__ records, int N, Mat4 inv_vp, int class_lo,
-                                                         int class_hi, uint16_t* __restrict__ lists) {
+                                                         int class_hi, int tile_y0, uint16_t* __restrict__ lists) {
     __shared__ float sred[8][14];
     __shared__ TileBounds stb;
     __shared__ float s_n10[1024];     // 10-bit channel -> v / 1023 * 2 - 1 (the IEEE division once per code instead of three per pixel)
     __shared__ float s_ndcy[kTile];   // tile row -> y / H * 2 - 1
     for (int i = threadIdx.x; i < 1024; i += 256) s_n10[i] = float(i) / 1023.0f * 2.0f - 1.0f;                 // final_gathering.comp:79
-    if (threadIdx.x < kTile) s_ndcy[threadIdx.x] = float(blockIdx.y * kTile + threadIdx.x) / float(H) * 2.0f - 1.0f;   // :70,74
+    if (threadIdx.x < kTile) s_ndcy[threadIdx.x] = float((blockIdx.y + tile_y0) * kTile + threadIdx.x) / float(H) * 2.0f - 1.0f;   // :70,74
     __syncthreads();
-    const int bx = blockIdx.x, by = blockIdx.y;
+    const int bx = blockIdx.x, by = blockIdx.y + tile_y0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float INF = __int_as_float(0x7f800000);
     float r[14];   // 0-2 pmin, 3-5 pmax, 6-8 nmin, 9-11 nmax, 12 emin, 13 emag
@@ -967,10 +967,11 @@ __global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict
     }
 }
 
+// tile rows [ty0, ty1) only (the host-input frame culls each G-buffer slab as soon as it is uploaded)
 int launch_cull_tiled(const float* depth, const uint32_t* face_normal, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
-                      int class_lo, int class_hi, uint16_t* lists, cudaStream_t st) {
-    dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile);
-    cull_tiled_kernel<<<grid, 256, 0, st>>>(depth, face_normal, W, H, records, N, inv_vp, class_lo, class_hi, lists);
+                      int class_lo, int class_hi, int ty0, int ty1, uint16_t* lists, cudaStream_t st) {
+    dim3 grid((W + kTile - 1) / kTile, ty1 - ty0);
+    cull_tiled_kernel<<<grid, 256, 0, st>>>(depth, face_normal, W, H, records, N, inv_vp, class_lo, class_hi, ty0, lists);
     return 1;
 }
 

@@ -135,11 +135,11 @@ __global__ void __launch_bounds__(256 / (2 * NP)) final_gather_kernel(const Gath
 
     const int ncls = a.class_hi - a.class_lo;
     const int TX = (a.W + kTile - 1) / kTile;
-    const int ntiles = TX * ((a.H + kTile - 1) / kTile);
+    const int ntiles = a.tile_count;
     // CTA order: class-major (all tiles of a class are consecutive, so co-resident CTAs share the class's VPL records
     // and ISM rows in L1/TEX) or tile-major (the 16 class-CTAs of a tile share its G-buffer sectors in L2)
     const int cls = a.class_lo + (a.class_major ? (int)(blockIdx.x / ntiles) : (int)(blockIdx.x % ncls));
-    const int tile = a.class_major ? (int)(blockIdx.x % ntiles) : (int)(blockIdx.x / ncls);
+    const int tile = a.tile_begin + (a.class_major ? (int)(blockIdx.x % ntiles) : (int)(blockIdx.x / ncls));
     const int tile_x = tile % TX, tile_y = tile / TX;
     const int cxo = cls & 3, cyo = cls >> 2;                    // class = (x&3) + 4*(y&3), final_gathering.comp:67,91
     const int L = a.N / 16;
@@ -308,9 +308,8 @@ static void launch_fg_mode(const GatherArgs& a, dim3 grid, cudaStream_t st) {
 }
 
 int launch_final_gather(const GatherArgs& a, cudaStream_t st) {
-    const int TX = (a.W + kTile - 1) / kTile, TY = (a.H + kTile - 1) / kTile;
     const int ncls = a.class_hi - a.class_lo;
-    dim3 grid((unsigned)(TX * TY * ncls));
+    dim3 grid((unsigned)(a.tile_count * ncls));
     if (a.cull_mode == MLGI_CULL_CLUSTERED) launch_fg_mode<MLGI_CULL_CLUSTERED>(a, grid, st);
     else if (a.cull_mode == MLGI_CULL_TILED) launch_fg_mode<MLGI_CULL_TILED>(a, grid, st);
     else launch_fg_mode<MLGI_CULL_NONE>(a, grid, st);

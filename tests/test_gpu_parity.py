@@ -476,6 +476,18 @@ def test_full_size_4k_4096_frame():
     assert np.array_equal(lists[mask], ref_lists[mask])
     gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)
     _check_radiance(gi[:, :, :3], c.gather(mlgi.CULL_TILED, True), "4K/4096")
+    # property: the host-input call (G-buffer slabs uploaded, culled, gathered and read back as a pipeline) returns the
+    # same bits as the device-input frame, and leaves the same tile lists behind
+    torch = _torch()
+    wl = c.wl
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
+    host_gi = torch.zeros((c.H, c.W, 4), dtype=torch.float32).pin_memory()
+    for _ in range(2):      # twice: the second call reuses staging buffers the first one's kernels were reading
+        host_gi.zero_()
+        g.ctx.frame_host(mlgi.make_rsm(h[0], h[1], h[2]), g.light, g.mesh, mlgi.make_gbuffer(h[3], h[4]), g.cam, p, host_gi=host_gi)
+        assert np.array_equal(host_gi.numpy(), gi)
+    assert np.array_equal(g.ctx.download(mlgi.BUF_TILE_LISTS, np.uint16).reshape(ref_lists.shape)[mask], ref_lists[mask])
     g.close()
     # property: two class shards reproduce the same pixels bit for bit
     for lo, hi in ((0, 8), (8, 16)):
