@@ -37,6 +37,9 @@ WORKLOADS = {
 FLOP_LISTED, FLOP_LIT, FLOP_PIXEL = 26.0, 48.0, 60.0
 
 
+PROFILE_FG, PROFILE_PP = "r1_final_gather_final", "r1_pullpush_final"   # committed ncu summaries the traffic figures come from
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -361,6 +364,18 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    def ncu_traffic(name):
+        """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` summary
+        (profiles/<name>.metrics.csv). Only valid for the configuration the capture was taken on."""
+        if args.workload != "4k_4096" or args.cull != "tiled" or world != 1:
+            return None
+        try:
+            import csv
+            m = {r[0]: (r[1], float(r[2])) for r in csv.reader(open(os.path.join(ROOT, "profiles", name + ".metrics.csv"))) if len(r) == 3 and r[0].startswith("dram__bytes")}
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            return sum(v * scale[u] for u, v in m.values()) if len(m) == 2 else None
+        except Exception:
+            return None
     listed, lit = ctx.gather_stats(gb, cam, params)
     npx = (W * H * (hi - lo)) // 16
     fg_flops = FLOP_LISTED * listed + FLOP_LIT * lit + FLOP_PIXEL * npx
@@ -370,13 +385,14 @@ def main():
     pp_bytes = 6.0 * A * A * (hi - lo) / 16.0
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {"kernel": "final_gather_kernel", "bound": "fp32", "achieved": fg_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": fg_tflops / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+                "frac": fg_tflops / fp32_peak if fp32_peak > 0 else None, "traffic": ncu_traffic(PROFILE_FG),
+                "traffic_note": "DRAM bytes per launch (read + write) from profiles/%s.metrics.csv; the kernel is FP32-bound, its algorithmic bytes are 8 B/pixel in + 20 B/pixel out" % PROFILE_FG,
                 "peak_source": "FFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP32-pipe figure; nominal 148*128*2*1.965 GHz = 74.4)",
                 "algorithmic_flops_per_launch": fg_flops, "pairs_listed": listed, "pairs_lit": lit, "pixels": npx,
                 "flop_model": "26*listed + 48*lit + 60*pixels (SURVEY 8d)", "kernel_ms": fg_ms,
                 "share_of_step": fg_ms / ms_step}
     roofline_hbm = {"kernel": "pullpush_kernel", "bound": "hbm", "achieved": pp_bytes / (pp_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": pp_bytes / (pp_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                    "unit": "GB/s", "frac": pp_bytes / (pp_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic(PROFILE_PP),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_launch": pp_bytes, "kernel_ms": pp_ms}
 
