@@ -166,6 +166,13 @@ MLGI_API int mlgi_final_gather(mlgi_ctx*, const mlgi_gbuffer*, const mlgi_camera
 /* n1  gi_blur.frag x2 (GIStage.cpp:308-344) */
 MLGI_API int mlgi_gi_blur(mlgi_ctx*, const mlgi_gbuffer*, const mlgi_camera*, void* stream);
 
+/* n4, ambient term of the deferred composite (deferredshading.frag:69-80 ambientTerm, tonemap :38-43, toSRGB
+ * srgb_utils.glsl): out = sRGB8(tonemap(gi * toLinear(diffuse) * occlusion)). diffuse_rgba8: camera diffuse G-buffer
+ * (device, width*height, r in bits 0-7); occlusion: device fp32 or NULL (= 1, SSAO is out of scope); use_blurred: read
+ * giBlurFinalBuffer (needs mlgi_gi_blur) instead of giBuffer; out_srgb8: device, width*height RGBA8 (alpha 255). */
+MLGI_API int mlgi_composite_ambient(mlgi_ctx*, const uint32_t* diffuse_rgba8, const float* occlusion, float exposure, int use_blurred,
+                                    uint32_t* out_srgb8, void* stream);
+
 /* a10 GIStage::process (GIStage.cpp:346-418) minus the RSM raster: a1..a9 in order, device inputs. */
 MLGI_API int mlgi_frame(mlgi_ctx*, const mlgi_rsm*, const mlgi_camera* light, const mlgi_mesh*,
                         const mlgi_gbuffer*, const mlgi_camera* cam, const mlgi_params*, void* stream);

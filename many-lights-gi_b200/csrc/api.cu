@@ -113,7 +113,7 @@ struct mlgi_ctx {
     uint32_t* st_rsm_diffuse = nullptr; uint32_t* st_rsm_normal = nullptr; float* st_rsm_depth = nullptr;
     float* st_depth = nullptr; uint32_t* st_normal = nullptr;
     // stage bookkeeping
-    bool have_vpl = false, have_points = false, have_atlas = false, have_ism = false, have_clustered = false, have_tiled = false, have_gi = false;
+    bool have_vpl = false, have_points = false, have_atlas = false, have_ism = false, have_clustered = false, have_tiled = false, have_gi = false, have_blur = false;
     cudaStream_t side = nullptr;          // culling runs beside the ISM build (both only depend on the VPL stage)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // host-input frame (frame_host_impl): G-buffer slabs are uploaded (side), culled (aux), gathered (caller's stream) and
@@ -570,7 +570,7 @@ MLGI_API int mlgi_final_gather(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi
         ctx->launches += launch_final_gather(a, st);
     }
     CK(cudaGetLastError());
-    ctx->have_gi = true;
+    ctx->have_gi = true; ctx->have_blur = false;
     return MLGI_OK;
 }
 
@@ -608,7 +608,7 @@ MLGI_API int mlgi_planar_to_raster(mlgi_ctx* ctx, const void* dev_planar16, floa
     else ctx->launches += launch_planar_to_raster((const float4*)dev_planar16, ctx->cfg.width, ctx->cfg.height, 0, 16,
                                              dev_raster ? (float4*)dev_raster : ctx->gi, st);
     CK(cudaGetLastError());
-    ctx->have_gi = true;
+    ctx->have_gi = true; ctx->have_blur = false;
     return MLGI_OK;
 }
 
@@ -668,7 +668,7 @@ MLGI_API int mlgi_exchange_finish(mlgi_ctx* ctx, void* stream) {
     if (ctx->cfg.gi_packed) ctx->launches += launch_planar_packed_to_raster((const uint32_t*)buf, ctx->cfg.width, ctx->cfg.height, ctx->gi_packed, ctx->gi, st);
     else ctx->launches += launch_planar_to_raster((const float4*)buf, ctx->cfg.width, ctx->cfg.height, 0, 16, ctx->gi, st);
     CK(cudaGetLastError());
-    ctx->have_gi = true;
+    ctx->have_gi = true; ctx->have_blur = false;
     return MLGI_OK;
 }
 
@@ -702,6 +702,20 @@ MLGI_API int mlgi_gi_blur(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_came
     StageTimer t(ctx, T_BLUR, st);
     ctx->launches += launch_gi_blur(ctx->gi, gb->depth, gb->face_normal, ctx->cfg.width, ctx->cfg.height, cam->proj[10], cam->proj[14],
                                     ctx->gi_tmp, ctx->gi_blur, st);
+    CK(cudaGetLastError());
+    ctx->have_blur = true;
+    return MLGI_OK;
+}
+
+// ------------------------------------------------------------------------------------- n4 (ambient term only)
+MLGI_API int mlgi_composite_ambient(mlgi_ctx* ctx, const uint32_t* diffuse_rgba8, const float* occlusion, float exposure, int use_blurred,
+                                    uint32_t* out_srgb8, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!diffuse_rgba8 || !out_srgb8) return fail(ctx, MLGI_E_INVALID, "diffuse/out is NULL");
+    if (!ctx->have_gi) return fail(ctx, MLGI_E_ORDER, "mlgi_composite_ambient needs mlgi_final_gather first");
+    if (use_blurred && !ctx->have_blur) return fail(ctx, MLGI_E_ORDER, "mlgi_composite_ambient(use_blurred) needs mlgi_gi_blur first");
+    ctx->launches += launch_composite_ambient(use_blurred ? ctx->gi_blur : ctx->gi, diffuse_rgba8, occlusion, ctx->cfg.width * ctx->cfg.height,
+                                              exposure, out_srgb8, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return MLGI_OK;
 }
@@ -811,7 +825,7 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
             CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         }
         CK(cudaGetLastError());
-        ctx->have_gi = true;
+        ctx->have_gi = true; ctx->have_blur = false;
         CK(cudaStreamSynchronize(st));
         return MLGI_OK;
     }

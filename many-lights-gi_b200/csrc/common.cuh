@@ -202,6 +202,8 @@ struct GatherArgs {
     unsigned long long* stats;  // null, or 2 counters (pairs listed / lit)
 };
 int launch_final_gather(const GatherArgs& a, cudaStream_t st);
+int launch_composite_ambient(const float4* gi, const uint32_t* diffuse_rgba8, const float* occlusion, int n, float exposure,
+                             uint32_t* out_srgb8, cudaStream_t st);
 int launch_gi_blur(const float4* gi, const float* depth, const uint32_t* face_normal, int W, int H, float projA,
                    float projB, float4* tmp, float4* out, cudaStream_t st);
 float measure_fp32_peak_tflops(cudaStream_t st);   // FFMA micro-benchmark: the FP32-pipe roofline denominator

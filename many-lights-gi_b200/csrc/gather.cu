@@ -471,4 +471,34 @@ int launch_gi_blur(const float4* gi, const float* depth, const uint32_t* face_no
     return 2;
 }
 
+// =====================================================================================
+// n4 (reduced to the term that depends on this path): deferredshading.frag:69-80 ambientTerm = gi * toLinear(diffuse) *
+// occlusion, then tonemap (:38-43, Reinhard with exposure) and toSRGB (srgb_utils.glsl, gamma 2.2) -> RGBA8. The direct
+// diffuse / specular terms need the VSM shadow map and are outside SURVEY section 8. HBM-bound: 16 + 4 (+4) B in, 4 B out.
+// =====================================================================================
+__global__ void composite_ambient_kernel(const float4* __restrict__ gi, const uint32_t* __restrict__ diffuse_rgba8, const float* __restrict__ occlusion,
+                                         int n, float exposure, uint32_t* __restrict__ out_srgb8) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 g = gi[i];
+    const uint32_t d = diffuse_rgba8[i];
+    const float occ = occlusion ? occlusion[i] : 1.0f;
+    const float gc[3] = {g.x, g.y, g.z};
+    uint32_t o = 0xFF000000u;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float dl = powf(float((d >> (8 * c)) & 0xFFu) / 255.0f, 2.2f);      // toLinear
+        float v = gc[c] * dl * occ;                                               // ambientTerm
+        v *= exposure; v = v / (1.0f + v);                                        // tonemap
+        v = powf(v, 1.0f / 2.2f);                                                 // toSRGB
+        o |= (uint32_t)__float2int_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f) << (8 * c);
+    }
+    out_srgb8[i] = o;
+}
+int launch_composite_ambient(const float4* gi, const uint32_t* diffuse_rgba8, const float* occlusion, int n, float exposure, uint32_t* out_srgb8,
+                             cudaStream_t st) {
+    composite_ambient_kernel<<<(n + 255) / 256, 256, 0, st>>>(gi, diffuse_rgba8, occlusion, n, exposure, out_srgb8);
+    return 1;
+}
+
 }  // namespace mlgi

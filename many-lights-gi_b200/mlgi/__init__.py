@@ -71,7 +71,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "mlgi_version", "mlgi_default_params", "mlgi_create", "mlgi_destroy", "mlgi_last_error",
     "mlgi_vpl_process", "mlgi_ism_points", "mlgi_ism_set_points", "mlgi_ism_splat", "mlgi_ism_pullpush",
-    "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_frame", "mlgi_frame_host", "mlgi_frame_host_packed",
+    "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_composite_ambient", "mlgi_frame", "mlgi_frame_host", "mlgi_frame_host_packed",
     "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_read_buffer_async", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_exchange_create", "mlgi_exchange_connect", "mlgi_exchange_finish", "mlgi_exchange_status", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
 ]
 
@@ -110,6 +110,7 @@ def load():
     lib.mlgi_cull_tiled.argtypes = [P, C.POINTER(GBuffer), C.POINTER(Camera), C.POINTER(Params), P]
     lib.mlgi_final_gather.argtypes = [P, C.POINTER(GBuffer), C.POINTER(Camera), P, C.POINTER(Params), P]
     lib.mlgi_gi_blur.argtypes = [P, C.POINTER(GBuffer), C.POINTER(Camera), P]
+    lib.mlgi_composite_ambient.argtypes = [P, P, P, C.c_float, C.c_int, P, P]
     lib.mlgi_frame.argtypes = [P, C.POINTER(Rsm), C.POINTER(Camera), C.POINTER(Mesh), C.POINTER(GBuffer), C.POINTER(Camera),
                                C.POINTER(Params), P]
     lib.mlgi_frame_host.argtypes = [P, C.POINTER(Rsm), C.POINTER(Camera), C.POINTER(Mesh), C.POINTER(GBuffer), C.POINTER(Camera),
@@ -220,6 +221,10 @@ class Context:
 
     def gi_blur(self, gb, cam, stream=None):
         self._ck(self.lib.mlgi_gi_blur(self.h, C.byref(gb), C.byref(cam), stream))
+
+    def composite_ambient(self, diffuse_rgba8, out_srgb8, occlusion=None, exposure=1.0, use_blurred=True, stream=None):
+        """ambient term of the deferred composite (device tensors / pointers): sRGB8(tonemap(gi * toLinear(diffuse) * occlusion))"""
+        self._ck(self.lib.mlgi_composite_ambient(self.h, _ptr(diffuse_rgba8), _ptr(occlusion), exposure, int(use_blurred), _ptr(out_srgb8), stream))
 
     def frame(self, rsm, light, mesh, gb, cam, params, stream=None):
         self._ck(self.lib.mlgi_frame(self.h, C.byref(rsm), C.byref(light), C.byref(mesh), C.byref(gb), C.byref(cam),

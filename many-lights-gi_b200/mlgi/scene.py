@@ -117,7 +117,7 @@ class Workload:
         sc = self.scene
         self.cam_view = sc.look_at((-13.0, 2.5, -0.23), (0.009, -0.019, -0.021))
         self.cam_proj = sc.perspective(math.radians(60.0), width / float(height), self.z_near, self.z_far)
-        self.depth, self.normal, _ = sc.render(self.cam_view, self.cam_proj, width, height)
+        self.depth, self.normal, self.diffuse = sc.render(self.cam_view, self.cam_proj, width, height, want_diffuse=True)
         self.set_sun(sun_cycle_position)
 
     def set_sun(self, sun_cycle_position):

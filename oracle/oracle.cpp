@@ -970,6 +970,31 @@ ORC_API void orc_unpack_r11g11b10(const uint32_t* in, long long n, float* rgb) {
 }
 
 // =====================================================================================
+// n4 (ambient term only): deferredshading.frag:69-80 (giColor * toLinear(diffuse) * occlusionFactor), tonemap :38-43,
+// toSRGB srgb_utils.glsl:19-27 (gamma 2.2). gi: W*H*3 fp32, diffuse: RGBA8 (r in bits 0-7), occlusion: W*H fp32 or NULL (= 1).
+// Returns the float sRGB value per channel (out_f, W*H*3) and its 8-bit quantisation (out_srgb8, alpha 255).
+// =====================================================================================
+ORC_API void orc_composite_ambient(const float* gi, const uint32_t* diffuse_rgba8, const float* occlusion, int n, float exposure,
+                                   float* out_f, uint32_t* out_srgb8) {
+#pragma omp parallel for
+    for (int i = 0; i < n; i++) {
+        const uint32_t d = diffuse_rgba8[i];
+        const float occ = occlusion ? occlusion[i] : 1.0f;
+        uint32_t o = 0xFF000000u;
+        for (int c = 0; c < 3; c++) {
+            float diffuseColor = powf(float((d >> (8 * c)) & 0xFFu) / 255.0f, 2.2f);   // toLinear
+            float color = gi[3 * (size_t)i + c] * diffuseColor * occ;                    // ambientTerm
+            color *= exposure;                                                           // tonemap
+            color /= 1.0f + color;
+            color = powf(color, 1.0f / 2.2f);                                            // toSRGB
+            if (out_f) out_f[3 * (size_t)i + c] = color;
+            o |= (uint32_t)lrintf(glsl::min(glsl::max(color, 0.0f), 1.0f) * 255.0f) << (8 * c);
+        }
+        if (out_srgb8) out_srgb8[i] = o;
+    }
+}
+
+// =====================================================================================
 // n1 ("next" row): gi/gi_blur.frag:24-72, two passes (GIStage.cpp:308-344, :425-439)
 //   in/out: W*H*3 fp32. direction 0 = (1,0), 1 = (0,1). texelFetch outside the image is
 //   undefined in GL; here out-of-image taps are skipped (weight 0) -- documented choice.

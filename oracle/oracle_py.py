@@ -54,6 +54,7 @@ def load():
         lib.orc_pack_r11g11b10.argtypes = [P, C.c_longlong, C.c_int, P]
         lib.orc_unpack_r11g11b10.argtypes = [P, C.c_longlong, P]
         lib.orc_gi_blur_pass.argtypes = [P, P, P, C.c_int, C.c_int, P, C.c_int, P]
+        lib.orc_composite_ambient.argtypes = [P, P, P, C.c_int, C.c_float, P, P]
         _lib = lib
     return _lib
 
@@ -213,6 +214,16 @@ def gi_blur(gi_rgb, depth, normal, proj):
     load().orc_gi_blur_pass(_p(g), _p(depth), _p(normal), W, H, _p(pr), 0, _p(tmp))
     load().orc_gi_blur_pass(_p(tmp), _p(depth), _p(normal), W, H, _p(pr), 1, _p(out))
     return out
+
+
+def composite_ambient(gi_rgb, diffuse_rgba8, occlusion=None, exposure=1.0):
+    """returns (float sRGB [H,W,3], RGBA8 [H,W] uint32)"""
+    H, W = diffuse_rgba8.shape
+    g = _f32(gi_rgb); d = np.ascontiguousarray(diffuse_rgba8, dtype=np.uint32)
+    occ = None if occlusion is None else _f32(occlusion)
+    out_f = np.empty((H, W, 3), np.float32); out8 = np.empty((H, W), np.uint32)
+    load().orc_composite_ambient(_p(g), _p(d), _p(occ) if occ is not None else None, W * H, exposure, _p(out_f), _p(out8))
+    return out_f, out8
 
 
 def pack_r11g11b10(rgb):

@@ -313,6 +313,32 @@ def test_n1_blur_within_tolerance(gpu_case):
     np.testing.assert_allclose(blur, ref, rtol=1e-4, atol=1e-6 * float(ref.mean()))
 
 
+def test_n4_ambient_composite_within_one_lsb(gpu_case):
+    """deferredshading.frag ambient term on the blurred and on the raw GI image: sRGB8 within one code of the oracle"""
+    g, c = gpu_case, gpu_case.case
+    import oracle_py as O
+    torch = _torch()
+    p = mlgi.default_params(c.N)
+    g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    diffuse = g.up(c.wl.diffuse)
+    out = torch.zeros((c.H, c.W), dtype=torch.int32, device="cuda:0")
+    with pytest.raises(mlgi.MlgiError):
+        g.ctx.composite_ambient(diffuse, out, use_blurred=True)           # blur has not run for this frame
+    g.ctx.gi_blur(g.gb, g.cam)
+    occ = np.linspace(0.25, 1.0, c.W * c.H, dtype=np.float32).reshape(c.H, c.W)
+    for blurred, occlusion, exposure in ((True, None, 1.0), (False, occ, 2.5)):
+        g.ctx.composite_ambient(diffuse, out, occlusion=None if occlusion is None else g.up(occlusion), exposure=exposure, use_blurred=blurred)
+        torch.cuda.synchronize()
+        src = g.ctx.download(mlgi.BUF_GI_BLUR if blurred else mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
+        _, ref = O.composite_ambient(src, c.wl.diffuse, occlusion, exposure)
+        got = out.cpu().numpy().view(np.uint32)
+        assert np.all(got >> 24 == 0xFF)
+        for ch in range(3):
+            diff = ((got >> (8 * ch)) & 0xFF).astype(np.int32) - ((ref >> (8 * ch)) & 0xFF).astype(np.int32)
+            assert np.abs(diff).max() <= 1
+            assert (diff != 0).mean() < 0.02
+
+
 def test_error_behaviour(case_small):
     g = Gpu(case_small)
     p = mlgi.default_params(case_small.N)

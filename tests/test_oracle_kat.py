@@ -132,3 +132,19 @@ def test_r11g11b10_packing_kats():
     rel = np.abs(back - x) / x
     assert rel[:, :2][x[:, :2] > 7e-5].max() <= 2.0 ** -7 and rel[:, 2][x[:, 2] > 7e-5].max() <= 2.0 ** -6
     assert np.array_equal(O.pack_r11g11b10(back), O.pack_r11g11b10(x))                # idempotent
+
+
+def test_composite_ambient_kats():
+    """n4 ambient term: deferredshading.frag:69-80 + tonemap + toSRGB on hand-computed values"""
+    gi = np.array([[[0.0, 1.0, 3.0], [0.5, 0.5, 0.5]]], np.float32)
+    diffuse = np.array([[0x00FFFFFF, 0x000080FF]], np.uint32)          # (1,1,1) and (1, 128/255, 0)
+    f, q = O.composite_ambient(gi, diffuse, None, 1.0)
+    expect0 = [0.0, (1.0 / 2.0) ** (1 / 2.2), (3.0 / 4.0) ** (1 / 2.2)]
+    np.testing.assert_allclose(f[0, 0], expect0, rtol=1e-6)
+    d1 = (128 / 255.0) ** 2.2
+    expect1 = [(0.5 / 1.5) ** (1 / 2.2), (0.5 * d1 / (1 + 0.5 * d1)) ** (1 / 2.2), 0.0]
+    np.testing.assert_allclose(f[0, 1], expect1, rtol=1e-5)
+    assert q[0, 0] == (0xFF000000 | (round(expect0[2] * 255) << 16) | (round(expect0[1] * 255) << 8))
+    # occlusion scales the ambient term; exposure scales before the Reinhard curve
+    f2, _ = O.composite_ambient(gi, diffuse, np.full((1, 2), 0.5, np.float32), 2.0)
+    np.testing.assert_allclose(f2, f, rtol=1e-6)
