@@ -89,6 +89,8 @@ struct mlgi_ctx {
     uint32_t* atlas = nullptr; uint16_t* ism = nullptr;
     uint32_t* tile_masks = nullptr; uint32_t* compact_ids = nullptr; uint16_t* light_list_ids = nullptr;
     uint16_t* light_lists = nullptr; uint16_t* tile_lists = nullptr;
+    uint32_t* tile_weight = nullptr; uint32_t* tile_order = nullptr;   // per-tile listed-VPL count and the longest-first tile permutation
+    int fg_sorted = 1; bool tile_order_valid = false;
     uint32_t* gi_packed = nullptr;
     float4* gi = nullptr; float4* gi_planar = nullptr; float4* gi_tmp = nullptr; float4* gi_blur = nullptr;
     unsigned long long* stats = nullptr;
@@ -283,6 +285,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     ALLOC(tile_masks, (size_t)ctx->X * ctx->Y); ALLOC(compact_ids, maxClusters); ALLOC(light_list_ids, maxClusters);
     ALLOC(light_lists, maxClusters * 16 * (ctx->L + 1));
     ALLOC(tile_lists, (size_t)ctx->TX * ctx->TY * 16 * (ctx->L + 1));
+    ALLOC(tile_weight, (size_t)ctx->TX * ctx->TY); ALLOC(tile_order, (size_t)ctx->TX * ctx->TY);
     ALLOC(gi, WH); ALLOC(gi_planar, (size_t)(cfg->class_hi - cfg->class_lo) * PW * PH); ALLOC(gi_tmp, WH); ALLOC(gi_blur, WH);
     ALLOC(stats, 2);
     if (cfg->gi_packed) ALLOC(gi_packed, WH);
@@ -316,6 +319,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     }
     if (const char* e5 = getenv("MLGI_HOST_SLABS")) ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5)));   // A/B switch
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) ctx->use_texture = strcmp(e2, "ldg") != 0;   // A/B switch: tex (default) | ldg
+    if (const char* e6 = getenv("MLGI_FG_SORTED")) ctx->fg_sorted = atoi(e6) != 0;             // A/B switch: longest-list tiles first (default) | row-major
     if (const char* e4 = getenv("MLGI_FG_ORDER")) ctx->fg_class_major = strcmp(e4, "class") == 0;    // A/B switch: tile (default) | class
     if (const char* e3 = getenv("MLGI_FG_PAIRS")) ctx->fg_pairs = atoi(e3);         // A/B switch: pixels per thread / 2
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
@@ -484,9 +488,10 @@ MLGI_API int mlgi_cull_tiled(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     mat_mul(vi, pi, inv);
     StageTimer t(ctx, T_TILED, st);
     ctx->launches += launch_cull_tiled(gb->depth, gb->face_normal, ctx->cfg.width, ctx->cfg.height, ctx->records, ctx->cfg.vpl_count, to_mat4(inv),
-                                       ctx->cfg.class_lo, ctx->cfg.class_hi, 0, ctx->TY, ctx->tile_lists, st);
+                                       ctx->cfg.class_lo, ctx->cfg.class_hi, 0, ctx->TY, ctx->tile_lists, ctx->tile_weight,
+                                       ctx->fg_sorted ? ctx->tile_order : nullptr, st);
     CK(cudaGetLastError());
-    ctx->have_tiled = true;
+    ctx->have_tiled = true; ctx->tile_order_valid = ctx->fg_sorted != 0;
     return MLGI_OK;
 }
 
@@ -537,6 +542,7 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     a.pairs_per_thread = ctx->fg_pairs;
     a.class_major = ctx->fg_class_major;
     a.tile_begin = 0; a.tile_count = ctx->TX * ctx->TY;
+    a.tile_order = (p->cull_mode == MLGI_CULL_TILED && ctx->fg_sorted && ctx->tile_order_valid) ? ctx->tile_order : nullptr;
     a.class_lo = ctx->cfg.class_lo; a.class_hi = ctx->cfg.class_hi;
     // output routing: a bound exchange buffer receives the class planes and the raster image is rebuilt by the
     // consumer (mlgi_planar_to_raster) after the all-gather; otherwise the raster image is written directly, plus
@@ -796,10 +802,10 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
             if (k > 0 && (rc = upload(k))) return rc;
             CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_up[k], 0));
             ctx->launches += launch_cull_tiled(ctx->st_depth, ctx->st_normal, W, H, ctx->records, ctx->cfg.vpl_count, to_mat4(inv),
-                                               ctx->cfg.class_lo, ctx->cfg.class_hi, row0[k], row0[k + 1], ctx->tile_lists, ctx->aux);
+                                               ctx->cfg.class_lo, ctx->cfg.class_hi, row0[k], row0[k + 1], ctx->tile_lists, ctx->tile_weight, nullptr, ctx->aux);
             CK(cudaEventRecord(ctx->ev_cull[k], ctx->aux));
         }
-        ctx->have_tiled = true;
+        ctx->have_tiled = true; ctx->tile_order_valid = false;   // slabs are gathered in row-major order
         GatherArgs a;
         if ((rc = build_gather_args(ctx, &dg, cam, nullptr, p, &a))) return rc;
         {

@@ -173,7 +173,7 @@ int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_
                        const Mat4& inv_vp, float projA, float projB, int W, int H,
                        const SliceTable& tab, int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);
 int launch_cull_tiled(const float* depth, const uint32_t* face_normal, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
-                      int class_lo, int class_hi, int ty0, int ty1, uint16_t* lists, cudaStream_t st);
+                      int class_lo, int class_hi, int ty0, int ty1, uint16_t* lists, uint32_t* tile_weight, uint32_t* tile_order, cudaStream_t st);
 
 struct GatherArgs {
     const float* depth; const uint32_t* face_normal; int W, H;
@@ -187,6 +187,7 @@ struct GatherArgs {
     float zFar, giScale /* giIntensityFactor / vplCount * 16 */, clampv;
     int enable_shadowing;
     int class_major;        // CTA enumeration order (see final_gather_kernel)
+    const uint32_t* tile_order;   // optional permutation of the tiles (longest list first); null = row-major
     int tile_begin, tile_count;   // 64x64 tiles [tile_begin, tile_begin + tile_count) in row-major order (whole image by default)
     int pairs_per_thread;   // 1: 128 threads x 2 pixels, 2: 64 threads x 4 pixels (two independent packed chains)
     int class_lo, class_hi;

@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
     // CTA order: class-major (all tiles of a class are consecutive, so co-resident CTAs share the class's VPL records
     // and ISM rows in L1/TEX) or tile-major (the 16 class-CTAs of a tile share its G-buffer sectors in L2)
     const int cls = a.class_lo + (a.class_major ? (int)(blockIdx.x / ntiles) : (int)(blockIdx.x % ncls));
-    const int tile = a.tile_begin + (a.class_major ? (int)(blockIdx.x % ntiles) : (int)(blockIdx.x / ncls));
+    const int slot = a.tile_begin + (a.class_major ? (int)(blockIdx.x % ntiles) : (int)(blockIdx.x / ncls));
+    const int tile = a.tile_order ? (int)a.tile_order[slot] : slot;
     const int tile_x = tile % TX, tile_y = tile / TX;
     const int cxo = cls & 3, cyo = cls >> 2;                    // class = (x&3) + 4*(y&3), final_gathering.comp:67,91
     const int L = a.N / 16;
