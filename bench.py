@@ -325,14 +325,22 @@ def main():
             def e2e_step():
                 ctx.frame_host_packed(hr, light, mesh, hg, cam, params, host_gi_packed=host_gi, stream=stream)
         else:
-            # N > 1: every rank uploads the inputs, gathers its classes, takes part in the exchange and reads the
-            # assembled image back (the public calls of the multi-GPU path, copies inside the timed region)
-            keys = ("rsm_diffuse", "rsm_normal", "rsm_depth", "depth", "normal")
+            # N > 1: the job's inputs cross PCIe once in total. Every rank uploads the (small) RSM and ITS 1/N slab of the
+            # camera G-buffer rows from pinned host memory, the slabs are all-gathered over NVLink (every rank needs the
+            # whole G-buffer: its pixels are interleaved over the image), then frame + exchange, and every rank reads ITS
+            # slab of the assembled image back -- the union over ranks is the full result on the host.
+            assert H % world == 0, "e2e at N GPUs splits the image rows evenly"
+            y0, y1 = rank * H // world, (rank + 1) * H // world
+            gkeys = ("depth", "normal")
             def e2e_step():
-                for k, src in zip(keys, h):
+                for k, src in zip(("rsm_diffuse", "rsm_normal", "rsm_depth"), h[:3]):
                     d[k].copy_(src.view(d[k].dtype).reshape(d[k].shape), non_blocking=True)
+                for k, src in zip(gkeys, h[3:]):
+                    full = d[k].view(torch.uint8).view(H, -1)
+                    full[y0:y1].copy_(src.view(torch.uint8).view(H, -1)[y0:y1], non_blocking=True)
+                    dist.all_gather_into_tensor(full.view(-1), full[y0:y1].reshape(-1))
                 step()
-                ctx.read_async(mlgi.BUF_GI_PACKED, host_gi, W * H * 4, stream=stream)
+                ctx.read_async(mlgi.BUF_GI_PACKED, host_gi[y0:y1], (y1 - y0) * W * 4, offset=y0 * W * 4, stream=stream)
                 torch.cuda.current_stream().synchronize()
         for _ in range(3):
             e2e_step()
@@ -346,12 +354,14 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = sum(x.numel() * x.element_size() for x in h)
+        nb = lambda x: x.numel() * x.element_size()
+        h2d = sum(nb(x) for x in h) if world == 1 else world * sum(nb(x) for x in h[:3]) + sum(nb(x) for x in h[3:])   # summed over ranks
         e2e = {"value": pairs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_gi.numel() * 4,
                "ms_per_step": dt * 1e3, "steps": n_e2e,
                "call": ("mlgi_frame_host_packed (pinned host RSM + G-buffer in, GL_R11F_G11F_B10F GI image out = the reference's giBuffer "
                         "format, stream sync)") if world == 1 else
-                       "per rank: pinned-host input upload + mlgi_frame + exchange + read-back of the assembled GL_R11F_G11F_B10F image"}
+                       "per rank: pinned-host upload of the RSM and of 1/N of the G-buffer rows + NVLink all-gather of the G-buffer + mlgi_frame + "
+                       "exchange + read-back of 1/N of the assembled GL_R11F_G11F_B10F image rows (bytes summed over ranks)"}
 
     if rank != 0:
         if world > 1:

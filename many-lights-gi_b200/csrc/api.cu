@@ -91,6 +91,8 @@ struct mlgi_ctx {
     uint16_t* light_lists = nullptr; uint16_t* tile_lists = nullptr;
     uint32_t* tile_weight = nullptr; uint32_t* tile_order = nullptr;   // per-tile listed-VPL count and the longest-first tile permutation
     int fg_sorted = 1; bool tile_order_valid = false;
+    bool atlas_precleared = false;  // mlgi_frame clears the atlas on the side stream while the points are generated
+    cudaEvent_t ev_clear = nullptr;
     uint32_t* gi_packed = nullptr;
     float4* gi = nullptr; float4* gi_planar = nullptr; float4* gi_tmp = nullptr; float4* gi_blur = nullptr;
     unsigned long long* stats = nullptr;
@@ -309,6 +311,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_clear, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->fg2, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_ism, cudaEventDisableTiming);
@@ -334,6 +337,7 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_clear) cudaEventDestroy(ctx->ev_clear);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->fg2) cudaStreamDestroy(ctx->fg2);
     if (ctx->ev_ism) cudaEventDestroy(ctx->ev_ism);
@@ -420,13 +424,15 @@ MLGI_API int mlgi_ism_set_points(mlgi_ctx* ctx, const float* points, const uint3
 // ------------------------------------------------------------------------------------- a3
 MLGI_API int mlgi_ism_splat(mlgi_ctx* ctx, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    const bool clear = !ctx->atlas_precleared;      // consumed on every path, so a failed call cannot leave it set
+    ctx->atlas_precleared = false;
     int rc = check_params(ctx, p);
     if (rc) return rc;
     if (!ctx->have_vpl || !ctx->have_points) return fail(ctx, MLGI_E_ORDER, "mlgi_ism_splat needs mlgi_vpl_process and mlgi_ism_points first");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_SPLAT, st);
     ctx->launches += launch_splat(ctx->points, ctx->bucket_start, (const float4*)ctx->packed, ctx->cfg.vpl_count, ctx->S, p->z_far, ctx->atlas,
-                                  ctx->ism_lo, ctx->ism_hi, st);
+                                  ctx->ism_lo, ctx->ism_hi, clear, st);
     CK(cudaGetLastError());
     ctx->have_atlas = true;
     return MLGI_OK;
@@ -739,12 +745,15 @@ MLGI_API int mlgi_frame(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* l
     if (fork) {
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        launch_atlas_clear(ctx->atlas, ctx->S, ctx->ism_lo, ctx->ism_hi, ctx->side);   // beside point generation; joined before the splat
+        CK(cudaEventRecord(ctx->ev_clear, ctx->side));
         void* cs = (void*)ctx->side;
         if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, gb, cam, p, cs))) return rc; }   // :392-403
         else { if ((rc = mlgi_cull_tiled(ctx, gb, cam, p, cs))) return rc; }
         CK(cudaEventRecord(ctx->ev_join, ctx->side));
     }
     if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;                  // :378-389 ISM render
+    if (fork) { CK(cudaStreamWaitEvent(st, ctx->ev_clear, 0)); ctx->atlas_precleared = true; }
     if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;                         //          ISM CS
     if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;             //          pull / push
     if (fork) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));

@@ -162,8 +162,9 @@ int launch_point_generate(const mlgi_mesh& mesh, int N, const uint32_t* tri_offs
                           uint32_t* bucket_start, uint32_t* bucket_cursor, float4* points_sorted,
                           uint32_t* num_points_dev, cudaStream_t st);
 
+void launch_atlas_clear(uint32_t* atlas, int S, int vpl_lo, int vpl_hi, cudaStream_t st);
 int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S,
-                 float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, cudaStream_t st);
+                 float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st);
 int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st);
 
 int launch_clustering(const float* depth, int W, int H, float projA, float projB, const SliceTable& tab,

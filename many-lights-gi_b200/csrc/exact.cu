@@ -290,26 +290,24 @@ int launch_point_generate(const mlgi_mesh& mesh, int N, const uint32_t* tri_offs
 }
 
 // =====================================================================================
-// a3: splat. One warp per bucket (ism.comp: one workgroup of 128 per bucket); the bucket's 16-VPL window
-// (position, unpacked normal, lookAtRH rows, atlas tile) is staged in shared memory per warp; the first <= 4
-// survivors of the two hemisphere tests are projected and written with atomicMin on (depth24<<8 | radius8).
+// a3: splat. One CTA of 128 threads per bucket (ism.comp: one workgroup of 128 per bucket); the bucket's 16-VPL window
+// (position, unpacked normal, lookAtRH rows, atlas tile) is staged in shared memory. A quad of lanes owns one point:
+// each lane runs 4 of the 16 hemisphere tests, the quad ORs its masks, and lane q projects the q-th survivor (the
+// reference keeps the first <= 4, ism.comp:112) and writes it with atomicMin on (depth24<<8 | radius8). The kernel is
+// latency-bound (few points per bucket, long IEEE division / square-root chains), so the four projections of a point
+// run side by side instead of one after the other; the arithmetic per (point, VPL) pair is unchanged.
 // =====================================================================================
 struct WinVpl { float3 pos, nrm, s, u; float tile_x, tile_y; };
-static constexpr int SPLAT_WARPS = 4;      // buckets per CTA: one warp per bucket
+static constexpr int SPLAT_THREADS = 128;
 
-__global__ void __launch_bounds__(SPLAT_WARPS * 32) splat_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ bucket_start,
-                                                                   const float4* __restrict__ packed_vpl, int N, int S, float zFar,
-                                                                   uint32_t* __restrict__ atlas, int bucket0, int num_buckets, int vpl_lo, int vpl_hi) {
-    __shared__ WinVpl win_s[SPLAT_WARPS][16];
-    __shared__ int win_id_s[SPLAT_WARPS][16];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bi = blockIdx.x * SPLAT_WARPS + warp;
-    if (bi >= num_buckets) return;                             // whole warp; only __syncwarp below
-    const int b = (bucket0 + bi) % N;
-    WinVpl* win = win_s[warp];
-    int* win_id = win_id_s[warp];
-    if (lane < 16) {                                           // ism.comp:60-69
-        int index = (b + lane) % N;
+__global__ void __launch_bounds__(SPLAT_THREADS) splat_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ bucket_start,
+                                                               const float4* __restrict__ packed_vpl, int N, int S, float zFar,
+                                                               uint32_t* __restrict__ atlas, int bucket0, int vpl_lo, int vpl_hi) {
+    __shared__ WinVpl win[16];
+    __shared__ int win_id[16];
+    const int b = (bucket0 + (int)blockIdx.x) % N;
+    if (threadIdx.x < 16) {                                    // ism.comp:60-69
+        int index = (b + (int)threadIdx.x) % N;
         float4 pv = packed_vpl[index];
         WinVpl w;
         w.pos = f3(pv.x, pv.y, pv.z);
@@ -321,16 +319,17 @@ __global__ void __launch_bounds__(SPLAT_WARPS * 32) splat_kernel(const float4* _
         float y = float(f2i(ismIndex / float(S)));
         w.tile_x = float(f2i(ismIndex - y * float(S)));
         w.tile_y = float(f2i(y));
-        win[lane] = w;
-        win_id[lane] = index;
+        win[threadIdx.x] = w;
+        win_id[threadIdx.x] = index;
     }
-    __syncwarp();
+    __syncthreads();
     const uint32_t begin = bucket_start[b], end = bucket_start[b + 1];
     const float fA = float(64 * S);
     const float invS = 1.0f / float(S);                        // S is a power of two: x * invS == x / S exactly
     const int A = 64 * S;
-    for (uint32_t base = begin; base < end; base += 32) {      // warp-uniform trip count
-        const uint32_t pid = base + lane;
+    const int q = threadIdx.x & 3, pl = threadIdx.x >> 2;      // slot within the quad, point within the pass
+    for (uint32_t base = begin; base < end; base += SPLAT_THREADS / 4) {   // CTA-uniform trip count
+        const uint32_t pid = base + pl;
         const bool have = pid < end;
         float3 position = f3(0, 0, 0), pointNormal = f3(0, 0, 0);
         float pointRadius = 0.0f;
@@ -343,67 +342,64 @@ __global__ void __launch_bounds__(SPLAT_WARPS * 32) splat_kernel(const float4* _
                              float((nr >> 16) & 0xFFu) / 255.0f * 2.0f - 1.0f);
             pointRadius = float((nr >> 24) & 0xFFu) / 255.0f * 25.0f;
 #pragma unroll
-            for (int i = 0; i < 16; i++) {                         // :94-107
+            for (int k = 0; k < 4; k++) {                          // :94-107, this lane's quarter of the window
+                const int i = 4 * q + k;
                 float3 rel = sub3(position, win[i].pos);
                 bool cull = dot3(win[i].nrm, rel) < 0.0f || dot3(pointNormal, neg3(rel)) < 0.0f;
                 if (!cull) survivors |= 1u << i;
             }
         }
-#pragma unroll 1
-        for (int i = 0; i < 4; i++) {                              // :112-137
-            bool active = survivors != 0;                          // first <= 4 survivors in window order
-            if (!__any_sync(FULL, active)) break;
-            uint32_t val = 0xFFFFFFFFu;
-            uint32_t addr = 0xFFFFFFFFu;
-            if (active) {
-                const int wi = __ffs(survivors) - 1;
-                const WinVpl& w = win[wi];
-                survivors &= survivors - 1;
-                const int gid = win_id[wi];
-                const bool owned = gid >= vpl_lo && gid < vpl_hi;   // multi-GPU shard: only this rank's ISMs
-                float3 rel = sub3(position, w.pos);
-                float dist = len3(rel);
-                // paraboloid_project(rel, dist, nrm, zFar, id, S, true)  ism_utils.glsl:15-40
-                float vx = (w.s.x * rel.x + w.s.y * rel.y) + w.s.z * rel.z;
-                float vy = (w.u.x * rel.x + w.u.y * rel.y) + w.u.z * rel.z;
-                float vz = -dot3(w.nrm, rel);
-                float sg = (vz > 0.0f) ? 1.0f : ((vz < 0.0f) ? -1.0f : 0.0f);
-                vx = vx / dist; vy = vy / dist; vz = vz / dist;
-                vz = 1.0f - vz;
-                vx = vx / vz; vy = vy / vz;
-                vz = dist / zFar;
-                vz = vz * -sg;
-                vx += 1.0f; vy += 1.0f;
-                vx *= 0.5f; vy *= 0.5f;
-                vx += w.tile_x; vy += w.tile_y;
-                vx *= invS; vy *= invS;
-                vx *= fA; vy *= fA;                                // ism.comp:131
-                vz *= 16777216.0f;                                 // :132
-                uint32_t depth24 = f2u(vz);
-                if (depth24 > 0xFFFFFFu) depth24 = 0xFFFFFFu;      // Q10
-                val = (depth24 << 8) | (f2u(pointRadius * 10.0f * 0.5f) & 0xFFu);  // :134-135  (/ sqrt(4.0))
-                int tx = f2i(vx), ty = f2i(vy);
-                if (!owned || tx < 0 || ty < 0 || tx >= A || ty >= A) active = false;
-                else addr = (uint32_t)ty * (uint32_t)A + (uint32_t)tx;
-            }
+        survivors |= __shfl_xor_sync(FULL, survivors, 1);
+        survivors |= __shfl_xor_sync(FULL, survivors, 2);
+        for (int k = 0; k < q; k++) survivors &= survivors - 1;   // lane q takes the q-th survivor in window order (:112-137)
+        if (survivors != 0) {
+            const int wi = __ffs(survivors) - 1;
+            const WinVpl& w = win[wi];
+            const int gid = win_id[wi];
+            const bool owned = gid >= vpl_lo && gid < vpl_hi;   // multi-GPU shard: only this rank's ISMs
+            float3 rel = sub3(position, w.pos);
+            float dist = len3(rel);
+            // paraboloid_project(rel, dist, nrm, zFar, id, S, true)  ism_utils.glsl:15-40
+            float vx = (w.s.x * rel.x + w.s.y * rel.y) + w.s.z * rel.z;
+            float vy = (w.u.x * rel.x + w.u.y * rel.y) + w.u.z * rel.z;
+            float vz = -dot3(w.nrm, rel);
+            float sg = (vz > 0.0f) ? 1.0f : ((vz < 0.0f) ? -1.0f : 0.0f);
+            vx = vx / dist; vy = vy / dist; vz = vz / dist;
+            vz = 1.0f - vz;
+            vx = vx / vz; vy = vy / vz;
+            vz = dist / zFar;
+            vz = vz * -sg;
+            vx += 1.0f; vy += 1.0f;
+            vx *= 0.5f; vy *= 0.5f;
+            vx += w.tile_x; vy += w.tile_y;
+            vx *= invS; vy *= invS;
+            vx *= fA; vy *= fA;                                // ism.comp:131
+            vz *= 16777216.0f;                                 // :132
+            uint32_t depth24 = f2u(vz);
+            if (depth24 > 0xFFFFFFu) depth24 = 0xFFFFFFu;      // Q10
+            const uint32_t val = (depth24 << 8) | (f2u(pointRadius * 10.0f * 0.5f) & 0xFFu);  // :134-135  (/ sqrt(4.0))
+            const int tx = f2i(vx), ty = f2i(vy);
             // imageAtomicMin :136. No warp aggregation: with 16 candidate ISMs x 4096 texels per bucket two lanes of a
             // warp almost never hit the same texel, and ncu showed match.any + redux costing 43% of the kernel's
             // stall samples (profiles/r1_splat_v1); a plain RED.MIN per splat is what the L2 handles best here.
-            if (active) atomicMin(&atlas[addr], val);
+            if (owned && tx >= 0 && ty >= 0 && tx < A && ty < A) atomicMin(&atlas[(uint32_t)ty * (uint32_t)A + (uint32_t)tx], val);
         }
     }
 }
 
 // ISMs [vpl_lo, vpl_hi) live in atlas tile rows [vpl_lo/S, ceil(vpl_hi/S)); only those rows are
 // cleared, and only the buckets whose 16-VPL window can reach the range are visited.
-int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S, float zFar,
-                 uint32_t* atlas, int vpl_lo, int vpl_hi, cudaStream_t st) {
+void launch_atlas_clear(uint32_t* atlas, int S, int vpl_lo, int vpl_hi, cudaStream_t st) {
     const size_t A = 64 * (size_t)S;
     const int ty0 = vpl_lo / S, ty1 = (vpl_hi + S - 1) / S;
     cudaMemsetAsync(atlas + (size_t)ty0 * 64 * A, 0xFF, (size_t)(ty1 - ty0) * 64 * A * sizeof(uint32_t), st);   // ImperfectShadowmap.cpp:212
+}
+int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S, float zFar,
+                 uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st) {
+    if (clear) launch_atlas_clear(atlas, S, vpl_lo, vpl_hi, st);
     int nb = vpl_hi - vpl_lo + 15, b0 = ((vpl_lo - 15) % N + N) % N;
     if (nb >= N) { nb = N; b0 = 0; }
-    splat_kernel<<<(nb + SPLAT_WARPS - 1) / SPLAT_WARPS, SPLAT_WARPS * 32, 0, st>>>(points, bucket_start, packed_vpl, N, S, zFar, atlas, b0, nb, vpl_lo, vpl_hi);
+    splat_kernel<<<nb, SPLAT_THREADS, 0, st>>>(points, bucket_start, packed_vpl, N, S, zFar, atlas, b0, vpl_lo, vpl_hi);
     return 1;
 }
 

@@ -254,8 +254,8 @@ class Context:
         self._ck(self.lib.mlgi_read_buffer(self.h, buf_id, out.ctypes.data, n * dt.itemsize, 0))
         return out
 
-    def read_async(self, buf_id, host_tensor, nbytes, stream=None):
-        self._ck(self.lib.mlgi_read_buffer_async(self.h, buf_id, _ptr(host_tensor), nbytes, 0, stream))
+    def read_async(self, buf_id, host_tensor, nbytes, offset=0, stream=None):
+        self._ck(self.lib.mlgi_read_buffer_async(self.h, buf_id, _ptr(host_tensor), nbytes, offset, stream))
 
     def counts(self):
         a, b = C.c_int(), C.c_int()
