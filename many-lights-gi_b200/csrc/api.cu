@@ -82,10 +82,10 @@ struct mlgi_ctx {
     unsigned long long launches = 0;
     // device buffers
     float* vpl = nullptr; float* packed = nullptr; VplRecord* records = nullptr; int32_t* shuffle = nullptr;
-    uint32_t* tri_offsets = nullptr; uint32_t* scan_tmp = nullptr;
     float4* points_unsorted = nullptr; float4* points = nullptr; uint32_t* point_bucket = nullptr;
     uint32_t* bucket_hist = nullptr; uint32_t* bucket_cursor = nullptr; uint32_t* bucket_start = nullptr;
-    uint32_t* counters = nullptr;   // [0] num points (clamped), [1] generated points, [2] num used clusters
+    uint32_t* counters = nullptr;   // [1] generated points (may exceed max_points: overflow), [2] num used clusters
+    bool grouped_valid = false;     // points / bucket_start (bucket-grouped view of the point list) match points_unsorted / point_bucket
     uint32_t* atlas = nullptr; uint16_t* ism = nullptr;
     uint32_t* tile_masks = nullptr; uint32_t* compact_ids = nullptr; uint16_t* light_list_ids = nullptr;
     uint16_t* light_lists = nullptr; uint16_t* tile_lists = nullptr;
@@ -279,7 +279,6 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
         }                                                                                                     \
     } while (0)
     ALLOC(vpl, (size_t)N * 12); ALLOC(packed, (size_t)N * 4); ALLOC(records, (size_t)N); ALLOC(shuffle, (size_t)N);
-    ALLOC(tri_offsets, (size_t)cfg->max_triangles + 1); ALLOC(scan_tmp, (size_t)cfg->max_triangles / 2048 + 4);
     ALLOC(points_unsorted, (size_t)cfg->max_points); ALLOC(points, (size_t)cfg->max_points); ALLOC(point_bucket, (size_t)cfg->max_points);
     ALLOC(bucket_hist, (size_t)N); ALLOC(bucket_cursor, (size_t)N); ALLOC(bucket_start, (size_t)N + 1);
     ALLOC(counters, 4);
@@ -385,11 +384,10 @@ MLGI_API int mlgi_vpl_process(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_cam
 MLGI_API int mlgi_ism_points(mlgi_ctx* ctx, const mlgi_mesh* mesh, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
     if (!mesh) return fail(ctx, MLGI_E_INVALID, "mesh is NULL");
-    if (mesh->num_triangles == 0) {            // no drawables (ImperfectShadowmap.cpp:225-240 draws nothing): empty buckets
+    if (mesh->num_triangles == 0) {            // no drawables (ImperfectShadowmap.cpp:225-240 draws nothing): no points
         cudaStream_t st0 = (cudaStream_t)stream;
-        CK(cudaMemsetAsync(ctx->bucket_start, 0, sizeof(uint32_t) * ((size_t)ctx->cfg.vpl_count + 1), st0));
         CK(cudaMemsetAsync(ctx->counters, 0, 2 * sizeof(uint32_t), st0));
-        ctx->have_points = true;
+        ctx->have_points = true; ctx->grouped_valid = false;
         return MLGI_OK;
     }
     if (!mesh->vertices || !mesh->normals || !mesh->indices || !mesh->prim_id) return fail(ctx, MLGI_E_INVALID, "mesh is NULL");
@@ -399,25 +397,27 @@ MLGI_API int mlgi_ism_points(mlgi_ctx* ctx, const mlgi_mesh* mesh, const mlgi_pa
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_POINTS, st);
-    ctx->launches += launch_point_counts(*mesh, p->tess_level_factor, ctx->tri_offsets, ctx->scan_tmp, st);
-    ctx->launches += launch_point_generate(*mesh, ctx->cfg.vpl_count, ctx->tri_offsets, ctx->cfg.max_points,
-                                           ctx->points_unsorted, ctx->point_bucket, ctx->bucket_hist, ctx->bucket_start, ctx->bucket_cursor,
-                                           ctx->points, ctx->counters, st);
+    ctx->launches += launch_point_generate(*mesh, ctx->cfg.vpl_count, p->tess_level_factor, ctx->cfg.max_points, ctx->points_unsorted,
+                                           ctx->point_bucket, ctx->counters + 1, st);
     CK(cudaGetLastError());
-    ctx->have_points = true;
+    ctx->have_points = true; ctx->grouped_valid = false;
     return MLGI_OK;
 }
 
+// a caller-provided bucket-grouped point list (the reference's pointBuffer layout, compacted): becomes the ctx point list
 MLGI_API int mlgi_ism_set_points(mlgi_ctx* ctx, const float* points, const uint32_t* bucket_start, int num_points, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
     if (!points || !bucket_start || num_points < 0) return fail(ctx, MLGI_E_INVALID, "points/bucket_start is NULL");
     if (num_points > ctx->cfg.max_points) return fail(ctx, MLGI_E_CAPACITY, "%d points exceed ctx capacity %d", num_points, ctx->cfg.max_points);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemcpyAsync(ctx->points, points, sizeof(float4) * (size_t)num_points, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->points_unsorted, points, sizeof(float4) * (size_t)num_points, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(ctx->bucket_start, bucket_start, sizeof(uint32_t) * ((size_t)ctx->cfg.vpl_count + 1), cudaMemcpyDeviceToDevice, st));
-    const uint32_t np[2] = {(uint32_t)num_points, (uint32_t)num_points};
-    CK(cudaMemcpyAsync(ctx->counters, np, sizeof(np), cudaMemcpyHostToDevice, st));
-    ctx->have_points = true;
+    ctx->launches += launch_bucket_expand(ctx->bucket_start, ctx->cfg.vpl_count, ctx->point_bucket, st);
+    const uint32_t np = (uint32_t)num_points;
+    CK(cudaMemcpyAsync(ctx->counters + 1, &np, sizeof(np), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));              // np lives on this stack frame
+    ctx->have_points = true; ctx->grouped_valid = true;
     return MLGI_OK;
 }
 
@@ -431,8 +431,8 @@ MLGI_API int mlgi_ism_splat(mlgi_ctx* ctx, const mlgi_params* p, void* stream) {
     if (!ctx->have_vpl || !ctx->have_points) return fail(ctx, MLGI_E_ORDER, "mlgi_ism_splat needs mlgi_vpl_process and mlgi_ism_points first");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_SPLAT, st);
-    ctx->launches += launch_splat(ctx->points, ctx->bucket_start, (const float4*)ctx->packed, ctx->cfg.vpl_count, ctx->S, p->z_far, ctx->atlas,
-                                  ctx->ism_lo, ctx->ism_hi, clear, st);
+    ctx->launches += launch_splat(ctx->points_unsorted, ctx->point_bucket, ctx->counters + 1, ctx->cfg.max_points, ctx->records,
+                                  ctx->cfg.vpl_count, ctx->S, p->z_far, ctx->atlas, ctx->ism_lo, ctx->ism_hi, clear, st);
     CK(cudaGetLastError());
     ctx->have_atlas = true;
     return MLGI_OK;
@@ -887,8 +887,19 @@ MLGI_API int mlgi_get_buffer(mlgi_ctx* ctx, int id, void** dev_ptr, size_t* byte
         case MLGI_BUF_VPL: *dev_ptr = ctx->vpl; *bytes = N * 48; break;
         case MLGI_BUF_PACKED_VPL: *dev_ptr = ctx->packed; *bytes = N * 16; break;
         case MLGI_BUF_SHUFFLE: *dev_ptr = ctx->shuffle; *bytes = N * 4; break;
-        case MLGI_BUF_POINTS: *dev_ptr = ctx->points; *bytes = (size_t)ctx->cfg.max_points * 16; break;
-        case MLGI_BUF_BUCKET_START: *dev_ptr = ctx->bucket_start; *bytes = (N + 1) * 4; break;
+        case MLGI_BUF_POINTS:
+        case MLGI_BUF_BUCKET_START:
+            // the bucket-grouped view (reference layout of pointBuffer) is not needed by the frame; build it on first request
+            if (ctx->have_points && !ctx->grouped_valid) {
+                CK(cudaDeviceSynchronize());
+                ctx->launches += launch_group_points(ctx->points_unsorted, ctx->point_bucket, ctx->counters + 1, ctx->cfg.max_points, ctx->cfg.vpl_count,
+                                                     ctx->bucket_hist, ctx->bucket_cursor, ctx->bucket_start, ctx->points, 0);
+                CK(cudaDeviceSynchronize());
+                ctx->grouped_valid = true;
+            }
+            if (id == MLGI_BUF_POINTS) { *dev_ptr = ctx->points; *bytes = (size_t)ctx->cfg.max_points * 16; }
+            else { *dev_ptr = ctx->bucket_start; *bytes = (N + 1) * 4; }
+            break;
         case MLGI_BUF_ATLAS: *dev_ptr = ctx->atlas; *bytes = AA * 4; break;
         case MLGI_BUF_ISM: *dev_ptr = ctx->ism; *bytes = AA * 2; break;
         case MLGI_BUF_COMPACT_CLUSTER_IDS: *dev_ptr = ctx->compact_ids; *bytes = maxClusters * 4; break;
@@ -935,9 +946,9 @@ MLGI_API int mlgi_get_counts(mlgi_ctx* ctx, int* num_points, int* num_used_clust
     uint32_t h[4];
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h, ctx->counters, sizeof(h), cudaMemcpyDeviceToHost));
-    if (num_points) *num_points = (int)h[0];
+    if (num_points) *num_points = (int)std::min<uint32_t>(h[1], (uint32_t)ctx->cfg.max_points);
     if (num_used_clusters) *num_used_clusters = (int)h[2];
-    if (h[1] > h[0]) return fail(ctx, MLGI_E_CAPACITY, "point buffer overflow: %u points generated, capacity %d", h[1], ctx->cfg.max_points);
+    if (h[1] > (uint32_t)ctx->cfg.max_points) return fail(ctx, MLGI_E_CAPACITY, "point buffer overflow: %u points generated, capacity %d", h[1], ctx->cfg.max_points);
     return MLGI_OK;
 }
 

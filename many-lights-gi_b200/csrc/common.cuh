@@ -155,16 +155,15 @@ int launch_vpl_process(const mlgi_rsm& rsm, int rsm_w, int rsm_h, int N, const M
                        float lightIntensity, int shuffle, const int32_t* shuffled, int S,
                        float* vpl, float* packed, VplRecord* records, cudaStream_t st);
 
-int launch_point_counts(const mlgi_mesh& mesh, float tessLevelFactor, uint32_t* tri_offsets /*ntri+1*/,
-                        uint32_t* scan_tmp, cudaStream_t st);
-int launch_point_generate(const mlgi_mesh& mesh, int N, const uint32_t* tri_offsets,
-                          int max_points, float4* points_unsorted, uint32_t* point_bucket, uint32_t* bucket_hist,
-                          uint32_t* bucket_start, uint32_t* bucket_cursor, float4* points_sorted,
-                          uint32_t* num_points_dev, cudaStream_t st);
-
+int launch_point_generate(const mlgi_mesh& mesh, int N, float tessLevelFactor, int max_points, float4* points, uint32_t* point_bucket,
+                          uint32_t* generated, cudaStream_t st);
+// inspection / injection helpers: bucket-grouped view <-> (point, bucket id) list
+int launch_group_points(const float4* points, const uint32_t* point_bucket, const uint32_t* generated, int max_points, int N,
+                        uint32_t* bucket_hist, uint32_t* bucket_cursor, uint32_t* bucket_start, float4* points_grouped, cudaStream_t st);
+int launch_bucket_expand(const uint32_t* bucket_start, int N, uint32_t* point_bucket, cudaStream_t st);
 void launch_atlas_clear(uint32_t* atlas, int S, int vpl_lo, int vpl_hi, cudaStream_t st);
-int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S,
-                 float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st);
+int launch_splat(const float4* points, const uint32_t* point_bucket, const uint32_t* generated, int max_points, const VplRecord* records,
+                 int N, int S, float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st);
 int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st);
 
 int launch_clustering(const float* depth, int W, int H, float projA, float projB, const SliceTable& tab,

@@ -73,7 +73,6 @@ int launch_vpl_process(const mlgi_rsm& rsm, int rsm_w, int rsm_h, int N, const M
 // =====================================================================================
 static constexpr int SCAN_THREADS = 1024;
 static constexpr int SCAN_ITEMS = 2;
-static constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -102,56 +101,6 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint32_t* __restrict__ in, int n, uint32_t* __restrict__ block_sums) {
-    __shared__ uint32_t ws[32];
-    __shared__ uint32_t total;
-    int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) s += in[base + k];
-    block_exclusive_scan(s, &total, ws);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-// single block: exclusive scan of block_sums in place (loops for > 1024 blocks); writes grand total to block_sums[nb]
-__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(uint32_t* __restrict__ block_sums, int nb) {
-    __shared__ uint32_t ws[32];
-    __shared__ uint32_t total;
-    uint32_t carry = 0;
-    for (int base = 0; base < nb; base += SCAN_THREADS) {
-        int i = base + threadIdx.x;
-        uint32_t v = (i < nb) ? block_sums[i] : 0u;
-        uint32_t e = block_exclusive_scan(v, &total, ws);
-        if (i < nb) block_sums[i] = carry + e;
-        carry += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) block_sums[nb] = carry;
-}
-// out[i] = exclusive prefix; out[n] = total
-__global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(const uint32_t* in, int n, const uint32_t* __restrict__ block_sums,
-                                                                   int nb, uint32_t* out) {   // in may alias out
-    __shared__ uint32_t ws[32];
-    __shared__ uint32_t total;
-    int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS];
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : 0u; s += v[k]; }
-    uint32_t e = block_exclusive_scan(s, &total, ws) + block_sums[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = e; e += v[k]; }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[nb];
-}
-// in may alias out. tmp needs ceil(n/SCAN_BLOCK)+1 words.
-static int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int n, uint32_t* tmp, cudaStream_t st) {
-    int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    if (nb < 1) nb = 1;
-    scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, tmp);
-    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(tmp, nb);
-    scan_final_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, tmp, nb, out);
-    return 3;
-}
-
 // =====================================================================================
 // a2: points. Deterministic tessellator:
 //   n = ceil(clamp(max edge * tessLevelFactor, 1, 64)), n^2 sub-triangles, sub id k enumerates
@@ -166,21 +115,6 @@ __device__ __forceinline__ int tess_n(float3 v0, float3 v1, float3 v2, float tf)
     return f2i(ceilf(gclamp(inner, 1.0f, 64.0f)));
 }
 
-__global__ void point_count_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ indices, int ntri, float tf,
-                                   uint32_t* __restrict__ counts) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntri) return;
-    float3 v0 = load_vertex(verts, indices[3 * t]), v1 = load_vertex(verts, indices[3 * t + 1]), v2 = load_vertex(verts, indices[3 * t + 2]);
-    int n = tess_n(v0, v1, v2, tf);
-    counts[t] = (uint32_t)(n * n);
-}
-
-int launch_point_counts(const mlgi_mesh& mesh, float tf, uint32_t* tri_offsets, uint32_t* scan_tmp, cudaStream_t st) {
-    int ntri = mesh.num_triangles;
-    point_count_kernel<<<(ntri + 255) / 256, 256, 0, st>>>(mesh.vertices, mesh.indices, ntri, tf, tri_offsets);
-    return 1 + exclusive_scan_u32(tri_offsets, tri_offsets, ntri, scan_tmp, st);
-}
-
 // random.glsl:34-46,50-59,65
 __device__ __forceinline__ uint32_t hash1(uint32_t x) {
     x += (x << 10u); x ^= (x >> 6u); x += (x << 3u); x ^= (x >> 11u); x += (x << 15u);
@@ -191,73 +125,119 @@ __device__ __forceinline__ float random3(float3 v) {
     return __uint_as_float((h & 0x007FFFFFu) | 0x3F800000u) - 1.0f;
 }
 
+// One warp takes 32 triangles at a time: per-lane sub-triangle counts, a warp scan, ONE atomicAdd per warp for the output
+// range, then the lanes walk the group's points (owner lane found by a 5-step shuffle search over the scan). There is no
+// global scan and no sort: the order of the point list is arbitrary (it depends on which warp allocates first), which is
+// immaterial -- the splat is an order-independent min, and the tests compare point lists as sets. Each point carries its
+// bucket id (ism.geom:57) in point_bucket; the bucket-grouped view of the reference's pointBuffer is only built on request
+// (launch_group_points, used by the inspection API).
 __global__ void __launch_bounds__(256) point_generate_kernel(const float* __restrict__ verts, const float* __restrict__ normals,
                                                              const uint32_t* __restrict__ indices, const uint32_t* __restrict__ prim_id,
-                                                             int ntri, int N, const uint32_t* __restrict__ tri_offsets, int max_points,
-                                                             float4* __restrict__ points_unsorted, uint32_t* __restrict__ point_bucket,
-                                                             uint32_t* __restrict__ bucket_hist, uint32_t* __restrict__ num_points_dev) {
-    const uint32_t total = tri_offsets[ntri];
-    const uint32_t P = total < (uint32_t)max_points ? total : (uint32_t)max_points;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { num_points_dev[0] = P; num_points_dev[1] = total; }
+                                                             int ntri, int N, float tf, int max_points, float4* __restrict__ points,
+                                                             uint32_t* __restrict__ point_bucket, uint32_t* __restrict__ generated) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
     const float sqrtN = sqrtf(float(N));
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-        // triangle owning point p: largest t with tri_offsets[t] <= p
-        int lo = 0, hi = ntri - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (tri_offsets[mid] <= p) lo = mid; else hi = mid - 1;
+    for (int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; group * 32 < ntri; group += warps_total) {
+        const int t = group * 32 + lane;
+        int n_mine = 0;
+        if (t < ntri) {
+            float3 v0 = load_vertex(verts, indices[3 * t]), v1 = load_vertex(verts, indices[3 * t + 1]), v2 = load_vertex(verts, indices[3 * t + 2]);
+            n_mine = tess_n(v0, v1, v2, tf);
         }
-        const int t = lo;
-        const uint32_t start = tri_offsets[t];
-        const int k = (int)(p - start);
-        const int nn = (int)(tri_offsets[t + 1] - start);
-        int n = __float2int_rn(sqrtf(float(nn)));
-        // row j: largest j with 2nj - j^2 <= k
-        int j = (int)(float(n) - sqrtf(float(nn - k)));
-        if (j < 0) j = 0;
-        if (j > n - 1) j = n - 1;
-        while (j > 0 && 2 * n * j - j * j > k) j--;
-        while (j < n - 1 && 2 * n * (j + 1) - (j + 1) * (j + 1) <= k) j++;
-        const int r = k - (2 * n * j - j * j);
-        const int i = r >> 1, down = r & 1;
-        uint32_t i0 = indices[3 * t], i1 = indices[3 * t + 1], i2 = indices[3 * t + 2];
-        float3 v0 = load_vertex(verts, i0), v1 = load_vertex(verts, i1), v2 = load_vertex(verts, i2);
-        float3 te_normal = load_vertex(normals, i0);                        // ism.tese:22
-        int gi[3], gj[3];
-        if (!down) { gi[0] = i; gj[0] = j; gi[1] = i + 1; gj[1] = j; gi[2] = i; gj[2] = j + 1; }
-        else       { gi[0] = i + 1; gj[0] = j; gi[1] = i + 1; gj[1] = j + 1; gi[2] = i; gj[2] = j + 1; }
-        const float fn = float(n);
-        float3 tc[3], pp[3];
+        const uint32_t cnt = (uint32_t)(n_mine * n_mine);
+        uint32_t incl = cnt;
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-            tc[q] = f3(float(n - gi[q] - gj[q]) / fn, float(gi[q]) / fn, float(gj[q]) / fn);
-            pp[q] = add3(add3(mul3s(v0, tc[q].x), mul3s(v1, tc[q].y)), mul3s(v2, tc[q].z));   // ism.tese:9-12
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        const uint32_t excl = incl - cnt;
+        const uint32_t T = __shfl_sync(FULL, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0 && T) base = atomicAdd(generated, T);
+        base = __shfl_sync(FULL, base, 0);
+        for (uint32_t k0 = 0; k0 < T; k0 += 32) {              // warp-uniform trip count
+            const uint32_t kk = k0 + lane;
+            int owner = 0;                                      // largest lane with excl <= kk (zero-count lanes can never win)
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t e = __shfl_sync(FULL, excl, (owner + step) & 31);
+                if (e <= kk) owner += step;
+            }
+            const uint32_t start = __shfl_sync(FULL, excl, owner);
+            const int n = __shfl_sync(FULL, n_mine, owner);
+            const uint32_t out = base + kk;
+            if (kk >= T || out >= (uint32_t)max_points) continue;
+            const int tt = group * 32 + owner;
+            const int k = (int)(kk - start);
+            const int nn = n * n;
+            // row j: largest j with 2nj - j^2 <= k
+            int j = (int)(float(n) - sqrtf(float(nn - k)));
+            if (j < 0) j = 0;
+            if (j > n - 1) j = n - 1;
+            while (j > 0 && 2 * n * j - j * j > k) j--;
+            while (j < n - 1 && 2 * n * (j + 1) - (j + 1) * (j + 1) <= k) j++;
+            const int r = k - (2 * n * j - j * j);
+            const int i = r >> 1, down = r & 1;
+            uint32_t i0 = indices[3 * tt], i1 = indices[3 * tt + 1], i2 = indices[3 * tt + 2];
+            float3 v0 = load_vertex(verts, i0), v1 = load_vertex(verts, i1), v2 = load_vertex(verts, i2);
+            float3 te_normal = load_vertex(normals, i0);                        // ism.tese:22
+            int gi[3], gj[3];
+            if (!down) { gi[0] = i; gj[0] = j; gi[1] = i + 1; gj[1] = j; gi[2] = i; gj[2] = j + 1; }
+            else       { gi[0] = i + 1; gj[0] = j; gi[1] = i + 1; gj[1] = j + 1; gi[2] = i; gj[2] = j + 1; }
+            const float fn = float(n);
+            float3 tc[3], pp[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                tc[q] = f3(float(n - gi[q] - gj[q]) / fn, float(gi[q]) / fn, float(gj[q]) / fn);
+                pp[q] = add3(add3(mul3s(v0, tc[q].x), mul3s(v1, tc[q].y)), mul3s(v2, tc[q].z));   // ism.tese:9-12
+            }
+            float3 position = div3s(add3(add3(pp[0], pp[1]), pp[2]), 3.0f);       // ism.geom:51
+            float3 bary = div3s(add3(add3(tc[0], tc[1]), tc[2]), 3.0f);           // :52
+            float maxdist = gmax(gmax(len3(sub3(position, pp[0])), len3(sub3(position, pp[1]))), len3(sub3(position, pp[2])));  // :54
+            float sd = float(prim_id[tt] % 4096u) / 4096.0f;                      // :56
+            float3 seed = f3(bary.x + sd, bary.y + sd, bary.z + sd);
+            int bkt = f2i(random3(seed) * float(N));                              // :57
+            if (bkt >= N) bkt = N - 1;
+            float radius = maxdist * sqrtN;                                       // :63
+            uint32_t nr = pack_unorm8(te_normal.x * 0.5f + 0.5f) | (pack_unorm8(te_normal.y * 0.5f + 0.5f) << 8) |
+                          (pack_unorm8(te_normal.z * 0.5f + 0.5f) << 16) | (pack_unorm8(radius / 25.0f) << 24);  // :64
+            points[out] = make_float4(position.x, position.y, position.z, __uint_as_float(nr));
+            point_bucket[out] = (uint32_t)bkt;
         }
-        float3 position = div3s(add3(add3(pp[0], pp[1]), pp[2]), 3.0f);       // ism.geom:51
-        float3 bary = div3s(add3(add3(tc[0], tc[1]), tc[2]), 3.0f);           // :52
-        float maxdist = gmax(gmax(len3(sub3(position, pp[0])), len3(sub3(position, pp[1]))), len3(sub3(position, pp[2])));  // :54
-        float sd = float(prim_id[t] % 4096u) / 4096.0f;                       // :56
-        float3 seed = f3(bary.x + sd, bary.y + sd, bary.z + sd);
-        int base = f2i(random3(seed) * float(N));                             // :57
-        if (base >= N) base = N - 1;
-        float radius = maxdist * sqrtN;                                       // :63
-        uint32_t nr = pack_unorm8(te_normal.x * 0.5f + 0.5f) | (pack_unorm8(te_normal.y * 0.5f + 0.5f) << 8) |
-                      (pack_unorm8(te_normal.z * 0.5f + 0.5f) << 16) | (pack_unorm8(radius / 25.0f) << 24);  // :64
-        points_unsorted[p] = make_float4(position.x, position.y, position.z, __uint_as_float(nr));
-        point_bucket[p] = (uint32_t)base;
-        atomicAdd(&bucket_hist[base], 1u);                                    // :66 (counter only; slot assigned after the scan)
     }
 }
 
-__global__ void __launch_bounds__(256) point_scatter_kernel(const float4* __restrict__ points_unsorted, const uint32_t* __restrict__ point_bucket,
-                                                            const uint32_t* __restrict__ num_points_dev, const uint32_t* __restrict__ bucket_start,
-                                                            uint32_t* __restrict__ bucket_cursor, float4* __restrict__ points_sorted) {
-    const uint32_t P = num_points_dev[0];
+int launch_point_generate(const mlgi_mesh& mesh, int N, float tf, int max_points, float4* points, uint32_t* point_bucket,
+                          uint32_t* generated, cudaStream_t st) {
+    cudaMemsetAsync(generated, 0, sizeof(uint32_t), st);
+    const int warps_needed = (mesh.num_triangles + 31) / 32;
+    const int grid = std::max(1, std::min(148 * 8, (warps_needed + 7) / 8));
+    point_generate_kernel<<<grid, 256, 0, st>>>(mesh.vertices, mesh.normals, mesh.indices, mesh.prim_id, mesh.num_triangles, N, tf,
+                                                max_points, points, point_bucket, generated);
+    return 1;
+}
+
+// ---- bucket-grouped view of the point list (reference layout: pointBuffer[bucket][slot], here compacted with
+// bucket_start[N+1]); built only when the inspection API asks for it ----
+__global__ void __launch_bounds__(256) bucket_hist_kernel(const uint32_t* __restrict__ point_bucket, const uint32_t* __restrict__ generated,
+                                                          int max_points, uint32_t* __restrict__ hist) {
+    const uint32_t P = min(generated[0], (uint32_t)max_points);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) atomicAdd(&hist[point_bucket[p]], 1u);
+}
+__global__ void __launch_bounds__(256) point_scatter_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ point_bucket,
+                                                            const uint32_t* __restrict__ generated, int max_points,
+                                                            const uint32_t* __restrict__ bucket_start, uint32_t* __restrict__ bucket_cursor,
+                                                            float4* __restrict__ points_grouped) {
+    const uint32_t P = min(generated[0], (uint32_t)max_points);
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         uint32_t b = point_bucket[p];
         uint32_t slot = bucket_start[b] + atomicAdd(&bucket_cursor[b], 1u);
-        points_sorted[slot] = points_unsorted[p];
+        points_grouped[slot] = points[p];
     }
+}
+// the reverse (mlgi_ism_set_points: a grouped list injected by the caller): bucket id of every point
+__global__ void __launch_bounds__(256) bucket_expand_kernel(const uint32_t* __restrict__ bucket_start, int N, uint32_t* __restrict__ point_bucket) {
+    for (int b = blockIdx.x; b < N; b += gridDim.x)
+        for (uint32_t p = bucket_start[b] + threadIdx.x; p < bucket_start[b + 1]; p += blockDim.x) point_bucket[p] = (uint32_t)b;
 }
 
 // single-block exclusive scan for the bucket histogram (N <= 16384): out has N+1 entries
@@ -276,61 +256,52 @@ __global__ void __launch_bounds__(SCAN_THREADS) bucket_scan_kernel(const uint32_
     if (threadIdx.x == 0) out[N] = carry;
 }
 
-int launch_point_generate(const mlgi_mesh& mesh, int N, const uint32_t* tri_offsets, int max_points,
-                          float4* points_unsorted, uint32_t* point_bucket, uint32_t* bucket_hist, uint32_t* bucket_start,
-                          uint32_t* bucket_cursor, float4* points_sorted, uint32_t* num_points_dev, cudaStream_t st) {
+int launch_group_points(const float4* points, const uint32_t* point_bucket, const uint32_t* generated, int max_points, int N,
+                        uint32_t* bucket_hist, uint32_t* bucket_cursor, uint32_t* bucket_start, float4* points_grouped, cudaStream_t st) {
     cudaMemsetAsync(bucket_hist, 0, sizeof(uint32_t) * N, st);
     cudaMemsetAsync(bucket_cursor, 0, sizeof(uint32_t) * N, st);
     const int grid = 148 * 8;
-    point_generate_kernel<<<grid, 256, 0, st>>>(mesh.vertices, mesh.normals, mesh.indices, mesh.prim_id, mesh.num_triangles, N,
-                                                tri_offsets, max_points, points_unsorted, point_bucket, bucket_hist, num_points_dev);
+    bucket_hist_kernel<<<grid, 256, 0, st>>>(point_bucket, generated, max_points, bucket_hist);
     bucket_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(bucket_hist, N, bucket_start);
-    point_scatter_kernel<<<grid, 256, 0, st>>>(points_unsorted, point_bucket, num_points_dev, bucket_start, bucket_cursor, points_sorted);
+    point_scatter_kernel<<<grid, 256, 0, st>>>(points, point_bucket, generated, max_points, bucket_start, bucket_cursor, points_grouped);
     return 3;
+}
+int launch_bucket_expand(const uint32_t* bucket_start, int N, uint32_t* point_bucket, cudaStream_t st) {
+    bucket_expand_kernel<<<std::min(N, 148 * 8), 256, 0, st>>>(bucket_start, N, point_bucket);
+    return 1;
 }
 
 // =====================================================================================
-// a3: splat. One CTA of 128 threads per bucket (ism.comp: one workgroup of 128 per bucket); the bucket's 16-VPL window
-// (position, unpacked normal, lookAtRH rows, atlas tile) is staged in shared memory. A quad of lanes owns one point:
-// each lane runs 4 of the 16 hemisphere tests, the quad ORs its masks, and lane q projects the q-th survivor (the
-// reference keeps the first <= 4, ism.comp:112) and writes it with atomicMin on (depth24<<8 | radius8). The kernel is
-// latency-bound (few points per bucket, long IEEE division / square-root chains), so the four projections of a point
-// run side by side instead of one after the other; the arithmetic per (point, VPL) pair is unchanged.
+// a3: splat (ism.comp). Point-parallel: a quad of lanes owns one point of the (unordered) point list. The point's bucket b
+// selects the 16-VPL window b..b+15 (ism.comp:60-69); each lane of the quad runs 4 of the 16 hemisphere tests (:94-107)
+// against the hoisted VPL records, the quad ORs its masks, and lane q projects the q-th survivor (the reference keeps the
+// first <= 4, :112) and writes it with atomicMin on (depth24<<8 | radius8). The window's lookAtRH rows come from the VPL
+// record (32*s, 32*u: the same expressions the reference evaluates per work group, scaled by an exact power of two).
+// No bucket sort and no shared memory: the kernel is latency-bound (long IEEE division / square-root chains), so it is laid
+// out for parallelism -- every (point, survivor) projection is its own lane.
 // =====================================================================================
-struct WinVpl { float3 pos, nrm, s, u; float tile_x, tile_y; };
-static constexpr int SPLAT_THREADS = 128;
-
-__global__ void __launch_bounds__(SPLAT_THREADS) splat_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ bucket_start,
-                                                               const float4* __restrict__ packed_vpl, int N, int S, float zFar,
-                                                               uint32_t* __restrict__ atlas, int bucket0, int vpl_lo, int vpl_hi) {
-    __shared__ WinVpl win[16];
-    __shared__ int win_id[16];
-    const int b = (bucket0 + (int)blockIdx.x) % N;
-    if (threadIdx.x < 16) {                                    // ism.comp:60-69
-        int index = (b + (int)threadIdx.x) % N;
-        float4 pv = packed_vpl[index];
-        WinVpl w;
-        w.pos = f3(pv.x, pv.y, pv.z);
-        w.nrm = unpack3SN(pv.w);
-        float3 up = f3(0.0f, 1.0f, 0.01f);                     // ism_utils.glsl:5-13
-        w.s = normalize3(cross3(w.nrm, up));
-        w.u = cross3(w.s, w.nrm);
-        float ismIndex = float(index);                         // ism_utils.glsl:35-36
-        float y = float(f2i(ismIndex / float(S)));
-        w.tile_x = float(f2i(ismIndex - y * float(S)));
-        w.tile_y = float(f2i(y));
-        win[threadIdx.x] = w;
-        win_id[threadIdx.x] = index;
-    }
-    __syncthreads();
-    const uint32_t begin = bucket_start[b], end = bucket_start[b + 1];
+__global__ void __launch_bounds__(256) splat_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ point_bucket,
+                                                    const uint32_t* __restrict__ generated, int max_points,
+                                                    const VplRecord* __restrict__ records, int N, int S, float zFar,
+                                                    uint32_t* __restrict__ atlas, int vpl_lo, int vpl_hi) {
+    const uint32_t P = min(generated[0], (uint32_t)max_points);
+    const int lane = threadIdx.x & 31, q = lane & 3;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const float fA = float(64 * S);
     const float invS = 1.0f / float(S);                        // S is a power of two: x * invS == x / S exactly
     const int A = 64 * S;
-    const int q = threadIdx.x & 3, pl = threadIdx.x >> 2;      // slot within the quad, point within the pass
-    for (uint32_t base = begin; base < end; base += SPLAT_THREADS / 4) {   // CTA-uniform trip count
-        const uint32_t pid = base + pl;
-        const bool have = pid < end;
+    const bool sharded = vpl_hi - vpl_lo < N;
+    for (uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8u; w0 < P; w0 += warps_total * 8u) {   // warp-uniform
+        const uint32_t pid = w0 + (uint32_t)(lane >> 2);
+        bool have = pid < P;
+        int b = 0;
+        if (have) {
+            b = (int)point_bucket[pid];
+            if (sharded) {                                         // does the window [b, b+15] (mod N) reach this rank's ISMs?
+                const int d0 = ((vpl_lo - b) % N + N) % N;         // distance from b to the first owned slot, going up
+                have = d0 < 16 || (b >= vpl_lo && b < vpl_hi);
+            }
+        }
         float3 position = f3(0, 0, 0), pointNormal = f3(0, 0, 0);
         float pointRadius = 0.0f;
         uint32_t survivors = 0;   // bit i set: window VPL i passed both hemisphere tests
@@ -344,8 +315,11 @@ __global__ void __launch_bounds__(SPLAT_THREADS) splat_kernel(const float4* __re
 #pragma unroll
             for (int k = 0; k < 4; k++) {                          // :94-107, this lane's quarter of the window
                 const int i = 4 * q + k;
-                float3 rel = sub3(position, win[i].pos);
-                bool cull = dot3(win[i].nrm, rel) < 0.0f || dot3(pointNormal, neg3(rel)) < 0.0f;
+                const int id = (b + i) % N;
+                const float4 r0 = __ldg(&records[id].r[0]);
+                const float2 r1 = __ldg(reinterpret_cast<const float2*>(&records[id].r[1]));
+                float3 rel = sub3(position, f3(-r0.x, -r0.y, -r0.z));
+                bool cull = dot3(f3(r0.w, r1.x, r1.y), rel) < 0.0f || dot3(pointNormal, neg3(rel)) < 0.0f;
                 if (!cull) survivors |= 1u << i;
             }
         }
@@ -354,15 +328,22 @@ __global__ void __launch_bounds__(SPLAT_THREADS) splat_kernel(const float4* __re
         for (int k = 0; k < q; k++) survivors &= survivors - 1;   // lane q takes the q-th survivor in window order (:112-137)
         if (survivors != 0) {
             const int wi = __ffs(survivors) - 1;
-            const WinVpl& w = win[wi];
-            const int gid = win_id[wi];
+            const int gid = (b + wi) % N;
             const bool owned = gid >= vpl_lo && gid < vpl_hi;   // multi-GPU shard: only this rank's ISMs
-            float3 rel = sub3(position, w.pos);
+            if (!owned) continue;
+            const float4 r0 = __ldg(&records[gid].r[0]), r1 = __ldg(&records[gid].r[1]), r2 = __ldg(&records[gid].r[2]);
+            const float3 wpos = f3(-r0.x, -r0.y, -r0.z), wnrm = f3(r0.w, r1.x, r1.y);
+            const float3 ws = f3(r1.z * 0.03125f, r2.x * 0.03125f, r2.z * 0.03125f);   // s = normalize(cross(nrm, up))  ism_utils.glsl:5-13
+            const float3 wu = f3(r1.w * 0.03125f, r2.y * 0.03125f, r2.w * 0.03125f);   // u = cross(s, nrm)
+            const float ismIndex = float(gid);                     // ism_utils.glsl:35-36
+            const float yy = float(f2i(ismIndex / float(S)));
+            const float tile_x = float(f2i(ismIndex - yy * float(S))), tile_y = float(f2i(yy));
+            float3 rel = sub3(position, wpos);
             float dist = len3(rel);
             // paraboloid_project(rel, dist, nrm, zFar, id, S, true)  ism_utils.glsl:15-40
-            float vx = (w.s.x * rel.x + w.s.y * rel.y) + w.s.z * rel.z;
-            float vy = (w.u.x * rel.x + w.u.y * rel.y) + w.u.z * rel.z;
-            float vz = -dot3(w.nrm, rel);
+            float vx = (ws.x * rel.x + ws.y * rel.y) + ws.z * rel.z;
+            float vy = (wu.x * rel.x + wu.y * rel.y) + wu.z * rel.z;
+            float vz = -dot3(wnrm, rel);
             float sg = (vz > 0.0f) ? 1.0f : ((vz < 0.0f) ? -1.0f : 0.0f);
             vx = vx / dist; vy = vy / dist; vz = vz / dist;
             vz = 1.0f - vz;
@@ -371,7 +352,7 @@ __global__ void __launch_bounds__(SPLAT_THREADS) splat_kernel(const float4* __re
             vz = vz * -sg;
             vx += 1.0f; vy += 1.0f;
             vx *= 0.5f; vy *= 0.5f;
-            vx += w.tile_x; vy += w.tile_y;
+            vx += tile_x; vy += tile_y;
             vx *= invS; vy *= invS;
             vx *= fA; vy *= fA;                                // ism.comp:131
             vz *= 16777216.0f;                                 // :132
@@ -379,27 +360,24 @@ __global__ void __launch_bounds__(SPLAT_THREADS) splat_kernel(const float4* __re
             if (depth24 > 0xFFFFFFu) depth24 = 0xFFFFFFu;      // Q10
             const uint32_t val = (depth24 << 8) | (f2u(pointRadius * 10.0f * 0.5f) & 0xFFu);  // :134-135  (/ sqrt(4.0))
             const int tx = f2i(vx), ty = f2i(vy);
-            // imageAtomicMin :136. No warp aggregation: with 16 candidate ISMs x 4096 texels per bucket two lanes of a
-            // warp almost never hit the same texel, and ncu showed match.any + redux costing 43% of the kernel's
-            // stall samples (profiles/r1_splat_v1); a plain RED.MIN per splat is what the L2 handles best here.
-            if (owned && tx >= 0 && ty >= 0 && tx < A && ty < A) atomicMin(&atlas[(uint32_t)ty * (uint32_t)A + (uint32_t)tx], val);
+            // imageAtomicMin :136. No warp aggregation: two lanes of a warp almost never hit the same texel, and ncu showed
+            // match.any + redux costing 43% of the first version's stall samples; a plain RED.MIN per splat is what the L2
+            // handles best here.
+            if (tx >= 0 && ty >= 0 && tx < A && ty < A) atomicMin(&atlas[(uint32_t)ty * (uint32_t)A + (uint32_t)tx], val);
         }
     }
 }
 
-// ISMs [vpl_lo, vpl_hi) live in atlas tile rows [vpl_lo/S, ceil(vpl_hi/S)); only those rows are
-// cleared, and only the buckets whose 16-VPL window can reach the range are visited.
+// ISMs [vpl_lo, vpl_hi) live in atlas tile rows [vpl_lo/S, ceil(vpl_hi/S)); only those rows are cleared.
 void launch_atlas_clear(uint32_t* atlas, int S, int vpl_lo, int vpl_hi, cudaStream_t st) {
     const size_t A = 64 * (size_t)S;
     const int ty0 = vpl_lo / S, ty1 = (vpl_hi + S - 1) / S;
     cudaMemsetAsync(atlas + (size_t)ty0 * 64 * A, 0xFF, (size_t)(ty1 - ty0) * 64 * A * sizeof(uint32_t), st);   // ImperfectShadowmap.cpp:212
 }
-int launch_splat(const float4* points, const uint32_t* bucket_start, const float4* packed_vpl, int N, int S, float zFar,
-                 uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st) {
+int launch_splat(const float4* points, const uint32_t* point_bucket, const uint32_t* generated, int max_points, const VplRecord* records,
+                 int N, int S, float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st) {
     if (clear) launch_atlas_clear(atlas, S, vpl_lo, vpl_hi, st);
-    int nb = vpl_hi - vpl_lo + 15, b0 = ((vpl_lo - 15) % N + N) % N;
-    if (nb >= N) { nb = N; b0 = 0; }
-    splat_kernel<<<nb, SPLAT_THREADS, 0, st>>>(points, bucket_start, packed_vpl, N, S, zFar, atlas, b0, vpl_lo, vpl_hi);
+    splat_kernel<<<148 * 8, 256, 0, st>>>(points, point_bucket, generated, max_points, records, N, S, zFar, atlas, vpl_lo, vpl_hi);
     return 1;
 }
 
