@@ -131,11 +131,12 @@ private:
 class TiledShading {
 public:
     explicit TiledShading(Context& ctx) : m_ctx(ctx) { tileLists = ctx.buffer<uint16_t>(MLGI_BUF_TILE_LISTS); }
+    // the tile test also bounds the receiver side, so it reads the face normals as well
     void process(const VPLProcessor&, const float view[16], const float projection[16], float zFar, const float* depthBuffer,
-                 mlgi_params params, void* stream = nullptr) {
+                 const uint32_t* faceNormalBuffer, mlgi_params params, void* stream = nullptr) {
         mlgi_camera cam;
         for (int i = 0; i < 16; i++) { cam.view[i] = view[i]; cam.proj[i] = projection[i]; }
-        mlgi_gbuffer gb = {depthBuffer, nullptr};
+        mlgi_gbuffer gb = {depthBuffer, faceNormalBuffer};
         params.z_far = zFar;
         m_ctx.check(mlgi_cull_tiled(m_ctx.get(), &gb, &cam, &params, stream));
     }
@@ -187,7 +188,7 @@ public:
         vplProcessor.process(rsmRenderer, lightIntensity, shuffleLights, p, stream);                                   // :373-376
         ism.process(drawablesMap, vplProcessor, vplStartIndex, vplEndIndex, scaleISMs, pointsOnlyIntoScaledISMs,
                     tessLevelFactor, usePushPull, zFar, p, stream);                                                    // :378-389
-        if (useTiledShading) tiledShading.process(vplProcessor, camera.view, camera.proj, zFar, depthBuffer, p, stream);
+        if (useTiledShading) tiledShading.process(vplProcessor, camera.view, camera.proj, zFar, depthBuffer, faceNormalBuffer, p, stream);
         else clusteredShading.process(vplProcessor, camera.view, camera.proj, zFar, vplStartIndex, vplEndIndex, depthBuffer, p, stream);   // :392-403
         compute_final_gathering(stream);                                                                               // :405-408
         if (blurPass) blur(stream);                                                                                    // :410-417

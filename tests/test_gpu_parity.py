@@ -1,10 +1,14 @@
 """Parity tests proper: every stage of the CUDA path, called through the C ABI, against the
 CPU oracle on the same seeded inputs. Bit-exact for integer/byte outputs (atlas, ISM R16,
 cluster ids, light lists, packed normals, buckets); 1e-3 relative for radiance."""
+import os
+
 import numpy as np
 import pytest
 
 import mlgi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -523,3 +527,27 @@ def test_full_size_4k_4096_frame():
         for cls in range(lo, hi):
             assert np.array_equal(part[cls >> 2::4, cls & 3::4], gi[cls >> 2::4, cls & 3::4])
         s.close()
+
+
+def test_cpp_stage_mirror_demo_frame_matches_python_path():
+    """host/mlgi_stages.hpp (C++ classes with the reference's stage names) drives the same C ABI: the demo program's
+    GI image has the mean radiance of the ctypes path on the same fixture"""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "many-lights-gi_b200", "bin", "demo_frame")
+    assert os.path.exists(exe), "bin/demo_frame missing -- run __graft_entry__.build()"
+    W, H, N = 640, 360, 1024
+    out = subprocess.run([exe, str(W), str(H), str(N)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"mean radiance ([0-9.eE+-]+)", out.stdout)
+    assert m, out.stdout
+    for name in ("VPLP", "ISM render", "ISM CS", "PullPush", "Tiled cull", "FG", "GI blur"):
+        assert name in out.stdout
+    from conftest import Case
+    c = Case(W, H, N, 1024, 256, cell=0.155, clutter=24)
+    g = Gpu(c, max_points=1 << 23)
+    p = mlgi.default_params(N)
+    g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(H, W, 4)[:, :, :3]
+    g.close()
+    assert abs(float(m.group(1)) - float(gi.astype(np.float64).mean())) <= 2e-6 * float(gi.mean()) + 1e-9
