@@ -99,8 +99,6 @@ struct mlgi_ctx {
     cudaTextureObject_t ism_tex = 0;      // ctx ISM atlas as an R16-unorm point-sampled texture
     cudaTextureObject_t override_tex = 0; const uint16_t* override_ptr = nullptr;   // cached texture of the last ISM override
     int use_texture = 1;
-    int fg_pairs = 1;
-    int fg_class_major = 0;
     // fused multi-GPU exchange (mlgi_exchange_*): two parity buffers + flag array in ONE IPC-exportable allocation
     struct Exchange {
         int rank = 0, world = 0;
@@ -322,8 +320,6 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     if (const char* e5 = getenv("MLGI_HOST_SLABS")) ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5)));   // A/B switch
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) ctx->use_texture = strcmp(e2, "ldg") != 0;   // A/B switch: tex (default) | ldg
     if (const char* e6 = getenv("MLGI_FG_SORTED")) ctx->fg_sorted = atoi(e6) != 0;             // A/B switch: longest-list tiles first (default) | row-major
-    if (const char* e4 = getenv("MLGI_FG_ORDER")) ctx->fg_class_major = strcmp(e4, "class") == 0;    // A/B switch: tile (default) | class
-    if (const char* e3 = getenv("MLGI_FG_PAIRS")) ctx->fg_pairs = atoi(e3);         // A/B switch: pixels per thread / 2
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
     *out = ctx;
     return MLGI_OK;
@@ -545,8 +541,6 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     a.giScale = p->gi_intensity_factor / float(p->vpl_end_index - p->vpl_start_index) * 16.0f;   // final_gathering.comp:132
     a.clampv = p->vpl_clamping_value;
     a.enable_shadowing = p->enable_shadowing;
-    a.pairs_per_thread = ctx->fg_pairs;
-    a.class_major = ctx->fg_class_major;
     a.tile_begin = 0; a.tile_count = ctx->TX * ctx->TY;
     a.tile_order = (p->cull_mode == MLGI_CULL_TILED && ctx->fg_sorted && ctx->tile_order_valid) ? ctx->tile_order : nullptr;
     a.class_lo = ctx->cfg.class_lo; a.class_hi = ctx->cfg.class_hi;

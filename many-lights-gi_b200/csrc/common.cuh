@@ -186,10 +186,8 @@ struct GatherArgs {
     SliceTable tab;
     float zFar, giScale /* giIntensityFactor / vplCount * 16 */, clampv;
     int enable_shadowing;
-    int class_major;        // CTA enumeration order (see final_gather_kernel)
     const uint32_t* tile_order;   // optional permutation of the tiles (longest list first); null = row-major
     int tile_begin, tile_count;   // 64x64 tiles [tile_begin, tile_begin + tile_count) in row-major order (whole image by default)
-    int pairs_per_thread;   // 1: 128 threads x 2 pixels, 2: 64 threads x 4 pixels (two independent packed chains)
     int class_lo, class_hi;
     float4* out_raster;     // may be null
     float4* out_planar;     // may be null; plane of class c starts at (c - planar_class0) * PH * PW

@@ -143,11 +143,10 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
 
     const int ncls = a.class_hi - a.class_lo;
     const int TX = (a.W + kTile - 1) / kTile;
-    const int ntiles = a.tile_count;
-    // CTA order: class-major (all tiles of a class are consecutive, so co-resident CTAs share the class's VPL records
-    // and ISM rows in L1/TEX) or tile-major (the 16 class-CTAs of a tile share its G-buffer sectors in L2)
-    const int cls = a.class_lo + (a.class_major ? (int)(blockIdx.x / ntiles) : (int)(blockIdx.x % ncls));
-    const int slot = a.tile_begin + (a.class_major ? (int)(blockIdx.x % ntiles) : (int)(blockIdx.x / ncls));
+    // CTA order: tile-major, class fastest (the class-CTAs of a tile share its G-buffer sectors in L2); the tiles themselves
+    // in the order given by tile_order (longest list first) when the cull kernel provided one
+    const int cls = a.class_lo + (int)(blockIdx.x % ncls);
+    const int slot = a.tile_begin + (int)(blockIdx.x / ncls);
     const int tile = a.tile_order ? (int)a.tile_order[slot] : slot;
     const int tile_x = tile % TX, tile_y = tile / TX;
     const int cxo = cls & 3, cyo = cls >> 2;                    // class = (x&3) + 4*(y&3), final_gathering.comp:67,91
@@ -312,7 +311,6 @@ static void launch_fg_mode(const GatherArgs& a, dim3 grid, cudaStream_t st) {
         else final_gather_kernel<MODE, false, true, false, 1><<<grid, 128, 0, st>>>(a);
     } else if (!sh) final_gather_kernel<MODE, false, false, false, 1><<<grid, 128, 0, st>>>(a);
     else if (!tex) final_gather_kernel<MODE, true, false, false, 1><<<grid, 128, 0, st>>>(a);
-    else if (a.pairs_per_thread == 2) final_gather_kernel<MODE, true, false, true, 2><<<grid, 64, 0, st>>>(a);
     else final_gather_kernel<MODE, true, false, true, 1><<<grid, 128, 0, st>>>(a);
 }
 
