@@ -1,11 +1,18 @@
 // oracle/oracle.cpp -- TEST INFRASTRUCTURE ONLY: CPU oracle for the GI frame pipeline.
 //
-// PARITY UNPINNED BY THE REFERENCE: karyon/many-lights-gi ships no tests, golden
-// vectors or fixtures, it is GLSL that needs a GL driver,
-// and neither glm nor any GLSL compiler exists in this image, so the reference itself
-// cannot be executed here. This file is a line-by-line restatement of the reference's
-// GLSL in C++ against oracle/glsl_compat.h; it is pinned by (i) the known-answer values
-// of SURVEY.md Appendix E (tests/test_oracle_kat.py) and (ii) structural invariants.
+// PARITY PINNED AGAINST THE REFERENCE'S SOURCE TEXT (not against a run of it on a GPU): karyon/many-lights-gi ships
+// no tests, golden vectors or fixtures and is GLSL that needs a GL driver, so the
+// reference program cannot be executed here. Instead oracle/refglsl/ compiles the reference's own shader files -- read
+// from /root/reference/data/shaders where they lie, rewritten only syntactically into C++20 -- with g++ against a small
+// GLSL runtime into oracle/_ref/libref_glsl.so, and tests/test_reference_glsl.py runs every shader stage of the path
+// (a1 vpl_processor.comp, a3 ism.comp, a4+a5 pull.comp / push.comp x12, a6 clustering.comp, a7 light_lists.comp,
+// a9 final_gathering.comp, n1 gi_blur.frag) on the same inputs as this file and compares BIT FOR BIT; committed
+// digests of those outputs (tests/golden/ref_mid.json) repeat the check where /root/reference is not mounted.
+// Not covered that way: a2 (the GL fixed-function tessellator has no source; its deterministic replacement is
+// specified in DESIGN.md) and the evaluation ORDER of floating-point expressions, which GLSL leaves to the
+// implementation (both sides use glm's order). This file is a line-by-line restatement of the reference's GLSL in
+// C++ against oracle/glsl_compat.h; it is additionally pinned by the known-answer values of SURVEY.md Appendix E
+// (tests/test_oracle_kat.py) and by structural invariants.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load this library. The product (libmlgi.so) never links or calls it.
@@ -216,6 +223,8 @@ ORC_API void orc_shuffle_table(int n, int32_t* out) {
     std::shuffle(v.begin(), v.end(), g);
     for (int i = 0; i < n; i++) out[i] = v[i];
 }
+static int g_reference_math = 0;
+ORC_API void orc_set_reference_math(int on) { g_reference_math = on; }
 // torchrun exports OMP_NUM_THREADS=1; the CPU baseline must still use every host core
 ORC_API void orc_set_num_threads(int n) {
 #ifdef _OPENMP
@@ -882,7 +891,10 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
                 if (angleFactor <= 0.0f) continue;                                   // :113-114
                 lit++;
                 float d2 = dist * dist;
-                float attenuation = 1.0f / (d2 * d2);                                // :115 pow(dist, 4.0)
+                // :115 pow(dist, 4.0). The default is two multiplies (what a CPU port would ship); with
+                // orc_set_reference_math(1) it is libm's powf, the evaluation the reference's GLSL source gets when it is
+                // compiled for the CPU (oracle/refglsl) -- the two differ by at most 1 ulp.
+                float attenuation = g_reference_math ? 1.0f / powf(dist, 4.0f) : 1.0f / (d2 * d2);
                 float geometryTerm = angleFactor * attenuation;
                 geometryTerm = min(geometryTerm, vplClampingValue);                  // :117
                 float gLo = geometryTerm, gHi = geometryTerm;

@@ -67,6 +67,11 @@ def _f32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 
 
+def set_reference_math(on):
+    """pow(dist, 4.0) through libm (bit-comparable with oracle/refglsl) instead of two multiplies"""
+    load().orc_set_reference_math(int(on))
+
+
 def num_threads():
     return load().orc_num_threads()
 

@@ -1,0 +1,118 @@
+"""ctypes wrapper of oracle/_ref/libref_glsl.so: the reference's own GLSL sources compiled as C++ (oracle/refglsl/).
+TEST INFRASTRUCTURE ONLY -- used by tests/test_reference_glsl.py and tests/golden/make_ref_golden.py to pin the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "libref_glsl.so")
+_lib = None
+P = C.c_void_p
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIB_PATH)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(P)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def vpl_process(rsm_diffuse, rsm_normal, rsm_depth, N, inv_biased_light_vp, light_intensity, shuffle, table):
+    h, w = rsm_depth.shape
+    vpl = np.zeros((N, 12), np.float32); packed = np.zeros((N, 4), np.float32)
+    m = _f32(inv_biased_light_vp)
+    load().ref_vplproc_run(_p(rsm_diffuse), _p(rsm_normal), _p(rsm_depth), w, h, N, _p(m), C.c_float(light_intensity), int(shuffle),
+                           _p(np.ascontiguousarray(table, np.int32)), _p(vpl), _p(packed))
+    return vpl, packed
+
+
+def ism_splat(points_grouped, bucket_start, packed_vpl, N, z_far, A):
+    """points in the reference's pointBuffer layout: bucket b at [b*stride, b*stride + count_b)"""
+    counts = np.diff(bucket_start.astype(np.int64)).astype(np.uint32)
+    stride = int(max(1, counts.max()))
+    cap = stride * N
+    buf = np.zeros((cap, 4), np.float32)
+    for b in range(N):
+        n = int(counts[b])
+        if n:
+            buf[b * stride:b * stride + n] = points_grouped[int(bucket_start[b]):int(bucket_start[b]) + n]
+    atlas = np.full((A, A), 0xFFFFFFFF, np.uint32)
+    pv = _f32(packed_vpl)
+    load().ref_splat_run(_p(pv), N, _p(buf), cap, _p(counts), C.c_float(z_far), _p(atlas), A)
+    return atlas
+
+
+def ism_pullpush(atlas, z_far, ism_pixel_size=64):
+    """the 6 pull and 6 push passes of ImperfectShadowmap::pullpush (ImperfectShadowmap.cpp:121-182)"""
+    lib = load()
+    atlas = np.ascontiguousarray(atlas, np.uint32)
+    A = atlas.shape[0]
+    pull = {}
+    out = np.zeros((A // 2, A // 2, 4), np.float32)
+    lib.ref_pull0_run(_p(atlas), A, _p(out), 1, C.c_float(z_far), ism_pixel_size); pull[1] = out
+    for l in range(2, 7):
+        out = np.zeros((A >> l, A >> l, 4), np.float32)
+        lib.ref_pull_run(_p(pull[l - 1]), A, _p(out), l, C.c_float(z_far), ism_pixel_size); pull[l] = out
+    push = {6: pull[6]}
+    for l in range(5, 0, -1):
+        out = np.zeros((A >> l, A >> l, 4), np.float32)
+        lib.ref_push_run(_p(pull[l]), _p(push[l + 1]), A, _p(out), l); push[l] = out
+    r16 = np.zeros((A, A), np.uint16)
+    lib.ref_push0_run(_p(atlas), _p(push[1]), A, _p(r16), 0)
+    return r16
+
+
+def clustering(depth, proj, z_far):
+    H, W = depth.shape
+    X, Y = (W + 127) // 128, (H + 127) // 128
+    cap = X * Y * 16
+    compact = np.zeros(cap, np.uint32); ids = np.full((16, Y, X), 0xFFFF, np.uint16); n = np.zeros(1, np.uint32)
+    load().ref_clustering_run(_p(_f32(depth)), W, H, _p(_f32(proj)), C.c_float(z_far), _p(compact), cap, _p(ids), _p(n))
+    return compact[:int(n[0])], ids, int(n[0])
+
+
+def light_lists(packed_vpl, N, compact_ids, W, H, proj, inv_proj_view, z_far, rows=None):
+    """returns the reference's lightLists image [slot][cluster] (r16ui; x = list id, y = class*64 + slot)"""
+    n = len(compact_ids)
+    rows = rows or N
+    img = np.zeros((rows, max(n, 1)), np.uint16)
+    load().ref_lightlists_run(_p(_f32(packed_vpl)), N, _p(np.ascontiguousarray(compact_ids, np.uint32)), n, W, H, _p(_f32(proj)),
+                              _p(_f32(inv_proj_view)), C.c_float(z_far), _p(img), img.shape[1], img.shape[0])
+    return img
+
+
+def final_gather(depth, normal, vpl, N, ism, list_ids, lists_img, proj, view_proj_inverted, z_far, z_near, gi_intensity_factor=3000.0,
+                 clamp=0.001, vpl_start=0, vpl_end=None, shadows=True):
+    H, W = depth.shape
+    out = np.zeros((H, W, 4), np.float32)
+    A = ism.shape[0]
+    Y, X = list_ids.shape[1], list_ids.shape[2]
+    fn = load().ref_gather_run if shadows else load().ref_gather_noshadow_run
+    fn(_p(_f32(depth)), _p(np.ascontiguousarray(normal, np.uint32)), W, H, _p(_f32(vpl)), N, _p(np.ascontiguousarray(ism, np.uint16)), A,
+       _p(np.ascontiguousarray(list_ids, np.uint16)), X, Y, _p(np.ascontiguousarray(lists_img, np.uint16)), lists_img.shape[1], lists_img.shape[0],
+       _p(_f32(proj)), _p(_f32(view_proj_inverted)), C.c_float(z_far), C.c_float(z_near), C.c_float(gi_intensity_factor), C.c_float(clamp),
+       vpl_start, N if vpl_end is None else vpl_end, _p(out))
+    return out[:, :, :3]
+
+
+def gi_blur(gi_rgb, depth, normal, proj):
+    H, W = depth.shape
+    rgba = np.zeros((H, W, 4), np.float32); rgba[:, :, :3] = gi_rgb
+    tmp = np.zeros((H, W, 3), np.float32); out = np.zeros((H, W, 3), np.float32)
+    load().ref_blur_h_run(_p(rgba), _p(_f32(depth)), _p(np.ascontiguousarray(normal, np.uint32)), W, H, _p(_f32(proj)), _p(tmp))
+    rgba[:, :, :3] = tmp
+    load().ref_blur_v_run(_p(rgba), _p(_f32(depth)), _p(np.ascontiguousarray(normal, np.uint32)), W, H, _p(_f32(proj)), _p(out))
+    return out

@@ -82,6 +82,10 @@ class Case:
         return self._c[key]
 
 
+def make_case_mid():
+    return Case(384, 216, 1024, 1024, 256, cell=0.5, clutter=12)
+
+
 @pytest.fixture(scope="session")
 def case_small():
     """ragged 160x100 viewport (not a multiple of 4, 64 or 128), 64 VPLs, coarse mesh (n>1 tessellation)"""
@@ -97,4 +101,4 @@ def case_c1():
 @pytest.fixture(scope="session")
 def case_mid():
     """reference defaults at reduced resolution: 1024 VPLs, 1024x256 RSM, 2048^2 atlas"""
-    return Case(384, 216, 1024, 1024, 256, cell=0.5, clutter=12)
+    return make_case_mid()
