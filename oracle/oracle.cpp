@@ -5,10 +5,10 @@
 // reference program cannot be executed here. Instead oracle/refglsl/ compiles the reference's own shader files -- read
 // from /root/reference/data/shaders where they lie, rewritten only syntactically into C++20 -- with g++ against a small
 // GLSL runtime into oracle/_ref/libref_glsl.so, and tests/test_reference_glsl.py runs every shader stage of the path
-// (a1 vpl_processor.comp, a3 ism.comp, a4+a5 pull.comp / push.comp x12, a6 clustering.comp, a7 light_lists.comp,
+// (a1 vpl_processor.comp, a2 ism.tesc / ism.tese / ism.geom, a3 ism.comp, a4+a5 pull.comp / push.comp x12, a6 clustering.comp, a7 light_lists.comp,
 // a9 final_gathering.comp, n1 gi_blur.frag) on the same inputs as this file and compares BIT FOR BIT; committed
 // digests of those outputs (tests/golden/ref_mid.json) repeat the check where /root/reference is not mounted.
-// Not covered that way: a2 (the GL fixed-function tessellator has no source; its deterministic replacement is
+// Not covered that way: the GL fixed-function tessellator inside a2 (no source; its deterministic replacement is
 // specified in DESIGN.md) and the evaluation ORDER of floating-point expressions, which GLSL leaves to the
 // implementation (both sides use glm's order). This file is a line-by-line restatement of the reference's GLSL in
 // C++ against oracle/glsl_compat.h; it is additionally pinned by the known-answer values of SURVEY.md Appendix E

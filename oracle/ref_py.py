@@ -116,3 +116,42 @@ def gi_blur(gi_rgb, depth, normal, proj):
     rgba[:, :, :3] = tmp
     load().ref_blur_v_run(_p(rgba), _p(_f32(depth)), _p(np.ascontiguousarray(normal, np.uint32)), W, H, _p(_f32(proj)), _p(out))
     return out
+
+
+def ism_points(vertices, normals, indices, prim_id, tess_level_factor, N, max_triangles=None):
+    """programmable stages of the point pipeline (ism.tesc -> [tessellator] -> ism.tese -> ism.geom, usePushPull path).
+    The fixed-function tessellator is replaced by the deterministic n^2 split of DESIGN.md section 3.4 (n = the
+    equal_spacing rounding ceil(clamp(inner level, 1, 64)) of the GL spec). Returns (points[P,4], bucket[P]) grouped by
+    bucket in pointBuffer order."""
+    lib = load()
+    assert N == 1024, "ism.geom hard-codes totalVplCount = 1024"
+    ntri = indices.shape[0] if max_triangles is None else min(indices.shape[0], max_triangles)
+    V, Tc, Nr, Pid = [], [], [], []
+    lv = np.zeros(4, np.float32); pos = np.zeros(3, np.float32)
+    for t in range(ntri):
+        tri = _f32(vertices[indices[t]])                      # 3 x 3
+        n0 = _f32(normals[indices[t][0]])                     # ism.tese:22: vertex 0's normal
+        lib.ref_tesc_run(_p(tri), C.c_float(tess_level_factor), _p(lv))
+        n = int(np.ceil(np.float32(min(max(lv[0], np.float32(1.0)), np.float32(64.0)))))
+        fn = np.float32(n)
+        for j in range(n):
+            for i in range(n - j):
+                for down in (0, 1):
+                    if down and i + j > n - 2:
+                        continue
+                    g = ((i, j), (i + 1, j), (i, j + 1)) if not down else ((i + 1, j), (i + 1, j + 1), (i, j + 1))
+                    vs, tcs = [], []
+                    for gi, gj in g:
+                        tc = np.array([np.float32(n - gi - gj) / fn, np.float32(gi) / fn, np.float32(gj) / fn], np.float32)
+                        lib.ref_tese_run(_p(tri), _p(n0), _p(tc), _p(pos))
+                        vs.append(pos.copy()); tcs.append(tc)
+                    V.append(vs); Tc.append(tcs); Nr.append(n0); Pid.append(int(prim_id[t]))
+    T = len(V)
+    V = _f32(np.array(V)); Tc = _f32(np.array(Tc)); Nr = _f32(np.array(Nr)); Pid = np.array(Pid, np.int32)
+    stride = 4096
+    buf = np.zeros((N * stride, 4), np.float32); counters = np.zeros(1024, np.uint32)
+    lib.ref_geom_run(_p(V), _p(Tc), _p(Nr), _p(Pid), T, N, _p(buf), N * stride, _p(counters))
+    assert counters.max() <= stride
+    pts = np.concatenate([buf[b * stride:b * stride + int(counters[b])] for b in range(N)])
+    bkt = np.repeat(np.arange(N, dtype=np.int32), counters[:N].astype(np.int64))
+    return pts, bkt

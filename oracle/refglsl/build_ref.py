@@ -39,6 +39,9 @@ UNITS = [
     ("clustering", "clustered_shading/clustering.comp", [], "clustering.inc"),
     ("lightlists", "clustered_shading/light_lists.comp", [], "lightlists.inc"),
     ("splat", "ism/ism.comp", [], "splat.inc"),
+    ("tesc", "ism/ism.tesc", [], "points.inc"),
+    ("tese", "ism/ism.tese", [], "points.inc"),
+    ("geom", "ism/ism.geom", [], "points.inc"),
     ("blur_h", "gi/gi_blur.frag", [("#define DIRECTION ivec2(0,0)", "#define DIRECTION ivec2(1,0)")], "blur.inc"),
     ("blur_v", "gi/gi_blur.frag", [("#define DIRECTION ivec2(0,0)", "#define DIRECTION ivec2(0,1)")], "blur.inc"),
 ]
@@ -89,6 +92,10 @@ def rewrite(lines, replacements, total_vpls):
         return "static const wgsize<%s, %s, %s> gl_WorkGroupSize;" % (d.get("x", "1"), d.get("y", "1"), d.get("z", "1"))
     src = re.sub(r"layout\s*\([^)]*local_size_[^)]*\)\s*in\s*;", local_size, src)
 
+    # tessellation / geometry stage interface: layout-only declarations, unsized per-vertex arrays, `flat`
+    src = re.sub(r"^\s*layout\s*\([^)]*\)\s*(?:in|out)\s*;", "", src, flags=re.M)
+    src = re.sub(r"^\s*(?:flat\s+)?(?:in|out)\s+(" + SCALARS + r")\s*\[\s*\]\s+(\w+)\s*;", r"\1 \2[3];", src, flags=re.M)
+    src = re.sub(r"^\s*flat\s+(in|out)\s+", r"\1 ", src, flags=re.M)
     # buffer / uniform blocks: `layout(...) buffer name_ { T member[...]; };`  ->  `T* member;`
     def block(m):
         body = m.group("body")
@@ -131,7 +138,7 @@ def rewrite(lines, replacements, total_vpls):
         names = [n.strip() for n in m.group(3).split(",")]
         return m.group(1) + m.group(2) + " " + ", ".join(n + "{}" for n in names) + ";"
     src = re.sub(r"^([ \t]+)(float|int|uint)\s+(\w+(?:\s*,\s*\w+)+)\s*;", multi, src, flags=re.M)
-    src = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", src)
+    src = re.sub(r"\bvoid\s+main\s*\(\s*(?:void)?\s*\)", "void shader_main()", src)
     return src
 
 

@@ -309,6 +309,7 @@ template <VecLike C> inline uint imageAtomicMin(uimage2D& im, const C& c, uint v
 template <Scalar C> inline uvec4 imageLoad(const uimage1D& im, C c) { return im.loadu(int(c), 0); }
 template <Scalar C, VecLike V> inline void imageStore(uimage1D& im, C c, const V& v) { im.storeu(int(c), 0, 0, uint(v[0])); }
 template <Scalar C> inline vec4 imageLoad(const imageBuffer& im, C c) { return im.loadf(int(c), 0); }
+template <Scalar C, VecLike V> inline void imageStore(imageBuffer& im, C c, const V& v) { im.storef(int(c), 0, vec4(v)); }
 inline ivec2 imageSize(const uimage2D& im) { return ivec2(im.w, im.h); }
 inline ivec2 imageSize(const image2D& im) { return ivec2(im.w, im.h); }
 struct size1 { int x; };
@@ -404,6 +405,18 @@ inline void dispatch_phased(void (*shader_main)(), const uvec3& local, uint gx, 
         }
     }
 }
+// tessellation / geometry stage built-ins (ism.tesc, ism.tese, ism.geom): plain variables, filled in by the driver
+struct PerVertex { vec4 gl_Position; float gl_PointSize = 1.0f; };
+inline PerVertex gl_in[3], gl_out[3];
+inline vec4 gl_Position;
+inline float gl_PointSize = 1.0f;
+inline int gl_InvocationID = 0, gl_PrimitiveIDIn = 0;
+inline vec3 gl_TessCoord;
+inline float gl_TessLevelOuter[4], gl_TessLevelInner[2];
+inline int g_emitted = 0;
+inline void EmitVertex() { g_emitted++; }
+inline void EndPrimitive() {}
+inline uint atomicAdd(uint& m, int v) { const uint old = m; m += (uint)v; return old; }
 inline vec4 g_FragCoord;
 #define gl_FragCoord (::glsl_rt::g_FragCoord)
 inline void memoryBarrierShared() {}

@@ -30,7 +30,12 @@ def main():
     inv = O.mat4_inverse(O.mat4_mul(O.mat4_mul(bias, wl.light_proj), wl.light_view))
     vpl, packed = R.vpl_process(wl.rsm_diffuse, wl.rsm_normal, wl.rsm_depth, c.N, inv, 5.0, True, O.shuffle_table(c.N))
     g["a1_vpl"], g["a1_packed"] = sha(vpl), sha(packed)
-    # a2 has no shader source (GL tessellator): the point list is the oracle's; everything downstream is the reference's
+    # a2: tesc / tese / geom from source on the first 6000 triangles (the GL tessellator itself has no source); the full point
+    # list fed to the stages downstream is the oracle's
+    from test_reference_glsl import canonical_points
+    sc = wl.scene
+    pts, bkt = R.ism_points(sc.vertices, sc.normals, sc.indices, sc.prim_id, 2.0, c.N, max_triangles=6000)
+    g["a2_points_first_6000_triangles"] = sha(canonical_points(pts, bkt))
     atlas = R.ism_splat(c.get("points"), c.get("bucket_start"), packed, c.N, 50.0, c.get("atlas").shape[0])
     g["a3_atlas"] = sha(atlas)
     ism = R.ism_pullpush(atlas, 50.0)

@@ -1,8 +1,8 @@
 """Pins the oracle (oracle/oracle.cpp) against the reference's OWN shader sources: oracle/refglsl/build_ref.py reads the
 GLSL files where they lie under /root/reference/data/shaders, rewrites them syntactically into C++20 and compiles them
 with g++ against a small GLSL runtime (oracle/refglsl/glsl_rt.h) into oracle/_ref/libref_glsl.so. Every stage of the
-hot path that is a shader (a1, a3, a4+a5, a6, a7, a9, n1) is then run on the same inputs as the oracle and compared
-BIT FOR BIT. (a2 is the GL fixed-function tessellator and has no source to compile.)
+hot path (a1, a2's programmable stages, a3, a4+a5, a6, a7, a9, n1) is then run on the same inputs as the oracle and
+compared BIT FOR BIT. (Only the GL fixed-function tessellator inside a2 has no source to compile.)
 
 Runs wherever the library exists (it is built here, where /root/reference is mounted, and travels with the snapshot);
 tests/test_golden.py::test_oracle_reproduces_reference_derived_golden covers the same ground from committed hashes."""
@@ -41,6 +41,22 @@ def test_a1_vpl_processor(ref, case_mid):
         vpl, packed = ref.vpl_process(wl.rsm_diffuse, wl.rsm_normal, wl.rsm_depth, c.N, inv, 5.0, shuffle, O.shuffle_table(c.N))
         o_vpl, o_packed = O.vpl_process(wl.rsm_diffuse, wl.rsm_normal, wl.rsm_depth, c.N, wl.light_view, wl.light_proj, 5.0, shuffle)
         assert np.array_equal(bits(vpl), bits(o_vpl)) and np.array_equal(bits(packed), bits(o_packed))
+
+
+def canonical_points(points, bucket):
+    a = np.concatenate([bits(points), np.asarray(bucket).astype(np.uint32)[:, None]], 1)
+    return a[np.lexsort(a.T[::-1])]
+
+
+def test_a2_programmable_point_stages(ref, case_mid):
+    """ism.tesc (tessellation levels), ism.tese (interpolation) and ism.geom (centre, radius, bucket, pointBuffer write) run
+    from source; only the fixed-function tessellator between them is replaced by the deterministic split of DESIGN.md 3.4"""
+    sc = case_mid.wl.scene
+    M = 6000
+    pts, bkt = ref.ism_points(sc.vertices, sc.normals, sc.indices, sc.prim_id, 2.0, case_mid.N, max_triangles=M)
+    o_pts, o_bkt = O.ism_points(sc.vertices, sc.normals, sc.indices[:M], sc.prim_id[:M], 2.0, case_mid.N)
+    assert pts.shape[0] > M            # some triangles are tessellated (n > 1)
+    assert np.array_equal(canonical_points(pts, bkt), canonical_points(o_pts, o_bkt))
 
 
 def test_a3_splat(ref, case_mid):
