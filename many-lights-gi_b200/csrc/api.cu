@@ -808,7 +808,7 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
                                                ctx->cfg.class_lo, ctx->cfg.class_hi, row0[k], row0[k + 1], ctx->tile_lists, ctx->tile_weight, nullptr, ctx->aux);
             CK(cudaEventRecord(ctx->ev_cull[k], ctx->aux));
         }
-        ctx->have_tiled = true; ctx->tile_order_valid = false;   // slabs are gathered in row-major order
+        ctx->have_tiled = true; ctx->tile_order_valid = false;   // slabs are gathered in row-major order (sorting inside a slab was measured: 2.40 vs 2.35 ms)
         GatherArgs a;
         if ((rc = build_gather_args(ctx, &dg, cam, nullptr, p, &a))) return rc;
         {

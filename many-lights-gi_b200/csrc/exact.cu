@@ -953,26 +953,29 @@ __global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict
 // Gathering CTAs are scheduled in launch order, and a tile's cost is proportional to its list length: ordering the tiles
 // by descending weight (longest first) removes the tail in which a few long-list tiles keep a handful of SMs busy. Counting
 // sort into 128 weight bins by one CTA; the order inside a bin is arbitrary, which is immaterial (tiles are independent).
-__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ tile_weight, int ntiles, int wmax, uint32_t* __restrict__ order) {
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ tile_weight, int tile0, int ntiles, int wmax,
+                                                          uint32_t* __restrict__ order) {
     __shared__ uint32_t hist[128], start[128];
     if (threadIdx.x < 128) hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t div = (uint32_t)wmax / 128u + 1u;
-    for (int t = threadIdx.x; t < ntiles; t += 1024) atomicAdd(&hist[127u - min(tile_weight[t] / div, 127u)], 1u);
+    for (int t = threadIdx.x; t < ntiles; t += 1024) atomicAdd(&hist[127u - min(tile_weight[tile0 + t] / div, 127u)], 1u);
     __syncthreads();
     if (threadIdx.x == 0) { uint32_t acc = 0; for (int b = 0; b < 128; b++) { start[b] = acc; acc += hist[b]; } }
     __syncthreads();
-    for (int t = threadIdx.x; t < ntiles; t += 1024) order[atomicAdd(&start[127u - min(tile_weight[t] / div, 127u)], 1u)] = (uint32_t)t;
+    for (int t = threadIdx.x; t < ntiles; t += 1024)
+        order[tile0 + atomicAdd(&start[127u - min(tile_weight[tile0 + t] / div, 127u)], 1u)] = (uint32_t)(tile0 + t);
 }
 
-// tile rows [ty0, ty1) only (the host-input frame culls each G-buffer slab as soon as it is uploaded)
+// tile rows [ty0, ty1) (the host-input frame culls each G-buffer slab as soon as it is uploaded); the order, if requested,
+// is a permutation of exactly those rows' tiles, stored at their own positions
 int launch_cull_tiled(const float* depth, const uint32_t* face_normal, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
                       int class_lo, int class_hi, int ty0, int ty1, uint16_t* lists, uint32_t* tile_weight, uint32_t* tile_order, cudaStream_t st) {
-    dim3 grid((W + kTile - 1) / kTile, ty1 - ty0);
+    const int TX = (W + kTile - 1) / kTile;
+    dim3 grid(TX, ty1 - ty0);
     cull_tiled_kernel<<<grid, 256, 0, st>>>(depth, face_normal, W, H, records, N, inv_vp, class_lo, class_hi, ty0, lists, tile_weight);
     if (!tile_order) return 1;
-    const int TX = (W + kTile - 1) / kTile, TY = (H + kTile - 1) / kTile;
-    tile_order_kernel<<<1, 1024, 0, st>>>(tile_weight, TX * TY, (class_hi - class_lo) * (N / 16), tile_order);   // whole image only
+    tile_order_kernel<<<1, 1024, 0, st>>>(tile_weight, ty0 * TX, (ty1 - ty0) * TX, (class_hi - class_lo) * (N / 16), tile_order);
     return 2;
 }
 
