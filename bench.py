@@ -332,14 +332,35 @@ def main():
             assert H % world == 0, "e2e at N GPUs splits the image rows evenly"
             y0, y1 = rank * H // world, (rank + 1) * H // world
             gkeys = ("depth", "normal")
+            # The G-buffer traffic (slab upload + all-gather) runs on a second stream beside the ISM build, which only needs
+            # the RSM; culling and gathering start when both are done (the stage entry points of the C ABI, in the order
+            # mlgi_frame runs them).
+            s_io = torch.cuda.Stream(device=dev)
             def e2e_step():
+                main = torch.cuda.current_stream()
+                s_io.wait_stream(main)
+                with torch.cuda.stream(s_io):
+                    for k, src in zip(gkeys, h[3:]):
+                        full = d[k].view(torch.uint8).view(H, -1)
+                        full[y0:y1].copy_(src.view(torch.uint8).view(H, -1)[y0:y1], non_blocking=True)
+                        dist.all_gather_into_tensor(full.view(-1), full[y0:y1].reshape(-1))
                 for k, src in zip(("rsm_diffuse", "rsm_normal", "rsm_depth"), h[:3]):
                     d[k].copy_(src.view(d[k].dtype).reshape(d[k].shape), non_blocking=True)
-                for k, src in zip(gkeys, h[3:]):
-                    full = d[k].view(torch.uint8).view(H, -1)
-                    full[y0:y1].copy_(src.view(torch.uint8).view(H, -1)[y0:y1], non_blocking=True)
-                    dist.all_gather_into_tensor(full.view(-1), full[y0:y1].reshape(-1))
-                step()
+                ctx.vpl_process(rsm, light, params, stream=stream)
+                ctx.ism_points(mesh, params, stream=stream)
+                ctx.ism_splat(params, stream=stream)
+                ctx.ism_pullpush(params, stream=stream)
+                main.wait_stream(s_io)
+                if args.cull == "tiled":
+                    ctx.cull_tiled(gb, cam, params, stream=stream)
+                else:
+                    ctx.cull_clustered(gb, cam, params, stream=stream)
+                ctx.final_gather(gb, cam, params, stream=stream)
+                if fused:
+                    ctx.exchange_finish(stream=stream)
+                else:
+                    mdist.allgather_planar(planar, rank, world)
+                    ctx.planar_to_raster(planar, None, stream=stream)
                 ctx.read_async(mlgi.BUF_GI_PACKED, host_gi[y0:y1], (y1 - y0) * W * 4, offset=y0 * W * 4, stream=stream)
                 torch.cuda.current_stream().synchronize()
         for _ in range(3):
@@ -354,14 +375,27 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # the end-to-end path must have produced the image of the device-resident path (same inputs): compare this rank's rows
+        step()
+        torch.cuda.synchronize()
+        ref_img = ctx.download(mlgi.BUF_GI_PACKED, np.uint32).reshape(H, W)
+        ra, rb = (0, H) if world == 1 else (y0, y1)
+        e2e_ok = bool(np.array_equal(host_gi.numpy().view(np.uint32)[ra:rb], ref_img[ra:rb]))
+        if world > 1:
+            t = torch.tensor([1.0 if e2e_ok else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            e2e_ok = bool(t.item() > 0.5)
+        if not e2e_ok:
+            raise SystemExit("bench.py: the end-to-end path did not reproduce the device-resident frame")
         nb = lambda x: x.numel() * x.element_size()
         h2d = sum(nb(x) for x in h) if world == 1 else world * sum(nb(x) for x in h[:3]) + sum(nb(x) for x in h[3:])   # summed over ranks
         e2e = {"value": pairs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_gi.numel() * 4,
-               "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "ms_per_step": dt * 1e3, "steps": n_e2e, "verified_against_device_path": e2e_ok,
                "call": ("mlgi_frame_host_packed (pinned host RSM + G-buffer in, GL_R11F_G11F_B10F GI image out = the reference's giBuffer "
                         "format, stream sync)") if world == 1 else
-                       "per rank: pinned-host upload of the RSM and of 1/N of the G-buffer rows + NVLink all-gather of the G-buffer + mlgi_frame + "
-                       "exchange + read-back of 1/N of the assembled GL_R11F_G11F_B10F image rows (bytes summed over ranks)"}
+                       "per rank: pinned-host upload of the RSM and of 1/N of the G-buffer rows + NVLink all-gather of the G-buffer (second stream, "
+                       "beside the ISM build) + the stage calls of mlgi_frame + exchange + read-back of 1/N of the assembled "
+                       "GL_R11F_G11F_B10F image rows (bytes summed over ranks)"}
 
     if rank != 0:
         if world > 1:
