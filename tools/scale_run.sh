@@ -10,5 +10,5 @@ import json; d=json.load(open('gpurun_out/scale_${TAG}_$4.json')); print('$4', d
 run 8 4k_4096 fused n8_fused
 run 4 4k_4096 fused n4_fused
 run 2 4k_4096 fused n2_fused
-run 8 8k_16384 fused 8k_n8_fused
-run 8 4k_4096 nccl n8_nccl
+
+
