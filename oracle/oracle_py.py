@@ -2,7 +2,7 @@
 
 May be imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs. The product path (many-lights-gi_b200/) never imports this module.
-PARITY UNPINNED by the reference (it has no tests / golden vectors; see oracle.cpp header).
+Parity: pinned against the reference's own shader sources compiled for the CPU (oracle/refglsl, see oracle.cpp header).
 """
 import ctypes as C
 import os

@@ -1,6 +1,6 @@
 """Oracle vs the known-answer values of SURVEY.md Appendix E and structural invariants.
-(The reference ships no tests or golden vectors -- 'parity unpinned' -- so these KATs plus the
-committed golden hashes in tests/golden/ are what pins the oracle.)"""
+(The reference ships no tests or golden vectors; the oracle is pinned against its shader sources by
+tests/test_reference_glsl.py, and additionally by these KATs and the committed golden hashes in tests/golden/.)"""
 import ctypes as C
 
 import numpy as np
