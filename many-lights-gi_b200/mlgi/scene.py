@@ -109,13 +109,13 @@ class Workload:
     """
 
     def __init__(self, width, height, vpl_count, rsm_w=1024, rsm_h=256, cell_size=0.155, seed=0x5EED,
-                 sun_cycle_position=266.0, clutter_boxes=24, scene=None):
+                 sun_cycle_position=266.0, clutter_boxes=24, scene=None, eye=(-13.0, 2.5, -0.23), center=(0.009, -0.019, -0.021)):
         self.W, self.H, self.N = width, height, vpl_count
         self.rsm_w, self.rsm_h = rsm_w, rsm_h
         self.z_near, self.z_far = 0.05, 50.0
         self.scene = scene if scene is not None else Scene(seed, cell_size, clutter_boxes)
         sc = self.scene
-        self.cam_view = sc.look_at((-13.0, 2.5, -0.23), (0.009, -0.019, -0.021))
+        self.cam_view = sc.look_at(eye, center)
         self.cam_proj = sc.perspective(math.radians(60.0), width / float(height), self.z_near, self.z_far)
         self.depth, self.normal, self.diffuse = sc.render(self.cam_view, self.cam_proj, width, height, want_diffuse=True)
         self.set_sun(sun_cycle_position)

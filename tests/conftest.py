@@ -36,9 +36,9 @@ _ensure_built()
 class Case:
     """A seeded synthetic workload plus lazily computed oracle results for every stage."""
 
-    def __init__(self, W, H, N, rsm_w, rsm_h, cell, clutter=8, sun=266.0):
+    def __init__(self, W, H, N, rsm_w, rsm_h, cell, clutter=8, sun=266.0, seed=0x5EED, **camera):
         from mlgi.scene import Workload
-        self.wl = Workload(W, H, N, rsm_w=rsm_w, rsm_h=rsm_h, cell_size=cell, clutter_boxes=clutter, sun_cycle_position=sun)
+        self.wl = Workload(W, H, N, rsm_w=rsm_w, rsm_h=rsm_h, cell_size=cell, clutter_boxes=clutter, sun_cycle_position=sun, seed=seed, **camera)
         self.W, self.H, self.N = W, H, N
         self.z_far = 50.0
         self._c = {}
@@ -80,6 +80,13 @@ class Case:
                                           cull_mode, ids, lists, wl.cam_view, wl.cam_proj, self.z_far, shadows=shadows,
                                           bounds=bounds, class_lo=class_lo, class_hi=class_hi)
         return self._c[key]
+
+
+@pytest.fixture(scope="session")
+def case_alt():
+    """another scene seed, sun position and camera (looking across the atrium from the far side): guards against a path
+    that only works for the default view"""
+    return Case(256, 144, 256, 256, 64, cell=1.0, clutter=10, sun=250.0, seed=1234, eye=(6.0, 3.0, 1.5), center=(-6.0, 4.0, -1.0))
 
 
 def make_case_mid():

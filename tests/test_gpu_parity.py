@@ -45,9 +45,9 @@ class Gpu:
         self.ctx.close()
 
 
-@pytest.fixture(scope="module", params=["small", "c1", "mid"])
-def gpu_case(request, case_small, case_c1, case_mid):
-    case = {"small": case_small, "c1": case_c1, "mid": case_mid}[request.param]
+@pytest.fixture(scope="module", params=["small", "c1", "mid", "alt"])
+def gpu_case(request, case_small, case_c1, case_mid, case_alt):
+    case = {"small": case_small, "c1": case_c1, "mid": case_mid, "alt": case_alt}[request.param]
     g = Gpu(case)
     yield g
     g.close()
