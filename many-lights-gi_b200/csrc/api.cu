@@ -98,7 +98,7 @@ struct mlgi_ctx {
     unsigned long long* stats = nullptr;
     cudaTextureObject_t ism_tex = 0;      // ctx ISM atlas as an R16-unorm point-sampled texture
     cudaTextureObject_t override_tex = 0; const uint16_t* override_ptr = nullptr;   // cached texture of the last ISM override
-    int use_texture = 1;
+    int use_texture = 1, tex_float_coord = 0;
     // fused multi-GPU exchange (mlgi_exchange_*): two parity buffers + flag array in ONE IPC-exportable allocation
     struct Exchange {
         int rank = 0, world = 0;
@@ -318,7 +318,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev_fg[k], cudaEventDisableTiming);
     }
     if (const char* e5 = getenv("MLGI_HOST_SLABS")) ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5)));   // A/B switch
-    if (const char* e2 = getenv("MLGI_ISM_FETCH")) ctx->use_texture = strcmp(e2, "ldg") != 0;   // A/B switch: tex (default) | ldg
+    if (const char* e2 = getenv("MLGI_ISM_FETCH")) { ctx->use_texture = strcmp(e2, "ldg") != 0; ctx->tex_float_coord = strcmp(e2, "texf") == 0; }   // A/B switch: tex (default) | texf | ldg
     if (const char* e6 = getenv("MLGI_FG_SORTED")) ctx->fg_sorted = atoi(e6) != 0;             // A/B switch: longest-list tiles first (default) | row-major
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
     *out = ctx;
@@ -542,6 +542,7 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     a.clampv = p->vpl_clamping_value;
     a.enable_shadowing = p->enable_shadowing;
     a.tile_begin = 0; a.tile_count = ctx->TX * ctx->TY;
+    a.tex_float_coord = ctx->tex_float_coord;
     a.tile_order = (p->cull_mode == MLGI_CULL_TILED && ctx->fg_sorted && ctx->tile_order_valid) ? ctx->tile_order : nullptr;
     a.class_lo = ctx->cfg.class_lo; a.class_hi = ctx->cfg.class_hi;
     // output routing: a bound exchange buffer receives the class planes and the raster image is rebuilt by the

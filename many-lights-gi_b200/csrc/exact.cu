@@ -56,7 +56,7 @@ __global__ void vpl_process_kernel(const uint32_t* __restrict__ diffuse, const u
     r.r[1] = make_float4(un.y, un.z, 32.0f * s.x, 32.0f * u.x);     // rows pre-scaled by half the ISM size (exact), paired by component
     r.r[2] = make_float4(32.0f * s.y, 32.0f * u.y, 32.0f * s.z, 32.0f * u.z);
     r.r[3] = make_float4(col.x, col.y, col.z, 0.0f);
-    r.r[4] = make_float4(12582912.0f + float(tx * 64 + 32), 12582912.0f + float(ty * 64 + 32), 0.0f, 0.0f);
+    r.r[4] = make_float4(12582912.0f + float(tx * 64 + 32), 12582912.0f + float(ty * 64 + 32), float(tx * 64 + 32), float(ty * 64 + 32));
     records[slot] = r;
 }
 

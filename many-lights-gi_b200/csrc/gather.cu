@@ -53,7 +53,7 @@ struct PixelPair {
 //   r0 = (-px,-py,-pz,nx) r1 = (ny,nz,32sx,32ux) r2 = (32sy,32uy,32sz,32uz) r3 = (cr,cg,cb,0) r4 = (Cx,Cy,0,0)
 //   Cx = 1.5*2^23 + tile_x*64 + 32: adding it with round-down leaves floor(texel x) in the mantissa.
 // VPL scalars enter the packed instructions through their scalar-broadcast operand form (R.F32).
-template <bool SHADOW, bool STATS, bool TEX, int NP>
+template <bool SHADOW, bool STATS, int TEX, int NP>
 __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __restrict__ rec, const uint16_t* __restrict__ ism,
                                           cudaTextureObject_t ism_tex, int A, float kz, float clampv, const Normal2 (&N)[NP], int nact,
                                           unsigned long long& listed, unsigned long long& lit) {
@@ -74,11 +74,12 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
     if (STATS) listed += nact;
     if (mmax > 0.0f) {
         const float4 r3 = rec[3];
-        float2 su_x, su_y, su_z, cxy;
+        float2 su_x, su_y, su_z, cxy, cxy_f;
         if (SHADOW) {
             const float4 r2 = rec[2];
             su_x = make_float2(r1.z, r1.w); su_y = make_float2(r2.x, r2.y); su_z = make_float2(r2.z, r2.w);
-            cxy = *reinterpret_cast<const float2*>(rec + 4);
+            if (TEX == 2) cxy_f = *(reinterpret_cast<const float2*>(rec + 4) + 1);     // tile origin + 32
+            else cxy = *reinterpret_cast<const float2*>(rec + 4);                      // 1.5*2^23 + tile origin + 32
         }
 #pragma unroll
         for (int p = 0; p < NP; p++) {                  // NP independent chains: the compiler interleaves them (ILP)
@@ -96,10 +97,24 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
                 const float2 p1 = fma2(su_z, dup(dz[p].y), fma2(su_y, dup(dy[p].y), mul2(su_x, dup(dx[p].y))));
                 const float2 den = add2(dist, a[p]);                                      // dist * (1 - v.z), v.z = -a/dist
                 const float q0 = rcp_approx(den.x), q1 = rcp_approx(den.y);
-                const float2 f0 = __ffma2_rd(p0, dup(q0), cxy);                           // 1.5*2^23 + floor(texel x | y)
-                const float2 f1 = __ffma2_rd(p1, dup(q1), cxy);
                 const float2 tb = fma2(dist, dup(kz), dup(1.0f));                         // (0.02 - dist/zFar) * 50
                 float2 t;
+                if (TEX == 2) {
+                    // the unfloored texel coordinate goes to the texture unit, which floors it itself (one packed FMA per
+                    // pixel instead of a round-down FMA plus a subtraction)
+                    const float2 x0 = fma2(p0, dup(q0), cxy_f), x1 = fma2(p1, dup(q1), cxy_f);
+                    const float o0 = tex2D<float>(ism_tex, x0.x, x0.y);
+                    const float o1 = tex2D<float>(ism_tex, x1.x, x1.y);
+                    t.x = fma_sat(o0, 50.0f, tb.x); t.y = fma_sat(o1, 50.0f, tb.y);
+                    g = mul2(g, mul2(mul2(t, t), fma2(t, dup(-2.0f), dup(3.0f))));
+                    g.x = m0[p] > 0.0f ? g.x : 0.0f; g.y = m1[p] > 0.0f ? g.y : 0.0f;
+                    px[p].ar = fma2(dup(r3.x), g, px[p].ar);
+                    px[p].ag = fma2(dup(r3.y), g, px[p].ag);
+                    px[p].ab = fma2(dup(r3.z), g, px[p].ab);
+                    continue;
+                }
+                const float2 f0 = __ffma2_rd(p0, dup(q0), cxy);                           // 1.5*2^23 + floor(texel x | y)
+                const float2 f1 = __ffma2_rd(p1, dup(q1), cxy);
                 if (TEX) {
                     // textureLod(ismDepthSampler, v.xy, 0) with NEAREST + CLAMP_TO_EDGE (final_gathering.comp:122) on the
                     // texture unit: address, clamp and R16-unorm -> float conversion cost no SM instructions. The coordinate
@@ -134,7 +149,7 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
     }
 }
 
-template <int MODE, bool SHADOW, bool STATS, bool TEX, int NP>
+template <int MODE, bool SHADOW, bool STATS, int TEX, int NP>
 __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(const GatherArgs a) {
     constexpr int THREADS = 256 / (2 * NP);     // 256 pixels of one class per CTA, 2*NP pixels per thread
     constexpr int NPX = 2 * NP;
@@ -306,12 +321,13 @@ template <int MODE>
 static void launch_fg_mode(const GatherArgs& a, dim3 grid, cudaStream_t st) {
     const bool sh = a.enable_shadowing != 0, stt = a.stats != nullptr;
     const bool tex = sh && a.ism_tex != 0;      // the ISM is fetched through the texture unit whenever a texture object exists
+    if (!stt && tex && a.tex_float_coord) { final_gather_kernel<MODE, true, false, 2, 1><<<grid, 128, 0, st>>>(a); return; }
     if (stt) {                                   // counting variant (work counters for the roofline accounting)
-        if (sh) final_gather_kernel<MODE, true, true, false, 1><<<grid, 128, 0, st>>>(a);
-        else final_gather_kernel<MODE, false, true, false, 1><<<grid, 128, 0, st>>>(a);
-    } else if (!sh) final_gather_kernel<MODE, false, false, false, 1><<<grid, 128, 0, st>>>(a);
-    else if (!tex) final_gather_kernel<MODE, true, false, false, 1><<<grid, 128, 0, st>>>(a);
-    else final_gather_kernel<MODE, true, false, true, 1><<<grid, 128, 0, st>>>(a);
+        if (sh) final_gather_kernel<MODE, true, true, 0, 1><<<grid, 128, 0, st>>>(a);
+        else final_gather_kernel<MODE, false, true, 0, 1><<<grid, 128, 0, st>>>(a);
+    } else if (!sh) final_gather_kernel<MODE, false, false, 0, 1><<<grid, 128, 0, st>>>(a);
+    else if (!tex) final_gather_kernel<MODE, true, false, 0, 1><<<grid, 128, 0, st>>>(a);
+    else final_gather_kernel<MODE, true, false, 1, 1><<<grid, 128, 0, st>>>(a);
 }
 
 int launch_final_gather(const GatherArgs& a, cudaStream_t st) {
