@@ -432,7 +432,7 @@ __device__ __forceinline__ float4 pull_combine(const PullSample* smp, int ix0, i
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         if (!valid[i]) continue;
-        minimum = gmin(depthSamples[i], minimum);
+        minimum = fminf(depthSamples[i], minimum);                // depths are finite and >= +0: FMNMX == the ternary min
         if (minimum == depthSamples[i]) maxDepth = maxDepths[i];
     }
 #pragma unroll
@@ -446,7 +446,7 @@ __device__ __forceinline__ float4 pull_combine(const PullSample* smp, int ix0, i
         depthAcc += depthSamples[i];
         dax += dv[i].x; day += dv[i].y;
         radiusAcc += radiuses[i];
-        maxValidMaxDepth = gmax(maxValidMaxDepth, maxDepths[i]);
+        maxValidMaxDepth = fmaxf(maxValidMaxDepth, maxDepths[i]);
         numValid++;
     }
     if (numValid > 0) {                                           // :116-123
@@ -491,7 +491,7 @@ __device__ __forceinline__ float4 push_pixel(const PushCoarse& c, int outputPixe
     for (int i = 0; i < 4; i++) {
         if (weights[i] == 0.0f) continue;
         any = true;
-        minimum = gmin(c.depth[i], minimum);
+        minimum = fminf(c.depth[i], minimum);                     // finite, >= +0: FMNMX == the ternary min
         if (minimum == c.depth[i]) maxDepth = c.maxDepth[i];
     }
     if (any) {
@@ -927,14 +927,14 @@ __global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const float lo = mm[c] * tb.pmin[c], hi = mm[c] * tb.pmax[c];
-                    S1 = S1 + gmax(lo, hi);
-                    mA = mA + gmax(fabsf(lo), fabsf(hi));
+                    S1 = S1 + fmaxf(lo, hi);                              // finite operands: FMNMX == the oracle's ternary max
+                    mA = mA + fmaxf(fabsf(lo), fabsf(hi));
                     const float tk = mm[c] * vv[c];
                     tt = tt + tk;
                     mA = mA + fabsf(tk);
                     const float l2 = tb.nmin[c] * vv[c], h2 = tb.nmax[c] * vv[c];
-                    S2 = S2 + gmax(l2, h2);
-                    mB = mB + gmax(fabsf(l2), fabsf(h2));
+                    S2 = S2 + fmaxf(l2, h2);
+                    mB = mB + fmaxf(fabsf(l2), fabsf(h2));
                 }
                 const bool keepA = (S1 - tt) > -(1e-5f * mA);
                 const bool keepB = (S2 - tb.emin) > -(1e-5f * (mB + tb.emag));
