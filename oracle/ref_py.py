@@ -155,3 +155,13 @@ def ism_points(vertices, normals, indices, prim_id, tess_level_factor, N, max_tr
     pts = np.concatenate([buf[b * stride:b * stride + int(counters[b])] for b in range(N)])
     bkt = np.repeat(np.arange(N, dtype=np.int32), counters[:N].astype(np.int64))
     return pts, bkt
+
+
+def composite_ambient(gi_rgb, diffuse_rgba8, occlusion=None, exposure=1.0):
+    """deferredshading.frag with the direct light off: float sRGB [H,W,3]"""
+    H, W = diffuse_rgba8.shape
+    rgba = np.zeros((H, W, 4), np.float32); rgba[:, :, :3] = gi_rgb
+    out = np.zeros((H, W, 3), np.float32)
+    occ = None if occlusion is None else _f32(occlusion)
+    load().ref_composite_run(_p(rgba), _p(np.ascontiguousarray(diffuse_rgba8, np.uint32)), _p(occ), W, H, C.c_float(exposure), _p(out))
+    return out

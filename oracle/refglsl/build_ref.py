@@ -44,6 +44,7 @@ UNITS = [
     ("geom", "ism/ism.geom", [], "points.inc"),
     ("blur_h", "gi/gi_blur.frag", [("#define DIRECTION ivec2(0,0)", "#define DIRECTION ivec2(1,0)")], "blur.inc"),
     ("blur_v", "gi/gi_blur.frag", [("#define DIRECTION ivec2(0,0)", "#define DIRECTION ivec2(0,1)")], "blur.inc"),
+    ("composite", "deferredshading.frag", [], "composite.inc"),
 ]
 
 SCALARS = r"(?:float|int|uint|bool|vec[234]|ivec[234]|uvec[234]|mat[34])"

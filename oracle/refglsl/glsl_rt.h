@@ -293,7 +293,7 @@ struct Image {            // a 2D (depth == 1) or 3D texture level / image; out-
     }
 };
 struct image2D : Image {}; struct uimage2D : Image {}; struct uimage3D : Image {}; struct uimage1D : Image {}; struct imageBuffer : Image {};
-struct sampler2D : Image {}; struct usampler2D : Image {}; struct sampler3D : Image {};
+struct sampler2D : Image {}; struct usampler2D : Image {}; struct sampler3D : Image {}; struct samplerCube : Image {};
 
 template <VecLike C> inline vec4 imageLoad(const image2D& im, const C& c) { return im.loadf(int(c[0]), int(c[1])); }
 template <VecLike C> inline uvec4 imageLoad(const uimage2D& im, const C& c) { return im.loadu(int(c[0]), int(c[1])); }
@@ -328,6 +328,7 @@ template <VecLike C> inline vec4 textureLod(const sampler2D& s, const C& uv, flo
 }
 template <VecLike C> inline vec4 texture(const sampler2D& s, const C& uv, float = 0.0f) { return textureLod(s, uv, 0.0f); }
 template <VecLike C> inline vec4 texture(const sampler3D&, const C&) { return vec4(0.0f); }
+template <VecLike C> inline vec4 texture(const samplerCube&, const C&) { return vec4(0.0f); }   // not on this path (omni shadow maps)
 
 // `layout(local_size_x = X, ...) in;` becomes `static const wgsize<X, Y, Z> gl_WorkGroupSize;` (its components must be
 // usable as array bounds)

@@ -60,6 +60,7 @@ def main():
     g["a9_pixels_compared"] = int(ok_px.sum())
     gi = c.gather(0, True, bounds=False)["rgb"]
     g["n1_blur_interior"] = sha(R.gi_blur(gi, wl.depth, wl.normal, wl.cam_proj)[3:-3, 3:-3])
+    g["n4_composite_ambient"] = sha(R.composite_ambient(gi, wl.diffuse, None, 1.0))
     json.dump(g, open(os.path.join(HERE, "ref_mid.json"), "w"), indent=1, sort_keys=True)
     print("wrote ref_mid.json", {k: (v[:12] if isinstance(v, str) else v) for k, v in g.items()})
 

@@ -146,3 +146,15 @@ def test_n1_blur(ref, case_mid):
     got, want = ref.gi_blur(gi, wl.depth, wl.normal, wl.cam_proj), O.gi_blur(gi, wl.depth, wl.normal, wl.cam_proj)
     inner = (slice(3, -3), slice(3, -3))      # texelFetch outside the image is undefined in GL; the oracle skips those taps
     assert np.array_equal(bits(got[inner]), bits(want[inner]))
+
+
+def test_n4_ambient_term_of_the_composite(ref, case_mid):
+    """deferredshading.frag from source with the direct light switched off (lightIntensity = 0, black specular buffer):
+    what remains is toSRGB(tonemap(gi * toLinear(diffuse) * occlusion)), the term mlgi_composite_ambient implements"""
+    c, wl = case_mid, case_mid.wl
+    gi = c.gather(0, True, bounds=False)["rgb"]
+    occ = np.linspace(0.25, 1.0, c.W * c.H, dtype=np.float32).reshape(c.H, c.W)
+    for occlusion, exposure in ((None, 1.0), (occ, 2.5)):
+        got = ref.composite_ambient(gi, wl.diffuse, occlusion, exposure)
+        want, _ = O.composite_ambient(gi, wl.diffuse, occlusion, exposure)
+        assert np.array_equal(bits(got), bits(want))
