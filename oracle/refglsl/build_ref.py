@@ -14,7 +14,7 @@ The rewrite is purely syntactic (what a GLSL front end does before code generati
     namespace-scope variables the driver fills in;
   * locals declared without an initialiser are value-initialised (reading them is undefined in GLSL; NVIDIA's
     compiler yields 0, which is also what the oracle assumes).
-Generated sources and the library go to oracle/_ref/ (git-ignored)."""
+The library goes to oracle/_ref/ (git-ignored); the generated sources are deleted after the build unless --keep is given."""
 import os
 import re
 import subprocess
@@ -144,30 +144,38 @@ def rewrite(lines, replacements, total_vpls):
 
 
 def main():
+    """usage: build_ref.py [--keep] [unit ...]   (--keep leaves the generated C++ under oracle/_ref/gen for inspection)"""
+    import shutil
     total_vpls = None
+    keep = "--keep" in sys.argv[1:]
+    shutil.rmtree(GEN, ignore_errors=True)
     os.makedirs(GEN, exist_ok=True)
     units = UNITS
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     if only:
         units = [u for u in UNITS if u[0] in only]
     srcs = []
-    for name, rel, repl, driver in units:
-        drv = os.path.join(HERE, "drivers", driver)
-        if not os.path.exists(drv):
-            continue
-        body = rewrite(expand_includes(os.path.join(REF_ROOT, "data/shaders", rel)), repl, total_vpls)
-        path = os.path.join(GEN, name + ".cpp")
-        with open(path, "w") as f:
-            f.write("// GENERATED by oracle/refglsl/build_ref.py from %s -- do not commit\n" % os.path.join(REF_ROOT, "data/shaders", rel))
-            f.write('#include "../../refglsl/glsl_rt.h"\n#define REF_UNIT %s\n#define REF_UNIT_%s 1\nnamespace glsl_rt { namespace u_%s {\n' % (name, name, name))
-            f.write(body)
-            f.write('\n#include "../../refglsl/drivers/%s"\n}}\n' % driver)
-        srcs.append(path)
-    lib = os.path.join(OUT, "libref_glsl.so")
-    cmd = [CXX, "-std=c++20", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-o", lib] + srcs
-    print(" ".join(cmd))
-    subprocess.check_call(cmd)
-    print("built", lib)
+    try:
+        for name, rel, repl, driver in units:
+            drv = os.path.join(HERE, "drivers", driver)
+            if not os.path.exists(drv):
+                continue
+            body = rewrite(expand_includes(os.path.join(REF_ROOT, "data/shaders", rel)), repl, total_vpls)
+            path = os.path.join(GEN, name + ".cpp")
+            with open(path, "w") as f:
+                f.write("// GENERATED by oracle/refglsl/build_ref.py from %s -- never commit\n" % os.path.join(REF_ROOT, "data/shaders", rel))
+                f.write('#include "../../refglsl/glsl_rt.h"\n#define REF_UNIT %s\n#define REF_UNIT_%s 1\nnamespace glsl_rt { namespace u_%s {\n' % (name, name, name))
+                f.write(body)
+                f.write('\n#include "../../refglsl/drivers/%s"\n}}\n' % driver)
+            srcs.append(path)
+        lib = os.path.join(OUT, "libref_glsl.so")
+        cmd = [CXX, "-std=c++20", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-o", lib] + srcs
+        print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        print("built", lib)
+    finally:
+        if not keep:
+            shutil.rmtree(GEN, ignore_errors=True)      # the rewritten reference text does not stay in the tree
 
 
 if __name__ == "__main__":
