@@ -568,6 +568,9 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MINB) pullpush_kernel(const uin
     __shared__ __align__(16) uint32_t L0[64 * 64];
     __shared__ __align__(16) float4 PY[1024 + 256 + 64 + 16 + 4 + 1];
     __shared__ float lut_r[256], lut_md[256];
+    __shared__ float4 s_empty;          // pull level 1 of an all-empty 2x2 block
+    __shared__ int s_count;
+    __shared__ uint16_t s_list[1024];   // level-1 outputs whose block holds at least one point
     // float4 offset of pyramid level l (1..6) inside PY: sum_{k<l} 4^(6-k)
     auto lvl_off = [](int l) { return (4096 - (4096 >> (2 * (l - 1)))) / 3; };
     const int A = 64 * S;
@@ -591,24 +594,44 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MINB) pullpush_kernel(const uin
     __syncthreads();
 
     // ---- pull level 1 (LEVEL_ZERO variant, pull.comp:37-41,55-65) ----
-    // the 8-bit radius only takes 256 values: its two division chains are tabulated per CTA (same IEEE ops)
+    // the 8-bit radius only takes 256 values: its two division chains are tabulated per CTA (same IEEE ops).
+    // Most 2x2 input blocks are entirely empty texels (0xFFFFFFFF: the atlas is sparse). Their result does not depend on
+    // the position -- every term of pull.comp:69 is exact, so the four displacement vectors are (+-0.25, +-0.25) everywhere --
+    // and is evaluated once per CTA by the general code (s_empty); the other blocks are collected and processed densely.
     const float ismPixelSize = 64.0f;          // A / S  (ImperfectShadowmap.cpp:187-191)
+    auto decode_l0 = [&](uint32_t u, PullSample& smp) {
+        float depthSample = float(u >> 8) / 16777216.0f;
+        float radius = lut_r[u & 0xFFu];                                   // float(u & 0xFF) / 10      :39
+        float maxDepth = depthSample + lut_md[u & 0xFFu];                  // + (radius*2)/zFar*0.6     :57
+        float distToCamera = depthSample * zFar;                           // :60
+        radius = radius / distToCamera / 3.14f * ismPixelSize;             // :61
+        radius *= 1.3f;                                                    // :63
+        radius = gmin(radius, 15.0f);                                      // :65
+        smp.depth = depthSample; smp.maxDepth = maxDepth; smp.radius = radius; smp.disp = make_float2(0.0f, 0.0f);
+    };
+    if (tid == 0) {
+        PullSample smp[4];
+        for (int i = 0; i < 4; i++) decode_l0(0xFFFFFFFFu, smp[i]);
+        const int ox = gx0 >> 1, oy = gy0 >> 1;
+        s_empty = pull_combine(smp, ox * 2, oy * 2, ox, oy, 1);
+        s_count = 0;
+    }
+    __syncthreads();
     for (int o = tid; o < 1024; o += PP_THREADS) {
-        int lx = o & 31, ly = o >> 5;
+        const int lx = o & 31, ly = o >> 5;
+        const uint2 top = *reinterpret_cast<const uint2*>(&L0[(ly * 2) * 64 + lx * 2]);
+        const uint2 bot = *reinterpret_cast<const uint2*>(&L0[(ly * 2 + 1) * 64 + lx * 2]);
+        if ((top.x & top.y & bot.x & bot.y) == 0xFFFFFFFFu) PY[lvl_off(1) + o] = s_empty;
+        else s_list[atomicAdd(&s_count, 1)] = (uint16_t)o;
+    }
+    __syncthreads();
+    for (int q = tid; q < s_count; q += PP_THREADS) {
+        const int o = s_list[q];
+        const int lx = o & 31, ly = o >> 5;
         PullSample smp[4];
         const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t u = L0[(ly * 2 + offy[i]) * 64 + lx * 2 + offx[i]];
-            float depthSample = float(u >> 8) / 16777216.0f;
-            float radius = lut_r[u & 0xFFu];                                   // float(u & 0xFF) / 10      :39
-            float maxDepth = depthSample + lut_md[u & 0xFFu];                  // + (radius*2)/zFar*0.6     :57
-            float distToCamera = depthSample * zFar;                           // :60
-            radius = radius / distToCamera / 3.14f * ismPixelSize;             // :61
-            radius *= 1.3f;                                                    // :63
-            radius = gmin(radius, 15.0f);                                      // :65
-            smp[i].depth = depthSample; smp[i].maxDepth = maxDepth; smp[i].radius = radius; smp[i].disp = make_float2(0.0f, 0.0f);
-        }
+        for (int i = 0; i < 4; i++) decode_l0(L0[(ly * 2 + offy[i]) * 64 + lx * 2 + offx[i]], smp[i]);
         int ox = (gx0 >> 1) + lx, oy = (gy0 >> 1) + ly;
         PY[lvl_off(1) + o] = pull_combine(smp, ox * 2, oy * 2, ox, oy, 1);
     }
