@@ -117,7 +117,8 @@ typedef enum {
     MLGI_BUF_VPL = 0,              /* N x 12 float {pos,_,nrm,_,col,_}          VPLProcessor.cpp:34-41   */
     MLGI_BUF_PACKED_VPL,           /* N x 4 float (pos, pack3SN(nrm))           VPLProcessor.cpp:29-32   */
     MLGI_BUF_SHUFFLE,              /* N x int32 permutation                     VPLProcessor.cpp:58-65   */
-    MLGI_BUF_POINTS,               /* P x 4 float (pos, unorm4x8(nrm, r/25)), grouped by bucket */
+    MLGI_BUF_POINTS,               /* P x 4 float (pos, unorm4x8(nrm, r/25)), grouped by bucket. The frame keeps an unordered
+                                      list; this view (and BUCKET_START) is built when first requested (synchronises) */
     MLGI_BUF_BUCKET_START,         /* (N+1) x uint32 prefix of bucket sizes (replaces atomicCounter[N]) */
     MLGI_BUF_ATLAS,                /* A x A uint32 depth24<<8|radius8           ImperfectShadowmap.cpp:76-80 */
     MLGI_BUF_ISM,                  /* A x A uint16 R16 unorm push-pull result   ImperfectShadowmap.cpp:102-106 */
