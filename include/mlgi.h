@@ -205,6 +205,9 @@ MLGI_API int mlgi_gather_stats(mlgi_ctx*, const mlgi_gbuffer*, const mlgi_camera
                                const mlgi_params*, unsigned long long* pairs_listed, unsigned long long* pairs_lit);
 /* FFMA micro-benchmark on the ctx device: the FP32-pipe roofline denominator in TFLOP/s. Synchronises. */
 MLGI_API float mlgi_measure_fp32_peak_tflops(mlgi_ctx*);
+/* test hook for the pull-push kernel's exact square-root elimination: thresholds[i] = T(radii[i]) with
+ * sqrtf(x) > r  <=>  x > T(r) for every float x. Device pointers. */
+MLGI_API int mlgi_debug_sqrt_thresholds(mlgi_ctx*, const float* dev_radii, int n, float* dev_thresholds, void* stream);
 
 /* multi-GPU exchange: the gathering kernel writes the class-planar planes of the classes this
  * ctx owns straight into a caller-owned [16][ceil(H/4)][ceil(W/4)] x 4 float device buffer (plane c at

@@ -695,6 +695,14 @@ MLGI_API int mlgi_set_timers(mlgi_ctx* ctx, int enable) {
     return MLGI_OK;
 }
 
+MLGI_API int mlgi_debug_sqrt_thresholds(mlgi_ctx* ctx, const float* dev_radii, int n, float* dev_thresholds, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    if (!dev_radii || !dev_thresholds || n < 0) return fail(ctx, MLGI_E_INVALID, "radii/thresholds is NULL");
+    ctx->launches += launch_sqrt_thresholds(dev_radii, n, dev_thresholds, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return MLGI_OK;
+}
+
 MLGI_API float mlgi_measure_fp32_peak_tflops(mlgi_ctx* ctx) {
     if (!ctx) return -1.0f;
     return measure_fp32_peak_tflops(0);

@@ -164,6 +164,7 @@ int launch_bucket_expand(const uint32_t* bucket_start, int N, uint32_t* point_bu
 void launch_atlas_clear(uint32_t* atlas, int S, int vpl_lo, int vpl_hi, cudaStream_t st);
 int launch_splat(const float4* points, const uint32_t* point_bucket, const uint32_t* generated, int max_points, const VplRecord* records,
                  int N, int S, float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st);
+int launch_sqrt_thresholds(const float* rs, int n, float* out, cudaStream_t st);
 int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st);
 
 int launch_clustering(const float* depth, int W, int H, float projA, float projB, const SliceTable& tab,

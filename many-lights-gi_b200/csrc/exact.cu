@@ -676,6 +676,16 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MINB) pullpush_kernel(const uin
     }
 }
 
+// test hook: the push phase's square-root elimination, evaluated on the device for caller-chosen radii
+__global__ void sqrt_threshold_kernel(const float* __restrict__ rs, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sqrt_gt_threshold(rs[i]);
+}
+int launch_sqrt_thresholds(const float* rs, int n, float* out, cudaStream_t st) {
+    sqrt_threshold_kernel<<<(n + 255) / 256, 256, 0, st>>>(rs, n, out);
+    return 1;
+}
+
 int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st) {
     const int ty0 = vpl_lo / S, ty1 = (vpl_hi + S - 1) / S;
     dim3 grid(S, ty1 - ty0);

@@ -72,7 +72,7 @@ EXPORTS = [
     "mlgi_version", "mlgi_default_params", "mlgi_create", "mlgi_destroy", "mlgi_last_error",
     "mlgi_vpl_process", "mlgi_ism_points", "mlgi_ism_set_points", "mlgi_ism_splat", "mlgi_ism_pullpush",
     "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_composite_ambient", "mlgi_frame", "mlgi_frame_host", "mlgi_frame_host_packed",
-    "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_read_buffer_async", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_exchange_create", "mlgi_exchange_connect", "mlgi_exchange_finish", "mlgi_exchange_status", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
+    "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_read_buffer_async", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_debug_sqrt_thresholds", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_exchange_create", "mlgi_exchange_connect", "mlgi_exchange_finish", "mlgi_exchange_status", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
 ]
 
 _lib = None
@@ -123,6 +123,7 @@ def load():
     lib.mlgi_gather_stats.argtypes = [P, C.POINTER(GBuffer), C.POINTER(Camera), P, C.POINTER(Params),
                                       C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     lib.mlgi_measure_fp32_peak_tflops.argtypes = [P]
+    lib.mlgi_debug_sqrt_thresholds.argtypes = [P, P, C.c_int, P, P]
     lib.mlgi_measure_fp32_peak_tflops.restype = C.c_float
     lib.mlgi_bind_planar_output.argtypes = [P, P]
     lib.mlgi_planar_to_raster.argtypes = [P, P, P, P]
@@ -267,6 +268,9 @@ class Context:
         self._ck(self.lib.mlgi_gather_stats(self.h, C.byref(gb), C.byref(cam), _ptr(ism_override), C.byref(params),
                                             C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def debug_sqrt_thresholds(self, radii, out, stream=None):
+        self._ck(self.lib.mlgi_debug_sqrt_thresholds(self.h, _ptr(radii), int(radii.numel()), _ptr(out), stream))
 
     def fp32_peak_tflops(self):
         return float(self.lib.mlgi_measure_fp32_peak_tflops(self.h))

@@ -551,3 +551,31 @@ def test_cpp_stage_mirror_demo_frame_matches_python_path():
     gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(H, W, 4)[:, :, :3]
     g.close()
     assert abs(float(m.group(1)) - float(gi.astype(np.float64).mean())) <= 2e-6 * float(gi.mean()) + 1e-9
+
+
+def test_sqrt_elimination_thresholds_are_exact(case_small):
+    """push.comp's `length(d) > radius` is evaluated as `dot(d, d) > T(radius)`. For a correctly rounded
+    square root the two are equivalent for EVERY x; checked here at the floats around each threshold, where a wrong T would
+    show, and on random x, for radii from zero and denormals to large values, infinity and NaN"""
+    torch = _torch()
+    g = Gpu(case_small)
+    rng = np.random.default_rng(11)
+    r = np.concatenate([
+        np.array([0.0, 1e-45, 1e-40, 1.17549435e-38, 1e-20, 0.25, 0.5, 1.0, 1.5, 2.0, 3.0, 15.0, 1e10, 3.4028235e38, np.inf, np.nan], np.float32),
+        rng.random(20000, dtype=np.float32) * 16.0, np.exp(rng.uniform(-80, 80, 20000)).astype(np.float32),
+        (rng.integers(0, 1 << 12, 5000).astype(np.float32) / 256.0)])          # values whose squares are exact floats
+    rt = torch.from_numpy(r).cuda()
+    out = torch.empty_like(rt)
+    g.ctx.debug_sqrt_thresholds(rt, out)
+    torch.cuda.synchronize()
+    T = out.cpu().numpy()
+    fin = np.isfinite(r)
+    assert np.all(np.isnan(T[~fin]))                       # inf / NaN radius: "never greater", like sqrt(x) > inf
+    rf, Tf = r[fin], T[fin]
+    with np.errstate(over="ignore", invalid="ignore"):
+        for x in (Tf, np.nextafter(Tf, np.float32(np.inf)), np.nextafter(Tf, np.float32(0)), (rf * rf).astype(np.float32),
+                  rng.random(len(rf), dtype=np.float32) * (rf * rf * 2).astype(np.float32)):
+            x = np.abs(x.astype(np.float32))
+            ok = np.isfinite(x)
+            assert np.array_equal((np.sqrt(x[ok]) > rf[ok]), (x[ok] > Tf[ok]))
+    g.close()
