@@ -851,9 +851,12 @@ int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_
 // a8: one CTA per 64x64 tile. Phase 1 unprojects the tile's pixels exactly as the gathering prologue does and reduces them
 // to 14 numbers (position AABB, normal box, emin, emag); phase 2 tests every VPL of the 16 classes against them (2 classes
 // per warp, ordered ballot compaction). The rule is stated in DESIGN.md section 4 / oracle.cpp tile_keeps_vpl.
+#ifndef CULL_MINB
+#define CULL_MINB 4
+#endif
 struct TileBounds { float pmin[3], pmax[3], nmin[3], nmax[3], emin, emag; };
 
-__global__ void __launch_bounds__(256) cull_tiled_kernel(const float* __restrict__ depth, const uint32_t* __restrict__ face_normal, int W, int H,
+__global__ void __launch_bounds__(256, CULL_MINB) cull_tiled_kernel(const float* __restrict__ depth, const uint32_t* __restrict__ face_normal, int W, int H,
                                                          const VplRecord* __restrict__ records, int N, Mat4 inv_vp, int class_lo,
                                                          int class_hi, int tile_y0, uint16_t* __restrict__ lists,
                                                          uint32_t* __restrict__ tile_weight) {
