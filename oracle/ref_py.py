@@ -11,15 +11,28 @@ _lib = None
 P = C.c_void_p
 
 
-def available():
-    return os.path.exists(LIB_PATH)
+_libs = {}
+_vpls = 1024          # which build the wrappers below call into (the reference's own constant is 1024)
+
+
+def lib_path(vpls=1024):
+    return LIB_PATH if vpls == 1024 else os.path.join(HERE, "_ref", "libref_glsl_v%d.so" % vpls)
+
+
+def available(vpls=1024):
+    return os.path.exists(lib_path(vpls))
+
+
+def use_vpls(vpls):
+    """select the build whose shaders were compiled with totalVplCount = vpls (build_ref.py --vpls)"""
+    global _vpls
+    _vpls = vpls
 
 
 def load():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(LIB_PATH)
-    return _lib
+    if _vpls not in _libs:
+        _libs[_vpls] = C.CDLL(lib_path(_vpls))
+    return _libs[_vpls]
 
 
 def _p(a):
@@ -124,7 +137,7 @@ def ism_points(vertices, normals, indices, prim_id, tess_level_factor, N, max_tr
     equal_spacing rounding ceil(clamp(inner level, 1, 64)) of the GL spec). Returns (points[P,4], bucket[P]) grouped by
     bucket in pointBuffer order."""
     lib = load()
-    assert N == 1024, "ism.geom hard-codes totalVplCount = 1024"
+    assert N == _vpls, "ism.geom was compiled for totalVplCount = %d" % _vpls
     ntri = indices.shape[0] if max_triangles is None else min(indices.shape[0], max_triangles)
     V, Tc, Nr, Pid = [], [], [], []
     lv = np.zeros(4, np.float32); pos = np.zeros(3, np.float32)
@@ -149,7 +162,7 @@ def ism_points(vertices, normals, indices, prim_id, tess_level_factor, N, max_tr
     T = len(V)
     V = _f32(np.array(V)); Tc = _f32(np.array(Tc)); Nr = _f32(np.array(Nr)); Pid = np.array(Pid, np.int32)
     stride = 4096
-    buf = np.zeros((N * stride, 4), np.float32); counters = np.zeros(1024, np.uint32)
+    buf = np.zeros((N * stride, 4), np.float32); counters = np.zeros(max(N, 1024), np.uint32)
     lib.ref_geom_run(_p(V), _p(Tc), _p(Nr), _p(Pid), T, N, _p(buf), N * stride, _p(counters))
     assert counters.max() <= stride
     pts = np.concatenate([buf[b * stride:b * stride + int(counters[b])] for b in range(N)])
@@ -165,3 +178,16 @@ def composite_ambient(gi_rgb, diffuse_rgba8, occlusion=None, exposure=1.0):
     occ = None if occlusion is None else _f32(occlusion)
     load().ref_composite_run(_p(rgba), _p(np.ascontiguousarray(diffuse_rgba8, np.uint32)), _p(occ), W, H, C.c_float(exposure), _p(out))
     return out
+
+
+def lists_image_from_canonical(lists, num_used, L):
+    """the reference's lightLists image (x = list id, y = class * L + slot) holding the given canonical lists
+    [cluster][16][L+1]; a full sub-list's last entry lands on the next class's counter and is overwritten by it, as in
+    the reference (the overflow race)"""
+    img = np.zeros((16 * L + L + 1, max(num_used, 1)), np.uint16)
+    for k in range(16):
+        for cl in range(num_used):
+            n = int(lists[cl, k, 0])
+            img[k * L + 1:k * L + n, cl] = lists[cl, k, 1:n]
+            img[k * L, cl] = n
+    return img

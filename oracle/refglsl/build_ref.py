@@ -146,7 +146,15 @@ def rewrite(lines, replacements, total_vpls):
 def main():
     """usage: build_ref.py [--keep] [unit ...]   (--keep leaves the generated C++ under oracle/_ref/gen for inspection)"""
     import shutil
+    # --vpls N: the reference hard-codes `const int totalVplCount = 1024;` in every shader; to exercise other VPL counts the
+    # literal is substituted (the same kind of textual replacement its host code applies to the #defines) and the library
+    # is written to libref_glsl_v<N>.so. light_lists.comp additionally hard-codes 64-entry sub-lists and is only meaningful
+    # at 1024.
     total_vpls = None
+    argv = sys.argv[1:]
+    if "--vpls" in argv:
+        i = argv.index("--vpls"); total_vpls = int(argv[i + 1]); del argv[i:i + 2]
+    sys.argv[1:] = argv
     keep = "--keep" in sys.argv[1:]
     shutil.rmtree(GEN, ignore_errors=True)
     os.makedirs(GEN, exist_ok=True)
@@ -168,7 +176,7 @@ def main():
                 f.write(body)
                 f.write('\n#include "../../refglsl/drivers/%s"\n}}\n' % driver)
             srcs.append(path)
-        lib = os.path.join(OUT, "libref_glsl.so")
+        lib = os.path.join(OUT, "libref_glsl.so" if total_vpls is None else "libref_glsl_v%d.so" % total_vpls)
         cmd = [CXX, "-std=c++20", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-o", lib] + srcs
         print(" ".join(cmd))
         subprocess.check_call(cmd)
