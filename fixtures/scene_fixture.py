@@ -1,4 +1,4 @@
-"""Synthetic-input fixture binding (libmlgi_scene.so, scene/scene.cpp): procedural atrium,
+"""Synthetic-input fixture binding (fixtures/libmlgi_scene.so, fixtures/scene.cpp): procedural atrium,
 its triangle mesh, cameras and ray-cast G-buffers. Untimed; stands in for the reference's
 out-of-scope rasteriser (RasterizationStage) and asset loader (ModelLoadingStage)."""
 import ctypes as C
@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmlgi_scene.so")
+LIB_PATH = os.path.join(_HERE, "libmlgi_scene.so")
 _lib = None
 
 

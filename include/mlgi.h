@@ -56,14 +56,15 @@ typedef enum { MLGI_CULL_CLUSTERED = 0, MLGI_CULL_TILED = 1, MLGI_CULL_NONE = 2 
 typedef struct {
     int device;          /* CUDA device ordinal */
     int width, height;   /* camera viewport (GIStage::resizeTexture, GIStage.cpp:468) */
-    int vpl_count;       /* N = totalVplCount; multiple of 16 and of ceil(sqrt(N)); 64..16384 */
+    int vpl_count;       /* N = totalVplCount; multiple of 16 and of ceil(sqrt(N)); 16..16384 */
     int rsm_width, rsm_height; /* RSM size (1024x256 in GIStage.cpp:236) */
     int max_triangles;   /* capacity of the scene mesh handed to mlgi_ism_points */
     int max_points;      /* capacity of the point buffer (reference: 2^23, ImperfectShadowmap.cpp:95) */
     int class_lo, class_hi; /* interleave classes [lo,hi) owned by this ctx; 0,16 = all (multi-GPU shard) */
     int enable_timers;   /* record per-stage cudaEvents (PerfCounter.cpp:50-76 scope names) */
     int gi_packed;       /* 1: gathering also emits the reference's giBuffer format GL_R11F_G11F_B10F (GIStage.cpp:470)
-                            into MLGI_BUF_GI_PACKED, and the multi-GPU exchange buffer is packed uint32 */
+                            into MLGI_BUF_GI_PACKED, and the multi-GPU exchange buffer is packed uint32;
+                            2: ONLY the packed image is produced (MLGI_BUF_GI is not written: 4 B instead of 20 B stored per pixel) */
 } mlgi_config;
 
 /* Tunables; names and defaults mirror GIStage (GIStage.h:84-100, GIStage.cpp:215-232). */
@@ -178,6 +179,18 @@ MLGI_API int mlgi_composite_ambient(mlgi_ctx*, const uint32_t* diffuse_rgba8, co
 MLGI_API int mlgi_frame(mlgi_ctx*, const mlgi_rsm*, const mlgi_camera* light, const mlgi_mesh*,
                         const mlgi_gbuffer*, const mlgi_camera* cam, const mlgi_params*, void* stream);
 
+/* The frame entry points replay a CUDA graph of the stage launches (re-captured only when pointers or values change; an
+ * animated light updates the instantiated graph in place). mlgi_set_graph(ctx, 0) or MLGI_GRAPH=0 selects direct launches;
+ * per-stage timers always use direct launches. */
+MLGI_API int mlgi_set_graph(mlgi_ctx*, int enable);
+typedef struct {
+    double host_enqueue_us;                 /* host time spent inside the last mlgi_frame / mlgi_frame_sharded call */
+    unsigned long long graph_replays;       /* frames issued as one cudaGraphLaunch */
+    unsigned long long graph_instantiations;/* captures that needed a new executable (value-only changes update in place) */
+    int graph_enabled;
+} mlgi_frame_stats;
+MLGI_API int mlgi_get_frame_stats(mlgi_ctx*, mlgi_frame_stats* out);
+
 /* Same, but the per-frame inputs (RSM + camera G-buffer) are HOST pointers (pinned for
  * full speed) and the GI image is copied back to host_gi (width*height*4 float, may be
  * NULL to skip). The mesh stays resident on the device (it is static scene data in the
@@ -214,19 +227,36 @@ MLGI_API int mlgi_debug_sqrt_thresholds(mlgi_ctx*, const float* dev_radii, int n
  * c*PH*PW), so one in-place all-gather over ranks assembles the image; NULL unbinds. With cfg.gi_packed the
  * buffer holds one uint32 (R11F_G11F_B10F) per pixel instead of 4 floats. */
 MLGI_API int mlgi_bind_planar_output(mlgi_ctx*, void* dev_planar16);
-/* Fused exchange (B200/NVSwitch path, replaces the all-gather): every rank allocates an exchange buffer, the 64-byte
- * CUDA IPC handles are swapped by the caller (any host transport), and from then on the gathering kernel of each rank
- * stores its class planes straight into EVERY rank's buffer over NVLink while it is still gathering; completion flags
- * in peer memory replace the collective. One process per GPU, all on one node, world <= 8.
+/* Peer-memory exchange (B200/NVSwitch path, replaces the all-gather; SURVEY 8(e) mlgi_dist_init / mlgi_allgather): every rank
+ * allocates an exchange region, the 64-byte CUDA IPC handles are swapped by the caller (any host transport), and from then
+ * on ONE kernel per frame signals "my class planes are written" in every peer's flag array, waits for all ranks, and
+ * assembles the image while pulling the other ranks' planes over NVLink with 16-byte loads (MLGI_XCH=push: the gathering
+ * epilogue stores into every rank's region instead, the round-1 scheme). The frame counter lives in device memory, so the
+ * whole frame is graph-replayable. One process per GPU (or one process, mlgi_exchange_connect_local), one node, world in
+ * {2,4,8}; rank r must own classes [16r/world, 16(r+1)/world).
  *   mlgi_exchange_create : allocate, return this rank's handle (out_handle64 = 64 bytes)
  *   mlgi_exchange_connect: all_handles = world x 64 bytes in rank order; maps the peers
- *   mlgi_exchange_finish : after mlgi_frame on the same stream: signal, wait for all ranks, de-interleave into
- *                          MLGI_BUF_GI (and MLGI_BUF_GI_PACKED). Asynchronous; bounded wait (no GPU hang if a peer dies)
+ *   mlgi_exchange_finish : after mlgi_frame on the same stream: signal, wait, pull + de-interleave into
+ *                          MLGI_BUF_GI_PACKED / MLGI_BUF_GI. Asynchronous; bounded wait (no GPU hang if a peer dies)
  *   mlgi_exchange_status : synchronises and reports a timed-out wait */
 MLGI_API int mlgi_exchange_create(mlgi_ctx*, int rank, int world, void* out_handle64);
 MLGI_API int mlgi_exchange_connect(mlgi_ctx*, const void* all_handles);
+/* same-process form (a host driving several GPUs from one thread, like the reference's single painter thread): all_ctx =
+ * world ctx pointers in rank order, every one after mlgi_exchange_create; peer access is enabled as needed */
+MLGI_API int mlgi_exchange_connect_local(mlgi_ctx*, mlgi_ctx* const* all_ctx);
 MLGI_API int mlgi_exchange_finish(mlgi_ctx*, void* stream);
 MLGI_API int mlgi_exchange_status(mlgi_ctx*);
+/* SURVEY 8(e) mlgi_frame_sharded: one rank's frame of a class-sharded job = mlgi_frame + mlgi_exchange_finish as ONE graph
+ * launch; afterwards MLGI_BUF_GI_PACKED / MLGI_BUF_GI hold the complete image on every rank. */
+MLGI_API int mlgi_frame_sharded(mlgi_ctx*, const mlgi_rsm*, const mlgi_camera* light, const mlgi_mesh*,
+                                const mlgi_gbuffer*, const mlgi_camera* cam, const mlgi_params*, void* stream);
+/* The same with HOST inputs (the N-GPU form of mlgi_frame_host_packed). host_gbuffer and host_gi_packed are FULL-size host
+ * arrays; this rank uploads rows [rank*H/world, (rank+1)*H/world) of the G-buffer, pushes them to every peer over NVLink
+ * (copy engines, beside the ISM build), and writes the same rows of the assembled GL_R11F_G11F_B10F image back. Every input
+ * byte crosses PCIe once in the whole job (the 3 MB RSM once per rank). Needs cfg.gi_packed. Synchronises the stream. */
+MLGI_API int mlgi_frame_sharded_host(mlgi_ctx*, const mlgi_rsm* host_rsm, const mlgi_camera* light, const mlgi_mesh* dev_mesh,
+                                     const mlgi_gbuffer* host_gbuffer, const mlgi_camera* cam, const mlgi_params*,
+                                     uint32_t* host_gi_packed, void* stream);
 /* consumer-side de-interleave of a complete planar image into raster order (dev_raster NULL = ctx GI buffer) */
 MLGI_API int mlgi_planar_to_raster(mlgi_ctx*, const void* dev_planar16, float* dev_raster, void* stream);
 

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <numeric>
 #include <random>
@@ -97,19 +98,31 @@ struct mlgi_ctx {
     float4* gi = nullptr; float4* gi_planar = nullptr; float4* gi_tmp = nullptr; float4* gi_blur = nullptr;
     unsigned long long* stats = nullptr;
     cudaTextureObject_t ism_tex = 0;      // ctx ISM atlas as an R16-unorm point-sampled texture
-    cudaTextureObject_t override_tex = 0; const uint16_t* override_ptr = nullptr;   // cached texture of the last ISM override
+    // textures of caller-supplied ISM overrides, one per distinct pointer. A texture object may still be referenced by a
+    // gathering kernel queued on some stream, so entries are only destroyed in mlgi_destroy (after a device synchronise)
+    // or, when the cache is full, after an explicit cudaDeviceSynchronize.
+    struct OverrideTex { const uint16_t* ptr; cudaTextureObject_t tex; };
+    std::vector<OverrideTex> override_tex;
     int use_texture = 1, tex_float_coord = 0;
-    // fused multi-GPU exchange (mlgi_exchange_*): two parity buffers + flag array in ONE IPC-exportable allocation
+    // multi-GPU exchange (mlgi_exchange_*): ONE IPC-exportable allocation per rank,
+    //   [flags 256 B][class planes, parity 0][class planes, parity 1][G-buffer depth W*H*4][G-buffer normals W*H*4]
+    // flags[0..7]: "planes of frame f written" per rank; flags[8..15]: "G-buffer slab of frame f pushed" per rank.
     struct Exchange {
         int rank = 0, world = 0;
-        char* base = nullptr;                 // own allocation: [flags 256 B][buffer 0][buffer 1]
-        size_t buf_bytes = 0;
+        int push = 0;                         // 0: gathering writes its own buffer, the exchange kernel pulls over NVLink (default)
+                                              // 1: the gathering epilogue stores into every rank's buffer (round-1 scheme; MLGI_XCH=push)
+        char* base = nullptr;
+        size_t buf_bytes = 0, gb_off = 0;
         char* peer_base[8] = {nullptr};       // peer-mapped allocations (own slot = base)
-        uint32_t** d_peer_flags = nullptr;    // device array of world pointers (for the signal kernel)
-        uint32_t* d_error = nullptr;
-        uint32_t frame = 0;
-        bool connected = false;
+        uint32_t** d_peer_flags = nullptr;    // device array of world pointers (for the flag kernels)
+        uint32_t* d_state = nullptr;          // [0] frame counter, [1] ticket, [2] error flag
+        bool connected = false, local_peers = false;
     } xch;
+    // CUDA graph of the frame (frame_graphed)
+    int use_graph = 1; bool graph_valid = false;
+    cudaStream_t cap = nullptr; cudaGraphExec_t graph_exec = nullptr; std::vector<char> graph_key;
+    unsigned long long graph_launches = 0, graph_replays = 0, graph_instantiations = 0;
+    double last_enqueue_us = 0.0;
     float4* planar_ext = nullptr;   // caller-owned [16][PH][PW] float4 exchange buffer (mlgi_bind_planar_output)
     // staging for mlgi_frame_host
     uint32_t* st_rsm_diffuse = nullptr; uint32_t* st_rsm_normal = nullptr; float* st_rsm_depth = nullptr;
@@ -187,6 +200,16 @@ int check_params(mlgi_ctx* ctx, const mlgi_params* p) {
     if (p->vpl_end_index <= p->vpl_start_index) return fail(ctx, MLGI_E_INVALID, "vpl_end_index must exceed vpl_start_index");
     return MLGI_OK;
 }
+
+// Every public entry point runs on the ctx device whatever device the calling thread had selected (a host may hold one ctx
+// per GPU, or another library may have switched devices); the caller's device is restored on return.
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(const mlgi_ctx* c) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != c->cfg.device) switched = cudaSetDevice(c->cfg.device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 struct StageTimer {
     mlgi_ctx* c; int id; cudaStream_t st; unsigned long long l0;
@@ -282,7 +305,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     ALLOC(counters, 4);
     ALLOC(atlas, AA); ALLOC(ism, AA);
     ALLOC(tile_masks, (size_t)ctx->X * ctx->Y); ALLOC(compact_ids, maxClusters); ALLOC(light_list_ids, maxClusters);
-    ALLOC(light_lists, maxClusters * 16 * (ctx->L + 1));
+    // light_lists ([clusters][16][L+1] uint16: 1 GB at 8K / 16384 VPLs) is allocated by the first clustered cull (ensure_clustered)
     ALLOC(tile_lists, (size_t)ctx->TX * ctx->TY * 16 * (ctx->L + 1));
     ALLOC(tile_weight, (size_t)ctx->TX * ctx->TY); ALLOC(tile_order, (size_t)ctx->TX * ctx->TY);
     ALLOC(gi, WH); ALLOC(gi_planar, (size_t)(cfg->class_hi - cfg->class_lo) * PW * PH); ALLOC(gi_tmp, WH); ALLOC(gi_blur, WH);
@@ -309,6 +332,8 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_clear, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->cap, cudaStreamNonBlocking);
+    if (const char* e7 = getenv("MLGI_GRAPH")) ctx->use_graph = atoi(e7) != 0;                  // A/B switch: graph replay (default) | direct launches
     cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->fg2, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_ism, cudaEventDisableTiming);
@@ -327,12 +352,14 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
 
 MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->cfg.device);
+    DeviceGuard dg_(ctx);
     cudaDeviceSynchronize();
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_clear) cudaEventDestroy(ctx->ev_clear);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->cap) cudaStreamDestroy(ctx->cap);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->fg2) cudaStreamDestroy(ctx->fg2);
     if (ctx->ev_ism) cudaEventDestroy(ctx->ev_ism);
@@ -341,13 +368,13 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
         if (ctx->ev_cull[k]) cudaEventDestroy(ctx->ev_cull[k]);
         if (ctx->ev_fg[k]) cudaEventDestroy(ctx->ev_fg[k]);
     }
-    for (int g = 0; g < ctx->xch.world; g++)
+    for (int g = 0; g < ctx->xch.world && !ctx->xch.local_peers; g++)
         if (g != ctx->xch.rank && ctx->xch.peer_base[g]) cudaIpcCloseMemHandle(ctx->xch.peer_base[g]);
     if (ctx->xch.base) cudaFree(ctx->xch.base);
     if (ctx->xch.d_peer_flags) cudaFree(ctx->xch.d_peer_flags);
-    if (ctx->xch.d_error) cudaFree(ctx->xch.d_error);
+    if (ctx->xch.d_state) cudaFree(ctx->xch.d_state);
     if (ctx->ism_tex) cudaDestroyTextureObject(ctx->ism_tex);
-    if (ctx->override_tex) cudaDestroyTextureObject(ctx->override_tex);
+    for (auto& o : ctx->override_tex) cudaDestroyTextureObject(o.tex);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->events_created)
         for (int i = 0; i < T_COUNT; i++) { cudaEventDestroy(ctx->ev[i][0]); cudaEventDestroy(ctx->ev[i][1]); }
@@ -358,6 +385,7 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
 // ------------------------------------------------------------------------------------- a1
 MLGI_API int mlgi_vpl_process(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!rsm || !light || !rsm->diffuse || !rsm->face_normal || !rsm->depth) return fail(ctx, MLGI_E_INVALID, "rsm/light is NULL");
     int rc = check_params(ctx, p);
     if (rc) return rc;
@@ -379,6 +407,7 @@ MLGI_API int mlgi_vpl_process(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_cam
 // ------------------------------------------------------------------------------------- a2
 MLGI_API int mlgi_ism_points(mlgi_ctx* ctx, const mlgi_mesh* mesh, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!mesh) return fail(ctx, MLGI_E_INVALID, "mesh is NULL");
     if (mesh->num_triangles == 0) {            // no drawables (ImperfectShadowmap.cpp:225-240 draws nothing): no points
         cudaStream_t st0 = (cudaStream_t)stream;
@@ -403,6 +432,7 @@ MLGI_API int mlgi_ism_points(mlgi_ctx* ctx, const mlgi_mesh* mesh, const mlgi_pa
 // a caller-provided bucket-grouped point list (the reference's pointBuffer layout, compacted): becomes the ctx point list
 MLGI_API int mlgi_ism_set_points(mlgi_ctx* ctx, const float* points, const uint32_t* bucket_start, int num_points, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!points || !bucket_start || num_points < 0) return fail(ctx, MLGI_E_INVALID, "points/bucket_start is NULL");
     if (num_points > ctx->cfg.max_points) return fail(ctx, MLGI_E_CAPACITY, "%d points exceed ctx capacity %d", num_points, ctx->cfg.max_points);
     cudaStream_t st = (cudaStream_t)stream;
@@ -420,6 +450,7 @@ MLGI_API int mlgi_ism_set_points(mlgi_ctx* ctx, const float* points, const uint3
 // ------------------------------------------------------------------------------------- a3
 MLGI_API int mlgi_ism_splat(mlgi_ctx* ctx, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     const bool clear = !ctx->atlas_precleared;      // consumed on every path, so a failed call cannot leave it set
     ctx->atlas_precleared = false;
     int rc = check_params(ctx, p);
@@ -437,6 +468,7 @@ MLGI_API int mlgi_ism_splat(mlgi_ctx* ctx, const mlgi_params* p, void* stream) {
 // ------------------------------------------------------------------------------------- a4+a5
 MLGI_API int mlgi_ism_pullpush(mlgi_ctx* ctx, const uint32_t* atlas_override, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     int rc = check_params(ctx, p);
     if (rc) return rc;
     if (!atlas_override && !ctx->have_atlas) return fail(ctx, MLGI_E_ORDER, "mlgi_ism_pullpush needs mlgi_ism_splat first (or an atlas override)");
@@ -450,12 +482,24 @@ MLGI_API int mlgi_ism_pullpush(mlgi_ctx* ctx, const uint32_t* atlas_override, co
 }
 
 // ------------------------------------------------------------------------------------- a6+a7
+// Clustered culling stores compact cluster ids as uint16 with 0xFFFF = "unused" (the reference's R16UI lightListIds texture,
+// ClusteredShading.cpp:122), so a viewport needs fewer than 65535 clusters; its worst-case list buffer is allocated on first
+// use (tiled culling, the default, never touches it). Must run outside stream capture (cudaMalloc).
+static int ensure_clustered(mlgi_ctx* ctx) {
+    const size_t maxClusters = (size_t)ctx->X * ctx->Y * 16;
+    if (maxClusters >= 65535) return fail(ctx, MLGI_E_UNSUPPORTED, "clustered culling needs X*Y*16 < 65535 clusters (16-bit list ids, ClusteredShading.cpp:122); this viewport has %zu -- use tiled culling", maxClusters);
+    if (!ctx->light_lists) CK(dalloc(ctx, &ctx->light_lists, maxClusters * 16 * (ctx->L + 1)));
+    return MLGI_OK;
+}
+
 MLGI_API int mlgi_cull_clustered(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!gb || !gb->depth || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
     int rc = check_params(ctx, p);
     if (rc) return rc;
     if (!ctx->have_vpl) return fail(ctx, MLGI_E_ORDER, "culling needs mlgi_vpl_process first");
+    if ((rc = ensure_clustered(ctx))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const SliceTable tab = slice_table(p->z_far);
     float pv[16], inv[16];
@@ -479,6 +523,7 @@ MLGI_API int mlgi_cull_clustered(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const ml
 // ------------------------------------------------------------------------------------- a8
 MLGI_API int mlgi_cull_tiled(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!gb || !gb->depth || !gb->face_normal || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
     int rc = check_params(ctx, p);
     if (rc) return rc;
@@ -517,13 +562,17 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     if (ctx->use_texture) {
         if (!ism_override) a.ism_tex = ctx->ism_tex;
         else {
-            if (ctx->override_ptr != ism_override) {
-                if (ctx->override_tex) cudaDestroyTextureObject(ctx->override_tex);
-                ctx->override_tex = 0; ctx->override_ptr = nullptr;
-                if (make_ism_texture(ism_override, ctx->A, &ctx->override_tex) == cudaSuccess) ctx->override_ptr = ism_override;
-                else cudaGetLastError();
+            for (auto& o : ctx->override_tex) if (o.ptr == ism_override) a.ism_tex = o.tex;
+            if (!a.ism_tex) {
+                if (ctx->override_tex.size() >= 16) {       // bounded cache: nothing may still be sampling the old objects
+                    cudaDeviceSynchronize();
+                    for (auto& o : ctx->override_tex) cudaDestroyTextureObject(o.tex);
+                    ctx->override_tex.clear();
+                }
+                cudaTextureObject_t t = 0;
+                if (make_ism_texture(ism_override, ctx->A, &t) == cudaSuccess) { ctx->override_tex.push_back({ism_override, t}); a.ism_tex = t; }
+                else cudaGetLastError();                    // no texture: the kernel falls back to plain loads of the override
             }
-            a.ism_tex = ctx->override_tex;
         }
     }
     a.cull_mode = p->cull_mode;
@@ -551,14 +600,16 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     const bool partial = ctx->cfg.class_lo != 0 || ctx->cfg.class_hi != 16;
     if (ctx->xch.connected) {
         a.out_raster = nullptr; a.planar_class0 = 0;
-        a.num_peers = ctx->xch.world; a.peer_packed = ctx->cfg.gi_packed;
-        const size_t boff = 256 + (size_t)((ctx->xch.frame + 1) & 1) * ctx->xch.buf_bytes;   // buffer of the frame being produced
-        for (int g = 0; g < ctx->xch.world; g++) a.peer_planar[g] = ctx->xch.peer_base[g] + boff;
+        a.peer_packed = ctx->cfg.gi_packed != 0;
+        a.peer_parity_stride = ctx->xch.buf_bytes; a.frame_ctr = ctx->xch.d_state;
+        if (ctx->xch.push) { a.num_peers = ctx->xch.world; for (int g = 0; g < ctx->xch.world; g++) a.peer_planar[g] = ctx->xch.peer_base[g] + 256; }
+        else { a.num_peers = 1; a.peer_planar[0] = ctx->xch.base + 256; }
     } else if (ctx->planar_ext) {
         a.out_raster = nullptr; a.planar_class0 = 0;
         if (ctx->cfg.gi_packed) a.out_planar_packed = (uint32_t*)ctx->planar_ext; else a.out_planar = ctx->planar_ext;
     } else {
-        a.out_raster = ctx->gi; a.out_planar = partial ? ctx->gi_planar : nullptr; a.planar_class0 = ctx->cfg.class_lo;
+        a.out_raster = ctx->cfg.gi_packed == 2 ? nullptr : ctx->gi;      // gi_packed == 2: only the packed image is produced
+        a.out_planar = (partial && ctx->cfg.gi_packed != 2) ? ctx->gi_planar : nullptr; a.planar_class0 = ctx->cfg.class_lo;
         a.out_packed = ctx->gi_packed;          // null unless cfg.gi_packed
     }
     a.stats = nullptr;
@@ -568,6 +619,7 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
 MLGI_API int mlgi_final_gather(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const uint16_t* ism_override,
                                const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     GatherArgs a;
     int rc = build_gather_args(ctx, gb, cam, ism_override, p, &a);
     if (rc) return rc;
@@ -584,12 +636,14 @@ MLGI_API int mlgi_final_gather(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi
 MLGI_API int mlgi_gather_stats(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const uint16_t* ism_override,
                                const mlgi_params* p, unsigned long long* listed, unsigned long long* lit) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     GatherArgs a;
     int rc = build_gather_args(ctx, gb, cam, ism_override, p, &a);
     if (rc) return rc;
     a.stats = ctx->stats;
     a.out_raster = nullptr;     // counting variant: same loop, counters instead of stores
     a.out_planar = nullptr; a.out_packed = nullptr; a.out_planar_packed = nullptr; a.num_peers = 0;
+    CK(cudaDeviceSynchronize());     // the legacy stream does not order against cudaStreamNonBlocking streams the stages ran on
     CK(cudaMemset(ctx->stats, 0, 2 * sizeof(unsigned long long)));
     ctx->launches += launch_final_gather(a, 0);
     unsigned long long h[2];
@@ -602,12 +656,15 @@ MLGI_API int mlgi_gather_stats(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi
 
 MLGI_API int mlgi_bind_planar_output(mlgi_ctx* ctx, void* dev_planar16) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     ctx->planar_ext = (float4*)dev_planar16;
+    ctx->graph_valid = false;
     return MLGI_OK;
 }
 
 MLGI_API int mlgi_planar_to_raster(mlgi_ctx* ctx, const void* dev_planar16, float* dev_raster, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!dev_planar16) return fail(ctx, MLGI_E_INVALID, "planar buffer is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->cfg.gi_packed) ctx->launches += launch_planar_packed_to_raster((const uint32_t*)dev_planar16, ctx->cfg.width, ctx->cfg.height,
@@ -619,21 +676,27 @@ MLGI_API int mlgi_planar_to_raster(mlgi_ctx* ctx, const void* dev_planar16, floa
     return MLGI_OK;
 }
 
-// ------------------------------------------------------------------------------------- fused exchange
+// ------------------------------------------------------------------------------------- multi-GPU exchange
 MLGI_API int mlgi_exchange_create(mlgi_ctx* ctx, int rank, int world, void* out_handle64) {
     if (!ctx) return MLGI_E_INVALID;
-    if (world < 2 || world > 8 || rank < 0 || rank >= world || !out_handle64) return fail(ctx, MLGI_E_INVALID, "exchange needs 2 <= world <= 8");
+    DeviceGuard dg_(ctx);
+    if (world < 2 || world > 8 || 16 % world || rank < 0 || rank >= world || !out_handle64) return fail(ctx, MLGI_E_INVALID, "exchange needs world in {2,4,8} and 0 <= rank < world");
+    if (ctx->cfg.class_lo != rank * (16 / world) || ctx->cfg.class_hi != (rank + 1) * (16 / world))
+        return fail(ctx, MLGI_E_INVALID, "rank %d of %d must own interleave classes [%d,%d)", rank, world, rank * (16 / world), (rank + 1) * (16 / world));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
     auto& x = ctx->xch;
     if (x.base) return fail(ctx, MLGI_E_INVALID, "exchange already created");
-    const size_t PW = (ctx->cfg.width + 3) / 4, PH = (ctx->cfg.height + 3) / 4;
+    const size_t PW = (ctx->cfg.width + 3) / 4, PH = (ctx->cfg.height + 3) / 4, WH = (size_t)ctx->cfg.width * ctx->cfg.height;
     x.buf_bytes = ((16 * PW * PH * (ctx->cfg.gi_packed ? 4 : 16)) + 255) & ~(size_t)255;
-    CK(cudaMalloc((void**)&x.base, 256 + 2 * x.buf_bytes));
-    CK(cudaMemset(x.base, 0, 256 + 2 * x.buf_bytes));
+    x.gb_off = 256 + 2 * x.buf_bytes;
+    const size_t total = x.gb_off + 2 * ((WH * 4 + 255) & ~(size_t)255);
+    CK(cudaMalloc((void**)&x.base, total));
+    CK(cudaMemset(x.base, 0, total));
     CK(cudaMalloc((void**)&x.d_peer_flags, 8 * sizeof(uint32_t*)));
-    CK(cudaMalloc((void**)&x.d_error, sizeof(uint32_t)));
-    CK(cudaMemset(x.d_error, 0, sizeof(uint32_t)));
+    CK(cudaMalloc((void**)&x.d_state, 4 * sizeof(uint32_t)));
+    CK(cudaMemset(x.d_state, 0, 4 * sizeof(uint32_t)));
     x.rank = rank; x.world = world;
+    if (const char* e = getenv("MLGI_XCH")) x.push = strcmp(e, "push") == 0;      // A/B switch
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, x.base));
     memcpy(out_handle64, &h, 64);
@@ -642,6 +705,7 @@ MLGI_API int mlgi_exchange_create(mlgi_ctx* ctx, int rank, int world, void* out_
 
 MLGI_API int mlgi_exchange_connect(mlgi_ctx* ctx, const void* all_handles) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     auto& x = ctx->xch;
     if (!x.base || !all_handles) return fail(ctx, MLGI_E_ORDER, "mlgi_exchange_connect needs mlgi_exchange_create first");
     uint32_t* flags[8] = {nullptr};
@@ -658,22 +722,65 @@ MLGI_API int mlgi_exchange_connect(mlgi_ctx* ctx, const void* all_handles) {
     }
     CK(cudaMemcpy(x.d_peer_flags, flags, sizeof(flags), cudaMemcpyHostToDevice));
     x.connected = true;
+    ctx->graph_valid = false;
     return MLGI_OK;
 }
 
-// signal peers that this rank's planes of the current frame are written, wait for every rank's signal, then
-// de-interleave the assembled planes into the ctx GI image(s). Call after mlgi_frame on the same stream.
+// same-process variant for a host that drives several GPUs from one process (e.g. the C++ GIStage mirror, or the
+// single-GPU sequential-shard test): the peers' allocations are handed over as plain device pointers
+MLGI_API int mlgi_exchange_connect_local(mlgi_ctx* ctx, mlgi_ctx* const* all_ctx) {
+    if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
+    auto& x = ctx->xch;
+    if (!x.base || !all_ctx) return fail(ctx, MLGI_E_ORDER, "mlgi_exchange_connect_local needs mlgi_exchange_create first");
+    uint32_t* flags[8] = {nullptr};
+    for (int g = 0; g < x.world; g++) {
+        if (!all_ctx[g] || !all_ctx[g]->xch.base) return fail(ctx, MLGI_E_ORDER, "rank %d has no exchange allocation", g);
+        if (all_ctx[g]->cfg.device != ctx->cfg.device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->cfg.device, all_ctx[g]->cfg.device));
+            if (!can) return fail(ctx, MLGI_E_UNSUPPORTED, "device %d cannot access device %d", ctx->cfg.device, all_ctx[g]->cfg.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(all_ctx[g]->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, MLGI_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        x.peer_base[g] = all_ctx[g]->xch.base;
+        flags[g] = (uint32_t*)x.peer_base[g];
+    }
+    for (int g = 0; g < x.world; g++) if (g != x.rank) x.peer_base[g] = all_ctx[g]->xch.base;
+    CK(cudaMemcpy(x.d_peer_flags, flags, sizeof(flags), cudaMemcpyHostToDevice));
+    x.connected = true; x.local_peers = true;
+    ctx->graph_valid = false;
+    return MLGI_OK;
+}
+
+static void build_exchange_args(mlgi_ctx* ctx, ExchangeArgs* out) {
+    auto& x = ctx->xch;
+    ExchangeArgs& e = *out;
+    memset(&e, 0, sizeof(e));
+    e.W = ctx->cfg.width; e.H = ctx->cfg.height; e.world = x.world; e.rank = x.rank; e.packed = ctx->cfg.gi_packed != 0;
+    for (int g = 0; g < x.world; g++) {
+        e.src[g] = (x.push ? x.base : x.peer_base[g]) + 256;
+        e.peer_flags[g] = (uint32_t*)x.peer_base[g];
+    }
+    e.parity_stride = x.buf_bytes;
+    e.flags = (const uint32_t*)x.base;
+    e.frame_ctr = x.d_state; e.ticket = x.d_state + 1; e.error = x.d_state + 2;
+    e.raster_packed = ctx->gi_packed;
+    e.raster = ctx->cfg.gi_packed == 2 ? nullptr : ctx->gi;
+}
+
+// signal the peers that this rank's planes of the current frame are written, wait for every rank's signal, then assemble
+// the image: MLGI_BUF_GI_PACKED / MLGI_BUF_GI. One kernel; call after mlgi_frame on the same stream (mlgi_frame_sharded
+// does both). Asynchronous; bounded wait.
 MLGI_API int mlgi_exchange_finish(mlgi_ctx* ctx, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     auto& x = ctx->xch;
     if (!x.connected) return fail(ctx, MLGI_E_ORDER, "exchange is not connected");
-    cudaStream_t st = (cudaStream_t)stream;
-    x.frame++;
-    ctx->launches += launch_exchange_signal(x.d_peer_flags, x.world, x.rank, x.frame, st);
-    ctx->launches += launch_exchange_wait((const uint32_t*)x.base, x.world, x.frame, x.d_error, st);
-    const char* buf = x.base + 256 + (size_t)(x.frame & 1) * x.buf_bytes;
-    if (ctx->cfg.gi_packed) ctx->launches += launch_planar_packed_to_raster((const uint32_t*)buf, ctx->cfg.width, ctx->cfg.height, ctx->gi_packed, ctx->gi, st);
-    else ctx->launches += launch_planar_to_raster((const float4*)buf, ctx->cfg.width, ctx->cfg.height, 0, 16, ctx->gi, st);
+    ExchangeArgs e;
+    build_exchange_args(ctx, &e);
+    ctx->launches += launch_exchange(e, (cudaStream_t)stream);
     CK(cudaGetLastError());
     ctx->have_gi = true; ctx->have_blur = false;
     return MLGI_OK;
@@ -681,22 +788,25 @@ MLGI_API int mlgi_exchange_finish(mlgi_ctx* ctx, void* stream) {
 
 MLGI_API int mlgi_exchange_status(mlgi_ctx* ctx) {      // synchronises; 0 = ok, MLGI_E_CUDA if a peer never signalled
     if (!ctx) return MLGI_E_INVALID;
-    if (!ctx->xch.d_error) return MLGI_OK;
+    DeviceGuard dg_(ctx);
+    if (!ctx->xch.d_state) return MLGI_OK;
     uint32_t e = 0;
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(&e, ctx->xch.d_error, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&e, ctx->xch.d_state + 2, 4, cudaMemcpyDeviceToHost));
     if (e) return fail(ctx, MLGI_E_CUDA, "exchange timed out waiting for rank %u", e - 1);
     return MLGI_OK;
 }
 
 MLGI_API int mlgi_set_timers(mlgi_ctx* ctx, int enable) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     ctx->cfg.enable_timers = enable ? 1 : 0;
     return MLGI_OK;
 }
 
 MLGI_API int mlgi_debug_sqrt_thresholds(mlgi_ctx* ctx, const float* dev_radii, int n, float* dev_thresholds, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!dev_radii || !dev_thresholds || n < 0) return fail(ctx, MLGI_E_INVALID, "radii/thresholds is NULL");
     ctx->launches += launch_sqrt_thresholds(dev_radii, n, dev_thresholds, (cudaStream_t)stream);
     CK(cudaGetLastError());
@@ -705,12 +815,14 @@ MLGI_API int mlgi_debug_sqrt_thresholds(mlgi_ctx* ctx, const float* dev_radii, i
 
 MLGI_API float mlgi_measure_fp32_peak_tflops(mlgi_ctx* ctx) {
     if (!ctx) return -1.0f;
-    return measure_fp32_peak_tflops(0);
+    DeviceGuard dg_(ctx);
+    return measure_fp32_peak_tflops(ctx->cfg.device, 0);
 }
 
 // ------------------------------------------------------------------------------------- n1
 MLGI_API int mlgi_gi_blur(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!gb || !gb->depth || !gb->face_normal || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
     if (!ctx->have_gi) return fail(ctx, MLGI_E_ORDER, "mlgi_gi_blur needs mlgi_final_gather first");
     cudaStream_t st = (cudaStream_t)stream;
@@ -726,6 +838,7 @@ MLGI_API int mlgi_gi_blur(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_came
 MLGI_API int mlgi_composite_ambient(mlgi_ctx* ctx, const uint32_t* diffuse_rgba8, const float* occlusion, float exposure, int use_blurred,
                                     uint32_t* out_srgb8, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!diffuse_rgba8 || !out_srgb8) return fail(ctx, MLGI_E_INVALID, "diffuse/out is NULL");
     if (!ctx->have_gi) return fail(ctx, MLGI_E_ORDER, "mlgi_composite_ambient needs mlgi_final_gather first");
     if (use_blurred && !ctx->have_blur) return fail(ctx, MLGI_E_ORDER, "mlgi_composite_ambient(use_blurred) needs mlgi_gi_blur first");
@@ -736,14 +849,14 @@ MLGI_API int mlgi_composite_ambient(mlgi_ctx* ctx, const uint32_t* diffuse_rgba8
 }
 
 // ------------------------------------------------------------------------------------- a10
-MLGI_API int mlgi_frame(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
-                        const mlgi_camera* cam, const mlgi_params* p, void* stream) {
-    if (!ctx) return MLGI_E_INVALID;
+// The frame as direct launches on `st` (also what gets captured into the CUDA graph).
+static int frame_body(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
+                      const mlgi_camera* cam, const mlgi_params* p, bool with_exchange, cudaStream_t st) {
     int rc;
+    void* stream = (void*)st;
     if ((rc = mlgi_vpl_process(ctx, rsm, light, p, stream))) return rc;          // GIStage.cpp:373-376
     // The reference runs ISM build and culling back to back on one GL queue (GIStage.cpp:378-403); they only share
     // the VPL buffer as input, so culling is forked onto a side stream and joined before gathering.
-    cudaStream_t st = (cudaStream_t)stream;
     const bool fork = ctx->side != nullptr && p->cull_mode != MLGI_CULL_NONE;
     if (fork) {
         CK(cudaEventRecord(ctx->ev_fork, st));
@@ -760,12 +873,104 @@ MLGI_API int mlgi_frame(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* l
     if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;                         //          ISM CS
     if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;             //          pull / push
     if (fork) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    return mlgi_final_gather(ctx, gb, cam, nullptr, p, stream);                   // :405-408
+    if ((rc = mlgi_final_gather(ctx, gb, cam, nullptr, p, stream))) return rc;    // :405-408
+    if (with_exchange) rc = mlgi_exchange_finish(ctx, stream);
+    return rc;
+}
+
+// mlgi_frame / mlgi_frame_sharded replay a CUDA graph of frame_body: one cudaGraphLaunch instead of 8 launches, 2 memsets
+// and 6 event operations per frame. The graph is captured on an internal stream (the caller's may be the legacy stream,
+// which cannot be captured) and keyed on everything the launches bake in -- pointers, matrices, parameters; when only
+// values change (an animated light moves every frame) the re-captured graph updates the executable in place
+// (cudaGraphExecUpdate), a structural change re-instantiates it. Per-stage timers need the direct path.
+struct FrameKey {
+    mlgi_rsm rsm; mlgi_camera light; mlgi_mesh mesh; mlgi_gbuffer gb; mlgi_camera cam; mlgi_params p;
+    int with_exchange, push, fg_sorted, use_texture, tex_float_coord; const void* planar_ext;
+};
+
+static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
+                         const mlgi_camera* cam, const mlgi_params* p, bool with_exchange, void* stream) {
+    if (!rsm || !light || !mesh || !gb || !cam || !p) return fail(ctx, MLGI_E_INVALID, "mlgi_frame: NULL argument");
+    if (with_exchange && !ctx->xch.connected) return fail(ctx, MLGI_E_ORDER, "mlgi_frame_sharded needs a connected exchange");
+    cudaStream_t st = (cudaStream_t)stream;
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = MLGI_OK;
+    if (!ctx->use_graph || ctx->cfg.enable_timers || !ctx->cap) {
+        rc = frame_body(ctx, rsm, light, mesh, gb, cam, p, with_exchange, st);
+    } else {
+        FrameKey key;
+        memset(&key, 0, sizeof(key));
+        key.rsm = *rsm; key.light = *light; key.mesh = *mesh; key.gb = *gb; key.cam = *cam; key.p = *p;
+        key.with_exchange = with_exchange; key.push = ctx->xch.push; key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture;
+        key.tex_float_coord = ctx->tex_float_coord; key.planar_ext = ctx->planar_ext;
+        if (!ctx->graph_valid || memcmp(&key, ctx->graph_key.data(), sizeof(key)) != 0) {
+            if (p->cull_mode == MLGI_CULL_CLUSTERED && (rc = ensure_clustered(ctx))) return rc;   // cudaMalloc must not run inside a capture
+            const unsigned long long l0 = ctx->launches;
+            CK(cudaStreamBeginCapture(ctx->cap, cudaStreamCaptureModeThreadLocal));
+            rc = frame_body(ctx, rsm, light, mesh, gb, cam, p, with_exchange, ctx->cap);
+            cudaGraph_t g = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(ctx->cap, &g);
+            ctx->graph_launches = ctx->launches - l0;
+            ctx->launches = l0;
+            if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); ctx->graph_valid = false; return rc; }
+            if (ce != cudaSuccess) { ctx->graph_valid = false; return fail(ctx, MLGI_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce)); }
+            bool updated = false;
+            if (ctx->graph_exec) {
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(ctx->graph_exec, g, &info) == cudaSuccess) updated = true;
+                else { cudaGetLastError(); cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            }
+            if (!updated) {
+                const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+                if (ie != cudaSuccess) { cudaGraphDestroy(g); ctx->graph_exec = nullptr; ctx->graph_valid = false; return fail(ctx, MLGI_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+                ctx->graph_instantiations++;
+            }
+            cudaGraphDestroy(g);
+            ctx->graph_key.assign((const char*)&key, (const char*)&key + sizeof(key));
+            ctx->graph_valid = true;
+        }
+        CK(cudaGraphLaunch(ctx->graph_exec, st));
+        ctx->launches += ctx->graph_launches;
+        ctx->graph_replays++;
+    }
+    ctx->last_enqueue_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+MLGI_API int mlgi_frame(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
+                        const mlgi_camera* cam, const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
+    return frame_graphed(ctx, rsm, light, mesh, gb, cam, p, false, stream);
+}
+
+// the frame of one rank of a class-sharded job = mlgi_frame + the exchange, as one graph launch
+MLGI_API int mlgi_frame_sharded(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
+                                const mlgi_camera* cam, const mlgi_params* p, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
+    return frame_graphed(ctx, rsm, light, mesh, gb, cam, p, true, stream);
+}
+
+MLGI_API int mlgi_set_graph(mlgi_ctx* ctx, int enable) {
+    if (!ctx) return MLGI_E_INVALID;
+    ctx->use_graph = enable ? 1 : 0;
+    return MLGI_OK;
+}
+
+MLGI_API int mlgi_get_frame_stats(mlgi_ctx* ctx, mlgi_frame_stats* out) {
+    if (!ctx || !out) return MLGI_E_INVALID;
+    out->host_enqueue_us = ctx->last_enqueue_us;
+    out->graph_replays = ctx->graph_replays;
+    out->graph_instantiations = ctx->graph_instantiations;
+    out->graph_enabled = ctx->use_graph && !ctx->cfg.enable_timers;
+    return MLGI_OK;
 }
 
 static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
                            const mlgi_camera* cam, const mlgi_params* p, void* host_out, bool packed, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!hr || !hg || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer is NULL");
     if (packed && !ctx->gi_packed) return fail(ctx, MLGI_E_INVALID, "mlgi_frame_host_packed needs cfg.gi_packed");
     cudaStream_t st = (cudaStream_t)stream;
@@ -869,6 +1074,72 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
     return MLGI_OK;
 }
 
+// ------------------------------------------------------------------------------------- sharded host-input frame
+// One rank of a class-sharded job with HOST inputs (the N-GPU form of mlgi_frame_host_packed). The job's inputs
+// cross PCIe once in total: every rank uploads the (small) RSM and ITS 1/world slab of the camera G-buffer rows; the copy
+// engines push the slab into every peer's exchange allocation over NVLink (every rank needs the whole G-buffer: its pixels
+// are interleaved over the image) while the ISM build, which only needs the RSM, already runs; flags in peer memory order
+// the slabs; then culling, gathering, the plane exchange, and the rank reads ITS slab of the assembled image back.
+// host_gbuffer / host_gi_packed are full-size host arrays (pinned for full speed); rows [rank*H/world, (rank+1)*H/world)
+// are the ones touched. Synchronises the stream before returning.
+MLGI_API int mlgi_frame_sharded_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
+                                     const mlgi_camera* cam, const mlgi_params* p, uint32_t* host_gi_packed, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
+    auto& x = ctx->xch;
+    if (!x.connected) return fail(ctx, MLGI_E_ORDER, "mlgi_frame_sharded_host needs a connected exchange");
+    if (!hr || !hg || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer is NULL");
+    if (!ctx->gi_packed) return fail(ctx, MLGI_E_INVALID, "mlgi_frame_sharded_host needs cfg.gi_packed");
+    if (ctx->cfg.enable_timers) return fail(ctx, MLGI_E_INVALID, "per-stage timers are not available on the sharded host path");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int W = ctx->cfg.width, H = ctx->cfg.height;
+    const size_t RS = (size_t)ctx->cfg.rsm_width * ctx->cfg.rsm_height, WH = (size_t)W * H;
+    const size_t y0 = (size_t)x.rank * H / x.world, y1 = (size_t)(x.rank + 1) * H / x.world;
+    const size_t gb_plane = (WH * 4 + 255) & ~(size_t)255;
+    int rc;
+    CK(cudaMemcpyAsync(ctx->st_rsm_diffuse, hr->diffuse, RS * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->st_rsm_normal, hr->face_normal, RS * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->st_rsm_depth, hr->depth, RS * 4, cudaMemcpyHostToDevice, st));
+    // G-buffer traffic on the side stream. It must not overtake the previous frame's readers of the G-buffer region on
+    // the peers: a peer's frame f gathering has finished before it signals its planes, and this rank's frame f exchange
+    // kernel (stream-ordered before this call returns) waited for that signal -- so ordering the side stream after `st`
+    // is enough.
+    CK(cudaEventRecord(ctx->ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    float* own_depth = (float*)(x.base + x.gb_off);
+    uint32_t* own_normal = (uint32_t*)(x.base + x.gb_off + gb_plane);
+    CK(cudaMemcpyAsync(own_depth + y0 * W, hg->depth + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
+    CK(cudaMemcpyAsync(own_normal + y0 * W, hg->face_normal + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
+    for (int k = 1; k < x.world; k++) {             // staggered peer order: at any time every link carries one copy
+        const int g = (x.rank + k) % x.world;
+        float* pd = (float*)(x.peer_base[g] + x.gb_off);
+        uint32_t* pn = (uint32_t*)(x.peer_base[g] + x.gb_off + gb_plane);
+        CK(cudaMemcpyAsync(pd + y0 * W, own_depth + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToDevice, ctx->side));
+        CK(cudaMemcpyAsync(pn + y0 * W, own_normal + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToDevice, ctx->side));
+    }
+    ctx->launches += launch_flag_signal(x.d_peer_flags, x.world, 8 + x.rank, x.d_state, ctx->side);
+    ctx->launches += launch_flag_wait((const uint32_t*)x.base + 8, x.world, x.d_state, x.d_state + 2, ctx->side);
+    mlgi_rsm dr = {ctx->st_rsm_diffuse, ctx->st_rsm_normal, ctx->st_rsm_depth};
+    mlgi_gbuffer dg = {own_depth, own_normal};
+    if ((rc = mlgi_vpl_process(ctx, &dr, light, p, stream))) return rc;
+    // culling needs the VPL records and the complete G-buffer
+    CK(cudaEventRecord(ctx->ev_ism, st));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_ism, 0));
+    void* cs = (void*)ctx->side;
+    if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, &dg, cam, p, cs))) return rc; }
+    else if (p->cull_mode == MLGI_CULL_TILED) { if ((rc = mlgi_cull_tiled(ctx, &dg, cam, p, cs))) return rc; }
+    CK(cudaEventRecord(ctx->ev_join, ctx->side));
+    if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;
+    if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;
+    if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;
+    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if ((rc = mlgi_final_gather(ctx, &dg, cam, nullptr, p, stream))) return rc;
+    if ((rc = mlgi_exchange_finish(ctx, stream))) return rc;
+    if (host_gi_packed) CK(cudaMemcpyAsync(host_gi_packed + y0 * W, ctx->gi_packed + y0 * W, (y1 - y0) * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MLGI_OK;
+}
+
 MLGI_API int mlgi_frame_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
                              const mlgi_camera* cam, const mlgi_params* p, float* host_gi, void* stream) {
     return frame_host_impl(ctx, hr, light, mesh, hg, cam, p, host_gi, false, stream);
@@ -882,6 +1153,7 @@ MLGI_API int mlgi_frame_host_packed(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlg
 // ------------------------------------------------------------------------------------- inspection
 MLGI_API int mlgi_get_buffer(mlgi_ctx* ctx, int id, void** dev_ptr, size_t* bytes) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     if (!dev_ptr || !bytes) return fail(ctx, MLGI_E_INVALID, "dev_ptr/bytes is NULL");
     const size_t N = ctx->cfg.vpl_count, WH = (size_t)ctx->cfg.width * ctx->cfg.height, AA = (size_t)ctx->A * ctx->A;
     const size_t maxClusters = (size_t)ctx->X * ctx->Y * 16, L1 = ctx->L + 1;
@@ -907,7 +1179,9 @@ MLGI_API int mlgi_get_buffer(mlgi_ctx* ctx, int id, void** dev_ptr, size_t* byte
         case MLGI_BUF_ISM: *dev_ptr = ctx->ism; *bytes = AA * 2; break;
         case MLGI_BUF_COMPACT_CLUSTER_IDS: *dev_ptr = ctx->compact_ids; *bytes = maxClusters * 4; break;
         case MLGI_BUF_LIGHT_LIST_IDS: *dev_ptr = ctx->light_list_ids; *bytes = maxClusters * 2; break;
-        case MLGI_BUF_LIGHT_LISTS: *dev_ptr = ctx->light_lists; *bytes = maxClusters * 16 * L1 * 2; break;
+        case MLGI_BUF_LIGHT_LISTS:      // allocated on first use; a viewport that cannot use clustered culling has none
+            if (ensure_clustered(ctx) != MLGI_OK) { *dev_ptr = nullptr; *bytes = 0; break; }
+            *dev_ptr = ctx->light_lists; *bytes = maxClusters * 16 * L1 * 2; break;
         case MLGI_BUF_TILE_LISTS: *dev_ptr = ctx->tile_lists; *bytes = (size_t)ctx->TX * ctx->TY * 16 * L1 * 2; break;
         case MLGI_BUF_NUM_USED_CLUSTERS: *dev_ptr = ctx->counters + 2; *bytes = 4; break;
         case MLGI_BUF_GI: *dev_ptr = ctx->gi; *bytes = WH * 16; break;
@@ -923,11 +1197,12 @@ MLGI_API int mlgi_get_buffer(mlgi_ctx* ctx, int id, void** dev_ptr, size_t* byte
 
 MLGI_API int mlgi_read_buffer(mlgi_ctx* ctx, int id, void* host_dst, size_t bytes, size_t offset) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     void* p = nullptr;
     size_t n = 0;
     int rc = mlgi_get_buffer(ctx, id, &p, &n);
     if (rc) return rc;
-    if (!host_dst || offset + bytes > n) return fail(ctx, MLGI_E_INVALID, "read of %zu bytes at %zu exceeds buffer %d (%zu bytes)", bytes, offset, id, n);
+    if (!host_dst || bytes > n || offset > n - bytes) return fail(ctx, MLGI_E_INVALID, "read of %zu bytes at %zu exceeds buffer %d (%zu bytes)", bytes, offset, id, n);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(host_dst, (const char*)p + offset, bytes, cudaMemcpyDeviceToHost));
     return MLGI_OK;
@@ -935,17 +1210,19 @@ MLGI_API int mlgi_read_buffer(mlgi_ctx* ctx, int id, void* host_dst, size_t byte
 
 MLGI_API int mlgi_read_buffer_async(mlgi_ctx* ctx, int id, void* host_dst, size_t bytes, size_t offset, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     void* p = nullptr;
     size_t n = 0;
     int rc = mlgi_get_buffer(ctx, id, &p, &n);
     if (rc) return rc;
-    if (!host_dst || offset + bytes > n) return fail(ctx, MLGI_E_INVALID, "read of %zu bytes at %zu exceeds buffer %d (%zu bytes)", bytes, offset, id, n);
+    if (!host_dst || bytes > n || offset > n - bytes) return fail(ctx, MLGI_E_INVALID, "read of %zu bytes at %zu exceeds buffer %d (%zu bytes)", bytes, offset, id, n);
     CK(cudaMemcpyAsync(host_dst, (const char*)p + offset, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return MLGI_OK;
 }
 
 MLGI_API int mlgi_get_counts(mlgi_ctx* ctx, int* num_points, int* num_used_clusters) {
     if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
     uint32_t h[4];
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h, ctx->counters, sizeof(h), cudaMemcpyDeviceToHost));
@@ -958,6 +1235,7 @@ MLGI_API int mlgi_get_counts(mlgi_ctx* ctx, int* num_points, int* num_used_clust
 MLGI_API int mlgi_get_timings(mlgi_ctx* ctx, mlgi_timing* out, int cap) {
     if (!ctx || !out) return 0;
     if (!ctx->cfg.enable_timers) return 0;
+    DeviceGuard dg_(ctx);
     cudaDeviceSynchronize();
     int n = 0;
     for (int i = 0; i < T_COUNT && n < cap; i++) {

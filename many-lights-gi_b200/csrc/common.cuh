@@ -196,10 +196,14 @@ struct GatherArgs {
     int planar_class0;
     uint32_t* out_packed;          // may be null: R11F_G11F_B10F raster
     uint32_t* out_planar_packed;   // may be null: R11F_G11F_B10F class planes
-    // fused exchange: the class planes are stored straight into every rank's exchange buffer (peer-mapped over NVLink)
+    // multi-GPU exchange: the class planes are stored into exchange buffers -- this rank's own one (pull mode, num_peers = 1)
+    // or every rank's, peer-mapped over NVLink (push mode). The buffers are double-buffered by frame parity; the frame
+    // counter lives in device memory so that a captured CUDA graph of the frame is valid for every frame.
     int num_peers;                 // 0 = off
     int peer_packed;
-    void* peer_planar[8];          // element = uint32 (gi_packed) or float4
+    void* peer_planar[8];          // parity buffer 0; element = uint32 (gi_packed) or float4
+    size_t peer_parity_stride;     // bytes from parity buffer 0 to parity buffer 1
+    const uint32_t* frame_ctr;     // frames completed so far; the frame being produced writes buffer (ctr + 1) & 1
     unsigned long long* stats;  // null, or 2 counters (pairs listed / lit)
 };
 int launch_final_gather(const GatherArgs& a, cudaStream_t st);
@@ -207,10 +211,25 @@ int launch_composite_ambient(const float4* gi, const uint32_t* diffuse_rgba8, co
                              uint32_t* out_srgb8, cudaStream_t st);
 int launch_gi_blur(const float4* gi, const float* depth, const uint32_t* face_normal, int W, int H, float projA,
                    float projB, float4* tmp, float4* out, cudaStream_t st);
-float measure_fp32_peak_tflops(cudaStream_t st);   // FFMA micro-benchmark: the FP32-pipe roofline denominator
+float measure_fp32_peak_tflops(int device, cudaStream_t st);   // FFMA micro-benchmark: the FP32-pipe roofline denominator
 int launch_planar_to_raster(const float4* planar, int W, int H, int class_lo, int class_hi, float4* raster, cudaStream_t st);
-int launch_exchange_signal(uint32_t* const* peer_flags, int world, int rank, uint32_t frame_id, cudaStream_t st);
-int launch_exchange_wait(const uint32_t* flags, int world, uint32_t frame_id, uint32_t* error_flag, cudaStream_t st);
+// one kernel = signal + wait + (pull over NVLink) + de-interleave; see gather.cu
+struct ExchangeArgs {
+    int W, H, world, rank, packed;
+    const char* src[8];            // parity buffer 0 of the rank that owns a class: peer-mapped (pull) or this rank's own (push mode)
+    size_t parity_stride;
+    uint32_t* peer_flags[8];       // flag array of every rank (peer-mapped): slot [rank] <- frame id
+    const uint32_t* flags;         // this rank's flag array
+    uint32_t* frame_ctr;           // device frame counter (incremented by the last CTA)
+    uint32_t* ticket;              // CTA completion counter
+    uint32_t* error;               // set when a wait times out (a peer died)
+    uint32_t* raster_packed;       // may be null
+    float4* raster;                // may be null
+};
+int launch_exchange(const ExchangeArgs& x, cudaStream_t st);
+// host-input sharded frame: G-buffer slabs are pushed to the peers by the copy engines; these two order them
+int launch_flag_signal(uint32_t* const* peer_flags, int world, int slot, const uint32_t* frame_ctr, cudaStream_t st);
+int launch_flag_wait(const uint32_t* flags, int world, const uint32_t* frame_ctr, uint32_t* error, cudaStream_t st);
 int launch_planar_packed_to_raster(const uint32_t* planar, int W, int H, uint32_t* raster_packed, float4* raster, cudaStream_t st);
 
 constexpr int kTile = 64;  // tiled-culling tile edge in pixels (one gathering CTA = one class of one tile)

@@ -9,6 +9,7 @@
 //   a7  light_lists_kernel      (light_lists.comp:50-126) ballot + popc compaction, ascending ids
 //   a8  cull_tiled_kernel       (tiled variant)
 #include "common.cuh"
+#include "pullpush_core.cuh"
 
 namespace mlgi {
 
@@ -386,300 +387,77 @@ int launch_splat(const float4* points, const uint32_t* point_bucket, const uint3
 // (16 KB level 0 + 21.3 KB RGBA32F levels 1..6); HBM traffic = 4 B read + 2 B written per
 // atlas texel instead of the reference's 12 full-atlas passes. Per-ISM independence: pull
 // 2x2 blocks never straddle a 64-px tile; push masks every coarse tap of another ISM
-// (push.comp:77-86), so out-of-tile taps are zero-filled (what an out-of-bounds imageLoad
-// returns) and carry weight 0. Coordinates in the arithmetic are GLOBAL atlas coordinates
-// because fp32 rounding of (coord + 0.5 + displacement) depends on their magnitude.
+// (push.comp:77-86). The arithmetic lives in pullpush_core.cuh as per-thread phases (also
+// compiled for the host by tests/hostemu, which checks it against the oracle without a GPU);
+// this kernel is the tile load, the phases with CTA barriers in between, and the tile store.
+// 44.9 KB of shared memory and <= 48 registers: 5 CTAs (40 warps) per SM.
 // =====================================================================================
-static constexpr int PP_THREADS = 256;
 #ifndef PP_MINB
-#define PP_MINB 4
+#define PP_MINB 5
 #endif
 
-struct PullSample { float depth, maxDepth, radius; float2 disp; };
-
-// Exact square-root elimination. For a correctly rounded sqrtf and rs >= 0:  sqrtf(x) > rs  <=>  sqrt(x) > m, where
-// m = (rs + nextafter(rs)) / 2 is the rounding boundary above rs  <=>  x > m*m. m has 25 significant bits, so m*m is
-// exact in fp64 and is never itself a float; hence  sqrtf(x) > rs  <=>  x > T  with T = round_down_to_float(m*m).
-// One threshold per coarse tap replaces one square root per (pixel, tap). rs = inf / NaN give T = NaN (never greater,
-// like the original comparison); a negative rs (cannot occur: radii are means of non-negative values) keeps
-// "always greater" through T = -1.
-__device__ __forceinline__ float sqrt_gt_threshold(float rs) {
-    const float next = __uint_as_float(__float_as_uint(rs) + 1u);
-    const double m = ((double)rs + (double)next) * 0.5;
-    const float T = __double2float_rd(m * m);
-    return rs < 0.0f ? -1.0f : T;
-}
-
-// pull.comp:67-123 given the four decoded inputs (absolute input coords ix0.., output coord ox,oy)
-__device__ __forceinline__ float4 pull_combine(const PullSample* smp, int ix0, int iy0, int ox, int oy, int level) {
-    const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};   // pull.comp:24
-    float depthSamples[4], maxDepths[4], radiuses[4];
-    float2 dv[4];
-    bool valid[4];
-    const float scale = __int_as_float((127 - level) << 23);     // 2^-level, exact
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float ndx = (float(ix0 + offx[i]) + 0.5f + smp[i].disp.x) / 2.0f - (float(ox) + 0.5f);   // :69
-        float ndy = (float(iy0 + offy[i]) + 0.5f + smp[i].disp.y) / 2.0f - (float(oy) + 0.5f);
-        const float scaledRadius = smp[i].radius * scale;         // :72
-        const bool radiusCheckPassed = sqrtf(ndx * ndx + ndy * ndy) <= scaledRadius;   // :70,74
-        depthSamples[i] = smp[i].depth; maxDepths[i] = smp[i].maxDepth; radiuses[i] = smp[i].radius;
-        dv[i] = make_float2(ndx, ndy);
-        valid[i] = (smp[i].depth != 1.0f) && radiusCheckPassed;   // :80-81
-    }
-    float minimum = __int_as_float(0x7f800000);                   // :84
-    float maxDepth = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        if (!valid[i]) continue;
-        minimum = fminf(depthSamples[i], minimum);                // depths are finite and >= +0: FMNMX == the ternary min
-        if (minimum == depthSamples[i]) maxDepth = maxDepths[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-        if (depthSamples[i] > maxDepth) valid[i] = false;         // :94-97
-    float depthAcc = 0.0f, radiusAcc = 0.0f, maxValidMaxDepth = 0.0f, dax = 0.0f, day = 0.0f;
-    uint32_t numValid = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {                                 // :104-113
-        if (!valid[i]) continue;
-        depthAcc += depthSamples[i];
-        dax += dv[i].x; day += dv[i].y;
-        radiusAcc += radiuses[i];
-        maxValidMaxDepth = fmaxf(maxValidMaxDepth, maxDepths[i]);
-        numValid++;
-    }
-    if (numValid > 0) {                                           // :116-123
-        float nv = float(numValid);
-        return make_float4(depthAcc / nv, maxValidMaxDepth, radiusAcc / nv, __uint_as_float(pack_half2(dax / nv, day / nv)));
-    }
-    return make_float4(1.0f, 0.0f, 0.0f, 0.0f);
-}
-
-// push.comp:44-165 for one thread T (absolute), tile-local bookkeeping by the caller. Everything that does not
-// depend on the output pixel is hoisted into PushCoarse once per T (same values, same roundings).
-struct PushCoarse {
-    float depth[4], maxDepth[4], radius[4];
-    float rs2[4];           // threshold T(radius * 2^-level): sqrt(x) > rs  <=>  x > T           (push.comp:104-108)
-    float w0[4];            // 1 if the tap may contribute at all (same ISM, depth != 1.0), else 0   (:77-93)
-    float cx[4], cy[4];     // (coarse tap coordinate + 0.5) * 2                   (:98)
-    float d2x[4], d2y[4];   // coarse displacement * 2                             (:101)
-};
-
-// LEVEL0: only the depth of the result is consumed (R16 store, push.comp:29-41), so the other weighted means,
-// their divisions and the half packing are not evaluated; at every level the means are evaluated only when the
-// texel is actually replaced (:159-161). Skipped work never feeds a stored value, so results stay bit-exact.
-template <bool LEVEL0>
-__device__ __forceinline__ float4 push_pixel(const PushCoarse& c, int outputPixel, int px, int py, float4 origSample) {
-    // weights are the small integers {9,3,1,3} rotated by the output pixel (:70-74); kept as floats (exact)
-    const float weightsX[4] = {9.0f, 3.0f, 1.0f, 3.0f};
-    float weights[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) weights[i] = weightsX[(i - outputPixel + 4) & 3] * c.w0[i];   // :77-93
-    const float ttx = float(px) + 0.5f, tty = float(py) + 0.5f;
-    float2 dv[4];
-#pragma unroll
-#pragma unroll
-    for (int i = 0; i < 4; i++) {                                             // :96-110
-        dv[i] = make_float2((c.cx[i] - ttx) + c.d2x[i], (c.cy[i] - tty) + c.d2y[i]);
-        if (dv[i].x * dv[i].x + dv[i].y * dv[i].y > c.rs2[i]) weights[i] = 0.0f;   // == (sqrt(..) > rs), see sqrt_gt_threshold
-    }
-    float minimum = 9001.0f;                                                  // :113
-    float maxDepth = 0.0f;
-    bool any = false;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        if (weights[i] == 0.0f) continue;
-        any = true;
-        minimum = fminf(c.depth[i], minimum);                     // finite, >= +0: FMNMX == the ternary min
-        if (minimum == c.depth[i]) maxDepth = c.maxDepth[i];
-    }
-    if (any) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) if (c.depth[i] > maxDepth) weights[i] = 0.0f;   // :123-126
-    }
-    const float wa = (weights[0] + weights[1]) + (weights[2] + weights[3]);   // integer-valued, <= 16: exact
-    const bool allSamplesInvalid = wa <= 0.0f;                                // :158
-    const bool invalid = origSample.x == 1.0f;                                // :151
-    bool occluded = false;
-#pragma unroll
-    for (int i = 0; i < 4; i++) occluded = occluded || (weights[i] > 0.0f && origSample.x > c.maxDepth[i]);   // :153-156
-    if (allSamplesInvalid || (!invalid && !occluded)) return origSample;      // :159-161
-    float depthAcc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; i++) depthAcc += c.depth[i] * weights[i];          // :135-141
-    if (LEVEL0) return make_float4(depthAcc / wa, 0.0f, 0.0f, 0.0f);          // :144
-    float radiusAcc = 0.0f, maxDepthAcc = 0.0f, dax = 0.0f, day = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const float w = weights[i];
-        maxDepthAcc += c.maxDepth[i] * w;
-        radiusAcc += c.radius[i] * w;
-        dax += dv[i].x * w; day += dv[i].y * w;
-    }
-    return make_float4(depthAcc / wa, maxDepthAcc / wa, radiusAcc / wa, __uint_as_float(pack_half2(dax / wa, day / wa)));   // :144-147
-}
-
-// one push pass (level i) over a 64x64 ISM tile held in shared memory
-template <bool LEVEL0>
-__device__ __forceinline__ void push_level(int level, uint32_t* __restrict__ L0, float4* __restrict__ PY, int coarse_off, int same_off,
-                                           int gx0, int gy0, int tid) {
-    const int size = 64 >> level, csz = size >> 1;        // this level / coarser level, tile-local
-    const int nT = csz + 1;
-    const float4* coarse = PY + coarse_off;
-    float4* same = PY + same_off;
-    const int gxl = gx0 >> level, gyl = gy0 >> level;     // tile origin at this level
-    const float scale = __int_as_float((127 - level) << 23);
-    for (int it = tid; it < nT * nT; it += PP_THREADS) {
-        const int tlx = it % nT, tly = it / nT;           // local T
-        const int Tx = (gxl >> 1) + tlx, Ty = (gyl >> 1) + tly;   // absolute T (push.comp:46: coarserLowerLeft = T - 1)
-        PushCoarse c;
-        const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 1, 0};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {                     // :55-62
-            const int cx = tlx - 1 + offx[i], cy = tly - 1 + offy[i];
-            const bool in = cx >= 0 && cy >= 0 && cx < csz && cy < csz;
-            const float4 cs = in ? coarse[cy * csz + cx] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            c.depth[i] = cs.x; c.maxDepth[i] = cs.y; c.radius[i] = cs.z;
-            const float2 disp = unpack_half2(__float_as_uint(cs.w));
-            c.rs2[i] = sqrt_gt_threshold(cs.z * scale);
-            c.w0[i] = (in && cs.x != 1.0f) ? 1.0f : 0.0f;
-            c.cx[i] = (float(Tx - 1 + offx[i]) + 0.5f) * 2.0f; c.cy[i] = (float(Ty - 1 + offy[i]) + 0.5f) * 2.0f;
-            c.d2x[i] = disp.x * 2.0f; c.d2y[i] = disp.y * 2.0f;
-        }
-#pragma unroll
-        for (int op = 0; op < 4; op++) {
-            const int plx = tlx * 2 - 1 + offx[op], ply = tly * 2 - 1 + offy[op];   // tile-local pixel (:67)
-            if (plx < 0 || ply < 0 || plx >= size || ply >= size) continue;         // belongs to a neighbouring ISM's CTA
-            const int px = gxl + plx, py = gyl + ply;
-            if (LEVEL0) {
-                const float4 orig = make_float4(float(L0[ply * 64 + plx] >> 8) / 16777216.0f, 0.0f, 0.0f, 0.0f);   // :19-27
-                const float4 res = push_pixel<true>(c, op, px, py, orig);
-                L0[ply * 64 + plx] = __float2uint_rn(gclamp(res.x, 0.0f, 1.0f) * 65535.0f);                         // :29-41 R16 unorm
-            } else {
-                const float4 orig = same[ply * size + plx];
-                same[ply * size + plx] = push_pixel<false>(c, op, px, py, orig);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(PP_THREADS, PP_MINB) pullpush_kernel(const uint32_t* __restrict__ atlas, int S, float zFar, uint16_t* __restrict__ ism, int tile_y0) {
-    __shared__ __align__(16) uint32_t L0[64 * 64];
-    __shared__ __align__(16) float4 PY[1024 + 256 + 64 + 16 + 4 + 1];
-    __shared__ float lut_r[256], lut_md[256];
-    __shared__ float4 s_empty;          // pull level 1 of an all-empty 2x2 block
-    __shared__ int s_count;
-    __shared__ uint16_t s_list[1024];   // level-1 outputs whose block holds at least one point
-    // float4 offset of pyramid level l (1..6) inside PY: sum_{k<l} 4^(6-k)
-    auto lvl_off = [](int l) { return (4096 - (4096 >> (2 * (l - 1)))) / 3; };
+__global__ void __launch_bounds__(pp::kThreads, PP_MINB) pullpush_kernel(const uint32_t* __restrict__ atlas, int S, float zFar,
+                                                                         uint16_t* __restrict__ ism, int tile_y0) {
+    __shared__ __align__(16) pp::Shared s;
     const int A = 64 * S;
-    const int tile_x = blockIdx.x, tile_y = blockIdx.y + tile_y0;
-    const int gx0 = tile_x * 64, gy0 = tile_y * 64;
+    const int gx0 = blockIdx.x * 64, gy0 = (blockIdx.y + tile_y0) * 64;
     const int tid = threadIdx.x;
+    const float ismPixelSize = 64.0f;          // A / S  (ImperfectShadowmap.cpp:187-191)
 
-    {
-        const float r = float(tid) / 10.0f;                // PP_THREADS == 256 entries
-        lut_r[tid] = r;
-        lut_md[tid] = (r * 2.0f) / zFar * 0.6f;
-    }
     // ---- load the 64x64 R32UI tile: 1024 x uint4, coalesced 256 B rows ----
+    uint4 v[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        int q = tid + k * PP_THREADS;          // uint4 index 0..1023
-        int row = q >> 4, c4 = q & 15;
-        uint4 v = *reinterpret_cast<const uint4*>(atlas + (size_t)(gy0 + row) * A + gx0 + c4 * 4);
-        *reinterpret_cast<uint4*>(&L0[row * 64 + c4 * 4]) = v;
+        const int q = tid + k * pp::kThreads;  // uint4 index 0..1023
+        v[k] = __ldg(reinterpret_cast<const uint4*>(atlas + (size_t)(gy0 + (q >> 4)) * A + gx0 + (q & 15) * 4));
     }
-    __syncthreads();
-
-    // ---- pull level 1 (LEVEL_ZERO variant, pull.comp:37-41,55-65) ----
-    // the 8-bit radius only takes 256 values: its two division chains are tabulated per CTA (same IEEE ops).
-    // Most 2x2 input blocks are entirely empty texels (0xFFFFFFFF: the atlas is sparse). Their result does not depend on
-    // the position -- every term of pull.comp:69 is exact, so the four displacement vectors are (+-0.25, +-0.25) everywhere --
-    // and is evaluated once per CTA by the general code (s_empty); the other blocks are collected and processed densely.
-    const float ismPixelSize = 64.0f;          // A / S  (ImperfectShadowmap.cpp:187-191)
-    auto decode_l0 = [&](uint32_t u, PullSample& smp) {
-        float depthSample = float(u >> 8) / 16777216.0f;
-        float radius = lut_r[u & 0xFFu];                                   // float(u & 0xFF) / 10      :39
-        float maxDepth = depthSample + lut_md[u & 0xFFu];                  // + (radius*2)/zFar*0.6     :57
-        float distToCamera = depthSample * zFar;                           // :60
-        radius = radius / distToCamera / 3.14f * ismPixelSize;             // :61
-        radius *= 1.3f;                                                    // :63
-        radius = gmin(radius, 15.0f);                                      // :65
-        smp.depth = depthSample; smp.maxDepth = maxDepth; smp.radius = radius; smp.disp = make_float2(0.0f, 0.0f);
-    };
-    if (tid == 0) {
-        PullSample smp[4];
-        for (int i = 0; i < 4; i++) decode_l0(0xFFFFFFFFu, smp[i]);
-        const int ox = gx0 >> 1, oy = gy0 >> 1;
-        s_empty = pull_combine(smp, ox * 2, oy * 2, ox, oy, 1);
-        s_count = 0;
-    }
-    __syncthreads();
-    for (int o = tid; o < 1024; o += PP_THREADS) {
-        const int lx = o & 31, ly = o >> 5;
-        const uint2 top = *reinterpret_cast<const uint2*>(&L0[(ly * 2) * 64 + lx * 2]);
-        const uint2 bot = *reinterpret_cast<const uint2*>(&L0[(ly * 2 + 1) * 64 + lx * 2]);
-        if ((top.x & top.y & bot.x & bot.y) == 0xFFFFFFFFu) PY[lvl_off(1) + o] = s_empty;
-        else s_list[atomicAdd(&s_count, 1)] = (uint16_t)o;
-    }
-    __syncthreads();
-    for (int q = tid; q < s_count; q += PP_THREADS) {
-        const int o = s_list[q];
-        const int lx = o & 31, ly = o >> 5;
-        PullSample smp[4];
-        const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};
+    pp::phase_luts(s, tid, zFar);
 #pragma unroll
-        for (int i = 0; i < 4; i++) decode_l0(L0[(ly * 2 + offy[i]) * 64 + lx * 2 + offx[i]], smp[i]);
-        int ox = (gx0 >> 1) + lx, oy = (gy0 >> 1) + ly;
-        PY[lvl_off(1) + o] = pull_combine(smp, ox * 2, oy * 2, ox, oy, 1);
+    for (int k = 0; k < 4; k++) {
+        const int q = tid + k * pp::kThreads;
+        *reinterpret_cast<uint4*>(&s.L0[(q >> 4) * 64 + (q & 15) * 4]) = v[k];
     }
     __syncthreads();
-    // ---- pull levels 2..6 ----
+    pp::phase_empty1(s, tid, zFar, ismPixelSize, gx0, gy0);
+    __syncthreads();
+    pp::phase_pull1_classify(s, tid);
+    __syncthreads();
+    pp::phase_pull1_dense(s, tid, zFar, ismPixelSize, gx0, gy0);
+    __syncthreads();
 #pragma unroll 1
     for (int level = 2; level <= 6; level++) {
-        const int osz = 64 >> level, isz = osz * 2;
-        const float4* in = PY + lvl_off(level - 1);
-        for (int o = tid; o < osz * osz; o += PP_THREADS) {
-            int lx = o % osz, ly = o / osz;
-            PullSample smp[4];
-            const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                float4 rd = in[(ly * 2 + offy[i]) * isz + lx * 2 + offx[i]];   // :43-47
-                smp[i].depth = rd.x; smp[i].maxDepth = rd.y; smp[i].radius = rd.z;
-                smp[i].disp = unpack_half2(__float_as_uint(rd.w));
-            }
-            int ox = (gx0 >> level) + lx, oy = (gy0 >> level) + ly;
-            PY[lvl_off(level) + o] = pull_combine(smp, ox * 2, oy * 2, ox, oy, level);
-        }
+        pp::phase_pull(s, tid, level, gx0, gy0);
         __syncthreads();
     }
-    // ---- push levels 5..0 (in place: push[i] overwrites pull[i]; only the owning thread reads orig) ----
+    // push levels 5..0, in place: push[i] overwrites pull[i]; only the owning thread reads the texel it replaces
 #pragma unroll 1
     for (int level = 5; level >= 1; level--) {
-        push_level<false>(level, L0, PY, lvl_off(level + 1), lvl_off(level), gx0, gy0, tid);
+        pp::phase_push_thresholds(s, tid, level);
+        __syncthreads();
+        pp::phase_push<false>(s, tid, level);
         __syncthreads();
     }
-    push_level<true>(0, L0, PY, lvl_off(1), 0, gx0, gy0, tid);
+    pp::phase_push_thresholds(s, tid, 0);
+    __syncthreads();
+    pp::phase_push<true>(s, tid, 0);
     __syncthreads();
     // ---- store the R16 tile: 64 rows x 128 B, coalesced uint4 ----
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        int q = tid + k * PP_THREADS;          // 0..511, 8 texels each
-        int row = q >> 3, c8 = q & 7;
-        const uint32_t* src = &L0[row * 64 + c8 * 8];
-        uint4 v;
-        v.x = src[0] | (src[1] << 16); v.y = src[2] | (src[3] << 16); v.z = src[4] | (src[5] << 16); v.w = src[6] | (src[7] << 16);
-        *reinterpret_cast<uint4*>(ism + (size_t)(gy0 + row) * A + gx0 + c8 * 8) = v;
+        const int q = tid + k * pp::kThreads;  // 0..511, 8 texels each
+        const int row = q >> 3, c8 = q & 7;
+        const uint4 a = *reinterpret_cast<const uint4*>(&s.L0[row * 64 + c8 * 8]);
+        const uint4 b = *reinterpret_cast<const uint4*>(&s.L0[row * 64 + c8 * 8 + 4]);
+        uint4 o;
+        o.x = a.x | (a.y << 16); o.y = a.z | (a.w << 16); o.z = b.x | (b.y << 16); o.w = b.z | (b.w << 16);
+        *reinterpret_cast<uint4*>(ism + (size_t)(gy0 + row) * A + gx0 + c8 * 8) = o;
     }
 }
 
 // test hook: the push phase's square-root elimination, evaluated on the device for caller-chosen radii
 __global__ void sqrt_threshold_kernel(const float* __restrict__ rs, int n, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = sqrt_gt_threshold(rs[i]);
+    if (i < n) out[i] = pp::sqrt_gt_threshold(rs[i]);
 }
 int launch_sqrt_thresholds(const float* rs, int n, float* out, cudaStream_t st) {
     sqrt_threshold_kernel<<<(n + 255) / 256, 256, 0, st>>>(rs, n, out);
@@ -689,7 +467,7 @@ int launch_sqrt_thresholds(const float* rs, int n, float* out, cudaStream_t st) 
 int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st) {
     const int ty0 = vpl_lo / S, ty1 = (vpl_hi + S - 1) / S;
     dim3 grid(S, ty1 - ty0);
-    pullpush_kernel<<<grid, PP_THREADS, 0, st>>>(atlas, S, zFar, ism, ty0);
+    pullpush_kernel<<<grid, pp::kThreads, 0, st>>>(atlas, S, zFar, ism, ty0);
     return 1;
 }
 

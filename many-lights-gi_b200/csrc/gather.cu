@@ -13,6 +13,8 @@
 //   * clustered mode walks the (<= 16) depth slices present in the tile and masks pixels.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace mlgi {
 
 // tuning constants (A/B measured at 4K/4096 on B200): 10 resident CTAs per SM (48 registers, no spills) 1.571 vs 1.593 ms at 9;
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
 
     // ---- epilogue: result = acc * giIntensityFactor / vplCount * 16  (:132) ----
     const int PW = (a.W + 3) >> 2, PH = (a.H + 3) >> 2;
+    const size_t pboff = a.frame_ctr ? (size_t)((*a.frame_ctr + 1u) & 1u) * a.peer_parity_stride : 0;
 #pragma unroll
     for (int k = 0; k < NPX; k++) {
         if (!valid[k]) continue;
@@ -294,16 +297,16 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
         if (a.out_packed) a.out_packed[(size_t)sy[k] * a.W + sx[k]] = pack_r11g11b10(o.x, o.y, o.z);
         if (a.out_planar_packed) a.out_planar_packed[((size_t)cls * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = pack_r11g11b10(o.x, o.y, o.z);
         if (a.num_peers) {
-            // fused exchange: this pixel's plane entry goes to every rank's buffer directly, so the
-            // NVLink transfer overlaps the gathering of the remaining tiles and no separate collective is launched
+            // multi-GPU exchange: this pixel's plane entry goes to the exchange buffer(s) directly -- in
+            // push mode to every rank's buffer, so the NVLink transfer overlaps the gathering of the remaining tiles
             const size_t off = ((size_t)cls * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2);
             if (a.peer_packed) {
                 const uint32_t v = pack_r11g11b10(o.x, o.y, o.z);
 #pragma unroll 1
-                for (int g = 0; g < a.num_peers; g++) static_cast<uint32_t*>(a.peer_planar[g])[off] = v;
+                for (int g = 0; g < a.num_peers; g++) reinterpret_cast<uint32_t*>(static_cast<char*>(a.peer_planar[g]) + pboff)[off] = v;
             } else {
 #pragma unroll 1
-                for (int g = 0; g < a.num_peers; g++) static_cast<float4*>(a.peer_planar[g])[off] = o;
+                for (int g = 0; g < a.num_peers; g++) reinterpret_cast<float4*>(static_cast<char*>(a.peer_planar[g]) + pboff)[off] = o;
             }
         }
     }
@@ -351,35 +354,133 @@ __global__ void planar_to_raster_kernel(const float4* __restrict__ planar, int W
     const int PW = (W + 3) >> 2, PH = (H + 3) >> 2;
     raster[(size_t)y * W + x] = planar[((size_t)(cls - class_lo) * PH + (y >> 2)) * PW + (x >> 2)];
 }
-// ---- fused exchange: completion flags in peer memory -------------------------------------------------------------
-// After its gathering kernel (whose peer stores are complete at the kernel boundary) a rank writes the frame id into
-// slot [rank] of every peer's flag array; a rank may read its exchange buffer once all `world` slots show the frame id.
-__global__ void exchange_signal_kernel(uint32_t* const* peer_flags, int world, int rank, uint32_t frame_id) {
-    const int g = threadIdx.x;
-    if (g < world) {
-        __threadfence_system();
-        *reinterpret_cast<volatile uint32_t*>(peer_flags[g] + rank) = frame_id;
-        __threadfence_system();
-    }
+// ---- multi-GPU exchange: ONE kernel = signal + wait + pull + de-interleave ----------------------------------------------
+// Runs after the gathering kernel on the same stream, so this rank's class planes are complete (in its own exchange buffer
+// in pull mode; in every rank's buffer in push mode). CTA 0 publishes the frame id into slot [rank] of every rank's flag
+// array (system-scope fence first); every CTA then waits until all `world` slots of the local array show the frame id
+// (bounded spin: a dead peer raises an error instead of hanging the GPU) and de-interleaves its share of the image,
+// reading the planes of class c from the rank that owns c -- over NVLink with 16-byte volatile loads (never cached
+// locally: the parity buffer is rewritten two frames later) in pull mode. Each thread transposes 4 planes x 4 entries
+// into 16 consecutive raster pixels, so both the (remote) reads and the writes are full 512 B / 2 KB warp transactions.
+// The last CTA to finish advances the device-resident frame counter, which makes the kernel graph-replayable.
+__device__ __forceinline__ uint4 ld_volatile_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
-__global__ void exchange_wait_kernel(const uint32_t* flags, int world, uint32_t frame_id, uint32_t* error_flag) {
-    const int g = threadIdx.x;
-    if (g < world) {
-        const volatile uint32_t* f = flags + g;
+__device__ __forceinline__ float4 unpack_gi(uint32_t v) {
+    return make_float4(__uint_as_float(unpack_ufloat_bits<6>(v & 0x7FFu)), __uint_as_float(unpack_ufloat_bits<6>((v >> 11) & 0x7FFu)),
+                       __uint_as_float(unpack_ufloat_bits<5>(v >> 22)), 0.0f);
+}
+__device__ __forceinline__ bool wait_flags(const uint32_t* flags, int world, uint32_t frame, uint32_t* error) {
+    // the first `world` threads of the CTA poll one slot each
+    if (threadIdx.x < (unsigned)world) {
+        const volatile uint32_t* f = flags + threadIdx.x;
         long long spins = 0;
-        while ((int)(*f - frame_id) < 0) {                  // wrap-safe "not yet"
-            __nanosleep(200);
-            if (++spins > 20000000LL) { atomicExch(error_flag, 1u + (uint32_t)g); break; }   // ~4 s: a peer died; do not hang the GPU
+        while ((int)(*f - frame) < 0) {                     // wrap-safe "not yet"
+            __nanosleep(100);
+            if (++spins > 20000000LL) { atomicExch(error, 1u + threadIdx.x); break; }   // seconds: a peer died; do not hang the GPU
         }
         __threadfence_system();
     }
+    __syncthreads();
+    return true;
 }
-int launch_exchange_signal(uint32_t* const* peer_flags, int world, int rank, uint32_t frame_id, cudaStream_t st) {
-    exchange_signal_kernel<<<1, 32, 0, st>>>(peer_flags, world, rank, frame_id);
+
+__global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs x) {
+    const uint32_t frame = *reinterpret_cast<volatile uint32_t*>(x.frame_ctr) + 1u;
+    if (blockIdx.x == 0 && threadIdx.x < (unsigned)x.world) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(x.peer_flags[threadIdx.x] + x.rank) = frame;
+        __threadfence_system();
+    }
+    wait_flags(x.flags, x.world, frame, x.error);
+    const int PW = (x.W + 3) >> 2, PH = (x.H + 3) >> 2;
+    const size_t par = (size_t)(frame & 1u) * x.parity_stride;
+    const int per = 16 / x.world;                               // classes per rank
+    if (x.packed && (PW & 3) == 0 && (x.W & 15) == 0) {
+        // unit = (raster row y, 16-pixel group i4): planes 4*cy .. 4*cy+3, entries [py][4*i4 .. 4*i4+3]
+        const int groups = PW >> 2;
+        const long long units = (long long)x.H * groups;
+        for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
+            const int y = (int)(u / groups), i4 = (int)(u - (long long)y * groups);
+            const int cy = y & 3, py = y >> 2;
+            uint4 pl[4];
+#pragma unroll
+            for (int cx = 0; cx < 4; cx++) {
+                const int cls = 4 * cy + cx;
+                const char* base = x.src[cls / per] + par;
+                pl[cx] = ld_volatile_u4(reinterpret_cast<const uint32_t*>(base) + ((size_t)cls * PH + py) * PW + 4 * i4);
+            }
+            const uint4 o0 = make_uint4(pl[0].x, pl[1].x, pl[2].x, pl[3].x), o1 = make_uint4(pl[0].y, pl[1].y, pl[2].y, pl[3].y);
+            const uint4 o2 = make_uint4(pl[0].z, pl[1].z, pl[2].z, pl[3].z), o3 = make_uint4(pl[0].w, pl[1].w, pl[2].w, pl[3].w);
+            const size_t r = (size_t)y * x.W + 16 * (size_t)i4;
+            if (x.raster_packed) {
+                uint4* dst = reinterpret_cast<uint4*>(x.raster_packed + r);
+                dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
+            }
+            if (x.raster) {
+                const uint32_t v[16] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w, o3.x, o3.y, o3.z, o3.w};
+#pragma unroll
+                for (int i = 0; i < 16; i++) x.raster[r + i] = unpack_gi(v[i]);
+            }
+        }
+    } else {
+        // general shapes / fp32 planes: one pixel per thread
+        const long long n = (long long)x.W * x.H;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const int y = (int)(i / x.W), xx = (int)(i - (long long)y * x.W);
+            const int cls = (xx & 3) + 4 * (y & 3);
+            const char* base = x.src[cls / per] + par;
+            const size_t e = ((size_t)cls * PH + (y >> 2)) * PW + (xx >> 2);
+            if (x.packed) {
+                const uint32_t v = *(reinterpret_cast<const volatile uint32_t*>(base) + e);
+                if (x.raster_packed) x.raster_packed[i] = v;
+                if (x.raster) x.raster[i] = unpack_gi(v);
+            } else {
+                const uint4 q = ld_volatile_u4(reinterpret_cast<const float4*>(base) + e);
+                if (x.raster) x.raster[i] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+            }
+        }
+    }
+    // last CTA out: advance the frame counter, re-arm the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(x.ticket, 1u) == gridDim.x - 1) {
+            *x.ticket = 0u;
+            *reinterpret_cast<volatile uint32_t*>(x.frame_ctr) = frame;
+            __threadfence();
+        }
+    }
+}
+int launch_exchange(const ExchangeArgs& x, cudaStream_t st) {
+    // every CTA must be resident (all of them spin on the flags before any of them can finish): at most one wave
+    const long long work = ((long long)x.W * x.H) / 16 + 1;
+    const int grid = (int)std::max(1LL, std::min<long long>(148 * 4, (work + 255) / 256));
+    exchange_kernel<<<grid, 256, 0, st>>>(x);
     return 1;
 }
-int launch_exchange_wait(const uint32_t* flags, int world, uint32_t frame_id, uint32_t* error_flag, cudaStream_t st) {
-    exchange_wait_kernel<<<1, 32, 0, st>>>(flags, world, frame_id, error_flag);
+
+// host-input sharded frame: "my G-buffer slab has been pushed to every peer" (slot = 8 + rank) and the matching wait
+__global__ void flag_signal_kernel(uint32_t* const* peer_flags, int world, int slot, const uint32_t* frame_ctr) {
+    const uint32_t frame = *reinterpret_cast<const volatile uint32_t*>(frame_ctr) + 1u;
+    if (threadIdx.x < (unsigned)world) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(peer_flags[threadIdx.x] + slot) = frame;
+        __threadfence_system();
+    }
+}
+__global__ void flag_wait_kernel(const uint32_t* flags, int world, const uint32_t* frame_ctr, uint32_t* error) {
+    const uint32_t frame = *reinterpret_cast<const volatile uint32_t*>(frame_ctr) + 1u;
+    wait_flags(flags, world, frame, error);
+}
+int launch_flag_signal(uint32_t* const* peer_flags, int world, int slot, const uint32_t* frame_ctr, cudaStream_t st) {
+    flag_signal_kernel<<<1, 32, 0, st>>>(peer_flags, world, slot, frame_ctr);
+    return 1;
+}
+int launch_flag_wait(const uint32_t* flags, int world, const uint32_t* frame_ctr, uint32_t* error, cudaStream_t st) {
+    flag_wait_kernel<<<1, 32, 0, st>>>(flags, world, frame_ctr, error);
     return 1;
 }
 
@@ -416,11 +517,11 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
     float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (r == 123.456f) out[0] = r;
 }
-float measure_fp32_peak_tflops(cudaStream_t st) {
+float measure_fp32_peak_tflops(int device, cudaStream_t st) {
     float* d = nullptr;
     if (cudaMalloc(&d, 4) != cudaSuccess) return -1.0f;
     int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int iters = 1 << 15, blocks = sms * 8;

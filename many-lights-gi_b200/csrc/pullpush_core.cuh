@@ -1,0 +1,348 @@
+// pullpush_core.cuh -- the arithmetic of pull.comp / push.comp for one 64x64 ISM held in shared memory, written as
+// per-thread "phases" (everything between two CTA barriers is one phase; inside a phase threads only communicate through
+// the list counter). The kernel in exact.cu runs phase(tid) on 256 threads with __syncthreads() in between; the test
+// harness tests/hostemu compiles the same phases for the host and runs tid = 0..255 in a loop, so the logic of this file is
+// checked bit for bit against the oracle on a machine without a GPU. Every operation is an IEEE fp32 operation with one
+// rounding (no FMA contraction: -fmad=false / -ffp-contract=off), so host and device agree.
+//
+// Bit-exact contract: pull.comp:20-126, push.comp:44-165, ImperfectShadowmap.cpp:121-182 (R16 result).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#if defined(__CUDACC__)
+#define PP_HD __host__ __device__ __forceinline__
+#else
+#define PP_HD inline
+#endif
+
+#if !defined(__CUDA_ARCH__)
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace mlgi {
+namespace pp {
+
+constexpr int kThreads = 256;
+constexpr int kThrPitch = 34;                      // padded threshold plane: coarse level (<= 32 wide) plus a one-texel ring
+
+// float4 offset of pyramid level l (1..6) inside PY: sum_{k<l} 4^(6-k)
+PP_HD constexpr int lvl_off(int l) { return (4096 - (4096 >> (2 * (l - 1)))) / 3; }
+
+struct Shared {
+    uint32_t L0[64 * 64];                          // R32UI tile in, R16 results (one per word) out
+    float4 PY[1024 + 256 + 64 + 16 + 4 + 1];       // RGBA32F levels 1..6 (pull results, overwritten in place by push results)
+    union {                                        // never live at the same time:
+        float thr[kThrPitch * kThrPitch];          //   push: per coarse texel T with  length(d) > radius * 2^-level  <=>  dot(d,d) > T
+        uint16_t list[1024];                       //   pull level 1: outputs whose 2x2 block holds a point
+    };
+    float lut_r[256], lut_md[256];                 // level-0 decode of the 8-bit radius (pull.comp:39,57)
+    float4 empty1;                                 // pull level 1 of an all-empty 2x2 block
+    int count;                                     // number of entries of `list`
+};
+
+// ---- bit casts / conversions with host equivalents -------------------------------------------------------------------
+PP_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+PP_HD uint32_t f2u_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+PP_HD float pinf() { return u2f(0x7f800000u); }
+PP_HD float min_glsl(float a, float b) { return (b < a) ? b : a; }
+PP_HD float max_glsl(float a, float b) { return (a < b) ? b : a; }
+PP_HD uint32_t pack_half2x(float x, float y) {
+    return (uint32_t)__half_as_ushort(__float2half_rn(x)) | ((uint32_t)__half_as_ushort(__float2half_rn(y)) << 16);
+}
+PP_HD float half_lo(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p & 0xFFFFu))); }
+PP_HD float half_hi(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p >> 16))); }
+PP_HD uint32_t r16_unorm(float d) {                // push.comp:29-41: imageStore to R16 (clamp, scale, round to nearest even)
+    const float c = min_glsl(max_glsl(d, 0.0f), 1.0f) * 65535.0f;
+#if defined(__CUDA_ARCH__)
+    return __float2uint_rn(c);
+#else
+    return (uint32_t)nearbyintf(c);
+#endif
+}
+PP_HD float sqrt_rn(float x) {
+#if defined(__CUDA_ARCH__)
+    return __fsqrt_rn(x);
+#else
+    return sqrtf(x);
+#endif
+}
+
+// Exact square-root elimination. For a correctly rounded sqrtf and rs >= 0:  sqrtf(x) > rs  <=>  sqrt(x) > m, where
+// m = (rs + nextafter(rs)) / 2 is the rounding boundary above rs  <=>  x > m*m. m has 25 significant bits, so m*m is
+// exact in fp64 and is never itself a float; hence  sqrtf(x) > rs  <=>  x > T  with T = round_down_to_float(m*m).
+// One threshold per coarse texel replaces one square root per (pixel, tap). rs = inf / NaN give T = NaN (never greater,
+// like the original comparison); a negative rs (cannot occur: radii are means of non-negative values) keeps
+// "always greater" through T = -1.
+PP_HD float sqrt_gt_threshold(float rs) {
+    const float next = u2f(f2u_bits(rs) + 1u);
+    const double m = ((double)rs + (double)next) * 0.5;
+    const double mm = m * m;
+#if defined(__CUDA_ARCH__)
+    const float T = __double2float_rd(mm);
+#else
+    float T = (float)mm;                           // round to nearest, then step down if that rounded up
+    if ((double)T > mm) T = nextafterf(T, -INFINITY);
+#endif
+    return rs < 0.0f ? -1.0f : T;
+}
+
+// ---- pull -------------------------------------------------------------------------------------------------------------
+struct PullSample { float depth, maxDepth, radius, dx, dy; };
+
+// level-0 decode, pull.comp:37-41,55-65 (ismPixelSize = A / S, ImperfectShadowmap.cpp:187-191)
+PP_HD void decode_l0(const Shared& s, uint32_t u, float zFar, float ismPixelSize, PullSample& smp) {
+    const float depthSample = float(u >> 8) / 16777216.0f;
+    float radius = s.lut_r[u & 0xFFu];                                  // float(u & 0xFF) / 10      :39
+    const float maxDepth = depthSample + s.lut_md[u & 0xFFu];           // + (radius*2)/zFar*0.6     :57
+    const float distToCamera = depthSample * zFar;                      // :60
+    radius = radius / distToCamera / 3.14f * ismPixelSize;              // :61
+    radius *= 1.3f;                                                     // :63
+    radius = min_glsl(radius, 15.0f);                                   // :65
+    smp.depth = depthSample; smp.maxDepth = maxDepth; smp.radius = radius; smp.dx = 0.0f; smp.dy = 0.0f;
+}
+
+// pull.comp:67-123 given the four decoded inputs (absolute input coords ix0.., output coord ox,oy). Coordinates are GLOBAL
+// atlas coordinates: the fp32 rounding of (coord + 0.5 + displacement) depends on their magnitude.
+PP_HD float4 pull_combine(const PullSample (&smp)[4], int ix0, int iy0, int ox, int oy, int level) {
+    const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};   // pull.comp:24
+    float e[4], ndx[4], ndy[4];
+    bool valid[4];
+    const float scale = u2f((uint32_t)(127 - level) << 23);      // 2^-level, exact (:72)
+    const float fox = float(ox) + 0.5f, foy = float(oy) + 0.5f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ndx[i] = (float(ix0 + offx[i]) + 0.5f + smp[i].dx) / 2.0f - fox;   // :69
+        ndy[i] = (float(iy0 + offy[i]) + 0.5f + smp[i].dy) / 2.0f - foy;
+        const bool radiusCheckPassed = sqrt_rn(ndx[i] * ndx[i] + ndy[i] * ndy[i]) <= smp[i].radius * scale;   // :70-74
+        valid[i] = (smp[i].depth != 1.0f) && radiusCheckPassed;            // :80-81
+        e[i] = valid[i] ? smp[i].depth : pinf();
+    }
+    // :84-92: maxDepth is taken from the LAST sample whose depth equals the running minimum, i.e. the last index that
+    // attains the minimum over the valid samples (depths are finite and >= +0, so fminf == the GLSL ternary min)
+    const float mn = fminf(fminf(e[0], e[1]), fminf(e[2], e[3]));
+    float maxDepth = smp[0].maxDepth;
+#pragma unroll
+    for (int i = 1; i < 4; i++) if (e[i] == mn) maxDepth = smp[i].maxDepth;
+    float depthAcc = 0.0f, radiusAcc = 0.0f, maxValidMaxDepth = 0.0f, dax = 0.0f, day = 0.0f;
+    int numValid = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                                 // :94-113
+        if (!valid[i] || smp[i].depth > maxDepth) continue;
+        depthAcc += smp[i].depth;
+        dax += ndx[i]; day += ndy[i];
+        radiusAcc += smp[i].radius;
+        maxValidMaxDepth = fmaxf(maxValidMaxDepth, smp[i].maxDepth);
+        numValid++;
+    }
+    if (numValid > 0) {                                           // :116-123
+        const float nv = float(numValid);
+        return make_float4(depthAcc / nv, maxValidMaxDepth, radiusAcc / nv, u2f(pack_half2x(dax / nv, day / nv)));
+    }
+    return make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// ---- push -------------------------------------------------------------------------------------------------------------
+// The four coarse texels of one push thread T (push.comp:46-62), in the shader's order {0,0},{0,1},{1,1},{1,0}.
+struct PushTaps {
+    float depth[4], maxDepth[4], radius[4];
+    float thr[4];           // threshold of the radius check; -1 for a tap that may not contribute at all (other ISM :77-86,
+                            // or depth == 1.0 :88-93): dot(d,d) >= 0 > -1 zeroes its weight like the shader does
+    float d2x[4], d2y[4];   // coarse displacement * 2                             (:101)
+};
+
+// One output pixel of thread T. OP is the shader's outputPixel (:65-67). displacementVectors[i] = (coarserTexCoord -
+// thisTexCoord) + disp*2 (:98-101): the bracket is +-0.5 or +-1.5 for every T (differences of small half-integers are
+// exact), so it is a compile-time constant per (OP, tap). Weights are {9,3,1,3} rotated by OP (:70-74). The weighted means
+// are evaluated only when the texel is replaced (:159-161), and at level 0 only the depth is consumed (R16 store), so the
+// other means are not evaluated there; skipped work never feeds a stored value.
+template <int OP, bool LEVEL0>
+PP_HD float4 push_pixel(const PushTaps& c, float4 orig) {
+    constexpr int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 1, 0};
+    constexpr float WX[4] = {9.0f, 3.0f, 1.0f, 3.0f};
+    float dvx[4], dvy[4], e[4];
+    bool p[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                                          // :96-110
+        const float kx = float(2 * offx[i] - offx[OP]) - 0.5f, ky = float(2 * offy[i] - offy[OP]) - 0.5f;
+        dvx[i] = kx + c.d2x[i];
+        dvy[i] = ky + c.d2y[i];
+        p[i] = !(dvx[i] * dvx[i] + dvy[i] * dvy[i] > c.thr[i]);            // == !(length(d) > radius * 2^-level)
+        e[i] = p[i] ? c.depth[i] : pinf();
+    }
+    // :113-126 depth range check: maxDepth of the last tap attaining the minimum depth over the surviving taps
+    const float mn = fminf(fminf(e[0], e[1]), fminf(e[2], e[3]));
+    float maxDepth = c.maxDepth[0];
+#pragma unroll
+    for (int i = 1; i < 4; i++) if (e[i] == mn) maxDepth = c.maxDepth[i];
+    bool any = false, occluded = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        p[i] = p[i] && !(c.depth[i] > maxDepth);
+        any = any || p[i];                                                 // weightAcc > 0                     (:158)
+        occluded = occluded || (p[i] && orig.x > c.maxDepth[i]);           // :153-156
+    }
+    const bool invalid = orig.x == 1.0f;                                   // :151 (never true at level 0: depth24 / 2^24 < 1)
+    if (!any || (!invalid && !occluded)) return orig;                      // :159-161
+    // weighted means (:129-147); a zero weight adds +-0 to a sum that starts at +0, which leaves it unchanged, so the
+    // terms of dropped taps are skipped
+    float wa = 0.0f, depthAcc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (p[i]) { const float w = WX[(i - OP + 4) & 3]; wa += w; depthAcc += c.depth[i] * w; }
+    if (LEVEL0) return make_float4(depthAcc / wa, 0.0f, 0.0f, 0.0f);
+    float radiusAcc = 0.0f, maxDepthAcc = 0.0f, dax = 0.0f, day = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (p[i]) {
+        const float w = WX[(i - OP + 4) & 3];
+        maxDepthAcc += c.maxDepth[i] * w;
+        radiusAcc += c.radius[i] * w;
+        dax += dvx[i] * w; day += dvy[i] * w;
+    }
+    return make_float4(depthAcc / wa, maxDepthAcc / wa, radiusAcc / wa, u2f(pack_half2x(dax / wa, day / wa)));
+}
+
+// ======================================================================================================================
+// phases (tid in [0, kThreads)); the caller puts a CTA barrier between consecutive phases
+// ======================================================================================================================
+PP_HD void phase_luts(Shared& s, int tid, float zFar) {
+    const float r = float(tid) / 10.0f;                // kThreads == 256 entries
+    s.lut_r[tid] = r;
+    s.lut_md[tid] = (r * 2.0f) / zFar * 0.6f;
+    if (tid == 0) s.count = 0;
+}
+
+// the result of an all-empty 2x2 block does not depend on its position: every term of pull.comp:69 is exact, so the four
+// displacement vectors are (+-0.25, +-0.25) everywhere; evaluated once per CTA by the general code
+PP_HD void phase_empty1(Shared& s, int tid, float zFar, float ismPixelSize, int gx0, int gy0) {
+    if (tid != 0) return;
+    PullSample smp[4];
+    for (int i = 0; i < 4; i++) decode_l0(s, 0xFFFFFFFFu, zFar, ismPixelSize, smp[i]);
+    const int ox = gx0 >> 1, oy = gy0 >> 1;
+    s.empty1 = pull_combine(smp, ox * 2, oy * 2, ox, oy, 1);
+}
+
+PP_HD void phase_pull1_classify(Shared& s, int tid) {
+    for (int o = tid; o < 1024; o += kThreads) {
+        const int lx = o & 31, ly = o >> 5;
+        const uint32_t* r0 = &s.L0[(ly * 2) * 64 + lx * 2];
+        const uint32_t* r1 = r0 + 64;
+        if ((r0[0] & r0[1] & r1[0] & r1[1]) == 0xFFFFFFFFu) s.PY[lvl_off(1) + o] = s.empty1;
+        else {
+#if defined(__CUDA_ARCH__)
+            const int slot = atomicAdd(&s.count, 1);
+#else
+            const int slot = s.count++;
+#endif
+            s.list[slot] = (uint16_t)o;
+        }
+    }
+}
+
+PP_HD void phase_pull1_dense(Shared& s, int tid, float zFar, float ismPixelSize, int gx0, int gy0) {
+    const int n = s.count;
+    for (int q = tid; q < n; q += kThreads) {
+        const int o = s.list[q];
+        const int lx = o & 31, ly = o >> 5;
+        PullSample smp[4];
+        const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};
+#pragma unroll
+        for (int i = 0; i < 4; i++) decode_l0(s, s.L0[(ly * 2 + offy[i]) * 64 + lx * 2 + offx[i]], zFar, ismPixelSize, smp[i]);
+        const int ox = (gx0 >> 1) + lx, oy = (gy0 >> 1) + ly;
+        s.PY[lvl_off(1) + o] = pull_combine(smp, ox * 2, oy * 2, ox, oy, 1);
+    }
+}
+
+PP_HD void phase_pull(Shared& s, int tid, int level, int gx0, int gy0) {      // level 2..6 from level - 1
+    const int osz = 64 >> level, isz = osz * 2;
+    const float4* in = s.PY + lvl_off(level - 1);
+    for (int o = tid; o < osz * osz; o += kThreads) {
+        const int lx = o & (osz - 1), ly = o >> (6 - level);
+        PullSample smp[4];
+        const int offx[4] = {0, 0, 1, 1}, offy[4] = {0, 1, 0, 1};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float4 rd = in[(ly * 2 + offy[i]) * isz + lx * 2 + offx[i]];   // pull.comp:43-47
+            smp[i].depth = rd.x; smp[i].maxDepth = rd.y; smp[i].radius = rd.z;
+            const uint32_t pk = f2u_bits(rd.w);
+            smp[i].dx = half_lo(pk); smp[i].dy = half_hi(pk);
+        }
+        const int ox = (gx0 >> level) + lx, oy = (gy0 >> level) + ly;
+        s.PY[lvl_off(level) + o] = pull_combine(smp, ox * 2, oy * 2, ox, oy, level);
+    }
+}
+
+// thresholds of the coarse level (level + 1) for the push pass that writes `level`: one per coarse texel instead of one
+// square root per (pixel, tap); texels that may never contribute (depth == 1.0, push.comp:88-93) and the ring around the
+// tile (a neighbouring ISM, :77-86; those CTAs own them) get -1
+PP_HD void phase_push_thresholds(Shared& s, int tid, int level) {
+    const int csz = 32 >> level, pitch = csz + 2;
+    const float4* coarse = s.PY + lvl_off(level + 1);
+    const float scale = u2f((uint32_t)(127 - level) << 23);                     // 2^-level (:106)
+    for (int q = tid; q < pitch * pitch; q += kThreads) {
+        const int px = q % pitch, py = q / pitch;
+        const int cx = px - 1, cy = py - 1;
+        float T = -1.0f;
+        if (cx >= 0 && cy >= 0 && cx < csz && cy < csz) {
+            const float4 cs = coarse[cy * csz + cx];
+            if (cs.x != 1.0f) T = sqrt_gt_threshold(cs.z * scale);
+        }
+        s.thr[py * kThrPitch + px] = T;
+    }
+}
+
+// one push pass (level 5..0) over the tile: thread T owns the (up to) four fine pixels that share its four coarse texels
+template <bool LEVEL0>
+PP_HD void phase_push(Shared& s, int tid, int level) {
+    const int size = 64 >> level, csz = size >> 1;        // this level / coarser level, tile-local
+    const int nT = csz + 1;
+    const float4* coarse = s.PY + lvl_off(level + 1);
+    float4* same = LEVEL0 ? nullptr : s.PY + lvl_off(level);
+    for (int it = tid; it < nT * nT; it += kThreads) {
+        const int tlx = it % nT, tly = it / nT;           // local T; coarserLowerLeftPixel = T - 1 (push.comp:46)
+        const int x0 = tlx > 0 ? tlx - 1 : 0, x1 = tlx < csz ? tlx : csz - 1;   // clamped: an out-of-tile tap carries thr = -1
+        const int y0 = tly > 0 ? tly - 1 : 0, y1 = tly < csz ? tly : csz - 1;
+        PushTaps c;
+        const int cxs[4] = {x0, x0, x1, x1}, cys[4] = {y0, y1, y1, y0};         // offsets {0,0},{0,1},{1,1},{1,0}  (:48)
+        const int pxs[4] = {tlx, tlx, tlx + 1, tlx + 1}, pys[4] = {tly, tly + 1, tly + 1, tly};   // ring-padded coordinates
+#pragma unroll
+        for (int i = 0; i < 4; i++) {                     // :55-62
+            const float4 cs = coarse[cys[i] * csz + cxs[i]];
+            c.depth[i] = cs.x; c.maxDepth[i] = cs.y; c.radius[i] = cs.z;
+            const uint32_t pk = f2u_bits(cs.w);
+            c.d2x[i] = half_lo(pk) * 2.0f; c.d2y[i] = half_hi(pk) * 2.0f;
+            c.thr[i] = s.thr[pys[i] * kThrPitch + pxs[i]];
+        }
+        const int bx = tlx * 2 - 1, by = tly * 2 - 1;     // tile-local pixel of outputPixel 0 (:67)
+#define PP_ONE(OP, OX, OY)                                                                                        \
+        {                                                                                                         \
+            const int plx = bx + OX, ply = by + OY;                                                               \
+            if (plx >= 0 && ply >= 0 && plx < size && ply < size) {   /* else: a neighbouring ISM's CTA owns it */ \
+                if (LEVEL0) {                                                                                     \
+                    const float4 orig = make_float4(float(s.L0[ply * 64 + plx] >> 8) / 16777216.0f, 0.0f, 0.0f, 0.0f);   /* :19-27 */ \
+                    s.L0[ply * 64 + plx] = r16_unorm(push_pixel<OP, true>(c, orig).x);                            \
+                } else {                                                                                          \
+                    same[ply * size + plx] = push_pixel<OP, false>(c, same[ply * size + plx]);                    \
+                }                                                                                                 \
+            }                                                                                                     \
+        }
+        PP_ONE(0, 0, 0) PP_ONE(1, 0, 1) PP_ONE(2, 1, 1) PP_ONE(3, 1, 0)
+#undef PP_ONE
+    }
+}
+
+}  // namespace pp
+}  // namespace mlgi

@@ -64,6 +64,11 @@ class Mesh(C.Structure):
                 ("num_vertices", C.c_int), ("num_triangles", C.c_int)]
 
 
+class FrameStats(C.Structure):
+    _fields_ = [("host_enqueue_us", C.c_double), ("graph_replays", C.c_ulonglong), ("graph_instantiations", C.c_ulonglong),
+                ("graph_enabled", C.c_int)]
+
+
 class Timing(C.Structure):
     _fields_ = [("name", C.c_char * 24), ("ms", C.c_float), ("launches", C.c_int)]
 
@@ -72,7 +77,8 @@ EXPORTS = [
     "mlgi_version", "mlgi_default_params", "mlgi_create", "mlgi_destroy", "mlgi_last_error",
     "mlgi_vpl_process", "mlgi_ism_points", "mlgi_ism_set_points", "mlgi_ism_splat", "mlgi_ism_pullpush",
     "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_composite_ambient", "mlgi_frame", "mlgi_frame_host", "mlgi_frame_host_packed",
-    "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_read_buffer_async", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_debug_sqrt_thresholds", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_exchange_create", "mlgi_exchange_connect", "mlgi_exchange_finish", "mlgi_exchange_status", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
+    "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_read_buffer_async", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_debug_sqrt_thresholds", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_exchange_create", "mlgi_exchange_connect", "mlgi_exchange_connect_local", "mlgi_exchange_finish", "mlgi_exchange_status",
+    "mlgi_frame_sharded", "mlgi_frame_sharded_host", "mlgi_set_graph", "mlgi_get_frame_stats", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
 ]
 
 _lib = None
@@ -129,6 +135,11 @@ def load():
     lib.mlgi_planar_to_raster.argtypes = [P, P, P, P]
     lib.mlgi_exchange_create.argtypes = [P, C.c_int, C.c_int, P]
     lib.mlgi_exchange_connect.argtypes = [P, P]
+    lib.mlgi_exchange_connect_local.argtypes = [P, C.POINTER(P)]
+    lib.mlgi_frame_sharded.argtypes = lib.mlgi_frame.argtypes
+    lib.mlgi_frame_sharded_host.argtypes = lib.mlgi_frame_host.argtypes
+    lib.mlgi_set_graph.argtypes = [P, C.c_int]
+    lib.mlgi_get_frame_stats.argtypes = [P, C.POINTER(FrameStats)]
     lib.mlgi_exchange_finish.argtypes = [P, P]
     lib.mlgi_exchange_status.argtypes = [P]
     lib.mlgi_get_timings.argtypes = [P, C.POINTER(Timing), C.c_int]
@@ -175,7 +186,7 @@ class Context:
                  device=0, class_lo=0, class_hi=16, enable_timers=False, gi_packed=False):
         self.lib = load()
         self.cfg = Config(device, width, height, vpl_count, rsm_width, rsm_height, max_triangles, max_points,
-                          class_lo, class_hi, int(enable_timers), int(gi_packed))
+                          class_lo, class_hi, int(enable_timers), int(gi_packed))      # gi_packed: False/True or 2 = packed image only
         self.h = C.c_void_p()
         rc = self.lib.mlgi_create(C.byref(self.cfg), C.byref(self.h))
         if rc != 0:
@@ -239,6 +250,23 @@ class Context:
         self._ck(self.lib.mlgi_frame_host_packed(self.h, C.byref(host_rsm), C.byref(light), C.byref(dev_mesh), C.byref(host_gb),
                                                  C.byref(cam), C.byref(params), _ptr(host_gi_packed), stream))
 
+    def frame_sharded(self, rsm, light, mesh, gb, cam, params, stream=None):
+        self._ck(self.lib.mlgi_frame_sharded(self.h, C.byref(rsm), C.byref(light), C.byref(mesh), C.byref(gb), C.byref(cam),
+                                             C.byref(params), stream))
+
+    def frame_sharded_host(self, host_rsm, light, dev_mesh, host_gb, cam, params, host_gi_packed=None, stream=None):
+        self._ck(self.lib.mlgi_frame_sharded_host(self.h, C.byref(host_rsm), C.byref(light), C.byref(dev_mesh), C.byref(host_gb),
+                                                  C.byref(cam), C.byref(params), _ptr(host_gi_packed), stream))
+
+    def set_graph(self, enable):
+        self._ck(self.lib.mlgi_set_graph(self.h, int(enable)))
+
+    def frame_stats(self):
+        st = FrameStats()
+        self._ck(self.lib.mlgi_get_frame_stats(self.h, C.byref(st)))
+        return {"host_enqueue_us": st.host_enqueue_us, "graph_replays": int(st.graph_replays),
+                "graph_instantiations": int(st.graph_instantiations), "graph_enabled": bool(st.graph_enabled)}
+
     def buffer(self, buf_id):
         p = C.c_void_p()
         n = C.c_size_t()
@@ -295,6 +323,11 @@ class Context:
     def exchange_connect(self, handles):
         blob = b"".join(handles)
         self._ck(self.lib.mlgi_exchange_connect(self.h, C.c_char_p(blob)))
+
+    def exchange_connect_local(self, contexts):
+        """same-process peers: `contexts` = the world Context objects in rank order"""
+        arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+        self._ck(self.lib.mlgi_exchange_connect_local(self.h, arr))
 
     def exchange_finish(self, stream=None):
         self._ck(self.lib.mlgi_exchange_finish(self.h, stream))

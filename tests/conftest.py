@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "many-lights-gi_b200"), os.path.join(ROOT, "oracle"), ROOT):
+for p in (os.path.join(ROOT, "many-lights-gi_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fixtures"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -24,7 +24,7 @@ def _ensure_built():
     library is built by __graft_entry__.build() (nvcc cross-compiles without a GPU)."""
     import subprocess
     need = [os.path.join(ROOT, "oracle", "liboracle.so"),
-            os.path.join(ROOT, "many-lights-gi_b200", "lib", "libmlgi_scene.so"),
+            os.path.join(ROOT, "fixtures", "libmlgi_scene.so"),
             os.path.join(ROOT, "many-lights-gi_b200", "lib", "libmlgi.so")]
     if not all(os.path.exists(p) for p in need):
         subprocess.check_call([sys.executable, "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT)
@@ -37,7 +37,7 @@ class Case:
     """A seeded synthetic workload plus lazily computed oracle results for every stage."""
 
     def __init__(self, W, H, N, rsm_w, rsm_h, cell, clutter=8, sun=266.0, seed=0x5EED, **camera):
-        from mlgi.scene import Workload
+        from scene_fixture import Workload
         self.wl = Workload(W, H, N, rsm_w=rsm_w, rsm_h=rsm_h, cell_size=cell, clutter_boxes=clutter, sun_cycle_position=sun, seed=seed, **camera)
         self.W, self.H, self.N = W, H, N
         self.z_far = 50.0

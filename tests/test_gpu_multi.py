@@ -1,5 +1,7 @@
-"""Multi-GPU tests (need >= 2 GPUs; skipped otherwise): the fused peer-store exchange and the NCCL all-gather path both
-reproduce the single-GPU image bit for bit on every rank."""
+"""Multi-GPU tests (need >= 2 GPUs; skipped otherwise -- the single-GPU box runs the same exchange kernels through
+test_gpu_parity.py::test_exchange_kernels_with_two_sequential_shards_on_one_gpu): the peer-memory exchange (pull and push
+modes, graph-replayed mlgi_frame_sharded), the host-input sharded frame and the NCCL all-gather path all reproduce the
+single-GPU image bit for bit on every rank."""
 import os
 import socket
 
@@ -32,6 +34,8 @@ def _worker(rank, world, port, mode, packed, q):
     from conftest import Case
     import mlgi
     from mlgi import dist as mdist
+    if mode in ("pull", "push"):
+        os.environ["MLGI_XCH"] = mode
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -57,13 +61,24 @@ def _worker(rank, world, port, mode, packed, q):
         ctx = mlgi.Context(case.W, case.H, case.N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 22, device=rank, class_lo=lo, class_hi=hi,
                            gi_packed=packed)
         ok = True
-        if mode == "fused":
+        if mode in ("pull", "push", "host"):
             handles = [None] * world
             dist.all_gather_object(handles, ctx.exchange_create(rank, world))
             ctx.exchange_connect(handles)
+        if mode in ("pull", "push"):
             for _ in range(3):                       # three frames: exercises the parity double-buffering
-                ctx.frame(rsm, light, mesh, gb, cam, p)
-                ctx.exchange_finish()
+                ctx.frame_sharded(rsm, light, mesh, gb, cam, p)
+            ctx.exchange_status()
+        elif mode == "host":
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
+            host_gi = torch.zeros((case.H, case.W), dtype=torch.int32).pin_memory()
+            y0, y1 = rank * case.H // world, (rank + 1) * case.H // world
+            for _ in range(3):
+                host_gi.zero_()
+                ctx.frame_sharded_host(mlgi.make_rsm(h[0], h[1], h[2]), light, mesh, mlgi.make_gbuffer(h[3], h[4]), cam, p, host_gi_packed=host_gi)
+                ok = ok and bool(np.array_equal(host_gi.numpy().view(np.uint32)[y0:y1].ravel(), ref.reshape(case.H, case.W)[y0:y1].ravel()))
+                ok = ok and not host_gi.numpy()[:y0].any() and not host_gi.numpy()[y1:].any()     # only this rank's rows are written
             ctx.exchange_status()
         else:
             PH, PW = (case.H + 3) // 4, (case.W + 3) // 4
@@ -76,9 +91,9 @@ def _worker(rank, world, port, mode, packed, q):
         torch.cuda.synchronize()
         got = ctx.download(mlgi.BUF_GI_PACKED, np.uint32) if packed else ctx.download(mlgi.BUF_GI, np.float32)
         if packed:
-            ok = bool(np.array_equal(got, ref))
+            ok = ok and bool(np.array_equal(got, ref))
         else:
-            ok = bool(np.array_equal(got.reshape(-1, 4)[:, :3], ref.reshape(-1, 4)[:, :3]))
+            ok = ok and bool(np.array_equal(got.reshape(-1, 4)[:, :3], ref.reshape(-1, 4)[:, :3]))
         dist.barrier()
         ctx.close()
         q.put((rank, ok))
@@ -86,7 +101,7 @@ def _worker(rank, world, port, mode, packed, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,packed", [("fused", True), ("fused", False), ("nccl", True)])
+@pytest.mark.parametrize("mode,packed", [("pull", True), ("pull", False), ("push", True), ("host", True), ("nccl", True)])
 def test_two_gpu_exchange_is_bit_identical(mode, packed):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")

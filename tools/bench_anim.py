@@ -6,7 +6,7 @@ each GPU, --depth contexts on separate streams let the ISM build of frame i+1 ru
 Prints one JSON line on rank 0: frames/s and Gpixel*VPL/s over the batch."""
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200"))
+sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200")); sys.path.insert(0, os.path.join(ROOT, "fixtures"))
 
 
 def main():
@@ -16,7 +16,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=3)
     args = ap.parse_args()
     import numpy as np, torch, mlgi
-    from mlgi.scene import Workload
+    from scene_fixture import Workload
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -1,8 +1,8 @@
 """offline study: warp-level lit coherence of the gathering kernel under different pixel->lane mappings"""
 import sys, os, numpy as np
-sys.path.insert(0, 'many-lights-gi_b200'); sys.path.insert(0, 'oracle')
+sys.path.insert(0, 'many-lights-gi_b200'); sys.path.insert(0, 'oracle'); sys.path.insert(0, 'fixtures')
 import oracle_py as O
-from mlgi.scene import Workload
+from scene_fixture import Workload
 W, H, N = 3840, 2160, 4096
 wl = Workload(W, H, N)
 vpl, packed = O.vpl_process(wl.rsm_diffuse, wl.rsm_normal, wl.rsm_depth, N, wl.light_view, wl.light_proj)

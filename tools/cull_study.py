@@ -3,8 +3,8 @@ that are actually lit (min(a,b) > 0). Used to choose the tiled-culling rule (DES
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200")); sys.path.insert(0, ROOT)
-from mlgi.scene import Workload
+sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200")); sys.path.insert(0, os.path.join(ROOT, "fixtures")); sys.path.insert(0, ROOT)
+from scene_fixture import Workload
 from oracle import oracle_py as orc
 
 W, H, N = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (3840, 2160, 4096)))

@@ -3,7 +3,7 @@ ambient composite (deferredshading.frag ambient term) and a crop of the ISM atla
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200")); sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200")); sys.path.insert(0, os.path.join(ROOT, "fixtures")); sys.path.insert(0, ROOT)
 import torch
 from PIL import Image
 import mlgi

@@ -3,7 +3,7 @@ coordinate (MLGI_ISM_FETCH=tex) and with the unfloored coordinate (texf) and cou
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200")); sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200")); sys.path.insert(0, os.path.join(ROOT, "fixtures")); sys.path.insert(0, ROOT)
 import torch, mlgi, bench
 name = sys.argv[1] if len(sys.argv) > 1 else "4k_4096"
 wl = bench.build_workload(name); sc, W, H, N = wl.scene, wl.W, wl.H, wl.N
