@@ -932,6 +932,11 @@ static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* 
         CK(cudaGraphLaunch(ctx->graph_exec, st));
         ctx->launches += ctx->graph_launches;
         ctx->graph_replays++;
+        // host-side stage bookkeeping of a replayed frame (what the stage calls set when they are issued directly)
+        ctx->have_vpl = ctx->have_points = ctx->have_atlas = ctx->have_ism = ctx->have_gi = true;
+        ctx->grouped_valid = false; ctx->have_blur = false; ctx->atlas_precleared = false;
+        if (p->cull_mode == MLGI_CULL_CLUSTERED) ctx->have_clustered = true;
+        if (p->cull_mode == MLGI_CULL_TILED) { ctx->have_tiled = true; ctx->tile_order_valid = ctx->fg_sorted != 0; }
     }
     ctx->last_enqueue_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     return rc;

@@ -390,7 +390,7 @@ int launch_splat(const float4* points, const uint32_t* point_bucket, const uint3
 // (push.comp:77-86). The arithmetic lives in pullpush_core.cuh as per-thread phases (also
 // compiled for the host by tests/hostemu, which checks it against the oracle without a GPU);
 // this kernel is the tile load, the phases with CTA barriers in between, and the tile store.
-// 44.9 KB of shared memory and <= 48 registers: 5 CTAs (40 warps) per SM.
+// ~42 KB of shared memory and <= 48 registers: 5 CTAs (40 warps) per SM.
 // =====================================================================================
 #ifndef PP_MINB
 #define PP_MINB 5
@@ -411,14 +411,12 @@ __global__ void __launch_bounds__(pp::kThreads, PP_MINB) pullpush_kernel(const u
         const int q = tid + k * pp::kThreads;  // uint4 index 0..1023
         v[k] = __ldg(reinterpret_cast<const uint4*>(atlas + (size_t)(gy0 + (q >> 4)) * A + gx0 + (q & 15) * 4));
     }
-    pp::phase_luts(s, tid, zFar);
+    pp::phase_tables(s, tid, zFar, ismPixelSize, gx0, gy0);      // tables + the all-empty block, while the loads are in flight
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int q = tid + k * pp::kThreads;
         *reinterpret_cast<uint4*>(&s.L0[(q >> 4) * 64 + (q & 15) * 4]) = v[k];
     }
-    __syncthreads();
-    pp::phase_empty1(s, tid, zFar, ismPixelSize, gx0, gy0);
     __syncthreads();
     pp::phase_pull1_classify(s, tid);
     __syncthreads();
@@ -431,15 +429,13 @@ __global__ void __launch_bounds__(pp::kThreads, PP_MINB) pullpush_kernel(const u
     }
     // push levels 5..0, in place: push[i] overwrites pull[i]; only the owning thread reads the texel it replaces
 #pragma unroll 1
-    for (int level = 5; level >= 1; level--) {
-        pp::phase_push_thresholds(s, tid, level);
-        __syncthreads();
-        pp::phase_push<false>(s, tid, level);
+    for (int level = 5; level >= 2; level--) {
+        pp::phase_push_top(s, tid, level);
         __syncthreads();
     }
-    pp::phase_push_thresholds(s, tid, 0);
+    pp::phase_push1(s, tid);
     __syncthreads();
-    pp::phase_push<true>(s, tid, 0);
+    pp::phase_push0(s, tid);
     __syncthreads();
     // ---- store the R16 tile: 64 rows x 128 B, coalesced uint4 ----
 #pragma unroll

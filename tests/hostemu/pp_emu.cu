@@ -20,17 +20,13 @@ void pp_emu(const uint32_t* atlas, int S, float zFar, float ismPixelSize, uint16
             for (int r = 0; r < 64; r++)
                 for (int c = 0; c < 64; c++) s.L0[r * 64 + c] = atlas[(size_t)(gy0 + r) * A + gx0 + c];
 #define ALL(call) for (int tid = 0; tid < kThreads; tid++) { call; }
-            ALL(phase_luts(s, tid, zFar))
-            ALL(phase_empty1(s, tid, zFar, ismPixelSize, gx0, gy0))
+            ALL(phase_tables(s, tid, zFar, ismPixelSize, gx0, gy0))
             ALL(phase_pull1_classify(s, tid))
             ALL(phase_pull1_dense(s, tid, zFar, ismPixelSize, gx0, gy0))
             for (int level = 2; level <= 6; level++) ALL(phase_pull(s, tid, level, gx0, gy0))
-            for (int level = 5; level >= 1; level--) {
-                ALL(phase_push_thresholds(s, tid, level))
-                ALL(phase_push<false>(s, tid, level))
-            }
-            ALL(phase_push_thresholds(s, tid, 0))
-            ALL(phase_push<true>(s, tid, 0))
+            for (int level = 5; level >= 2; level--) ALL(phase_push_top(s, tid, level))
+            ALL(phase_push1(s, tid))
+            ALL(phase_push0(s, tid))
 #undef ALL
             for (int r = 0; r < 64; r++)
                 for (int c = 0; c < 64; c++) ism[(size_t)(gy0 + r) * A + gx0 + c] = (uint16_t)s.L0[r * 64 + c];
