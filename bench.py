@@ -492,6 +492,7 @@ def main():
     acc = {}
     for _ in range(min(args.steps, 50)):
         ctx.frame(job.rsm, job.light, job.mesh, gb, cam, params, stream=job.stream)
+        ctx.gi_blur(gb, cam, stream=job.stream)          # n1, the consumer right after the path (not part of the GI frame metric)
         torch.cuda.synchronize()
         for k, (ms, n) in ctx.timings().items():
             a = acc.setdefault(k, [0.0, 0, n])
@@ -566,6 +567,13 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_launch": pp_bytes, "kernel_ms": pp_ms, "share_of_step": pp_ms / ms_step}
 
+    blur_ms = stages.get("GI blur")
+    blur_bytes = float(W) * H * (4 + 4 + 4 + 16)        # packed GI + depth + normal in, fp32 RGBA out
+    roofline_blur = None if not blur_ms else {"kernel": "gi_blur_fused_kernel", "bound": "hbm", "achieved": blur_bytes / (blur_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                              "unit": "GB/s", "frac": blur_bytes / (blur_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                              "algorithmic_bytes_per_launch": blur_bytes, "kernel_ms": blur_ms,
+                                              "note": "n1 (gi_blur.frag x2 fused); runs after the GI frame, not inside the timed region"}
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
         cpu = CpuPort(wl)
@@ -586,7 +594,7 @@ def main():
            "image_sha256": digest, "single_gpu_image_sha256": single_digest, "matches_single_gpu_image": single_gpu_ok,
            "stage_ms": stages, "stage_launches": stage_launches, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
            "host_enqueue_us_per_frame": enqueue_us, "graph": frame_stats,
-           "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "scale_8k": scale_8k}
+           "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_blur": roofline_blur, "cpu_baseline": cpu_baseline, "scale_8k": scale_8k}
     if args.workload == "anim64":
         out["frames_per_s"] = frames_per_step / (ms_step * 1e-3)
     print(json.dumps(out), flush=True)

@@ -45,7 +45,7 @@ typedef enum {
     MLGI_E_INVALID = -1,      /* bad argument / configuration */
     MLGI_E_CUDA = -2,         /* CUDA runtime error (message has the cudaError string) */
     MLGI_E_NO_DEVICE = -3,    /* no usable CUDA device: the product has no CPU path */
-    MLGI_E_UNSUPPORTED = -4,  /* reference feature outside the hot path (scaled ISMs, non push-pull ...) */
+    MLGI_E_UNSUPPORTED = -4,  /* reference feature outside the hot path (non push-pull raster path, debug overlay ...) */
     MLGI_E_CAPACITY = -5,     /* a ctx buffer is too small for the input (e.g. max_points) */
     MLGI_E_ORDER = -6         /* a stage was called before the stage that produces its input */
 } mlgi_status;
@@ -73,9 +73,12 @@ typedef struct {
     float gi_intensity_factor;    /* 3000  */
     float vpl_clamping_value;     /* 0.001 */
     int   vpl_start_index;        /* 0     */
-    int   vpl_end_index;          /* N     (only affects normalisation: Q12) */
-    int   scale_isms;             /* 0     (1 -> MLGI_E_UNSUPPORTED) */
-    int   points_only_into_scaled_isms; /* 0 (1 -> MLGI_E_UNSUPPORTED) */
+    int   vpl_end_index;          /* N     (by itself only affects the normalisation: Q12) */
+    int   scale_isms;             /* 0     n3: vplCount = end - start larger ISMs fill the atlas (ISM of VPL i at index i - start;
+                                           ism.comp:38-39,124, final_gathering.comp:43-46 as rewritten by GIStage.cpp:430) */
+    int   points_only_into_scaled_isms; /* 0  n3: point buckets and their 16-VPL windows wrap inside [start, end) (ism.geom:43,57,
+                                           ism.comp:56-66). Both flags need an unsharded ctx (class_lo = 0, class_hi = 16). The
+                                           VPL records carry the ISM layout: pass the same params to every stage of a frame. */
     float tess_level_factor;      /* 2.0   */
     int   use_push_pull;          /* 1     (0 = legacy point-sprite raster path -> MLGI_E_UNSUPPORTED) */
     int   enable_shadowing;       /* 1     */

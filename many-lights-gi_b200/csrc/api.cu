@@ -95,7 +95,7 @@ struct mlgi_ctx {
     bool atlas_precleared = false;  // mlgi_frame clears the atlas on the side stream while the points are generated
     cudaEvent_t ev_clear = nullptr;
     uint32_t* gi_packed = nullptr;
-    float4* gi = nullptr; float4* gi_planar = nullptr; float4* gi_tmp = nullptr; float4* gi_blur = nullptr;
+    float4* gi = nullptr; float4* gi_planar = nullptr; float4* gi_blur = nullptr;
     unsigned long long* stats = nullptr;
     cudaTextureObject_t ism_tex = 0;      // ctx ISM atlas as an R16-unorm point-sampled texture
     // textures of caller-supplied ISM overrides, one per distinct pointer. A texture object may still be referenced by a
@@ -104,6 +104,7 @@ struct mlgi_ctx {
     struct OverrideTex { const uint16_t* ptr; cudaTextureObject_t tex; };
     std::vector<OverrideTex> override_tex;
     int use_texture = 1, tex_float_coord = 0;
+    IsmMode mode_vpl{}, mode_points{};   // the n3 knobs the VPL records / the point list were built with
     // multi-GPU exchange (mlgi_exchange_*): ONE IPC-exportable allocation per rank,
     //   [flags 256 B][class planes, parity 0][class planes, parity 1][G-buffer depth W*H*4][G-buffer normals W*H*4]
     // flags[0..7]: "planes of frame f written" per rank; flags[8..15]: "G-buffer slab of frame f pushed" per rank.
@@ -191,8 +192,9 @@ cudaError_t dalloc(mlgi_ctx* c, T** p, size_t count) {
 
 int check_params(mlgi_ctx* ctx, const mlgi_params* p) {
     if (!p) return fail(ctx, MLGI_E_INVALID, "params is NULL");
-    if (p->scale_isms || p->points_only_into_scaled_isms)
-        return fail(ctx, MLGI_E_UNSUPPORTED, "scaleISMs / pointsOnlyIntoScaledISMs are outside the hot path (SURVEY 8f n3)");
+    if (p->vpl_start_index < 0 || p->vpl_end_index > ctx->cfg.vpl_count) return fail(ctx, MLGI_E_INVALID, "need 0 <= vpl_start_index < vpl_end_index <= vpl_count");
+    if ((p->scale_isms || p->points_only_into_scaled_isms) && (ctx->cfg.class_lo != 0 || ctx->cfg.class_hi != 16))
+        return fail(ctx, MLGI_E_UNSUPPORTED, "scaleISMs / pointsOnlyIntoScaledISMs are not available in a class-sharded ctx (the ISM rows of a class are no longer contiguous)");
     if (!p->use_push_pull) return fail(ctx, MLGI_E_UNSUPPORTED, "usePushPull=false (legacy point-sprite raster path) is out of scope");
     if (p->show_vpl_positions) return fail(ctx, MLGI_E_UNSUPPORTED, "SHOW_VPL_POSITIONS debug overlay is out of scope");
     if (!p->use_interleaving) return fail(ctx, MLGI_E_UNSUPPORTED, "USE_INTERLEAVING=false is broken upstream (SURVEY A.9) and out of scope");
@@ -210,6 +212,24 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
+
+// n3: ism.geom:42-45 / ism.comp:36-39 / final_gathering.comp:42-46 / ImperfectShadowmap.cpp:187-191
+IsmMode ism_mode(const mlgi_ctx* ctx, const mlgi_params* p) {
+    IsmMode m;
+    m.N = ctx->cfg.vpl_count;
+    m.vpl_start = p->vpl_start_index;
+    m.vpl_count = p->vpl_end_index - p->vpl_start_index;
+    m.scale = p->scale_isms != 0; m.points_only = p->points_only_into_scaled_isms != 0;
+    m.sampled = m.points_only ? m.vpl_count : m.N;
+    m.ism_count = m.scale ? m.vpl_count : m.N;
+    m.S2 = ism_indices_1d(m.ism_count);
+    m.px = float(ctx->A / m.S2);
+    return m;
+}
+bool same_mode(const IsmMode& a, const IsmMode& b) {
+    return a.scale == b.scale && a.points_only == b.points_only && a.S2 == b.S2 && a.sampled == b.sampled && a.ism_count == b.ism_count &&
+           (a.vpl_start == b.vpl_start || (!a.scale && !a.points_only));
+}
 
 struct StageTimer {
     mlgi_ctx* c; int id; cudaStream_t st; unsigned long long l0;
@@ -308,7 +328,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     // light_lists ([clusters][16][L+1] uint16: 1 GB at 8K / 16384 VPLs) is allocated by the first clustered cull (ensure_clustered)
     ALLOC(tile_lists, (size_t)ctx->TX * ctx->TY * 16 * (ctx->L + 1));
     ALLOC(tile_weight, (size_t)ctx->TX * ctx->TY); ALLOC(tile_order, (size_t)ctx->TX * ctx->TY);
-    ALLOC(gi, WH); ALLOC(gi_planar, (size_t)(cfg->class_hi - cfg->class_lo) * PW * PH); ALLOC(gi_tmp, WH); ALLOC(gi_blur, WH);
+    ALLOC(gi, WH); ALLOC(gi_planar, (size_t)(cfg->class_hi - cfg->class_lo) * PW * PH); ALLOC(gi_blur, WH);
     ALLOC(stats, 2);
     if (cfg->gi_packed) ALLOC(gi_packed, WH);
     ALLOC(st_rsm_diffuse, RS); ALLOC(st_rsm_normal, RS); ALLOC(st_rsm_depth, RS); ALLOC(st_depth, WH); ALLOC(st_normal, WH);
@@ -398,9 +418,9 @@ MLGI_API int mlgi_vpl_process(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_cam
     mat_inverse(bpv, inv);
     StageTimer t(ctx, T_VPLP, st);
     ctx->launches += launch_vpl_process(*rsm, ctx->cfg.rsm_width, ctx->cfg.rsm_height, ctx->cfg.vpl_count, to_mat4(inv), p->light_intensity,
-                                        p->shuffle_lights, ctx->shuffle, ctx->S, ctx->vpl, ctx->packed, ctx->records, st);
+                                        p->shuffle_lights, ctx->shuffle, ism_mode(ctx, p), ctx->vpl, ctx->packed, ctx->records, st);
     CK(cudaGetLastError());
-    ctx->have_vpl = true;
+    ctx->have_vpl = true; ctx->mode_vpl = ism_mode(ctx, p);
     return MLGI_OK;
 }
 
@@ -422,10 +442,10 @@ MLGI_API int mlgi_ism_points(mlgi_ctx* ctx, const mlgi_mesh* mesh, const mlgi_pa
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_POINTS, st);
-    ctx->launches += launch_point_generate(*mesh, ctx->cfg.vpl_count, p->tess_level_factor, ctx->cfg.max_points, ctx->points_unsorted,
+    ctx->launches += launch_point_generate(*mesh, ism_mode(ctx, p), p->tess_level_factor, ctx->cfg.max_points, ctx->points_unsorted,
                                            ctx->point_bucket, ctx->counters + 1, st);
     CK(cudaGetLastError());
-    ctx->have_points = true; ctx->grouped_valid = false;
+    ctx->have_points = true; ctx->grouped_valid = false; ctx->mode_points = ism_mode(ctx, p);
     return MLGI_OK;
 }
 
@@ -456,10 +476,12 @@ MLGI_API int mlgi_ism_splat(mlgi_ctx* ctx, const mlgi_params* p, void* stream) {
     int rc = check_params(ctx, p);
     if (rc) return rc;
     if (!ctx->have_vpl || !ctx->have_points) return fail(ctx, MLGI_E_ORDER, "mlgi_ism_splat needs mlgi_vpl_process and mlgi_ism_points first");
+    const IsmMode mode = ism_mode(ctx, p);
+    if (!same_mode(mode, ctx->mode_vpl)) return fail(ctx, MLGI_E_ORDER, "the VPL records were built with other scaleISMs / VPL-range settings: call mlgi_vpl_process with these params first");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_SPLAT, st);
     ctx->launches += launch_splat(ctx->points_unsorted, ctx->point_bucket, ctx->counters + 1, ctx->cfg.max_points, ctx->records,
-                                  ctx->cfg.vpl_count, ctx->S, p->z_far, ctx->atlas, ctx->ism_lo, ctx->ism_hi, clear, st);
+                                  mode, ctx->S, p->z_far, ctx->atlas, ctx->ism_lo, ctx->ism_hi, clear, st);
     CK(cudaGetLastError());
     ctx->have_atlas = true;
     return MLGI_OK;
@@ -474,7 +496,7 @@ MLGI_API int mlgi_ism_pullpush(mlgi_ctx* ctx, const uint32_t* atlas_override, co
     if (!atlas_override && !ctx->have_atlas) return fail(ctx, MLGI_E_ORDER, "mlgi_ism_pullpush needs mlgi_ism_splat first (or an atlas override)");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_PULLPUSH, st);
-    ctx->launches += launch_pullpush(atlas_override ? atlas_override : ctx->atlas, ctx->S, p->z_far, ctx->ism,
+    ctx->launches += launch_pullpush(atlas_override ? atlas_override : ctx->atlas, ctx->S, p->z_far, ism_mode(ctx, p).px, ctx->ism,
                                      ctx->ism_lo, ctx->ism_hi, st);
     CK(cudaGetLastError());
     ctx->have_ism = true;
@@ -549,6 +571,8 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     int rc = check_params(ctx, p);
     if (rc) return rc;
     if (!ctx->have_vpl) return fail(ctx, MLGI_E_ORDER, "mlgi_final_gather needs mlgi_vpl_process first");
+    if (p->enable_shadowing && !same_mode(ism_mode(ctx, p), ctx->mode_vpl))
+        return fail(ctx, MLGI_E_ORDER, "the VPL records were built with other scaleISMs / VPL-range settings: call mlgi_vpl_process with these params first");
     if (p->enable_shadowing && !ism_override && !ctx->have_ism) return fail(ctx, MLGI_E_ORDER, "shadowing needs mlgi_ism_pullpush first (or an ISM override)");
     if (p->cull_mode == MLGI_CULL_CLUSTERED && !ctx->have_clustered) return fail(ctx, MLGI_E_ORDER, "clustered gathering needs mlgi_cull_clustered first");
     if (p->cull_mode == MLGI_CULL_TILED && !ctx->have_tiled) return fail(ctx, MLGI_E_ORDER, "tiled gathering needs mlgi_cull_tiled first");
@@ -827,8 +851,9 @@ MLGI_API int mlgi_gi_blur(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_came
     if (!ctx->have_gi) return fail(ctx, MLGI_E_ORDER, "mlgi_gi_blur needs mlgi_final_gather first");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer t(ctx, T_BLUR, st);
-    ctx->launches += launch_gi_blur(ctx->gi, gb->depth, gb->face_normal, ctx->cfg.width, ctx->cfg.height, cam->proj[10], cam->proj[14],
-                                    ctx->gi_tmp, ctx->gi_blur, st);
+    // packed-only contexts blur the GL_R11F_G11F_B10F image -- which is what the reference blurs (its giBuffer has that format)
+    ctx->launches += launch_gi_blur(ctx->gi, ctx->cfg.gi_packed == 2 ? ctx->gi_packed : nullptr, gb->depth, gb->face_normal, ctx->cfg.width,
+                                    ctx->cfg.height, cam->proj[10], cam->proj[14], ctx->gi_blur, st);
     CK(cudaGetLastError());
     ctx->have_blur = true;
     return MLGI_OK;
@@ -934,6 +959,7 @@ static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* 
         ctx->graph_replays++;
         // host-side stage bookkeeping of a replayed frame (what the stage calls set when they are issued directly)
         ctx->have_vpl = ctx->have_points = ctx->have_atlas = ctx->have_ism = ctx->have_gi = true;
+        ctx->mode_vpl = ctx->mode_points = ism_mode(ctx, p);
         ctx->grouped_valid = false; ctx->have_blur = false; ctx->atlas_precleared = false;
         if (p->cull_mode == MLGI_CULL_CLUSTERED) ctx->have_clustered = true;
         if (p->cull_mode == MLGI_CULL_TILED) { ctx->have_tiled = true; ctx->tile_order_valid = ctx->fg_sorted != 0; }

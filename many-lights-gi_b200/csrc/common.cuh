@@ -22,10 +22,24 @@ struct Mat4 { float m[16]; };
 // Hoisted per-VPL record used by the gathering kernel (80 B, 5 x float4, in the order the kernel
 // consumes it; lookAtRH rows s,u from ism_utils.glsl:5-13 and the atlas tile origin :35-38 are pure
 // functions of the VPL):
-//   r0 = (-pos.x, -pos.y, -pos.z, nrm.x)   r1 = (nrm.y, nrm.z, 32 s.x, 32 s.y)   r2 = (32 s.z, 32 u.x, 32 u.y, 32 u.z)
-//   r3 = (col.r, col.g, col.b, Cx)         r4 = (Cy, 0, 0, 0)
-//   Cx = 1.5*2^23 + tile_x*64 + 32, Cy likewise: round-down FMA onto it yields floor(texel coordinate).
+//   r0 = (-pos.x, -pos.y, -pos.z, nrm.x)   r1 = (nrm.y, nrm.z, h s.x, h u.x)   r2 = (h s.y, h u.y, h s.z, h u.z)
+//   r3 = (col.r, col.g, col.b, 0)          r4 = (Cx, Cy, ox, oy)
+//   h = half the ISM edge in texels (32 by default; IsmMode::px / 2), (ox, oy) = ISM tile origin + h in texels,
+//   Cx = 1.5*2^23 + ox, Cy likewise: a round-down FMA onto it yields floor(texel coordinate).
 struct VplRecord { float4 r[5]; };
+
+// n3: the scaled-ISM experiment knobs (ism.geom:37-46, ism.comp:31-40, final_gathering.comp:40-46), resolved on the host.
+// Defaults: sampled = ism_count = N, S2 = ism_indices_1d(N), px = 64.
+struct IsmMode {
+    int N;              // totalVplCount
+    int vpl_start;      // vplStartIndex
+    int vpl_count;      // vplEndIndex - vplStartIndex
+    int sampled;        // sampledVplCount = pointsOnlyIntoScaledISMs ? vplCount : totalVplCount   (number of point buckets)
+    int ism_count;      // ismCount = scaleISMs ? vplCount : totalVplCount
+    int S2;             // ismIndices1d(ismCount): ISMs per atlas row in this mode
+    int scale, points_only;
+    float px;           // ISM edge in texels = atlas edge / S2 (ImperfectShadowmap.cpp:187-191); a power of two
+};
 
 struct DevLists {              // what the gathering kernel needs to find a pixel's list
     const uint16_t* light_list_ids;  // clustered: [16][Y][X]
@@ -152,10 +166,10 @@ __device__ __forceinline__ uint32_t pack_r11g11b10(float r, float g, float b) {
 struct SliceTable { float b[17]; };
 
 int launch_vpl_process(const mlgi_rsm& rsm, int rsm_w, int rsm_h, int N, const Mat4& inv_biased_light_vp,
-                       float lightIntensity, int shuffle, const int32_t* shuffled, int S,
+                       float lightIntensity, int shuffle, const int32_t* shuffled, const IsmMode& mode,
                        float* vpl, float* packed, VplRecord* records, cudaStream_t st);
 
-int launch_point_generate(const mlgi_mesh& mesh, int N, float tessLevelFactor, int max_points, float4* points, uint32_t* point_bucket,
+int launch_point_generate(const mlgi_mesh& mesh, const IsmMode& mode, float tessLevelFactor, int max_points, float4* points, uint32_t* point_bucket,
                           uint32_t* generated, cudaStream_t st);
 // inspection / injection helpers: bucket-grouped view <-> (point, bucket id) list
 int launch_group_points(const float4* points, const uint32_t* point_bucket, const uint32_t* generated, int max_points, int N,
@@ -163,9 +177,9 @@ int launch_group_points(const float4* points, const uint32_t* point_bucket, cons
 int launch_bucket_expand(const uint32_t* bucket_start, int N, uint32_t* point_bucket, cudaStream_t st);
 void launch_atlas_clear(uint32_t* atlas, int S, int vpl_lo, int vpl_hi, cudaStream_t st);
 int launch_splat(const float4* points, const uint32_t* point_bucket, const uint32_t* generated, int max_points, const VplRecord* records,
-                 int N, int S, float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st);
+                 const IsmMode& mode, int S, float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st);
 int launch_sqrt_thresholds(const float* rs, int n, float* out, cudaStream_t st);
-int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st);
+int launch_pullpush(const uint32_t* atlas, int S, float zFar, float ism_pixel_size, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st);
 
 int launch_clustering(const float* depth, int W, int H, float projA, float projB, const SliceTable& tab,
                       uint32_t* tile_masks, uint32_t* compact_ids, uint16_t* light_list_ids, uint32_t* num_used,
@@ -209,8 +223,9 @@ struct GatherArgs {
 int launch_final_gather(const GatherArgs& a, cudaStream_t st);
 int launch_composite_ambient(const float4* gi, const uint32_t* diffuse_rgba8, const float* occlusion, int n, float exposure,
                              uint32_t* out_srgb8, cudaStream_t st);
-int launch_gi_blur(const float4* gi, const float* depth, const uint32_t* face_normal, int W, int H, float projA,
-                   float projB, float4* tmp, float4* out, cudaStream_t st);
+// gi (fp32 raster) or gi_packed (GL_R11F_G11F_B10F raster, takes precedence when not null)
+int launch_gi_blur(const float4* gi, const uint32_t* gi_packed, const float* depth, const uint32_t* face_normal, int W, int H, float projA,
+                   float projB, float4* out, cudaStream_t st);
 float measure_fp32_peak_tflops(int device, cudaStream_t st);   // FFMA micro-benchmark: the FP32-pipe roofline denominator
 int launch_planar_to_raster(const float4* planar, int W, int H, int class_lo, int class_hi, float4* raster, cudaStream_t st);
 // one kernel = signal + wait + (pull over NVLink) + de-interleave; see gather.cu

@@ -21,7 +21,7 @@ static constexpr unsigned FULL = 0xFFFFFFFFu;
 // =====================================================================================
 __global__ void vpl_process_kernel(const uint32_t* __restrict__ diffuse, const uint32_t* __restrict__ normal10,
                                    const float* __restrict__ depth, int rsm_w, int rsm_h, int N, Mat4 inv,
-                                   float lightIntensity, int shuffle, const int32_t* __restrict__ shuffled, int S,
+                                   float lightIntensity, int shuffle, const int32_t* __restrict__ shuffled, IsmMode mode,
                                    float* __restrict__ vpl, float* __restrict__ packed, VplRecord* __restrict__ records) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint32_t)N) return;
@@ -51,21 +51,28 @@ __global__ void vpl_process_kernel(const uint32_t* __restrict__ diffuse, const u
     float3 up = f3(0.0f, 1.0f, 0.01f);
     float3 s = normalize3(cross3(un, up));
     float3 u = cross3(s, un);
-    int ty = (int)slot / S, tx = (int)slot - ty * S;
+    // ISM tile of this VPL: ism_utils.glsl:35-36 with ismIndex = slot - (scaleISMs ? vplStartIndex : 0) (ism.comp:124,
+    // final_gathering.comp:44,120) in a layout of S2 x S2 ISMs; the int() truncations are the shader's (a slot outside the
+    // scaled range lands on a negative or out-of-atlas tile, as it does in the reference)
+    const float ismIndex = mode.scale ? float(slot) - float(mode.vpl_start) : float(slot);
+    const float yy = float(f2i(ismIndex / float(mode.S2)));
+    const float tx = float(f2i(ismIndex - yy * float(mode.S2))), ty = float(f2i(yy));
+    const float h = mode.px * 0.5f;                                   // half the ISM edge: 32 by default (power of two: exact scaling)
+    const float ox = tx * mode.px + h, oy = ty * mode.px + h;
     VplRecord r;
     r.r[0] = make_float4(-w.x, -w.y, -w.z, un.x);
-    r.r[1] = make_float4(un.y, un.z, 32.0f * s.x, 32.0f * u.x);     // rows pre-scaled by half the ISM size (exact), paired by component
-    r.r[2] = make_float4(32.0f * s.y, 32.0f * u.y, 32.0f * s.z, 32.0f * u.z);
+    r.r[1] = make_float4(un.y, un.z, h * s.x, h * u.x);             // rows pre-scaled by half the ISM size (exact), paired by component
+    r.r[2] = make_float4(h * s.y, h * u.y, h * s.z, h * u.z);
     r.r[3] = make_float4(col.x, col.y, col.z, 0.0f);
-    r.r[4] = make_float4(12582912.0f + float(tx * 64 + 32), 12582912.0f + float(ty * 64 + 32), float(tx * 64 + 32), float(ty * 64 + 32));
+    r.r[4] = make_float4(12582912.0f + ox, 12582912.0f + oy, ox, oy);
     records[slot] = r;
 }
 
 int launch_vpl_process(const mlgi_rsm& rsm, int rsm_w, int rsm_h, int N, const Mat4& inv, float lightIntensity,
-                       int shuffle, const int32_t* shuffled, int S, float* vpl, float* packed, VplRecord* records,
+                       int shuffle, const int32_t* shuffled, const IsmMode& mode, float* vpl, float* packed, VplRecord* records,
                        cudaStream_t st) {
     vpl_process_kernel<<<(N + 63) / 64, 64, 0, st>>>(rsm.diffuse, rsm.face_normal, rsm.depth, rsm_w, rsm_h, N, inv,
-                                                    lightIntensity, shuffle, shuffled, S, vpl, packed, records);
+                                                    lightIntensity, shuffle, shuffled, mode, vpl, packed, records);
     return 1;
 }
 
@@ -134,11 +141,12 @@ __device__ __forceinline__ float random3(float3 v) {
 // (launch_group_points, used by the inspection API).
 __global__ void __launch_bounds__(256) point_generate_kernel(const float* __restrict__ verts, const float* __restrict__ normals,
                                                              const uint32_t* __restrict__ indices, const uint32_t* __restrict__ prim_id,
-                                                             int ntri, int N, float tf, int max_points, float4* __restrict__ points,
-                                                             uint32_t* __restrict__ point_bucket, uint32_t* __restrict__ generated) {
+                                                             int ntri, int N /* sampledVplCount: buckets */, int ismCount, float tf, int max_points,
+                                                             float4* __restrict__ points, uint32_t* __restrict__ point_bucket,
+                                                             uint32_t* __restrict__ generated) {
     const int lane = threadIdx.x & 31;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
-    const float sqrtN = sqrtf(float(N));
+    const float sqrtN = sqrtf(float(ismCount));                                           // ism.geom:63
     for (int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; group * 32 < ntri; group += warps_total) {
         const int t = group * 32 + lane;
         int n_mine = 0;
@@ -207,13 +215,13 @@ __global__ void __launch_bounds__(256) point_generate_kernel(const float* __rest
     }
 }
 
-int launch_point_generate(const mlgi_mesh& mesh, int N, float tf, int max_points, float4* points, uint32_t* point_bucket,
+int launch_point_generate(const mlgi_mesh& mesh, const IsmMode& mode, float tf, int max_points, float4* points, uint32_t* point_bucket,
                           uint32_t* generated, cudaStream_t st) {
     cudaMemsetAsync(generated, 0, sizeof(uint32_t), st);
     const int warps_needed = (mesh.num_triangles + 31) / 32;
     const int grid = std::max(1, std::min(148 * 8, (warps_needed + 7) / 8));
-    point_generate_kernel<<<grid, 256, 0, st>>>(mesh.vertices, mesh.normals, mesh.indices, mesh.prim_id, mesh.num_triangles, N, tf,
-                                                max_points, points, point_bucket, generated);
+    point_generate_kernel<<<grid, 256, 0, st>>>(mesh.vertices, mesh.normals, mesh.indices, mesh.prim_id, mesh.num_triangles, mode.sampled,
+                                                mode.ism_count, tf, max_points, points, point_bucket, generated);
     return 1;
 }
 
@@ -283,13 +291,16 @@ int launch_bucket_expand(const uint32_t* bucket_start, int N, uint32_t* point_bu
 // =====================================================================================
 __global__ void __launch_bounds__(256) splat_kernel(const float4* __restrict__ points, const uint32_t* __restrict__ point_bucket,
                                                     const uint32_t* __restrict__ generated, int max_points,
-                                                    const VplRecord* __restrict__ records, int N, int S, float zFar,
+                                                    const VplRecord* __restrict__ records, IsmMode mode, int S, float zFar,
                                                     uint32_t* __restrict__ atlas, int vpl_lo, int vpl_hi) {
     const uint32_t P = min(generated[0], (uint32_t)max_points);
     const int lane = threadIdx.x & 31, q = lane & 3;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    const float fA = float(64 * S);
-    const float invS = 1.0f / float(S);                        // S is a power of two: x * invS == x / S exactly
+    const int N = mode.N;
+    const float fA = float(64 * S);                            // atlas edge (fixed by totalVplCount)
+    const float fS2 = float(mode.S2);
+    const float invS = 1.0f / fS2;                             // S2 is a power of two: x * invS == x / S2 exactly
+    const float inv_h = 2.0f / mode.px;                        // the record rows carry half the ISM edge (a power of two)
     const int A = 64 * S;
     const bool sharded = vpl_hi - vpl_lo < N;
     for (uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8u; w0 < P; w0 += warps_total * 8u) {   // warp-uniform
@@ -316,7 +327,8 @@ __global__ void __launch_bounds__(256) splat_kernel(const float4* __restrict__ p
 #pragma unroll
             for (int k = 0; k < 4; k++) {                          // :94-107, this lane's quarter of the window
                 const int i = 4 * q + k;
-                const int id = (b + i) % N;
+                int id = (b + i) % N;                                                            // ism.comp:61-62
+                if (mode.points_only) id = id % mode.vpl_count + mode.vpl_start;                  // :63-66
                 const float4 r0 = __ldg(&records[id].r[0]);
                 const float2 r1 = __ldg(reinterpret_cast<const float2*>(&records[id].r[1]));
                 float3 rel = sub3(position, f3(-r0.x, -r0.y, -r0.z));
@@ -329,16 +341,17 @@ __global__ void __launch_bounds__(256) splat_kernel(const float4* __restrict__ p
         for (int k = 0; k < q; k++) survivors &= survivors - 1;   // lane q takes the q-th survivor in window order (:112-137)
         if (survivors != 0) {
             const int wi = __ffs(survivors) - 1;
-            const int gid = (b + wi) % N;
+            int gid = (b + wi) % N;
+            if (mode.points_only) gid = gid % mode.vpl_count + mode.vpl_start;
             const bool owned = gid >= vpl_lo && gid < vpl_hi;   // multi-GPU shard: only this rank's ISMs
             if (!owned) continue;
             const float4 r0 = __ldg(&records[gid].r[0]), r1 = __ldg(&records[gid].r[1]), r2 = __ldg(&records[gid].r[2]);
             const float3 wpos = f3(-r0.x, -r0.y, -r0.z), wnrm = f3(r0.w, r1.x, r1.y);
-            const float3 ws = f3(r1.z * 0.03125f, r2.x * 0.03125f, r2.z * 0.03125f);   // s = normalize(cross(nrm, up))  ism_utils.glsl:5-13
-            const float3 wu = f3(r1.w * 0.03125f, r2.y * 0.03125f, r2.w * 0.03125f);   // u = cross(s, nrm)
-            const float ismIndex = float(gid);                     // ism_utils.glsl:35-36
-            const float yy = float(f2i(ismIndex / float(S)));
-            const float tile_x = float(f2i(ismIndex - yy * float(S))), tile_y = float(f2i(yy));
+            const float3 ws = f3(r1.z * inv_h, r2.x * inv_h, r2.z * inv_h);   // s = normalize(cross(nrm, up))  ism_utils.glsl:5-13
+            const float3 wu = f3(r1.w * inv_h, r2.y * inv_h, r2.w * inv_h);   // u = cross(s, nrm)
+            const float ismIndex = mode.scale ? float(gid) - float(mode.vpl_start) : float(gid);   // ism.comp:124
+            const float yy = float(f2i(ismIndex / fS2));           // ism_utils.glsl:35-36
+            const float tile_x = float(f2i(ismIndex - yy * fS2)), tile_y = float(f2i(yy));
             float3 rel = sub3(position, wpos);
             float dist = len3(rel);
             // paraboloid_project(rel, dist, nrm, zFar, id, S, true)  ism_utils.glsl:15-40
@@ -376,9 +389,9 @@ void launch_atlas_clear(uint32_t* atlas, int S, int vpl_lo, int vpl_hi, cudaStre
     cudaMemsetAsync(atlas + (size_t)ty0 * 64 * A, 0xFF, (size_t)(ty1 - ty0) * 64 * A * sizeof(uint32_t), st);   // ImperfectShadowmap.cpp:212
 }
 int launch_splat(const float4* points, const uint32_t* point_bucket, const uint32_t* generated, int max_points, const VplRecord* records,
-                 int N, int S, float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st) {
+                 const IsmMode& mode, int S, float zFar, uint32_t* atlas, int vpl_lo, int vpl_hi, bool clear, cudaStream_t st) {
     if (clear) launch_atlas_clear(atlas, S, vpl_lo, vpl_hi, st);
-    splat_kernel<<<148 * 8, 256, 0, st>>>(points, point_bucket, generated, max_points, records, N, S, zFar, atlas, vpl_lo, vpl_hi);
+    splat_kernel<<<148 * 8, 256, 0, st>>>(points, point_bucket, generated, max_points, records, mode, S, zFar, atlas, vpl_lo, vpl_hi);
     return 1;
 }
 
@@ -397,12 +410,14 @@ int launch_splat(const float4* points, const uint32_t* point_bucket, const uint3
 #endif
 
 __global__ void __launch_bounds__(pp::kThreads, PP_MINB) pullpush_kernel(const uint32_t* __restrict__ atlas, int S, float zFar,
-                                                                         uint16_t* __restrict__ ism, int tile_y0) {
+                                                                         float ismPixelSize, uint16_t* __restrict__ ism, int tile_y0) {
     __shared__ __align__(16) pp::Shared s;
     const int A = 64 * S;
     const int gx0 = blockIdx.x * 64, gy0 = (blockIdx.y + tile_y0) * 64;
     const int tid = threadIdx.x;
-    const float ismPixelSize = 64.0f;          // A / S  (ImperfectShadowmap.cpp:187-191)
+    // ismPixelSize = A / ismIndices1d(ismCount) (ImperfectShadowmap.cpp:187-191): 64 unless scaleISMs. The 64x64 tile stays the
+    // unit either way: pull blocks never straddle it, and push.comp:83 masks coarse taps across 64-texel borders whatever
+    // the ISM size (an upstream inconsistency of the scaled mode, reproduced as it is).
 
     // ---- load the 64x64 R32UI tile: 1024 x uint4, coalesced 256 B rows ----
     uint4 v[4];
@@ -460,10 +475,10 @@ int launch_sqrt_thresholds(const float* rs, int n, float* out, cudaStream_t st) 
     return 1;
 }
 
-int launch_pullpush(const uint32_t* atlas, int S, float zFar, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st) {
+int launch_pullpush(const uint32_t* atlas, int S, float zFar, float ism_pixel_size, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st) {
     const int ty0 = vpl_lo / S, ty1 = (vpl_hi + S - 1) / S;
     dim3 grid(S, ty1 - ty0);
-    pullpush_kernel<<<grid, pp::kThreads, 0, st>>>(atlas, S, zFar, ism, ty0);
+    pullpush_kernel<<<grid, pp::kThreads, 0, st>>>(atlas, S, zFar, ism_pixel_size, ism, ty0);
     return 1;
 }
 

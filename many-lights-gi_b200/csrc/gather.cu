@@ -286,6 +286,30 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
     // ---- epilogue: result = acc * giIntensityFactor / vplCount * 16  (:132) ----
     const int PW = (a.W + 3) >> 2, PH = (a.H + 3) >> 2;
     const size_t pboff = a.frame_ctr ? (size_t)((*a.frame_ctr + 1u) & 1u) * a.peer_parity_stride : 0;
+    // Multi-GPU exchange, packed planes, CTA fully inside the image: the CTA's 16x16 plane entries are staged in shared memory
+    // (the record buffer is free by now) and written as 16 rows of 64 contiguous bytes with 16-byte stores -- to this rank's
+    // exchange region (pull mode) or to every rank's region over NVLink (push mode: the transfer overlaps the gathering of
+    // the remaining tiles). 4 store instructions per thread and peer instead of 2 scattered 4-byte stores per pixel and peer.
+    const bool rows_path = a.num_peers && a.peer_packed && !a.out_raster && !a.out_packed && (PW & 3) == 0 &&
+                           tile_x * kTile + kTile <= a.W && tile_y * kTile + kTile <= a.H;
+    if (rows_path) {
+        uint32_t* s_out = reinterpret_cast<uint32_t*>(srec);
+        __syncthreads();                                        // every warp is done with the staged records
+#pragma unroll
+        for (int k = 0; k < NPX; k++) {
+            const PixelPair& pp = px[k >> 1];
+            const float r = (k & 1) ? pp.ar.y : pp.ar.x, g = (k & 1) ? pp.ag.y : pp.ag.x, b = (k & 1) ? pp.ab.y : pp.ab.x;
+            s_out[(pj0 + 4 * k) * 16 + pi] = pack_r11g11b10(r * a.giScale, g * a.giScale, b * a.giScale);
+        }
+        __syncthreads();
+        const size_t row0 = ((size_t)cls * PH + (size_t)tile_y * 16) * PW + (size_t)tile_x * 16;     // plane entry of the CTA's corner
+        for (int item = threadIdx.x; item < a.num_peers * 64; item += THREADS) {
+            const int g = item >> 6, row = (item >> 2) & 15, quad = item & 3;
+            const uint4 v = *reinterpret_cast<const uint4*>(s_out + row * 16 + quad * 4);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(static_cast<char*>(a.peer_planar[g]) + pboff) + row0 + (size_t)row * PW + quad * 4;
+            *reinterpret_cast<uint4*>(dst) = v;
+        }
+    } else {
 #pragma unroll
     for (int k = 0; k < NPX; k++) {
         if (!valid[k]) continue;
@@ -297,8 +321,7 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
         if (a.out_packed) a.out_packed[(size_t)sy[k] * a.W + sx[k]] = pack_r11g11b10(o.x, o.y, o.z);
         if (a.out_planar_packed) a.out_planar_packed[((size_t)cls * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = pack_r11g11b10(o.x, o.y, o.z);
         if (a.num_peers) {
-            // multi-GPU exchange: this pixel's plane entry goes to the exchange buffer(s) directly -- in
-            // push mode to every rank's buffer, so the NVLink transfer overlaps the gathering of the remaining tiles
+            // general shapes: this pixel's plane entry goes to the exchange region(s) directly
             const size_t off = ((size_t)cls * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2);
             if (a.peer_packed) {
                 const uint32_t v = pack_r11g11b10(o.x, o.y, o.z);
@@ -309,6 +332,7 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
                 for (int g = 0; g < a.num_peers; g++) reinterpret_cast<float4*>(static_cast<char*>(a.peer_planar[g]) + pboff)[off] = o;
             }
         }
+    }
     }
     if (STATS) {
 #pragma unroll
@@ -543,48 +567,97 @@ float measure_fp32_peak_tflops(int device, cudaStream_t st) {
 }
 
 // =====================================================================================
-// n1: gi_blur.frag:24-72, two separable 7-tap passes (GIStage.cpp:308-344). Out-of-image taps
-// are skipped (texelFetch outside the image is undefined in GL; same choice as the oracle).
+// n1: gi_blur.frag:24-72, the two separable 7-tap passes of GIStage::blur (GIStage.cpp:308-344) as ONE kernel. A CTA owns a
+// 32x16-pixel tile: it stages the tile plus a 3-pixel halo (GI colour, linearised depth, decoded normal: each texel is
+// fetched and decoded once instead of once per tap and pass) in shared memory, runs the horizontal pass for the tile rows
+// and the vertical halo into shared memory, then the vertical pass. HBM traffic per pixel: 16 B (fp32 GI) or 4 B
+// (GL_R11F_G11F_B10F GI, the reference's giBuffer format) + 4 B depth + 4 B normal in, 16 B out -- the intermediate image of
+// the two-pass form (16 B written + 7 x 16 B read per pixel) never leaves the SM. Out-of-image taps are skipped (texelFetch
+// outside the image is undefined in GL; same choice as the oracle).
 // =====================================================================================
-__global__ void gi_blur_kernel(const float4* __restrict__ gi, const float* __restrict__ depth, const uint32_t* __restrict__ face_normal,
-                               int W, int H, float projA, float projB, int dxs, int dys, float4* __restrict__ out) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= W || y >= H) return;
-    auto lin = [&](float d) { return -projB / (projA + (2.0f * d - 1.0f)); };          // reprojection.glsl:6-14
-    auto nrm = [&](uint32_t n10) {
-        return make_float3(float(n10 & 0x3FFu) * (2.0f / 1023.0f) - 1.0f, float((n10 >> 10) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f,
-                           float((n10 >> 20) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f);
-    };
-    const size_t c = (size_t)y * W + x;
-    const float d = lin(depth[c]);                              // :58
-    const float3 Nn = nrm(face_normal[c]);                      // :59
-    float4 g0 = gi[c];
-    float3 acc = make_float3(g0.x, g0.y, g0.z);                 // :60
-    float factorAcc = 1.0f;
-#pragma unroll
-    for (int sgn = -1; sgn <= 1; sgn += 2)
-#pragma unroll
-        for (int i = 1; i <= 3; i++) {                          // :63-69
-            const int tx = x + sgn * dxs * i, ty = y + sgn * dys * i;
-            if (tx < 0 || ty < 0 || tx >= W || ty >= H) continue;
-            const size_t t = (size_t)ty * W + tx;
-            const float4 g = gi[t];
-            const float3 ns = nrm(face_normal[t]);
-            const float normalFactor = 1.0f - fmaxf(0.0f, Nn.x * ns.x + Nn.y * ns.y + Nn.z * ns.z);   // :44
-            const float depthDiff = lin(depth[t]) - d;
-            const float nd = normalFactor * 5.0f;
-            const float w = fmaxf(0.0f, (3.0f - float(i) + 1.0f) / 4.0f - depthDiff * depthDiff - nd * nd);   // :24-35
-            factorAcc += w;
-            acc.x += g.x * w; acc.y += g.y * w; acc.z += g.z * w;
-        }
-    out[c] = make_float4(acc.x / factorAcc, acc.y / factorAcc, acc.z / factorAcc, 0.0f);   // :71
+namespace blur {
+constexpr int TW = 32, TH = 16, R = 3, SW = TW + 2 * R, SH = TH + 2 * R;
 }
-int launch_gi_blur(const float4* gi, const float* depth, const uint32_t* face_normal, int W, int H, float projA, float projB,
-                   float4* tmp, float4* out, cudaStream_t st) {
-    dim3 grid((W + 255) / 256, H);
-    gi_blur_kernel<<<grid, 256, 0, st>>>(gi, depth, face_normal, W, H, projA, projB, 1, 0, tmp);   // GIStage.cpp:427 DIRECTION (1,0)
-    gi_blur_kernel<<<grid, 256, 0, st>>>(tmp, depth, face_normal, W, H, projA, projB, 0, 1, out);  // :431 DIRECTION (0,1)
-    return 2;
+template <bool PACKED>
+__global__ void __launch_bounds__(256) gi_blur_fused_kernel(const float4* __restrict__ gi, const uint32_t* __restrict__ gi_packed,
+                                                            const float* __restrict__ depth, const uint32_t* __restrict__ face_normal,
+                                                            int W, int H, float projA, float projB, float4* __restrict__ out) {
+    using namespace blur;
+    __shared__ float s_rgb[3][SH][SW], s_d[SH][SW], s_n[3][SH][SW];
+    __shared__ float s_tmp[3][SH][TW];
+    const int x0 = blockIdx.x * TW - R, y0 = blockIdx.y * TH - R;
+    for (int q = threadIdx.x; q < SW * SH; q += 256) {
+        const int lx = q % SW, ly = q / SW, x = x0 + lx, y = y0 + ly;
+        float r = 0.0f, g = 0.0f, b = 0.0f, d = 0.0f, nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (x >= 0 && y >= 0 && x < W && y < H) {
+            const size_t t = (size_t)y * W + x;
+            if (PACKED) {
+                const uint32_t v = __ldg(gi_packed + t);
+                r = __uint_as_float(unpack_ufloat_bits<6>(v & 0x7FFu)); g = __uint_as_float(unpack_ufloat_bits<6>((v >> 11) & 0x7FFu));
+                b = __uint_as_float(unpack_ufloat_bits<5>(v >> 22));
+            } else {
+                const float4 c = __ldg(gi + t);
+                r = c.x; g = c.y; b = c.z;
+            }
+            d = -projB / (projA + (2.0f * __ldg(depth + t) - 1.0f));                      // reprojection.glsl:6-14
+            const uint32_t n10 = __ldg(face_normal + t);
+            nx = float(n10 & 0x3FFu) * (2.0f / 1023.0f) - 1.0f; ny = float((n10 >> 10) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f;
+            nz = float((n10 >> 20) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f;
+        }
+        s_rgb[0][ly][lx] = r; s_rgb[1][ly][lx] = g; s_rgb[2][ly][lx] = b; s_d[ly][lx] = d;
+        s_n[0][ly][lx] = nx; s_n[1][ly][lx] = ny; s_n[2][ly][lx] = nz;
+    }
+    __syncthreads();
+    // weight of tap (tx, ty) for centre (cx, cy), gi_blur.frag:24-47
+    auto weight = [&](int cx, int cy, int tx, int ty, int i) {
+        const float normalFactor = 1.0f - fmaxf(0.0f, s_n[0][cy][cx] * s_n[0][ty][tx] + s_n[1][cy][cx] * s_n[1][ty][tx] + s_n[2][cy][cx] * s_n[2][ty][tx]);   // :44
+        const float depthDiff = s_d[ty][tx] - s_d[cy][cx];
+        const float nd = normalFactor * 5.0f;
+        return fmaxf(0.0f, (3.0f - float(i) + 1.0f) / 4.0f - depthDiff * depthDiff - nd * nd);
+    };
+    // horizontal pass (DIRECTION (1,0), GIStage.cpp:427) for every staged row: SH x TW results
+    for (int q = threadIdx.x; q < SH * TW; q += 256) {
+        const int lx = q % TW + R, ly = q / TW, x = x0 + lx, y = y0 + ly;
+        float ar = s_rgb[0][ly][lx], ag = s_rgb[1][ly][lx], ab = s_rgb[2][ly][lx], fa = 1.0f;   // :60
+        if (x < W && y >= 0 && y < H) {
+#pragma unroll
+            for (int sgn = -1; sgn <= 1; sgn += 2)
+#pragma unroll
+                for (int i = 1; i <= 3; i++) {                                             // :63-69
+                    const int tx = x + sgn * i;
+                    if (tx < 0 || tx >= W) continue;
+                    const float w = weight(lx, ly, lx + sgn * i, ly, i);
+                    fa += w;
+                    ar += s_rgb[0][ly][lx + sgn * i] * w; ag += s_rgb[1][ly][lx + sgn * i] * w; ab += s_rgb[2][ly][lx + sgn * i] * w;
+                }
+        }
+        s_tmp[0][ly][lx - R] = ar / fa; s_tmp[1][ly][lx - R] = ag / fa; s_tmp[2][ly][lx - R] = ab / fa;   // :71
+    }
+    __syncthreads();
+    // vertical pass (DIRECTION (0,1), GIStage.cpp:431)
+    for (int q = threadIdx.x; q < TH * TW; q += 256) {
+        const int lx = q % TW, ly = q / TW + R, x = x0 + R + lx, y = y0 + ly;
+        if (x >= W || y >= H) continue;
+        float ar = s_tmp[0][ly][lx], ag = s_tmp[1][ly][lx], ab = s_tmp[2][ly][lx], fa = 1.0f;
+#pragma unroll
+        for (int sgn = -1; sgn <= 1; sgn += 2)
+#pragma unroll
+            for (int i = 1; i <= 3; i++) {
+                const int ty = y + sgn * i;
+                if (ty < 0 || ty >= H) continue;
+                const float w = weight(lx + R, ly, lx + R, ly + sgn * i, i);
+                fa += w;
+                ar += s_tmp[0][ly + sgn * i][lx] * w; ag += s_tmp[1][ly + sgn * i][lx] * w; ab += s_tmp[2][ly + sgn * i][lx] * w;
+            }
+        out[(size_t)y * W + x] = make_float4(ar / fa, ag / fa, ab / fa, 0.0f);
+    }
+}
+int launch_gi_blur(const float4* gi, const uint32_t* gi_packed, const float* depth, const uint32_t* face_normal, int W, int H, float projA,
+                   float projB, float4* out, cudaStream_t st) {
+    dim3 grid((W + blur::TW - 1) / blur::TW, (H + blur::TH - 1) / blur::TH);
+    if (gi_packed) gi_blur_fused_kernel<true><<<grid, 256, 0, st>>>(nullptr, gi_packed, depth, face_normal, W, H, projA, projB, out);
+    else gi_blur_fused_kernel<false><<<grid, 256, 0, st>>>(gi, nullptr, depth, face_normal, W, H, projA, projB, out);
+    return 1;
 }
 
 // =====================================================================================

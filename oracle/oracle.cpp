@@ -305,9 +305,12 @@ static int tess_n(vec3 v0, vec3 v1, vec3 v2, float tessLevelFactor) {
     float c = clamp(inner, 1.0f, 64.0f);
     return f2i(ceilf(c));
 }
-ORC_API long long orc_ism_points(const float* verts, const float* normals, const uint32_t* indices, int ntri,
-                                 const uint32_t* prim_id, float tessLevelFactor, int N,
-                                 float* points, int32_t* bucket, long long capacity) {
+// n3 (ism.geom:37-46): sampledVplCount = pointsOnlyIntoScaledISMs ? vplCount : totalVplCount is the number of buckets,
+// ismCount = scaleISMs ? vplCount : totalVplCount boosts the point radius (:63). Defaults: both = N.
+ORC_API long long orc_ism_points_ex(const float* verts, const float* normals, const uint32_t* indices, int ntri,
+                                    const uint32_t* prim_id, float tessLevelFactor, int sampledVplCount, int ismCount,
+                                    float* points, int32_t* bucket, long long capacity) {
+    const int N = sampledVplCount;
     long long count = 0;
     for (int t = 0; t < ntri; t++) {
         uint i0 = indices[3 * t], i1 = indices[3 * t + 1], i2 = indices[3 * t + 2];
@@ -338,7 +341,7 @@ ORC_API long long orc_ism_points(const float* verts, const float* normals, const
                     int base = f2i(random3(seed) * float(N));                            // ism.geom:57
                     if (base >= N) base = N - 1;  // random() < 1 so unreachable; guards fp32 product rounding up
                     float pointWorldRadius = maxdist;
-                    pointWorldRadius *= sqrtf(float(N));                                 // ism.geom:63
+                    pointWorldRadius *= sqrtf(float(ismCount));                          // ism.geom:63
                     float normalRadius = pack4UNToFloat(vec4(te_normal * 0.5f + 0.5f, pointWorldRadius / 25.0f));  // :64
                     if (count < capacity) {
                         float* o = points + 4 * count;
@@ -353,22 +356,37 @@ ORC_API long long orc_ism_points(const float* verts, const float* normals, const
     return count;
 }
 
+ORC_API long long orc_ism_points(const float* verts, const float* normals, const uint32_t* indices, int ntri,
+                                 const uint32_t* prim_id, float tessLevelFactor, int N,
+                                 float* points, int32_t* bucket, long long capacity) {
+    return orc_ism_points_ex(verts, normals, indices, ntri, prim_id, tessLevelFactor, N, N, points, bucket, capacity);
+}
+
 // =====================================================================================
 // a3: ism/ism.comp:54-139 (scaleISMs=false, pointsOnlyIntoScaledISMs=false)
 //   points are grouped by bucket: bucket b owns points[bucket_start[b] .. bucket_start[b+1])
 //   atlas: A x A uint32, A = 64*S, must be pre-cleared to 0xFFFFFFFF by the caller or clear=1
 // =====================================================================================
-ORC_API void orc_ism_splat(const float* points, const uint32_t* bucket_start, const float* packed_vpl, int N,
-                           float zFar, uint32_t* atlas, int clear) {
-    const int S = ism_indices_1d(N);
-    const int A = 64 * S;
+// n3 (ism.comp:31-40,56-66,124): with scaleISMs the ISM of VPL id sits at index id - vplStartIndex of a layout of
+// ismIndices1d(vplCount)^2 larger ISMs inside the same atlas; with pointsOnlyIntoScaledISMs the 16-VPL window of a bucket
+// wraps inside [vplStartIndex, vplEndIndex). The atlas edge A stays 64 * ismIndices1d(totalVplCount) (the reference's fixed
+// 2048 for 1024 VPLs, ImperfectShadowmap.cpp:20-37). bucket_start always has N + 1 entries.
+ORC_API void orc_ism_splat_ex(const float* points, const uint32_t* bucket_start, const float* packed_vpl, int N,
+                              float zFar, uint32_t* atlas, int clear, int vplStartIndex, int vplEndIndex, int scaleISMs,
+                              int pointsOnlyIntoScaledISMs) {
+    const int vplCount = vplEndIndex - vplStartIndex;                  // ism.comp:36
+    const int ismCount = scaleISMs ? vplCount : N;                     // :38
+    const int S = ism_indices_1d(ismCount);                            // :39
+    const int A = 64 * ism_indices_1d(N);
     if (clear) std::fill(atlas, atlas + (size_t)A * A, 0xFFFFFFFFu);  // ImperfectShadowmap.cpp:212
     const int maxVplTestCount = 16, maxVplCollectCount = 4;            // ism.comp:44,49
     // serial over buckets: min is order independent, but keep it simple and race free
     for (int b = 0; b < N; b++) {
+        if (pointsOnlyIntoScaledISMs && b > vplCount) continue;        // ism.comp:56-57
         vec4 vpls[16]; int vplIDs[16];
         for (int t = 0; t < maxVplTestCount; t++) {                    // ism.comp:60-69
             int index = (b + t) % N;
+            if (pointsOnlyIntoScaledISMs) { index %= vplCount; index += vplStartIndex; }   // :63-66
             vplIDs[t] = index;
             const float* p = packed_vpl + 4 * (size_t)index;
             vpls[t] = vec4(p[0], p[1], p[2], p[3]);
@@ -394,7 +412,7 @@ ORC_API void orc_ism_splat(const float* points, const uint32_t* bucket_start, co
                 vec3 vplNormal2 = unpack3SNFromFloat(vpls[localVplID].w);
                 vec3 rel = position - vplPosition;
                 float distToCamera = length(rel);
-                float ismIndex = float(globalVplID);
+                float ismIndex = scaleISMs ? float(globalVplID) - float(vplStartIndex) : float(globalVplID);   // :124
                 vec3 v = paraboloid_project(rel, distToCamera, vplNormal2, zFar, ismIndex, S, true);
                 v.x *= float(A); v.y *= float(A);                      // :131
                 v.z *= 16777216.0f;                                    // :132
@@ -426,6 +444,11 @@ struct Img4 {
         return px[(size_t)y * size + x];
     }
 };
+
+ORC_API void orc_ism_splat(const float* points, const uint32_t* bucket_start, const float* packed_vpl, int N,
+                           float zFar, uint32_t* atlas, int clear) {
+    orc_ism_splat_ex(points, bucket_start, packed_vpl, N, zFar, atlas, clear, 0, N, 0, 0);
+}
 
 static void pull_pass(int level, const uint32_t* atlas, int A, const Img4* in, Img4& out, float zFar, int ismPixelSize) {
     const int osz = A >> level;
@@ -602,11 +625,12 @@ static void push_pass(int level, const uint32_t* atlas, int A, const Img4* same,
     }
 }
 
-ORC_API void orc_ism_pullpush(const uint32_t* atlas, int N, float zFar, uint16_t* result_r16,
-                              float** pull_dump, float** push_dump) {
-    const int S = ism_indices_1d(N);
-    const int A = 64 * S;
-    const int ismPixelSize = A / S;  // ImperfectShadowmap.cpp:187-191
+// ismCount = scaleISMs ? vplCount : totalVplCount; ismPixelSize = atlas edge / ismIndices1d(ismCount)
+// (ImperfectShadowmap.cpp:187-191). push.comp:83 keeps its hard-coded 64-pixel ISM borders whatever the ISM size.
+ORC_API void orc_ism_pullpush_ex(const uint32_t* atlas, int N, int ismCount, float zFar, uint16_t* result_r16,
+                                 float** pull_dump, float** push_dump) {
+    const int A = 64 * ism_indices_1d(N);
+    const int ismPixelSize = A / ism_indices_1d(ismCount);  // ImperfectShadowmap.cpp:187-191
     Img4 pull[7], push[7];
     for (int i = 1; i <= 6; i++)     // ImperfectShadowmap.cpp:128-150
         pull_pass(i, atlas, A, i == 1 ? nullptr : &pull[i - 1], pull[i], zFar, ismPixelSize);
@@ -618,6 +642,11 @@ ORC_API void orc_ism_pullpush(const uint32_t* atlas, int N, float zFar, uint16_t
         if (pull_dump && pull_dump[i]) memcpy(pull_dump[i], pull[i].px.data(), pull[i].px.size() * sizeof(vec4));
         if (push_dump && i <= 5 && push_dump[i]) memcpy(push_dump[i], push[i].px.data(), push[i].px.size() * sizeof(vec4));
     }
+}
+
+ORC_API void orc_ism_pullpush(const uint32_t* atlas, int N, float zFar, uint16_t* result_r16,
+                              float** pull_dump, float** push_dump) {
+    orc_ism_pullpush_ex(atlas, N, N, zFar, result_r16, pull_dump, push_dump);
 }
 
 // =====================================================================================
@@ -809,6 +838,10 @@ ORC_API void orc_cull_tiled(const float* depth, const uint32_t* face_normal, int
 //   the same texel fetches. |out_rgb - out_f64| is the fp32 restatement's own rounding uncertainty (large only where a
 //   cosine cancels to ~0 at grazing incidence); tests widen the 1e-3 tolerance by it.
 // =====================================================================================
+static thread_local int g_fg_scale_isms = 0;
+// n3: the SCALE_ISMS define of final_gathering.comp:43-46, which GIStage.cpp:430 rewrites from the scaleISMs property
+ORC_API void orc_final_gather_scale_isms(int on) { g_fg_scale_isms = on; }
+
 ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, int W, int H,
                               const float* vpl, int N, const uint16_t* ism_r16,
                               int cull_mode, const uint16_t* light_list_ids, const uint16_t* lists,
@@ -816,13 +849,16 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
                               float giIntensityFactor, float vplClampingValue, int vplStartIndex, int vplEndIndex,
                               int enableShadowing, int class_lo, int class_hi, int tile, int row_begin, int row_end,
                               float* out_rgb, float* out_lo, float* out_hi, float tie_eps, long long* stats, float* out_f64) {
+    const bool SCALE_ISMS = g_fg_scale_isms != 0;
     mat4 P(proj), V(view);
     // GIStage.cpp:289: camera->viewInverted() * projection->projectionInverted()
     mat4 viewProjectionInvertedMatrix = inverse(V) * inverse(P);
-    const int S = ism_indices_1d(N);  // final_gathering.comp:45-46 (SCALE_ISMS false)
-    const int A = 64 * S;
-    const int L = N / 16;
     const int vplCount = vplEndIndex - vplStartIndex;  // :42
+    const float ismIndexOffset = SCALE_ISMS ? float(vplStartIndex) : 0.0f;   // :44
+    const int ismCount = SCALE_ISMS ? vplCount : N;    // :45
+    const int S = ism_indices_1d(ismCount);            // :46
+    const int A = 64 * ism_indices_1d(N);              // the atlas keeps its size
+    const int L = N / 16;
     const int X = (W + 127) / 128, Y = (H + 127) / 128;
     const int BX = (W + tile - 1) / tile;
     float B[17];
@@ -878,7 +914,7 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
                     if (ca > 0.0 && cb > 0.0) {
                         g64 = std::min(ca * cb / (dd * dd * dd * dd), (double)vplClampingValue);
                         if (enableShadowing) {
-                            vec3 v = paraboloid_project(diff, dist, vnrm, zFar, float(vplIndex), S, false);
+                            vec3 v = paraboloid_project(diff, dist, vnrm, zFar, float(vplIndex) - ismIndexOffset, S, false);
                             int cx = glsl::min(glsl::max((int)floorf(v.x * float(A)), 0), A - 1), cy = glsl::min(glsl::max((int)floorf(v.y * float(A)), 0), A - 1);
                             const double occ = (double)ism_r16[(size_t)cy * A + cx] / 65535.0;
                             double t = (1.0 - (dd / (double)zFar - occ) - 0.98) / 0.02;
@@ -899,7 +935,7 @@ ORC_API void orc_final_gather(const float* depth, const uint32_t* face_normal, i
                 geometryTerm = min(geometryTerm, vplClampingValue);                  // :117
                 float gLo = geometryTerm, gHi = geometryTerm;
                 if (enableShadowing) {                                               // :119-127
-                    float ismIndex = float(vplIndex);
+                    float ismIndex = float(vplIndex) - ismIndexOffset;               // :120
                     vec3 v = paraboloid_project(diff, dist, vnrm, zFar, ismIndex, S, false);
                     // textureLod(..., NEAREST, CLAMP_TO_EDGE): texel = floor(uv * size), clamped
                     float sx = v.x * float(A), sy = v.y * float(A);

@@ -45,6 +45,11 @@ def load():
         lib.orc_ism_points.restype = C.c_longlong
         lib.orc_ism_splat.argtypes = [P, P, P, C.c_int, C.c_float, P, C.c_int]
         lib.orc_ism_pullpush.argtypes = [P, C.c_int, C.c_float, P, P, P]
+        lib.orc_ism_points_ex.argtypes = [P, P, P, C.c_int, P, C.c_float, C.c_int, C.c_int, P, P, C.c_longlong]
+        lib.orc_ism_points_ex.restype = C.c_longlong
+        lib.orc_ism_splat_ex.argtypes = [P, P, P, C.c_int, C.c_float, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.orc_ism_pullpush_ex.argtypes = [P, C.c_int, C.c_int, C.c_float, P, P, P]
+        lib.orc_final_gather_scale_isms.argtypes = [C.c_int]
         lib.orc_clustering.argtypes = [P, C.c_int, C.c_int, P, C.c_float, P, P]; lib.orc_clustering.restype = C.c_int
         lib.orc_light_lists.argtypes = [P, C.c_int, P, C.c_int, P, P, C.c_int, C.c_int, C.c_float, P]
         lib.orc_cull_tiled.argtypes = [P, P, C.c_int, C.c_int, P, C.c_int, P, P, C.c_int, P]
@@ -123,14 +128,23 @@ def vpl_process(rsm_diffuse, rsm_normal, rsm_depth, N, light_view, light_proj, l
     return vpl, packed
 
 
-def ism_points(vertices, normals, indices, prim_id, tess_level_factor, N):
-    """returns (points[P,4] f32, bucket[P] i32) in canonical (triangle, sub id) order"""
+def ism_mode(N, vpl_start=0, vpl_end=None, scale_isms=False, points_only=False):
+    """n3 knobs -> (sampledVplCount, ismCount) of ism.geom:42-44 / ism.comp:36-38"""
+    vpl_end = N if vpl_end is None else vpl_end
+    count = vpl_end - vpl_start
+    return (count if points_only else N), (count if scale_isms else N)
+
+
+def ism_points(vertices, normals, indices, prim_id, tess_level_factor, N, sampled=None, ism_count=None):
+    """returns (points[P,4] f32, bucket[P] i32) in canonical (triangle, sub id) order. sampled / ism_count: ism_mode()"""
     lib = load()
     ntri = indices.shape[0]
-    count = lib.orc_ism_points(_p(vertices), _p(normals), _p(indices), ntri, _p(prim_id), tess_level_factor, N, None, None, 0)
+    sampled = N if sampled is None else sampled
+    ism_count = N if ism_count is None else ism_count
+    count = lib.orc_ism_points_ex(_p(vertices), _p(normals), _p(indices), ntri, _p(prim_id), tess_level_factor, sampled, ism_count, None, None, 0)
     pts = np.empty((count, 4), np.float32)
     bkt = np.empty(count, np.int32)
-    c2 = lib.orc_ism_points(_p(vertices), _p(normals), _p(indices), ntri, _p(prim_id), tess_level_factor, N, _p(pts), _p(bkt), count)
+    c2 = lib.orc_ism_points_ex(_p(vertices), _p(normals), _p(indices), ntri, _p(prim_id), tess_level_factor, sampled, ism_count, _p(pts), _p(bkt), count)
     assert c2 == count
     return pts, bkt
 
@@ -144,18 +158,19 @@ def group_by_bucket(points, bucket, N):
     return np.ascontiguousarray(points[order]), start
 
 
-def ism_splat(points_grouped, bucket_start, packed_vpl, N, z_far):
+def ism_splat(points_grouped, bucket_start, packed_vpl, N, z_far, vpl_start=0, vpl_end=None, scale_isms=False, points_only=False):
     S = ism_indices_1d(N)
     A = 64 * S
     atlas = np.empty((A, A), np.uint32)
-    load().orc_ism_splat(_p(points_grouped), _p(bucket_start), _p(packed_vpl), N, z_far, _p(atlas), 1)
+    load().orc_ism_splat_ex(_p(points_grouped), _p(bucket_start), _p(packed_vpl), N, z_far, _p(atlas), 1, vpl_start,
+                            N if vpl_end is None else vpl_end, int(scale_isms), int(points_only))
     return atlas
 
 
-def ism_pullpush(atlas, N, z_far):
+def ism_pullpush(atlas, N, z_far, ism_count=None):
     A = atlas.shape[0]
     out = np.empty((A, A), np.uint16)
-    load().orc_ism_pullpush(_p(atlas), N, z_far, _p(out), None, None)
+    load().orc_ism_pullpush_ex(_p(atlas), N, N if ism_count is None else ism_count, z_far, _p(out), None, None)
     return out
 
 
@@ -190,7 +205,7 @@ def cull_tiled(depth, normal, vpl, N, view, proj, tile=64):
 
 def final_gather(depth, normal, vpl, N, ism, cull_mode, light_list_ids, lists, view, proj, z_far,
                  gi_intensity_factor=3000.0, clamp=0.001, vpl_start=0, vpl_end=None, shadows=True,
-                 class_lo=0, class_hi=16, tile=64, bounds=False, tie_eps=None, rows=None):
+                 class_lo=0, class_hi=16, tile=64, bounds=False, tie_eps=None, rows=None, scale_isms=False):
     """returns dict(rgb[H,W,3], lo, hi, f64, listed, lit); lo/hi/f64 only with bounds=True"""
     H, W = depth.shape
     if vpl_end is None:
@@ -204,9 +219,13 @@ def final_gather(depth, normal, vpl, N, ism, cull_mode, light_list_ids, lists, v
         tie_eps = 64 * ism_indices_1d(N) * 1e-6   # a few fp32 ulps of the atlas coordinate, in texels
     r0, r1 = (0, H) if rows is None else rows
     v, p = _f32(view), _f32(proj)
-    load().orc_final_gather(_p(depth), _p(normal), W, H, _p(vpl), N, _p(ism), cull_mode, _p(light_list_ids), _p(lists),
-                            _p(v), _p(p), z_far, gi_intensity_factor, clamp, vpl_start, vpl_end, int(shadows),
-                            class_lo, class_hi, tile, r0, r1, _p(out), _p(lo), _p(hi), tie_eps, _p(stats), _p(f64))
+    load().orc_final_gather_scale_isms(int(scale_isms))          # the SCALE_ISMS define (GIStage.cpp:430)
+    try:
+        load().orc_final_gather(_p(depth), _p(normal), W, H, _p(vpl), N, _p(ism), cull_mode, _p(light_list_ids), _p(lists),
+                                _p(v), _p(p), z_far, gi_intensity_factor, clamp, vpl_start, vpl_end, int(shadows),
+                                class_lo, class_hi, tile, r0, r1, _p(out), _p(lo), _p(hi), tie_eps, _p(stats), _p(f64))
+    finally:
+        load().orc_final_gather_scale_isms(0)
     return dict(rgb=out, lo=lo, hi=hi, f64=f64, listed=int(stats[0]), lit=int(stats[1]))
 
 

@@ -52,19 +52,22 @@ def vpl_process(rsm_diffuse, rsm_normal, rsm_depth, N, inv_biased_light_vp, ligh
     return vpl, packed
 
 
-def ism_splat(points_grouped, bucket_start, packed_vpl, N, z_far, A):
-    """points in the reference's pointBuffer layout: bucket b at [b*stride, b*stride + count_b)"""
+def ism_splat(points_grouped, bucket_start, packed_vpl, N, z_far, A, vpl_start=0, vpl_end=None, scale_isms=False, points_only=False):
+    """points in the reference's pointBuffer layout: bucket b at [b*stride, b*stride + count_b), stride = imageSize /
+    sampledVplCount (ism.comp:81)"""
     counts = np.diff(bucket_start.astype(np.int64)).astype(np.uint32)
     stride = int(max(1, counts.max()))
-    cap = stride * N
+    sampled = (N if vpl_end is None else vpl_end) - vpl_start if points_only else N
+    cap = stride * sampled
     buf = np.zeros((cap, 4), np.float32)
-    for b in range(N):
+    for b in range(sampled):
         n = int(counts[b])
         if n:
             buf[b * stride:b * stride + n] = points_grouped[int(bucket_start[b]):int(bucket_start[b]) + n]
     atlas = np.full((A, A), 0xFFFFFFFF, np.uint32)
     pv = _f32(packed_vpl)
-    load().ref_splat_run(_p(pv), N, _p(buf), cap, _p(counts), C.c_float(z_far), _p(atlas), A)
+    load().ref_splat_run2(_p(pv), N, _p(buf), cap, _p(counts), C.c_float(z_far), _p(atlas), A, vpl_start, N if vpl_end is None else vpl_end,
+                          int(scale_isms), int(points_only))
     return atlas
 
 
@@ -108,12 +111,12 @@ def light_lists(packed_vpl, N, compact_ids, W, H, proj, inv_proj_view, z_far, ro
 
 
 def final_gather(depth, normal, vpl, N, ism, list_ids, lists_img, proj, view_proj_inverted, z_far, z_near, gi_intensity_factor=3000.0,
-                 clamp=0.001, vpl_start=0, vpl_end=None, shadows=True):
+                 clamp=0.001, vpl_start=0, vpl_end=None, shadows=True, scale_isms=False):
     H, W = depth.shape
     out = np.zeros((H, W, 4), np.float32)
     A = ism.shape[0]
     Y, X = list_ids.shape[1], list_ids.shape[2]
-    fn = load().ref_gather_run if shadows else load().ref_gather_noshadow_run
+    fn = (load().ref_gather_scaled_run if scale_isms else load().ref_gather_run) if shadows else load().ref_gather_noshadow_run
     fn(_p(_f32(depth)), _p(np.ascontiguousarray(normal, np.uint32)), W, H, _p(_f32(vpl)), N, _p(np.ascontiguousarray(ism, np.uint16)), A,
        _p(np.ascontiguousarray(list_ids, np.uint16)), X, Y, _p(np.ascontiguousarray(lists_img, np.uint16)), lists_img.shape[1], lists_img.shape[0],
        _p(_f32(proj)), _p(_f32(view_proj_inverted)), C.c_float(z_far), C.c_float(z_near), C.c_float(gi_intensity_factor), C.c_float(clamp),
@@ -131,7 +134,8 @@ def gi_blur(gi_rgb, depth, normal, proj):
     return out
 
 
-def ism_points(vertices, normals, indices, prim_id, tess_level_factor, N, max_triangles=None):
+def ism_points(vertices, normals, indices, prim_id, tess_level_factor, N, max_triangles=None, vpl_start=0, vpl_end=None, scale_isms=False,
+               points_only=False):
     """programmable stages of the point pipeline (ism.tesc -> [tessellator] -> ism.tese -> ism.geom, usePushPull path).
     The fixed-function tessellator is replaced by the deterministic n^2 split of DESIGN.md section 3.4 (n = the
     equal_spacing rounding ceil(clamp(inner level, 1, 64)) of the GL spec). Returns (points[P,4], bucket[P]) grouped by
@@ -163,7 +167,10 @@ def ism_points(vertices, normals, indices, prim_id, tess_level_factor, N, max_tr
     V = _f32(np.array(V)); Tc = _f32(np.array(Tc)); Nr = _f32(np.array(Nr)); Pid = np.array(Pid, np.int32)
     stride = 4096
     buf = np.zeros((N * stride, 4), np.float32); counters = np.zeros(max(N, 1024), np.uint32)
-    lib.ref_geom_run(_p(V), _p(Tc), _p(Nr), _p(Pid), T, N, _p(buf), N * stride, _p(counters))
+    sampled = (N if vpl_end is None else vpl_end) - vpl_start if points_only else N
+    # capacity = sampledVplCount * stride keeps ism.geom:67's `imageSize / sampledVplCount` equal to stride
+    lib.ref_geom_run2(_p(V), _p(Tc), _p(Nr), _p(Pid), T, N, _p(buf), sampled * stride, _p(counters), vpl_start, N if vpl_end is None else vpl_end,
+                      int(scale_isms), int(points_only))
     assert counters.max() <= stride
     pts = np.concatenate([buf[b * stride:b * stride + int(counters[b])] for b in range(N)])
     bkt = np.repeat(np.arange(N, dtype=np.int32), counters[:N].astype(np.int64))

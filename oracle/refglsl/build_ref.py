@@ -36,6 +36,7 @@ UNITS = [
     ("vplproc", "gi/vpl_processor.comp", [], "vplproc.inc"),
     ("gather", "gi/final_gathering.comp", [], "gather.inc"),
     ("gather_noshadow", "gi/final_gathering.comp", [("#define ENABLE_SHADOWING true", "#define ENABLE_SHADOWING false")], "gather.inc"),
+    ("gather_scaled", "gi/final_gathering.comp", [("#define SCALE_ISMS false", "#define SCALE_ISMS true")], "gather.inc"),
     ("clustering", "clustered_shading/clustering.comp", [], "clustering.inc"),
     ("lightlists", "clustered_shading/light_lists.comp", [], "lightlists.inc"),
     ("splat", "ism/ism.comp", [], "splat.inc"),

@@ -336,6 +336,23 @@ def test_n1_blur_within_tolerance(gpu_case):
     np.testing.assert_allclose(blur, ref, rtol=1e-4, atol=1e-6 * float(ref.mean()))
 
 
+def test_n1_blur_of_the_packed_image(case_mid):
+    """a packed-only ctx (cfg.gi_packed = 2) blurs the GL_R11F_G11F_B10F image -- the format of the reference's giBuffer"""
+    import oracle_py as O
+    c, wl, sc = case_mid, case_mid.wl, case_mid.wl.scene
+    g = Gpu(c)
+    g.ctx.close()
+    g.ctx = mlgi.Context(c.W, c.H, c.N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 22, gi_packed=2)
+    p = mlgi.default_params(c.N)
+    g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    packed = g.ctx.download(mlgi.BUF_GI_PACKED, np.uint32).reshape(c.H, c.W)
+    g.ctx.gi_blur(g.gb, g.cam)
+    blur = g.ctx.download(mlgi.BUF_GI_BLUR, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
+    ref = O.gi_blur(O.unpack_r11g11b10(packed), wl.depth, wl.normal, wl.cam_proj)
+    np.testing.assert_allclose(blur, ref, rtol=1e-4, atol=1e-6 * float(ref.mean()))
+    g.close()
+
+
 def test_n4_ambient_composite_within_one_lsb(gpu_case):
     """deferredshading.frag ambient term on the blurred and on the raw GI image: sRGB8 within one code of the oracle"""
     g, c = gpu_case, gpu_case.case
@@ -368,12 +385,28 @@ def test_error_behaviour(case_small):
     with pytest.raises(mlgi.MlgiError) as e:      # stage order
         g.ctx.ism_splat(p)
     assert e.value.code == mlgi.E_ORDER
-    for field in ("scale_isms", "points_only_into_scaled_isms", "show_vpl_positions"):
-        q = mlgi.default_params(case_small.N)
-        setattr(q, field, 1)
-        with pytest.raises(mlgi.MlgiError) as e:
-            g.ctx.vpl_process(g.rsm, g.light, q)
-        assert e.value.code == mlgi.E_UNSUPPORTED
+    q = mlgi.default_params(case_small.N)
+    q.show_vpl_positions = 1
+    with pytest.raises(mlgi.MlgiError) as e:
+        g.ctx.vpl_process(g.rsm, g.light, q)
+    assert e.value.code == mlgi.E_UNSUPPORTED
+    q = mlgi.default_params(case_small.N)           # VPL range outside [0, N]
+    q.vpl_end_index = case_small.N + 1
+    with pytest.raises(mlgi.MlgiError) as e:
+        g.ctx.vpl_process(g.rsm, g.light, q)
+    assert e.value.code == mlgi.E_INVALID
+    q = mlgi.default_params(case_small.N)           # the VPL records carry the ISM layout: stages of one frame must agree on it
+    q.scale_isms, q.vpl_end_index = 1, 16
+    g.ctx.vpl_process(g.rsm, g.light, p)
+    g.ctx.ism_points(g.mesh, p)
+    with pytest.raises(mlgi.MlgiError) as e:
+        g.ctx.ism_splat(q)
+    assert e.value.code == mlgi.E_ORDER
+    shard = Gpu(case_small, class_lo=0, class_hi=8)  # scaled ISMs break the class <-> ISM-row correspondence a shard relies on
+    with pytest.raises(mlgi.MlgiError) as e:
+        shard.ctx.vpl_process(shard.rsm, shard.light, q)
+    assert e.value.code == mlgi.E_UNSUPPORTED
+    shard.close()
     q = mlgi.default_params(case_small.N)
     q.use_push_pull = 0
     with pytest.raises(mlgi.MlgiError) as e:
@@ -735,3 +768,51 @@ def test_full_size_8k_16384_row_band():
     for cls in (2, 3):
         assert np.array_equal(part[cls >> 2::4, cls & 3::4], gi[cls >> 2::4, cls & 3::4])
     s.close()
+
+
+N3_MODES = [dict(vpl_start=256, vpl_end=512, scale_isms=True, points_only=True),
+            dict(vpl_start=256, vpl_end=512, scale_isms=True, points_only=False),
+            dict(vpl_start=0, vpl_end=256, scale_isms=False, points_only=True),
+            dict(vpl_start=100, vpl_end=1000, scale_isms=True, points_only=True)]
+
+
+@pytest.mark.parametrize("mode", N3_MODES, ids=lambda m: "s%d_e%d_scale%d_only%d" % (m["vpl_start"], m["vpl_end"], m["scale_isms"], m["points_only"]))
+def test_n3_scaled_ism_modes(case_mid, mode):
+    """vplStartIndex / vplEndIndex, scaleISMs, pointsOnlyIntoScaledISMs (ism.geom:37-46, ism.comp:31-40,56-66,124,
+    final_gathering.comp:40-46 + GIStage.cpp:430, ImperfectShadowmap.cpp:187-191). Point set, atlas and ISM bit-exact against
+    the oracle (which tests/test_reference_glsl.py::test_n3_scaled_isms pins against the compiled reference shaders); radiance
+    inside the contract for tiled and clustered culling; stage calls and the graph-replayed frame agree."""
+    import oracle_py as O
+    c, wl, sc, N = case_mid, case_mid.wl, case_mid.wl.scene, case_mid.N
+    sampled, ism_count = O.ism_mode(N, **mode)
+    g = Gpu(c)
+    p = mlgi.default_params(N)
+    p.vpl_start_index, p.vpl_end_index = mode["vpl_start"], mode["vpl_end"]
+    p.scale_isms, p.points_only_into_scaled_isms = int(mode["scale_isms"]), int(mode["points_only"])
+    o_pts, o_bkt = O.ism_points(sc.vertices, sc.normals, sc.indices, sc.prim_id, 2.0, N, sampled, ism_count)
+    pg, bs = O.group_by_bucket(o_pts, o_bkt, N)
+    atlas_ref = O.ism_splat(pg, bs, c.get("packed"), N, 50.0, **mode)
+    ism_ref = O.ism_pullpush(atlas_ref, N, 50.0, ism_count=ism_count)
+    g.ctx.vpl_process(g.rsm, g.light, p)
+    g.ctx.ism_points(g.mesh, p)
+    npts, _ = g.ctx.counts()
+    assert npts == pg.shape[0]
+    start = g.ctx.download(mlgi.BUF_BUCKET_START, np.uint32)
+    assert np.array_equal(start, bs)
+    pts = g.ctx.download(mlgi.BUF_POINTS, np.float32, count=npts * 4).reshape(npts, 4)
+    assert np.array_equal(_sorted_points(pts, start, N), _sorted_points(pg, bs, N))
+    g.ctx.ism_splat(p)
+    assert np.array_equal(g.ctx.download(mlgi.BUF_ATLAS, np.uint32), atlas_ref.ravel())
+    g.ctx.ism_pullpush(p)
+    assert np.array_equal(g.ctx.download(mlgi.BUF_ISM, np.uint16), ism_ref.ravel())
+    for cull in (mlgi.CULL_TILED, mlgi.CULL_CLUSTERED):
+        p.cull_mode = cull
+        ids = c.get("list_ids") if cull == 0 else None
+        lists = c.get("light_lists") if cull == 0 else c.get("tile_lists")
+        ref = O.final_gather(wl.depth, wl.normal, c.get("vpl"), N, ism_ref, cull, ids, lists, wl.cam_view, wl.cam_proj, 50.0, bounds=True,
+                             vpl_start=mode["vpl_start"], vpl_end=mode["vpl_end"], scale_isms=mode["scale_isms"])
+        g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+        assert np.array_equal(g.ctx.download(mlgi.BUF_ISM, np.uint16), ism_ref.ravel())
+        gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
+        _check_radiance(gi, ref, "n3 %s cull %d" % (mode, cull))
+    g.close()

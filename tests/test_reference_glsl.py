@@ -204,3 +204,47 @@ def test_other_vpl_counts(vpls, case_small):
         assert np.array_equal(bits(got)[~full], bits(want)[~full])
     finally:
         R.use_vpls(1024)
+
+
+# n3: the scaled-ISM experiment knobs (vplStartIndex / vplEndIndex, scaleISMs, pointsOnlyIntoScaledISMs; ism.geom:37-46,
+# ism.comp:31-40,56-66,124, final_gathering.comp:40-46 with GIStage.cpp:430's rewrite of SCALE_ISMS,
+# ImperfectShadowmap.cpp:184-191 for the pull-push pixel size)
+N3_MODES = [dict(vpl_start=256, vpl_end=512, scale_isms=True, points_only=True),      # 256 ISMs of 128^2, points only into them
+            dict(vpl_start=256, vpl_end=512, scale_isms=True, points_only=False),     # scaled layout, every VPL still splatted
+            dict(vpl_start=0, vpl_end=256, scale_isms=False, points_only=True),       # buckets wrap inside the range, 64^2 ISMs
+            dict(vpl_start=100, vpl_end=1000, scale_isms=True, points_only=True)]     # 900 ISMs: ismIndices1d stays 32
+
+
+@pytest.mark.parametrize("mode", N3_MODES, ids=lambda m: "s%d_e%d_scale%d_only%d" % (m["vpl_start"], m["vpl_end"], m["scale_isms"], m["points_only"]))
+def test_n3_scaled_isms(ref, case_mid, mode):
+    c, wl, sc, N = case_mid, case_mid.wl, case_mid.wl.scene, case_mid.N
+    sampled, ism_count = O.ism_mode(N, **mode)
+    M = 3000
+    pts, bkt = ref.ism_points(sc.vertices, sc.normals, sc.indices, sc.prim_id, 2.0, N, max_triangles=M, **mode)
+    o_pts, o_bkt = O.ism_points(sc.vertices, sc.normals, sc.indices[:M], sc.prim_id[:M], 2.0, N, sampled, ism_count)
+    assert np.array_equal(canonical_points(pts, bkt), canonical_points(o_pts, o_bkt))
+    assert int(o_bkt.max()) < sampled
+    # splat + 12 pull-push passes on the full point set of the mode
+    a_pts, a_bkt = O.ism_points(sc.vertices, sc.normals, sc.indices, sc.prim_id, 2.0, N, sampled, ism_count)
+    pg, bs = O.group_by_bucket(a_pts, a_bkt, N)
+    A = c.get("atlas").shape[0]
+    atlas = O.ism_splat(pg, bs, c.get("packed"), N, 50.0, **mode)
+    assert np.array_equal(ref.ism_splat(pg, bs, c.get("packed"), N, 50.0, A, **mode), atlas)
+    assert not np.array_equal(atlas, c.get("atlas"))
+    ism = O.ism_pullpush(atlas, N, 50.0, ism_count=ism_count)
+    assert np.array_equal(ref.ism_pullpush(atlas, 50.0, ism_pixel_size=A // O.ism_indices_1d(ism_count)), ism)
+    # final gathering with the matching SCALE_ISMS define
+    oc, oi, on, ol = c.get("compact"), c.get("list_ids"), c.get("num_used"), c.get("light_lists")
+    inv_pv = O.mat4_inverse(O.mat4_mul(wl.cam_proj, wl.cam_view))
+    img = ref.light_lists(c.get("packed"), N, oc[:on], c.W, c.H, wl.cam_proj, inv_pv, 50.0, rows=N + 64)
+    vpi = O.mat4_mul(O.mat4_inverse(wl.cam_view), O.mat4_inverse(wl.cam_proj))
+    got = ref.final_gather(wl.depth, wl.normal, c.get("vpl"), N, ism, oi, img, wl.cam_proj, vpi, 50.0, 0.05, vpl_start=mode["vpl_start"],
+                           vpl_end=mode["vpl_end"], scale_isms=mode["scale_isms"])
+    ok_px = ~_full_sublist_pixels(c)
+    O.set_reference_math(1)
+    try:
+        want = O.final_gather(wl.depth, wl.normal, c.get("vpl"), N, ism, 0, oi, ol, wl.cam_view, wl.cam_proj, 50.0, vpl_start=mode["vpl_start"],
+                              vpl_end=mode["vpl_end"], scale_isms=mode["scale_isms"])["rgb"]
+    finally:
+        O.set_reference_math(0)
+    assert np.array_equal(bits(got)[ok_px], bits(want)[ok_px])
