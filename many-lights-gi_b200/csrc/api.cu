@@ -103,7 +103,7 @@ struct mlgi_ctx {
     // or, when the cache is full, after an explicit cudaDeviceSynchronize.
     struct OverrideTex { const uint16_t* ptr; cudaTextureObject_t tex; };
     std::vector<OverrideTex> override_tex;
-    int use_texture = 1, tex_float_coord = 0;
+    int use_texture = 1, tex_float_coord = 0, fg_bulk = 1;
     IsmMode mode_vpl{}, mode_points{};   // the n3 knobs the VPL records / the point list were built with
     // multi-GPU exchange (mlgi_exchange_*): ONE IPC-exportable allocation per rank,
     //   [flags 256 B][class planes, parity 0][class planes, parity 1][G-buffer depth W*H*4][G-buffer normals W*H*4]
@@ -120,7 +120,7 @@ struct mlgi_ctx {
         bool connected = false, local_peers = false;
     } xch;
     // CUDA graph of the frame (frame_graphed)
-    int use_graph = 1; bool graph_valid = false;
+    int use_graph = 1, graph_topo = -1; bool graph_valid = false;
     cudaStream_t cap = nullptr; cudaGraphExec_t graph_exec = nullptr; std::vector<char> graph_key;
     unsigned long long graph_launches = 0, graph_replays = 0, graph_instantiations = 0;
     double last_enqueue_us = 0.0;
@@ -364,6 +364,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     }
     if (const char* e5 = getenv("MLGI_HOST_SLABS")) ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5)));   // A/B switch
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) { ctx->use_texture = strcmp(e2, "ldg") != 0; ctx->tex_float_coord = strcmp(e2, "texf") == 0; }   // A/B switch: tex (default) | texf | ldg
+    if (const char* e8 = getenv("MLGI_FG_BULK")) ctx->fg_bulk = atoi(e8) != 0;                 // A/B switch: records staged by cp.async.bulk (default) | LDG + STS
     if (const char* e6 = getenv("MLGI_FG_SORTED")) ctx->fg_sorted = atoi(e6) != 0;             // A/B switch: longest-list tiles first (default) | row-major
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
     *out = ctx;
@@ -616,6 +617,7 @@ static int build_gather_args(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     a.enable_shadowing = p->enable_shadowing;
     a.tile_begin = 0; a.tile_count = ctx->TX * ctx->TY;
     a.tex_float_coord = ctx->tex_float_coord;
+    a.bulk_staging = ctx->fg_bulk;
     a.tile_order = (p->cull_mode == MLGI_CULL_TILED && ctx->fg_sorted && ctx->tile_order_valid) ? ctx->tile_order : nullptr;
     a.class_lo = ctx->cfg.class_lo; a.class_hi = ctx->cfg.class_hi;
     // output routing: a bound exchange buffer receives the class planes and the raster image is rebuilt by the
@@ -910,7 +912,7 @@ static int frame_body(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* lig
 // (cudaGraphExecUpdate), a structural change re-instantiates it. Per-stage timers need the direct path.
 struct FrameKey {
     mlgi_rsm rsm; mlgi_camera light; mlgi_mesh mesh; mlgi_gbuffer gb; mlgi_camera cam; mlgi_params p;
-    int with_exchange, push, fg_sorted, use_texture, tex_float_coord; const void* planar_ext;
+    int with_exchange, push, fg_sorted, use_texture, tex_float_coord, fg_bulk; const void* planar_ext;
 };
 
 static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
@@ -927,7 +929,7 @@ static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* 
         memset(&key, 0, sizeof(key));
         key.rsm = *rsm; key.light = *light; key.mesh = *mesh; key.gb = *gb; key.cam = *cam; key.p = *p;
         key.with_exchange = with_exchange; key.push = ctx->xch.push; key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture;
-        key.tex_float_coord = ctx->tex_float_coord; key.planar_ext = ctx->planar_ext;
+        key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk; key.planar_ext = ctx->planar_ext;
         if (!ctx->graph_valid || memcmp(&key, ctx->graph_key.data(), sizeof(key)) != 0) {
             if (p->cull_mode == MLGI_CULL_CLUSTERED && (rc = ensure_clustered(ctx))) return rc;   // cudaMalloc must not run inside a capture
             const unsigned long long l0 = ctx->launches;
@@ -940,6 +942,11 @@ static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* 
             if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); ctx->graph_valid = false; return rc; }
             if (ce != cudaSuccess) { ctx->graph_valid = false; return fail(ctx, MLGI_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce)); }
             bool updated = false;
+            // value-only changes (matrices, RSM pointers of an animated light ...) update the executable in place; a change of
+            // the launch structure (culling mode, exchange, empty mesh) needs a new one
+            const int topo = p->cull_mode | (with_exchange ? 8 : 0) | (mesh->num_triangles == 0 ? 16 : 0) | (ctx->xch.push ? 32 : 0) | (ctx->planar_ext ? 64 : 0);
+            if (ctx->graph_exec && topo != ctx->graph_topo) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            ctx->graph_topo = topo;
             if (ctx->graph_exec) {
                 cudaGraphExecUpdateResultInfo info;
                 if (cudaGraphExecUpdate(ctx->graph_exec, g, &info) == cudaSuccess) updated = true;

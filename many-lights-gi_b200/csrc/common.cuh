@@ -202,6 +202,7 @@ struct GatherArgs {
     float zFar, giScale /* giIntensityFactor / vplCount * 16 */, clampv;
     int enable_shadowing;
     int tex_float_coord;    // texture path: hand the unfloored texel coordinate to the unit (A/B: MLGI_ISM_FETCH=texf)
+    int bulk_staging;       // stage the VPL records with cp.async.bulk + mbarrier, double-buffered (A/B: MLGI_FG_BULK)
     const uint32_t* tile_order;   // optional permutation of the tiles (longest list first); null = row-major
     int tile_begin, tile_count;   // 64x64 tiles [tile_begin, tile_begin + tile_count) in row-major order (whole image by default)
     int class_lo, class_hi;

@@ -10,6 +10,11 @@
 //   a8  cull_tiled_kernel       (tiled variant)
 #include "common.cuh"
 #include "pullpush_core.cuh"
+#include "bulk_async.cuh"
+
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
 
 namespace mlgi {
 
@@ -465,6 +470,63 @@ __global__ void __launch_bounds__(pp::kThreads, PP_MINB) pullpush_kernel(const u
     }
 }
 
+// TMA variant (default): the 64x64 R32UI tile arrives as ONE 2-D tensor-map copy (cp.async.bulk.tensor, 16 KB) issued by one
+// thread and completing on an mbarrier while all threads fill the tables; the R16 result leaves as one tensor-map store of
+// the packed 64x64x2 B tile. No register staging, no per-thread address arithmetic for the tile.
+__global__ void __launch_bounds__(pp::kThreads, PP_MINB) pullpush_tma_kernel(const __grid_constant__ CUtensorMap tm_atlas,
+                                                                             const __grid_constant__ CUtensorMap tm_ism, float zFar,
+                                                                             float ismPixelSize, int tile_y0) {
+    __shared__ __align__(128) pp::Shared s;
+    __shared__ __align__(8) uint64_t bar;
+    const int gx0 = blockIdx.x * 64, gy0 = (blockIdx.y + tile_y0) * 64;
+    const int tid = threadIdx.x;
+    if (tid == 0) { tma::mbar_init(&bar, 1); tma::fence_barrier_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_arrive_expect_tx(&bar, 64 * 64 * 4);
+        tma::tile_g2s(s.L0, &tm_atlas, gx0, gy0, &bar);
+    }
+    pp::phase_tables(s, tid, zFar, ismPixelSize, gx0, gy0);      // tables + the all-empty block, while the tile is in flight
+    tma::mbar_wait(&bar, 0);
+    __syncthreads();
+    pp::phase_pull1_classify(s, tid);
+    __syncthreads();
+    pp::phase_pull1_dense(s, tid, zFar, ismPixelSize, gx0, gy0);
+    __syncthreads();
+#pragma unroll 1
+    for (int level = 2; level <= 6; level++) {
+        pp::phase_pull(s, tid, level, gx0, gy0);
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int level = 5; level >= 2; level--) {
+        pp::phase_push_top(s, tid, level);
+        __syncthreads();
+    }
+    pp::phase_push1(s, tid);
+    __syncthreads();
+    pp::phase_push0(s, tid);
+    __syncthreads();
+    // pack the R16 codes (one per 32-bit word of L0) into a dense 64x64 uint16 tile in the pyramid's memory (dead by now)
+    uint16_t* packed = reinterpret_cast<uint16_t*>(s.PY);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int q = tid + k * pp::kThreads;  // 0..511, 8 texels each
+        const uint4 a = *reinterpret_cast<const uint4*>(&s.L0[q * 8]);
+        const uint4 b = *reinterpret_cast<const uint4*>(&s.L0[q * 8 + 4]);
+        uint4 o;
+        o.x = a.x | (a.y << 16); o.y = a.z | (a.w << 16); o.z = b.x | (b.y << 16); o.w = b.z | (b.w << 16);
+        *reinterpret_cast<uint4*>(packed + q * 8) = o;
+    }
+    tma::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        tma::tile_s2g(&tm_ism, gx0, gy0, packed);
+        tma::bulk_commit();
+        tma::bulk_wait_read0();                // shared memory must stay valid until the copy engine has read it
+    }
+}
+
 // test hook: the push phase's square-root elimination, evaluated on the device for caller-chosen radii
 __global__ void sqrt_threshold_kernel(const float* __restrict__ rs, int n, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -475,9 +537,37 @@ int launch_sqrt_thresholds(const float* rs, int n, float* out, cudaStream_t st) 
     return 1;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libmlgi does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+static bool make_tile_map(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, int A) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)A, (cuuint64_t)A}, strides[1] = {(cuuint64_t)A * elem_bytes};
+    const cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
+    return fn(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_pullpush(const uint32_t* atlas, int S, float zFar, float ism_pixel_size, uint16_t* ism, int vpl_lo, int vpl_hi, cudaStream_t st) {
     const int ty0 = vpl_lo / S, ty1 = (vpl_hi + S - 1) / S;
     dim3 grid(S, ty1 - ty0);
+    static const bool want_tma = [] { const char* e = getenv("MLGI_PP_TMA"); return !e || atoi(e) != 0; }();   // A/B switch: TMA tile copies (default) | LDG/STG
+    CUtensorMap tm_atlas, tm_ism;
+    if (want_tma && make_tile_map(&tm_atlas, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, atlas, 64 * S) &&
+        make_tile_map(&tm_ism, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, ism, 64 * S)) {
+        pullpush_tma_kernel<<<grid, pp::kThreads, 0, st>>>(tm_atlas, tm_ism, zFar, ism_pixel_size, ty0);
+        return 1;
+    }
     pullpush_kernel<<<grid, pp::kThreads, 0, st>>>(atlas, S, zFar, ism_pixel_size, ism, ty0);
     return 1;
 }

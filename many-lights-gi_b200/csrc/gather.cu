@@ -12,6 +12,7 @@
 //   * ISM shadow lookups are 2-byte nearest-texel gathers straight from the L2-resident atlas;
 //   * clustered mode walks the (<= 16) depth slices present in the tile and masks pixels.
 #include "common.cuh"
+#include "bulk_async.cuh"
 
 #include <algorithm>
 
@@ -151,12 +152,19 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
     }
 }
 
-template <int MODE, bool SHADOW, bool STATS, int TEX, int NP>
+// BULK: the list's records are staged by the copy engine instead of LDG -> STS -- one 80-byte cp.async.bulk per record,
+// issued by one thread each and completing on an mbarrier, double-buffered in two 64-record halves of the staging buffer:
+// chunk c + 1 lands while chunk c is shaded, the first two chunks of a tiled list are already in flight during the pixel
+// prologue, and a chunk costs one CTA barrier instead of two.
+template <int MODE, bool SHADOW, bool STATS, int TEX, int NP, bool BULK>
 __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(const GatherArgs a) {
     constexpr int THREADS = 256 / (2 * NP);     // 256 pixels of one class per CTA, 2*NP pixels per thread
     constexpr int NPX = 2 * NP;
-    __shared__ float4 srec[FG_CHUNK * FG_REC_Q];
+    constexpr int BCH = 64;                     // records per bulk-staged chunk (two chunks fit the staging buffer)
+    static_assert(!BULK || (THREADS >= BCH && FG_CHUNK >= 2 * BCH), "bulk staging: one issuing thread per record, two buffers");
+    __shared__ __align__(16) float4 srec[FG_CHUNK * FG_REC_Q];
     __shared__ uint32_t s_slices;
+    __shared__ __align__(8) uint64_t s_full[2];
 
     const int ncls = a.class_hi - a.class_lo;
     const int TX = (a.W + kTile - 1) / kTile;
@@ -175,7 +183,27 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
     const int pi = 8 * (warp & 1) + (lane & 7);
     const int pj0 = (NP == 1 ? 8 * (warp >> 1) : 0) + (lane >> 3);
 
-    if (MODE == MLGI_CULL_CLUSTERED) { if (threadIdx.x == 0) s_slices = 0; __syncthreads(); }
+    if (MODE == MLGI_CULL_CLUSTERED) { if (threadIdx.x == 0) s_slices = 0; }
+    if (BULK && threadIdx.x == 0) { tma::mbar_init(&s_full[0], 1); tma::mbar_init(&s_full[1], 1); tma::fence_barrier_init(); }
+    if (MODE == MLGI_CULL_CLUSTERED || BULK) __syncthreads();
+    // bulk staging of chunk c of a list into buffer c & 1 (sub == nullptr: the class's whole VPL range, MLGI_CULL_NONE)
+    auto issue_chunk = [&](const uint16_t* sub, int count, int c) {
+        const int n = min(BCH, count - c * BCH);
+        float4* dst = srec + (c & 1) * BCH * FG_REC_Q;
+        if (threadIdx.x == 0) tma::mbar_arrive_expect_tx(&s_full[c & 1], (uint32_t)n * (uint32_t)sizeof(VplRecord));
+        if ((int)threadIdx.x < n) {
+            const uint32_t id = sub ? (uint32_t)sub[1 + c * BCH + threadIdx.x] : (uint32_t)(cls * L + c * BCH + threadIdx.x);   // :98
+            tma::bulk_g2s(dst + threadIdx.x * FG_REC_Q, &a.records[id], (uint32_t)sizeof(VplRecord), &s_full[c & 1]);
+        }
+    };
+    uint32_t full_phase = 0;                    // bit b: parity of the next completion of s_full[b]
+    const uint16_t* sub_first = nullptr;
+    int count_first = L;
+    if (BULK && MODE != MLGI_CULL_CLUSTERED) {  // one list per CTA, known before any pixel work: start fetching it now
+        if (MODE == MLGI_CULL_TILED) { sub_first = a.lists.lists + ((size_t)tile * 16 + cls) * (L + 1); count_first = (int)sub_first[0] - 1; }
+        if (count_first > 0) issue_chunk(sub_first, count_first, 0);
+        if (count_first > BCH) issue_chunk(sub_first, count_first, 1);
+    }
 
     float P[NPX][3], Nn[NPX][3];
     int sx[NPX], sy[NPX], slice[NPX];
@@ -267,6 +295,25 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
             nact += (act0 ? 1 : 0) + (act1 ? 1 : 0);
         }
 
+        if (BULK) {
+            const int nchunks = (count + BCH - 1) / BCH;
+            if (MODE == MLGI_CULL_CLUSTERED) {                  // (the tiled / unculled list was started before the prologue)
+                if (nchunks > 0) issue_chunk(sub, count, 0);
+                if (nchunks > 1) issue_chunk(sub, count, 1);
+            }
+            for (int c = 0; c < nchunks; c++) {
+                const int b = c & 1, n = min(BCH, count - c * BCH);
+                tma::mbar_wait(&s_full[b], (full_phase >> b) & 1u);
+                full_phase ^= 1u << b;
+                const float4* recs = srec + b * BCH * FG_REC_Q;
+#pragma unroll 2
+                for (int e = 0; e < n; e++)                     // :97
+                    shade_vpl<SHADOW, STATS, TEX, NP>(px, recs + e * FG_REC_Q, a.ism, a.ism_tex, A, kz, a.clampv, N, nact, listed, lit);
+                __syncthreads();                                // every warp is done with buffer b: refill it
+                if (c + 2 < nchunks) issue_chunk(sub, count, c + 2);
+            }
+            continue;
+        }
         for (int base = 0; base < count; base += FG_CHUNK) {
             const int n = min(FG_CHUNK, count - base);
             __syncthreads();                                    // previous chunk fully consumed
@@ -348,13 +395,14 @@ template <int MODE>
 static void launch_fg_mode(const GatherArgs& a, dim3 grid, cudaStream_t st) {
     const bool sh = a.enable_shadowing != 0, stt = a.stats != nullptr;
     const bool tex = sh && a.ism_tex != 0;      // the ISM is fetched through the texture unit whenever a texture object exists
-    if (!stt && tex && a.tex_float_coord) { final_gather_kernel<MODE, true, false, 2, 1><<<grid, 128, 0, st>>>(a); return; }
+    if (!stt && tex && a.tex_float_coord) { final_gather_kernel<MODE, true, false, 2, 1, false><<<grid, 128, 0, st>>>(a); return; }
     if (stt) {                                   // counting variant (work counters for the roofline accounting)
-        if (sh) final_gather_kernel<MODE, true, true, 0, 1><<<grid, 128, 0, st>>>(a);
-        else final_gather_kernel<MODE, false, true, 0, 1><<<grid, 128, 0, st>>>(a);
-    } else if (!sh) final_gather_kernel<MODE, false, false, 0, 1><<<grid, 128, 0, st>>>(a);
-    else if (!tex) final_gather_kernel<MODE, true, false, 0, 1><<<grid, 128, 0, st>>>(a);
-    else final_gather_kernel<MODE, true, false, 1, 1><<<grid, 128, 0, st>>>(a);
+        if (sh) final_gather_kernel<MODE, true, true, 0, 1, false><<<grid, 128, 0, st>>>(a);
+        else final_gather_kernel<MODE, false, true, 0, 1, false><<<grid, 128, 0, st>>>(a);
+    } else if (!sh) final_gather_kernel<MODE, false, false, 0, 1, false><<<grid, 128, 0, st>>>(a);
+    else if (!tex) final_gather_kernel<MODE, true, false, 0, 1, false><<<grid, 128, 0, st>>>(a);
+    else if (a.bulk_staging) final_gather_kernel<MODE, true, false, 1, 1, true><<<grid, 128, 0, st>>>(a);
+    else final_gather_kernel<MODE, true, false, 1, 1, false><<<grid, 128, 0, st>>>(a);
 }
 
 int launch_final_gather(const GatherArgs& a, cudaStream_t st) {
