@@ -348,11 +348,18 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     if (e != cudaSuccess) { fail(nullptr, MLGI_E_CUDA, "init: %s", cudaGetErrorString(e)); mlgi_destroy(ctx); return MLGI_E_CUDA; }
     for (int i = 0; i < T_COUNT; i++) { cudaEventCreate(&ctx->ev[i][0]); cudaEventCreate(&ctx->ev[i][1]); }
     ctx->events_created = true;
-    cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+    // The ISM chain (points -> splat -> pull-push) is the critical path into gathering; culling, forked beside it, only has
+    // to be done by the time the chain ends. In the captured graph the chain's kernels therefore carry the highest stream
+    // priority and the culling branch the lowest (kernel-node priorities are captured from the streams): when both have CTAs
+    // to place, the chain goes first and culling fills what is left.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char* e9 = getenv("MLGI_PRIO")) { if (atoi(e9) == 0) prio_hi = prio_lo; }          // A/B switch
+    cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_clear, cudaEventDisableTiming);
-    cudaStreamCreateWithFlags(&ctx->cap, cudaStreamNonBlocking);
+    cudaStreamCreateWithPriority(&ctx->cap, cudaStreamNonBlocking, prio_hi);
     if (const char* e7 = getenv("MLGI_GRAPH")) ctx->use_graph = atoi(e7) != 0;                  // A/B switch: graph replay (default) | direct launches
     cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->fg2, cudaStreamNonBlocking);
