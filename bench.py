@@ -454,7 +454,7 @@ def main():
             # N > 1, ONE library call per rank and frame: upload of the RSM and of this rank's 1/N of the G-buffer rows from pinned
             # host memory, copy-engine push of the slab to every peer over NVLink beside the ISM build, stages, plane exchange,
             # read-back of this rank's 1/N of the assembled image rows -- the union over ranks is the full result on the host
-            y0, y1 = rank * H // world, (rank + 1) * H // world
+            y0, y1 = ctx.sharded_rows()
             def e2e_step():
                 ctx.frame_sharded_host(hr, job.light, job.mesh, hg, cam, params, host_gi_packed=host_gi, stream=job.stream)
         for _ in range(3):
@@ -483,9 +483,9 @@ def main():
                "ms_per_step": dt * 1e3, "steps": n_e2e, "verified_against_device_path": e2e_ok,
                "call": ("mlgi_frame_host_packed (pinned host RSM + G-buffer in, GL_R11F_G11F_B10F GI image out = the reference's giBuffer "
                         "format, stream sync)") if world == 1 else
-                       "mlgi_frame_sharded_host, one call per rank: pinned-host upload of the RSM and of 1/N of the G-buffer rows, copy-engine "
-                       "push of the slab to every peer over NVLink (beside the ISM build), stages, plane exchange, read-back of 1/N of the "
-                       "assembled GL_R11F_G11F_B10F image rows (bytes summed over ranks)"}
+                       "mlgi_frame_sharded_host, one call per rank: pinned-host upload of the RSM and of 1/N of the G-buffer (whole tile rows), "
+                       "tile bounds exchanged between ranks, gathering reads each tile's pixels from the rank holding them over NVLink, plane "
+                       "exchange, 1/N of the assembled GL_R11F_G11F_B10F image rows written straight to pinned host memory (bytes summed over ranks)"}
 
     # ---- per-stage times + the dominant kernels' live durations (events on the launching stream; direct launches) ----
     ctx.set_timers(True)

@@ -250,13 +250,22 @@ MLGI_API int mlgi_exchange_connect_local(mlgi_ctx*, mlgi_ctx* const* all_ctx);
 MLGI_API int mlgi_exchange_finish(mlgi_ctx*, void* stream);
 MLGI_API int mlgi_exchange_status(mlgi_ctx*);
 /* SURVEY 8(e) mlgi_frame_sharded: one rank's frame of a class-sharded job = mlgi_frame + mlgi_exchange_finish as ONE graph
- * launch; afterwards MLGI_BUF_GI_PACKED / MLGI_BUF_GI hold the complete image on every rank. */
+ * launch; afterwards MLGI_BUF_GI_PACKED / MLGI_BUF_GI hold the complete image on every rank. With tiled culling the ranks also
+ * split the per-pixel half of the culling: each rank bounds the tiles of ITS tile rows (mlgi_sharded_rows) and publishes the
+ * 14 numbers per tile to the peers' exchange regions (a second bounded wait inside the frame). A collective: every rank of
+ * the job calls it once per frame. */
 MLGI_API int mlgi_frame_sharded(mlgi_ctx*, const mlgi_rsm*, const mlgi_camera* light, const mlgi_mesh*,
                                 const mlgi_gbuffer*, const mlgi_camera* cam, const mlgi_params*, void* stream);
-/* The same with HOST inputs (the N-GPU form of mlgi_frame_host_packed). host_gbuffer and host_gi_packed are FULL-size host
- * arrays; this rank uploads rows [rank*H/world, (rank+1)*H/world) of the G-buffer, pushes them to every peer over NVLink
- * (copy engines, beside the ISM build), and writes the same rows of the assembled GL_R11F_G11F_B10F image back. Every input
- * byte crosses PCIe once in the whole job (the 3 MB RSM once per rank). Needs cfg.gi_packed. Synchronises the stream. */
+/* image rows [*row_begin, *row_end) = the whole 64-pixel tile rows this rank is responsible for in the sharded frames (tile
+ * rows [TY*rank/world, TY*(rank+1)/world)): the tiles it bounds, and in mlgi_frame_sharded_host the G-buffer rows it uploads
+ * and the image rows it returns. Valid after mlgi_exchange_create. */
+MLGI_API int mlgi_sharded_rows(mlgi_ctx*, int* row_begin, int* row_end);
+/* The same with HOST inputs (the N-GPU form of mlgi_frame_host_packed; tiled culling). host_gbuffer and host_gi_packed are
+ * FULL-size host arrays; this rank uploads only ITS rows (mlgi_sharded_rows) of the G-buffer and the G-buffer is never
+ * replicated: the ranks exchange tile bounds (64 B per tile), and every rank's gathering CTAs read a tile's pixels from the
+ * rank that uploaded them, over NVLink. The exchange kernel assembles only this rank's rows of the GL_R11F_G11F_B10F image,
+ * directly into host_gi_packed when that is pinned (mapped) memory. Every input byte crosses PCIe once in the whole job (the
+ * 3 MB RSM once per rank). MLGI_BUF_GI_PACKED then holds this rank's rows only. Needs cfg.gi_packed. Synchronises the stream. */
 MLGI_API int mlgi_frame_sharded_host(mlgi_ctx*, const mlgi_rsm* host_rsm, const mlgi_camera* light, const mlgi_mesh* dev_mesh,
                                      const mlgi_gbuffer* host_gbuffer, const mlgi_camera* cam, const mlgi_params*,
                                      uint32_t* host_gi_packed, void* stream);

@@ -91,6 +91,8 @@ struct mlgi_ctx {
     uint32_t* tile_masks = nullptr; uint32_t* compact_ids = nullptr; uint16_t* light_list_ids = nullptr;
     uint16_t* light_lists = nullptr; uint16_t* tile_lists = nullptr;
     uint32_t* tile_weight = nullptr; uint32_t* tile_order = nullptr;   // per-tile listed-VPL count and the longest-first tile permutation
+    float* tile_bounds = nullptr;   // [tiles][16]: the 14 numbers the tile test uses (a8)
+    uint32_t* slab_order = nullptr; // host-input frame: the tiles listed slab by slab (slab k = tile rows k, k + K, ...)
     int fg_sorted = 1; bool tile_order_valid = false;
     bool atlas_precleared = false;  // mlgi_frame clears the atlas on the side stream while the points are generated
     cudaEvent_t ev_clear = nullptr;
@@ -104,16 +106,19 @@ struct mlgi_ctx {
     struct OverrideTex { const uint16_t* ptr; cudaTextureObject_t tex; };
     std::vector<OverrideTex> override_tex;
     int use_texture = 1, tex_float_coord = 0, fg_bulk = 1;
+    int xch_cull = 1;               // connected ranks bound 1/world of the tiles each and exchange the bounds (A/B: MLGI_XCH_CULL)
     IsmMode mode_vpl{}, mode_points{};   // the n3 knobs the VPL records / the point list were built with
     // multi-GPU exchange (mlgi_exchange_*): ONE IPC-exportable allocation per rank,
     //   [flags 256 B][class planes, parity 0][class planes, parity 1][G-buffer depth W*H*4][G-buffer normals W*H*4]
-    // flags[0..7]: "planes of frame f written" per rank; flags[8..15]: "G-buffer slab of frame f pushed" per rank.
+    //   [tile bounds, parity 0][tile bounds, parity 1]
+    // flags[0..7]: "planes of frame f written" per rank; flags[16..23]: "tile bounds of frame f published" per rank.
     struct Exchange {
         int rank = 0, world = 0;
         int push = 0;                         // 0: gathering writes its own buffer, the exchange kernel pulls over NVLink (default)
                                               // 1: the gathering epilogue stores into every rank's buffer (round-1 scheme; MLGI_XCH=push)
         char* base = nullptr;
-        size_t buf_bytes = 0, gb_off = 0;
+        size_t buf_bytes = 0, gb_off = 0, bounds_off = 0, bounds_bytes = 0;
+        int row_end[8] = {0};                 // tile rows [row_end[g-1], row_end[g]) belong to rank g (bounds; G-buffer slab of the host-input frame)
         char* peer_base[8] = {nullptr};       // peer-mapped allocations (own slot = base)
         uint32_t** d_peer_flags = nullptr;    // device array of world pointers (for the flag kernels)
         uint32_t* d_state = nullptr;          // [0] frame counter, [1] ticket, [2] error flag
@@ -131,11 +136,12 @@ struct mlgi_ctx {
     // stage bookkeeping
     bool have_vpl = false, have_points = false, have_atlas = false, have_ism = false, have_clustered = false, have_tiled = false, have_gi = false, have_blur = false;
     cudaStream_t side = nullptr;          // culling runs beside the ISM build (both only depend on the VPL stage)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_vpl = nullptr, ev_rsm = nullptr;
     // host-input frame (frame_host_impl): G-buffer slabs are uploaded (side), culled (aux), gathered (caller's stream) and
     // read back (aux) as a pipeline
     static constexpr int kSlabs = 16;
     cudaStream_t aux = nullptr, fg2 = nullptr;   // fg2: odd slabs' gathering launches, so that one slab's tail overlaps the next slab
+    cudaStream_t rd = nullptr;                   // read-back of finished slabs (its own stream: the D2H copies must not queue behind the culling of later slabs)
     cudaEvent_t ev_ism = nullptr;
     cudaEvent_t ev_up[kSlabs] = {nullptr}, ev_cull[kSlabs] = {nullptr}, ev_fg[kSlabs] = {nullptr};
     int host_slabs = 6;     // measured at 4K on PCIe 5 x16: 1 slab 3.60 ms, 2: 2.95, 4: 2.49, 6: 2.42, 8: 2.49, 16: 2.51
@@ -144,6 +150,9 @@ struct mlgi_ctx {
     bool events_created = false;
     int ev_launches[T_COUNT];
     std::vector<void*> allocs;
+    // MLGI_HOST_TRACE=1: timeline of the host-input frame (timestamps of uploads, stages, read-backs) printed to stderr
+    bool trace_on = false; size_t trace_n = 0;
+    std::vector<std::pair<const char*, cudaEvent_t>> trace;
 };
 
 namespace {
@@ -156,6 +165,24 @@ int fail(mlgi_ctx* c, int code, const char* fmt, ...) {
     va_end(ap);
     if (c) c->err = buf; else g_create_error = buf;
     return code;
+}
+void trace_mark(mlgi_ctx* c, const char* name, cudaStream_t st) {
+    if (!c->trace_on) return;
+    if (c->trace_n == c->trace.size()) { cudaEvent_t e; cudaEventCreate(&e); c->trace.push_back({name, e}); }
+    c->trace[c->trace_n].first = name;
+    cudaEventRecord(c->trace[c->trace_n++].second, st);
+}
+void trace_dump(mlgi_ctx* c) {              // call after the frame's final synchronise
+    if (!c->trace_on || c->trace_n == 0) return;
+    fprintf(stderr, "[mlgi trace]");
+    for (size_t i = 0; i < c->trace_n; i++) {
+        float ms = 0.0f;
+        cudaEventSynchronize(c->trace[i].second);
+        cudaEventElapsedTime(&ms, c->trace[0].second, c->trace[i].second);
+        fprintf(stderr, " %s=%.3f", c->trace[i].first, ms);
+    }
+    fprintf(stderr, "\n");
+    c->trace_n = 0;
 }
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -327,7 +354,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     ALLOC(tile_masks, (size_t)ctx->X * ctx->Y); ALLOC(compact_ids, maxClusters); ALLOC(light_list_ids, maxClusters);
     // light_lists ([clusters][16][L+1] uint16: 1 GB at 8K / 16384 VPLs) is allocated by the first clustered cull (ensure_clustered)
     ALLOC(tile_lists, (size_t)ctx->TX * ctx->TY * 16 * (ctx->L + 1));
-    ALLOC(tile_weight, (size_t)ctx->TX * ctx->TY); ALLOC(tile_order, (size_t)ctx->TX * ctx->TY);
+    ALLOC(tile_weight, (size_t)ctx->TX * ctx->TY); ALLOC(tile_order, (size_t)ctx->TX * ctx->TY); ALLOC(tile_bounds, (size_t)ctx->TX * ctx->TY * 16); ALLOC(slab_order, (size_t)ctx->TX * ctx->TY);
     ALLOC(gi, WH); ALLOC(gi_planar, (size_t)(cfg->class_hi - cfg->class_lo) * PW * PH); ALLOC(gi_blur, WH);
     ALLOC(stats, 2);
     if (cfg->gi_packed) ALLOC(gi_packed, WH);
@@ -359,21 +386,39 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_clear, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_vpl, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_rsm, cudaEventDisableTiming);
     cudaStreamCreateWithPriority(&ctx->cap, cudaStreamNonBlocking, prio_hi);
     if (const char* e7 = getenv("MLGI_GRAPH")) ctx->use_graph = atoi(e7) != 0;                  // A/B switch: graph replay (default) | direct launches
-    cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+    // aux carries the slab culling of the host-input frame: highest priority, so that its (small) kernels are placed as soon as
+    // a slab has arrived instead of waiting behind the resident gathering CTAs of earlier slabs
+    cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi);
     cudaStreamCreateWithFlags(&ctx->fg2, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->rd, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_ism, cudaEventDisableTiming);
     for (int k = 0; k < mlgi_ctx::kSlabs; k++) {
         cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_cull[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_fg[k], cudaEventDisableTiming);
     }
+    if (const char* e10 = getenv("MLGI_HOST_TRACE")) ctx->trace_on = atoi(e10) != 0;
     if (const char* e5 = getenv("MLGI_HOST_SLABS")) ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5)));   // A/B switch
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) { ctx->use_texture = strcmp(e2, "ldg") != 0; ctx->tex_float_coord = strcmp(e2, "texf") == 0; }   // A/B switch: tex (default) | texf | ldg
+    if (const char* e11 = getenv("MLGI_XCH_CULL")) ctx->xch_cull = atoi(e11) != 0;             // A/B switch: bounds exchanged between ranks (default) | every rank bounds all tiles
     if (const char* e8 = getenv("MLGI_FG_BULK")) ctx->fg_bulk = atoi(e8) != 0;                 // A/B switch: records staged by cp.async.bulk (default) | LDG + STS
     if (const char* e6 = getenv("MLGI_FG_SORTED")) ctx->fg_sorted = atoi(e6) != 0;             // A/B switch: longest-list tiles first (default) | row-major
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
+    {   // the gathering order of the host-input frame: tiles slab by slab
+        const int K = std::min(ctx->host_slabs, ctx->TY);
+        std::vector<uint32_t> order;
+        order.reserve((size_t)ctx->TX * ctx->TY);
+        for (int k = 0; k < K; k++)
+            for (int ty = k; ty < ctx->TY; ty += K)
+                for (int tx = 0; tx < ctx->TX; tx++) order.push_back((uint32_t)(ty * ctx->TX + tx));
+        if (cudaMemcpy(ctx->slab_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            fail(nullptr, MLGI_E_CUDA, "init: slab order"); mlgi_destroy(ctx); return MLGI_E_CUDA;
+        }
+    }
     *out = ctx;
     return MLGI_OK;
 }
@@ -386,10 +431,13 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_clear) cudaEventDestroy(ctx->ev_clear);
+    if (ctx->ev_vpl) cudaEventDestroy(ctx->ev_vpl);
+    if (ctx->ev_rsm) cudaEventDestroy(ctx->ev_rsm);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->cap) cudaStreamDestroy(ctx->cap);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->fg2) cudaStreamDestroy(ctx->fg2);
+    if (ctx->rd) cudaStreamDestroy(ctx->rd);
     if (ctx->ev_ism) cudaEventDestroy(ctx->ev_ism);
     for (int k = 0; k < mlgi_ctx::kSlabs; k++) {
         if (ctx->ev_up[k]) cudaEventDestroy(ctx->ev_up[k]);
@@ -403,6 +451,7 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
     if (ctx->xch.d_state) cudaFree(ctx->xch.d_state);
     if (ctx->ism_tex) cudaDestroyTextureObject(ctx->ism_tex);
     for (auto& o : ctx->override_tex) cudaDestroyTextureObject(o.tex);
+    for (auto& t : ctx->trace) cudaEventDestroy(t.second);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->events_created)
         for (int i = 0; i < T_COUNT; i++) { cudaEventDestroy(ctx->ev[i][0]); cudaEventDestroy(ctx->ev[i][1]); }
@@ -551,6 +600,16 @@ MLGI_API int mlgi_cull_clustered(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const ml
 }
 
 // ------------------------------------------------------------------------------------- a8
+// bounds + lists of tile rows ty0, ty0 + ystride, ... (nrows of them), single-GPU form (bounds stay in the ctx)
+static int cull_tiled_rows(mlgi_ctx* ctx, const float* depth, const uint32_t* face_normal, const Mat4& inv, int ty0, int ystride, int nrows, cudaStream_t st) {
+    BoundsOut bo;
+    memset(&bo, 0, sizeof(bo));
+    bo.local = ctx->tile_bounds;
+    int n = launch_tile_bounds(depth, face_normal, ctx->cfg.width, ctx->cfg.height, inv, ty0, ystride, nrows, bo, st);
+    n += launch_tile_lists(ctx->tile_bounds, 0, nullptr, ctx->cfg.width, ctx->records, ctx->cfg.vpl_count, ctx->cfg.class_lo, ctx->cfg.class_hi, ty0, ystride, nrows,
+                           ctx->tile_lists, ctx->tile_weight, st);
+    return n;
+}
 MLGI_API int mlgi_cull_tiled(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_camera* cam, const mlgi_params* p, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
     DeviceGuard dg_(ctx);
@@ -564,9 +623,8 @@ MLGI_API int mlgi_cull_tiled(mlgi_ctx* ctx, const mlgi_gbuffer* gb, const mlgi_c
     mat_inverse(cam->proj, pi);
     mat_mul(vi, pi, inv);
     StageTimer t(ctx, T_TILED, st);
-    ctx->launches += launch_cull_tiled(gb->depth, gb->face_normal, ctx->cfg.width, ctx->cfg.height, ctx->records, ctx->cfg.vpl_count, to_mat4(inv),
-                                       ctx->cfg.class_lo, ctx->cfg.class_hi, 0, ctx->TY, ctx->tile_lists, ctx->tile_weight,
-                                       ctx->fg_sorted ? ctx->tile_order : nullptr, st);
+    ctx->launches += cull_tiled_rows(ctx, gb->depth, gb->face_normal, to_mat4(inv), 0, 1, ctx->TY, st);
+    if (ctx->fg_sorted) ctx->launches += launch_tile_order(ctx->tile_weight, ctx->cfg.width, ctx->cfg.vpl_count, ctx->cfg.class_lo, ctx->cfg.class_hi, 0, ctx->TY, ctx->tile_order, st);
     CK(cudaGetLastError());
     ctx->have_tiled = true; ctx->tile_order_valid = ctx->fg_sorted != 0;
     return MLGI_OK;
@@ -722,7 +780,10 @@ MLGI_API int mlgi_exchange_create(mlgi_ctx* ctx, int rank, int world, void* out_
     const size_t PW = (ctx->cfg.width + 3) / 4, PH = (ctx->cfg.height + 3) / 4, WH = (size_t)ctx->cfg.width * ctx->cfg.height;
     x.buf_bytes = ((16 * PW * PH * (ctx->cfg.gi_packed ? 4 : 16)) + 255) & ~(size_t)255;
     x.gb_off = 256 + 2 * x.buf_bytes;
-    const size_t total = x.gb_off + 2 * ((WH * 4 + 255) & ~(size_t)255);
+    x.bounds_off = x.gb_off + 2 * ((WH * 4 + 255) & ~(size_t)255);
+    x.bounds_bytes = (((size_t)ctx->TX * ctx->TY * 16 * sizeof(float)) + 255) & ~(size_t)255;
+    const size_t total = x.bounds_off + 2 * x.bounds_bytes;
+    for (int g = 0; g < world; g++) x.row_end[g] = (int)((long long)ctx->TY * (g + 1) / world);
     CK(cudaMalloc((void**)&x.base, total));
     CK(cudaMemset(x.base, 0, total));
     CK(cudaMalloc((void**)&x.d_peer_flags, 8 * sizeof(uint32_t*)));
@@ -801,6 +862,31 @@ static void build_exchange_args(mlgi_ctx* ctx, ExchangeArgs* out) {
     e.frame_ctr = x.d_state; e.ticket = x.d_state + 1; e.error = x.d_state + 2;
     e.raster_packed = ctx->gi_packed;
     e.raster = ctx->cfg.gi_packed == 2 ? nullptr : ctx->gi;
+    e.row_begin = 0; e.row_end = ctx->cfg.height;
+}
+
+// Tiled culling of one rank of a connected job (inside mlgi_frame_sharded / mlgi_frame_sharded_host, which every rank calls
+// once per frame): the rank bounds only ITS tile rows -- 1/world of the G-buffer instead of all of it -- and stores the 14
+// numbers per tile into every rank's bounds buffer (64 B per tile over NVLink, 130 KB per frame at 4K); flags order the
+// exchange (bounded wait), then the rank builds the lists of its classes for all tiles. Same bounds, same lists as the
+// single-GPU call.
+static int cull_tiled_sharded(mlgi_ctx* ctx, const float* depth, const uint32_t* face_normal, const Mat4& inv, cudaStream_t st) {
+    auto& x = ctx->xch;
+    BoundsOut bo;
+    memset(&bo, 0, sizeof(bo));
+    bo.local = (float*)(x.base + x.bounds_off);
+    for (int g = 0; g < x.world; g++) if (g != x.rank) bo.peers[bo.num_peers++] = (float*)(x.peer_base[g] + x.bounds_off);
+    bo.parity_stride = x.bounds_bytes / sizeof(float);
+    bo.frame_ctr = x.d_state;
+    const int r0 = x.rank ? x.row_end[x.rank - 1] : 0, r1 = x.row_end[x.rank];
+    int n = launch_tile_bounds(depth, face_normal, ctx->cfg.width, ctx->cfg.height, inv, r0, 1, r1 - r0, bo, st);
+    n += launch_flag_signal(x.d_peer_flags, x.world, 16 + x.rank, x.d_state, st);
+    n += launch_flag_wait((const uint32_t*)x.base + 16, x.world, x.d_state, x.d_state + 2, st);
+    n += launch_tile_lists(bo.local, bo.parity_stride, x.d_state, ctx->cfg.width, ctx->records, ctx->cfg.vpl_count, ctx->cfg.class_lo, ctx->cfg.class_hi,
+                           0, 1, ctx->TY, ctx->tile_lists, ctx->tile_weight, st);
+    if (ctx->fg_sorted) n += launch_tile_order(ctx->tile_weight, ctx->cfg.width, ctx->cfg.vpl_count, ctx->cfg.class_lo, ctx->cfg.class_hi, 0, ctx->TY, ctx->tile_order, st);
+    ctx->have_tiled = true; ctx->tile_order_valid = ctx->fg_sorted != 0;
+    return n;
 }
 
 // signal the peers that this rank's planes of the current frame are written, wait for every rank's signal, then assemble
@@ -888,22 +974,41 @@ static int frame_body(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* lig
                       const mlgi_camera* cam, const mlgi_params* p, bool with_exchange, cudaStream_t st) {
     int rc;
     void* stream = (void*)st;
-    if ((rc = mlgi_vpl_process(ctx, rsm, light, p, stream))) return rc;          // GIStage.cpp:373-376
-    // The reference runs ISM build and culling back to back on one GL queue (GIStage.cpp:378-403); they only share
-    // the VPL buffer as input, so culling is forked onto a side stream and joined before gathering.
-    const bool fork = ctx->side != nullptr && p->cull_mode != MLGI_CULL_NONE;
+    // The reference runs VPL build, ISM build and culling back to back on one GL queue (GIStage.cpp:373-403). Their real
+    // dependencies are: point generation needs nothing from this frame, the atlas clear nothing at all, splat needs points +
+    // VPL records + the cleared atlas, culling needs the VPL records, gathering needs the ISM and the lists. So the frame
+    // forks three ways after the caller's stream position -- [points] on the caller's stream, [VPL build -> culling] on the
+    // side stream, [atlas clear] on the aux stream -- and joins before the splat and before gathering.
+    const bool fork = ctx->side != nullptr && ctx->aux != nullptr && p->cull_mode != MLGI_CULL_NONE;
     if (fork) {
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-        launch_atlas_clear(ctx->atlas, ctx->S, ctx->ism_lo, ctx->ism_hi, ctx->side);   // beside point generation; joined before the splat
-        CK(cudaEventRecord(ctx->ev_clear, ctx->side));
+        CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        launch_atlas_clear(ctx->atlas, ctx->S, ctx->ism_lo, ctx->ism_hi, ctx->aux);
+        CK(cudaEventRecord(ctx->ev_clear, ctx->aux));
         void* cs = (void*)ctx->side;
+        if ((rc = mlgi_vpl_process(ctx, rsm, light, p, cs))) return rc;           // GIStage.cpp:373-376
+        CK(cudaEventRecord(ctx->ev_vpl, ctx->side));
         if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, gb, cam, p, cs))) return rc; }   // :392-403
+        else if (with_exchange && ctx->xch_cull) {          // every rank bounds 1/world of the tiles; the bounds are exchanged
+            if (!gb || !gb->depth || !gb->face_normal || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
+            float vi[16], pi[16], inv[16];
+            mat_inverse(cam->view, vi); mat_inverse(cam->proj, pi); mat_mul(vi, pi, inv);
+            StageTimer t(ctx, T_TILED, ctx->side);
+            ctx->launches += cull_tiled_sharded(ctx, gb->depth, gb->face_normal, to_mat4(inv), ctx->side);
+            CK(cudaGetLastError());
+        }
         else { if ((rc = mlgi_cull_tiled(ctx, gb, cam, p, cs))) return rc; }
         CK(cudaEventRecord(ctx->ev_join, ctx->side));
+    } else {
+        if ((rc = mlgi_vpl_process(ctx, rsm, light, p, stream))) return rc;
     }
     if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;                  // :378-389 ISM render
-    if (fork) { CK(cudaStreamWaitEvent(st, ctx->ev_clear, 0)); ctx->atlas_precleared = true; }
+    if (fork) {
+        CK(cudaStreamWaitEvent(st, ctx->ev_vpl, 0));
+        CK(cudaStreamWaitEvent(st, ctx->ev_clear, 0));
+        ctx->atlas_precleared = true;
+    }
     if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;                         //          ISM CS
     if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;             //          pull / push
     if (fork) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
@@ -919,7 +1024,7 @@ static int frame_body(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* lig
 // (cudaGraphExecUpdate), a structural change re-instantiates it. Per-stage timers need the direct path.
 struct FrameKey {
     mlgi_rsm rsm; mlgi_camera light; mlgi_mesh mesh; mlgi_gbuffer gb; mlgi_camera cam; mlgi_params p;
-    int with_exchange, push, fg_sorted, use_texture, tex_float_coord, fg_bulk; const void* planar_ext;
+    int with_exchange, push, fg_sorted, use_texture, tex_float_coord, fg_bulk, xch_cull; const void* planar_ext;
 };
 
 static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
@@ -936,7 +1041,7 @@ static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* 
         memset(&key, 0, sizeof(key));
         key.rsm = *rsm; key.light = *light; key.mesh = *mesh; key.gb = *gb; key.cam = *cam; key.p = *p;
         key.with_exchange = with_exchange; key.push = ctx->xch.push; key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture;
-        key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk; key.planar_ext = ctx->planar_ext;
+        key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk; key.xch_cull = ctx->xch_cull; key.planar_ext = ctx->planar_ext;
         if (!ctx->graph_valid || memcmp(&key, ctx->graph_key.data(), sizeof(key)) != 0) {
             if (p->cull_mode == MLGI_CULL_CLUSTERED && (rc = ensure_clustered(ctx))) return rc;   // cudaMalloc must not run inside a capture
             const unsigned long long l0 = ctx->launches;
@@ -1012,6 +1117,11 @@ MLGI_API int mlgi_get_frame_stats(mlgi_ctx* ctx, mlgi_frame_stats* out) {
     return MLGI_OK;
 }
 
+static const char* const kTrUp[16] = {"up0","up1","up2","up3","up4","up5","up6","up7","up8","up9","up10","up11","up12","up13","up14","up15"};
+static const char* const kTrCull[16] = {"cull0","cull1","cull2","cull3","cull4","cull5","cull6","cull7","cull8","cull9","cull10","cull11","cull12","cull13","cull14","cull15"};
+static const char* const kTrFg[16] = {"fg0","fg1","fg2","fg3","fg4","fg5","fg6","fg7","fg8","fg9","fg10","fg11","fg12","fg13","fg14","fg15"};
+static const char* const kTrRd[16] = {"rd0","rd1","rd2","rd3","rd4","rd5","rd6","rd7","rd8","rd9","rd10","rd11","rd12","rd13","rd14","rd15"};
+
 static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
                            const mlgi_camera* cam, const mlgi_params* p, void* host_out, bool packed, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
@@ -1020,94 +1130,143 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
     if (packed && !ctx->gi_packed) return fail(ctx, MLGI_E_INVALID, "mlgi_frame_host_packed needs cfg.gi_packed");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t RS = (size_t)ctx->cfg.rsm_width * ctx->cfg.rsm_height, WH = (size_t)ctx->cfg.width * ctx->cfg.height;
-    // The RSM (3 MB) goes first on the compute stream; the camera G-buffer (8 B/pixel) is uploaded on the side stream
-    // while VPL build, point generation, splat and pull-push (which do not read it) already run.
+    // Three streams start together (after whatever the caller queued on `st` before): the side stream carries every upload
+    // (RSM first, 3 MB, then the camera G-buffer, 8 B/pixel); the aux stream clears the atlas, builds the VPLs as soon as the RSM
+    // has arrived and later culls the G-buffer slabs; the caller's stream generates the points (which need neither) and then
+    // runs splat, pull-push and the gathering.
+    CK(cudaEventRecord(ctx->ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    trace_mark(ctx, "start", st);
     {
-        StageTimer t(ctx, T_H2D, st);
-        CK(cudaMemcpyAsync(ctx->st_rsm_diffuse, hr->diffuse, RS * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->st_rsm_normal, hr->face_normal, RS * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->st_rsm_depth, hr->depth, RS * 4, cudaMemcpyHostToDevice, st));
+        StageTimer t(ctx, T_H2D, ctx->side);
+        CK(cudaMemcpyAsync(ctx->st_rsm_diffuse, hr->diffuse, RS * 4, cudaMemcpyHostToDevice, ctx->side));
+        CK(cudaMemcpyAsync(ctx->st_rsm_normal, hr->face_normal, RS * 4, cudaMemcpyHostToDevice, ctx->side));
+        CK(cudaMemcpyAsync(ctx->st_rsm_depth, hr->depth, RS * 4, cudaMemcpyHostToDevice, ctx->side));
     }
+    CK(cudaEventRecord(ctx->ev_rsm, ctx->side));
     mlgi_rsm dr = {ctx->st_rsm_diffuse, ctx->st_rsm_normal, ctx->st_rsm_depth};
     mlgi_gbuffer dg = {ctx->st_depth, ctx->st_normal};
     int rc;
-    if ((rc = mlgi_vpl_process(ctx, &dr, light, p, stream))) return rc;
+    launch_atlas_clear(ctx->atlas, ctx->S, ctx->ism_lo, ctx->ism_hi, ctx->aux);
+    CK(cudaEventRecord(ctx->ev_clear, ctx->aux));
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_rsm, 0));
+    if ((rc = mlgi_vpl_process(ctx, &dr, light, p, (void*)ctx->aux))) return rc;
+    CK(cudaEventRecord(ctx->ev_vpl, ctx->aux));
+    trace_mark(ctx, "vpl", ctx->aux);
+    // points -> [VPL records, cleared atlas] -> splat -> pull-push on the caller's stream
+    auto ism_chain = [&]() -> int {
+        int r;
+        if ((r = mlgi_ism_points(ctx, mesh, p, stream))) return r;
+        CK(cudaStreamWaitEvent(st, ctx->ev_vpl, 0));
+        CK(cudaStreamWaitEvent(st, ctx->ev_clear, 0));
+        ctx->atlas_precleared = true;
+        if ((r = mlgi_ism_splat(ctx, p, stream))) return r;
+        return mlgi_ism_pullpush(ctx, nullptr, p, stream);
+    };
     const bool whole_image = !ctx->xch.connected && !ctx->planar_ext;
-    if (p->cull_mode == MLGI_CULL_TILED && whole_image && ctx->aux && ctx->fg2 && ctx->host_slabs > 1) {
-        // Slab pipeline: the image is cut into horizontal slabs of whole tile rows. Slab k is uploaded on the side stream,
-        // culled on the aux stream as soon as it has arrived, gathered on the caller's stream (after the ISM build) and
-        // read back on the aux stream while slab k+1 is still being gathered, so PCIe traffic in both directions hides
-        // behind the ISM build and the gathering instead of bracketing them.
-        const int K = std::min(ctx->host_slabs, ctx->TY), W = ctx->cfg.width, H = ctx->cfg.height;
-        int row0[mlgi_ctx::kSlabs + 1];
-        for (int k = 0; k <= K; k++) row0[k] = (int)((long long)ctx->TY * k / K);
+    if (p->cull_mode == MLGI_CULL_TILED && whole_image && ctx->aux && ctx->fg2 && ctx->rd && ctx->host_slabs > 1) {
+        // Slab pipeline: the image is cut into K interleaved slabs of whole tile rows -- slab k = tile rows k, k + K, k + 2K, ... --
+        // so that every slab is a representative sample of the image: gathering cost per tile varies by an order of magnitude
+        // over the image (sky vs. floor), and with contiguous slabs the cheap slabs are gathered faster than the next one
+        // uploads while the expensive ones pile up at the end (measured: GPU idle early, 0.9 of 1.9 ms in the last two of six
+        // slabs). Slab k is uploaded on the side stream (one strided 2-D copy per G-buffer plane), culled on the aux stream as
+        // soon as it has arrived, gathered on the caller's stream (after the ISM build) and read back on its own stream while
+        // the next slabs are gathered, so PCIe traffic in both directions hides behind the ISM build and the gathering.
+        const int K = std::min(ctx->host_slabs, ctx->TY), W = ctx->cfg.width, H = ctx->cfg.height, TY = ctx->TY;
         float vi[16], pi[16], inv[16];
         mat_inverse(cam->view, vi); mat_inverse(cam->proj, pi); mat_mul(vi, pi, inv);
+        const size_t row_px = (size_t)kTile * W;                       // pixels of one full tile row
+        const int last_rows = H - (TY - 1) * kTile;                    // image rows of the last tile row (1..64)
+        // strided copy of slab k between two images with 4-byte pixels (tile rows k, k + K, ...; the last tile row may be partial)
+        auto copy_slab = [&](void* dst, const void* src, int k, cudaMemcpyKind kind, cudaStream_t cs) -> int {
+            const int nrows = (TY - k + K - 1) / K;
+            const bool has_last = (TY - 1) % K == k;
+            const int full_rows = (has_last && last_rows < kTile) ? nrows - 1 : nrows;
+            const size_t off = (size_t)k * row_px * 4, pitch = (size_t)K * row_px * 4;
+            if (full_rows > 0) CK(cudaMemcpy2DAsync((char*)dst + off, pitch, (const char*)src + off, pitch, row_px * 4, full_rows, kind, cs));
+            if (full_rows < nrows) {
+                const size_t o2 = (size_t)(TY - 1) * row_px * 4;
+                CK(cudaMemcpyAsync((char*)dst + o2, (const char*)src + o2, (size_t)last_rows * W * 4, kind, cs));
+            }
+            return MLGI_OK;
+        };
         // Enqueue order matters: the host issues ~10 calls per slab, so the first slab's upload and the ISM build are
         // queued before the remaining slabs -- both the copy engine and the SMs have work while the host is still enqueueing.
         // The uploads need no ordering against earlier work: this call returns only after every reader of the staging
-        // buffers has finished. Culling waits for the VPL records (ev_fork) and its slab (ev_up).
-        CK(cudaEventRecord(ctx->ev_fork, st));
-        CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        // buffers has finished. Culling follows the VPL build on the aux stream and waits for its slab (ev_up).
         auto upload = [&](int k) -> int {
-            const size_t y0 = (size_t)row0[k] * kTile, y1 = std::min((size_t)H, (size_t)row0[k + 1] * kTile);
-            CK(cudaMemcpyAsync(ctx->st_depth + y0 * W, hg->depth + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
-            CK(cudaMemcpyAsync(ctx->st_normal + y0 * W, hg->face_normal + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
+            int r;
+            if ((r = copy_slab(ctx->st_depth, hg->depth, k, cudaMemcpyHostToDevice, ctx->side))) return r;
+            if ((r = copy_slab(ctx->st_normal, hg->face_normal, k, cudaMemcpyHostToDevice, ctx->side))) return r;
             CK(cudaEventRecord(ctx->ev_up[k], ctx->side));
+            trace_mark(ctx, kTrUp[k], ctx->side);
             return MLGI_OK;
         };
         if ((rc = upload(0))) return rc;
-        if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;
-        if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;
-        if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;
+        if ((rc = ism_chain())) return rc;
+        trace_mark(ctx, "ism", st);
         for (int k = 0; k < K; k++) {
             if (k > 0 && (rc = upload(k))) return rc;
             CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_up[k], 0));
-            ctx->launches += launch_cull_tiled(ctx->st_depth, ctx->st_normal, W, H, ctx->records, ctx->cfg.vpl_count, to_mat4(inv),
-                                               ctx->cfg.class_lo, ctx->cfg.class_hi, row0[k], row0[k + 1], ctx->tile_lists, ctx->tile_weight, nullptr, ctx->aux);
+            ctx->launches += cull_tiled_rows(ctx, ctx->st_depth, ctx->st_normal, to_mat4(inv), k, K, (TY - k + K - 1) / K, ctx->aux);
             CK(cudaEventRecord(ctx->ev_cull[k], ctx->aux));
+            trace_mark(ctx, kTrCull[k], ctx->aux);
         }
-        ctx->have_tiled = true; ctx->tile_order_valid = false;   // slabs are gathered in row-major order (sorting inside a slab was measured: 2.40 vs 2.35 ms)
+        ctx->have_tiled = true; ctx->tile_order_valid = false;
         GatherArgs a;
         if ((rc = build_gather_args(ctx, &dg, cam, nullptr, p, &a))) return rc;
+        a.tile_order = ctx->slab_order;          // the tiles slab by slab (ensure_slab_order)
         {
             // consecutive slabs alternate between the caller's stream and fg2: the gathering kernel's tail (a few long-list
             // tiles keeping a handful of SMs busy) then overlaps the next slab instead of idling the GPU once per slab
             StageTimer t(ctx, T_FG, st);
             CK(cudaEventRecord(ctx->ev_ism, st));
             CK(cudaStreamWaitEvent(ctx->fg2, ctx->ev_ism, 0));
+            int tile0 = 0;
             for (int k = 0; k < K; k++) {
                 cudaStream_t fs = (k & 1) ? ctx->fg2 : st;
                 CK(cudaStreamWaitEvent(fs, ctx->ev_cull[k], 0));
-                a.tile_begin = row0[k] * ctx->TX; a.tile_count = (row0[k + 1] - row0[k]) * ctx->TX;
+                a.tile_begin = tile0; a.tile_count = ((TY - k + K - 1) / K) * ctx->TX;
+                tile0 += a.tile_count;
                 ctx->launches += launch_final_gather(a, fs);
                 CK(cudaEventRecord(ctx->ev_fg[k], fs));
-                CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fg[k], 0));
+                trace_mark(ctx, kTrFg[k], fs);
+                CK(cudaStreamWaitEvent(ctx->rd, ctx->ev_fg[k], 0));
                 if (host_out) {
-                    const size_t y0 = (size_t)row0[k] * kTile, y1 = std::min((size_t)H, (size_t)row0[k + 1] * kTile);
-                    if (packed) CK(cudaMemcpyAsync((uint32_t*)host_out + y0 * W, ctx->gi_packed + y0 * W, (y1 - y0) * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->aux));
-                    else CK(cudaMemcpyAsync((float4*)host_out + y0 * W, ctx->gi + y0 * W, (y1 - y0) * W * sizeof(float4), cudaMemcpyDeviceToHost, ctx->aux));
+                    if (packed) { if ((rc = copy_slab(host_out, ctx->gi_packed, k, cudaMemcpyDeviceToHost, ctx->rd))) return rc; }
+                    else {       // fp32 RGBA: 16-byte pixels = four 4-byte "pixels" per pixel, the same strides scaled by 4
+                        const int nrows = (TY - k + K - 1) / K;
+                        const bool has_last = (TY - 1) % K == k;
+                        const int full_rows = (has_last && last_rows < kTile) ? nrows - 1 : nrows;
+                        const size_t off = (size_t)k * row_px * 16, pitch = (size_t)K * row_px * 16;
+                        if (full_rows > 0) CK(cudaMemcpy2DAsync((char*)host_out + off, pitch, (const char*)ctx->gi + off, pitch, row_px * 16, full_rows, cudaMemcpyDeviceToHost, ctx->rd));
+                        if (full_rows < nrows) {
+                            const size_t o2 = (size_t)(TY - 1) * row_px * 16;
+                            CK(cudaMemcpyAsync((char*)host_out + o2, (const char*)ctx->gi + o2, (size_t)last_rows * W * 16, cudaMemcpyDeviceToHost, ctx->rd));
+                        }
+                    }
+                    trace_mark(ctx, kTrRd[k], ctx->rd);
                 }
             }
-            CK(cudaEventRecord(ctx->ev_join, ctx->aux));
+            CK(cudaEventRecord(ctx->ev_join, ctx->rd));
             CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         }
         CK(cudaGetLastError());
         ctx->have_gi = true; ctx->have_blur = false;
+        trace_mark(ctx, "end", st);
         CK(cudaStreamSynchronize(st));
+        trace_dump(ctx);
         return MLGI_OK;
     }
-    CK(cudaEventRecord(ctx->ev_fork, st));
-    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));        // also orders the upload after the previous frame's readers
     CK(cudaMemcpyAsync(ctx->st_depth, hg->depth, WH * 4, cudaMemcpyHostToDevice, ctx->side));
     CK(cudaMemcpyAsync(ctx->st_normal, hg->face_normal, WH * 4, cudaMemcpyHostToDevice, ctx->side));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_vpl, 0));         // culling needs the VPL records
     void* cs = (void*)ctx->side;
     if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, &dg, cam, p, cs))) return rc; }
     else if (p->cull_mode == MLGI_CULL_TILED) { if ((rc = mlgi_cull_tiled(ctx, &dg, cam, p, cs))) return rc; }
     CK(cudaEventRecord(ctx->ev_join, ctx->side));
-    if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;
-    if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;
-    if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;
+    if ((rc = ism_chain())) return rc;
     CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     if ((rc = mlgi_final_gather(ctx, &dg, cam, nullptr, p, stream))) return rc;
     if (host_out) {
@@ -1121,67 +1280,120 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
 
 // ------------------------------------------------------------------------------------- sharded host-input frame
 // One rank of a class-sharded job with HOST inputs (the N-GPU form of mlgi_frame_host_packed). The job's inputs
-// cross PCIe once in total: every rank uploads the (small) RSM and ITS 1/world slab of the camera G-buffer rows; the copy
-// engines push the slab into every peer's exchange allocation over NVLink (every rank needs the whole G-buffer: its pixels
-// are interleaved over the image) while the ISM build, which only needs the RSM, already runs; flags in peer memory order
-// the slabs; then culling, gathering, the plane exchange, and the rank reads ITS slab of the assembled image back.
-// host_gbuffer / host_gi_packed are full-size host arrays (pinned for full speed); rows [rank*H/world, (rank+1)*H/world)
-// are the ones touched. Synchronises the stream before returning.
+// cross PCIe once in total and the camera G-buffer is never replicated: rank r uploads the (small) RSM and ITS slab of the
+// G-buffer -- the tile rows mlgi_sharded_rows reports, 1/world of the image -- into its exchange allocation; it bounds the
+// tiles of that slab and publishes the bounds (64 B per tile) to every rank; the gathering CTAs of every rank then read a
+// tile's pixels from the rank that holds them, over NVLink (a rank's classes touch 1/world of each slab's pixels once);
+// the exchange kernel finally assembles only this rank's rows of the image, writing them straight into the caller's
+// pinned host buffer (mapped; a pageable buffer is served through a device staging copy instead).
+// host_gbuffer / host_gi_packed are full-size host arrays; only this rank's rows are read / written. Synchronises the
+// stream before returning. Every rank of the job must make this call for every frame (it contains two bounded waits on
+// the peers: tile bounds, class planes).
+MLGI_API int mlgi_sharded_rows(mlgi_ctx* ctx, int* row_begin, int* row_end) {
+    if (!ctx) return MLGI_E_INVALID;
+    auto& x = ctx->xch;
+    if (!x.base) return fail(ctx, MLGI_E_ORDER, "mlgi_sharded_rows needs mlgi_exchange_create first");
+    const int t0 = x.rank ? x.row_end[x.rank - 1] : 0, t1 = x.row_end[x.rank];
+    if (row_begin) *row_begin = std::min(ctx->cfg.height, t0 * kTile);
+    if (row_end) *row_end = std::min(ctx->cfg.height, t1 * kTile);
+    return MLGI_OK;
+}
+
 MLGI_API int mlgi_frame_sharded_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
                                      const mlgi_camera* cam, const mlgi_params* p, uint32_t* host_gi_packed, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
     DeviceGuard dg_(ctx);
     auto& x = ctx->xch;
     if (!x.connected) return fail(ctx, MLGI_E_ORDER, "mlgi_frame_sharded_host needs a connected exchange");
-    if (!hr || !hg || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer is NULL");
+    if (!hr || !hg || !cam || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer/camera is NULL");
     if (!ctx->gi_packed) return fail(ctx, MLGI_E_INVALID, "mlgi_frame_sharded_host needs cfg.gi_packed");
     if (ctx->cfg.enable_timers) return fail(ctx, MLGI_E_INVALID, "per-stage timers are not available on the sharded host path");
+    if (p && p->cull_mode != MLGI_CULL_TILED) return fail(ctx, MLGI_E_UNSUPPORTED, "mlgi_frame_sharded_host runs tiled culling (the G-buffer is distributed by tile rows)");
     cudaStream_t st = (cudaStream_t)stream;
     const int W = ctx->cfg.width, H = ctx->cfg.height;
     const size_t RS = (size_t)ctx->cfg.rsm_width * ctx->cfg.rsm_height, WH = (size_t)W * H;
-    const size_t y0 = (size_t)x.rank * H / x.world, y1 = (size_t)(x.rank + 1) * H / x.world;
+    int y0i = 0, y1i = 0;
+    mlgi_sharded_rows(ctx, &y0i, &y1i);
+    const size_t y0 = (size_t)y0i, y1 = (size_t)y1i;
     const size_t gb_plane = (WH * 4 + 255) & ~(size_t)255;
     int rc;
-    CK(cudaMemcpyAsync(ctx->st_rsm_diffuse, hr->diffuse, RS * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->st_rsm_normal, hr->face_normal, RS * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->st_rsm_depth, hr->depth, RS * 4, cudaMemcpyHostToDevice, st));
-    // G-buffer traffic on the side stream. It must not overtake the previous frame's readers of the G-buffer region on
-    // the peers: a peer's frame f gathering has finished before it signals its planes, and this rank's frame f exchange
-    // kernel (stream-ordered before this call returns) waited for that signal -- so ordering the side stream after `st`
-    // is enough.
+    // side: G-buffer slab first (it heads the longer dependency chain: slab -> bounds -> exchange -> lists -> gathering), then the RSM;
+    // aux: atlas clear, VPL build after the RSM; caller's stream: points, then splat / pull-push / gathering / exchange
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    trace_mark(ctx, "start", st);
     float* own_depth = (float*)(x.base + x.gb_off);
     uint32_t* own_normal = (uint32_t*)(x.base + x.gb_off + gb_plane);
-    CK(cudaMemcpyAsync(own_depth + y0 * W, hg->depth + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
-    CK(cudaMemcpyAsync(own_normal + y0 * W, hg->face_normal + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
-    for (int k = 1; k < x.world; k++) {             // staggered peer order: at any time every link carries one copy
-        const int g = (x.rank + k) % x.world;
-        float* pd = (float*)(x.peer_base[g] + x.gb_off);
-        uint32_t* pn = (uint32_t*)(x.peer_base[g] + x.gb_off + gb_plane);
-        CK(cudaMemcpyAsync(pd + y0 * W, own_depth + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToDevice, ctx->side));
-        CK(cudaMemcpyAsync(pn + y0 * W, own_normal + y0 * W, (y1 - y0) * W * 4, cudaMemcpyDeviceToDevice, ctx->side));
+    if (y1 > y0) {
+        CK(cudaMemcpyAsync(own_depth + y0 * W, hg->depth + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
+        CK(cudaMemcpyAsync(own_normal + y0 * W, hg->face_normal + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
     }
-    ctx->launches += launch_flag_signal(x.d_peer_flags, x.world, 8 + x.rank, x.d_state, ctx->side);
-    ctx->launches += launch_flag_wait((const uint32_t*)x.base + 8, x.world, x.d_state, x.d_state + 2, ctx->side);
+    CK(cudaEventRecord(ctx->ev_up[0], ctx->side));
+    trace_mark(ctx, "up", ctx->side);
+    CK(cudaMemcpyAsync(ctx->st_rsm_diffuse, hr->diffuse, RS * 4, cudaMemcpyHostToDevice, ctx->side));
+    CK(cudaMemcpyAsync(ctx->st_rsm_normal, hr->face_normal, RS * 4, cudaMemcpyHostToDevice, ctx->side));
+    CK(cudaMemcpyAsync(ctx->st_rsm_depth, hr->depth, RS * 4, cudaMemcpyHostToDevice, ctx->side));
+    CK(cudaEventRecord(ctx->ev_rsm, ctx->side));
     mlgi_rsm dr = {ctx->st_rsm_diffuse, ctx->st_rsm_normal, ctx->st_rsm_depth};
     mlgi_gbuffer dg = {own_depth, own_normal};
-    if ((rc = mlgi_vpl_process(ctx, &dr, light, p, stream))) return rc;
-    // culling needs the VPL records and the complete G-buffer
-    CK(cudaEventRecord(ctx->ev_ism, st));
-    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_ism, 0));
-    void* cs = (void*)ctx->side;
-    if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, &dg, cam, p, cs))) return rc; }
-    else if (p->cull_mode == MLGI_CULL_TILED) { if ((rc = mlgi_cull_tiled(ctx, &dg, cam, p, cs))) return rc; }
-    CK(cudaEventRecord(ctx->ev_join, ctx->side));
+    launch_atlas_clear(ctx->atlas, ctx->S, ctx->ism_lo, ctx->ism_hi, ctx->aux);
+    CK(cudaEventRecord(ctx->ev_clear, ctx->aux));
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_rsm, 0));
+    if ((rc = mlgi_vpl_process(ctx, &dr, light, p, (void*)ctx->aux))) return rc;
+    CK(cudaEventRecord(ctx->ev_vpl, ctx->aux));
+    trace_mark(ctx, "vpl", ctx->aux);
+    // culling on the aux stream (highest priority): own bounds as soon as the slab is here, lists once every rank has published
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_up[0], 0));
+    {
+        float vi[16], pi[16], inv[16];
+        mat_inverse(cam->view, vi); mat_inverse(cam->proj, pi); mat_mul(vi, pi, inv);
+        ctx->launches += cull_tiled_sharded(ctx, own_depth, own_normal, to_mat4(inv), ctx->aux);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux));
+    trace_mark(ctx, "cull", ctx->aux);
     if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;
+    CK(cudaStreamWaitEvent(st, ctx->ev_vpl, 0));
+    CK(cudaStreamWaitEvent(st, ctx->ev_clear, 0));
+    ctx->atlas_precleared = true;
     if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;
     if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;
+    trace_mark(ctx, "ism", st);
     CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    if ((rc = mlgi_final_gather(ctx, &dg, cam, nullptr, p, stream))) return rc;
-    if ((rc = mlgi_exchange_finish(ctx, stream))) return rc;
-    if (host_gi_packed) CK(cudaMemcpyAsync(host_gi_packed + y0 * W, ctx->gi_packed + y0 * W, (y1 - y0) * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    GatherArgs a;
+    if ((rc = build_gather_args(ctx, &dg, cam, nullptr, p, &a))) return rc;
+    a.gb_world = x.world;
+    for (int g = 0; g < x.world; g++) {
+        a.gb_depth[g] = (const float*)(x.peer_base[g] + x.gb_off);
+        a.gb_normal[g] = (const uint32_t*)(x.peer_base[g] + x.gb_off + gb_plane);
+        a.gb_row_end[g] = x.row_end[g];
+    }
+    ctx->launches += launch_final_gather(a, st);
+    CK(cudaGetLastError());
+    trace_mark(ctx, "fg", st);
+    // exchange: assemble only this rank's rows, straight into the caller's buffer when it is mapped pinned memory
+    ExchangeArgs e;
+    build_exchange_args(ctx, &e);
+    e.raster = nullptr;
+    e.row_begin = y0i; e.row_end = y1i;
+    bool direct = false;
+    if (host_gi_packed) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, host_gi_packed) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+            e.raster_packed = (uint32_t*)pa.devicePointer;
+            direct = true;
+        } else cudaGetLastError();
+    }
+    ctx->launches += launch_exchange(e, st);
+    CK(cudaGetLastError());
+    trace_mark(ctx, "xch", st);
+    if (host_gi_packed && !direct && y1 > y0)
+        CK(cudaMemcpyAsync(host_gi_packed + y0 * W, ctx->gi_packed + y0 * W, (y1 - y0) * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ctx->have_gi = true; ctx->have_blur = false;
+    trace_mark(ctx, "end", st);
     CK(cudaStreamSynchronize(st));
+    trace_dump(ctx);
     return MLGI_OK;
 }
 

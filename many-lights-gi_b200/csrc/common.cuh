@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/mlgi.h"
 
@@ -153,6 +154,24 @@ __host__ __device__ inline uint32_t unpack_ufloat_bits(uint32_t v) {   // return
     if (e == 31) return 0x7F800000u | (m << (23 - MBITS));
     return ((e - 15 + 127) << 23) | (m << (23 - MBITS));
 }
+// branch-free form of unpack_ufloat_bits for the hot consumers (blur, de-interleave): v holds only the 5 + MBITS bits.
+// Normal codes re-bias the exponent with one add; subnormal codes (e == 0) are m * 2^-(14 + MBITS), an exact int -> float
+// conversion times a power of two (no normalisation loop); e == 31 (inf / NaN) moves on to fp32's all-ones exponent.
+// Checked against unpack_ufloat_bits for every code by tests/hostemu.
+template <int MBITS>
+__host__ __device__ inline float unpack_ufloat_fast(uint32_t v) {
+    const uint32_t e = v >> MBITS, m = v & ((1u << MBITS) - 1u);
+    uint32_t bits = (v << (23 - MBITS)) + (112u << 23);
+    if (e == 31u) bits += 112u << 23;
+    float f;
+#if defined(__CUDA_ARCH__)
+    f = __uint_as_float(bits);
+#else
+    memcpy(&f, &bits, 4);
+#endif
+    const float sub = float(m) * (MBITS == 6 ? 9.5367431640625e-07f : 1.9073486328125e-06f);   // 2^-20, 2^-19
+    return e == 0u ? sub : f;
+}
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t pack_r11g11b10(float r, float g, float b) {
     return pack_ufloat<6>(__float_as_uint(r)) | (pack_ufloat<6>(__float_as_uint(g)) << 11) | (pack_ufloat<5>(__float_as_uint(b)) << 22);
@@ -187,8 +206,21 @@ int launch_clustering(const float* depth, int W, int H, float projA, float projB
 int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_ids, const uint32_t* num_used,
                        const Mat4& inv_vp, float projA, float projB, int W, int H,
                        const SliceTable& tab, int class_lo, int class_hi, uint16_t* lists, cudaStream_t st);
-int launch_cull_tiled(const float* depth, const uint32_t* face_normal, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
-                      int class_lo, int class_hi, int ty0, int ty1, uint16_t* lists, uint32_t* tile_weight, uint32_t* tile_order, cudaStream_t st);
+// a8 (tiled culling) = tile_bounds (14 numbers per 64x64 tile, streamed from the G-buffer) + tile_lists (per-class VPL lists from
+// the bounds) [+ tile_order]. bounds: float[tiles][16]. Across GPUs every rank bounds its own tile rows and stores them into the
+// peers' bounds buffers as well (BoundsOut::peers), double-buffered by frame parity like the class planes.
+struct BoundsOut {
+    float* local;                  // this rank's bounds buffer (parity 0)
+    int num_peers;                 // 0 = single GPU
+    float* peers[8];               // the OTHER ranks' bounds buffers (parity 0), peer-mapped
+    size_t parity_stride;          // floats from parity buffer 0 to parity buffer 1
+    const uint32_t* frame_ctr;     // null = no parity (always buffer 0)
+};
+int launch_tile_bounds(const float* depth, const uint32_t* face_normal, int W, int H, const Mat4& inv_vp, int ty0, int ystride, int nrows,
+                       const BoundsOut& bo, cudaStream_t st);
+int launch_tile_lists(const float* bounds, size_t parity_stride, const uint32_t* frame_ctr, int W, const VplRecord* records, int N, int class_lo, int class_hi, int ty0, int ystride, int nrows,
+                      uint16_t* lists, uint32_t* tile_weight, cudaStream_t st);
+int launch_tile_order(const uint32_t* tile_weight, int W, int N, int class_lo, int class_hi, int ty0, int nrows, uint32_t* tile_order, cudaStream_t st);
 
 struct GatherArgs {
     const float* depth; const uint32_t* face_normal; int W, H;
@@ -203,6 +235,10 @@ struct GatherArgs {
     int enable_shadowing;
     int tex_float_coord;    // texture path: hand the unfloored texel coordinate to the unit (A/B: MLGI_ISM_FETCH=texf)
     int bulk_staging;       // stage the VPL records with cp.async.bulk + mbarrier, double-buffered (A/B: MLGI_FG_BULK)
+    // host-input sharded frame: the G-buffer is not replicated -- tile rows [gb_row_end[g-1], gb_row_end[g]) live in rank g's memory
+    // (peer-mapped) and a gathering CTA reads its tile's pixels from the owner over NVLink (8 B per pixel, once)
+    int gb_world;                        // 0 = depth / face_normal above hold the whole image
+    const float* gb_depth[8]; const uint32_t* gb_normal[8]; int gb_row_end[8];
     const uint32_t* tile_order;   // optional permutation of the tiles (longest list first); null = row-major
     int tile_begin, tile_count;   // 64x64 tiles [tile_begin, tile_begin + tile_count) in row-major order (whole image by default)
     int class_lo, class_hi;
@@ -239,8 +275,9 @@ struct ExchangeArgs {
     uint32_t* frame_ctr;           // device frame counter (incremented by the last CTA)
     uint32_t* ticket;              // CTA completion counter
     uint32_t* error;               // set when a wait times out (a peer died)
-    uint32_t* raster_packed;       // may be null
+    uint32_t* raster_packed;       // may be null (may be a mapped pinned-host pointer: mlgi_frame_sharded_host)
     float4* raster;                // may be null
+    int row_begin, row_end;        // image rows to assemble (whole image by default)
 };
 int launch_exchange(const ExchangeArgs& x, cudaStream_t st);
 // host-input sharded frame: G-buffer slabs are pushed to the peers by the copy engines; these two order them

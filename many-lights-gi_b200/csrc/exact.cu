@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 namespace mlgi {
 
@@ -727,28 +728,30 @@ int launch_light_lists(const VplRecord* records, int N, const uint32_t* compact_
     return 1;
 }
 
-// a8: one CTA per 64x64 tile. Phase 1 unprojects the tile's pixels exactly as the gathering prologue does and reduces them
-// to 14 numbers (position AABB, normal box, emin, emag); phase 2 tests every VPL of the 16 classes against them (2 classes
-// per warp, ordered ballot compaction). The rule is stated in DESIGN.md section 4 / oracle.cpp tile_keeps_vpl.
+// a8, two kernels. tile_bounds_kernel: one CTA per 64x64 tile unprojects the tile's pixels exactly as the gathering prologue
+// does and reduces them to 14 numbers (position AABB, normal box, emin, emag) -- a streaming pass over the G-buffer (8 B per
+// pixel). tile_lists_kernel: one warp per (tile, class) tests the class's VPLs against the 14 numbers (ordered ballot
+// compaction). The rule is stated in DESIGN.md section 4 / oracle.cpp tile_keeps_vpl. Split in two because (1) the phases
+// want different shapes (256 threads x 16 pixels at 40 registers vs one warp per sub-list), and (2) across GPUs the bounds are
+// the exchange unit: every rank bounds only ITS tile rows and publishes 64 B per tile to the peers (bounds_peers), instead of
+// every rank streaming the whole G-buffer.
 #ifndef CULL_MINB
-#define CULL_MINB 4
+#define CULL_MINB 5
 #endif
 struct TileBounds { float pmin[3], pmax[3], nmin[3], nmax[3], emin, emag; };
 
-__global__ void __launch_bounds__(256, CULL_MINB) cull_tiled_kernel(const float* __restrict__ depth, const uint32_t* __restrict__ face_normal, int W, int H,
-                                                         const VplRecord* __restrict__ records, int N, Mat4 inv_vp, int class_lo,
-                                                         int class_hi, int tile_y0, uint16_t* __restrict__ lists,
-                                                         uint32_t* __restrict__ tile_weight) {
+__global__ void __launch_bounds__(256, CULL_MINB) tile_bounds_kernel(const float* __restrict__ depth, const uint32_t* __restrict__ face_normal, int W, int H,
+                                                                    Mat4 inv_vp, int tile_y0, int ystride, BoundsOut bo) {
     __shared__ float sred[8][14];
-    __shared__ uint32_t s_weight;
-    if (threadIdx.x == 0) s_weight = 0;
-    __shared__ TileBounds stb;
     __shared__ float s_n10[1024];     // 10-bit channel -> v / 1023 * 2 - 1 (the IEEE division once per code instead of three per pixel)
-    __shared__ float s_ndcy[kTile];   // tile row -> y / H * 2 - 1
+    __shared__ float4 s_rowy[kTile];  // tile row -> column 1 of inv_vp times ndc.y = y / H * 2 - 1
+    const int bx = blockIdx.x, by = tile_y0 + blockIdx.y * ystride;
     for (int i = threadIdx.x; i < 1024; i += 256) s_n10[i] = float(i) / 1023.0f * 2.0f - 1.0f;                 // final_gathering.comp:79
-    if (threadIdx.x < kTile) s_ndcy[threadIdx.x] = float((blockIdx.y + tile_y0) * kTile + threadIdx.x) / float(H) * 2.0f - 1.0f;   // :70,74
+    if (threadIdx.x < kTile) {
+        const float ny = float(by * kTile + threadIdx.x) / float(H) * 2.0f - 1.0f;                              // :70,74
+        s_rowy[threadIdx.x] = make_float4(inv_vp.m[4] * ny, inv_vp.m[5] * ny, inv_vp.m[6] * ny, inv_vp.m[7] * ny);
+    }
     __syncthreads();
-    const int bx = blockIdx.x, by = blockIdx.y + tile_y0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float INF = __int_as_float(0x7f800000);
     float r[14];   // 0-2 pmin, 3-5 pmax, 6-8 nmin, 9-11 nmax, 12 emin, 13 emag
@@ -756,44 +759,50 @@ __global__ void __launch_bounds__(256, CULL_MINB) cull_tiled_kernel(const float*
     for (int k = 0; k < 3; k++) { r[k] = INF; r[3 + k] = -INF; r[6 + k] = INF; r[9 + k] = -INF; }
     r[12] = INF; r[13] = 0.0f;
     {
-        constexpr int Q = kTile * kTile / 256;
-        float dv[Q]; uint32_t nv[Q];
-#pragma unroll
-        for (int q = 0; q < Q; q++) {              // all loads in flight before the first use
-            const int p = threadIdx.x + q * 256;
-            const int x = bx * kTile + (p % kTile), y = by * kTile + (p / kTile);
-            const bool in = x < W && y < H;
-            dv[q] = in ? __ldg(depth + (size_t)y * W + x) : 0.0f;
-            nv[q] = in ? __ldg(face_normal + (size_t)y * W + x) : 0u;
-        }
+        // A thread owns one column of the tile (x is fixed) and rows row0, row0 + 4, ...: everything of the unprojection
+        // (:75, (m0*x + m1*y) + (m2*z + m3*1) per row of the matrix) that depends only on x is evaluated once per thread,
+        // everything that depends only on y once per CTA (s_rowy); the per-pixel rest is 4 multiplies and 12 additions.
+        // Same operations in the same order as the oracle (no FMA in this translation unit).
+        constexpr int Q = kTile * kTile / 256, QB = 8;        // 16 pixels per thread, loads issued 8 at a time
+        const int col = threadIdx.x & (kTile - 1), row0 = threadIdx.x / kTile;
+        const int x = bx * kTile + col;
+        const bool full = bx * kTile + kTile <= W && by * kTile + kTile <= H;   // CTA-uniform: no per-pixel bounds checks
         const float* m = inv_vp.m;
+        const float nx = float(x) / float(W) * 2.0f - 1.0f;                    // final_gathering.comp:70,74
+        const float mx0 = m[0] * nx, mx1 = m[1] * nx, mx2 = m[2] * nx, mx3 = m[3] * nx;
+        const uint32_t off0 = (uint32_t)(by * kTile + row0) * (uint32_t)W + (uint32_t)x, step = 4u * (uint32_t)W;
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const int p = threadIdx.x + q * 256;
-            const int x = bx * kTile + (p % kTile), y = by * kTile + (p / kTile);
-            if (x < W && y < H) {
-                const float nx = float(x) / float(W) * 2.0f - 1.0f;                // final_gathering.comp:70,74
-                const float ny = s_ndcy[p / kTile];
-                const float nz = dv[q] * 2.0f - 1.0f;
-                float w4[4];
+        for (int qb = 0; qb < Q; qb += QB) {
+            float dv[QB]; uint32_t nv[QB];
 #pragma unroll
-                for (int c = 0; c < 4; c++) w4[c] = (m[c] * nx + m[4 + c] * ny) + (m[8 + c] * nz + m[12 + c]);   // :75
-                // bounds only: one IEEE reciprocal and three multiplies instead of the gathering pass's three divisions
-                // (:76). The position differs from the gathering pass's by <= 1.5 ulp, which the slack of the tile test
-                // covers many times over; the oracle evaluates the same expression.
-                float P[3], n[3];
-                const float rw = 1.0f / w4[3];
+            for (int q = 0; q < QB; q++) {         // the batch's loads in flight before the first use
+                const bool in = full || (x < W && by * kTile + row0 + 4 * (qb + q) < H);
+                dv[q] = in ? __ldg(depth + off0 + (qb + q) * step) : 0.0f;
+                nv[q] = in ? __ldg(face_normal + off0 + (qb + q) * step) : 0u;
+            }
 #pragma unroll
-                for (int c = 0; c < 3; c++) P[c] = w4[c] * rw;
-                n[0] = s_n10[nv[q] & 0x3FFu]; n[1] = s_n10[(nv[q] >> 10) & 0x3FFu]; n[2] = s_n10[(nv[q] >> 20) & 0x3FFu];   // :79
+            for (int q = 0; q < QB; q++) {
+                if (full || (x < W && by * kTile + row0 + 4 * (qb + q) < H)) {
+                    const float4 ry = s_rowy[row0 + 4 * (qb + q)];
+                    const float nz = dv[q] * 2.0f - 1.0f;
+                    const float w0 = (mx0 + ry.x) + (m[8] * nz + m[12]), w1 = (mx1 + ry.y) + (m[9] * nz + m[13]);    // :75
+                    const float w2 = (mx2 + ry.z) + (m[10] * nz + m[14]), w3 = (mx3 + ry.w) + (m[11] * nz + m[15]);
+                    // bounds only: one IEEE reciprocal and three multiplies instead of the gathering pass's three divisions
+                    // (:76). The position differs from the gathering pass's by <= 1.5 ulp, which the slack of the tile test
+                    // covers many times over; the oracle evaluates the same expression.
+                    float P[3], n[3];
+                    const float rw = 1.0f / w3;
+                    P[0] = w0 * rw; P[1] = w1 * rw; P[2] = w2 * rw;
+                    n[0] = s_n10[nv[q] & 0x3FFu]; n[1] = s_n10[(nv[q] >> 10) & 0x3FFu]; n[2] = s_n10[(nv[q] >> 20) & 0x3FFu];   // :79
 #pragma unroll
-                for (int c = 0; c < 3; c++) {       // FMNMX: equals the oracle's ternary min/max on the finite values seen here
-                    r[c] = fminf(r[c], P[c]); r[3 + c] = fmaxf(r[3 + c], P[c]);
-                    r[6 + c] = fminf(r[6 + c], n[c]); r[9 + c] = fmaxf(r[9 + c], n[c]);
+                    for (int c = 0; c < 3; c++) {   // FMNMX: equals the oracle's ternary min/max on the finite values seen here
+                        r[c] = fminf(r[c], P[c]); r[3 + c] = fmaxf(r[3 + c], P[c]);
+                        r[6 + c] = fminf(r[6 + c], n[c]); r[9 + c] = fmaxf(r[9 + c], n[c]);
+                    }
+                    const float ex = n[0] * P[0], ey = n[1] * P[1], ez = n[2] * P[2];
+                    r[12] = fminf(r[12], (ex + ey) + ez);
+                    r[13] = fmaxf(r[13], (fabsf(ex) + fabsf(ey)) + fabsf(ez));
                 }
-                const float ex = n[0] * P[0], ey = n[1] * P[1], ez = n[2] * P[2];
-                r[12] = fminf(r[12], (ex + ey) + ez);
-                r[13] = fmaxf(r[13], (fabsf(ex) + fabsf(ey)) + fabsf(ez));
             }
         }
     }
@@ -815,13 +824,35 @@ __global__ void __launch_bounds__(256, CULL_MINB) cull_tiled_kernel(const float*
         float v = sred[0][i];
 #pragma unroll
         for (int w = 1; w < 8; w++) v = is_min ? fminf(v, sred[w][i]) : fmaxf(v, sred[w][i]);
-        reinterpret_cast<float*>(&stb)[i] = v;
+        const size_t e = ((size_t)by * gridDim.x + bx) * 16 + i;
+        const size_t par = bo.frame_ctr ? (size_t)((*bo.frame_ctr + 1u) & 1u) * bo.parity_stride : 0;   // floats
+        bo.local[par + e] = v;
+#pragma unroll
+        for (int g = 0; g < 8; g++) if (g < bo.num_peers) bo.peers[g][par + e] = v;      // multi-GPU: 64 B per tile to every other rank
     }
+}
+
+__global__ void __launch_bounds__(512) tile_lists_kernel(const float* __restrict__ bounds, size_t parity_stride, const uint32_t* __restrict__ frame_ctr,
+                                                         const VplRecord* __restrict__ records, int N, int class_lo,
+                                                         int class_hi, int tile_y0, int ystride, uint16_t* __restrict__ lists,
+                                                         uint32_t* __restrict__ tile_weight) {
+    __shared__ uint32_t s_weight;
+    if (threadIdx.x == 0) s_weight = 0;
     __syncthreads();
-    const TileBounds tb = stb;
-    const int L = N / 16;
+    const int bx = blockIdx.x, by = tile_y0 + blockIdx.y * ystride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const size_t tile = (size_t)by * gridDim.x + bx;
-    for (int k = class_lo + warp; k < class_hi; k += 8) {
+    TileBounds tb;
+    {
+        // (plain load: across GPUs the buffer was just written by the peers; the frame counter selects the parity buffer)
+        const size_t par = frame_ctr ? (size_t)((*frame_ctr + 1u) & 1u) * parity_stride : 0;
+        const float v = lane < 14 ? bounds[par + tile * 16 + lane] : 0.0f;
+        float* t = reinterpret_cast<float*>(&tb);
+#pragma unroll
+        for (int i = 0; i < 14; i++) t[i] = __shfl_sync(FULL, v, i);
+    }
+    const int L = N / 16;
+    for (int k = class_lo + warp; k < class_hi; k += nwarps) {
         uint16_t* sub = lists + (tile * 16 + k) * (L + 1);
         uint32_t counter = 1;
         constexpr int G = 4;                                  // chunks of 32 VPLs in flight per warp (ILP over the record loads)
@@ -882,16 +913,27 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __rest
         order[tile0 + atomicAdd(&start[127u - min(tile_weight[tile0 + t] / div, 127u)], 1u)] = (uint32_t)(tile0 + t);
 }
 
-// tile rows [ty0, ty1) (the host-input frame culls each G-buffer slab as soon as it is uploaded); the order, if requested,
-// is a permutation of exactly those rows' tiles, stored at their own positions
-int launch_cull_tiled(const float* depth, const uint32_t* face_normal, int W, int H, const VplRecord* records, int N, const Mat4& inv_vp,
-                      int class_lo, int class_hi, int ty0, int ty1, uint16_t* lists, uint32_t* tile_weight, uint32_t* tile_order, cudaStream_t st) {
+// tile rows ty0, ty0 + ystride, ... (nrows of them): the host-input frame culls each G-buffer slab as soon as it is uploaded
+int launch_tile_bounds(const float* depth, const uint32_t* face_normal, int W, int H, const Mat4& inv_vp, int ty0, int ystride, int nrows,
+                       const BoundsOut& bo, cudaStream_t st) {
+    if (nrows <= 0) return 0;
     const int TX = (W + kTile - 1) / kTile;
-    dim3 grid(TX, ty1 - ty0);
-    cull_tiled_kernel<<<grid, 256, 0, st>>>(depth, face_normal, W, H, records, N, inv_vp, class_lo, class_hi, ty0, lists, tile_weight);
-    if (!tile_order) return 1;
-    tile_order_kernel<<<1, 1024, 0, st>>>(tile_weight, ty0 * TX, (ty1 - ty0) * TX, (class_hi - class_lo) * (N / 16), tile_order);
-    return 2;
+    tile_bounds_kernel<<<dim3(TX, nrows), 256, 0, st>>>(depth, face_normal, W, H, inv_vp, ty0, ystride, bo);
+    return 1;
+}
+int launch_tile_lists(const float* bounds, size_t parity_stride, const uint32_t* frame_ctr, int W, const VplRecord* records, int N, int class_lo, int class_hi, int ty0, int ystride, int nrows,
+                      uint16_t* lists, uint32_t* tile_weight, cudaStream_t st) {
+    if (nrows <= 0) return 0;
+    const int TX = (W + kTile - 1) / kTile;
+    const int warps = std::min(16, std::max(1, class_hi - class_lo));       // one warp per class of the tile
+    tile_lists_kernel<<<dim3(TX, nrows), 32 * warps, 0, st>>>(bounds, parity_stride, frame_ctr, records, N, class_lo, class_hi, ty0, ystride, lists, tile_weight);
+    return 1;
+}
+// the order, if requested, is a permutation of the tiles of rows [ty0, ty0 + nrows) (ystride 1), stored at their own positions
+int launch_tile_order(const uint32_t* tile_weight, int W, int N, int class_lo, int class_hi, int ty0, int nrows, uint32_t* tile_order, cudaStream_t st) {
+    const int TX = (W + kTile - 1) / kTile;
+    tile_order_kernel<<<1, 1024, 0, st>>>(tile_weight, ty0 * TX, nrows * TX, (class_hi - class_lo) * (N / 16), tile_order);
+    return 1;
 }
 
 }  // namespace mlgi

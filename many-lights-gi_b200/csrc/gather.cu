@@ -41,6 +41,12 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) { float r; a
 __device__ __forceinline__ float2 lo2(const float4& q) { return make_float2(q.x, q.y); }
 __device__ __forceinline__ float2 hi2(const float4& q) { return make_float2(q.z, q.w); }
 
+// -t*t*(3 - 2t) / 2 = t*t*(t - 1.5): the addition takes an immediate, where 3 - 2t needs a register holding the 2 (a
+// per-iteration IMAD.MOV at 48 registers). Negating and halving are exact (t - 1.5 is the correctly rounded 3 - 2t scaled by
+// -1/2, and round-to-nearest is symmetric), so the shadowed loop accumulates exactly -1/2 of the reference's sums and the
+// epilogue undoes it.
+__device__ __forceinline__ float2 neg_half_smoothstep(float2 t) { return mul2(mul2(t, t), add2(t, dup(-1.5f))); }
+
 struct Normal2 { float2 x, y, z; };   // negated face normals of the two pixels; zero for a pixel that is not active
 
 // Two pixels of one thread, component-wise packed: .x = pixel 0, .y = pixel 1
@@ -106,10 +112,10 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
                     // the unfloored texel coordinate goes to the texture unit, which floors it itself (one packed FMA per
                     // pixel instead of a round-down FMA plus a subtraction)
                     const float2 x0 = fma2(p0, dup(q0), cxy_f), x1 = fma2(p1, dup(q1), cxy_f);
-                    const float o0 = tex2D<float>(ism_tex, x0.x, x0.y);
-                    const float o1 = tex2D<float>(ism_tex, x1.x, x1.y);
+                    const float o0 = tex2DLod<float>(ism_tex, x0.x, x0.y, 0.0f);
+                    const float o1 = tex2DLod<float>(ism_tex, x1.x, x1.y, 0.0f);
                     t.x = fma_sat(o0, 50.0f, tb.x); t.y = fma_sat(o1, 50.0f, tb.y);
-                    g = mul2(g, mul2(mul2(t, t), fma2(t, dup(-2.0f), dup(3.0f))));
+                    g = mul2(g, neg_half_smoothstep(t));
                     g.x = m0[p] > 0.0f ? g.x : 0.0f; g.y = m1[p] > 0.0f ? g.y : 0.0f;
                     px[p].ar = fma2(dup(r3.x), g, px[p].ar);
                     px[p].ag = fma2(dup(r3.y), g, px[p].ag);
@@ -126,8 +132,9 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
                     const float2 k0 = add2(f0, dup(-12582912.0f)), k1 = add2(f1, dup(-12582912.0f));
                     // both fetches are unconditional: the pixel of the pair that is not lit has its g zeroed below and the
                     // texture unit clamps whatever coordinate it is given (no predicates, no per-branch handle reload)
-                    const float o0 = tex2D<float>(ism_tex, k0.x, k0.y);
-                    const float o1 = tex2D<float>(ism_tex, k1.x, k1.y);
+                    // (tex2DLod with level 0 = TEX.LZ: no LOD register to materialise per fetch)
+                    const float o0 = tex2DLod<float>(ism_tex, k0.x, k0.y, 0.0f);
+                    const float o1 = tex2DLod<float>(ism_tex, k1.x, k1.y, 0.0f);
                     // smoothstep(0.98, 1, 1 - (z - occ)); scalar FFMA.SAT: the packed form has no saturate modifier
                     t.x = fma_sat(o0, 50.0f, tb.x); t.y = fma_sat(o1, 50.0f, tb.y);
                 } else {
@@ -142,7 +149,7 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
                     t = fma2(occ, dup(50.0f / 65535.0f), tb);
                     t.x = __saturatef(t.x); t.y = __saturatef(t.y);
                 }
-                g = mul2(g, mul2(mul2(t, t), fma2(t, dup(-2.0f), dup(3.0f))));            // :125-126
+                g = mul2(g, neg_half_smoothstep(t));                                             // :125-126
             }
             g.x = m0[p] > 0.0f ? g.x : 0.0f; g.y = m1[p] > 0.0f ? g.y : 0.0f;
             px[p].ar = fma2(dup(r3.x), g, px[p].ar);                                      // :129
@@ -156,7 +163,9 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
 // issued by one thread each and completing on an mbarrier, double-buffered in two 64-record halves of the staging buffer:
 // chunk c + 1 lands while chunk c is shaded, the first two chunks of a tiled list are already in flight during the pixel
 // prologue, and a chunk costs one CTA barrier instead of two.
-template <int MODE, bool SHADOW, bool STATS, int TEX, int NP, bool BULK>
+// RGB (remote G-buffer): the tile's pixels are read from the rank that uploaded them (GatherArgs::gb_*); a separate
+// instantiation, so that the single-GPU kernel's register budget (48, no spills) is untouched.
+template <int MODE, bool SHADOW, bool STATS, int TEX, int NP, bool BULK, bool RGB = false>
 __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(const GatherArgs a) {
     constexpr int THREADS = 256 / (2 * NP);     // 256 pixels of one class per CTA, 2*NP pixels per thread
     constexpr int NPX = 2 * NP;
@@ -205,6 +214,14 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
         if (count_first > BCH) issue_chunk(sub_first, count_first, 1);
     }
 
+    // the tile's G-buffer: this rank's copy, or (host-input sharded frame) the memory of the rank that uploaded these rows
+    const float* gdepth = a.depth;
+    const uint32_t* gnormal = a.face_normal;
+    if (RGB) {
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+            if (g < a.gb_world && tile_y < a.gb_row_end[g] && (g == 0 || tile_y >= a.gb_row_end[g > 0 ? g - 1 : 0])) { gdepth = a.gb_depth[g]; gnormal = a.gb_normal[g]; }
+    }
     float P[NPX][3], Nn[NPX][3];
     int sx[NPX], sy[NPX], slice[NPX];
     bool valid[NPX];
@@ -218,7 +235,7 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
         P[k][0] = P[k][1] = P[k][2] = 0.0f;
         Nn[k][0] = Nn[k][1] = Nn[k][2] = 0.0f;
         if (valid[k]) {
-            const float depthSample = a.depth[(size_t)y * a.W + x];                // :73
+            const float depthSample = gdepth[(size_t)y * a.W + x];                 // :73
             // World position and normal are evaluated with the oracle's exact operation order (IEEE
             // mul/add/div, no FMA): unprojecting a window depth near 1 cancels catastrophically, so a
             // differently rounded P would move every pair of this pixel by far more than 1e-3.
@@ -231,7 +248,7 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
             for (int r = 0; r < 4; r++)                                            // :75  (m0*x + m1*y) + (m2*z + m3*1)
                 w4[r] = __fadd_rn(__fadd_rn(__fmul_rn(m[r], nx), __fmul_rn(m[4 + r], ny)), __fadd_rn(__fmul_rn(m[8 + r], nz), m[12 + r]));
             P[k][0] = __fdiv_rn(w4[0], w4[3]); P[k][1] = __fdiv_rn(w4[1], w4[3]); P[k][2] = __fdiv_rn(w4[2], w4[3]);   // :76
-            const uint32_t n10 = a.face_normal[(size_t)y * a.W + x];               // :79 (negated: b = -n . d)
+            const uint32_t n10 = gnormal[(size_t)y * a.W + x];                     // :79 (negated: b = -n . d)
             Nn[k][0] = -__fadd_rn(__fmul_rn(__fdiv_rn(float(n10 & 0x3FFu), 1023.0f), 2.0f), -1.0f);
             Nn[k][1] = -__fadd_rn(__fmul_rn(__fdiv_rn(float((n10 >> 10) & 0x3FFu), 1023.0f), 2.0f), -1.0f);
             Nn[k][2] = -__fadd_rn(__fmul_rn(__fdiv_rn(float((n10 >> 20) & 0x3FFu), 1023.0f), 2.0f), -1.0f);
@@ -331,6 +348,7 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
     }
 
     // ---- epilogue: result = acc * giIntensityFactor / vplCount * 16  (:132) ----
+    const float giScale = SHADOW ? 2.0f * a.giScale : a.giScale;     // the shadowed loop accumulates -1/2 of the sums (neg_half_smoothstep)
     const int PW = (a.W + 3) >> 2, PH = (a.H + 3) >> 2;
     const size_t pboff = a.frame_ctr ? (size_t)((*a.frame_ctr + 1u) & 1u) * a.peer_parity_stride : 0;
     // Multi-GPU exchange, packed planes, CTA fully inside the image: the CTA's 16x16 plane entries are staged in shared memory
@@ -345,8 +363,9 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
 #pragma unroll
         for (int k = 0; k < NPX; k++) {
             const PixelPair& pp = px[k >> 1];
-            const float r = (k & 1) ? pp.ar.y : pp.ar.x, g = (k & 1) ? pp.ag.y : pp.ag.x, b = (k & 1) ? pp.ab.y : pp.ab.x;
-            s_out[(pj0 + 4 * k) * 16 + pi] = pack_r11g11b10(r * a.giScale, g * a.giScale, b * a.giScale);
+            float r = (k & 1) ? pp.ar.y : pp.ar.x, g = (k & 1) ? pp.ag.y : pp.ag.x, b = (k & 1) ? pp.ab.y : pp.ab.x;
+            if (SHADOW) { r = 0.0f - r; g = 0.0f - g; b = 0.0f - b; }      // (0 - (+0) = +0: an unlit pixel stays +0)
+            s_out[(pj0 + 4 * k) * 16 + pi] = pack_r11g11b10(r * giScale, g * giScale, b * giScale);
         }
         __syncthreads();
         const size_t row0 = ((size_t)cls * PH + (size_t)tile_y * 16) * PW + (size_t)tile_x * 16;     // plane entry of the CTA's corner
@@ -361,8 +380,9 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
     for (int k = 0; k < NPX; k++) {
         if (!valid[k]) continue;
         const PixelPair& pp = px[k >> 1];
-        const float r = (k & 1) ? pp.ar.y : pp.ar.x, g = (k & 1) ? pp.ag.y : pp.ag.x, b = (k & 1) ? pp.ab.y : pp.ab.x;
-        const float4 o = make_float4(r * a.giScale, g * a.giScale, b * a.giScale, 0.0f);
+        float r = (k & 1) ? pp.ar.y : pp.ar.x, g = (k & 1) ? pp.ag.y : pp.ag.x, b = (k & 1) ? pp.ab.y : pp.ab.x;
+        if (SHADOW) { r = 0.0f - r; g = 0.0f - g; b = 0.0f - b; }
+        const float4 o = make_float4(r * giScale, g * giScale, b * giScale, 0.0f);
         if (a.out_raster) a.out_raster[(size_t)sy[k] * a.W + sx[k]] = o;
         if (a.out_planar) a.out_planar[((size_t)(cls - a.planar_class0) * PH + (sy[k] >> 2)) * PW + (sx[k] >> 2)] = o;
         if (a.out_packed) a.out_packed[(size_t)sy[k] * a.W + sx[k]] = pack_r11g11b10(o.x, o.y, o.z);
@@ -395,6 +415,12 @@ template <int MODE>
 static void launch_fg_mode(const GatherArgs& a, dim3 grid, cudaStream_t st) {
     const bool sh = a.enable_shadowing != 0, stt = a.stats != nullptr;
     const bool tex = sh && a.ism_tex != 0;      // the ISM is fetched through the texture unit whenever a texture object exists
+    if (a.gb_world) {                            // host-input sharded frame: G-buffer rows live on the rank that uploaded them
+        if (!sh) final_gather_kernel<MODE, false, false, 0, 1, false, true><<<grid, 128, 0, st>>>(a);
+        else if (!tex) final_gather_kernel<MODE, true, false, 0, 1, false, true><<<grid, 128, 0, st>>>(a);
+        else final_gather_kernel<MODE, true, false, 1, 1, true, true><<<grid, 128, 0, st>>>(a);
+        return;
+    }
     if (!stt && tex && a.tex_float_coord) { final_gather_kernel<MODE, true, false, 2, 1, false><<<grid, 128, 0, st>>>(a); return; }
     if (stt) {                                   // counting variant (work counters for the roofline accounting)
         if (sh) final_gather_kernel<MODE, true, true, 0, 1, false><<<grid, 128, 0, st>>>(a);
@@ -473,9 +499,9 @@ __global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs x) {
     if (x.packed && (PW & 3) == 0 && (x.W & 15) == 0) {
         // unit = (raster row y, 16-pixel group i4): planes 4*cy .. 4*cy+3, entries [py][4*i4 .. 4*i4+3]
         const int groups = PW >> 2;
-        const long long units = (long long)x.H * groups;
+        const long long units = (long long)(x.row_end - x.row_begin) * groups;
         for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
-            const int y = (int)(u / groups), i4 = (int)(u - (long long)y * groups);
+            const int y = x.row_begin + (int)(u / groups), i4 = (int)(u - (long long)(y - x.row_begin) * groups);
             const int cy = y & 3, py = y >> 2;
             uint4 pl[4];
 #pragma unroll
@@ -499,8 +525,9 @@ __global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs x) {
         }
     } else {
         // general shapes / fp32 planes: one pixel per thread
-        const long long n = (long long)x.W * x.H;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = (long long)x.W * (x.row_end - x.row_begin), i0 = (long long)x.W * x.row_begin;
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+            const long long i = i0 + j;
             const int y = (int)(i / x.W), xx = (int)(i - (long long)y * x.W);
             const int cls = (xx & 3) + 4 * (y & 3);
             const char* base = x.src[cls / per] + par;
@@ -528,7 +555,7 @@ __global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs x) {
 }
 int launch_exchange(const ExchangeArgs& x, cudaStream_t st) {
     // every CTA must be resident (all of them spin on the flags before any of them can finish): at most one wave
-    const long long work = ((long long)x.W * x.H) / 16 + 1;
+    const long long work = ((long long)x.W * (x.row_end - x.row_begin)) / 16 + 1;
     const int grid = (int)std::max(1LL, std::min<long long>(148 * 4, (work + 255) / 256));
     exchange_kernel<<<grid, 256, 0, st>>>(x);
     return 1;
@@ -616,33 +643,70 @@ float measure_fp32_peak_tflops(int device, cudaStream_t st) {
 
 // =====================================================================================
 // n1: gi_blur.frag:24-72, the two separable 7-tap passes of GIStage::blur (GIStage.cpp:308-344) as ONE kernel. A CTA owns a
-// 32x16-pixel tile: it stages the tile plus a 3-pixel halo (GI colour, linearised depth, decoded normal: each texel is
-// fetched and decoded once instead of once per tap and pass) in shared memory, runs the horizontal pass for the tile rows
-// and the vertical halo into shared memory, then the vertical pass. HBM traffic per pixel: 16 B (fp32 GI) or 4 B
-// (GL_R11F_G11F_B10F GI, the reference's giBuffer format) + 4 B depth + 4 B normal in, 16 B out -- the intermediate image of
-// the two-pass form (16 B written + 7 x 16 B read per pixel) never leaves the SM. Out-of-image taps are skipped (texelFetch
-// outside the image is undefined in GL; same choice as the oracle).
+// 32x26-pixel tile and stages the tile plus a 3-pixel halo (38x32 texels: GI colour, linearised depth, decoded normal -- each
+// texel is fetched and decoded once instead of once per tap and pass) in shared memory; the intermediate image of the
+// two-pass form never leaves the SM. HBM traffic per pixel: 4 B (GL_R11F_G11F_B10F GI, the reference's giBuffer format) or
+// 16 B (fp32 GI) + 4 B depth + 4 B normal in, 16 B out.
+// The passes are bound by shared-memory traffic (7 values per tap), so each thread computes a RUN of 4 consecutive outputs
+// along the pass direction from a 10-texel window held in registers (2.5 instead of 7 texel reads per output), and the
+// weight of a texel pair -- symmetric in its two texels (:24-47) -- is evaluated once and used for both outputs (18 instead
+// of 24 weights per run). Lanes run ACROSS the pass direction (horizontal pass: lane = row; vertical pass: lane = column) and
+// the planes have odd pitches, so every shared-memory access of a warp is conflict-free.
+// Out-of-image taps are skipped by the reference (texelFetch outside the image is undefined in GL; same choice as the
+// oracle): such texels are staged with depth 1e18, which drives the weight to max(0, -huge) = 0 exactly.
 // =====================================================================================
 namespace blur {
-constexpr int TW = 32, TH = 16, R = 3, SW = TW + 2 * R, SH = TH + 2 * R;
+constexpr int TW = 32, TH = 26, R = 3, SW = TW + 2 * R, SH = TH + 2 * R, PITCH = SW + 1, TPITCH = TW + 1, RUN = 4, WIN = RUN + 2 * R;
+static_assert(SH == 32 && TW == 32, "lanes map to staged rows (horizontal pass) and tile columns (vertical pass)");
+struct Texel { float r, g, b, d, nx, ny, nz; };
+// weight between two texels i apart (gi_blur.frag:24-47); symmetric in (c, t)
+__device__ __forceinline__ float weight(const Texel& c, const Texel& t, int i) {
+    const float normalFactor = 1.0f - fmaxf(0.0f, c.nx * t.nx + c.ny * t.ny + c.nz * t.nz);   // :44
+    const float depthDiff = t.d - c.d;
+    const float nd = normalFactor * 5.0f;
+    return fmaxf(0.0f, (3.0f - float(i) + 1.0f) / 4.0f - depthDiff * depthDiff - nd * nd);
 }
+// one run: outputs are window positions R .. R + RUN - 1; acc starts at the centre texel with weight 1 (:60)
+__device__ __forceinline__ void run_pass(const Texel (&w)[WIN], float (&ar)[RUN], float (&ag)[RUN], float (&ab)[RUN]) {
+    float fa[RUN];
+#pragma unroll
+    for (int j = 0; j < RUN; j++) { ar[j] = w[R + j].r; ag[j] = w[R + j].g; ab[j] = w[R + j].b; fa[j] = 1.0f; }
+#pragma unroll
+    for (int p = 0; p < WIN; p++)
+#pragma unroll
+        for (int i = 1; i <= R; i++) {                                                         // :63-69, both directions at once
+            const int q = p + i;
+            if (q >= WIN) continue;
+            const bool op = p >= R && p < R + RUN, oq = q >= R && q < R + RUN;
+            if (!op && !oq) continue;
+            const float wt = weight(w[p], w[q], i);
+            if (op) { fa[p - R] += wt; ar[p - R] += w[q].r * wt; ag[p - R] += w[q].g * wt; ab[p - R] += w[q].b * wt; }
+            if (oq) { fa[q - R] += wt; ar[q - R] += w[p].r * wt; ag[q - R] += w[p].g * wt; ab[q - R] += w[p].b * wt; }
+        }
+#pragma unroll
+    for (int j = 0; j < RUN; j++) {                                                            // :71
+        const float inv = __frcp_rn(fa[j]);                                                    // fa >= 1
+        ar[j] *= inv; ag[j] *= inv; ab[j] *= inv;
+    }
+}
+}  // namespace blur
 template <bool PACKED>
-__global__ void __launch_bounds__(256) gi_blur_fused_kernel(const float4* __restrict__ gi, const uint32_t* __restrict__ gi_packed,
-                                                            const float* __restrict__ depth, const uint32_t* __restrict__ face_normal,
-                                                            int W, int H, float projA, float projB, float4* __restrict__ out) {
+__global__ void __launch_bounds__(256, 4) gi_blur_fused_kernel(const float4* __restrict__ gi, const uint32_t* __restrict__ gi_packed,
+                                                               const float* __restrict__ depth, const uint32_t* __restrict__ face_normal,
+                                                               int W, int H, float projA, float projB, float4* __restrict__ out) {
     using namespace blur;
-    __shared__ float s_rgb[3][SH][SW], s_d[SH][SW], s_n[3][SH][SW];
-    __shared__ float s_tmp[3][SH][TW];
+    __shared__ float s_c[3][SH][PITCH], s_d[SH][PITCH], s_n[3][SH][PITCH];
+    __shared__ float s_t[3][SH][TPITCH];
     const int x0 = blockIdx.x * TW - R, y0 = blockIdx.y * TH - R;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q = threadIdx.x; q < SW * SH; q += 256) {
         const int lx = q % SW, ly = q / SW, x = x0 + lx, y = y0 + ly;
-        float r = 0.0f, g = 0.0f, b = 0.0f, d = 0.0f, nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        float r = 0.0f, g = 0.0f, b = 0.0f, d = 1e18f, nx = 0.0f, ny = 0.0f, nz = 0.0f;
         if (x >= 0 && y >= 0 && x < W && y < H) {
             const size_t t = (size_t)y * W + x;
             if (PACKED) {
                 const uint32_t v = __ldg(gi_packed + t);
-                r = __uint_as_float(unpack_ufloat_bits<6>(v & 0x7FFu)); g = __uint_as_float(unpack_ufloat_bits<6>((v >> 11) & 0x7FFu));
-                b = __uint_as_float(unpack_ufloat_bits<5>(v >> 22));
+                r = unpack_ufloat_fast<6>(v & 0x7FFu); g = unpack_ufloat_fast<6>((v >> 11) & 0x7FFu); b = unpack_ufloat_fast<5>(v >> 22);
             } else {
                 const float4 c = __ldg(gi + t);
                 r = c.x; g = c.y; b = c.z;
@@ -652,52 +716,41 @@ __global__ void __launch_bounds__(256) gi_blur_fused_kernel(const float4* __rest
             nx = float(n10 & 0x3FFu) * (2.0f / 1023.0f) - 1.0f; ny = float((n10 >> 10) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f;
             nz = float((n10 >> 20) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f;
         }
-        s_rgb[0][ly][lx] = r; s_rgb[1][ly][lx] = g; s_rgb[2][ly][lx] = b; s_d[ly][lx] = d;
+        s_c[0][ly][lx] = r; s_c[1][ly][lx] = g; s_c[2][ly][lx] = b; s_d[ly][lx] = d;
         s_n[0][ly][lx] = nx; s_n[1][ly][lx] = ny; s_n[2][ly][lx] = nz;
     }
     __syncthreads();
-    // weight of tap (tx, ty) for centre (cx, cy), gi_blur.frag:24-47
-    auto weight = [&](int cx, int cy, int tx, int ty, int i) {
-        const float normalFactor = 1.0f - fmaxf(0.0f, s_n[0][cy][cx] * s_n[0][ty][tx] + s_n[1][cy][cx] * s_n[1][ty][tx] + s_n[2][cy][cx] * s_n[2][ty][tx]);   // :44
-        const float depthDiff = s_d[ty][tx] - s_d[cy][cx];
-        const float nd = normalFactor * 5.0f;
-        return fmaxf(0.0f, (3.0f - float(i) + 1.0f) / 4.0f - depthDiff * depthDiff - nd * nd);
-    };
-    // horizontal pass (DIRECTION (1,0), GIStage.cpp:427) for every staged row: SH x TW results
-    for (int q = threadIdx.x; q < SH * TW; q += 256) {
-        const int lx = q % TW + R, ly = q / TW, x = x0 + lx, y = y0 + ly;
-        float ar = s_rgb[0][ly][lx], ag = s_rgb[1][ly][lx], ab = s_rgb[2][ly][lx], fa = 1.0f;   // :60
-        if (x < W && y >= 0 && y < H) {
+    float ar[RUN], ag[RUN], ab[RUN];
+    {   // horizontal pass (DIRECTION (1,0), GIStage.cpp:427): lane = staged row, warp w -> tile columns 4w .. 4w+3
+        const int row = lane, c0 = RUN * warp;                                             // window = staged columns c0 .. c0+9
+        Texel w[WIN];
 #pragma unroll
-            for (int sgn = -1; sgn <= 1; sgn += 2)
+        for (int k = 0; k < WIN; k++)
+            w[k] = Texel{s_c[0][row][c0 + k], s_c[1][row][c0 + k], s_c[2][row][c0 + k], s_d[row][c0 + k],
+                         s_n[0][row][c0 + k], s_n[1][row][c0 + k], s_n[2][row][c0 + k]};
+        run_pass(w, ar, ag, ab);
 #pragma unroll
-                for (int i = 1; i <= 3; i++) {                                             // :63-69
-                    const int tx = x + sgn * i;
-                    if (tx < 0 || tx >= W) continue;
-                    const float w = weight(lx, ly, lx + sgn * i, ly, i);
-                    fa += w;
-                    ar += s_rgb[0][ly][lx + sgn * i] * w; ag += s_rgb[1][ly][lx + sgn * i] * w; ab += s_rgb[2][ly][lx + sgn * i] * w;
-                }
-        }
-        s_tmp[0][ly][lx - R] = ar / fa; s_tmp[1][ly][lx - R] = ag / fa; s_tmp[2][ly][lx - R] = ab / fa;   // :71
+        for (int j = 0; j < RUN; j++) { s_t[0][row][c0 + j] = ar[j]; s_t[1][row][c0 + j] = ag[j]; s_t[2][row][c0 + j] = ab[j]; }
     }
     __syncthreads();
-    // vertical pass (DIRECTION (0,1), GIStage.cpp:431)
-    for (int q = threadIdx.x; q < TH * TW; q += 256) {
-        const int lx = q % TW, ly = q / TW + R, x = x0 + R + lx, y = y0 + ly;
-        if (x >= W || y >= H) continue;
-        float ar = s_tmp[0][ly][lx], ag = s_tmp[1][ly][lx], ab = s_tmp[2][ly][lx], fa = 1.0f;
+    {   // vertical pass (DIRECTION (0,1), GIStage.cpp:431): lane = tile column, warp w -> tile rows 4w .. 4w+3 (w = 6: two rows)
+        const int col = lane, r0 = RUN * warp;                                             // window = staged rows r0 .. r0+9
+        if (r0 >= TH) return;
+        Texel w[WIN];
 #pragma unroll
-        for (int sgn = -1; sgn <= 1; sgn += 2)
+        for (int k = 0; k < WIN; k++) {
+            const int rr = r0 + k;
+            if (rr < SH) w[k] = Texel{s_t[0][rr][col], s_t[1][rr][col], s_t[2][rr][col], s_d[rr][col + R],
+                                      s_n[0][rr][col + R], s_n[1][rr][col + R], s_n[2][rr][col + R]};
+            else w[k] = Texel{0.0f, 0.0f, 0.0f, 1e18f, 0.0f, 0.0f, 0.0f};                  // below the staged rows: only reached by rows that are not stored
+        }
+        run_pass(w, ar, ag, ab);
+        const int x = x0 + R + col;
 #pragma unroll
-            for (int i = 1; i <= 3; i++) {
-                const int ty = y + sgn * i;
-                if (ty < 0 || ty >= H) continue;
-                const float w = weight(lx + R, ly, lx + R, ly + sgn * i, i);
-                fa += w;
-                ar += s_tmp[0][ly + sgn * i][lx] * w; ag += s_tmp[1][ly + sgn * i][lx] * w; ab += s_tmp[2][ly + sgn * i][lx] * w;
-            }
-        out[(size_t)y * W + x] = make_float4(ar / fa, ag / fa, ab / fa, 0.0f);
+        for (int j = 0; j < RUN; j++) {
+            const int y = y0 + R + r0 + j;
+            if (r0 + j < TH && x < W && y < H) out[(size_t)y * W + x] = make_float4(ar[j], ag[j], ab[j], 0.0f);
+        }
     }
 }
 int launch_gi_blur(const float4* gi, const uint32_t* gi_packed, const float* depth, const uint32_t* face_normal, int W, int H, float projA,

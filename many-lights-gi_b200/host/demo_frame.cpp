@@ -1,10 +1,11 @@
 // demo_frame.cpp -- drives one GI frame through the C++ stage classes (mlgi_stages.hpp), the way
 // MultiFramePainter::onPaint drives GIStage::process (MultiFramePainter.cpp:182-201), on the synthetic
 // atrium fixture. Prints per-stage timers (PerfCounter scope names) and a checksum of the GI image.
-//   usage: demo_frame [width height vpls]
+//   usage: demo_frame [width height vpls [gi_image.raw]]   (the raw file receives the fp32 RGBA GI image of the graph-replayed frame)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -69,16 +70,34 @@ int main(int argc, char** argv) {
         gi.rsmRenderer.light = light;
         float* dv = upload(verts); float* dn = upload(normals); uint32_t* di = upload(indices); uint32_t* dp = upload(prim);
         gi.drawablesMap = {dv, dn, di, dp, nv, nt};
-        for (int i = 0; i < 3; i++) gi.process();      // frames; the last one is reported
+        for (int i = 0; i < 3; i++) gi.process();      // frames (direct launches: the per-stage timers are on); the last one is reported
         cudaDeviceSynchronize();
         mlgi_timing t[16];
         const int n = mlgi_get_timings(gi.context().get(), t, 16);
         for (int i = 0; i < n; i++) printf("%-12s %8.3f ms  (%d launches)\n", t[i].name, t[i].ms, t[i].launches);
-        std::vector<float> img((size_t)W * H * 4);
+        std::vector<float> img((size_t)W * H * 4), img2((size_t)W * H * 4);
         gi.context().check(mlgi_read_buffer(gi.context().get(), MLGI_BUF_GI, img.data(), img.size() * 4, 0));
+        // the same frame as one CUDA-graph launch (timers off), and stage by stage on one stream: all three must agree to the bit
+        gi.context().check(mlgi_set_timers(gi.context().get(), 0));
+        gi.process(nullptr, false);
+        gi.context().check(mlgi_read_buffer(gi.context().get(), MLGI_BUF_GI, img2.data(), img2.size() * 4, 0));
+        const bool same_graph = memcmp(img.data(), img2.data(), img.size() * 4) == 0;
+        gi.processStaged(nullptr, false);
+        gi.context().check(mlgi_read_buffer(gi.context().get(), MLGI_BUF_GI, img2.data(), img2.size() * 4, 0));
+        const bool same_staged = memcmp(img.data(), img2.data(), img.size() * 4) == 0;
+        mlgi_frame_stats fs;
+        mlgi_get_frame_stats(gi.context().get(), &fs);
+        printf("graph replay == direct launches: %s, staged == direct launches: %s (graph replays %llu)\n", same_graph ? "yes" : "NO",
+               same_staged ? "yes" : "NO", (unsigned long long)fs.graph_replays);
+        if (argc > 4) {
+            FILE* f = fopen(argv[4], "wb");
+            if (!f || fwrite(img2.data(), 4, img2.size(), f) != img2.size()) { fprintf(stderr, "cannot write %s\n", argv[4]); return 2; }
+            fclose(f);
+        }
         double sum = 0;
         for (size_t i = 0; i < img.size(); i += 4) sum += img[i] + img[i + 1] + img[i + 2];
         printf("mean radiance %.6f  (%dx%d, %d VPLs, %d triangles)\n", sum / (3.0 * W * H), W, H, N, nt);
+        if (!same_graph || !same_staged) return 3;
     } catch (const mlgi::Error& e) {
         fprintf(stderr, "%s\n", e.what());
         return 1;

@@ -182,8 +182,17 @@ public:
 
     Context& context() { return m_ctx; }
 
-    // GIStage.cpp:346-418 (the RSM raster :367-371 is the caller's: rsmRenderer holds its outputs)
+    // GIStage.cpp:346-418 (the RSM raster :367-371 is the caller's: rsmRenderer holds its outputs). One call = mlgi_frame: the
+    // stages in the reference's order with culling and the VPL build forked beside point generation, replayed as a CUDA graph
+    // (direct launches while per-stage timers are enabled).
     void process(void* stream = nullptr, bool blurPass = true) {
+        mlgi_params p = params();
+        mlgi_gbuffer gb = {depthBuffer, faceNormalBuffer};
+        m_ctx.check(mlgi_frame(m_ctx.get(), &rsmRenderer.buffers, &rsmRenderer.light, &drawablesMap, &gb, &camera, &p, stream));
+        if (blurPass) blur(stream);                                                                                    // :410-417
+    }
+    // the same frame issued stage by stage on one stream, literally as GIStage.cpp:373-417 does on its GL queue
+    void processStaged(void* stream = nullptr, bool blurPass = true) {
         mlgi_params p = params();
         vplProcessor.process(rsmRenderer, lightIntensity, shuffleLights, p, stream);                                   // :373-376
         ism.process(drawablesMap, vplProcessor, vplStartIndex, vplEndIndex, scaleISMs, pointsOnlyIntoScaledISMs,
@@ -192,6 +201,33 @@ public:
         else clusteredShading.process(vplProcessor, camera.view, camera.proj, zFar, vplStartIndex, vplEndIndex, depthBuffer, p, stream);   // :392-403
         compute_final_gathering(stream);                                                                               // :405-408
         if (blurPass) blur(stream);                                                                                    // :410-417
+    }
+    // Multi-GPU (no counterpart in the reference): one GIStage per GPU, each owning the interleave classes
+    // [16 r / world, 16 (r+1) / world) (cfg.class_lo / class_hi). exchangeCreate + exchangeConnect (one process per GPU: the
+    // 64-byte handles travel over any host transport) or connectLocal (one process driving all GPUs), then processSharded on
+    // every rank per frame: mlgi_frame + the peer-memory exchange as one graph launch; giPackedBuffer / giBuffer then hold the
+    // whole image on every rank.
+    void exchangeCreate(int rank, int world, void* outHandle64) { m_ctx.check(mlgi_exchange_create(m_ctx.get(), rank, world, outHandle64)); }
+    void exchangeConnect(const void* allHandles) { m_ctx.check(mlgi_exchange_connect(m_ctx.get(), allHandles)); }
+    static void connectLocal(GIStage* const* ranks, int world) {
+        mlgi_ctx* all[8] = {nullptr};
+        unsigned char handle[64];
+        for (int r = 0; r < world; r++) { ranks[r]->exchangeCreate(r, world, handle); all[r] = ranks[r]->m_ctx.get(); }
+        for (int r = 0; r < world; r++) ranks[r]->m_ctx.check(mlgi_exchange_connect_local(all[r], all));
+    }
+    void processSharded(void* stream = nullptr) {
+        mlgi_params p = params();
+        mlgi_gbuffer gb = {depthBuffer, faceNormalBuffer};
+        m_ctx.check(mlgi_frame_sharded(m_ctx.get(), &rsmRenderer.buffers, &rsmRenderer.light, &drawablesMap, &gb, &camera, &p, stream));
+    }
+    // host-input forms: pinned host RSM / G-buffer in, GL_R11F_G11F_B10F image out (GIStage.cpp:470's giBuffer format)
+    void processHost(const mlgi_rsm& hostRsm, const mlgi_gbuffer& hostGbuffer, uint32_t* hostGiPacked, void* stream = nullptr) {
+        mlgi_params p = params();
+        m_ctx.check(mlgi_frame_host_packed(m_ctx.get(), &hostRsm, &rsmRenderer.light, &drawablesMap, &hostGbuffer, &camera, &p, hostGiPacked, stream));
+    }
+    void processShardedHost(const mlgi_rsm& hostRsm, const mlgi_gbuffer& hostGbuffer, uint32_t* hostGiPacked, void* stream = nullptr) {
+        mlgi_params p = params();
+        m_ctx.check(mlgi_frame_sharded_host(m_ctx.get(), &hostRsm, &rsmRenderer.light, &drawablesMap, &hostGbuffer, &camera, &p, hostGiPacked, stream));
     }
 
     VPLProcessor vplProcessor;

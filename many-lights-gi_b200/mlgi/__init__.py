@@ -78,7 +78,7 @@ EXPORTS = [
     "mlgi_vpl_process", "mlgi_ism_points", "mlgi_ism_set_points", "mlgi_ism_splat", "mlgi_ism_pullpush",
     "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_composite_ambient", "mlgi_frame", "mlgi_frame_host", "mlgi_frame_host_packed",
     "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_read_buffer_async", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_debug_sqrt_thresholds", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_exchange_create", "mlgi_exchange_connect", "mlgi_exchange_connect_local", "mlgi_exchange_finish", "mlgi_exchange_status",
-    "mlgi_frame_sharded", "mlgi_frame_sharded_host", "mlgi_set_graph", "mlgi_get_frame_stats", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
+    "mlgi_frame_sharded", "mlgi_frame_sharded_host", "mlgi_sharded_rows", "mlgi_set_graph", "mlgi_get_frame_stats", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
 ]
 
 _lib = None
@@ -138,6 +138,7 @@ def load():
     lib.mlgi_exchange_connect_local.argtypes = [P, C.POINTER(P)]
     lib.mlgi_frame_sharded.argtypes = lib.mlgi_frame.argtypes
     lib.mlgi_frame_sharded_host.argtypes = lib.mlgi_frame_host.argtypes
+    lib.mlgi_sharded_rows.argtypes = [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mlgi_set_graph.argtypes = [P, C.c_int]
     lib.mlgi_get_frame_stats.argtypes = [P, C.POINTER(FrameStats)]
     lib.mlgi_exchange_finish.argtypes = [P, P]
@@ -257,6 +258,12 @@ class Context:
     def frame_sharded_host(self, host_rsm, light, dev_mesh, host_gb, cam, params, host_gi_packed=None, stream=None):
         self._ck(self.lib.mlgi_frame_sharded_host(self.h, C.byref(host_rsm), C.byref(light), C.byref(dev_mesh), C.byref(host_gb),
                                                   C.byref(cam), C.byref(params), _ptr(host_gi_packed), stream))
+
+    def sharded_rows(self):
+        """image rows [y0, y1) this rank uploads / bounds / returns in the sharded frames"""
+        y0, y1 = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.mlgi_sharded_rows(self.h, C.byref(y0), C.byref(y1)))
+        return int(y0.value), int(y1.value)
 
     def set_graph(self, enable):
         self._ck(self.lib.mlgi_set_graph(self.h, int(enable)))

@@ -10,6 +10,11 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Some -m gpu tests emulate two ranks on ONE GPU: rank 0's exchange kernel spins until rank 1's frame (issued later, on other
+# streams) has signalled. With the default 8 hardware work queues, unrelated streams can share a queue, and a kernel of rank 1
+# queued behind rank 0's spinning kernel would never start (a false dependency that cannot occur with one process per GPU).
+# More queues remove the aliasing; read by the driver when the CUDA context is created, i.e. after this line.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 for p in (os.path.join(ROOT, "many-lights-gi_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fixtures"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)

@@ -4,6 +4,7 @@
 // libmlgi.so; the product has no CPU path.
 #include <vector>
 #include "../../many-lights-gi_b200/csrc/pullpush_core.cuh"
+#include "../../many-lights-gi_b200/csrc/common.cuh"
 
 using namespace mlgi::pp;
 
@@ -32,4 +33,14 @@ void pp_emu(const uint32_t* atlas, int S, float zFar, float ismPixelSize, uint16
                 for (int c = 0; c < 64; c++) ism[(size_t)(gy0 + r) * A + gx0 + c] = (uint16_t)s.L0[r * 64 + c];
         }
     }
+}
+
+// unpack_ufloat_fast (the branch-free decode the blur / de-interleave kernels use) against unpack_ufloat_bits (the reference
+// decode the oracle mirrors), for every 11-bit and 10-bit code: number of codes whose fp32 bit patterns differ
+extern "C" __attribute__((visibility("default")))
+int ufloat_fast_mismatches() {
+    int bad = 0;
+    for (uint32_t v = 0; v < 2048; v++) { float f = mlgi::unpack_ufloat_fast<6>(v); uint32_t b; memcpy(&b, &f, 4); bad += b != mlgi::unpack_ufloat_bits<6>(v); }
+    for (uint32_t v = 0; v < 1024; v++) { float f = mlgi::unpack_ufloat_fast<5>(v); uint32_t b; memcpy(&b, &f, 4); bad += b != mlgi::unpack_ufloat_bits<5>(v); }
+    return bad;
 }

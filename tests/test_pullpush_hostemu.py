@@ -58,3 +58,11 @@ def test_phases_match_oracle_on_synthetic_atlases(emu, N):
 def test_other_z_far(emu, case_small):
     atlas = case_small.get("atlas")
     assert np.array_equal(emu(atlas, 20.0), O.ism_pullpush(atlas, case_small.N, 20.0))
+
+
+def test_fast_ufloat_decode_equals_reference_decode_for_every_code(emu):
+    """common.cuh unpack_ufloat_fast (branch-free decode of the R11F_G11F_B10F channels used by the blur and de-interleave
+    kernels) against unpack_ufloat_bits, all 2048 + 1024 codes including subnormals, inf and NaN"""
+    lib = C.CDLL(os.path.join(HERE, "libpp_emu.so"))
+    lib.ufloat_fast_mismatches.restype = C.c_int
+    assert lib.ufloat_fast_mismatches() == 0

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) k(float* out, int iters, float a, float b
             if (MODE == 0) { x[i].x = fmaf(x[i].x, a, b); x[i].y = fmaf(x[i].y, a, b); }
             if (MODE == 1) { x[i] = __ffma2_rn(x[i], A, B); }
             if (MODE == 2) { x[i] = __ffma2_rn(x[i], A, B); u = (u ^ (u >> 3)) + 0x9E3779B9u; }            // + 2 ALU ops per FFMA2
+            if (MODE == 4) { x[i] = __ffma2_rn(x[i], A, B); if (i & 1) u = (u ^ (u >> 3)); }                           // + 1/2 ALU op per FFMA2
+            if (MODE == 5) { float sc = __uint_as_float(u | 0x3F000000u); x[i] = __ffma2_rn(x[i], make_float2(sc, sc), B); }   // scalar-broadcast operand (R.F32)
             if (MODE == 3) { x[i].x = fmaf(x[i].x, a, b); x[i].y = fmaf(x[i].y, a, b); u = (u ^ (u >> 3)) + 0x9E3779B9u; }
         }
     }
@@ -29,4 +31,4 @@ template <int MODE> void run(const char* name) {
     double fma = 16.0 * iters * 256.0 * blocks;
     printf("%-28s %.3f ms  %.2f TFLOP/s (fp32 fma flops)\n", name, best, 2 * fma / best / 1e9);
 }
-int main() { run<0>("FFMA x2"); run<1>("FFMA2"); run<2>("FFMA2 + 2 ALU"); run<3>("FFMA x2 + 2 ALU"); return 0; }
+int main() { run<0>("FFMA x2"); run<1>("FFMA2"); run<2>("FFMA2 + 2 ALU"); run<3>("FFMA x2 + 2 ALU"); run<4>("FFMA2 + 0.5 ALU"); run<5>("FFMA2 bcast operand"); return 0; }
