@@ -15,6 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # queued behind rank 0's spinning kernel would never start (a false dependency that cannot occur with one process per GPU).
 # More queues remove the aliasing; read by the driver when the CUDA context is created, i.e. after this line.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# Same emulation, second hazard: with lazy module loading the FIRST launch of a kernel loads it, which can wait for running
+# work -- i.e. for rank 0's spinning kernel, which waits for that very launch of rank 1 (measured: a 2 s bounded-wait timeout in
+# the first frame only). Loading every kernel when the context is created removes it.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 for p in (os.path.join(ROOT, "many-lights-gi_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fixtures"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)

@@ -430,7 +430,7 @@ def test_timers_and_launch_count(case_small):
     p = mlgi.default_params(case_small.N)
     n0 = g.ctx.launch_count()
     g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
-    assert g.ctx.launch_count() - n0 == 7      # VPLP, points, splat, pull-push, tiled cull + tile order, gathering
+    assert g.ctx.launch_count() - n0 == 8      # VPLP, points, splat, pull-push, tile bounds + tile lists + tile order, gathering
     t = g.ctx.timings()
     for name in ("VPLP", "ISM render", "ISM CS", "PullPush", "Tiled cull", "FG"):   # PerfCounter scope names
         assert name in t and t[name][0] >= 0.0
@@ -653,7 +653,7 @@ def test_graph_replay_matches_direct_launches(case_mid):
         g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
     st = g.ctx.frame_stats()
     assert st["graph_enabled"] and st["graph_replays"] == 3 and st["graph_instantiations"] == 1
-    assert g.ctx.launch_count() - n_direct == 3 * 7          # the replayed launches are counted like direct ones
+    assert g.ctx.launch_count() - n_direct == 3 * 8          # the replayed launches are counted like direct ones
     assert np.array_equal(g.ctx.download(mlgi.BUF_ISM, np.uint16), ism0)
     assert np.array_equal(g.ctx.download(mlgi.BUF_GI, np.float32), gi0)
     assert np.array_equal(g.ctx.download(mlgi.BUF_TILE_LISTS, np.uint16), lists0)
@@ -784,6 +784,8 @@ def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid):
         for t in th:
             t.join(timeout=120)
         assert not errors, errors
+        for s in shards:
+            s.exchange_status()          # a timed-out wait (a rank that never signalled) is an error, not a wrong image
         for r in range(world):
             y0, y1 = rows[r]
             got = bufs[r].numpy().view(np.uint32)
