@@ -446,15 +446,16 @@ def main():
         host_gi = torch.zeros((H, W), dtype=torch.int32).pin_memory()          # R11F_G11F_B10F
         hr, hg = mlgi.make_rsm(h[0], h[1], h[2]), mlgi.make_gbuffer(h[3], h[4])
         n_e2e = max(5, min(args.steps, 50))
-        y0, y1 = 0, H
+        rowmask = np.ones(H, dtype=bool)
         if not job.sharded:
             def e2e_step():
                 ctx.frame_host_packed(hr, job.light, job.mesh, hg, cam, params, host_gi_packed=host_gi, stream=job.stream)
         else:
-            # N > 1, ONE library call per rank and frame: upload of the RSM and of this rank's 1/N of the G-buffer rows from pinned
-            # host memory, copy-engine push of the slab to every peer over NVLink beside the ISM build, stages, plane exchange,
-            # read-back of this rank's 1/N of the assembled image rows -- the union over ranks is the full result on the host
-            y0, y1 = ctx.sharded_rows()
+            # N > 1, ONE library call per rank and frame: upload of the RSM and of this rank's 1/N of the G-buffer rows (its tile
+            # rows t mod N) from pinned host memory, tile-bounds exchange, gathering with remote G-buffer reads over NVLink, plane
+            # exchange, read-back of this rank's 1/N of the assembled image rows, pipelined in phases -- the union over ranks is
+            # the full result on the host
+            rowmask = ctx.sharded_row_mask()
             def e2e_step():
                 ctx.frame_sharded_host(hr, job.light, job.mesh, hg, cam, params, host_gi_packed=host_gi, stream=job.stream)
         for _ in range(3):
@@ -470,7 +471,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         # the end-to-end path must have produced the image of the device-resident path (same inputs): this rank's rows
-        e2e_ok = bool(np.array_equal(host_gi.numpy().view(np.uint32)[y0:y1], img.reshape(H, W)[y0:y1]))
+        e2e_ok = bool(np.array_equal(host_gi.numpy().view(np.uint32)[rowmask], img.reshape(H, W)[rowmask]))
         if world > 1:
             t = torch.tensor([1.0 if e2e_ok else 0.0], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -256,16 +256,19 @@ MLGI_API int mlgi_exchange_status(mlgi_ctx*);
  * the job calls it once per frame. */
 MLGI_API int mlgi_frame_sharded(mlgi_ctx*, const mlgi_rsm*, const mlgi_camera* light, const mlgi_mesh*,
                                 const mlgi_gbuffer*, const mlgi_camera* cam, const mlgi_params*, void* stream);
-/* image rows [*row_begin, *row_end) = the whole 64-pixel tile rows this rank is responsible for in the sharded frames (tile
- * rows [TY*rank/world, TY*(rank+1)/world)): the tiles it bounds, and in mlgi_frame_sharded_host the G-buffer rows it uploads
- * and the image rows it returns. Valid after mlgi_exchange_create. */
-MLGI_API int mlgi_sharded_rows(mlgi_ctx*, int* row_begin, int* row_end);
+/* The image rows this rank is responsible for in the sharded frames: the 64-pixel tile rows t with t mod world == rank, i.e. the
+ * blocks of *row_block (= 64) rows starting at *row_begin + j * *row_stride, j = 0, 1, ..., clipped to the image height. These are
+ * the tiles it bounds and, in mlgi_frame_sharded_host, the G-buffer rows it uploads and the image rows it returns (interleaved
+ * so that every rank owns the same share of every phase of that frame). Valid after mlgi_exchange_create. */
+MLGI_API int mlgi_sharded_rows(mlgi_ctx*, int* row_begin, int* row_block, int* row_stride);
 /* The same with HOST inputs (the N-GPU form of mlgi_frame_host_packed; tiled culling). host_gbuffer and host_gi_packed are
  * FULL-size host arrays; this rank uploads only ITS rows (mlgi_sharded_rows) of the G-buffer and the G-buffer is never
  * replicated: the ranks exchange tile bounds (64 B per tile), and every rank's gathering CTAs read a tile's pixels from the
- * rank that uploaded them, over NVLink. The exchange kernel assembles only this rank's rows of the GL_R11F_G11F_B10F image,
- * directly into host_gi_packed when that is pinned (mapped) memory. Every input byte crosses PCIe once in the whole job (the
- * 3 MB RSM once per rank). MLGI_BUF_GI_PACKED then holds this rank's rows only. Needs cfg.gi_packed. Synchronises the stream. */
+ * rank that uploaded them, over NVLink. The frame runs in phases (blocks of tile rows): while one phase is gathered the next
+ * one's rows are uploaded, bounded and published, and the previous one's rows of the GL_R11F_G11F_B10F image are assembled
+ * from every rank's class planes and copied back -- only this rank's rows, into host_gi_packed (pinned for full speed). Every
+ * input byte crosses PCIe once in the whole job (the 3 MB RSM once per rank). MLGI_BUF_GI_PACKED then holds this rank's rows
+ * only. Needs cfg.gi_packed. Synchronises the stream. */
 MLGI_API int mlgi_frame_sharded_host(mlgi_ctx*, const mlgi_rsm* host_rsm, const mlgi_camera* light, const mlgi_mesh* dev_mesh,
                                      const mlgi_gbuffer* host_gbuffer, const mlgi_camera* cam, const mlgi_params*,
                                      uint32_t* host_gi_packed, void* stream);

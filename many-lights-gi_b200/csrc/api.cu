@@ -105,20 +105,22 @@ struct mlgi_ctx {
     // or, when the cache is full, after an explicit cudaDeviceSynchronize.
     struct OverrideTex { const uint16_t* ptr; cudaTextureObject_t tex; };
     std::vector<OverrideTex> override_tex;
-    int use_texture = 1, tex_float_coord = 0, fg_bulk = 1;
+    int use_texture = 1, tex_float_coord = 0, fg_bulk = 1, xch_direct = 0;
     int xch_cull = 1;               // connected ranks bound 1/world of the tiles each and exchange the bounds (A/B: MLGI_XCH_CULL)
     IsmMode mode_vpl{}, mode_points{};   // the n3 knobs the VPL records / the point list were built with
     // multi-GPU exchange (mlgi_exchange_*): ONE IPC-exportable allocation per rank,
     //   [flags 256 B][class planes, parity 0][class planes, parity 1][G-buffer depth W*H*4][G-buffer normals W*H*4]
     //   [tile bounds, parity 0][tile bounds, parity 1]
-    // flags[0..7]: "planes of frame f written" per rank; flags[16..23]: "tile bounds of frame f published" per rank.
+    // flags[0..7]: "planes of frame f written" per rank; flags[16..23]: "tile bounds of frame f published" per rank;
+    // flags[32..39] / flags[48..55]: the same two signals per PHASE of the host-input sharded frame (value 16 f + phase).
     struct Exchange {
         int rank = 0, world = 0;
         int push = 0;                         // 0: gathering writes its own buffer, the exchange kernel pulls over NVLink (default)
                                               // 1: the gathering epilogue stores into every rank's buffer (round-1 scheme; MLGI_XCH=push)
         char* base = nullptr;
         size_t buf_bytes = 0, gb_off = 0, bounds_off = 0, bounds_bytes = 0;
-        int row_end[8] = {0};                 // tile rows [row_end[g-1], row_end[g]) belong to rank g (bounds; G-buffer slab of the host-input frame)
+        // 64-pixel tile row t belongs to rank t mod world: the tiles it bounds, and in the host-input frame the G-buffer rows it
+        // uploads and the image rows it returns (interleaved, so that every phase of that frame is a contiguous block of tile rows)
         char* peer_base[8] = {nullptr};       // peer-mapped allocations (own slot = base)
         uint32_t** d_peer_flags = nullptr;    // device array of world pointers (for the flag kernels)
         uint32_t* d_state = nullptr;          // [0] frame counter, [1] ticket, [2] error flag
@@ -144,6 +146,7 @@ struct mlgi_ctx {
     cudaStream_t rd = nullptr;                   // read-back of finished slabs (its own stream: the D2H copies must not queue behind the culling of later slabs)
     cudaEvent_t ev_ism = nullptr;
     cudaEvent_t ev_up[kSlabs] = {nullptr}, ev_cull[kSlabs] = {nullptr}, ev_fg[kSlabs] = {nullptr};
+    bool host_slabs_set = false;   // MLGI_HOST_SLABS given: also fixes the phase count of the sharded host frame (default there: by grid size)
     int host_slabs = 6;     // measured at 4K on PCIe 5 x16: 1 slab 3.60 ms, 2: 2.95, 4: 2.49, 6: 2.42, 8: 2.49, 16: 2.51
     cudaEvent_t ev[T_COUNT][2];
     bool ev_used[T_COUNT];
@@ -402,8 +405,9 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev_fg[k], cudaEventDisableTiming);
     }
     if (const char* e10 = getenv("MLGI_HOST_TRACE")) ctx->trace_on = atoi(e10) != 0;
-    if (const char* e5 = getenv("MLGI_HOST_SLABS")) ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5)));   // A/B switch
-    if (const char* e2 = getenv("MLGI_ISM_FETCH")) { ctx->use_texture = strcmp(e2, "ldg") != 0; ctx->tex_float_coord = strcmp(e2, "texf") == 0; }   // A/B switch: tex (default) | texf | ldg
+    if (const char* e5 = getenv("MLGI_HOST_SLABS")) ctx->host_slabs_set = true, ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5)));   // A/B switch
+    if (const char* e3 = getenv("MLGI_XCH_DIRECT")) ctx->xch_direct = atoi(e3) != 0;
+    if (const char* e2 = getenv("MLGI_ISM_FETCH")) { ctx->use_texture = strcmp(e2, "ldg") != 0; ctx->tex_float_coord = strcmp(e2, "texf") == 0 ? 1 : strcmp(e2, "texi") == 0 ? 2 : strcmp(e2, "none") == 0 ? 3 : 0; }   // A/B switch: tex (default) | texf | texi | ldg
     if (const char* e11 = getenv("MLGI_XCH_CULL")) ctx->xch_cull = atoi(e11) != 0;             // A/B switch: bounds exchanged between ranks (default) | every rank bounds all tiles
     if (const char* e8 = getenv("MLGI_FG_BULK")) ctx->fg_bulk = atoi(e8) != 0;                 // A/B switch: records staged by cp.async.bulk (default) | LDG + STS
     if (const char* e6 = getenv("MLGI_FG_SORTED")) ctx->fg_sorted = atoi(e6) != 0;             // A/B switch: longest-list tiles first (default) | row-major
@@ -783,7 +787,6 @@ MLGI_API int mlgi_exchange_create(mlgi_ctx* ctx, int rank, int world, void* out_
     x.bounds_off = x.gb_off + 2 * ((WH * 4 + 255) & ~(size_t)255);
     x.bounds_bytes = (((size_t)ctx->TX * ctx->TY * 16 * sizeof(float)) + 255) & ~(size_t)255;
     const size_t total = x.bounds_off + 2 * x.bounds_bytes;
-    for (int g = 0; g < world; g++) x.row_end[g] = (int)((long long)ctx->TY * (g + 1) / world);
     CK(cudaMalloc((void**)&x.base, total));
     CK(cudaMemset(x.base, 0, total));
     CK(cudaMalloc((void**)&x.d_peer_flags, 8 * sizeof(uint32_t*)));
@@ -862,11 +865,12 @@ static void build_exchange_args(mlgi_ctx* ctx, ExchangeArgs* out) {
     e.frame_ctr = x.d_state; e.ticket = x.d_state + 1; e.error = x.d_state + 2;
     e.raster_packed = ctx->gi_packed;
     e.raster = ctx->cfg.gi_packed == 2 ? nullptr : ctx->gi;
-    e.row_begin = 0; e.row_end = ctx->cfg.height;
+    e.row_begin = 0; e.row_block = ctx->cfg.height; e.row_stride = ctx->cfg.height; e.row_blocks = 1;
+    e.signal_wait = 1; e.advance = 1;
 }
 
 // Tiled culling of one rank of a connected job (inside mlgi_frame_sharded / mlgi_frame_sharded_host, which every rank calls
-// once per frame): the rank bounds only ITS tile rows -- 1/world of the G-buffer instead of all of it -- and stores the 14
+// once per frame): the rank bounds only ITS tile rows (t mod world == rank) -- 1/world of the G-buffer instead of all of it -- and stores the 14
 // numbers per tile into every rank's bounds buffer (64 B per tile over NVLink, 130 KB per frame at 4K); flags order the
 // exchange (bounded wait), then the rank builds the lists of its classes for all tiles. Same bounds, same lists as the
 // single-GPU call.
@@ -878,10 +882,10 @@ static int cull_tiled_sharded(mlgi_ctx* ctx, const float* depth, const uint32_t*
     for (int g = 0; g < x.world; g++) if (g != x.rank) bo.peers[bo.num_peers++] = (float*)(x.peer_base[g] + x.bounds_off);
     bo.parity_stride = x.bounds_bytes / sizeof(float);
     bo.frame_ctr = x.d_state;
-    const int r0 = x.rank ? x.row_end[x.rank - 1] : 0, r1 = x.row_end[x.rank];
-    int n = launch_tile_bounds(depth, face_normal, ctx->cfg.width, ctx->cfg.height, inv, r0, 1, r1 - r0, bo, st);
-    n += launch_flag_signal(x.d_peer_flags, x.world, 16 + x.rank, x.d_state, st);
-    n += launch_flag_wait((const uint32_t*)x.base + 16, x.world, x.d_state, x.d_state + 2, st);
+    const int own = x.rank < ctx->TY ? (ctx->TY - x.rank + x.world - 1) / x.world : 0;      // tile rows rank, rank + world, ...
+    int n = launch_tile_bounds(depth, face_normal, ctx->cfg.width, ctx->cfg.height, inv, x.rank, x.world, own, bo, st);
+    n += launch_flag_signal(x.d_peer_flags, x.world, 16 + x.rank, x.d_state, 1u, 0u, st);
+    n += launch_flag_wait((const uint32_t*)x.base + 16, x.world, x.d_state, x.d_state + 2, 1u, 0u, st);
     n += launch_tile_lists(bo.local, bo.parity_stride, x.d_state, ctx->cfg.width, ctx->records, ctx->cfg.vpl_count, ctx->cfg.class_lo, ctx->cfg.class_hi,
                            0, 1, ctx->TY, ctx->tile_lists, ctx->tile_weight, st);
     if (ctx->fg_sorted) n += launch_tile_order(ctx->tile_weight, ctx->cfg.width, ctx->cfg.vpl_count, ctx->cfg.class_lo, ctx->cfg.class_hi, 0, ctx->TY, ctx->tile_order, st);
@@ -1280,22 +1284,22 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
 
 // ------------------------------------------------------------------------------------- sharded host-input frame
 // One rank of a class-sharded job with HOST inputs (the N-GPU form of mlgi_frame_host_packed). The job's inputs
-// cross PCIe once in total and the camera G-buffer is never replicated: rank r uploads the (small) RSM and ITS slab of the
-// G-buffer -- the tile rows mlgi_sharded_rows reports, 1/world of the image -- into its exchange allocation; it bounds the
-// tiles of that slab and publishes the bounds (64 B per tile) to every rank; the gathering CTAs of every rank then read a
-// tile's pixels from the rank that holds them, over NVLink (a rank's classes touch 1/world of each slab's pixels once);
-// the exchange kernel finally assembles only this rank's rows of the image, writing them straight into the caller's
-// pinned host buffer (mapped; a pageable buffer is served through a device staging copy instead).
-// host_gbuffer / host_gi_packed are full-size host arrays; only this rank's rows are read / written. Synchronises the
-// stream before returning. Every rank of the job must make this call for every frame (it contains two bounded waits on
-// the peers: tile bounds, class planes).
-MLGI_API int mlgi_sharded_rows(mlgi_ctx* ctx, int* row_begin, int* row_end) {
+// cross PCIe once in total and the camera G-buffer is never replicated: rank r uploads the (small) RSM and ITS rows of the
+// G-buffer -- the tile rows t mod world == r (mlgi_sharded_rows), 1/world of the image -- into its exchange allocation; it
+// bounds the tiles of those rows and publishes the bounds (64 B per tile) to every rank; the gathering CTAs of every rank then
+// read a tile's pixels from the rank that holds them, over NVLink (a rank's classes touch 1/world of a tile's pixels, once);
+// finally the rank assembles its rows of the image from every rank's class planes and copies them to the caller's buffer.
+// All of this runs as a pipeline over K phases (blocks of tile rows, see below), so that the PCIe traffic in both directions
+// hides behind the gathering. host_gbuffer / host_gi_packed are full-size host arrays; only this rank's rows are read /
+// written. Synchronises the stream before returning. Every rank of the job must make this call for every frame (each phase
+// contains two bounded waits on the peers: tile bounds, class planes).
+MLGI_API int mlgi_sharded_rows(mlgi_ctx* ctx, int* row_begin, int* row_block, int* row_stride) {
     if (!ctx) return MLGI_E_INVALID;
     auto& x = ctx->xch;
     if (!x.base) return fail(ctx, MLGI_E_ORDER, "mlgi_sharded_rows needs mlgi_exchange_create first");
-    const int t0 = x.rank ? x.row_end[x.rank - 1] : 0, t1 = x.row_end[x.rank];
-    if (row_begin) *row_begin = std::min(ctx->cfg.height, t0 * kTile);
-    if (row_end) *row_end = std::min(ctx->cfg.height, t1 * kTile);
+    if (row_begin) *row_begin = x.rank * kTile;
+    if (row_block) *row_block = kTile;
+    if (row_stride) *row_stride = x.world * kTile;
     return MLGI_OK;
 }
 
@@ -1309,32 +1313,64 @@ MLGI_API int mlgi_frame_sharded_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const ml
     if (!ctx->gi_packed) return fail(ctx, MLGI_E_INVALID, "mlgi_frame_sharded_host needs cfg.gi_packed");
     if (ctx->cfg.enable_timers) return fail(ctx, MLGI_E_INVALID, "per-stage timers are not available on the sharded host path");
     if (p && p->cull_mode != MLGI_CULL_TILED) return fail(ctx, MLGI_E_UNSUPPORTED, "mlgi_frame_sharded_host runs tiled culling (the G-buffer is distributed by tile rows)");
+    if (!ctx->aux || !ctx->side || !ctx->rd) return fail(ctx, MLGI_E_CUDA, "internal streams missing");
     cudaStream_t st = (cudaStream_t)stream;
-    const int W = ctx->cfg.width, H = ctx->cfg.height;
+    const int W = ctx->cfg.width, H = ctx->cfg.height, TX = ctx->TX, TY = ctx->TY, G = x.world, g = x.rank;
     const size_t RS = (size_t)ctx->cfg.rsm_width * ctx->cfg.rsm_height, WH = (size_t)W * H;
-    int y0i = 0, y1i = 0;
-    mlgi_sharded_rows(ctx, &y0i, &y1i);
-    const size_t y0 = (size_t)y0i, y1 = (size_t)y1i;
     const size_t gb_plane = (WH * 4 + 255) & ~(size_t)255;
     int rc;
-    // side: G-buffer slab first (it heads the longer dependency chain: slab -> bounds -> exchange -> lists -> gathering), then the RSM;
-    // aux: atlas clear, VPL build after the RSM; caller's stream: points, then splat / pull-push / gathering / exchange
+    // Phases: the image is cut into K blocks of whole tile rows, each a multiple of `world` rows high, so every rank owns the
+    // same share (rows t mod world == rank) of every phase. Phase k's rows are uploaded, bounded and published while phase
+    // k - 1 is gathered and phase k - 2 is assembled and read back: PCIe in both directions hides behind the gathering, as in
+    // the single-GPU slab pipeline. K is sized so that a phase's gathering launch still fills the GPU a few times over
+    // (MLGI_HOST_SLABS overrides it).
+    const long long ctas = (long long)TX * TY * (ctx->cfg.class_hi - ctx->cfg.class_lo);
+    int K = ctx->host_slabs_set ? ctx->host_slabs : (int)((ctas + 1850) / 3700);
+    K = std::max(1, std::min(K, std::min((int)mlgi_ctx::kSlabs, (TY + G - 1) / G)));
+    const int rows_per_phase = G * ((TY + K * G - 1) / (K * G));
+    K = (TY + rows_per_phase - 1) / rows_per_phase;
+    const size_t row_px = (size_t)kTile * W;                      // pixels of one full tile row
+    const int last_rows = H - (TY - 1) * kTile;                   // image rows of the last tile row (1..64)
+    // this rank's tile rows inside tile rows [a, b): first, count
+    auto own = [&](int a, int b, int* first, int* count) { *first = a + g; *count = *first < b ? (b - *first + G - 1) / G : 0; };
+    // copy of those rows between two images with 4-byte pixels (the last tile row of the image may be partial)
+    auto copy_rows = [&](void* dst, const void* src, int first, int count, cudaMemcpyKind kind, cudaStream_t cs) -> int {
+        if (count <= 0) return MLGI_OK;
+        const bool has_last = first + (count - 1) * G == TY - 1 && last_rows < kTile;
+        const int full = has_last ? count - 1 : count;
+        const size_t off = (size_t)first * row_px * 4, pitch = (size_t)G * row_px * 4;
+        if (full > 0) CK(cudaMemcpy2DAsync((char*)dst + off, pitch, (const char*)src + off, pitch, row_px * 4, full, kind, cs));
+        if (has_last) {
+            const size_t o2 = (size_t)(TY - 1) * row_px * 4;
+            CK(cudaMemcpyAsync((char*)dst + o2, (const char*)src + o2, (size_t)last_rows * W * 4, kind, cs));
+        }
+        return MLGI_OK;
+    };
+    // side: the RSM (3 MB; the ISM chain it feeds then runs under the G-buffer uploads), then this rank's rows phase by phase;
+    // aux: atlas clear, VPL build, then per phase bounds -> publish -> wait -> lists -> order;
+    // caller's stream: points, splat, pull-push, then per phase gathering + "planes written" signal;
+    // rd: per phase wait for every rank's planes, assemble this rank's rows, copy them to the host.
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    CK(cudaStreamWaitEvent(ctx->rd, ctx->ev_fork, 0));
     trace_mark(ctx, "start", st);
     float* own_depth = (float*)(x.base + x.gb_off);
     uint32_t* own_normal = (uint32_t*)(x.base + x.gb_off + gb_plane);
-    if (y1 > y0) {
-        CK(cudaMemcpyAsync(own_depth + y0 * W, hg->depth + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
-        CK(cudaMemcpyAsync(own_normal + y0 * W, hg->face_normal + y0 * W, (y1 - y0) * W * 4, cudaMemcpyHostToDevice, ctx->side));
-    }
-    CK(cudaEventRecord(ctx->ev_up[0], ctx->side));
-    trace_mark(ctx, "up", ctx->side);
     CK(cudaMemcpyAsync(ctx->st_rsm_diffuse, hr->diffuse, RS * 4, cudaMemcpyHostToDevice, ctx->side));
     CK(cudaMemcpyAsync(ctx->st_rsm_normal, hr->face_normal, RS * 4, cudaMemcpyHostToDevice, ctx->side));
     CK(cudaMemcpyAsync(ctx->st_rsm_depth, hr->depth, RS * 4, cudaMemcpyHostToDevice, ctx->side));
     CK(cudaEventRecord(ctx->ev_rsm, ctx->side));
+    auto upload = [&](int k) -> int {
+        int first, count, r;
+        own(k * rows_per_phase, std::min(TY, (k + 1) * rows_per_phase), &first, &count);
+        if ((r = copy_rows(own_depth, hg->depth, first, count, cudaMemcpyHostToDevice, ctx->side))) return r;
+        if ((r = copy_rows(own_normal, hg->face_normal, first, count, cudaMemcpyHostToDevice, ctx->side))) return r;
+        CK(cudaEventRecord(ctx->ev_up[k], ctx->side));
+        trace_mark(ctx, kTrUp[k], ctx->side);
+        return MLGI_OK;
+    };
+    if ((rc = upload(0))) return rc;
     mlgi_rsm dr = {ctx->st_rsm_diffuse, ctx->st_rsm_normal, ctx->st_rsm_depth};
     mlgi_gbuffer dg = {own_depth, own_normal};
     launch_atlas_clear(ctx->atlas, ctx->S, ctx->ism_lo, ctx->ism_hi, ctx->aux);
@@ -1343,16 +1379,6 @@ MLGI_API int mlgi_frame_sharded_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const ml
     if ((rc = mlgi_vpl_process(ctx, &dr, light, p, (void*)ctx->aux))) return rc;
     CK(cudaEventRecord(ctx->ev_vpl, ctx->aux));
     trace_mark(ctx, "vpl", ctx->aux);
-    // culling on the aux stream (highest priority): own bounds as soon as the slab is here, lists once every rank has published
-    CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_up[0], 0));
-    {
-        float vi[16], pi[16], inv[16];
-        mat_inverse(cam->view, vi); mat_inverse(cam->proj, pi); mat_mul(vi, pi, inv);
-        ctx->launches += cull_tiled_sharded(ctx, own_depth, own_normal, to_mat4(inv), ctx->aux);
-        CK(cudaGetLastError());
-    }
-    CK(cudaEventRecord(ctx->ev_join, ctx->aux));
-    trace_mark(ctx, "cull", ctx->aux);
     if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;
     CK(cudaStreamWaitEvent(st, ctx->ev_vpl, 0));
     CK(cudaStreamWaitEvent(st, ctx->ev_clear, 0));
@@ -1360,36 +1386,75 @@ MLGI_API int mlgi_frame_sharded_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const ml
     if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;
     if ((rc = mlgi_ism_pullpush(ctx, nullptr, p, stream))) return rc;
     trace_mark(ctx, "ism", st);
-    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    GatherArgs a;
-    if ((rc = build_gather_args(ctx, &dg, cam, nullptr, p, &a))) return rc;
-    a.gb_world = x.world;
-    for (int g = 0; g < x.world; g++) {
-        a.gb_depth[g] = (const float*)(x.peer_base[g] + x.gb_off);
-        a.gb_normal[g] = (const uint32_t*)(x.peer_base[g] + x.gb_off + gb_plane);
-        a.gb_row_end[g] = x.row_end[g];
+    // culling, phase by phase (aux): own bounds as soon as the rows are here, lists once every rank has published the phase
+    float vi[16], pi[16], inv[16];
+    mat_inverse(cam->view, vi); mat_inverse(cam->proj, pi); mat_mul(vi, pi, inv);
+    BoundsOut bo;
+    memset(&bo, 0, sizeof(bo));
+    bo.local = (float*)(x.base + x.bounds_off);
+    for (int q = 0; q < G; q++) if (q != g) bo.peers[bo.num_peers++] = (float*)(x.peer_base[q] + x.bounds_off);
+    bo.parity_stride = x.bounds_bytes / sizeof(float);
+    bo.frame_ctr = x.d_state;
+    for (int k = 0; k < K; k++) {
+        const int a = k * rows_per_phase, b = std::min(TY, (k + 1) * rows_per_phase);
+        int first, count;
+        own(a, b, &first, &count);
+        if (k > 0 && (rc = upload(k))) return rc;
+        CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_up[k], 0));
+        ctx->launches += launch_tile_bounds(own_depth, own_normal, W, H, to_mat4(inv), first, G, count, bo, ctx->aux);
+        ctx->launches += launch_flag_signal(x.d_peer_flags, G, 32 + g, x.d_state, 16u, (uint32_t)k, ctx->aux);
+        ctx->launches += launch_flag_wait((const uint32_t*)x.base + 32, G, x.d_state, x.d_state + 2, 16u, (uint32_t)k, ctx->aux);
+        ctx->launches += launch_tile_lists(bo.local, bo.parity_stride, x.d_state, W, ctx->records, ctx->cfg.vpl_count, ctx->cfg.class_lo, ctx->cfg.class_hi,
+                                           a, 1, b - a, ctx->tile_lists, ctx->tile_weight, ctx->aux);
+        if (ctx->fg_sorted) ctx->launches += launch_tile_order(ctx->tile_weight, W, ctx->cfg.vpl_count, ctx->cfg.class_lo, ctx->cfg.class_hi, a, b - a, ctx->tile_order, ctx->aux);
+        CK(cudaEventRecord(ctx->ev_cull[k], ctx->aux));
+        trace_mark(ctx, kTrCull[k], ctx->aux);
     }
-    ctx->launches += launch_final_gather(a, st);
     CK(cudaGetLastError());
-    trace_mark(ctx, "fg", st);
-    // exchange: assemble only this rank's rows, straight into the caller's buffer when it is mapped pinned memory
+    ctx->have_tiled = true; ctx->tile_order_valid = ctx->fg_sorted != 0;
+    // gathering, phase by phase (caller's stream); assembly + read-back of the finished phase on rd
+    GatherArgs ga;
+    if ((rc = build_gather_args(ctx, &dg, cam, nullptr, p, &ga))) return rc;
+    ga.gb_world = G;
+    for (int q = 0; q < G; q++) {
+        ga.gb_depth[q] = (const float*)(x.peer_base[q] + x.gb_off);
+        ga.gb_normal[q] = (const uint32_t*)(x.peer_base[q] + x.gb_off + gb_plane);
+    }
     ExchangeArgs e;
     build_exchange_args(ctx, &e);
     e.raster = nullptr;
-    e.row_begin = y0i; e.row_end = y1i;
+    e.signal_wait = 0;
     bool direct = false;
-    if (host_gi_packed) {
+    // (measured at 2 GPUs, 4K: the exchange kernel storing 16.6 MB straight into mapped pinned memory takes 1.3 ms -- 13 GB/s of
+    // SM stores over PCIe -- against 0.05 ms into HBM plus 0.3 ms for the copy engine; MLGI_XCH_DIRECT=1 keeps the direct form for A/B)
+    if (host_gi_packed && ctx->xch_direct) {
         cudaPointerAttributes pa;
         if (cudaPointerGetAttributes(&pa, host_gi_packed) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
             e.raster_packed = (uint32_t*)pa.devicePointer;
             direct = true;
         } else cudaGetLastError();
     }
-    ctx->launches += launch_exchange(e, st);
+    for (int k = 0; k < K; k++) {
+        const int a = k * rows_per_phase, b = std::min(TY, (k + 1) * rows_per_phase);
+        int first, count;
+        own(a, b, &first, &count);
+        CK(cudaStreamWaitEvent(st, ctx->ev_cull[k], 0));
+        ga.tile_begin = a * TX; ga.tile_count = (b - a) * TX;
+        ctx->launches += launch_final_gather(ga, st);
+        ctx->launches += launch_flag_signal(x.d_peer_flags, G, 48 + g, x.d_state, 16u, (uint32_t)k, st);
+        CK(cudaEventRecord(ctx->ev_fg[k], st));
+        trace_mark(ctx, kTrFg[k], st);
+        CK(cudaStreamWaitEvent(ctx->rd, ctx->ev_fg[k], 0));
+        ctx->launches += launch_flag_wait((const uint32_t*)x.base + 48, G, x.d_state, x.d_state + 2, 16u, (uint32_t)k, ctx->rd);
+        e.row_begin = first * kTile; e.row_block = kTile; e.row_stride = G * kTile; e.row_blocks = count;
+        e.advance = k == K - 1;
+        if (count > 0 || e.advance) ctx->launches += launch_exchange(e, ctx->rd);
+        if (host_gi_packed && !direct && (rc = copy_rows(host_gi_packed, ctx->gi_packed, first, count, cudaMemcpyDeviceToHost, ctx->rd))) return rc;
+        trace_mark(ctx, kTrRd[k], ctx->rd);
+    }
     CK(cudaGetLastError());
-    trace_mark(ctx, "xch", st);
-    if (host_gi_packed && !direct && y1 > y0)
-        CK(cudaMemcpyAsync(host_gi_packed + y0 * W, ctx->gi_packed + y0 * W, (y1 - y0) * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev_join, ctx->rd));
+    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     ctx->have_gi = true; ctx->have_blur = false;
     trace_mark(ctx, "end", st);
     CK(cudaStreamSynchronize(st));

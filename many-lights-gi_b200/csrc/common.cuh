@@ -233,12 +233,12 @@ struct GatherArgs {
     SliceTable tab;
     float zFar, giScale /* giIntensityFactor / vplCount * 16 */, clampv;
     int enable_shadowing;
-    int tex_float_coord;    // texture path: hand the unfloored texel coordinate to the unit (A/B: MLGI_ISM_FETCH=texf)
+    int tex_float_coord;    // texture path, A/B: 1 = hand the unfloored texel coordinate to the unit (MLGI_ISM_FETCH=texf), 2 = integer texel coordinates (texi)
     int bulk_staging;       // stage the VPL records with cp.async.bulk + mbarrier, double-buffered (A/B: MLGI_FG_BULK)
-    // host-input sharded frame: the G-buffer is not replicated -- tile rows [gb_row_end[g-1], gb_row_end[g]) live in rank g's memory
+    // host-input sharded frame: the G-buffer is not replicated -- tile row t lives in the memory of rank t mod gb_world
     // (peer-mapped) and a gathering CTA reads its tile's pixels from the owner over NVLink (8 B per pixel, once)
     int gb_world;                        // 0 = depth / face_normal above hold the whole image
-    const float* gb_depth[8]; const uint32_t* gb_normal[8]; int gb_row_end[8];
+    const float* gb_depth[8]; const uint32_t* gb_normal[8];
     const uint32_t* tile_order;   // optional permutation of the tiles (longest list first); null = row-major
     int tile_begin, tile_count;   // 64x64 tiles [tile_begin, tile_begin + tile_count) in row-major order (whole image by default)
     int class_lo, class_hi;
@@ -277,12 +277,16 @@ struct ExchangeArgs {
     uint32_t* error;               // set when a wait times out (a peer died)
     uint32_t* raster_packed;       // may be null (may be a mapped pinned-host pointer: mlgi_frame_sharded_host)
     float4* raster;                // may be null
-    int row_begin, row_end;        // image rows to assemble (whole image by default)
+    // image rows to assemble: row_blocks blocks of row_block rows, the first at row_begin, row_stride apart, clipped to H
+    // (whole image: one block of H rows; a rank of the host-input sharded frame: its 64-row tile rows, world * 64 apart)
+    int row_begin, row_block, row_stride, row_blocks;
+    int signal_wait;               // 1: publish "my planes are written" (slot [rank]) and wait for every rank first (the one-kernel exchange)
+    int advance;                   // 1: the last CTA advances the frame counter
 };
 int launch_exchange(const ExchangeArgs& x, cudaStream_t st);
 // host-input sharded frame: G-buffer slabs are pushed to the peers by the copy engines; these two order them
-int launch_flag_signal(uint32_t* const* peer_flags, int world, int slot, const uint32_t* frame_ctr, cudaStream_t st);
-int launch_flag_wait(const uint32_t* flags, int world, const uint32_t* frame_ctr, uint32_t* error, cudaStream_t st);
+int launch_flag_signal(uint32_t* const* peer_flags, int world, int slot, const uint32_t* frame_ctr, uint32_t mul, uint32_t add, cudaStream_t st);
+int launch_flag_wait(const uint32_t* flags, int world, const uint32_t* frame_ctr, uint32_t* error, uint32_t mul, uint32_t add, cudaStream_t st);
 int launch_planar_packed_to_raster(const uint32_t* planar, int W, int H, uint32_t* raster_packed, float4* raster, cudaStream_t st);
 
 constexpr int kTile = 64;  // tiled-culling tile edge in pixels (one gathering CTA = one class of one tile)

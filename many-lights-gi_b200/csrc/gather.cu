@@ -47,6 +47,15 @@ __device__ __forceinline__ float2 hi2(const float4& q) { return make_float2(q.z,
 // epilogue undoes it.
 __device__ __forceinline__ float2 neg_half_smoothstep(float2 t) { return mul2(mul2(t, t), add2(t, dup(-1.5f))); }
 
+// nearest-texel fetch with INTEGER texel coordinates (PTX tex.2d with .s32 coordinates: unnormalised, no filtering, the
+// sampler's clamp-to-edge applies): the floored coordinate leaves the round-down FMA as the bit pattern 0x4B400000 + k, so
+// k costs one integer subtraction on the ALU pipe instead of a packed FP32 subtraction on the FMA pipe (A/B: MLGI_ISM_FETCH=texi)
+__device__ __forceinline__ float tex2d_s32(cudaTextureObject_t t, int x, int y) {
+    float r, g, b, a;
+    asm("tex.2d.v4.f32.s32 {%0,%1,%2,%3}, [%4, {%5,%6}];" : "=f"(r), "=f"(g), "=f"(b), "=f"(a) : "l"(t), "r"(x), "r"(y));
+    return r;
+}
+
 struct Normal2 { float2 x, y, z; };   // negated face normals of the two pixels; zero for a pixel that is not active
 
 // Two pixels of one thread, component-wise packed: .x = pixel 0, .y = pixel 1
@@ -124,7 +133,15 @@ __device__ __forceinline__ void shade_vpl(PixelPair (&px)[NP], const float4* __r
                 }
                 const float2 f0 = __ffma2_rd(p0, dup(q0), cxy);                           // 1.5*2^23 + floor(texel x | y)
                 const float2 f1 = __ffma2_rd(p1, dup(q1), cxy);
-                if (TEX) {
+                if (TEX == 4) {
+                    // measurement only (MLGI_ISM_FETCH=none, wrong image): no fetch at all, the coordinates still feed the result --
+                    // what the kernel would cost if the shadow lookup had no latency and used no texture bandwidth
+                    t.x = fma_sat(f0.x + f0.y, 1e-30f, tb.x); t.y = fma_sat(f1.x + f1.y, 1e-30f, tb.y);
+                } else if (TEX == 3) {
+                    const float o0 = tex2d_s32(ism_tex, __float_as_int(f0.x) - 0x4B400000, __float_as_int(f0.y) - 0x4B400000);
+                    const float o1 = tex2d_s32(ism_tex, __float_as_int(f1.x) - 0x4B400000, __float_as_int(f1.y) - 0x4B400000);
+                    t.x = fma_sat(o0, 50.0f, tb.x); t.y = fma_sat(o1, 50.0f, tb.y);
+                } else if (TEX) {
                     // textureLod(ismDepthSampler, v.xy, 0) with NEAREST + CLAMP_TO_EDGE (final_gathering.comp:122) on the
                     // texture unit: address, clamp and R16-unorm -> float conversion cost no SM instructions. The coordinate
                     // handed over is the already floored texel index (an exact integer), so the unit's own rounding cannot
@@ -217,11 +234,7 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
     // the tile's G-buffer: this rank's copy, or (host-input sharded frame) the memory of the rank that uploaded these rows
     const float* gdepth = a.depth;
     const uint32_t* gnormal = a.face_normal;
-    if (RGB) {
-#pragma unroll
-        for (int g = 0; g < 8; g++)
-            if (g < a.gb_world && tile_y < a.gb_row_end[g] && (g == 0 || tile_y >= a.gb_row_end[g > 0 ? g - 1 : 0])) { gdepth = a.gb_depth[g]; gnormal = a.gb_normal[g]; }
-    }
+    if (RGB) { const int g = tile_y % a.gb_world; gdepth = a.gb_depth[g]; gnormal = a.gb_normal[g]; }   // tile row t lives on rank t mod world
     float P[NPX][3], Nn[NPX][3];
     int sx[NPX], sy[NPX], slice[NPX];
     bool valid[NPX];
@@ -421,7 +434,9 @@ static void launch_fg_mode(const GatherArgs& a, dim3 grid, cudaStream_t st) {
         else final_gather_kernel<MODE, true, false, 1, 1, true, true><<<grid, 128, 0, st>>>(a);
         return;
     }
-    if (!stt && tex && a.tex_float_coord) { final_gather_kernel<MODE, true, false, 2, 1, false><<<grid, 128, 0, st>>>(a); return; }
+    if (!stt && tex && a.tex_float_coord == 1) { final_gather_kernel<MODE, true, false, 2, 1, false><<<grid, 128, 0, st>>>(a); return; }
+    if (!stt && tex && a.tex_float_coord == 3) { final_gather_kernel<MODE, true, false, 4, 1, true><<<grid, 128, 0, st>>>(a); return; }
+    if (!stt && tex && a.tex_float_coord == 2) { final_gather_kernel<MODE, true, false, 3, 1, true><<<grid, 128, 0, st>>>(a); return; }
     if (stt) {                                   // counting variant (work counters for the roofline accounting)
         if (sh) final_gather_kernel<MODE, true, true, 0, 1, false><<<grid, 128, 0, st>>>(a);
         else final_gather_kernel<MODE, false, true, 0, 1, false><<<grid, 128, 0, st>>>(a);
@@ -487,21 +502,26 @@ __device__ __forceinline__ bool wait_flags(const uint32_t* flags, int world, uin
 
 __global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs x) {
     const uint32_t frame = *reinterpret_cast<volatile uint32_t*>(x.frame_ctr) + 1u;
-    if (blockIdx.x == 0 && threadIdx.x < (unsigned)x.world) {
-        __threadfence_system();
-        *reinterpret_cast<volatile uint32_t*>(x.peer_flags[threadIdx.x] + x.rank) = frame;
-        __threadfence_system();
+    if (x.signal_wait) {
+        if (blockIdx.x == 0 && threadIdx.x < (unsigned)x.world) {
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(x.peer_flags[threadIdx.x] + x.rank) = frame;
+            __threadfence_system();
+        }
+        wait_flags(x.flags, x.world, frame, x.error);
     }
-    wait_flags(x.flags, x.world, frame, x.error);
     const int PW = (x.W + 3) >> 2, PH = (x.H + 3) >> 2;
+    const int nrows = x.row_blocks * x.row_block;               // rows = row_blocks blocks of row_block rows, row_stride apart (clipped to H)
     const size_t par = (size_t)(frame & 1u) * x.parity_stride;
     const int per = 16 / x.world;                               // classes per rank
     if (x.packed && (PW & 3) == 0 && (x.W & 15) == 0) {
         // unit = (raster row y, 16-pixel group i4): planes 4*cy .. 4*cy+3, entries [py][4*i4 .. 4*i4+3]
         const int groups = PW >> 2;
-        const long long units = (long long)(x.row_end - x.row_begin) * groups;
+        const long long units = (long long)nrows * groups;
         for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
-            const int y = x.row_begin + (int)(u / groups), i4 = (int)(u - (long long)(y - x.row_begin) * groups);
+            const int ri = (int)(u / groups), i4 = (int)(u - (long long)ri * groups);
+            const int y = x.row_begin + (ri / x.row_block) * x.row_stride + ri % x.row_block;
+            if (y >= x.H) continue;
             const int cy = y & 3, py = y >> 2;
             uint4 pl[4];
 #pragma unroll
@@ -525,10 +545,12 @@ __global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs x) {
         }
     } else {
         // general shapes / fp32 planes: one pixel per thread
-        const long long n = (long long)x.W * (x.row_end - x.row_begin), i0 = (long long)x.W * x.row_begin;
+        const long long n = (long long)x.W * nrows;
         for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
-            const long long i = i0 + j;
-            const int y = (int)(i / x.W), xx = (int)(i - (long long)y * x.W);
+            const int ri = (int)(j / x.W), xx = (int)(j - (long long)ri * x.W);
+            const int y = x.row_begin + (ri / x.row_block) * x.row_stride + ri % x.row_block;
+            if (y >= x.H) continue;
+            const long long i = (long long)y * x.W + xx;
             const int cls = (xx & 3) + 4 * (y & 3);
             const char* base = x.src[cls / per] + par;
             const size_t e = ((size_t)cls * PH + (y >> 2)) * PW + (xx >> 2);
@@ -542,7 +564,8 @@ __global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs x) {
             }
         }
     }
-    // last CTA out: advance the frame counter, re-arm the ticket
+    // last CTA out: advance the frame counter, re-arm the ticket (a phased frame advances in its last exchange kernel only)
+    if (!x.advance) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -555,31 +578,34 @@ __global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs x) {
 }
 int launch_exchange(const ExchangeArgs& x, cudaStream_t st) {
     // every CTA must be resident (all of them spin on the flags before any of them can finish): at most one wave
-    const long long work = ((long long)x.W * (x.row_end - x.row_begin)) / 16 + 1;
+    const long long work = ((long long)x.W * x.row_blocks * x.row_block) / 16 + 1;
     const int grid = (int)std::max(1LL, std::min<long long>(148 * 4, (work + 255) / 256));
     exchange_kernel<<<grid, 256, 0, st>>>(x);
     return 1;
 }
 
-// host-input sharded frame: "my G-buffer slab has been pushed to every peer" (slot = 8 + rank) and the matching wait
-__global__ void flag_signal_kernel(uint32_t* const* peer_flags, int world, int slot, const uint32_t* frame_ctr) {
-    const uint32_t frame = *reinterpret_cast<const volatile uint32_t*>(frame_ctr) + 1u;
+// one-warp signal / bounded-wait kernels that order the cross-rank exchanges outside the exchange kernel: the tile bounds of the
+// sharded frames (slots 16 + rank), and the per-phase bounds and class planes of the host-input sharded frame (32 + rank, 48 + rank)
+// flag value = (frames completed + 1) * mul + add: mul = 1, add = 0 for one signal per frame; a phased frame (host-input
+// sharded frame) uses mul = 16, add = phase, which stays monotonic over phases and frames
+__global__ void flag_signal_kernel(uint32_t* const* peer_flags, int world, int slot, const uint32_t* frame_ctr, uint32_t mul, uint32_t add) {
+    const uint32_t frame = (*reinterpret_cast<const volatile uint32_t*>(frame_ctr) + 1u) * mul + add;
     if (threadIdx.x < (unsigned)world) {
         __threadfence_system();
         *reinterpret_cast<volatile uint32_t*>(peer_flags[threadIdx.x] + slot) = frame;
         __threadfence_system();
     }
 }
-__global__ void flag_wait_kernel(const uint32_t* flags, int world, const uint32_t* frame_ctr, uint32_t* error) {
-    const uint32_t frame = *reinterpret_cast<const volatile uint32_t*>(frame_ctr) + 1u;
+__global__ void flag_wait_kernel(const uint32_t* flags, int world, const uint32_t* frame_ctr, uint32_t* error, uint32_t mul, uint32_t add) {
+    const uint32_t frame = (*reinterpret_cast<const volatile uint32_t*>(frame_ctr) + 1u) * mul + add;
     wait_flags(flags, world, frame, error);
 }
-int launch_flag_signal(uint32_t* const* peer_flags, int world, int slot, const uint32_t* frame_ctr, cudaStream_t st) {
-    flag_signal_kernel<<<1, 32, 0, st>>>(peer_flags, world, slot, frame_ctr);
+int launch_flag_signal(uint32_t* const* peer_flags, int world, int slot, const uint32_t* frame_ctr, uint32_t mul, uint32_t add, cudaStream_t st) {
+    flag_signal_kernel<<<1, 32, 0, st>>>(peer_flags, world, slot, frame_ctr, mul, add);
     return 1;
 }
-int launch_flag_wait(const uint32_t* flags, int world, const uint32_t* frame_ctr, uint32_t* error, cudaStream_t st) {
-    flag_wait_kernel<<<1, 32, 0, st>>>(flags, world, frame_ctr, error);
+int launch_flag_wait(const uint32_t* flags, int world, const uint32_t* frame_ctr, uint32_t* error, uint32_t mul, uint32_t add, cudaStream_t st) {
+    flag_wait_kernel<<<1, 32, 0, st>>>(flags, world, frame_ctr, error, mul, add);
     return 1;
 }
 

@@ -138,7 +138,7 @@ def load():
     lib.mlgi_exchange_connect_local.argtypes = [P, C.POINTER(P)]
     lib.mlgi_frame_sharded.argtypes = lib.mlgi_frame.argtypes
     lib.mlgi_frame_sharded_host.argtypes = lib.mlgi_frame_host.argtypes
-    lib.mlgi_sharded_rows.argtypes = [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.mlgi_sharded_rows.argtypes = [P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mlgi_set_graph.argtypes = [P, C.c_int]
     lib.mlgi_get_frame_stats.argtypes = [P, C.POINTER(FrameStats)]
     lib.mlgi_exchange_finish.argtypes = [P, P]
@@ -260,10 +260,18 @@ class Context:
                                                   C.byref(cam), C.byref(params), _ptr(host_gi_packed), stream))
 
     def sharded_rows(self):
-        """image rows [y0, y1) this rank uploads / bounds / returns in the sharded frames"""
-        y0, y1 = C.c_int(0), C.c_int(0)
-        self._ck(self.lib.mlgi_sharded_rows(self.h, C.byref(y0), C.byref(y1)))
-        return int(y0.value), int(y1.value)
+        """(row_begin, row_block, row_stride): this rank uploads / bounds / returns the blocks of row_block image rows that start
+        at row_begin + j * row_stride (its 64-pixel tile rows t with t mod world == rank)"""
+        y0, blk, stride = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.mlgi_sharded_rows(self.h, C.byref(y0), C.byref(blk), C.byref(stride)))
+        return int(y0.value), int(blk.value), int(stride.value)
+
+    def sharded_row_mask(self):
+        """boolean array over the image rows: True for the rows of sharded_rows()"""
+        import numpy as np
+        y0, blk, stride = self.sharded_rows()
+        y = np.arange(self.cfg.height)
+        return (y >= y0) & (((y - y0) % stride) < blk)
 
     def set_graph(self, enable):
         self._ck(self.lib.mlgi_set_graph(self.h, int(enable)))

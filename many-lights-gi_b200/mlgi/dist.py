@@ -20,6 +20,24 @@ def class_range(rank, world):
     return rank * per, (rank + 1) * per
 
 
+TILE = 64
+
+
+def row_mask(rank, world, height, tile=TILE):
+    """image rows rank `rank` of `world` is responsible for in the sharded frames (mlgi_sharded_rows): the 64-pixel tile
+    rows t with t mod world == rank -- the tiles it bounds, the G-buffer rows it uploads and the image rows it returns."""
+    y = np.arange(height)
+    return (y // tile) % world == rank
+
+
+def host_frame_phases(tile_rows, world, phases):
+    """phases of mlgi_frame_sharded_host as (first tile row, end tile row) blocks: whole tile rows, every block but the
+    last a multiple of `world` rows high, so that each rank owns the same share of every phase (same arithmetic as the library)"""
+    k = max(1, min(phases, (tile_rows + world - 1) // world))
+    rows_per_phase = world * ((tile_rows + k * world - 1) // (k * world))
+    return [(a, min(tile_rows, a + rows_per_phase)) for a in range(0, tile_rows, rows_per_phase)]
+
+
 def planar_shape(width, height):
     return (NUM_CLASSES, (height + 3) // 4, (width + 3) // 4, 4)
 

@@ -26,6 +26,26 @@ def test_class_partition():
                 assert (lo * L) % S == 0 and (hi * L) % S == 0
 
 
+def test_row_ownership_and_phases():
+    """tile row t belongs to rank t mod world: the ranks' rows partition the image, and every phase of the host-input frame is
+    a block of whole tile rows in which each rank owns the same number of rows (+-1 in the last phase)"""
+    for H in (216, 2160, 4320, 64, 100):
+        TY = (H + 63) // 64
+        for world in (2, 4, 8):
+            masks = np.stack([mdist.row_mask(r, world, H) for r in range(world)])
+            assert (masks.sum(0) == 1).all()
+            assert mdist.row_mask(0, world, H)[:min(H, 64)].all()
+            for K in (1, 2, 4, 6):
+                ph = mdist.host_frame_phases(TY, world, K)
+                assert ph[0][0] == 0 and ph[-1][1] == TY and all(a[1] == b[0] for a, b in zip(ph, ph[1:]))
+                assert len(ph) <= K
+                for (a, b) in ph[:-1]:
+                    assert (b - a) % world == 0 and a % world == 0
+                for (a, b) in ph:
+                    own = [sum(1 for t in range(a, b) if t % world == r) for r in range(world)]
+                    assert max(own) - min(own) <= 1
+
+
 def test_planar_layout_roundtrip():
     rng = np.random.default_rng(0)
     for (H, W) in ((8, 8), (100, 160), (37, 53)):

@@ -758,8 +758,9 @@ def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid):
         s.exchange_create(r, world)
     for s in shards:
         s.exchange_connect_local(shards)
-    rows = [s.sharded_rows() for s in shards]
-    assert rows[0][0] == 0 and rows[0][1] == rows[1][0] and rows[1][1] == c.H and rows[0][1] % 64 == 0
+    assert [s.sharded_rows() for s in shards] == [(0, 64, 128), (64, 64, 128)]      # tile row t belongs to rank t mod world
+    rows = [s.sharded_row_mask() for s in shards]
+    assert (rows[0] ^ rows[1]).all()
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
     hr, hg = mlgi.make_rsm(h[0], h[1], h[2]), mlgi.make_gbuffer(h[3], h[4])
@@ -787,10 +788,9 @@ def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid):
         for s in shards:
             s.exchange_status()          # a timed-out wait (a rank that never signalled) is an error, not a wrong image
         for r in range(world):
-            y0, y1 = rows[r]
             got = bufs[r].numpy().view(np.uint32)
-            assert np.array_equal(got[y0:y1], ref[y0:y1]), "frame %d rank %d" % (frame, r)
-            assert not got[:y0].any() and not got[y1:].any()
+            assert np.array_equal(got[rows[r]], ref[rows[r]]), "frame %d rank %d" % (frame, r)
+            assert not got[~rows[r]].any()
     for s in shards:
         s.exchange_status()
         s.close()

@@ -18,7 +18,7 @@ world = 2
 shards = [mlgi.Context(c.W, c.H, c.N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 22, class_lo=8 * r, class_hi=8 * r + 8, gi_packed=2) for r in range(world)]
 for r, s in enumerate(shards): s.exchange_create(r, world)
 for s in shards: s.exchange_connect_local(shards)
-rows = [s.sharded_rows() for s in shards]
+rows = [s.sharded_row_mask() for s in shards]
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
 h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
 hr, hg = mlgi.make_rsm(h[0], h[1], h[2]), mlgi.make_gbuffer(h[3], h[4])
@@ -40,13 +40,12 @@ for frame in range(4):
     dt = time.time() - t0
     print("frame", frame, "errors", errors, "seconds %.3f" % dt)
     for r in range(world):
-        y0, y1 = rows[r]
         got = outs[r].numpy().view(np.uint32)
-        bad = got[y0:y1] != ref[y0:y1]
+        bad = (got != ref) & rows[r][:, None]
         ys, xs = np.nonzero(bad)
-        cls = (xs & 3) + 4 * ((ys + y0) & 3)
-        print(" rank", r, "rows", (y0, y1), "bad", int(bad.sum()), "bad rows", sorted(set((ys + y0).tolist()))[:12], "bad classes", sorted(set(cls.tolist())),
-              "zeros among bad", int((got[y0:y1][bad] == 0).sum()))
+        cls = (xs & 3) + 4 * (ys & 3)
+        print(" rank", r, "bad", int(bad.sum()), "bad rows", sorted(set(ys.tolist()))[:12], "bad classes", sorted(set(cls.tolist())),
+              "zeros among bad", int((got[bad] == 0).sum()), "written outside own rows", int(got[~rows[r]].any()))
     for r, s in enumerate(shards):
         try: s.exchange_status(); print(" status rank", r, "ok")
         except Exception as e: print(" status rank", r, repr(e))

@@ -6,12 +6,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "many-lights-gi_b200")); sys.path.insert(0, os.path.join(ROOT, "fixtures")); sys.path.insert(0, ROOT)
 import torch, mlgi, bench
 name = sys.argv[1] if len(sys.argv) > 1 else "4k_4096"
+other = sys.argv[2] if len(sys.argv) > 2 else "texf"        # texf | texi | ldg
 wl = bench.build_workload(name); sc, W, H, N = wl.scene, wl.W, wl.H, wl.N
 dev = torch.device("cuda", 0)
 up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 t = [up(a) for a in (wl.rsm_diffuse, wl.rsm_normal, wl.rsm_depth, wl.depth, wl.normal, sc.vertices, sc.normals, sc.indices, sc.prim_id)]
 imgs = {}
-for mode in ("tex", "texf"):
+for mode in ("tex", other):
     os.environ["MLGI_ISM_FETCH"] = mode
     ctx = mlgi.Context(W, H, N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 23)
     p = mlgi.default_params(N)
@@ -26,7 +27,7 @@ for mode in ("tex", "texf"):
     imgs[mode] = ctx.download(mlgi.BUF_GI, np.float32).reshape(H, W, 4)[:, :, :3].copy()
     print(mode, "frame %.4f ms" % (e0.elapsed_time(e1) / 50))
     ctx.close()
-a, b = imgs["tex"], imgs["texf"]
+a, b = imgs["tex"], imgs[other]
 diff = (a.view(np.uint32) != b.view(np.uint32)).any(-1)
 rel = np.abs(a - b).max(-1) / np.maximum(np.abs(a).max(-1), 1e-12)
 print("pixels differing: %d of %d (%.4f %%), max relative difference %.3e, pixels above 1e-3: %d" % (diff.sum(), diff.size, 100.0 * diff.mean(), rel.max(), (rel > 1e-3).sum()))

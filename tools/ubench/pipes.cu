@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256) k(float* out, int iters, float a, float b
             if (MODE == 10) { x[i] = __fmul2_rn(x[i], make_float2(s, s)); }                                 // FMUL2 with scalar-broadcast
             if (MODE == 11) { x[i].x = x[i].x * a; x[i].y = x[i].y * b; }                                   // 2 x FMUL
             if (MODE == 12) { x[i].x = x[i].x + a; x[i].y = x[i].y + b; }                                   // 2 x FADD
+            if (MODE == 13) { if (i < 4) x[i] = __ffma2_rn(x[i], A, B); else { x[i].x = fmaf(x[i].x, a, b); x[i].y = fmaf(x[i].y, a, b); } }   // 4 FFMA2 + 8 FFMA per trip
+            if (MODE == 14) { if (i < 6) x[i] = __ffma2_rn(x[i], A, B); else { x[i].x = fmaf(x[i].x, a, b); x[i].y = fmaf(x[i].y, a, b); } }   // 6 FFMA2 + 4 FFMA per trip
         }
         if (MODE == 2 || MODE == 10) s = __uint_as_float((__float_as_uint(s) & 0x3FFFFFFFu) | 0x3F000000u);
     }
@@ -53,5 +55,6 @@ int main() {
     run<0>("2 x FFMA (reg)", 16); run<6>("2 x FFMA (imm)", 16); run<11>("2 x FMUL", 16); run<12>("2 x FADD", 16);
     run<1>("FFMA2 (3 x 64-bit)", 8); run<2>("FFMA2 (scalar-broadcast operand)", 8); run<3>("FMUL2", 8); run<10>("FMUL2 (scalar-broadcast)", 8);
     run<4>("FADD2", 8); run<5>("FADD2 (imm)", 8); run<7>("2 x FMNMX", 16); run<8>("FFMA2 + 2 ALU", 24); run<9>("FFMA2 + FMNMX", 16);
+    run<13>("4 FFMA2 + 8 FFMA (flop-equal mix)", 12); run<14>("6 FFMA2 + 4 FFMA", 10);
     return 0;
 }
