@@ -486,7 +486,8 @@ def main():
                         "format, stream sync)") if world == 1 else
                        "mlgi_frame_sharded_host, one call per rank: pinned-host upload of the RSM and of 1/N of the G-buffer (whole tile rows), "
                        "tile bounds exchanged between ranks, gathering reads each tile's pixels from the rank holding them over NVLink, plane "
-                       "exchange, 1/N of the assembled GL_R11F_G11F_B10F image rows written straight to pinned host memory (bytes summed over ranks)"}
+                       "exchange, 1/N of the assembled GL_R11F_G11F_B10F image rows copied back to pinned host memory; upload, culling, gathering and "
+                       "read-back pipelined over phases of tile rows (bytes summed over ranks)"}
 
     # ---- per-stage times + the dominant kernels' live durations (events on the launching stream; direct launches) ----
     ctx.set_timers(True)

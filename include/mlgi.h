@@ -186,6 +186,10 @@ MLGI_API int mlgi_frame(mlgi_ctx*, const mlgi_rsm*, const mlgi_camera* light, co
  * animated light updates the instantiated graph in place). mlgi_set_graph(ctx, 0) or MLGI_GRAPH=0 selects direct launches;
  * per-stage timers always use direct launches. */
 MLGI_API int mlgi_set_graph(mlgi_ctx*, int enable);
+/* Builds (captures, instantiates, uploads) the graph that the next mlgi_frame (sharded = 0) or mlgi_frame_sharded (sharded = 1)
+ * call with the same arguments replays, without launching it: takes the first-frame cost out of the first frame. Optional. */
+MLGI_API int mlgi_frame_prepare(mlgi_ctx*, const mlgi_rsm*, const mlgi_camera* light, const mlgi_mesh*, const mlgi_gbuffer*,
+                                const mlgi_camera* cam, const mlgi_params*, int sharded, void* stream);
 typedef struct {
     double host_enqueue_us;                 /* host time spent inside the last mlgi_frame / mlgi_frame_sharded call */
     unsigned long long graph_replays;       /* frames issued as one cudaGraphLaunch */

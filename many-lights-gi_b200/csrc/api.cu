@@ -1031,6 +1031,48 @@ struct FrameKey {
     int with_exchange, push, fg_sorted, use_texture, tex_float_coord, fg_bulk, xch_cull; const void* planar_ext;
 };
 
+// capture (if the key changed) and instantiate / update the frame's graph; no launch
+static int ensure_graph(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
+                        const mlgi_camera* cam, const mlgi_params* p, bool with_exchange) {
+    int rc = MLGI_OK;
+    FrameKey key;
+    memset(&key, 0, sizeof(key));
+    key.rsm = *rsm; key.light = *light; key.mesh = *mesh; key.gb = *gb; key.cam = *cam; key.p = *p;
+    key.with_exchange = with_exchange; key.push = ctx->xch.push; key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture;
+    key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk; key.xch_cull = ctx->xch_cull; key.planar_ext = ctx->planar_ext;
+    if (ctx->graph_valid && memcmp(&key, ctx->graph_key.data(), sizeof(key)) == 0) return MLGI_OK;
+    if (p->cull_mode == MLGI_CULL_CLUSTERED && (rc = ensure_clustered(ctx))) return rc;   // cudaMalloc must not run inside a capture
+    const unsigned long long l0 = ctx->launches;
+    CK(cudaStreamBeginCapture(ctx->cap, cudaStreamCaptureModeThreadLocal));
+    rc = frame_body(ctx, rsm, light, mesh, gb, cam, p, with_exchange, ctx->cap);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->cap, &g);
+    ctx->graph_launches = ctx->launches - l0;
+    ctx->launches = l0;
+    if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); ctx->graph_valid = false; return rc; }
+    if (ce != cudaSuccess) { ctx->graph_valid = false; return fail(ctx, MLGI_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce)); }
+    bool updated = false;
+    // value-only changes (matrices, RSM pointers of an animated light ...) update the executable in place; a change of
+    // the launch structure (culling mode, exchange, empty mesh) needs a new one
+    const int topo = p->cull_mode | (with_exchange ? 8 : 0) | (mesh->num_triangles == 0 ? 16 : 0) | (ctx->xch.push ? 32 : 0) | (ctx->planar_ext ? 64 : 0);
+    if (ctx->graph_exec && topo != ctx->graph_topo) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+    ctx->graph_topo = topo;
+    if (ctx->graph_exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(ctx->graph_exec, g, &info) == cudaSuccess) updated = true;
+        else { cudaGetLastError(); cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+    }
+    if (!updated) {
+        const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+        if (ie != cudaSuccess) { cudaGraphDestroy(g); ctx->graph_exec = nullptr; ctx->graph_valid = false; return fail(ctx, MLGI_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+        ctx->graph_instantiations++;
+    }
+    cudaGraphDestroy(g);
+    ctx->graph_key.assign((const char*)&key, (const char*)&key + sizeof(key));
+    ctx->graph_valid = true;
+    return MLGI_OK;
+}
+
 static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
                          const mlgi_camera* cam, const mlgi_params* p, bool with_exchange, void* stream) {
     if (!rsm || !light || !mesh || !gb || !cam || !p) return fail(ctx, MLGI_E_INVALID, "mlgi_frame: NULL argument");
@@ -1041,42 +1083,7 @@ static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* 
     if (!ctx->use_graph || ctx->cfg.enable_timers || !ctx->cap) {
         rc = frame_body(ctx, rsm, light, mesh, gb, cam, p, with_exchange, st);
     } else {
-        FrameKey key;
-        memset(&key, 0, sizeof(key));
-        key.rsm = *rsm; key.light = *light; key.mesh = *mesh; key.gb = *gb; key.cam = *cam; key.p = *p;
-        key.with_exchange = with_exchange; key.push = ctx->xch.push; key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture;
-        key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk; key.xch_cull = ctx->xch_cull; key.planar_ext = ctx->planar_ext;
-        if (!ctx->graph_valid || memcmp(&key, ctx->graph_key.data(), sizeof(key)) != 0) {
-            if (p->cull_mode == MLGI_CULL_CLUSTERED && (rc = ensure_clustered(ctx))) return rc;   // cudaMalloc must not run inside a capture
-            const unsigned long long l0 = ctx->launches;
-            CK(cudaStreamBeginCapture(ctx->cap, cudaStreamCaptureModeThreadLocal));
-            rc = frame_body(ctx, rsm, light, mesh, gb, cam, p, with_exchange, ctx->cap);
-            cudaGraph_t g = nullptr;
-            const cudaError_t ce = cudaStreamEndCapture(ctx->cap, &g);
-            ctx->graph_launches = ctx->launches - l0;
-            ctx->launches = l0;
-            if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); ctx->graph_valid = false; return rc; }
-            if (ce != cudaSuccess) { ctx->graph_valid = false; return fail(ctx, MLGI_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce)); }
-            bool updated = false;
-            // value-only changes (matrices, RSM pointers of an animated light ...) update the executable in place; a change of
-            // the launch structure (culling mode, exchange, empty mesh) needs a new one
-            const int topo = p->cull_mode | (with_exchange ? 8 : 0) | (mesh->num_triangles == 0 ? 16 : 0) | (ctx->xch.push ? 32 : 0) | (ctx->planar_ext ? 64 : 0);
-            if (ctx->graph_exec && topo != ctx->graph_topo) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
-            ctx->graph_topo = topo;
-            if (ctx->graph_exec) {
-                cudaGraphExecUpdateResultInfo info;
-                if (cudaGraphExecUpdate(ctx->graph_exec, g, &info) == cudaSuccess) updated = true;
-                else { cudaGetLastError(); cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
-            }
-            if (!updated) {
-                const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
-                if (ie != cudaSuccess) { cudaGraphDestroy(g); ctx->graph_exec = nullptr; ctx->graph_valid = false; return fail(ctx, MLGI_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
-                ctx->graph_instantiations++;
-            }
-            cudaGraphDestroy(g);
-            ctx->graph_key.assign((const char*)&key, (const char*)&key + sizeof(key));
-            ctx->graph_valid = true;
-        }
+        if ((rc = ensure_graph(ctx, rsm, light, mesh, gb, cam, p, with_exchange))) return rc;
         CK(cudaGraphLaunch(ctx->graph_exec, st));
         ctx->launches += ctx->graph_launches;
         ctx->graph_replays++;
@@ -1089,6 +1096,23 @@ static int frame_graphed(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* 
     }
     ctx->last_enqueue_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     return rc;
+}
+
+// Builds (captures, instantiates, uploads) the graph the next mlgi_frame / mlgi_frame_sharded call with the same arguments
+// will replay, without launching anything: takes the first-frame cost (capture + instantiation, ~1 ms of host time) out of the
+// first frame, and -- for several ranks driven by one process on ONE GPU -- keeps a rank's instantiation from queueing behind
+// another rank's kernel that is already waiting for it.
+MLGI_API int mlgi_frame_prepare(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,
+                                const mlgi_camera* cam, const mlgi_params* p, int sharded, void* stream) {
+    if (!ctx) return MLGI_E_INVALID;
+    DeviceGuard dg_(ctx);
+    if (!rsm || !light || !mesh || !gb || !cam || !p) return fail(ctx, MLGI_E_INVALID, "mlgi_frame_prepare: NULL argument");
+    if (sharded && !ctx->xch.connected) return fail(ctx, MLGI_E_ORDER, "mlgi_frame_prepare(sharded) needs a connected exchange");
+    if (!ctx->use_graph || ctx->cfg.enable_timers || !ctx->cap) return MLGI_OK;       // direct launches: nothing to build
+    int rc = ensure_graph(ctx, rsm, light, mesh, gb, cam, p, sharded != 0);
+    if (rc) return rc;
+    CK(cudaGraphUpload(ctx->graph_exec, (cudaStream_t)stream));
+    return MLGI_OK;
 }
 
 MLGI_API int mlgi_frame(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* gb,

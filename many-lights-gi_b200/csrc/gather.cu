@@ -711,7 +711,7 @@ __device__ __forceinline__ void run_pass(const Texel (&w)[WIN], float (&ar)[RUN]
         }
 #pragma unroll
     for (int j = 0; j < RUN; j++) {                                                            // :71
-        const float inv = __frcp_rn(fa[j]);                                                    // fa >= 1
+        const float inv = rcp_approx(fa[j]);                                                   // fa >= 1 (1 ulp; the blur's contract is 1e-4)
         ar[j] *= inv; ag[j] *= inv; ab[j] *= inv;
     }
 }
@@ -725,20 +725,36 @@ __global__ void __launch_bounds__(256, 4) gi_blur_fused_kernel(const float4* __r
     __shared__ float s_t[3][SH][TPITCH];
     const int x0 = blockIdx.x * TW - R, y0 = blockIdx.y * TH - R;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = threadIdx.x; q < SW * SH; q += 256) {
-        const int lx = q % SW, ly = q / SW, x = x0 + lx, y = y0 + ly;
-        float r = 0.0f, g = 0.0f, b = 0.0f, d = 1e18f, nx = 0.0f, ny = 0.0f, nz = 0.0f;
-        if (x >= 0 && y >= 0 && x < W && y < H) {
+    // staging in two steps, so that all of a thread's global loads (3 per texel, 5 texels) are in flight before the first use
+    constexpr int NQ = (SW * SH + 255) / 256;
+    uint32_t gv[NQ], nv[NQ];
+    float4 gc[NQ];
+    float dv[NQ];
+    bool in[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; k++) {
+        const int q = threadIdx.x + k * 256, lx = q % SW, ly = q / SW, x = x0 + lx, y = y0 + ly;
+        in[k] = q < SW * SH && x >= 0 && y >= 0 && x < W && y < H;
+        gv[k] = 0u; nv[k] = 0u; dv[k] = 0.0f; gc[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (in[k]) {
             const size_t t = (size_t)y * W + x;
+            if (PACKED) gv[k] = __ldg(gi_packed + t); else gc[k] = __ldg(gi + t);
+            dv[k] = __ldg(depth + t);
+            nv[k] = __ldg(face_normal + t);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NQ; k++) {
+        const int q = threadIdx.x + k * 256, lx = q % SW, ly = q / SW;
+        if (q >= SW * SH) continue;
+        float r = 0.0f, g = 0.0f, b = 0.0f, d = 1e18f, nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (in[k]) {
             if (PACKED) {
-                const uint32_t v = __ldg(gi_packed + t);
+                const uint32_t v = gv[k];
                 r = unpack_ufloat_fast<6>(v & 0x7FFu); g = unpack_ufloat_fast<6>((v >> 11) & 0x7FFu); b = unpack_ufloat_fast<5>(v >> 22);
-            } else {
-                const float4 c = __ldg(gi + t);
-                r = c.x; g = c.y; b = c.z;
-            }
-            d = -projB / (projA + (2.0f * __ldg(depth + t) - 1.0f));                      // reprojection.glsl:6-14
-            const uint32_t n10 = __ldg(face_normal + t);
+            } else { r = gc[k].x; g = gc[k].y; b = gc[k].z; }
+            d = __fdividef(-projB, projA + (2.0f * dv[k] - 1.0f));                          // reprojection.glsl:6-14 (2 ulp; contract 1e-4)
+            const uint32_t n10 = nv[k];
             nx = float(n10 & 0x3FFu) * (2.0f / 1023.0f) - 1.0f; ny = float((n10 >> 10) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f;
             nz = float((n10 >> 20) & 0x3FFu) * (2.0f / 1023.0f) - 1.0f;
         }

@@ -78,7 +78,7 @@ EXPORTS = [
     "mlgi_vpl_process", "mlgi_ism_points", "mlgi_ism_set_points", "mlgi_ism_splat", "mlgi_ism_pullpush",
     "mlgi_cull_clustered", "mlgi_cull_tiled", "mlgi_final_gather", "mlgi_gi_blur", "mlgi_composite_ambient", "mlgi_frame", "mlgi_frame_host", "mlgi_frame_host_packed",
     "mlgi_get_buffer", "mlgi_read_buffer", "mlgi_read_buffer_async", "mlgi_get_counts", "mlgi_gather_stats", "mlgi_measure_fp32_peak_tflops", "mlgi_debug_sqrt_thresholds", "mlgi_bind_planar_output", "mlgi_planar_to_raster", "mlgi_exchange_create", "mlgi_exchange_connect", "mlgi_exchange_connect_local", "mlgi_exchange_finish", "mlgi_exchange_status",
-    "mlgi_frame_sharded", "mlgi_frame_sharded_host", "mlgi_sharded_rows", "mlgi_set_graph", "mlgi_get_frame_stats", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
+    "mlgi_frame_sharded", "mlgi_frame_sharded_host", "mlgi_frame_prepare", "mlgi_sharded_rows", "mlgi_set_graph", "mlgi_get_frame_stats", "mlgi_get_timings", "mlgi_set_timers", "mlgi_launch_count",
 ]
 
 _lib = None
@@ -137,6 +137,7 @@ def load():
     lib.mlgi_exchange_connect.argtypes = [P, P]
     lib.mlgi_exchange_connect_local.argtypes = [P, C.POINTER(P)]
     lib.mlgi_frame_sharded.argtypes = lib.mlgi_frame.argtypes
+    lib.mlgi_frame_prepare.argtypes = lib.mlgi_frame.argtypes[:-1] + [C.c_int, P]
     lib.mlgi_frame_sharded_host.argtypes = lib.mlgi_frame_host.argtypes
     lib.mlgi_sharded_rows.argtypes = [P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mlgi_set_graph.argtypes = [P, C.c_int]
@@ -254,6 +255,11 @@ class Context:
     def frame_sharded(self, rsm, light, mesh, gb, cam, params, stream=None):
         self._ck(self.lib.mlgi_frame_sharded(self.h, C.byref(rsm), C.byref(light), C.byref(mesh), C.byref(gb), C.byref(cam),
                                              C.byref(params), stream))
+
+    def frame_prepare(self, rsm, light, mesh, gb, cam, params, sharded=False, stream=None):
+        """build the graph the next frame / frame_sharded call replays, without launching it"""
+        self._ck(self.lib.mlgi_frame_prepare(self.h, C.byref(rsm), C.byref(light), C.byref(mesh), C.byref(gb), C.byref(cam),
+                                             C.byref(params), int(bool(sharded)), stream))
 
     def frame_sharded_host(self, host_rsm, light, dev_mesh, host_gb, cam, params, host_gi_packed=None, stream=None):
         self._ck(self.lib.mlgi_frame_sharded_host(self.h, C.byref(host_rsm), C.byref(light), C.byref(dev_mesh), C.byref(host_gb),

@@ -721,6 +721,9 @@ def test_exchange_kernels_with_two_sequential_shards_on_one_gpu(case_mid, push, 
     for s in shards:
         s.exchange_connect_local(shards)
     streams = [torch.cuda.Stream() for _ in range(world)]
+    for r, s in enumerate(shards):              # graphs built before any rank starts waiting for another (one GPU, one host thread)
+        s.frame_prepare(full.rsm, full.light, full.mesh, full.gb, full.cam, p, sharded=True, stream=streams[r].cuda_stream)
+    assert shards[0].frame_stats()["graph_instantiations"] == 1 and shards[0].frame_stats()["graph_replays"] == 0
     for frame in range(3):
         for r, s in enumerate(shards):          # rank 0's exchange kernel waits (on its own stream) for rank 1's signal
             s.frame_sharded(full.rsm, full.light, full.mesh, full.gb, full.cam, p, stream=streams[r].cuda_stream)
@@ -735,15 +738,17 @@ def test_exchange_kernels_with_two_sequential_shards_on_one_gpu(case_mid, push, 
     full.close()
 
 
-def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid):
+@pytest.mark.parametrize("phases", [1, 2])
+def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid, phases, monkeypatch):
     """mlgi_frame_sharded_host (the N-GPU host-input frame: distributed G-buffer, exchanged tile bounds, remote G-buffer reads
-    in the gathering kernel, row-range exchange written straight to pinned host memory) exercised on ONE GPU: two class-shard
-    contexts connected through mlgi_exchange_connect_local, one host thread per rank (the call synchronises, and each rank
-    waits for the other inside the frame). Each rank must return exactly its rows of the unsharded image, bit for bit, and
-    touch no other row, for several frames."""
+    in the gathering kernel, per-phase plane exchange and read-back of the rank's own tile rows) exercised on ONE GPU: two
+    class-shard contexts connected through mlgi_exchange_connect_local, one host thread per rank (the call synchronises, and
+    each rank waits for the other inside the frame), as one phase and as a two-phase pipeline. Each rank must return exactly
+    its rows of the unsharded image, bit for bit, and touch no other row, for several frames."""
     import threading
     torch = _torch()
     c = case_mid
+    monkeypatch.setenv("MLGI_HOST_SLABS", str(phases))
     wl, sc = c.wl, c.wl.scene
     full = Gpu(c)
     full.ctx.close()
