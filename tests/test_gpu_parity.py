@@ -643,7 +643,10 @@ def test_graph_replay_matches_direct_launches(case_mid):
     g = Gpu(c)
     p = mlgi.default_params(c.N)
     g.ctx.set_graph(False)
+    n_before = g.ctx.launch_count()
     g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    per_frame = g.ctx.launch_count() - n_before     # VPLP, points, splat, pull-push, tile bounds + lists + order, gathering
+    assert per_frame == 8
     ism0 = g.ctx.download(mlgi.BUF_ISM, np.uint16)
     gi0 = g.ctx.download(mlgi.BUF_GI, np.float32)
     lists0 = g.ctx.download(mlgi.BUF_TILE_LISTS, np.uint16)
@@ -653,7 +656,7 @@ def test_graph_replay_matches_direct_launches(case_mid):
         g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
     st = g.ctx.frame_stats()
     assert st["graph_enabled"] and st["graph_replays"] == 3 and st["graph_instantiations"] == 1
-    assert g.ctx.launch_count() - n_direct == 3 * 8          # the replayed launches are counted like direct ones
+    assert g.ctx.launch_count() - n_direct == 3 * per_frame  # the replayed launches are counted like direct ones
     assert np.array_equal(g.ctx.download(mlgi.BUF_ISM, np.uint16), ism0)
     assert np.array_equal(g.ctx.download(mlgi.BUF_GI, np.float32), gi0)
     assert np.array_equal(g.ctx.download(mlgi.BUF_TILE_LISTS, np.uint16), lists0)
@@ -675,6 +678,33 @@ def test_graph_replay_matches_direct_launches(case_mid):
     gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4)[:, :, :3]
     _check_radiance(gi, c2.gather(mlgi.CULL_TILED, True), "graph animated light")
     g.close()
+
+
+def test_pullpush_gathering_pipeline_option(case_mid, monkeypatch):
+    """MLGI_PP_PARTS (A/B switch, off by default): pull-push bands and gathering class groups as a pipeline on two streams --
+    the same bits as the two whole-frame launches, as direct launches and as a graph, also for a class shard"""
+    c = case_mid
+    p = mlgi.default_params(c.N)
+    for kw in (dict(), dict(class_lo=4, class_hi=12)):
+        imgs = []
+        for parts in ("1", "4"):
+            monkeypatch.setenv("MLGI_PP_PARTS", parts)
+            g = Gpu(c, **kw)
+            for graph in (False, True):
+                g.ctx.set_graph(graph)
+                n0 = g.ctx.launch_count()
+                g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+                assert g.ctx.launch_count() - n0 == (8 if parts == "1" else 14)
+                imgs.append((g.ctx.download(mlgi.BUF_ISM, np.uint16), g.ctx.download(mlgi.BUF_GI, np.float32)))
+            g.close()
+        yy, xx = np.mgrid[0:c.H, 0:c.W]
+        cls = (xx & 3) + 4 * (yy & 3)
+        own = (cls >= kw.get("class_lo", 0)) & (cls < kw.get("class_hi", 16))      # a shard writes only its classes' pixels
+        ref = imgs[0][1].reshape(c.H, c.W, 4).view(np.uint32)[own]
+        for ism, gi in imgs[1:]:
+            assert np.array_equal(gi.reshape(c.H, c.W, 4).view(np.uint32)[own], ref)
+            if not kw:
+                assert np.array_equal(ism, imgs[0][0])
 
 
 def test_packed_only_output(case_small, case_mid):
