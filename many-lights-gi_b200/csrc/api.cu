@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -132,6 +133,11 @@ struct mlgi_ctx {
     cudaStream_t cap = nullptr; cudaGraphExec_t graph_exec = nullptr; std::vector<char> graph_key;
     unsigned long long graph_launches = 0, graph_replays = 0, graph_instantiations = 0;
     double last_enqueue_us = 0.0;
+    // CUDA graph of the host-input frames (mlgi_frame_host*, mlgi_frame_sharded_host): uploads, stages and read-backs of one frame
+    int host_graph = -1;            // -1: replay the sharded host frame only (measured at 4K on one GPU: the graph of mlgi_frame_host is 0.03-0.08 ms slower than
+                                    // its direct launches, whose enqueueing overlaps the 2 ms of device work); 0 / 1: MLGI_HOST_GRAPH
+    cudaGraphExec_t hgraph_exec = nullptr; std::vector<char> hgraph_key, hgraph_seen; bool hgraph_valid = false;
+    unsigned long long hgraph_launches = 0, hgraph_replays = 0;
     float4* planar_ext = nullptr;   // caller-owned [16][PH][PW] float4 exchange buffer (mlgi_bind_planar_output)
     // staging for mlgi_frame_host
     uint32_t* st_rsm_diffuse = nullptr; uint32_t* st_rsm_normal = nullptr; float* st_rsm_depth = nullptr;
@@ -148,7 +154,7 @@ struct mlgi_ctx {
     cudaEvent_t ev_ism = nullptr;
     cudaEvent_t ev_up[kSlabs] = {nullptr}, ev_cull[kSlabs] = {nullptr}, ev_fg[kSlabs] = {nullptr};
     bool host_slabs_set = false;   // MLGI_HOST_SLABS given: also fixes the phase count of the sharded host frame (default there: by grid size)
-    int host_slabs = 6;     // measured at 4K on PCIe 5 x16: 1 slab 3.60 ms, 2: 2.95, 4: 2.49, 6: 2.42, 8: 2.49, 16: 2.51
+    int host_slabs = 8;     // measured at 4K on PCIe 5 x16 (interleaved slabs, tiles sorted per slab): 4 slabs 2.16 ms, 6: 2.07, 8: 2.03
     cudaEvent_t ev[T_COUNT][2];
     bool ev_used[T_COUNT];
     bool events_created = false;
@@ -393,6 +399,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     cudaEventCreateWithFlags(&ctx->ev_vpl, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_rsm, cudaEventDisableTiming);
     cudaStreamCreateWithPriority(&ctx->cap, cudaStreamNonBlocking, prio_hi);
+    if (const char* e12 = getenv("MLGI_HOST_GRAPH")) ctx->host_graph = atoi(e12) != 0;          // A/B switch: host-input frames replayed as a graph (default) | direct launches
     if (const char* e7 = getenv("MLGI_GRAPH")) ctx->use_graph = atoi(e7) != 0;                  // A/B switch: graph replay (default) | direct launches
     // aux carries the slab culling of the host-input frame: highest priority, so that its (small) kernels are placed as soon as
     // a slab has arrived instead of waiting behind the resident gathering CTAs of earlier slabs
@@ -440,6 +447,7 @@ MLGI_API void mlgi_destroy(mlgi_ctx* ctx) {
     if (ctx->ev_vpl) cudaEventDestroy(ctx->ev_vpl);
     if (ctx->ev_rsm) cudaEventDestroy(ctx->ev_rsm);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->hgraph_exec) cudaGraphExecDestroy(ctx->hgraph_exec);
     if (ctx->cap) cudaStreamDestroy(ctx->cap);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->fg2) cudaStreamDestroy(ctx->fg2);
@@ -1190,13 +1198,101 @@ static const char* const kTrCull[16] = {"cull0","cull1","cull2","cull3","cull4",
 static const char* const kTrFg[16] = {"fg0","fg1","fg2","fg3","fg4","fg5","fg6","fg7","fg8","fg9","fg10","fg11","fg12","fg13","fg14","fg15"};
 static const char* const kTrRd[16] = {"rd0","rd1","rd2","rd3","rd4","rd5","rd6","rd7","rd8","rd9","rd10","rd11","rd12","rd13","rd14","rd15"};
 
+// The host-input frames as a CUDA graph. Each of them issues 40-80 API calls per frame (strided uploads, stage launches, event
+// edges between five streams, read-backs); with several GPUs the device work per frame drops below a millisecond and those
+// calls -- and the jitter of eight host processes issuing them -- become the frame time. A frame whose arguments (host pointers
+// included) equal the previous frame's is captured once and replayed with one launch; arguments that change every frame (an
+// animated light) keep the direct path, which needs no capture. Only pinned host memory is captured (pageable copies are
+// staged synchronously by the runtime); per-stage timers and the timeline trace use the direct path.
+struct HostFrameKey {
+    mlgi_rsm hr; mlgi_camera light; mlgi_mesh mesh; mlgi_gbuffer hg; mlgi_camera cam; mlgi_params p;
+    const void* host_out; int kind, packed, fg_sorted, use_texture, tex_float_coord, fg_bulk, host_slabs, xch_direct;
+};
+static bool is_pinned_host(const void* ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return pa.type == cudaMemoryTypeHost;
+}
+static void mark_host_frame_done(mlgi_ctx* ctx, const mlgi_params* p) {
+    ctx->have_vpl = ctx->have_points = ctx->have_atlas = ctx->have_ism = ctx->have_gi = true;
+    ctx->mode_vpl = ctx->mode_points = ism_mode(ctx, p);
+    ctx->grouped_valid = false; ctx->have_blur = false; ctx->atlas_precleared = false;
+    if (p->cull_mode == MLGI_CULL_CLUSTERED) ctx->have_clustered = true;
+    if (p->cull_mode == MLGI_CULL_TILED) { ctx->have_tiled = true; ctx->tile_order_valid = false; }
+}
+// body(stream) issues the frame without its final synchronise. Returns < 0 on error, 0 if the caller has to run the direct path,
+// 1 if the frame was launched as a graph.
+static int host_frame_graph(mlgi_ctx* ctx, const HostFrameKey& key, const mlgi_params* p, cudaStream_t st, const std::function<int(cudaStream_t)>& body) {
+    const bool want = ctx->host_graph < 0 ? key.kind == 1 : ctx->host_graph != 0;
+    if (!ctx->use_graph || !want || ctx->cfg.enable_timers || ctx->trace_on || !ctx->cap || key.xch_direct) return 0;
+    const char* kb = (const char*)&key;
+    const bool hit = ctx->hgraph_valid && memcmp(kb, ctx->hgraph_key.data(), sizeof(key)) == 0;
+    if (!hit) {
+        const bool seen = ctx->hgraph_seen.size() == sizeof(key) && memcmp(kb, ctx->hgraph_seen.data(), sizeof(key)) == 0;
+        ctx->hgraph_seen.assign(kb, kb + sizeof(key));
+        if (!seen) return 0;                         // first frame with these arguments: direct; capture when they repeat
+        if (!is_pinned_host(key.hr.diffuse) || !is_pinned_host(key.hr.face_normal) || !is_pinned_host(key.hr.depth) || !is_pinned_host(key.hg.depth) ||
+            !is_pinned_host(key.hg.face_normal) || !is_pinned_host(key.host_out)) return 0;
+        if (p->cull_mode == MLGI_CULL_CLUSTERED) { int rc = ensure_clustered(ctx); if (rc) return rc; }
+        const unsigned long long l0 = ctx->launches;
+        CK(cudaStreamBeginCapture(ctx->cap, cudaStreamCaptureModeThreadLocal));
+        const int rc = body(ctx->cap);
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(ctx->cap, &g);
+        ctx->hgraph_launches = ctx->launches - l0;
+        ctx->launches = l0;
+        ctx->hgraph_valid = false;
+        if (rc) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
+        if (ce != cudaSuccess) { cudaGetLastError(); return fail(ctx, MLGI_E_CUDA, "host frame: cudaStreamEndCapture: %s", cudaGetErrorString(ce)); }
+        bool updated = false;
+        if (ctx->hgraph_exec) {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(ctx->hgraph_exec, g, &info) == cudaSuccess) updated = true;
+            else { cudaGetLastError(); cudaGraphExecDestroy(ctx->hgraph_exec); ctx->hgraph_exec = nullptr; }
+        }
+        if (!updated) {
+            const cudaError_t ie = cudaGraphInstantiate(&ctx->hgraph_exec, g, 0);
+            if (ie != cudaSuccess) { cudaGraphDestroy(g); ctx->hgraph_exec = nullptr; return fail(ctx, MLGI_E_CUDA, "host frame: cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+            ctx->graph_instantiations++;
+        }
+        cudaGraphDestroy(g);
+        ctx->hgraph_key.assign(kb, kb + sizeof(key));
+        ctx->hgraph_valid = true;
+    }
+    CK(cudaGraphLaunch(ctx->hgraph_exec, st));
+    ctx->launches += ctx->hgraph_launches;
+    ctx->hgraph_replays++; ctx->graph_replays++;
+    mark_host_frame_done(ctx, p);
+    return 1;
+}
+
+static int frame_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
+                           const mlgi_camera* cam, const mlgi_params* p, void* host_out, bool packed, cudaStream_t st);
+
 static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
                            const mlgi_camera* cam, const mlgi_params* p, void* host_out, bool packed, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
     DeviceGuard dg_(ctx);
-    if (!hr || !hg || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer is NULL");
+    if (!hr || !hg || !light || !mesh || !cam || !p || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer is NULL");
     if (packed && !ctx->gi_packed) return fail(ctx, MLGI_E_INVALID, "mlgi_frame_host_packed needs cfg.gi_packed");
     cudaStream_t st = (cudaStream_t)stream;
+    HostFrameKey key;
+    memset(&key, 0, sizeof(key));
+    key.hr = *hr; key.light = *light; key.mesh = *mesh; key.hg = *hg; key.cam = *cam; key.p = *p; key.host_out = host_out; key.kind = 0; key.packed = packed;
+    key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture; key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk;
+    key.host_slabs = ctx->host_slabs;
+    int rc = host_frame_graph(ctx, key, p, st, [&](cudaStream_t cs) { return frame_host_body(ctx, hr, light, mesh, hg, cam, p, host_out, packed, cs); });
+    if (rc < 0) return rc;
+    if (rc == 0 && (rc = frame_host_body(ctx, hr, light, mesh, hg, cam, p, host_out, packed, st))) return rc;
+    CK(cudaStreamSynchronize(st));
+    trace_dump(ctx);
+    return MLGI_OK;
+}
+
+static int frame_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
+                           const mlgi_camera* cam, const mlgi_params* p, void* host_out, bool packed, cudaStream_t st) {
+    void* stream = (void*)st;
     const size_t RS = (size_t)ctx->cfg.rsm_width * ctx->cfg.rsm_height, WH = (size_t)ctx->cfg.width * ctx->cfg.height;
     // Three streams start together (after whatever the caller queued on `st` before): the side stream carries every upload
     // (RSM first, 3 MB, then the camera G-buffer, 8 B/pixel); the aux stream clears the atlas, builds the VPLs as soon as the RSM
@@ -1274,17 +1370,23 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
         if ((rc = upload(0))) return rc;
         if ((rc = ism_chain())) return rc;
         trace_mark(ctx, "ism", st);
+        int slab_tile0 = 0;
         for (int k = 0; k < K; k++) {
             if (k > 0 && (rc = upload(k))) return rc;
             CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_up[k], 0));
             ctx->launches += cull_tiled_rows(ctx, ctx->st_depth, ctx->st_normal, to_mat4(inv), k, K, (TY - k + K - 1) / K, ctx->aux);
+            if (ctx->fg_sorted) {       // the slab's tiles, longest list first (a slab launch has a tail like the whole-frame launch)
+                ctx->launches += launch_tile_order_ids(ctx->tile_weight, ctx->slab_order, slab_tile0, ((TY - k + K - 1) / K) * ctx->TX, ctx->cfg.vpl_count,
+                                                       ctx->cfg.class_lo, ctx->cfg.class_hi, ctx->tile_order, ctx->aux);
+                slab_tile0 += ((TY - k + K - 1) / K) * ctx->TX;
+            }
             CK(cudaEventRecord(ctx->ev_cull[k], ctx->aux));
             trace_mark(ctx, kTrCull[k], ctx->aux);
         }
         ctx->have_tiled = true; ctx->tile_order_valid = false;
         GatherArgs a;
         if ((rc = build_gather_args(ctx, &dg, cam, nullptr, p, &a))) return rc;
-        a.tile_order = ctx->slab_order;          // the tiles slab by slab (ensure_slab_order)
+        a.tile_order = ctx->fg_sorted ? ctx->tile_order : ctx->slab_order;   // the tiles slab by slab, inside a slab longest list first
         {
             // consecutive slabs alternate between the caller's stream and fg2: the gathering kernel's tail (a few long-list
             // tiles keeping a handful of SMs busy) then overlaps the next slab instead of idling the GPU once per slab
@@ -1323,8 +1425,6 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
         CK(cudaGetLastError());
         ctx->have_gi = true; ctx->have_blur = false;
         trace_mark(ctx, "end", st);
-        CK(cudaStreamSynchronize(st));
-        trace_dump(ctx);
         return MLGI_OK;
     }
     CK(cudaMemcpyAsync(ctx->st_depth, hg->depth, WH * 4, cudaMemcpyHostToDevice, ctx->side));
@@ -1342,7 +1442,6 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
         if (packed) CK(cudaMemcpyAsync(host_out, ctx->gi_packed, WH * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         else CK(cudaMemcpyAsync(host_out, ctx->gi, WH * sizeof(float4), cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaStreamSynchronize(st));
     return MLGI_OK;
 }
 
@@ -1367,18 +1466,38 @@ MLGI_API int mlgi_sharded_rows(mlgi_ctx* ctx, int* row_begin, int* row_block, in
     return MLGI_OK;
 }
 
+static int frame_sharded_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
+                                   const mlgi_camera* cam, const mlgi_params* p, uint32_t* host_gi_packed, cudaStream_t st);
+
 MLGI_API int mlgi_frame_sharded_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
                                      const mlgi_camera* cam, const mlgi_params* p, uint32_t* host_gi_packed, void* stream) {
     if (!ctx) return MLGI_E_INVALID;
     DeviceGuard dg_(ctx);
     auto& x = ctx->xch;
     if (!x.connected) return fail(ctx, MLGI_E_ORDER, "mlgi_frame_sharded_host needs a connected exchange");
-    if (!hr || !hg || !cam || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer/camera is NULL");
+    if (!hr || !hg || !cam || !light || !mesh || !p || !hr->diffuse || !hr->face_normal || !hr->depth || !hg->depth || !hg->face_normal) return fail(ctx, MLGI_E_INVALID, "host rsm/gbuffer/camera is NULL");
     if (!ctx->gi_packed) return fail(ctx, MLGI_E_INVALID, "mlgi_frame_sharded_host needs cfg.gi_packed");
     if (ctx->cfg.enable_timers) return fail(ctx, MLGI_E_INVALID, "per-stage timers are not available on the sharded host path");
-    if (p && p->cull_mode != MLGI_CULL_TILED) return fail(ctx, MLGI_E_UNSUPPORTED, "mlgi_frame_sharded_host runs tiled culling (the G-buffer is distributed by tile rows)");
+    if (p->cull_mode != MLGI_CULL_TILED) return fail(ctx, MLGI_E_UNSUPPORTED, "mlgi_frame_sharded_host runs tiled culling (the G-buffer is distributed by tile rows)");
     if (!ctx->aux || !ctx->side || !ctx->rd) return fail(ctx, MLGI_E_CUDA, "internal streams missing");
     cudaStream_t st = (cudaStream_t)stream;
+    HostFrameKey key;
+    memset(&key, 0, sizeof(key));
+    key.hr = *hr; key.light = *light; key.mesh = *mesh; key.hg = *hg; key.cam = *cam; key.p = *p; key.host_out = host_gi_packed; key.kind = 1; key.packed = 1;
+    key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture; key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk;
+    key.host_slabs = ctx->host_slabs_set ? ctx->host_slabs : 0; key.xch_direct = ctx->xch_direct;
+    int rc = host_frame_graph(ctx, key, p, st, [&](cudaStream_t cs) { return frame_sharded_host_body(ctx, hr, light, mesh, hg, cam, p, host_gi_packed, cs); });
+    if (rc < 0) return rc;
+    if (rc == 0 && (rc = frame_sharded_host_body(ctx, hr, light, mesh, hg, cam, p, host_gi_packed, st))) return rc;
+    CK(cudaStreamSynchronize(st));
+    trace_dump(ctx);
+    return MLGI_OK;
+}
+
+static int frame_sharded_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera* light, const mlgi_mesh* mesh, const mlgi_gbuffer* hg,
+                                   const mlgi_camera* cam, const mlgi_params* p, uint32_t* host_gi_packed, cudaStream_t st) {
+    auto& x = ctx->xch;
+    void* stream = (void*)st;
     const int W = ctx->cfg.width, H = ctx->cfg.height, TX = ctx->TX, TY = ctx->TY, G = x.world, g = x.rank;
     const size_t RS = (size_t)ctx->cfg.rsm_width * ctx->cfg.rsm_height, WH = (size_t)W * H;
     const size_t gb_plane = (WH * 4 + 255) & ~(size_t)255;
@@ -1521,8 +1640,6 @@ MLGI_API int mlgi_frame_sharded_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const ml
     CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     ctx->have_gi = true; ctx->have_blur = false;
     trace_mark(ctx, "end", st);
-    CK(cudaStreamSynchronize(st));
-    trace_dump(ctx);
     return MLGI_OK;
 }
 

@@ -221,6 +221,7 @@ int launch_tile_bounds(const float* depth, const uint32_t* face_normal, int W, i
 int launch_tile_lists(const float* bounds, size_t parity_stride, const uint32_t* frame_ctr, int W, const VplRecord* records, int N, int class_lo, int class_hi, int ty0, int ystride, int nrows,
                       uint16_t* lists, uint32_t* tile_weight, cudaStream_t st);
 int launch_tile_order(const uint32_t* tile_weight, int W, int N, int class_lo, int class_hi, int ty0, int nrows, uint32_t* tile_order, cudaStream_t st);
+int launch_tile_order_ids(const uint32_t* tile_weight, const uint32_t* ids, int first, int ntiles, int N, int class_lo, int class_hi, uint32_t* tile_order, cudaStream_t st);
 
 struct GatherArgs {
     const float* depth; const uint32_t* face_normal; int W, H;

@@ -899,18 +899,25 @@ __global__ void __launch_bounds__(512) tile_lists_kernel(const float* __restrict
 // Gathering CTAs are scheduled in launch order, and a tile's cost is proportional to its list length: ordering the tiles
 // by descending weight (longest first) removes the tail in which a few long-list tiles keep a handful of SMs busy. Counting
 // sort into 128 weight bins by one CTA; the order inside a bin is arbitrary, which is immaterial (tiles are independent).
-__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ tile_weight, int tile0, int ntiles, int wmax,
-                                                          uint32_t* __restrict__ order) {
+// The tiles to order are tile0 .. tile0 + ntiles - 1, or, with `ids`, the listed ones ids[tile0 .. tile0 + ntiles - 1] (a slab of
+// interleaved tile rows of the host-input frame); the permutation is written to order[tile0 .. tile0 + ntiles - 1] either way.
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ tile_weight, const uint32_t* __restrict__ ids, int tile0, int ntiles,
+                                                          int wmax, uint32_t* __restrict__ order) {
     __shared__ uint32_t hist[128], start[128];
     if (threadIdx.x < 128) hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t div = (uint32_t)wmax / 128u + 1u;
-    for (int t = threadIdx.x; t < ntiles; t += 1024) atomicAdd(&hist[127u - min(tile_weight[tile0 + t] / div, 127u)], 1u);
+    for (int t = threadIdx.x; t < ntiles; t += 1024) {
+        const uint32_t id = ids ? ids[tile0 + t] : (uint32_t)(tile0 + t);
+        atomicAdd(&hist[127u - min(tile_weight[id] / div, 127u)], 1u);
+    }
     __syncthreads();
     if (threadIdx.x == 0) { uint32_t acc = 0; for (int b = 0; b < 128; b++) { start[b] = acc; acc += hist[b]; } }
     __syncthreads();
-    for (int t = threadIdx.x; t < ntiles; t += 1024)
-        order[tile0 + atomicAdd(&start[127u - min(tile_weight[tile0 + t] / div, 127u)], 1u)] = (uint32_t)(tile0 + t);
+    for (int t = threadIdx.x; t < ntiles; t += 1024) {
+        const uint32_t id = ids ? ids[tile0 + t] : (uint32_t)(tile0 + t);
+        order[tile0 + atomicAdd(&start[127u - min(tile_weight[id] / div, 127u)], 1u)] = id;
+    }
 }
 
 // tile rows ty0, ty0 + ystride, ... (nrows of them): the host-input frame culls each G-buffer slab as soon as it is uploaded
@@ -932,7 +939,13 @@ int launch_tile_lists(const float* bounds, size_t parity_stride, const uint32_t*
 // the order, if requested, is a permutation of the tiles of rows [ty0, ty0 + nrows) (ystride 1), stored at their own positions
 int launch_tile_order(const uint32_t* tile_weight, int W, int N, int class_lo, int class_hi, int ty0, int nrows, uint32_t* tile_order, cudaStream_t st) {
     const int TX = (W + kTile - 1) / kTile;
-    tile_order_kernel<<<1, 1024, 0, st>>>(tile_weight, ty0 * TX, nrows * TX, (class_hi - class_lo) * (N / 16), tile_order);
+    tile_order_kernel<<<1, 1024, 0, st>>>(tile_weight, nullptr, ty0 * TX, nrows * TX, (class_hi - class_lo) * (N / 16), tile_order);
+    return 1;
+}
+// the same for the tiles ids[first .. first + ntiles): order[first .. first + ntiles) = those tiles, longest list first
+int launch_tile_order_ids(const uint32_t* tile_weight, const uint32_t* ids, int first, int ntiles, int N, int class_lo, int class_hi, uint32_t* tile_order, cudaStream_t st) {
+    if (ntiles <= 0) return 0;
+    tile_order_kernel<<<1, 1024, 0, st>>>(tile_weight, ids, first, ntiles, (class_hi - class_lo) * (N / 16), tile_order);
     return 1;
 }
 

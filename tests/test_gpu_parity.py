@@ -285,6 +285,49 @@ def test_frame_host_end_to_end_matches_device_frame(gpu_case):
     assert np.array_equal(host_gi.numpy(), dev_gi)
 
 
+def test_host_frame_graph_replay(case_mid, monkeypatch):
+    """the host-input frame is captured into a CUDA graph when its arguments repeat (first call direct, second call captured,
+    later calls replayed): every call returns the device-resident frame's bits, fresh inputs written into the same pinned
+    buffers are picked up by the replay, new pointers fall back to the direct path, and a pageable buffer is never captured"""
+    from conftest import Case
+    torch = _torch()
+    c = case_mid
+    wl = c.wl
+    monkeypatch.setenv("MLGI_HOST_GRAPH", "1")       # (the default replays only the sharded host frame)
+    g = Gpu(c)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
+    hr, hg = mlgi.make_rsm(h[0], h[1], h[2]), mlgi.make_gbuffer(h[3], h[4])
+    host_gi = torch.zeros((c.H, c.W, 4), dtype=torch.float32).pin_memory()
+    p = mlgi.default_params(c.N)
+    g.ctx.frame(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    dev_gi = g.ctx.download(mlgi.BUF_GI, np.float32).reshape(c.H, c.W, 4).copy()
+    r0 = g.ctx.frame_stats()["graph_replays"]
+    for k in range(4):
+        host_gi.zero_()
+        g.ctx.frame_host(hr, g.light, g.mesh, hg, g.cam, p, host_gi=host_gi)
+        assert np.array_equal(host_gi.numpy(), dev_gi), "call %d" % k
+    assert g.ctx.frame_stats()["graph_replays"] - r0 == 3          # calls 1..3 (call 0 saw these arguments for the first time)
+    # new contents in the SAME pinned buffers: the replayed uploads read them
+    c2 = Case(c.W, c.H, c.N, 1024, 256, cell=0.5, clutter=12, sun=270.0)
+    for dst, src in zip(h[:3], (c2.wl.rsm_diffuse, c2.wl.rsm_normal, c2.wl.rsm_depth)):
+        dst.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+    light2 = mlgi.Camera.make(c2.wl.light_view, c2.wl.light_proj)
+    g.ctx.frame_host(hr, light2, g.mesh, hg, g.cam, p, host_gi=host_gi)          # new light matrices: direct path
+    assert g.ctx.frame_stats()["graph_replays"] - r0 == 3
+    gi = host_gi.numpy().reshape(c.H, c.W, 4)[:, :, :3].copy()
+    _check_radiance(gi, c2.gather(mlgi.CULL_TILED, True), "host frame, animated light")
+    g.ctx.frame_host(hr, light2, g.mesh, hg, g.cam, p, host_gi=host_gi)          # repeated: captured
+    assert g.ctx.frame_stats()["graph_replays"] - r0 == 4
+    assert np.array_equal(host_gi.numpy().reshape(c.H, c.W, 4)[:, :, :3], gi)
+    pageable = torch.zeros((c.H, c.W, 4), dtype=torch.float32)
+    for _ in range(3):
+        g.ctx.frame_host(hr, light2, g.mesh, hg, g.cam, p, host_gi=pageable)
+        assert np.array_equal(pageable.numpy().reshape(c.H, c.W, 4)[:, :, :3], gi)
+    assert g.ctx.frame_stats()["graph_replays"] - r0 == 4
+    g.close()
+
+
 def test_planar_output_and_class_sharding_is_bit_identical(case_small, case_mid):
     """multi-GPU contract: a ctx that owns classes [lo,hi) produces exactly the
     1-GPU pixels of those classes; the class-planar sub-images tile the full image."""
@@ -779,6 +822,9 @@ def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid, phases, monkeypatch):
     torch = _torch()
     c = case_mid
     monkeypatch.setenv("MLGI_HOST_SLABS", str(phases))
+    # direct launches: on ONE GPU a rank's graph instantiation can queue behind the other rank's kernel that is already waiting
+    # for it (the graph-replayed form is covered on two GPUs by tests/test_gpu_multi.py and on one GPU by test_host_frame_graph_replay)
+    monkeypatch.setenv("MLGI_HOST_GRAPH", "0")
     wl, sc = c.wl, c.wl.scene
     full = Gpu(c)
     full.ctx.close()
