@@ -479,7 +479,9 @@ def main():
         if not e2e_ok:
             raise SystemExit("bench.py: the end-to-end path did not reproduce the device-resident frame")
         nb = lambda x: x.numel() * x.element_size()
-        h2d = sum(nb(x) for x in h) if world == 1 else world * sum(nb(x) for x in h[:3]) + sum(nb(x) for x in h[3:])   # summed over ranks
+        # bytes that cross PCIe host->device per step, summed over ranks: the library uploads the camera G-buffer once in total and, per
+        # rank, the N RSM texels the VPL build samples (12 B per VPL, gathered on the host from the caller's RSM planes)
+        h2d = world * wl.N * 12 + sum(nb(x) for x in h[3:])
         e2e = {"value": pairs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_gi.numel() * 4,
                "ms_per_step": dt * 1e3, "steps": n_e2e, "verified_against_device_path": e2e_ok,
                "call": ("mlgi_frame_host_packed (pinned host RSM + G-buffer in, GL_R11F_G11F_B10F GI image out = the reference's giBuffer "

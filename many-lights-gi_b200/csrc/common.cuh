@@ -185,7 +185,7 @@ __device__ __forceinline__ uint32_t pack_r11g11b10(float r, float g, float b) {
 struct SliceTable { float b[17]; };
 
 int launch_vpl_process(const mlgi_rsm& rsm, int rsm_w, int rsm_h, int N, const Mat4& inv_biased_light_vp,
-                       float lightIntensity, int shuffle, const int32_t* shuffled, const IsmMode& mode,
+                       float lightIntensity, int shuffle, const int32_t* shuffled, const IsmMode& mode, int compact,
                        float* vpl, float* packed, VplRecord* records, cudaStream_t st);
 
 int launch_point_generate(const mlgi_mesh& mesh, const IsmMode& mode, float tessLevelFactor, int max_points, float4* points, uint32_t* point_bucket,

@@ -27,7 +27,7 @@ static constexpr unsigned FULL = 0xFFFFFFFFu;
 // =====================================================================================
 __global__ void vpl_process_kernel(const uint32_t* __restrict__ diffuse, const uint32_t* __restrict__ normal10,
                                    const float* __restrict__ depth, int rsm_w, int rsm_h, int N, Mat4 inv,
-                                   float lightIntensity, int shuffle, const int32_t* __restrict__ shuffled, IsmMode mode,
+                                   float lightIntensity, int shuffle, const int32_t* __restrict__ shuffled, IsmMode mode, int compact,
                                    float* __restrict__ vpl, float* __restrict__ packed, VplRecord* __restrict__ records) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint32_t)N) return;
@@ -36,7 +36,8 @@ __global__ void vpl_process_kernel(const uint32_t* __restrict__ diffuse, const u
     uint32_t tcx = (idx % ax) * (uint32_t)rsm_w / ax;                 // :50
     uint32_t tcy = (idx / ax) * (uint32_t)rsm_h / ay;
     float tfx = float(tcx) / float(rsm_w), tfy = float(tcy) / float(rsm_h);  // :51
-    size_t t = (size_t)tcy * rsm_w + tcx;
+    // compact: the three planes hold only the N sampled texels, in VPL order (host-input frames upload 12 B per VPL instead of the RSM)
+    size_t t = compact ? (size_t)idx : (size_t)tcy * rsm_w + tcx;
     uint32_t d8 = diffuse[t];
     float3 dif = f3(float(d8 & 0xFFu) / 255.0f, float((d8 >> 8) & 0xFFu) / 255.0f, float((d8 >> 16) & 0xFFu) / 255.0f);
     float3 nrm = decode_rgb10_sn(normal10[t]);                        // :54
@@ -75,10 +76,10 @@ __global__ void vpl_process_kernel(const uint32_t* __restrict__ diffuse, const u
 }
 
 int launch_vpl_process(const mlgi_rsm& rsm, int rsm_w, int rsm_h, int N, const Mat4& inv, float lightIntensity,
-                       int shuffle, const int32_t* shuffled, const IsmMode& mode, float* vpl, float* packed, VplRecord* records,
+                       int shuffle, const int32_t* shuffled, const IsmMode& mode, int compact, float* vpl, float* packed, VplRecord* records,
                        cudaStream_t st) {
     vpl_process_kernel<<<(N + 63) / 64, 64, 0, st>>>(rsm.diffuse, rsm.face_normal, rsm.depth, rsm_w, rsm_h, N, inv,
-                                                    lightIntensity, shuffle, shuffled, mode, vpl, packed, records);
+                                                    lightIntensity, shuffle, shuffled, mode, compact, vpl, packed, records);
     return 1;
 }
 
