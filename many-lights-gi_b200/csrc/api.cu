@@ -826,6 +826,9 @@ MLGI_API int mlgi_exchange_create(mlgi_ctx* ctx, int rank, int world, void* out_
     CK(cudaMalloc((void**)&x.d_state, 4 * sizeof(uint32_t)));
     CK(cudaMemset(x.d_state, 0, 4 * sizeof(uint32_t)));
     x.rank = rank; x.world = world;
+    // measured at 4K/4096 (device-resident frame, profiles/r2_sweep_host_frame.txt): pull 0.386 / push 0.358 ms on 8 GPUs, 0.565 / 0.540 on 4:
+    // with many small ranks the gathering is short and the pull is an exposed tail, while pushed planes travel under the gathering
+    x.push = world >= 4;
     if (const char* e = getenv("MLGI_XCH")) x.push = strcmp(e, "push") == 0;      // A/B switch
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, x.base));
@@ -1530,8 +1533,11 @@ static int frame_sharded_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi
     // k - 1 is gathered and phase k - 2 is assembled and read back: PCIe in both directions hides behind the gathering, as in
     // the single-GPU slab pipeline. K is sized so that a phase's gathering launch still fills the GPU a few times over
     // (MLGI_HOST_SLABS overrides it).
+    // Measured at 4K (profiles/r2_sweep_host_frame.txt, end to end in ms by phase count): 2 GPUs 1.65 / 1.59 / 1.61 (2 / 4 / 6 phases),
+    // 4 GPUs 1.53 / 1.19 / 1.28 (1 / 2 / 3), 8 GPUs 1.06 / 0.90 / 0.89 (1 / 2 / 3; the uploads of eight ranks share the host's
+    // memory bandwidth, so finer phases pay there). Small images (less than about one wave of gathering CTAs per phase) use one phase.
     const long long ctas = (long long)TX * TY * (ctx->cfg.class_hi - ctx->cfg.class_lo);
-    int K = ctx->host_slabs_set ? ctx->host_slabs : (int)((ctas + 1850) / 3700);
+    int K = ctx->host_slabs_set ? ctx->host_slabs : ctas < 3000 ? 1 : G == 2 ? 4 : G == 4 ? 2 : 3;
     K = std::max(1, std::min(K, std::min((int)mlgi_ctx::kSlabs, (TY + G - 1) / G)));
     const int rows_per_phase = G * ((TY + K * G - 1) / (K * G));
     K = (TY + rows_per_phase - 1) / rows_per_phase;
