@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--cull", default="tiled", choices=["tiled", "clustered"])
     ap.add_argument("--exchange", default="auto", choices=["auto", "pull", "push", "nccl"],
                     help="N>1: one exchange kernel pulls the class planes over NVLink peer memory (pull), the gathering epilogue stores "
-                         "them into every peer (push), the library's default (auto: pull on 2 GPUs, push on 4 and 8), or one NCCL all-gather")
+                         "them into every peer (push), the library's default (auto = push), or one NCCL all-gather")
     ap.add_argument("--anim-shard", default="class", choices=["class", "frame"],
                     help="anim64 at N>1: shard every frame by interleave class (default) or hand whole frames to replicas")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -387,7 +387,7 @@ def main():
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
     if args.exchange == "auto":
-        args.exchange = os.environ.get("MLGI_XCH") or ("push" if world >= 4 else "pull")       # the library's own default
+        args.exchange = os.environ.get("MLGI_XCH") or "push"       # the library's own default
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -117,8 +117,8 @@ struct mlgi_ctx {
     // flags[32..39] / flags[48..55]: the same two signals per PHASE of the host-input sharded frame (value 16 f + phase).
     struct Exchange {
         int rank = 0, world = 0;
-        int push = 0;                         // 0: gathering writes its own buffer, the exchange kernel pulls over NVLink (default)
-                                              // 1: the gathering epilogue stores into every rank's buffer (round-1 scheme; MLGI_XCH=push)
+        int push = 1;                         // 1: the gathering epilogue stores its staged 64-byte rows into every rank's buffer (default, measured)
+                                              // 0: gathering writes its own buffer, the exchange kernel pulls over NVLink (MLGI_XCH=pull)
         char* base = nullptr;
         size_t buf_bytes = 0, gb_off = 0, bounds_off = 0, bounds_bytes = 0;
         // 64-pixel tile row t belongs to rank t mod world: the tiles it bounds, and in the host-input frame the G-buffer rows it
@@ -826,9 +826,9 @@ MLGI_API int mlgi_exchange_create(mlgi_ctx* ctx, int rank, int world, void* out_
     CK(cudaMalloc((void**)&x.d_state, 4 * sizeof(uint32_t)));
     CK(cudaMemset(x.d_state, 0, 4 * sizeof(uint32_t)));
     x.rank = rank; x.world = world;
-    // measured at 4K/4096 (device-resident frame, profiles/r2_sweep_host_frame.txt): pull 0.386 / push 0.358 ms on 8 GPUs, 0.565 / 0.540 on 4:
-    // with many small ranks the gathering is short and the pull is an exposed tail, while pushed planes travel under the gathering
-    x.push = world >= 4;
+    // measured at 4K/4096 (device-resident frame, profiles/r2_sweep_host_frame.txt): pull / push 0.386 / 0.358 ms on 8 GPUs, 0.565 / 0.540 on 4,
+    // 0.965 / 0.945 on 2: a pull is an exposed tail after the gathering, pushed planes travel under it
+    x.push = 1;
     if (const char* e = getenv("MLGI_XCH")) x.push = strcmp(e, "push") == 0;      // A/B switch
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, x.base));
