@@ -107,6 +107,7 @@ struct mlgi_ctx {
     struct OverrideTex { const uint16_t* ptr; cudaTextureObject_t tex; };
     std::vector<OverrideTex> override_tex;
     int use_texture = 1, tex_float_coord = 0, fg_bulk = 1, xch_direct = 0;
+    int fg_host_occ = 10;           // resident gathering CTAs per SM in the single-GPU host pipeline (A/B: MLGI_FG_HOST_OCC; 10 = no cap, the measured best)
     int pp_parts = 1;               // class groups of the pull-push / gathering pipeline in mlgi_frame (A/B: MLGI_PP_PARTS; measured: no gain, off)
     int xch_cull = 1;               // connected ranks bound 1/world of the tiles each and exchange the bounds (A/B: MLGI_XCH_CULL)
     IsmMode mode_vpl{}, mode_points{};   // the n3 knobs the VPL records / the point list were built with
@@ -154,8 +155,11 @@ struct mlgi_ctx {
     cudaStream_t rd = nullptr;                   // read-back of finished slabs (its own stream: the D2H copies must not queue behind the culling of later slabs)
     cudaEvent_t ev_ism = nullptr;
     cudaEvent_t ev_up[kSlabs] = {nullptr}, ev_cull[kSlabs] = {nullptr}, ev_fg[kSlabs] = {nullptr};
+    // slab k of the single-GPU host pipeline = tile rows off, off + stride, ... (host_slab_plan)
+    struct SlabPlan { int off, stride; };
+    std::vector<SlabPlan> slab_plan;
     bool host_slabs_set = false;   // MLGI_HOST_SLABS given: also fixes the phase count of the sharded host frame (default there: by grid size)
-    int host_slabs = 8;     // measured at 4K on PCIe 5 x16 (interleaved slabs, tiles sorted per slab): 4 slabs 2.16 ms, 6: 2.07, 8: 2.03
+    int host_slabs = 10;    // measured at 4K on PCIe 5 x16 (interleaved slabs, tiles sorted per slab): 4 slabs 2.16 ms, 6: 2.07, 8: 2.01, 10: 1.99, 12: 2.06, 16: 2.03
     cudaEvent_t ev[T_COUNT][2];
     bool ev_used[T_COUNT];
     bool events_created = false;
@@ -415,20 +419,34 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev_fg[k], cudaEventDisableTiming);
     }
     if (const char* e10 = getenv("MLGI_HOST_TRACE")) ctx->trace_on = atoi(e10) != 0;
-    if (const char* e5 = getenv("MLGI_HOST_SLABS")) ctx->host_slabs_set = true, ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5)));   // A/B switch
+    if (const char* e5 = getenv("MLGI_HOST_SLABS")) { if (atoi(e5) > 0) ctx->host_slabs_set = true, ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5))); }   // A/B switch
     if (const char* e3 = getenv("MLGI_XCH_DIRECT")) ctx->xch_direct = atoi(e3) != 0;
+    if (const char* e13 = getenv("MLGI_FG_HOST_OCC")) ctx->fg_host_occ = std::max(1, std::min(10, atoi(e13)));
     if (const char* e4 = getenv("MLGI_PP_PARTS")) ctx->pp_parts = std::max(1, std::min(16, atoi(e4)));
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) { ctx->use_texture = strcmp(e2, "ldg") != 0; ctx->tex_float_coord = strcmp(e2, "texf") == 0 ? 1 : strcmp(e2, "texi") == 0 ? 2 : strcmp(e2, "none") == 0 ? 3 : 0; }   // A/B switch: tex (default) | texf | texi | ldg
     if (const char* e11 = getenv("MLGI_XCH_CULL")) ctx->xch_cull = atoi(e11) != 0;             // A/B switch: bounds exchanged between ranks (default) | every rank bounds all tiles
     if (const char* e8 = getenv("MLGI_FG_BULK")) ctx->fg_bulk = atoi(e8) != 0;                 // A/B switch: records staged by cp.async.bulk (default) | LDG + STS
     if (const char* e6 = getenv("MLGI_FG_SORTED")) ctx->fg_sorted = atoi(e6) != 0;             // A/B switch: longest-list tiles first (default) | row-major
     if (make_ism_texture(ctx->ism, ctx->A, &ctx->ism_tex) != cudaSuccess) { cudaGetLastError(); ctx->ism_tex = 0; }
-    {   // the gathering order of the host-input frame: tiles slab by slab
-        const int K = std::min(ctx->host_slabs, ctx->TY);
+    {   // Slabs of the host-input frame, and its gathering order: tiles slab by slab. K uniform interleaved slabs (rows k, k + K, ...;
+        // default 10, MLGI_HOST_SLABS = K). MLGI_HOST_SLABS=shaped selects seven slabs with 1/8, 1/4, 1/4, 1/8, 1/8, 1/16, 1/16 of the
+        // tile rows (each still an arithmetic progression of rows: a small first slab that is ready when the ISM chain ends, small
+        // last slabs because the frame ends with the last slab's upload -> cull -> gathering -> read-back) -- measured, no gain
+        // (2.03 vs 2.01 / 1.99 ms for 8 / 10 uniform slabs): what delays a slab's gathering is its culling kernels waiting for SM
+        // slots under the running gathering, and capping the gathering's occupancy to make room (MLGI_FG_HOST_OCC) costs more
+        // than it saves (2.05 ms at 8 CTAs per SM).
+        const char* e5 = getenv("MLGI_HOST_SLABS");
+        if (e5 && strcmp(e5, "shaped") == 0 && ctx->TY >= 16) {
+            const int plan[7][2] = {{0, 8}, {1, 4}, {2, 4}, {3, 8}, {7, 8}, {4, 16}, {12, 16}};
+            for (auto& q : plan) ctx->slab_plan.push_back({q[0], q[1]});
+        } else {
+            const int K = std::min(ctx->host_slabs, ctx->TY);
+            for (int k = 0; k < K; k++) ctx->slab_plan.push_back({k, K});
+        }
         std::vector<uint32_t> order;
         order.reserve((size_t)ctx->TX * ctx->TY);
-        for (int k = 0; k < K; k++)
-            for (int ty = k; ty < ctx->TY; ty += K)
+        for (auto& sp : ctx->slab_plan)
+            for (int ty = sp.off; ty < ctx->TY; ty += sp.stride)
                 for (int tx = 0; tx < ctx->TX; tx++) order.push_back((uint32_t)(ty * ctx->TX + tx));
         if (cudaMemcpy(ctx->slab_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
             fail(nullptr, MLGI_E_CUDA, "init: slab order"); mlgi_destroy(ctx); return MLGI_E_CUDA;
@@ -1354,7 +1372,7 @@ static int frame_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
         return mlgi_ism_pullpush(ctx, nullptr, p, stream);
     };
     const bool whole_image = !ctx->xch.connected && !ctx->planar_ext;
-    if (p->cull_mode == MLGI_CULL_TILED && whole_image && ctx->aux && ctx->fg2 && ctx->rd && ctx->host_slabs > 1) {
+    if (p->cull_mode == MLGI_CULL_TILED && whole_image && ctx->aux && ctx->fg2 && ctx->rd && ctx->slab_plan.size() > 1) {
         // Slab pipeline: the image is cut into K interleaved slabs of whole tile rows -- slab k = tile rows k, k + K, k + 2K, ... --
         // so that every slab is a representative sample of the image: gathering cost per tile varies by an order of magnitude
         // over the image (sky vs. floor), and with contiguous slabs the cheap slabs are gathered faster than the next one
@@ -1362,17 +1380,21 @@ static int frame_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
         // slabs). Slab k is uploaded on the side stream (one strided 2-D copy per G-buffer plane), culled on the aux stream as
         // soon as it has arrived, gathered on the caller's stream (after the ISM build) and read back on its own stream while
         // the next slabs are gathered, so PCIe traffic in both directions hides behind the ISM build and the gathering.
-        const int K = std::min(ctx->host_slabs, ctx->TY), W = ctx->cfg.width, H = ctx->cfg.height, TY = ctx->TY;
+        const int K = (int)ctx->slab_plan.size(), W = ctx->cfg.width, H = ctx->cfg.height, TY = ctx->TY;
+        auto slab_off = [&](int k) { return ctx->slab_plan[k].off; };
+        auto slab_stride = [&](int k) { return ctx->slab_plan[k].stride; };
+        auto slab_rows = [&](int k) { return slab_off(k) < TY ? (TY - slab_off(k) + slab_stride(k) - 1) / slab_stride(k) : 0; };
         float vi[16], pi[16], inv[16];
         mat_inverse(cam->view, vi); mat_inverse(cam->proj, pi); mat_mul(vi, pi, inv);
         const size_t row_px = (size_t)kTile * W;                       // pixels of one full tile row
         const int last_rows = H - (TY - 1) * kTile;                    // image rows of the last tile row (1..64)
         // strided copy of slab k between two images with 4-byte pixels (tile rows k, k + K, ...; the last tile row may be partial)
         auto copy_slab = [&](void* dst, const void* src, int k, cudaMemcpyKind kind, cudaStream_t cs) -> int {
-            const int nrows = (TY - k + K - 1) / K;
-            const bool has_last = (TY - 1) % K == k;
+            const int nrows = slab_rows(k);
+            if (nrows <= 0) return MLGI_OK;
+            const bool has_last = (TY - 1 - slab_off(k)) % slab_stride(k) == 0;
             const int full_rows = (has_last && last_rows < kTile) ? nrows - 1 : nrows;
-            const size_t off = (size_t)k * row_px * 4, pitch = (size_t)K * row_px * 4;
+            const size_t off = (size_t)slab_off(k) * row_px * 4, pitch = (size_t)slab_stride(k) * row_px * 4;
             if (full_rows > 0) CK(cudaMemcpy2DAsync((char*)dst + off, pitch, (const char*)src + off, pitch, row_px * 4, full_rows, kind, cs));
             if (full_rows < nrows) {
                 const size_t o2 = (size_t)(TY - 1) * row_px * 4;
@@ -1399,11 +1421,11 @@ static int frame_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
         for (int k = 0; k < K; k++) {
             if (k > 0 && (rc = upload(k))) return rc;
             CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_up[k], 0));
-            ctx->launches += cull_tiled_rows(ctx, ctx->st_depth, ctx->st_normal, to_mat4(inv), k, K, (TY - k + K - 1) / K, ctx->aux);
+            ctx->launches += cull_tiled_rows(ctx, ctx->st_depth, ctx->st_normal, to_mat4(inv), slab_off(k), slab_stride(k), slab_rows(k), ctx->aux);
             if (ctx->fg_sorted) {       // the slab's tiles, longest list first (a slab launch has a tail like the whole-frame launch)
-                ctx->launches += launch_tile_order_ids(ctx->tile_weight, ctx->slab_order, slab_tile0, ((TY - k + K - 1) / K) * ctx->TX, ctx->cfg.vpl_count,
+                ctx->launches += launch_tile_order_ids(ctx->tile_weight, ctx->slab_order, slab_tile0, slab_rows(k) * ctx->TX, ctx->cfg.vpl_count,
                                                        ctx->cfg.class_lo, ctx->cfg.class_hi, ctx->tile_order, ctx->aux);
-                slab_tile0 += ((TY - k + K - 1) / K) * ctx->TX;
+                slab_tile0 += slab_rows(k) * ctx->TX;
             }
             CK(cudaEventRecord(ctx->ev_cull[k], ctx->aux));
             trace_mark(ctx, kTrCull[k], ctx->aux);
@@ -1412,6 +1434,7 @@ static int frame_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
         GatherArgs a;
         if ((rc = build_gather_args(ctx, &dg, cam, nullptr, p, &a))) return rc;
         a.tile_order = ctx->fg_sorted ? ctx->tile_order : ctx->slab_order;   // the tiles slab by slab, inside a slab longest list first
+        a.max_ctas_per_sm = ctx->fg_host_occ;
         {
             // consecutive slabs alternate between the caller's stream and fg2: the gathering kernel's tail (a few long-list
             // tiles keeping a handful of SMs busy) then overlaps the next slab instead of idling the GPU once per slab
@@ -1422,7 +1445,7 @@ static int frame_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
             for (int k = 0; k < K; k++) {
                 cudaStream_t fs = (k & 1) ? ctx->fg2 : st;
                 CK(cudaStreamWaitEvent(fs, ctx->ev_cull[k], 0));
-                a.tile_begin = tile0; a.tile_count = ((TY - k + K - 1) / K) * ctx->TX;
+                a.tile_begin = tile0; a.tile_count = slab_rows(k) * ctx->TX;
                 tile0 += a.tile_count;
                 ctx->launches += launch_final_gather(a, fs);
                 CK(cudaEventRecord(ctx->ev_fg[k], fs));
@@ -1431,10 +1454,10 @@ static int frame_host_body(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
                 if (host_out) {
                     if (packed) { if ((rc = copy_slab(host_out, ctx->gi_packed, k, cudaMemcpyDeviceToHost, ctx->rd))) return rc; }
                     else {       // fp32 RGBA: 16-byte pixels = four 4-byte "pixels" per pixel, the same strides scaled by 4
-                        const int nrows = (TY - k + K - 1) / K;
-                        const bool has_last = (TY - 1) % K == k;
+                        const int nrows = slab_rows(k);
+                        const bool has_last = nrows > 0 && (TY - 1 - slab_off(k)) % slab_stride(k) == 0;
                         const int full_rows = (has_last && last_rows < kTile) ? nrows - 1 : nrows;
-                        const size_t off = (size_t)k * row_px * 16, pitch = (size_t)K * row_px * 16;
+                        const size_t off = (size_t)slab_off(k) * row_px * 16, pitch = (size_t)slab_stride(k) * row_px * 16;
                         if (full_rows > 0) CK(cudaMemcpy2DAsync((char*)host_out + off, pitch, (const char*)ctx->gi + off, pitch, row_px * 16, full_rows, cudaMemcpyDeviceToHost, ctx->rd));
                         if (full_rows < nrows) {
                             const size_t o2 = (size_t)(TY - 1) * row_px * 16;

@@ -236,6 +236,7 @@ struct GatherArgs {
     int enable_shadowing;
     int tex_float_coord;    // texture path, A/B: 1 = hand the unfloored texel coordinate to the unit (MLGI_ISM_FETCH=texf), 2 = integer texel coordinates (texi)
     int bulk_staging;       // stage the VPL records with cp.async.bulk + mbarrier, double-buffered (A/B: MLGI_FG_BULK)
+    int max_ctas_per_sm;    // 0 = as compiled (10); smaller: cap the resident CTAs per SM (host-input pipeline, see launch_fg_mode)
     // host-input sharded frame: the G-buffer is not replicated -- tile row t lives in the memory of rank t mod gb_world
     // (peer-mapped) and a gathering CTA reads its tile's pixels from the owner over NVLink (8 B per pixel, once)
     int gb_world;                        // 0 = depth / face_normal above hold the whole image

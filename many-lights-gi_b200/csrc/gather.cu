@@ -438,24 +438,27 @@ __global__ void __launch_bounds__(256 / (2 * NP), FG_MINB) final_gather_kernel(c
 
 template <int MODE>
 static void launch_fg_mode(const GatherArgs& a, dim3 grid, cudaStream_t st) {
+    // occupancy cap (host-input pipeline): unused dynamic shared memory sized so that at most max_ctas_per_sm CTAs fit an SM, which
+    // leaves registers and thread slots for the culling kernels of the next slab that run beside the gathering
+    const size_t dyn = (a.max_ctas_per_sm > 0 && a.max_ctas_per_sm < FG_MINB) ? (size_t)(232448 / (a.max_ctas_per_sm + 1) + 64 - (FG_CHUNK * FG_REC_Q * 16 + 64) - 1024) : 0;
     const bool sh = a.enable_shadowing != 0, stt = a.stats != nullptr;
     const bool tex = sh && a.ism_tex != 0;      // the ISM is fetched through the texture unit whenever a texture object exists
     if (a.gb_world) {                            // host-input sharded frame: G-buffer rows live on the rank that uploaded them
-        if (!sh) final_gather_kernel<MODE, false, false, 0, 1, false, true><<<grid, 128, 0, st>>>(a);
-        else if (!tex) final_gather_kernel<MODE, true, false, 0, 1, false, true><<<grid, 128, 0, st>>>(a);
-        else final_gather_kernel<MODE, true, false, 1, 1, true, true><<<grid, 128, 0, st>>>(a);
+        if (!sh) final_gather_kernel<MODE, false, false, 0, 1, false, true><<<grid, 128, dyn, st>>>(a);
+        else if (!tex) final_gather_kernel<MODE, true, false, 0, 1, false, true><<<grid, 128, dyn, st>>>(a);
+        else final_gather_kernel<MODE, true, false, 1, 1, true, true><<<grid, 128, dyn, st>>>(a);
         return;
     }
-    if (!stt && tex && a.tex_float_coord == 1) { final_gather_kernel<MODE, true, false, 2, 1, false><<<grid, 128, 0, st>>>(a); return; }
-    if (!stt && tex && a.tex_float_coord == 3) { final_gather_kernel<MODE, true, false, 4, 1, true><<<grid, 128, 0, st>>>(a); return; }
-    if (!stt && tex && a.tex_float_coord == 2) { final_gather_kernel<MODE, true, false, 3, 1, true><<<grid, 128, 0, st>>>(a); return; }
+    if (!stt && tex && a.tex_float_coord == 1) { final_gather_kernel<MODE, true, false, 2, 1, false><<<grid, 128, dyn, st>>>(a); return; }
+    if (!stt && tex && a.tex_float_coord == 3) { final_gather_kernel<MODE, true, false, 4, 1, true><<<grid, 128, dyn, st>>>(a); return; }
+    if (!stt && tex && a.tex_float_coord == 2) { final_gather_kernel<MODE, true, false, 3, 1, true><<<grid, 128, dyn, st>>>(a); return; }
     if (stt) {                                   // counting variant (work counters for the roofline accounting)
-        if (sh) final_gather_kernel<MODE, true, true, 0, 1, false><<<grid, 128, 0, st>>>(a);
-        else final_gather_kernel<MODE, false, true, 0, 1, false><<<grid, 128, 0, st>>>(a);
-    } else if (!sh) final_gather_kernel<MODE, false, false, 0, 1, false><<<grid, 128, 0, st>>>(a);
-    else if (!tex) final_gather_kernel<MODE, true, false, 0, 1, false><<<grid, 128, 0, st>>>(a);
-    else if (a.bulk_staging) final_gather_kernel<MODE, true, false, 1, 1, true><<<grid, 128, 0, st>>>(a);
-    else final_gather_kernel<MODE, true, false, 1, 1, false><<<grid, 128, 0, st>>>(a);
+        if (sh) final_gather_kernel<MODE, true, true, 0, 1, false><<<grid, 128, dyn, st>>>(a);
+        else final_gather_kernel<MODE, false, true, 0, 1, false><<<grid, 128, dyn, st>>>(a);
+    } else if (!sh) final_gather_kernel<MODE, false, false, 0, 1, false><<<grid, 128, dyn, st>>>(a);
+    else if (!tex) final_gather_kernel<MODE, true, false, 0, 1, false><<<grid, 128, dyn, st>>>(a);
+    else if (a.bulk_staging) final_gather_kernel<MODE, true, false, 1, 1, true><<<grid, 128, dyn, st>>>(a);
+    else final_gather_kernel<MODE, true, false, 1, 1, false><<<grid, 128, dyn, st>>>(a);
 }
 
 int launch_final_gather(const GatherArgs& a, cudaStream_t st) {
