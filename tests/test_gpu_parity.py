@@ -768,14 +768,14 @@ def test_packed_only_output(case_small, case_mid):
         assert np.array_equal(imgs[0], imgs[1])
 
 
-@pytest.mark.parametrize("push", [False, True])
-@pytest.mark.parametrize("packed", [2, 0])
-def test_exchange_kernels_with_two_sequential_shards_on_one_gpu(case_mid, push, packed, monkeypatch):
+@pytest.mark.parametrize("push,packed,world", [(False, 2, 2), (True, 2, 2), (False, 0, 2), (True, 0, 2), (True, 2, 4), (False, 2, 4)])
+def test_exchange_kernels_with_two_sequential_shards_on_one_gpu(case_mid, push, packed, world, monkeypatch):
     """The multi-GPU exchange exercised on ONE GPU (so that it runs on the single-GPU test box): two class-shard contexts in
     this process, connected through mlgi_exchange_connect_local, each on its own stream; mlgi_frame_sharded (graph replay:
     gathering into the exchange region + the signal / wait / pull / de-interleave kernel) must leave the bits of the
     unsharded frame in BOTH contexts, for several frames (parity double-buffering, device-resident frame counter), in the
-    pull (default) and the push (gathering epilogue stores to every rank) mode, packed and fp32 planes."""
+    pull and the push (gathering epilogue stores to every rank, the default) mode, packed and fp32 planes; with four shards
+    the image's four tile rows are bounded by one rank each (tile row t belongs to rank t mod world)."""
     torch = _torch()
     c = case_mid
     monkeypatch.setenv("MLGI_XCH", "push" if push else "pull")
@@ -786,8 +786,8 @@ def test_exchange_kernels_with_two_sequential_shards_on_one_gpu(case_mid, push, 
     p = mlgi.default_params(c.N)
     full.ctx.frame(full.rsm, full.light, full.mesh, full.gb, full.cam, p)
     ref = full.ctx.download(mlgi.BUF_GI_PACKED, np.uint32) if packed else full.ctx.download(mlgi.BUF_GI, np.float32)
-    world = 2
-    shards = [mlgi.Context(c.W, c.H, c.N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 22, class_lo=8 * r, class_hi=8 * r + 8, gi_packed=packed)
+    per = 16 // world
+    shards = [mlgi.Context(c.W, c.H, c.N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 22, class_lo=per * r, class_hi=per * r + per, gi_packed=packed)
               for r in range(world)]
     for r, s in enumerate(shards):
         s.exchange_create(r, world)
@@ -811,8 +811,8 @@ def test_exchange_kernels_with_two_sequential_shards_on_one_gpu(case_mid, push, 
     full.close()
 
 
-@pytest.mark.parametrize("phases", [1, 2])
-def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid, phases, monkeypatch):
+@pytest.mark.parametrize("phases,world", [(1, 2), (2, 2), (1, 4)])
+def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid, phases, world, monkeypatch):
     """mlgi_frame_sharded_host (the N-GPU host-input frame: distributed G-buffer, exchanged tile bounds, remote G-buffer reads
     in the gathering kernel, per-phase plane exchange and read-back of the rank's own tile rows) exercised on ONE GPU: two
     class-shard contexts connected through mlgi_exchange_connect_local, one host thread per rank (the call synchronises, and
@@ -832,16 +832,16 @@ def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid, phases, monkeypatch):
     p = mlgi.default_params(c.N)
     full.ctx.frame(full.rsm, full.light, full.mesh, full.gb, full.cam, p)
     ref = full.ctx.download(mlgi.BUF_GI_PACKED, np.uint32).reshape(c.H, c.W)
-    world = 2
-    shards = [mlgi.Context(c.W, c.H, c.N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 22, class_lo=8 * r, class_hi=8 * r + 8, gi_packed=2)
+    per = 16 // world
+    shards = [mlgi.Context(c.W, c.H, c.N, wl.rsm_w, wl.rsm_h, sc.num_triangles, 1 << 22, class_lo=per * r, class_hi=per * r + per, gi_packed=2)
               for r in range(world)]
     for r, s in enumerate(shards):
         s.exchange_create(r, world)
     for s in shards:
         s.exchange_connect_local(shards)
-    assert [s.sharded_rows() for s in shards] == [(0, 64, 128), (64, 64, 128)]      # tile row t belongs to rank t mod world
+    assert [s.sharded_rows() for s in shards] == [(64 * r, 64, 64 * world) for r in range(world)]      # tile row t belongs to rank t mod world
     rows = [s.sharded_row_mask() for s in shards]
-    assert (rows[0] ^ rows[1]).all()
+    assert (np.sum(rows, axis=0) == 1).all()
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h = [pin(wl.rsm_diffuse), pin(wl.rsm_normal), pin(wl.rsm_depth), pin(wl.depth), pin(wl.normal)]
     hr, hg = mlgi.make_rsm(h[0], h[1], h[2]), mlgi.make_gbuffer(h[3], h[4])
@@ -859,7 +859,9 @@ def test_sharded_host_frame_two_ranks_on_one_gpu(case_mid, phases, monkeypatch):
     for frame in range(3):
         for o in outs:
             o.zero_()
-        bufs = [outs[0], outs[2] if frame == 2 else outs[1]]
+        bufs = outs[:world]
+        if frame == 2:
+            bufs = bufs[:1] + [outs[world]] + bufs[2:]          # rank 1: the pageable buffer
         th = [threading.Thread(target=run, args=(r, bufs[r])) for r in range(world)]
         for t in th:
             t.start()
