@@ -176,9 +176,12 @@ PP_HD float4 pull_combine(const PullSample (&smp)[4], int ix0, int iy0, int ox, 
         numValid++;
     }
     if (numValid > 0) {                                           // :116-123
+        // depth sums are 0 or >= 2^-24 and <= 4; displacement sums are multiples of 2^-25 below 2^13 (coordinates < 2^13 plus halves
+        // with a 2^-24 grid): all inside div_small's exact range, so only the radius -- which may be inf or NaN for a zero-depth
+        // texel (radius / distToCamera, pull.comp:61) -- takes the checked form
         const float nv = float(numValid), y = rcp[numValid];
-        return make_float4(div_small(depthAcc, nv, y), maxValidMaxDepth, div_small(radiusAcc, nv, y),
-                           u2f(pack_half2x(div_small(dax, nv, y), div_small(day, nv, y))));
+        return make_float4(div_small_unchecked(depthAcc, nv, y), maxValidMaxDepth, div_small(radiusAcc, nv, y),
+                           u2f(pack_half2x(div_small_unchecked(dax, nv, y), div_small_unchecked(day, nv, y))));
     }
     return make_float4(1.0f, 0.0f, 0.0f, 0.0f);
 }
@@ -232,9 +235,9 @@ PP_HD float4 push_pixel(int OP, const PushTaps& c, float4 orig, const float* rcp
     float depthAcc = 0.0f;
     int wi = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) if (p[i]) { wi += (int)w[i]; depthAcc += c.depth[i] * w[i]; }
+    for (int i = 0; i < 4; i++) if (p[i]) { const int d = (i - OP) & 3; wi += d == 0 ? 9 : (d == 2 ? 1 : 3); depthAcc += c.depth[i] * w[i]; }
     const float wa = float(wi), y = rcp[wi];
-    if (LEVEL0) return make_float4(div_small(depthAcc, wa, y), 0.0f, 0.0f, 0.0f);
+    if (LEVEL0) return make_float4(div_small_unchecked(depthAcc, wa, y), 0.0f, 0.0f, 0.0f);
     float radiusAcc = 0.0f, maxDepthAcc = 0.0f, dax = 0.0f, day = 0.0f;
 #pragma unroll
     for (int i = 0; i < 4; i++) if (p[i]) {
@@ -242,8 +245,9 @@ PP_HD float4 push_pixel(int OP, const PushTaps& c, float4 orig, const float* rcp
         radiusAcc += c.radius[i] * w[i];
         dax += dvx[i] * w[i]; day += dvy[i] * w[i];
     }
-    return make_float4(div_small(depthAcc, wa, y), div_small(maxDepthAcc, wa, y), div_small(radiusAcc, wa, y),
-                       u2f(pack_half2x(div_small(dax, wa, y), div_small(day, wa, y))));
+    // (same ranges as in pull_combine: depth / maxDepth sums are 0 or in [2^-24, 40], displacement sums multiples of 2^-25)
+    return make_float4(div_small_unchecked(depthAcc, wa, y), div_small_unchecked(maxDepthAcc, wa, y), div_small(radiusAcc, wa, y),
+                       u2f(pack_half2x(div_small_unchecked(dax, wa, y), div_small_unchecked(day, wa, y))));
 }
 template <int OP, bool LEVEL0>
 PP_HD float4 push_pixel_c(const PushTaps& c, float4 orig, const float* rcp) { return push_pixel<LEVEL0>(OP, c, orig, rcp); }
@@ -329,15 +333,22 @@ PP_HD void phase_pull1_classify(Shared& s, int tid) {
         const int lx = o & 31, ly = o >> 5;
         const uint32_t* r0 = &s.L0[(ly * 2) * 64 + lx * 2];
         const uint32_t* r1 = r0 + 64;
-        if ((r0[0] & r0[1] & r1[0] & r1[1]) == 0xFFFFFFFFu) s.PY[lvl_off(1) + o] = s.empty1;
-        else {
+        const bool empty = (r0[0] & r0[1] & r1[0] & r1[1]) == 0xFFFFFFFFu;
+        if (empty) s.PY[lvl_off(1) + o] = s.empty1;
 #if defined(__CUDA_ARCH__)
-            const int slot = atomicAdd(&s.count, 1);
-#else
-            const int slot = s.count++;
-#endif
-            s.list[slot] = (uint16_t)o;
+        // one shared-memory atomic per warp (the trip count is warp-uniform: 1024 outputs / 256 threads); the order of the list is
+        // immaterial, every entry is processed on its own
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, !empty);
+        if (m) {
+            const int lane = tid & 31, leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&s.count, __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (!empty) s.list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)o;
         }
+#else
+        if (!empty) s.list[s.count++] = (uint16_t)o;
+#endif
     }
 }
 
