@@ -455,7 +455,11 @@ __global__ void __launch_bounds__(pp::kThreads, PP_MINB) pullpush_kernel(const u
         pp::phase_push_top(s, tid, level);
         __syncthreads();
     }
+#ifdef PP_PUSH1_PER_PIXEL
+    pp::phase_push_top(s, tid, 1);
+#else
     pp::phase_push1(s, tid);
+#endif
     __syncthreads();
     pp::phase_push0(s, tid);
     __syncthreads();
@@ -505,7 +509,11 @@ __global__ void __launch_bounds__(pp::kThreads, PP_MINB) pullpush_tma_kernel(con
         pp::phase_push_top(s, tid, level);
         __syncthreads();
     }
+#ifdef PP_PUSH1_PER_PIXEL
+    pp::phase_push_top(s, tid, 1);
+#else
     pp::phase_push1(s, tid);
+#endif
     __syncthreads();
     pp::phase_push0(s, tid);
     __syncthreads();

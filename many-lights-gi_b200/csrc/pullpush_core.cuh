@@ -431,7 +431,10 @@ PP_HD void store_mid(Shared& s, int level, int plx, int ply, float4 res) {
     s.PY[lvl_off(level) + ply * size + plx] = res;
 }
 // levels 5..2 are small, so the pass is latency-bound: one thread per fine pixel (four times the threads of the shader's
-// 4-pixels-per-thread layout, a quarter of the dependent work per thread)
+// 4-pixels-per-thread layout, a quarter of the dependent work per thread). The same layout for level 1 (-DPP_PUSH1_PER_PIXEL: four
+// balanced rounds of 256 threads instead of 289 threads, i.e. a second round with 33 of 256 threads working) was measured: 5.5 %
+// more instructions, same time (171.8 vs 171.2 us) -- ncu attributes 38 % of the kernel's warp time to CTA-barrier waits, but those
+// are the idle warps of the serial top of the pyramid (pull 3..6, push 5..3: at most 64 texels per phase), not this round.
 PP_HD void phase_push_top(Shared& s, int tid, int level) {
     const int size = 64 >> level;
     for (int it = tid; it < size * size; it += kThreads) {
@@ -443,7 +446,7 @@ PP_HD void phase_push_top(Shared& s, int tid, int level) {
         load_taps(s, level, tlx, tly, c);
         store_mid(s, level, plx, ply, push_pixel<false>(OP, c, s.PY[lvl_off(level) + it], s.rcp));
     }
-    fill_thr_ring(s.thr[(level - 1) & 1], size, tid);
+    if (level > 1) fill_thr_ring(s.thr[(level - 1) & 1], size, tid);     // (level 1 carries its thresholds in .z, no plane)
 }
 // level 1 (1024 texels): the shader's layout, taps loaded and unpacked once per four pixels
 PP_HD void phase_push1(Shared& s, int tid) {
