@@ -142,6 +142,31 @@ class ClockSampler:
                 "source": self.source}
 
 
+def bind_to_gpu_numa_node(device):
+    """N > 1, one process per GPU: run this rank on the CPU cores NVML reports as local to its GPU, BEFORE the pinned host buffers are
+    allocated (first touch), so that the rank's uploads and read-backs do not cross the socket interconnect. Eight ranks uploading at
+    once share the host's memory bandwidth; a host application would place its staging buffers the same way. MLGI_BENCH_BIND=0 disables.
+    Returns the number of cores bound to, or None."""
+    if os.environ.get("MLGI_BENCH_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[device]) if vis else device
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 64
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cores = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1} & allowed
+        if cores and cores != allowed:
+            os.sched_setaffinity(0, cores)
+            return len(cores)
+    except Exception:
+        return None
+    return None
+
+
 def build_workload(name):
     from scene_fixture import Workload
     W, H, N, rw, rh, cell = WORKLOADS[name]
@@ -400,6 +425,7 @@ def main():
     if world > 1 and args.exchange in ("pull", "push"):
         os.environ["MLGI_XCH"] = args.exchange
     torch.cuda.set_device(local)
+    cpu_bind = bind_to_gpu_numa_node(local) if world > 1 else None
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
@@ -492,6 +518,8 @@ def main():
                        "tile bounds exchanged between ranks, gathering reads each tile's pixels from the rank holding them over NVLink, plane "
                        "exchange, 1/N of the assembled GL_R11F_G11F_B10F image rows copied back to pinned host memory; upload, culling, gathering and "
                        "read-back pipelined over phases of tile rows (bytes summed over ranks)"}
+        if world > 1:
+            e2e["host_cores_bound_to_gpu_numa_node"] = cpu_bind      # bind_to_gpu_numa_node (None: not bound)
 
     # ---- per-stage times + the dominant kernels' live durations (events on the launching stream; direct launches) ----
     ctx.set_timers(True)
