@@ -201,7 +201,8 @@ MLGI_API int mlgi_get_frame_stats(mlgi_ctx*, mlgi_frame_stats* out);
 /* Same, but the per-frame inputs (RSM + camera G-buffer) are HOST pointers (pinned for
  * full speed) and the GI image is copied back to host_gi (width*height*4 float, may be
  * NULL to skip). The mesh stays resident on the device (it is static scene data in the
- * reference too). Synchronises the stream before returning. This is the end-to-end call. */
+ * reference too). Of the RSM only the N texels the VPL build samples are read (by the CPU) and uploaded, 12 B per VPL; the
+ * RSM planes may be pageable memory. Synchronises the stream before returning. This is the end-to-end call. */
 MLGI_API int mlgi_frame_host(mlgi_ctx*, const mlgi_rsm* host_rsm, const mlgi_camera* light, const mlgi_mesh* dev_mesh,
                              const mlgi_gbuffer* host_gbuffer, const mlgi_camera* cam, const mlgi_params*,
                              float* host_gi, void* stream);

@@ -504,6 +504,12 @@ MLGI_API int mlgi_vpl_process(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_cam
 // The VPL build samples the RSM at N fixed texels (vpl_processor.comp:46-54: a regular sub-grid). The host-input frames gather
 // those texels on the host (12 B per VPL: 48 KB at 4096 VPLs) and upload them instead of the 3 MB RSM -- per rank, so with G
 // GPUs the job saves G x 3 MB of PCIe traffic per frame, and the VPL build that heads the ISM chain starts 0.06 ms earlier.
+// the host-input frames read the RSM planes with the CPU: a device pointer there is a caller error, not a crash
+static bool is_device_pointer(const void* ptr) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return pa.type == cudaMemoryTypeDevice;
+}
 static void gather_rsm_samples(mlgi_ctx* ctx, const mlgi_rsm* hr) {
     const uint32_t N = (uint32_t)ctx->cfg.vpl_count, rw = (uint32_t)ctx->cfg.rsm_width, rh = (uint32_t)ctx->cfg.rsm_height;
     const uint32_t ax = (uint32_t)ceilf(sqrtf(float(N))), ay = N / ax;              // the kernel's own arithmetic
@@ -1325,6 +1331,8 @@ static int frame_host_impl(mlgi_ctx* ctx, const mlgi_rsm* hr, const mlgi_camera*
     key.hr = *hr; key.light = *light; key.mesh = *mesh; key.hg = *hg; key.cam = *cam; key.p = *p; key.host_out = host_out; key.kind = 0; key.packed = packed;
     key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture; key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk;
     key.host_slabs = ctx->host_slabs;
+    if (is_device_pointer(hr->diffuse) || is_device_pointer(hr->face_normal) || is_device_pointer(hr->depth))
+        return fail(ctx, MLGI_E_INVALID, "mlgi_frame_host: the RSM planes must be HOST pointers (the VPL samples are gathered by the CPU)");
     gather_rsm_samples(ctx, hr);
     int rc = host_frame_graph(ctx, key, p, st, [&](cudaStream_t cs) { return frame_host_body(ctx, hr, light, mesh, hg, cam, p, host_out, packed, cs); });
     if (rc < 0) return rc;
@@ -1534,6 +1542,8 @@ MLGI_API int mlgi_frame_sharded_host(mlgi_ctx* ctx, const mlgi_rsm* hr, const ml
     key.hr = *hr; key.light = *light; key.mesh = *mesh; key.hg = *hg; key.cam = *cam; key.p = *p; key.host_out = host_gi_packed; key.kind = 1; key.packed = 1;
     key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture; key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk;
     key.host_slabs = ctx->host_slabs_set ? ctx->host_slabs : 0; key.xch_direct = ctx->xch_direct;
+    if (is_device_pointer(hr->diffuse) || is_device_pointer(hr->face_normal) || is_device_pointer(hr->depth))
+        return fail(ctx, MLGI_E_INVALID, "mlgi_frame_sharded_host: the RSM planes must be HOST pointers (the VPL samples are gathered by the CPU)");
     gather_rsm_samples(ctx, hr);
     int rc = host_frame_graph(ctx, key, p, st, [&](cudaStream_t cs) { return frame_sharded_host_body(ctx, hr, light, mesh, hg, cam, p, host_gi_packed, cs); });
     if (rc < 0) return rc;

@@ -428,6 +428,9 @@ def test_error_behaviour(case_small):
     with pytest.raises(mlgi.MlgiError) as e:      # stage order
         g.ctx.ism_splat(p)
     assert e.value.code == mlgi.E_ORDER
+    with pytest.raises(mlgi.MlgiError) as e:      # the host-input frame reads the RSM with the CPU: device pointers are refused, not dereferenced
+        g.ctx.frame_host(g.rsm, g.light, g.mesh, g.gb, g.cam, p)
+    assert e.value.code == mlgi.E_INVALID
     q = mlgi.default_params(case_small.N)
     q.show_vpl_positions = 1
     with pytest.raises(mlgi.MlgiError) as e:
