@@ -108,6 +108,7 @@ struct mlgi_ctx {
     std::vector<OverrideTex> override_tex;
     int use_texture = 1, tex_float_coord = 0, fg_bulk = 1, xch_direct = 0;
     int fg_host_occ = 10;           // resident gathering CTAs per SM in the single-GPU host pipeline (A/B: MLGI_FG_HOST_OCC; 10 = no cap, the measured best)
+    int cull_late = 0;              // start the culling after the splat instead of beside point generation (A/B: MLGI_CULL_LATE; measured 1.7595 vs 1.7529 ms: off)
     int pp_parts = 1;               // class groups of the pull-push / gathering pipeline in mlgi_frame (A/B: MLGI_PP_PARTS; measured: no gain, off)
     int xch_cull = 1;               // connected ranks bound 1/world of the tiles each and exchange the bounds (A/B: MLGI_XCH_CULL)
     IsmMode mode_vpl{}, mode_points{};   // the n3 knobs the VPL records / the point list were built with
@@ -422,6 +423,7 @@ MLGI_API int mlgi_create(const mlgi_config* cfg, mlgi_ctx** out) {
     if (const char* e5 = getenv("MLGI_HOST_SLABS")) { if (atoi(e5) > 0) ctx->host_slabs_set = true, ctx->host_slabs = std::max(1, std::min((int)mlgi_ctx::kSlabs, atoi(e5))); }   // A/B switch
     if (const char* e3 = getenv("MLGI_XCH_DIRECT")) ctx->xch_direct = atoi(e3) != 0;
     if (const char* e13 = getenv("MLGI_FG_HOST_OCC")) ctx->fg_host_occ = std::max(1, std::min(10, atoi(e13)));
+    if (const char* e14 = getenv("MLGI_CULL_LATE")) ctx->cull_late = atoi(e14) != 0;
     if (const char* e4 = getenv("MLGI_PP_PARTS")) ctx->pp_parts = std::max(1, std::min(16, atoi(e4)));
     if (const char* e2 = getenv("MLGI_ISM_FETCH")) { ctx->use_texture = strcmp(e2, "ldg") != 0; ctx->tex_float_coord = strcmp(e2, "texf") == 0 ? 1 : strcmp(e2, "texi") == 0 ? 2 : strcmp(e2, "none") == 0 ? 3 : 0; }   // A/B switch: tex (default) | texf | texi | ldg
     if (const char* e11 = getenv("MLGI_XCH_CULL")) ctx->xch_cull = atoi(e11) != 0;             // A/B switch: bounds exchanged between ranks (default) | every rank bounds all tiles
@@ -1053,7 +1055,15 @@ static int frame_body(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* lig
         void* cs = (void*)ctx->side;
         if ((rc = mlgi_vpl_process(ctx, rsm, light, p, cs))) return rc;           // GIStage.cpp:373-376
         CK(cudaEventRecord(ctx->ev_vpl, ctx->side));
-        if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((rc = mlgi_cull_clustered(ctx, gb, cam, p, cs))) return rc; }   // :392-403
+    } else {
+        if ((rc = mlgi_vpl_process(ctx, rsm, light, p, stream))) return rc;
+    }
+    // culling on the side stream (fork only): right after the VPL build, or (cull_late) only once the splat is done, so that it
+    // runs beside the throughput-bound pull-push instead of stretching the latency-bound point generation and splat
+    auto issue_cull = [&]() -> int {
+        void* cs = (void*)ctx->side;
+        int r;
+        if (p->cull_mode == MLGI_CULL_CLUSTERED) { if ((r = mlgi_cull_clustered(ctx, gb, cam, p, cs))) return r; }   // :392-403
         else if (with_exchange && ctx->xch_cull) {          // every rank bounds 1/world of the tiles; the bounds are exchanged
             if (!gb || !gb->depth || !gb->face_normal || !cam) return fail(ctx, MLGI_E_INVALID, "gbuffer/camera is NULL");
             float vi[16], pi[16], inv[16];
@@ -1062,11 +1072,12 @@ static int frame_body(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* lig
             ctx->launches += cull_tiled_sharded(ctx, gb->depth, gb->face_normal, to_mat4(inv), ctx->side);
             CK(cudaGetLastError());
         }
-        else { if ((rc = mlgi_cull_tiled(ctx, gb, cam, p, cs))) return rc; }
+        else { if ((r = mlgi_cull_tiled(ctx, gb, cam, p, cs))) return r; }
         CK(cudaEventRecord(ctx->ev_join, ctx->side));
-    } else {
-        if ((rc = mlgi_vpl_process(ctx, rsm, light, p, stream))) return rc;
-    }
+        return MLGI_OK;
+    };
+    const bool cull_late = fork && ctx->cull_late && !with_exchange;      // (sharded frames: the bounds exchange wants an early start)
+    if (fork && !cull_late && (rc = issue_cull())) return rc;
     if ((rc = mlgi_ism_points(ctx, mesh, p, stream))) return rc;                  // :378-389 ISM render
     if (fork) {
         CK(cudaStreamWaitEvent(st, ctx->ev_vpl, 0));
@@ -1074,6 +1085,11 @@ static int frame_body(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* lig
         ctx->atlas_precleared = true;
     }
     if ((rc = mlgi_ism_splat(ctx, p, stream))) return rc;                         //          ISM CS
+    if (cull_late) {
+        CK(cudaEventRecord(ctx->ev_rsm, st));                                     // (ev_rsm is free outside the host-input frames)
+        CK(cudaStreamWaitEvent(ctx->side, ctx->ev_rsm, 0));
+        if ((rc = issue_cull())) return rc;
+    }
     // Optional (MLGI_PP_PARTS = 2..16, default off): pull-push and gathering as a pipeline over class groups. Gathering for classes
     // [c0, c1) only reads the ISMs of those classes' VPLs, i.e. a band of atlas rows (plus one halo row), so the pull-push of the
     // NEXT band (ALU-pipe bound) can run beside the gathering of this one (FMA-pipe bound) instead of in front of all of it
@@ -1126,7 +1142,7 @@ static int frame_body(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* lig
 // (cudaGraphExecUpdate), a structural change re-instantiates it. Per-stage timers need the direct path.
 struct FrameKey {
     mlgi_rsm rsm; mlgi_camera light; mlgi_mesh mesh; mlgi_gbuffer gb; mlgi_camera cam; mlgi_params p;
-    int with_exchange, push, fg_sorted, use_texture, tex_float_coord, fg_bulk, xch_cull, pp_parts; const void* planar_ext;
+    int with_exchange, push, fg_sorted, use_texture, tex_float_coord, fg_bulk, xch_cull, pp_parts, cull_late; const void* planar_ext;
 };
 
 // capture (if the key changed) and instantiate / update the frame's graph; no launch
@@ -1137,7 +1153,7 @@ static int ensure_graph(mlgi_ctx* ctx, const mlgi_rsm* rsm, const mlgi_camera* l
     memset(&key, 0, sizeof(key));
     key.rsm = *rsm; key.light = *light; key.mesh = *mesh; key.gb = *gb; key.cam = *cam; key.p = *p;
     key.with_exchange = with_exchange; key.push = ctx->xch.push; key.fg_sorted = ctx->fg_sorted; key.use_texture = ctx->use_texture;
-    key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk; key.xch_cull = ctx->xch_cull; key.pp_parts = ctx->pp_parts; key.planar_ext = ctx->planar_ext;
+    key.tex_float_coord = ctx->tex_float_coord; key.fg_bulk = ctx->fg_bulk; key.xch_cull = ctx->xch_cull; key.pp_parts = ctx->pp_parts; key.cull_late = ctx->cull_late; key.planar_ext = ctx->planar_ext;
     if (ctx->graph_valid && memcmp(&key, ctx->graph_key.data(), sizeof(key)) == 0) return MLGI_OK;
     if (p->cull_mode == MLGI_CULL_CLUSTERED && (rc = ensure_clustered(ctx))) return rc;   // cudaMalloc must not run inside a capture
     const unsigned long long l0 = ctx->launches;
